@@ -1,0 +1,20 @@
+// Shared host-side declarations for the mmu_b200 CUDA library.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+// Error codes returned across the C ABI (0 = success).  Mirrored in include/mmu_b200.h.
+#define MMU_OK 0
+#define MMU_ERR_SHAPE (-1)   // unsupported / inconsistent dimensions
+#define MMU_ERR_ALIGN (-2)   // pointer or leading dimension not 16-byte aligned
+#define MMU_ERR_DRIVER (-3)  // CUDA driver entry point unavailable (no GPU / no libcuda)
+#define MMU_ERR_TMAP (-4)    // cuTensorMapEncodeTiled rejected the descriptor
+#define MMU_ERR_CUDA (-5)    // launch failed; see cudaGetLastError
+#define MMU_ERR_ARG (-6)     // null pointer / bad enum
+#define MMU_ERR_WORKSPACE (-7)  // workspace too small
+
+namespace mmu {
+int sm_count();
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, long long inner, long long outer,
+                      long long ld, int box_inner, int box_outer);
+}  // namespace mmu

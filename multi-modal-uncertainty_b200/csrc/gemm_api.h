@@ -1,0 +1,41 @@
+// Public (library-internal) description of one GEMM launch: problem, operand majorness and
+// the fused epilogue.  Shared by the kernel, the engine and the test harness.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mmu {
+
+enum GemmEpiMode : int {
+  EPI_STORE = 0,      // out = alpha*acc + bias
+  EPI_QUICKGELU = 1,  // z = alpha*acc + bias ; out = z (optional) ; out2 = z*sigmoid(1.702 z)
+  EPI_RESIDUAL = 2,   // out(f32) = aux(f32) + alpha*acc + bias
+  EPI_DGELU = 3,      // out = alpha*acc * d/dz[z*sigmoid(1.702 z)] with z = aux (bf16)
+  EPI_ATOMIC = 4,     // out(f32) += alpha*acc   (split-K partial sums)
+};
+
+struct GemmEpilogue {
+  int mode;
+  int out_bf16;  // 1: out/out2 are bf16, 0: f32
+  void* out;
+  void* out2;
+  const float* bias;
+  const void* aux;
+  long long ld_out, ld_out2, ld_aux;
+  // optional row remap (fuses torch.cat of the per-modality projections, src/model.py:273):
+  // out_row = (r / seg_len) * seg_stride + seg_off + r % seg_len      (seg_len <= 0: identity)
+  int seg_len, seg_stride, seg_off;
+  float alpha;
+};
+
+struct GemmProblem {
+  int M, N, K;
+  int a_mn_major, b_mn_major;
+  int splits;  // split-K factor (only with EPI_ATOMIC)
+};
+
+// ---------------------------------------------------------------- host side
+// Returns 0 on success, negative error code otherwise (never throws).
+int gemm_bf16_launch(const void* A, long long lda, const void* B, long long ldb,
+                     const GemmProblem& p, const GemmEpilogue& e, cudaStream_t stream);
+
+}  // namespace mmu

@@ -1,0 +1,123 @@
+// Host side of the tcgen05 GEMM: tensor-map encoding and launch.
+#include "gemm_tcgen05.cuh"
+
+#include <cstdio>
+#include <mutex>
+
+#include "common.h"
+
+namespace mmu {
+
+namespace {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libcuda is resolved at run time through the runtime API so that the shared library
+// still loads (and exports its symbols) on a machine without a driver.
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+}  // namespace
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch `ld`
+// elements; box = box_inner x box_outer, 128-byte swizzle, out-of-bounds reads give zeros.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, long long inner, long long outer,
+                      long long ld, int box_inner, int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return MMU_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) return MMU_ERR_ALIGN;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MMU_ERR_TMAP;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+namespace {
+template <int MODE>
+int launch_mode(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const GemmProblem& p,
+                const GemmEpilogue& e, cudaStream_t stream) {
+  using namespace gemm;
+  static cudaError_t attr_err = cudaFuncSetAttribute(
+      gemm_bf16_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (attr_err != cudaSuccess) {
+    fprintf(stderr, "mmu: cudaFuncSetAttribute(smem=%d): %s\n", SMEM_BYTES,
+            cudaGetErrorString(attr_err));
+    return MMU_ERR_CUDA;
+  }
+  gemm_bf16_tcgen05_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p, e);
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    fprintf(stderr, "mmu: gemm launch failed: %s\n", cudaGetErrorString(err));
+    return MMU_ERR_CUDA;
+  }
+  return 0;
+}
+}  // namespace
+
+int gemm_bf16_launch(const void* A, long long lda, const void* B, long long ldb,
+                     const GemmProblem& p_in, const GemmEpilogue& e, cudaStream_t stream) {
+  using namespace gemm;
+  GemmProblem p = p_in;
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return MMU_ERR_SHAPE;
+  if (p.N % 4 != 0) return MMU_ERR_SHAPE;
+  const int kb_total = (p.K + BK - 1) / BK;
+  if (p.splits < 1) p.splits = 1;
+  if (p.splits > 1 && e.mode != EPI_ATOMIC) return MMU_ERR_SHAPE;
+  if (p.splits > kb_total) p.splits = kb_total;
+  {  // no split may be empty: the epilogue would add an undefined accumulator
+    const int kb_per = (kb_total + p.splits - 1) / p.splits;
+    p.splits = (kb_total + kb_per - 1) / kb_per;
+  }
+  CUtensorMap ta, tb;
+  int rc;
+  if (!p.a_mn_major) rc = make_tmap_bf16_2d(&ta, A, p.K, p.M, lda, BK, BM);
+  else               rc = make_tmap_bf16_2d(&ta, A, p.M, p.K, lda, 64, BK);
+  if (rc != 0) return rc;
+  if (!p.b_mn_major) rc = make_tmap_bf16_2d(&tb, B, p.K, p.N, ldb, BK, BN);
+  else               rc = make_tmap_bf16_2d(&tb, B, p.N, p.K, ldb, 64, BK);
+  if (rc != 0) return rc;
+
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const long long tiles = 1LL * m_tiles * n_tiles * p.splits;
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  switch (e.mode) {
+    case EPI_STORE: return launch_mode<EPI_STORE>(grid, ta, tb, p, e, stream);
+    case EPI_QUICKGELU: return launch_mode<EPI_QUICKGELU>(grid, ta, tb, p, e, stream);
+    case EPI_RESIDUAL: return launch_mode<EPI_RESIDUAL>(grid, ta, tb, p, e, stream);
+    case EPI_DGELU: return launch_mode<EPI_DGELU>(grid, ta, tb, p, e, stream);
+    case EPI_ATOMIC: return launch_mode<EPI_ATOMIC>(grid, ta, tb, p, e, stream);
+    default: return MMU_ERR_ARG;
+  }
+}
+
+}  // namespace mmu

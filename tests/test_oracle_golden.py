@@ -1,0 +1,161 @@
+"""Pin the CPU oracle to the reference: every golden fixture was produced by the unmodified
+reference modules (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fusion, optim, shaping, uncertainty
+
+SMALL = ["plain_E2", "plain_E1", "avgpool_E2", "cls_E3", "plain_E5_h3"]
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_flava_forward_loss_grads(golden, name):
+    c = golden("flava_small.pt")[name]
+    cfg = c["cfg"]
+    P = c["state_dict"]
+    logits, loss, grads = fusion.loss_and_grads(P, (c["img"], c["txt"]), c["y_train"],
+                                                cfg["heads"], cfg["avg_pool"])
+    assert rel_err(logits, c["logits"]) < 1e-5
+    assert abs(float(loss) - float(c["loss"])) < 1e-5 * max(1.0, abs(float(c["loss"])))
+    for k, g in c["grads"].items():
+        scale = max(float(g.abs().max()), 1e-6)
+        assert float((grads[k] - g).abs().max()) <= 2e-4 * scale + 1e-7, k
+    # eval path: CE on the head-mean logits, argmax of the same
+    le = fusion.flava_fusion_forward(P, (c["img"], c["txt"]), cfg["heads"], cfg["avg_pool"])
+    assert rel_err(le, c["logits_eval"]) < 1e-5
+    assert abs(float(fusion.compute_loss(le, c["y"], eval=True)) - float(c["loss_eval"])) < 1e-5
+    assert float(fusion.acc(le, c["y"], True, True)) == float(c["eval_acc"])
+    assert float(fusion.acc(logits, c["y_train"], False, True)) == float(c["train_acc"])
+
+
+def test_flava_missing_modality(golden):
+    c = golden("flava_small.pt")["cls_E3"]
+    P, h = c["state_dict"], c["cfg"]["heads"]
+    assert rel_err(fusion.flava_fusion_forward(P, (c["img"], None), h), c["logits_img_only"]) < 1e-5
+    assert rel_err(fusion.flava_fusion_forward(P, (None, c["txt"]), h), c["logits_txt_only"]) < 1e-5
+
+
+def test_dead_text_projection_grad(golden):
+    """without avg_pool only positions < E are live."""
+    c = golden("flava_small.pt")["plain_E2"]
+    assert float(c["grads"]["text_to_mm_projection.weight"].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_adamw_one_step(golden, name):
+    c = golden("flava_small.pt")[name]
+    for k, g in c["grads"].items():
+        p0 = c["state_dict"][k]
+        p1, _, _ = optim.adamw_step(p0, g, torch.zeros_like(p0), torch.zeros_like(p0), 1, 1e-3)
+        assert float((p1 - c["params_after_adamw"][k]).abs().max()) < 2e-6, k
+
+
+def test_adamw_cosine_trajectory(golden):
+    c = golden("adamw_cosine.pt")
+    p = c["p0"].clone()
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for t, g in enumerate(c["grads"]):
+        lr = c["lr"] * optim.cosine_with_warmup_factor(t, c["warmup"], c["total"])
+        assert abs(lr - c["lrs"][t]) < 1e-12
+        p, m, v = optim.adamw_step(p, g, m, v, t + 1, lr)
+        assert float((p - c["traj"][t]).abs().max()) < 5e-6
+    assert float((m - c["exp_avg"]).abs().max()) < 1e-6
+    assert float((v - c["exp_avg_sq"]).abs().max()) < 1e-6
+
+
+def test_full_width_model(golden):
+    from tests.golden.make_golden import det_state_dict
+    c = golden("flava_768.pt")
+    P = det_state_dict(c["shapes"], c["cfg"]["seed"])
+    logits, loss, grads = fusion.loss_and_grads(P, (c["img"], c["txt"]), c["y_train"], 3, False)
+    assert rel_err(logits, c["logits"]) < 2e-5
+    assert abs(float(loss) - float(c["loss"])) < 1e-5 * float(c["loss"])
+    for k, s in c["grad_summaries"].items():
+        g = grads[k].double()
+        got = torch.stack([g.sum(), g.abs().sum(), g.pow(2).sum()])
+        assert torch.allclose(got[1:], s[1:], rtol=2e-3, atol=1e-7), k
+        assert abs(float(got[0] - s[0])) <= 1e-5 * float(s[1]) + 1e-7, k  # signed sum cancels
+    for k, sl in c["grad_slices"].items():
+        scale = max(float(sl.abs().max()), 1e-6)
+        assert float((grads[k].reshape(-1)[:64] - sl).abs().max()) < 1e-3 * scale + 1e-7, k
+
+
+def test_mimo_transformer(golden):
+    c = golden("mimo_transformer.pt")
+    logits, loss, grads = fusion.loss_and_grads(c["state_dict"], c["x"], c["y_train"],
+                                                c["cfg"]["heads"], model="mimo")
+    assert rel_err(logits, c["logits"]) < 1e-5
+    assert abs(float(loss) - float(c["loss"])) < 1e-5
+    for k, g in c["grads"].items():
+        scale = max(float(g.abs().max()), 1e-6)
+        assert float((grads[k] - g).abs().max()) <= 2e-4 * scale + 1e-7, k
+
+
+def test_shaping_bit_exact(golden):
+    c = golden("shaping.pt")
+    inp = c["inputs"]
+    for mt in ["Vanilla", "MultiHead", "MIMO-shuffle-instance"]:
+        for phase in ["train", "eval"]:
+            torch.manual_seed(42)
+            (i2, t2), y2 = shaping.data_forming_func_transformer((inp["img"], inp["txt"]),
+                                                                 inp["y"], phase, mt)
+            g = c[f"transformer/{mt}/{phase}"]
+            assert torch.equal(i2, g["img"]) and torch.equal(t2, g["txt"]) and torch.equal(y2, g["y"])
+    for mt in ["Vanilla", "single-model-weight-sharing", "MultiHead", "MIMO-shuffle-instance",
+               "MIMO-shuffle-view", "MIMO-shuffle-all"]:
+        for phase in ["train", "eval"]:
+            torch.manual_seed(42)
+            x2, y2 = shaping.data_forming_func(inp["x"], inp["yv"], phase, mt)
+            g = c[f"fmnist/{mt}/{phase}"]
+            assert torch.equal(x2, g["x"]) and torch.equal(y2, g["y"]), (mt, phase)
+    col = c["collate"]
+    (pi, pt), pl = shaping.collate_fn_flava(col["ragged"])
+    assert torch.equal(pi, col["img"]) and torch.equal(pt, col["txt"]) and torch.equal(pl, col["labels"])
+
+
+def test_input_sampling_bit_exact(golden):
+    c = golden("input_sampling.pt")
+    np.random.seed(c["np_seed"])
+    torch.manual_seed(c["torch_seed"])
+    variants = shaping.robustness_variants(c["l_img"], c["l_txt"], c["n_repeats"])
+    assert len(variants) == 3 + 2 * c["n_repeats"]
+    for (ii, it), (gi, gt) in zip(variants[3:], c["draws"]):
+        ii = ii if ii is not None else torch.zeros(0, dtype=torch.int64)
+        it = it if it is not None else torch.zeros(0, dtype=torch.int64)
+        assert torch.equal(ii, gi) and torch.equal(it, gt)
+
+
+def test_notebook_scoring(golden):
+    c = golden("notebook_scoring.pt")
+    preds, labels = c["preds"].numpy(), c["labels"].numpy()
+    ori, image, text, ic, tc = uncertainty.process_predictions(preds, labels)
+    assert np.allclose(ori, c["ori"].numpy(), rtol=1e-6)
+    assert np.allclose(ic, c["image_corr"].numpy(), rtol=1e-6)
+    assert np.allclose(tc, c["text_corr"].numpy(), rtol=1e-6)
+    corr = uncertainty.get_correlation(ori, image, text, ic, tc)
+    assert abs(corr["image"] - c["corr_image"]) < 1e-6  # reference runs pearsonr in fp32
+    assert abs(corr["text"] - c["corr_text"]) < 1e-6
+    assert abs(uncertainty.acc_table(preds, labels)["full"] - c["acc_full"]) < 1e-9
+
+
+def test_uncertainty_identities():
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(500, 5, 101, generator=g) * 3
+    y = torch.randint(0, 101, (500,), generator=g)
+    s = uncertainty.ensemble_scores(logits)
+    assert float(s["mi"].min()) > -1e-12                      # MI >= 0 (Jensen)
+    assert float((s["h_pred"] - np.log(101)).max()) < 1e-12    # H <= log C
+    same = logits[:, :1].expand(-1, 5, -1)                     # identical heads -> MI = 0
+    assert float(uncertainty.ensemble_scores(same)["mi"].abs().max()) < 1e-12
+    h = uncertainty.calibration_histograms(logits, y)
+    assert int(h["conf_count"].sum()) == 500 and int(h["hpred_count"].sum()) == 500
+    assert int(h["conf_correct"].sum()) == h["n_correct_prob"]
+    ece = uncertainty.ece_from_bins(h["conf_count"], h["conf_correct"], h["conf_sum"])
+    assert 0.0 <= ece <= 1.0
