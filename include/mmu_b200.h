@@ -1,0 +1,202 @@
+/* mmu_b200 -- C ABI of the B200-native hot path of wooginawunan/multi-modal-uncertainty.
+ *
+ * The reference has no FFI / plugin registry: its boundary is a Python protocol
+ * (SURVEY.md section 8b).  This header is therefore the interface a maintainer would bind from
+ * Python (ctypes) to replace, call site by call site, the ATen operators
+ * the reference path dispatches to.  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless stated otherwise;
+ *   - the caller owns every buffer; the library never allocates, frees or synchronises;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); calls are re-entrant per
+ *     stream;
+ *   - return value: 0 on success, a negative MMU_ERR_* code otherwise; nothing throws;
+ *   - dtype arguments: MMU_F32 or MMU_BF16 (storage of GEMM operands / activations); all
+ *     accumulation, statistics, losses and optimiser state are fp32;
+ *   - there is NO CPU fallback: without a B200 and libcuda every compute entry point returns
+ *     MMU_ERR_DRIVER / MMU_ERR_CUDA.
+ */
+#ifndef MMU_B200_H_
+#define MMU_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MMU_API __attribute__((visibility("default")))
+#else
+#define MMU_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMU_OK 0
+#define MMU_ERR_SHAPE (-1)
+#define MMU_ERR_ALIGN (-2)
+#define MMU_ERR_DRIVER (-3)
+#define MMU_ERR_TMAP (-4)
+#define MMU_ERR_CUDA (-5)
+#define MMU_ERR_ARG (-6)
+#define MMU_ERR_WORKSPACE (-7)
+
+#define MMU_F32 0
+#define MMU_BF16 1
+
+/* GEMM epilogue modes */
+#define MMU_EPI_STORE 0
+#define MMU_EPI_QUICKGELU 1
+#define MMU_EPI_RESIDUAL 2
+#define MMU_EPI_DGELU 3
+#define MMU_EPI_ATOMIC 4
+
+MMU_API const char* mmu_version(void);
+MMU_API const char* mmu_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense contraction  C[M,N] = epilogue( sum_k A(m,k) B(n,k) )
+ * Replaces nn.Linear / F.linear (src/model.py:262,264 projections; :193 MHA in_proj/out_proj;
+ * :195-201 MLP c_fc/c_proj) and their autograd backward (dgrad / wgrad).
+ *   a_mn_major = 0: A stored [M][K] (lda = row pitch);  1: A stored [K][M].  Same for B/[N].
+ *   dtype MMU_BF16: tcgen05/TMEM/TMA tensor-core kernel, fp32 accumulate;
+ *   dtype MMU_F32 : fp32 FFMA kernel (the 1e-3 parity path).
+ * Epilogues (alpha scales the accumulator, bias is fp32[N] or NULL):
+ *   STORE      out = alpha*acc + bias                      (out: dtype if out_lp else fp32)
+ *   QUICKGELU  z = alpha*acc + bias; out = z (may be NULL); out2 = z*sigmoid(1.702 z)
+ *              (src/model.py:183-185 QuickGELU fused behind c_fc)
+ *   RESIDUAL   out(fp32) = aux(fp32) + alpha*acc + bias    (src/model.py:210-211)
+ *   DGELU      out = alpha*acc * d/dz QuickGELU(z), z = aux (dtype)
+ *   ATOMIC     out(fp32) += alpha*acc, split-K `splits` ways (weight gradients)
+ * seg_len > 0 remaps output rows r -> (r/seg_len)*seg_stride + seg_off + r%seg_len, which writes
+ * a per-modality projection straight into the concatenated sequence (fuses torch.cat :273). */
+typedef struct {
+  int mode;
+  int out_lp;      /* 1: out/out2 stored in `dtype`; 0: fp32 */
+  void* out;
+  void* out2;
+  const float* bias;
+  const void* aux;
+  long long ld_out, ld_out2, ld_aux;
+  int seg_len, seg_stride, seg_off;
+  float alpha;
+} mmu_gemm_epilogue;
+
+MMU_API int mmu_gemm(int dtype, const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+             int b_mn_major, int M, int N, int K, int splits, const mmu_gemm_epilogue* epi,
+             void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Input staging: token-subset gather + per-sample modality zero-fill + cast.
+ * Replaces the fancy indexing `img[:, indices_img, :]` of eval_transformer_robustness.py:118-119,
+ * the zero-fill masking of eval_robustness.py:92-97 and the H2D-side dtype handling.
+ * src fp32 (B, l_src, d) -> dst (B, n_sel, d).  idx: int32[n_sel] or NULL (identity);
+ * keep: int32[B,2] or NULL; `modality` (0 image, 1 text) selects the keep column. */
+MMU_API int mmu_mask_gather_tokens(const float* src, void* dst, int dst_dtype, int B, int l_src, int d,
+                           const int* idx, int n_sel, const int* keep, int modality, void* stream);
+
+/* LayerNorm, eps 1e-5, biased variance, fp32 statistics (src/model.py:174-180 LayerNorm
+ * subclass; :252-253 ln_pre / ln_post).  mean/rstd: fp32[M], saved for the backward. */
+MMU_API int mmu_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
+                      float* mean, float* rstd, int M, int D, void* stream);
+/* dx(fp32) = (accumulate ? dx : 0) + dLN(dy); dgamma/dbeta += ; dcolsum (may be NULL) += column
+ * sums of the final dx; dx_lp (may be NULL): copy of the final dx in lp_dtype. */
+MMU_API int mmu_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* mean,
+                      const float* rstd, const float* gamma, float* dx, int accumulate, void* dx_lp,
+                      int lp_dtype, float* dgamma, float* dbeta, float* dcolsum, int M, int D,
+                      void* stream);
+
+/* Batch-axis multi-head attention (src/model.py:193,205-207: nn.MultiheadAttention with
+ * batch_first=False fed (B, L, D), i.e. attention across the mini-batch, per token position).
+ * qkv: [B*L, 3D] packed q|k|v; out: [B*L, D]; lse: fp32[L*H*B]; B <= 256. */
+MMU_API int mmu_batchaxis_attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int L,
+                                int D, int H, void* stream);
+MMU_API int mmu_batchaxis_attention_bwd(const void* qkv, const void* out, const void* dout,
+                                const float* lse, float* delta_ws /* fp32[L*H*B] */, void* dqkv,
+                                int dtype, int B, int L, int D, int H, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused softmax / cross-entropy (+gradient) / accuracy / uncertainty / calibration epilogue.
+ * Replaces CrossEntropyLoss in compute_loss (src/model.py:293-304), `acc` (train.py:119-130)
+ * and the .cpu().numpy() logits dump + notebook scoring of the robustness scripts
+ * (eval_transformer_robustness.py:123-137) with on-device accumulators.
+ *   mode 0 (train): one CE row per (sample, head) against labels[n*label_stride + e*label_estride]
+ *   mode 1 (eval) : CE on the head-mean logits against labels[n*label_stride]
+ *   dlogits (mode 0, may be NULL): (softmax - onehot) * grad_scale, same layout as logits.
+ *   pred_out: int32[N,2] = (prediction behind `acc`, argmax of the mean probability) or NULL.
+ *   scores_out: fp32[N,4] = (confidence, H_pred, H_exp, MI) or NULL.
+ *   accum: device mmu_metric_accum, accumulated with atomics (zero it first); may be NULL. */
+typedef struct {
+  unsigned long long conf_count[15];   /* confidence histogram, bin = min(floor(conf*15), 14) */
+  unsigned long long conf_correct[15];
+  unsigned long long hpred_count[32];  /* H_pred / log C    in 32 equal bins */
+  unsigned long long mi_count[32];     /* MI / log max(E,2) in 32 equal bins */
+  unsigned long long n_samples;
+  unsigned long long n_rows;
+  unsigned long long n_correct_rows;
+  unsigned long long n_correct_prob;
+  double conf_sum[15];
+  double loss_sum;
+  double sum_h_pred, sum_h_exp, sum_mi;
+} mmu_metric_accum;
+
+MMU_API int mmu_heads_uncertainty_epilogue(const float* logits, const long long* labels, int label_stride,
+                                   int label_estride, int N, int E, int C, int mode,
+                                   float grad_scale, float* dlogits, int* pred_out,
+                                   float* scores_out, mmu_metric_accum* accum, void* stream);
+
+/* Fused AdamW over a flat fp32 buffer: torch.optim.AdamW as configured in train.py:196-202.
+ * `step` is the 1-based step count; grad_scale multiplies g first (1/world_size for DDP);
+ * p_bf16 (may be NULL) receives the bf16 shadow of the updated parameters.  n % 4 == 0. */
+MMU_API int mmu_adamw_flat_step(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                        float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FLAVA-fusion engine: FlavaFusionTransfomer / FlavaFusionTransfomerwithCLSToken forward and
+ * backward (src/model.py:225-374) over caller-owned flat buffers. */
+typedef struct {
+  int B, l_img, l_txt, d_img, d_txt, D, n_head, n_layers, E, C;
+  int avg_pool;   /* kwargs["avg_pool"], src/model.py:256,281-284 */
+  int cls_token;  /* 1: the CLS-token variant, src/model.py:306-361 */
+  int precision;  /* MMU_F32 or MMU_BF16 */
+} mmu_flava_config;
+
+typedef struct {
+  char name[96];      /* reference state_dict key, e.g. "mm_encoder.resblocks.0.attn.in_proj_weight" */
+  long long offset;   /* element offset into the flat parameter / gradient buffers */
+  long long numel;
+  int rows, cols;     /* cols == 0: vector */
+  int stage;          /* backward stage that completes this gradient */
+} mmu_param_entry;
+
+MMU_API long long mmu_flava_param_count(const mmu_flava_config* cfg);
+MMU_API int mmu_flava_param_table(const mmu_flava_config* cfg, mmu_param_entry* out /* host */, int max);
+MMU_API long long mmu_flava_workspace_bytes(const mmu_flava_config* cfg, int training);
+MMU_API int mmu_flava_num_stages(const mmu_flava_config* cfg);
+
+typedef struct {
+  const float* img;    /* (B, l_img, d_img) fp32 or NULL (modality absent) */
+  const float* txt;    /* (B, l_txt, d_txt) fp32 or NULL */
+  const int* idx_img;  /* int32[n_img] token subset or NULL (first n_img tokens) */
+  const int* idx_txt;
+  int n_img, n_txt;    /* tokens fed to the model (<= l_img / l_txt) */
+  const int* keep;     /* int32[B,2] modality keep mask (0: zero-fill) or NULL */
+} mmu_flava_inputs;
+
+/* logits: fp32 (B, E, C).  training != 0 keeps the activations the backward needs. */
+MMU_API int mmu_flava_forward(const mmu_flava_config* cfg, const float* params, const mmu_flava_inputs* in,
+                      void* workspace, long long workspace_bytes, int training, float* logits,
+                      void* stream);
+/* grads (flat fp32, same layout as params) are ACCUMULATED (+=), like autograd's .grad.
+ * Stages [stage_begin, stage_end): 0 heads+ln_post, 1..n_layers the blocks in reverse order,
+ * n_layers+1 the stem; running them in separate calls lets the caller overlap a bucketed
+ * gradient all-reduce with the rest of the backward. */
+MMU_API int mmu_flava_backward(const mmu_flava_config* cfg, const float* params, const mmu_flava_inputs* in,
+                       void* workspace, long long workspace_bytes, const float* dlogits,
+                       float* grads, int stage_begin, int stage_end, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMU_B200_H_ */

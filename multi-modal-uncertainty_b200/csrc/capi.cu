@@ -1,0 +1,162 @@
+// extern "C" surface of libmmu_b200.so: thin, exception-free adapters over the C++ launchers.
+#include <cstring>
+
+#include "../../include/mmu_b200.h"
+#include "common.h"
+#include "engine.h"
+#include "gemm_api.h"
+#include "kernels.h"
+
+using namespace mmu;
+
+static_assert(sizeof(mmu_metric_accum) == sizeof(MetricAccum), "metric accumulator layout");
+static_assert(sizeof(mmu_flava_config) == sizeof(FlavaConfig), "config layout");
+static_assert(sizeof(mmu_param_entry) == sizeof(ParamEntry), "param entry layout");
+static_assert(sizeof(mmu_flava_inputs) == sizeof(FlavaInputs), "inputs layout");
+
+namespace {
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+inline FlavaConfig cfg_of(const mmu_flava_config* c) {
+  FlavaConfig r;
+  std::memcpy(&r, c, sizeof(r));
+  return r;
+}
+inline FlavaInputs in_of(const mmu_flava_inputs* i) {
+  FlavaInputs r;
+  std::memcpy(&r, i, sizeof(r));
+  return r;
+}
+}  // namespace
+
+extern "C" {
+
+const char* mmu_version(void) { return "mmu_b200 0.1 (sm_100a)"; }
+
+const char* mmu_error_string(int code) {
+  switch (code) {
+    case MMU_OK: return "ok";
+    case MMU_ERR_SHAPE: return "unsupported or inconsistent shape";
+    case MMU_ERR_ALIGN: return "pointer or leading dimension not 16-byte aligned";
+    case MMU_ERR_DRIVER: return "CUDA driver entry point unavailable (no GPU?)";
+    case MMU_ERR_TMAP: return "tensor-map encoding failed";
+    case MMU_ERR_CUDA: return "CUDA launch failed";
+    case MMU_ERR_ARG: return "bad argument";
+    case MMU_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown error";
+  }
+}
+
+int mmu_gemm(int dtype, const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+             int b_mn_major, int M, int N, int K, int splits, const mmu_gemm_epilogue* epi,
+             void* stream) {
+  if (A == nullptr || B == nullptr || epi == nullptr || epi->out == nullptr && epi->out2 == nullptr)
+    return MMU_ERR_ARG;
+  GemmProblem p{M, N, K, a_mn_major, b_mn_major, splits};
+  GemmEpilogue e{};
+  e.mode = epi->mode;
+  e.out_bf16 = (dtype == MMU_BF16 && epi->out_lp) ? 1 : 0;
+  e.out = epi->out;
+  e.out2 = epi->out2;
+  e.bias = epi->bias;
+  e.aux = epi->aux;
+  e.ld_out = epi->ld_out;
+  e.ld_out2 = epi->ld_out2;
+  e.ld_aux = epi->ld_aux;
+  e.seg_len = epi->seg_len;
+  e.seg_stride = epi->seg_stride;
+  e.seg_off = epi->seg_off;
+  e.alpha = epi->alpha;
+  if (dtype == MMU_BF16) return gemm_bf16_launch(A, lda, B, ldb, p, e, S(stream));
+  if (dtype == MMU_F32)
+    return gemm_f32_launch(static_cast<const float*>(A), lda, static_cast<const float*>(B), ldb, p,
+                           e, S(stream));
+  return MMU_ERR_ARG;
+}
+
+int mmu_mask_gather_tokens(const float* src, void* dst, int dst_dtype, int B, int l_src, int d,
+                           const int* idx, int n_sel, const int* keep, int modality, void* stream) {
+  if (src == nullptr || dst == nullptr) return MMU_ERR_ARG;
+  return cast_gather(src, dst, dst_dtype, B, l_src, d, idx, n_sel, keep, modality, S(stream));
+}
+
+int mmu_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
+                      float* mean, float* rstd, int M, int D, void* stream) {
+  if (x == nullptr || gamma == nullptr || beta == nullptr || y == nullptr) return MMU_ERR_ARG;
+  return layernorm_fwd(x, gamma, beta, y, y_dtype, mean, rstd, M, D, S(stream));
+}
+
+int mmu_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* mean,
+                      const float* rstd, const float* gamma, float* dx, int accumulate, void* dx_lp,
+                      int lp_dtype, float* dgamma, float* dbeta, float* dcolsum, int M, int D,
+                      void* stream) {
+  if (dy == nullptr || x == nullptr || mean == nullptr || rstd == nullptr || gamma == nullptr ||
+      dx == nullptr || dgamma == nullptr || dbeta == nullptr)
+    return MMU_ERR_ARG;
+  return layernorm_bwd(dy, dy_dtype, x, mean, rstd, gamma, dx, accumulate, dx_lp, lp_dtype, dgamma,
+                       dbeta, dcolsum, M, D, S(stream));
+}
+
+int mmu_batchaxis_attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int L,
+                                int D, int H, void* stream) {
+  if (qkv == nullptr || out == nullptr || lse == nullptr) return MMU_ERR_ARG;
+  return attention_fwd(qkv, out, lse, dtype, B, L, D, H, S(stream));
+}
+
+int mmu_batchaxis_attention_bwd(const void* qkv, const void* out, const void* dout,
+                                const float* lse, float* delta_ws, void* dqkv, int dtype, int B,
+                                int L, int D, int H, void* stream) {
+  if (qkv == nullptr || out == nullptr || dout == nullptr || lse == nullptr ||
+      delta_ws == nullptr || dqkv == nullptr)
+    return MMU_ERR_ARG;
+  return attention_bwd(qkv, out, dout, lse, delta_ws, dqkv, dtype, B, L, D, H, S(stream));
+}
+
+int mmu_heads_uncertainty_epilogue(const float* logits, const long long* labels, int label_stride,
+                                   int label_estride, int N, int E, int C, int mode,
+                                   float grad_scale, float* dlogits, int* pred_out,
+                                   float* scores_out, mmu_metric_accum* accum, void* stream) {
+  if (logits == nullptr || labels == nullptr) return MMU_ERR_ARG;
+  return ce_uncertainty(logits, labels, label_stride, label_estride, N, E, C, mode, grad_scale,
+                        dlogits, pred_out, scores_out, reinterpret_cast<MetricAccum*>(accum),
+                        S(stream));
+}
+
+int mmu_adamw_flat_step(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                        float grad_scale, void* stream) {
+  if (p == nullptr || g == nullptr || m == nullptr || v == nullptr) return MMU_ERR_ARG;
+  return adamw_flat(p, g, m, v, p_bf16, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                    S(stream));
+}
+
+long long mmu_flava_param_count(const mmu_flava_config* cfg) {
+  return cfg == nullptr ? MMU_ERR_ARG : flava_param_count(cfg_of(cfg));
+}
+int mmu_flava_param_table(const mmu_flava_config* cfg, mmu_param_entry* out, int max) {
+  return cfg == nullptr ? MMU_ERR_ARG
+                        : flava_param_table(cfg_of(cfg), reinterpret_cast<ParamEntry*>(out), max);
+}
+long long mmu_flava_workspace_bytes(const mmu_flava_config* cfg, int training) {
+  return cfg == nullptr ? MMU_ERR_ARG : flava_workspace_bytes(cfg_of(cfg), training);
+}
+int mmu_flava_num_stages(const mmu_flava_config* cfg) {
+  return cfg == nullptr ? MMU_ERR_ARG : flava_num_stages(cfg_of(cfg));
+}
+
+int mmu_flava_forward(const mmu_flava_config* cfg, const float* params, const mmu_flava_inputs* in,
+                      void* workspace, long long workspace_bytes, int training, float* logits,
+                      void* stream) {
+  if (cfg == nullptr || in == nullptr) return MMU_ERR_ARG;
+  return flava_forward(cfg_of(cfg), params, in_of(in), workspace, workspace_bytes, training, logits,
+                       S(stream));
+}
+
+int mmu_flava_backward(const mmu_flava_config* cfg, const float* params, const mmu_flava_inputs* in,
+                       void* workspace, long long workspace_bytes, const float* dlogits,
+                       float* grads, int stage_begin, int stage_end, void* stream) {
+  if (cfg == nullptr || in == nullptr) return MMU_ERR_ARG;
+  return flava_backward(cfg_of(cfg), params, in_of(in), workspace, workspace_bytes, dlogits, grads,
+                        stage_begin, stage_end, S(stream));
+}
+
+}  // extern "C"

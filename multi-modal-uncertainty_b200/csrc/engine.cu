@@ -1,0 +1,520 @@
+// FLAVA-fusion engine implementation.  See engine.h.
+//
+// Data layout in HBM (all row-major, row r = b*L + l of the (B, L, .) activation tensors):
+//   residual stream x          fp32 [B*L, D]      (kept in fp32 in both precisions)
+//   GEMM operands / outputs    fp32 or bf16       (h = LN(x), qkv, attention out, z, u, grads)
+//   parameters / gradients     one flat fp32 buffer each (+ bf16 shadow of the parameters)
+// Forward, per layer (src/model.py:209-212):
+//   h1 = ln_1(x0) ; qkv = h1 Win^T + bin ; o = batch-axis attention(qkv)
+//   x1 = x0 + o Wout^T + bout                       (GEMM, residual epilogue)
+//   h2 = ln_2(x1) ; z = h2 Wfc^T + bfc ; u = z sigmoid(1.702 z)   (GEMM, QuickGELU epilogue)
+//   x2 = x1 + u Wproj^T + bproj                     (GEMM, residual epilogue)
+// Backward mirrors it with dgrad GEMMs (MN-major weight operand), split-K wgrad GEMMs
+// (MN-major activations, fp32 atomics into the flat gradient buffer), the dGELU epilogue and
+// LayerNorm-backward kernels that also emit the bias gradient of the preceding projection.
+#include "engine.h"
+
+#include <cstdio>
+#include <cstring>
+
+#include "common.h"
+#include "gemm_api.h"
+#include "kernels.h"
+
+namespace mmu {
+
+namespace {
+
+constexpr long long ALIGN_ELEMS = 64;
+
+long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+struct LayerParams {
+  long long ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b;
+};
+struct Layout {
+  long long img_w, img_b, txt_w, txt_b, cls, lnpre_w, lnpre_b;
+  LayerParams layer[64];
+  long long lnpost_w, lnpost_b, head_w[16], head_b[16];
+  long long total;
+};
+
+struct TableBuilder {
+  ParamEntry* out;
+  int max, n;
+  long long cursor;
+  long long add(const char* name, int rows, int cols, int stage) {
+    const long long numel = static_cast<long long>(rows) * (cols > 0 ? cols : 1);
+    const long long off = cursor;
+    if (out != nullptr && n < max) {
+      ParamEntry& e = out[n];
+      std::memset(&e, 0, sizeof(e));
+      std::snprintf(e.name, sizeof(e.name), "%s", name);
+      e.offset = off;
+      e.numel = numel;
+      e.rows = rows;
+      e.cols = cols;
+      e.stage = stage;
+    }
+    ++n;
+    cursor = align_up(cursor + numel, ALIGN_ELEMS);
+    return off;
+  }
+};
+
+int build_layout(const FlavaConfig& c, Layout* L, ParamEntry* out, int max_entries) {
+  if (c.n_layers < 0 || c.n_layers > 64 || c.E < 1 || c.E > 16) return MMU_ERR_SHAPE;
+  TableBuilder tb{out, max_entries, 0, 0};
+  const int stem = c.n_layers + 1;
+  char nm[96];
+  L->img_w = tb.add("image_to_mm_projection.weight", c.D, c.d_img, stem);
+  L->img_b = tb.add("image_to_mm_projection.bias", c.D, 0, stem);
+  L->txt_w = tb.add("text_to_mm_projection.weight", c.D, c.d_txt, stem);
+  L->txt_b = tb.add("text_to_mm_projection.bias", c.D, 0, stem);
+  L->cls = -1;
+  if (c.cls_token) L->cls = tb.add("class_embeddings", c.D, c.E, stem);
+  L->lnpre_w = tb.add("ln_pre.weight", c.D, 0, stem);
+  L->lnpre_b = tb.add("ln_pre.bias", c.D, 0, stem);
+  for (int i = 0; i < c.n_layers; ++i) {
+    LayerParams& p = L->layer[i];
+    const int st = c.n_layers - i;  // backward visits the last layer first
+    auto name = [&](const char* suffix) {
+      std::snprintf(nm, sizeof(nm), "mm_encoder.resblocks.%d.%s", i, suffix);
+      return nm;
+    };
+    p.ln1_w = tb.add(name("ln_1.weight"), c.D, 0, st);
+    p.ln1_b = tb.add(name("ln_1.bias"), c.D, 0, st);
+    p.in_w = tb.add(name("attn.in_proj_weight"), 3 * c.D, c.D, st);
+    p.in_b = tb.add(name("attn.in_proj_bias"), 3 * c.D, 0, st);
+    p.out_w = tb.add(name("attn.out_proj.weight"), c.D, c.D, st);
+    p.out_b = tb.add(name("attn.out_proj.bias"), c.D, 0, st);
+    p.ln2_w = tb.add(name("ln_2.weight"), c.D, 0, st);
+    p.ln2_b = tb.add(name("ln_2.bias"), c.D, 0, st);
+    p.fc_w = tb.add(name("mlp.c_fc.weight"), 4 * c.D, c.D, st);
+    p.fc_b = tb.add(name("mlp.c_fc.bias"), 4 * c.D, 0, st);
+    p.proj_w = tb.add(name("mlp.c_proj.weight"), c.D, 4 * c.D, st);
+    p.proj_b = tb.add(name("mlp.c_proj.bias"), c.D, 0, st);
+  }
+  L->lnpost_w = tb.add("ln_post.weight", c.D, 0, 0);
+  L->lnpost_b = tb.add("ln_post.bias", c.D, 0, 0);
+  for (int e = 0; e < c.E; ++e) {
+    std::snprintf(nm, sizeof(nm), "output_layers.%d.weight", e);
+    L->head_w[e] = tb.add(nm, c.C, c.D, 0);
+    std::snprintf(nm, sizeof(nm), "output_layers.%d.bias", e);
+    L->head_b[e] = tb.add(nm, c.C, 0, 0);
+  }
+  L->total = tb.cursor;
+  return tb.n;
+}
+
+// ------------------------------------------------------------------ workspace carving
+struct LayerWs {
+  float* x0;       // layer input (residual stream)
+  float* stats1;   // mean | rstd of ln_1
+  void* h1;
+  void* qkv;
+  float* lse;
+  void* o;
+  float* x1;
+  float* stats2;
+  void* h2;
+  void* z;
+  void* u;
+};
+struct Ws {
+  void* params_lp;
+  void* img_t;
+  void* txt_t;
+  float* mm_x;
+  float* stats_pre;
+  LayerWs layer[64];
+  float* x_out[2];   // ping-pong outputs when activations are not saved
+  float* x_final;    // training: dedicated buffer
+  float* stats_post;
+  float* vec;
+  // backward
+  float* dvec;
+  float* dx;
+  void* dx_lp;
+  void* dbig;   // dz / dqkv
+  void* dh;     // dh2 / do / dh1
+  float* delta;
+  void* dimg;
+  void* dtxt;
+  long long bytes;
+};
+
+struct Bump {
+  char* base;
+  long long off;
+  template <typename T>
+  T* take(long long bytes) {
+    const long long o = off;
+    off = align_up(off + bytes, 256);
+    return base != nullptr ? reinterpret_cast<T*>(base + o) : nullptr;
+  }
+};
+
+void carve(const FlavaConfig& c, int training, void* base, const Layout& lay, Ws* w) {
+  Bump b{static_cast<char*>(base), 0};
+  const long long s = c.precision == PREC_BF16 ? 2 : 4;
+  const long long L = (c.cls_token ? c.E : 0) + c.l_img + c.l_txt;
+  const long long M = static_cast<long long>(c.B) * L;
+  const long long D = c.D;
+  w->params_lp = c.precision == PREC_BF16 ? b.take<void>(lay.total * 2) : nullptr;
+  w->img_t = b.take<void>(static_cast<long long>(c.B) * c.l_img * c.d_img * s);
+  w->txt_t = b.take<void>(static_cast<long long>(c.B) * c.l_txt * c.d_txt * s);
+  w->mm_x = b.take<float>(M * D * 4);
+  w->stats_pre = b.take<float>(2 * M * 4);
+  const int slots = training ? c.n_layers : (c.n_layers > 0 ? 1 : 0);
+  for (int i = 0; i < slots; ++i) {
+    LayerWs& l = w->layer[i];
+    l.x0 = training ? b.take<float>(M * D * 4) : nullptr;
+    l.stats1 = b.take<float>(2 * M * 4);
+    l.h1 = b.take<void>(M * D * s);
+    l.qkv = b.take<void>(M * 3 * D * s);
+    l.lse = b.take<float>(L * c.n_head * c.B * 4);
+    l.o = b.take<void>(M * D * s);
+    l.x1 = b.take<float>(M * D * 4);
+    l.stats2 = b.take<float>(2 * M * 4);
+    l.h2 = b.take<void>(M * D * s);
+    l.z = b.take<void>(M * 4 * D * s);
+    l.u = b.take<void>(M * 4 * D * s);
+  }
+  for (int i = slots; i < c.n_layers; ++i) w->layer[i] = w->layer[0];
+  w->x_out[0] = b.take<float>(M * D * 4);
+  w->x_out[1] = training ? nullptr : b.take<float>(M * D * 4);
+  w->x_final = w->x_out[0];
+  w->stats_post = b.take<float>(2 * M * 4);
+  w->vec = b.take<float>(static_cast<long long>(c.B) * c.E * D * 4);
+  if (training) {
+    w->dvec = b.take<float>(static_cast<long long>(c.B) * c.E * D * 4);
+    w->dx = b.take<float>(M * D * 4);
+    w->dx_lp = c.precision == PREC_BF16 ? b.take<void>(M * D * s) : static_cast<void*>(w->dx);
+    w->dbig = b.take<void>(M * 4 * D * s);
+    w->dh = b.take<void>(M * D * s);
+    w->delta = b.take<float>(L * c.n_head * c.B * 4);
+    w->dimg = b.take<void>(static_cast<long long>(c.B) * c.l_img * D * s);
+    w->dtxt = b.take<void>(static_cast<long long>(c.B) * c.l_txt * D * s);
+  } else {
+    w->dvec = nullptr; w->dx = nullptr; w->dx_lp = nullptr; w->dbig = nullptr; w->dh = nullptr;
+    w->delta = nullptr; w->dimg = nullptr; w->dtxt = nullptr;
+  }
+  w->bytes = b.off;
+}
+
+int check_config(const FlavaConfig& c) {
+  if (c.B < 1 || c.D < 4 || c.n_head < 1 || c.E < 1 || c.E > 16 || c.C < 1) return MMU_ERR_SHAPE;
+  if (c.D % c.n_head != 0 || (c.D / c.n_head) % 4 != 0) return MMU_ERR_SHAPE;
+  if (c.D % 4 != 0 || c.d_img % 4 != 0 || c.d_txt % 4 != 0 || c.D > 1024) return MMU_ERR_SHAPE;
+  if (c.precision == PREC_BF16 && (c.D % 8 != 0 || c.d_img % 8 != 0 || c.d_txt % 8 != 0))
+    return MMU_ERR_SHAPE;
+  if (c.precision != PREC_FP32 && c.precision != PREC_BF16) return MMU_ERR_ARG;
+  if (c.avg_pool && !c.cls_token && c.E != 2) return MMU_ERR_SHAPE;  // src/model.py:282-284
+  return 0;
+}
+
+// One dense contraction, dispatched on precision.  A: [M,K] (K-major) or [K,M] (MN-major).
+struct Gemm {
+  int prec;
+  cudaStream_t stream;
+  int operator()(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn,
+                 int M, int N, int K, GemmEpilogue e, int splits = 1) const {
+    GemmProblem p{M, N, K, a_mn, b_mn, splits};
+    e.out_bf16 = prec == PREC_BF16 ? e.out_bf16 : 0;
+    if (prec == PREC_BF16) return gemm_bf16_launch(A, lda, B, ldb, p, e, stream);
+    return gemm_f32_launch(static_cast<const float*>(A), lda, static_cast<const float*>(B), ldb, p,
+                           e, stream);
+  }
+};
+
+GemmEpilogue epi(int mode, void* out, int out_bf16, long long ld_out, const float* bias) {
+  GemmEpilogue e{};
+  e.mode = mode;
+  e.out_bf16 = out_bf16;
+  e.out = out;
+  e.ld_out = ld_out;
+  e.bias = bias;
+  e.alpha = 1.0f;
+  e.seg_len = 0;
+  return e;
+}
+
+int wgrad_splits(int Mg, int Ng, int K) {
+  const int tiles = ((Mg + 127) / 128) * ((Ng + 255) / 256);
+  int s = (sm_count() + tiles - 1) / tiles;
+  const int kb = (K + 63) / 64;
+  if (s > kb / 4) s = kb / 4;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return s;
+}
+
+#define MMU_TRY(x)            \
+  do {                        \
+    const int rc__ = (x);     \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+struct Shape {
+  int n_cls, n_img, n_txt, L, M;
+};
+int resolve_shape(const FlavaConfig& c, const FlavaInputs& in, Shape* s) {
+  s->n_cls = c.cls_token ? c.E : 0;
+  s->n_img = in.img != nullptr ? in.n_img : 0;
+  s->n_txt = in.txt != nullptr ? in.n_txt : 0;
+  if (s->n_img < 0 || s->n_img > c.l_img || s->n_txt < 0 || s->n_txt > c.l_txt) return MMU_ERR_SHAPE;
+  s->L = s->n_cls + s->n_img + s->n_txt;
+  s->M = c.B * s->L;
+  if (s->n_img + s->n_txt == 0) return MMU_ERR_SHAPE;
+  if (!c.avg_pool || c.cls_token) {
+    if (c.E > s->L) return MMU_ERR_SHAPE;  // head i reads token position i (src/model.py:286-287)
+  }
+  return 0;
+}
+
+HeadSegments head_segments(const FlavaConfig& c, const Shape& s) {
+  HeadSegments hs{};
+  hs.E = c.E;
+  if (c.avg_pool && !c.cls_token) {
+    hs.seg_begin[0] = 0; hs.seg_end[0] = s.n_img;
+    hs.seg_begin[1] = s.n_img; hs.seg_end[1] = s.n_img + s.n_txt;
+  } else {
+    for (int e = 0; e < c.E; ++e) { hs.seg_begin[e] = e; hs.seg_end[e] = e + 1; }
+  }
+  return hs;
+}
+
+}  // namespace
+
+// =========================================================================== public
+int flava_param_table(const FlavaConfig& c, ParamEntry* out, int max_entries) {
+  Layout lay;
+  return build_layout(c, &lay, out, max_entries);
+}
+
+long long flava_param_count(const FlavaConfig& c) {
+  Layout lay;
+  if (build_layout(c, &lay, nullptr, 0) < 0) return MMU_ERR_SHAPE;
+  return lay.total;
+}
+
+int flava_num_stages(const FlavaConfig& c) { return c.n_layers + 2; }
+
+long long flava_workspace_bytes(const FlavaConfig& c, int training) {
+  if (int rc = check_config(c)) return rc;
+  Layout lay;
+  if (build_layout(c, &lay, nullptr, 0) < 0) return MMU_ERR_SHAPE;
+  Ws w;
+  carve(c, training, nullptr, lay, &w);
+  return w.bytes;
+}
+
+int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& in, void* ws,
+                  long long ws_bytes, int training, float* logits, cudaStream_t stream) {
+  MMU_TRY(check_config(c));
+  if (params == nullptr || ws == nullptr || logits == nullptr) return MMU_ERR_ARG;
+  Layout lay;
+  if (build_layout(c, &lay, nullptr, 0) < 0) return MMU_ERR_SHAPE;
+  Ws w;
+  carve(c, training, ws, lay, &w);
+  if (w.bytes > ws_bytes) return MMU_ERR_WORKSPACE;
+  Shape s;
+  MMU_TRY(resolve_shape(c, in, &s));
+  const int bf = c.precision == PREC_BF16;
+  const int dt = bf ? DT_BF16 : DT_F32;
+  const int D = c.D, M = s.M;
+  const Gemm gemm{c.precision, stream};
+  // operand view of the parameters (bf16 shadow refreshed from the fp32 master every forward)
+  auto W = [&](long long off) -> const void* {
+    return bf ? static_cast<const void*>(static_cast<const uint16_t*>(w.params_lp) + off)
+              : static_cast<const void*>(params + off);
+  };
+  if (bf) MMU_TRY(cast_f32_to_bf16(params, w.params_lp, static_cast<size_t>(lay.total), stream));
+
+  // ---- stem: gather/mask/cast inputs, per-modality projections written straight into the
+  //      concatenated (B, L, D) buffer (fuses torch.cat, src/model.py:262-273), CLS rows
+  if (s.n_img > 0) {
+    MMU_TRY(cast_gather(in.img, w.img_t, dt, c.B, c.l_img, c.d_img, in.idx_img, s.n_img, in.keep, 0,
+                        stream));
+    GemmEpilogue e = epi(EPI_STORE, w.mm_x, 0, D, params + lay.img_b);
+    e.seg_len = s.n_img; e.seg_stride = s.L; e.seg_off = s.n_cls;
+    MMU_TRY(gemm(w.img_t, c.d_img, 0, W(lay.img_w), c.d_img, 0, c.B * s.n_img, D, c.d_img, e));
+  }
+  if (s.n_txt > 0) {
+    MMU_TRY(cast_gather(in.txt, w.txt_t, dt, c.B, c.l_txt, c.d_txt, in.idx_txt, s.n_txt, in.keep, 1,
+                        stream));
+    GemmEpilogue e = epi(EPI_STORE, w.mm_x, 0, D, params + lay.txt_b);
+    e.seg_len = s.n_txt; e.seg_stride = s.L; e.seg_off = s.n_cls + s.n_img;
+    MMU_TRY(gemm(w.txt_t, c.d_txt, 0, W(lay.txt_w), c.d_txt, 0, c.B * s.n_txt, D, c.d_txt, e));
+  }
+  if (c.cls_token) MMU_TRY(cls_fill(params + lay.cls, w.mm_x, c.B, s.L, D, c.E, stream));
+
+  float* x = training && c.n_layers > 0 ? w.layer[0].x0 : w.x_out[0];
+  MMU_TRY(layernorm_fwd(w.mm_x, params + lay.lnpre_w, params + lay.lnpre_b, x, DT_F32, w.stats_pre,
+                        w.stats_pre + M, M, D, stream));
+
+  // ---- transformer blocks
+  for (int i = 0; i < c.n_layers; ++i) {
+    const LayerParams& p = lay.layer[i];
+    const LayerWs& l = w.layer[i];
+    float* x_next;
+    if (training) x_next = (i + 1 < c.n_layers) ? w.layer[i + 1].x0 : w.x_final;
+    else x_next = w.x_out[(i + 1) & 1];
+    MMU_TRY(layernorm_fwd(x, params + p.ln1_w, params + p.ln1_b, l.h1, dt, l.stats1, l.stats1 + M,
+                          M, D, stream));
+    MMU_TRY(gemm(l.h1, D, 0, W(p.in_w), D, 0, M, 3 * D, D,
+                 epi(EPI_STORE, l.qkv, bf, 3 * D, params + p.in_b)));
+    MMU_TRY(attention_fwd(l.qkv, l.o, l.lse, dt, c.B, s.L, D, c.n_head, stream));
+    {
+      GemmEpilogue e = epi(EPI_RESIDUAL, l.x1, 0, D, params + p.out_b);
+      e.aux = x; e.ld_aux = D;
+      MMU_TRY(gemm(l.o, D, 0, W(p.out_w), D, 0, M, D, D, e));
+    }
+    MMU_TRY(layernorm_fwd(l.x1, params + p.ln2_w, params + p.ln2_b, l.h2, dt, l.stats2,
+                          l.stats2 + M, M, D, stream));
+    {
+      GemmEpilogue e = epi(EPI_QUICKGELU, training ? l.z : nullptr, bf, 4 * D, params + p.fc_b);
+      e.out2 = l.u; e.ld_out2 = 4 * D;
+      MMU_TRY(gemm(l.h2, D, 0, W(p.fc_w), D, 0, M, 4 * D, D, e));
+    }
+    {
+      GemmEpilogue e = epi(EPI_RESIDUAL, x_next, 0, D, params + p.proj_b);
+      e.aux = l.x1; e.ld_aux = D;
+      MMU_TRY(gemm(l.u, 4 * D, 0, W(p.proj_w), 4 * D, 0, M, D, 4 * D, e));
+    }
+    x = x_next;
+  }
+
+  // ---- ln_post + row gather / mean pooling + heads (src/model.py:277-289)
+  const HeadSegments hs = head_segments(c, s);
+  MMU_TRY(pool_ln_fwd(x, params + lay.lnpost_w, params + lay.lnpost_b, hs, w.vec, w.stats_post,
+                      w.stats_post + M, c.B, s.L, D, stream));
+  HeadParams hp{};
+  for (int e = 0; e < c.E; ++e) {
+    hp.w[e] = params + lay.head_w[e];
+    hp.b[e] = params + lay.head_b[e];
+  }
+  MMU_TRY(heads_fwd(w.vec, hp, logits, c.B, c.E, c.C, D, stream));
+  return 0;
+}
+
+int flava_backward(const FlavaConfig& c, const float* params, const FlavaInputs& in, void* ws,
+                   long long ws_bytes, const float* dlogits, float* grads, int stage_begin,
+                   int stage_end, cudaStream_t stream) {
+  MMU_TRY(check_config(c));
+  if (params == nullptr || ws == nullptr || dlogits == nullptr || grads == nullptr) return MMU_ERR_ARG;
+  Layout lay;
+  if (build_layout(c, &lay, nullptr, 0) < 0) return MMU_ERR_SHAPE;
+  Ws w;
+  carve(c, 1, ws, lay, &w);
+  if (w.bytes > ws_bytes) return MMU_ERR_WORKSPACE;
+  Shape s;
+  MMU_TRY(resolve_shape(c, in, &s));
+  const int bf = c.precision == PREC_BF16;
+  const int dt = bf ? DT_BF16 : DT_F32;
+  const int D = c.D, M = s.M;
+  const Gemm gemm{c.precision, stream};
+  auto W = [&](long long off) -> const void* {
+    return bf ? static_cast<const void*>(static_cast<const uint16_t*>(w.params_lp) + off)
+              : static_cast<const void*>(params + off);
+  };
+  const int n_stages = c.n_layers + 2;
+  if (stage_begin < 0) stage_begin = 0;
+  if (stage_end > n_stages) stage_end = n_stages;
+
+  for (int st = stage_begin; st < stage_end; ++st) {
+    if (st == 0) {
+      // ---- heads + ln_post: dx (fp32) for the head rows, zero elsewhere
+      const HeadSegments hs = head_segments(c, s);
+      HeadParams hp{};
+      for (int e = 0; e < c.E; ++e) {
+        hp.w[e] = params + lay.head_w[e];
+        hp.b[e] = params + lay.head_b[e];
+        hp.dw[e] = grads + lay.head_w[e];
+        hp.db[e] = grads + lay.head_b[e];
+      }
+      MMU_TRY(heads_bwd(dlogits, w.vec, hp, w.dvec, c.B, c.E, c.C, D, stream));
+      if (cudaMemsetAsync(w.dx, 0, static_cast<size_t>(M) * D * 4, stream) != cudaSuccess)
+        return MMU_ERR_CUDA;
+      const float* x_last = c.n_layers > 0 ? w.x_final : w.x_out[0];
+      MMU_TRY(pool_ln_bwd(w.dvec, x_last, w.stats_post, w.stats_post + M, params + lay.lnpost_w, hs,
+                          w.dx, grads + lay.lnpost_w, grads + lay.lnpost_b, c.B, s.L, D, stream));
+      if (c.n_layers > 0) {
+        // bias gradient of the last c_proj = column sum of dx; later layers get it from ln_1 bwd
+        MMU_TRY(colsum_accumulate(w.dx, DT_F32, grads + lay.layer[c.n_layers - 1].proj_b, M, D,
+                                  stream));
+        if (bf) MMU_TRY(cast_f32_to_bf16(w.dx, w.dx_lp, static_cast<size_t>(M) * D, stream));
+      }
+    } else if (st <= c.n_layers) {
+      const int i = c.n_layers - st;
+      const LayerParams& p = lay.layer[i];
+      const LayerWs& l = w.layer[i];
+      // x2 = x1 + u Wproj^T + bproj
+      {  // dz = (dx Wproj) * gelu'(z)
+        GemmEpilogue e = epi(EPI_DGELU, w.dbig, bf, 4 * D, nullptr);
+        e.aux = l.z; e.ld_aux = 4 * D;
+        MMU_TRY(gemm(w.dx_lp, D, 0, W(p.proj_w), 4 * D, 1, M, 4 * D, D, e));
+      }
+      // dWproj[D, 4D] += dx^T u
+      MMU_TRY(gemm(w.dx_lp, D, 1, l.u, 4 * D, 1, D, 4 * D, M,
+                   epi(EPI_ATOMIC, grads + p.proj_w, 0, 4 * D, nullptr),
+                   wgrad_splits(D, 4 * D, M)));
+      // dWfc[4D, D] += dz^T h2 ; dbfc += colsum(dz)
+      MMU_TRY(gemm(w.dbig, 4 * D, 1, l.h2, D, 1, 4 * D, D, M,
+                   epi(EPI_ATOMIC, grads + p.fc_w, 0, D, nullptr), wgrad_splits(4 * D, D, M)));
+      MMU_TRY(colsum_accumulate(w.dbig, dt, grads + p.fc_b, M, 4 * D, stream));
+      // dh2 = dz Wfc
+      MMU_TRY(gemm(w.dbig, 4 * D, 0, W(p.fc_w), D, 1, M, D, 4 * D,
+                   epi(EPI_STORE, w.dh, bf, D, nullptr)));
+      // dx1 = dx + LN2'(dh2); dbout += colsum(dx1)
+      MMU_TRY(layernorm_bwd(w.dh, dt, l.x1, l.stats2, l.stats2 + M, params + p.ln2_w, w.dx, 1,
+                            bf ? w.dx_lp : nullptr, dt, grads + p.ln2_w, grads + p.ln2_b,
+                            grads + p.out_b, M, D, stream));
+      // x1 = x0 + o Wout^T + bout:  dWout += dx1^T o ; do = dx1 Wout
+      MMU_TRY(gemm(w.dx_lp, D, 1, l.o, D, 1, D, D, M, epi(EPI_ATOMIC, grads + p.out_w, 0, D, nullptr),
+                   wgrad_splits(D, D, M)));
+      MMU_TRY(gemm(w.dx_lp, D, 0, W(p.out_w), D, 1, M, D, D, epi(EPI_STORE, w.dh, bf, D, nullptr)));
+      // attention backward: dqkv
+      MMU_TRY(attention_bwd(l.qkv, l.o, w.dh, l.lse, w.delta, w.dbig, dt, c.B, s.L, D, c.n_head,
+                            stream));
+      // dWin[3D, D] += dqkv^T h1 ; dbin += colsum(dqkv) ; dh1 = dqkv Win
+      MMU_TRY(gemm(w.dbig, 3 * D, 1, l.h1, D, 1, 3 * D, D, M,
+                   epi(EPI_ATOMIC, grads + p.in_w, 0, D, nullptr), wgrad_splits(3 * D, D, M)));
+      MMU_TRY(colsum_accumulate(w.dbig, dt, grads + p.in_b, M, 3 * D, stream));
+      MMU_TRY(gemm(w.dbig, 3 * D, 0, W(p.in_w), D, 1, M, D, 3 * D,
+                   epi(EPI_STORE, w.dh, bf, D, nullptr)));
+      // dx0 = dx1 + LN1'(dh1); previous layer's dbproj += colsum(dx0)
+      float* dprev_bias = i > 0 ? grads + lay.layer[i - 1].proj_b : nullptr;
+      MMU_TRY(layernorm_bwd(w.dh, dt, l.x0, l.stats1, l.stats1 + M, params + p.ln1_w, w.dx, 1,
+                            bf ? w.dx_lp : nullptr, dt, grads + p.ln1_w, grads + p.ln1_b,
+                            dprev_bias, M, D, stream));
+    } else {
+      // ---- stem: ln_pre backward, CLS rows, per-modality projection wgrads
+      // dmm = LNpre'(dx), written (not accumulated) into an fp32 [M, D] buffer that is free by now
+      float* dmm = c.n_layers > 0 ? w.layer[0].x1 : w.x_out[0];
+      MMU_TRY(layernorm_bwd(w.dx, DT_F32, w.mm_x, w.stats_pre, w.stats_pre + M, params + lay.lnpre_w,
+                            dmm, 0, nullptr, DT_F32, grads + lay.lnpre_w, grads + lay.lnpre_b,
+                            nullptr, M, D, stream));
+      if (c.cls_token) MMU_TRY(cls_bwd(dmm, grads + lay.cls, c.B, s.L, D, c.E, stream));
+      MMU_TRY(split_rows(dmm, w.dimg, w.dtxt, dt, c.B, s.L, s.n_cls, s.n_img, s.n_txt, D, stream));
+      if (s.n_img > 0) {
+        const int Mi = c.B * s.n_img;
+        MMU_TRY(gemm(w.dimg, D, 1, w.img_t, c.d_img, 1, D, c.d_img, Mi,
+                     epi(EPI_ATOMIC, grads + lay.img_w, 0, c.d_img, nullptr),
+                     wgrad_splits(D, c.d_img, Mi)));
+        MMU_TRY(colsum_accumulate(w.dimg, dt, grads + lay.img_b, Mi, D, stream));
+      }
+      if (s.n_txt > 0) {
+        const int Mt = c.B * s.n_txt;
+        MMU_TRY(gemm(w.dtxt, D, 1, w.txt_t, c.d_txt, 1, D, c.d_txt, Mt,
+                     epi(EPI_ATOMIC, grads + lay.txt_w, 0, c.d_txt, nullptr),
+                     wgrad_splits(D, c.d_txt, Mt)));
+        MMU_TRY(colsum_accumulate(w.dtxt, dt, grads + lay.txt_b, Mt, D, stream));
+      }
+    }
+  }
+  return 0;
+}
+
+}  // namespace mmu

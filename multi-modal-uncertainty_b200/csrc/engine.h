@@ -1,0 +1,59 @@
+// FLAVA-fusion engine: host-side orchestration of the forward / backward pass of
+// FlavaFusionTransfomer[withCLSToken] (reference src/model.py:225-374) over caller-owned
+// flat buffers.  No allocation, no synchronisation, no exceptions: everything is enqueued on
+// the caller's stream and errors come back as negative codes.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mmu {
+
+enum Precision : int { PREC_FP32 = 0, PREC_BF16 = 1 };
+
+struct FlavaConfig {
+  int B;          // mini-batch (the attended axis!)
+  int l_img;      // max image tokens per sample
+  int l_txt;      // max text tokens per sample
+  int d_img;      // image_hidden_size
+  int d_txt;      // text_hidden_size
+  int D;          // multimodal_hidden_size
+  int n_head;     // multimodal_num_attention_heads
+  int n_layers;   // multimodal_num_hidden_layers
+  int E;          // out_dim (number of heads / ensemble members)
+  int C;          // num_classes
+  int avg_pool;   // kwargs["avg_pool"]
+  int cls_token;  // FlavaFusionTransfomerwithCLSToken
+  int precision;  // Precision
+};
+
+struct ParamEntry {
+  char name[96];  // reference state_dict key
+  long long offset;  // in elements, into the flat fp32 parameter / gradient buffers
+  long long numel;
+  int rows, cols;    // cols == 0 for vectors
+  int stage;         // backward stage that finishes this gradient (for bucketed all-reduce)
+};
+
+int flava_param_table(const FlavaConfig& c, ParamEntry* out, int max_entries);  // returns count
+long long flava_param_count(const FlavaConfig& c);  // padded flat length (elements)
+long long flava_workspace_bytes(const FlavaConfig& c, int training);
+int flava_num_stages(const FlavaConfig& c);  // backward stages: heads, layers (reversed), stem
+
+struct FlavaInputs {
+  const float* img;     // (B, l_img, d_img) fp32 or null
+  const float* txt;     // (B, l_txt, d_txt) fp32 or null
+  const int* idx_img;   // device int32[n_img] token subset, or null for identity
+  const int* idx_txt;
+  int n_img;            // tokens used (0: modality absent); <= l_img
+  int n_txt;
+  const int* keep;      // device int32[B,2] modality keep mask (zero-fill), or null
+};
+
+int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& in, void* ws,
+                  long long ws_bytes, int training, float* logits, cudaStream_t stream);
+int flava_backward(const FlavaConfig& c, const float* params, const FlavaInputs& in, void* ws,
+                   long long ws_bytes, const float* dlogits, float* grads, int stage_begin,
+                   int stage_end, cudaStream_t stream);
+
+}  // namespace mmu

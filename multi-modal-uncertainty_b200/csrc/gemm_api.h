@@ -38,4 +38,8 @@ struct GemmProblem {
 int gemm_bf16_launch(const void* A, long long lda, const void* B, long long ldb,
                      const GemmProblem& p, const GemmEpilogue& e, cudaStream_t stream);
 
+// fp32 SIMT twin (parity path): fp32 operands, fp32 out/aux (out_bf16 must be 0).
+int gemm_f32_launch(const float* A, long long lda, const float* B, long long ldb,
+                    const GemmProblem& p, const GemmEpilogue& e, cudaStream_t stream);
+
 }  // namespace mmu

@@ -1,0 +1,95 @@
+// Host-callable launchers of the row-wise / elementwise kernels (library-internal C++ API;
+// the exported C ABI lives in capi.cu and include/mmu_b200.h).  All functions enqueue on
+// `stream`, never allocate and never synchronise; they return 0 or a negative MMU_ERR_* code.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mmu {
+
+enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+
+// ---- input staging: token-subset gather + per-sample modality zero-fill + cast
+// src fp32 [B, l_src, d] -> dst (dtype) [B, n_sel, d].  idx (device int32[n_sel]) may be null
+// (identity).  keep (device int32[B, 2]) may be null; modality selects its column.
+int cast_gather(const float* src, void* dst, int dst_dtype, int B, int l_src, int d, const int* idx,
+                int n_sel, const int* keep, int modality, cudaStream_t stream);
+int cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t stream);
+
+// ---- LayerNorm (eps 1e-5, biased variance, src/model.py:174-180, :252-253)
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
+                  float* mean, float* rstd, int M, int D, cudaStream_t stream);
+// dx (fp32) = [accumulate ? dx : 0] + LN'(dy); optional low-precision copy of the final dx,
+// optional column sum of the final dx (bias gradient of the layer that produced x).
+int layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* mean,
+                  const float* rstd, const float* gamma, float* dx, int accumulate, void* dx_lp,
+                  int lp_dtype, float* dgamma, float* dbeta, float* dcolsum, int M, int D,
+                  cudaStream_t stream);
+int colsum_accumulate(const void* x, int dtype, float* out, int M, int N, cudaStream_t stream);
+
+// ---- heads: LayerNorm(ln_post) + row gather / segment mean pooling + E small Linears
+struct HeadSegments {
+  int E;
+  int seg_begin[16];
+  int seg_end[16];  // rows [begin, end) of each sample's L rows feed head e
+};
+struct HeadParams {
+  const float* w[16];  // (C, D) each
+  const float* b[16];
+  float* dw[16];
+  float* db[16];
+};
+int pool_ln_fwd(const float* x, const float* gamma, const float* beta, const HeadSegments& seg,
+                float* vec, float* mean, float* rstd, int B, int L, int D, cudaStream_t stream);
+int pool_ln_bwd(const float* dvec, const float* x, const float* mean, const float* rstd,
+                const float* gamma, const HeadSegments& seg, float* dx, float* dgamma, float* dbeta,
+                int B, int L, int D, cudaStream_t stream);
+int heads_fwd(const float* vec, const HeadParams& hp, float* logits, int B, int E, int C, int D,
+              cudaStream_t stream);
+int heads_bwd(const float* dlogits, const float* vec, const HeadParams& hp, float* dvec, int B,
+              int E, int C, int D, cudaStream_t stream);
+
+// ---- CLS rows (FlavaFusionTransfomerwithCLSToken, src/model.py:327-347)
+int cls_fill(const float* class_emb /*(D,E)*/, float* mm_x, int B, int L, int D, int E,
+             cudaStream_t stream);
+int cls_bwd(const float* dmm, float* dclass_emb, int B, int L, int D, int E, cudaStream_t stream);
+// split the (B, L, D) gradient of the concatenated sequence into per-modality compact buffers
+int split_rows(const float* dmm, void* dimg, void* dtxt, int dtype, int B, int L, int off_img,
+               int l_img, int l_txt, int D, cudaStream_t stream);
+
+// ---- batch-axis attention (src/model.py:193,205-207: MHA with batch_first=False on (B,L,D))
+// qkv (dtype) [B*L, 3D] packed q|k|v; out (dtype) [B*L, D]; lse fp32 [L*H*B].
+int attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int L, int D, int H,
+                  cudaStream_t stream);
+int attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                  float* delta_ws, void* dqkv, int dtype, int B, int L, int D, int H,
+                  cudaStream_t stream);
+
+// ---- fused softmax-CE / accuracy / uncertainty / calibration-histogram epilogue
+struct MetricAccum {  // lives in device memory; all-reduced (sum) across ranks
+  unsigned long long conf_count[15];
+  unsigned long long conf_correct[15];
+  unsigned long long hpred_count[32];
+  unsigned long long mi_count[32];
+  unsigned long long n_samples;
+  unsigned long long n_rows;          // rows that contributed to loss_sum
+  unsigned long long n_correct_rows;  // `acc` numerator (train: per head row; eval: mean logits)
+  unsigned long long n_correct_prob;  // argmax of the mean probability == label
+  double conf_sum[15];
+  double loss_sum;
+  double sum_h_pred, sum_h_exp, sum_mi;
+};
+// mode 0 (train): CE per (sample, head) row vs labels[n*label_stride + e*label_estride];
+// mode 1 (eval): CE on the head-mean logits vs labels[n*label_stride].
+int ce_uncertainty(const float* logits, const long long* labels, int label_stride,
+                   int label_estride, int N, int E, int C, int mode, float grad_scale,
+                   float* dlogits, int* pred_out, float* scores_out /*[N,4]*/, MetricAccum* acc,
+                   cudaStream_t stream);
+
+// ---- fused AdamW over the flat parameter buffer (train.py:196-202 hyper-parameters)
+int adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n, float lr,
+               float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+               cudaStream_t stream);
+
+}  // namespace mmu

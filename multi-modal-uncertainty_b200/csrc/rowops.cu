@@ -1,0 +1,690 @@
+// Row-wise HBM-bound kernels: input staging (gather/mask/cast), LayerNorm forward/backward,
+// column sums (bias gradients), ln_post + pooling + classifier heads, CLS rows.
+// One warp owns one row; every global access is a 128-bit (or 64-bit for bf16) vector,
+// reductions are warp shuffles, per-column partial sums are reduced through shared memory and
+// finished with one atomicAdd per column per block.
+#include <cuda_bf16.h>
+
+#include <cstdio>
+
+#include "common.h"
+#include "kernels.h"
+
+namespace mmu {
+
+namespace {
+
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+
+#define MMU_CHECK_LAUNCH()                                                      \
+  do {                                                                          \
+    const cudaError_t err__ = cudaGetLastError();                               \
+    if (err__ != cudaSuccess) {                                                 \
+      fprintf(stderr, "mmu: launch failed at %s:%d: %s\n", __FILE__, __LINE__, \
+              cudaGetErrorString(err__));                                       \
+      return MMU_ERR_CUDA;                                                      \
+    }                                                                           \
+  } while (0)
+
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  static __device__ __forceinline__ float4 ld(const float* p) {
+    return *reinterpret_cast<const float4*>(p);
+  }
+  static __device__ __forceinline__ void st(float* p, float4 v) {
+    *reinterpret_cast<float4*>(p) = v;
+  }
+};
+template <>
+struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) {
+    const uint2 pk = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = pk;
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+int grid_for(size_t work_items, int per_block) {
+  size_t blocks = (work_items + per_block - 1) / per_block;
+  const size_t cap = static_cast<size_t>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// ------------------------------------------------------------------ cast / gather / mask
+template <typename T>
+__global__ void cast_gather_kernel(const float* __restrict__ src, T* __restrict__ dst, int B,
+                                   int l_src, int d, const int* __restrict__ idx, int n_sel,
+                                   const int* __restrict__ keep, int modality) {
+  const int dv = d >> 2;
+  const size_t total = static_cast<size_t>(B) * n_sel * dv;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % dv);
+    const size_t row = i / dv;
+    const int j = static_cast<int>(row % n_sel);
+    const int b = static_cast<int>(row / n_sel);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (keep == nullptr || keep[b * 2 + modality] != 0) {
+      const int l = idx != nullptr ? idx[j] : j;
+      v = *reinterpret_cast<const float4*>(src + (static_cast<size_t>(b) * l_src + l) * d + 4 * c);
+    }
+    Vec4<T>::st(dst + row * d + 4 * c, v);
+  }
+}
+
+// ----------------------------------------------------------------------- LayerNorm
+// Row held in registers: NV float4 per lane (D <= 128*NV).
+template <int NV>
+struct RowRegs {
+  float4 v[NV];
+  template <typename T>
+  __device__ __forceinline__ void load(const T* row, int nvec, int lane) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < nvec ? Vec4<T>::ld(row + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __device__ __forceinline__ float sum() const {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    return s;
+  }
+};
+
+template <int NV>
+__device__ __forceinline__ void row_stats(const RowRegs<NV>& r, int nvec, int lane, int D,
+                                          float& mean, float& rstd) {
+  mean = warp_sum(r.sum()) / D;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + 32 * i < nvec) {
+      const float a = r.v[i].x - mean, b = r.v[i].y - mean, c = r.v[i].z - mean,
+                  d = r.v[i].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  rstd = rsqrtf(warp_sum(ss) / D + 1e-5f);
+}
+
+template <int NV, typename TO>
+__global__ void __launch_bounds__(THREADS)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, TO* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int M, int D) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D >> 2;
+  for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
+    RowRegs<NV> r;
+    r.load(x + static_cast<size_t>(row) * D, nvec, lane);
+    float mean, rstd;
+    row_stats<NV>(r, nvec, lane, D, mean, rstd);
+    if (lane == 0 && mean_out != nullptr) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c);
+        const float4 b = *reinterpret_cast<const float4*>(beta + 4 * c);
+        float4 o;
+        o.x = (r.v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (r.v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (r.v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (r.v[i].w - mean) * rstd * g.w + b.w;
+        Vec4<TO>::st(y + static_cast<size_t>(row) * D + 4 * c, o);
+      }
+    }
+  }
+}
+
+// Reduce per-warp column partials (acc[NV] float4 per lane) across the block's warps and
+// atomically add into out[D].  `red` is WARPS*D floats of shared memory.
+template <int NV>
+__device__ __forceinline__ void block_colreduce(const float4 (&acc)[NV], float* red, float* out,
+                                                int nvec, int D) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) *reinterpret_cast<float4*>(red + warp * D + 4 * c) = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) s += red[w * D + c];
+    atomicAdd(out + c, s);
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void zero_acc(float4 (&a)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <int NV, typename TDY, typename TLP>
+__global__ void __launch_bounds__(THREADS)
+layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ gamma, float* __restrict__ dx, int accumulate,
+                     TLP* __restrict__ dx_lp, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float* __restrict__ dcolsum, int M, int D) {
+  extern __shared__ float red[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D >> 2;
+  float4 acc_g[NV], acc_b[NV], acc_c[NV];
+  zero_acc<NV>(acc_g);
+  zero_acc<NV>(acc_b);
+  zero_acc<NV>(acc_c);
+  float4 g[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    g[i] = c < nvec ? *reinterpret_cast<const float4*>(gamma + 4 * c) : make_float4(0, 0, 0, 0);
+  }
+  for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
+    RowRegs<NV> rx, rdy;
+    rx.load(x + static_cast<size_t>(row) * D, nvec, lane);
+    rdy.load(dy + static_cast<size_t>(row) * D, nvec, lane);
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+        float4& xv = rx.v[i];
+        xv.x = (xv.x - mu) * rs; xv.y = (xv.y - mu) * rs;
+        xv.z = (xv.z - mu) * rs; xv.w = (xv.w - mu) * rs;  // xhat
+        const float4 d = rdy.v[i];
+        acc_g[i].x += d.x * xv.x; acc_g[i].y += d.y * xv.y;
+        acc_g[i].z += d.z * xv.z; acc_g[i].w += d.w * xv.w;
+        acc_b[i].x += d.x; acc_b[i].y += d.y; acc_b[i].z += d.z; acc_b[i].w += d.w;
+        const float a = d.x * g[i].x, b = d.y * g[i].y, c = d.z * g[i].z, e = d.w * g[i].w;
+        s1 += (a + b) + (c + e);
+        s2 += (a * xv.x + b * xv.y) + (c * xv.z + e * xv.w);
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 d = rdy.v[i], xv = rx.v[i];
+        float4 o;
+        o.x = rs * (d.x * g[i].x - s1 - xv.x * s2);
+        o.y = rs * (d.y * g[i].y - s1 - xv.y * s2);
+        o.z = rs * (d.z * g[i].z - s1 - xv.z * s2);
+        o.w = rs * (d.w * g[i].w - s1 - xv.w * s2);
+        float* dst = dx + static_cast<size_t>(row) * D + 4 * c;
+        if (accumulate) {
+          const float4 prev = *reinterpret_cast<const float4*>(dst);
+          o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+        }
+        *reinterpret_cast<float4*>(dst) = o;
+        if (dx_lp != nullptr) Vec4<TLP>::st(dx_lp + static_cast<size_t>(row) * D + 4 * c, o);
+        acc_c[i].x += o.x; acc_c[i].y += o.y; acc_c[i].z += o.z; acc_c[i].w += o.w;
+      }
+    }
+  }
+  block_colreduce<NV>(acc_g, red, dgamma, nvec, D);
+  block_colreduce<NV>(acc_b, red, dbeta, nvec, D);
+  if (dcolsum != nullptr) block_colreduce<NV>(acc_c, red, dcolsum, nvec, D);
+}
+
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int M, int N,
+                              int rows_per_block) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= N) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0; r < r1; ++r) {
+    const float4 v = Vec4<T>::ld(x + static_cast<size_t>(r) * N + c);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  atomicAdd(out + c, s.x);
+  atomicAdd(out + c + 1, s.y);
+  atomicAdd(out + c + 2, s.z);
+  atomicAdd(out + c + 3, s.w);
+}
+
+// ------------------------------------------------- ln_post + pooling + heads (small)
+template <int NV>
+__global__ void __launch_bounds__(THREADS)
+pool_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, HeadSegments seg, float* __restrict__ vec,
+                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int L, int D) {
+  extern __shared__ float red[];
+  const int b = blockIdx.x, e = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D >> 2;
+  const int s0 = seg.seg_begin[e], s1 = seg.seg_end[e];
+  float4 acc[NV];
+  zero_acc<NV>(acc);
+  for (int l = s0 + warp; l < s1; l += WARPS) {
+    const size_t row = static_cast<size_t>(b) * L + l;
+    RowRegs<NV> r;
+    r.load(x + row * D, nvec, lane);
+    float mean, rstd;
+    row_stats<NV>(r, nvec, lane, D, mean, rstd);
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c);
+        const float4 bb = *reinterpret_cast<const float4*>(beta + 4 * c);
+        acc[i].x += (r.v[i].x - mean) * rstd * g.x + bb.x;
+        acc[i].y += (r.v[i].y - mean) * rstd * g.y + bb.y;
+        acc[i].z += (r.v[i].z - mean) * rstd * g.z + bb.z;
+        acc[i].w += (r.v[i].w - mean) * rstd * g.w + bb.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) *reinterpret_cast<float4*>(red + warp * D + 4 * c) = acc[i];
+  }
+  __syncthreads();
+  const float inv = 1.0f / static_cast<float>(max(1, s1 - s0));
+  float* out = vec + (static_cast<size_t>(b) * seg.E + e) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) s += red[w * D + c];
+    out[c] = s * inv;
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(THREADS)
+pool_ln_bwd_kernel(const float* __restrict__ dvec, const float* __restrict__ x,
+                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                   const float* __restrict__ gamma, HeadSegments seg, float* __restrict__ dx,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, int L, int D) {
+  extern __shared__ float red[];
+  const int b = blockIdx.x, e = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D >> 2;
+  const int s0 = seg.seg_begin[e], s1 = seg.seg_end[e];
+  const float inv = 1.0f / static_cast<float>(max(1, s1 - s0));
+  float4 acc_g[NV], acc_b[NV], g[NV], dy[NV];
+  zero_acc<NV>(acc_g);
+  zero_acc<NV>(acc_b);
+  const float* dv = dvec + (static_cast<size_t>(b) * seg.E + e) * D;
+  float s1sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      g[i] = *reinterpret_cast<const float4*>(gamma + 4 * c);
+      float4 d = *reinterpret_cast<const float4*>(dv + 4 * c);
+      d.x *= inv; d.y *= inv; d.z *= inv; d.w *= inv;
+      dy[i] = d;
+      s1sum += (d.x * g[i].x + d.y * g[i].y) + (d.z * g[i].z + d.w * g[i].w);
+    } else {
+      g[i] = make_float4(0, 0, 0, 0);
+      dy[i] = make_float4(0, 0, 0, 0);
+    }
+  }
+  s1sum = warp_sum(s1sum) / D;
+  for (int l = s0 + warp; l < s1; l += WARPS) {
+    const size_t row = static_cast<size_t>(b) * L + l;
+    RowRegs<NV> rx;
+    rx.load(x + row * D, nvec, lane);
+    const float mu = mean[row], rs = rstd[row];
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+        float4& xv = rx.v[i];
+        xv.x = (xv.x - mu) * rs; xv.y = (xv.y - mu) * rs;
+        xv.z = (xv.z - mu) * rs; xv.w = (xv.w - mu) * rs;
+        const float4 d = dy[i];
+        acc_g[i].x += d.x * xv.x; acc_g[i].y += d.y * xv.y;
+        acc_g[i].z += d.z * xv.z; acc_g[i].w += d.w * xv.w;
+        acc_b[i].x += d.x; acc_b[i].y += d.y; acc_b[i].z += d.z; acc_b[i].w += d.w;
+        s2 += (d.x * g[i].x * xv.x + d.y * g[i].y * xv.y) +
+              (d.z * g[i].z * xv.z + d.w * g[i].w * xv.w);
+      }
+    }
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 d = dy[i], xv = rx.v[i];
+        float4 o;
+        o.x = rs * (d.x * g[i].x - s1sum - xv.x * s2);
+        o.y = rs * (d.y * g[i].y - s1sum - xv.y * s2);
+        o.z = rs * (d.z * g[i].z - s1sum - xv.z * s2);
+        o.w = rs * (d.w * g[i].w - s1sum - xv.w * s2);
+        *reinterpret_cast<float4*>(dx + row * D + 4 * c) = o;
+      }
+    }
+  }
+  block_colreduce<NV>(acc_g, red, dgamma, nvec, D);
+  block_colreduce<NV>(acc_b, red, dbeta, nvec, D);
+}
+
+__global__ void heads_fwd_kernel(const float* __restrict__ vec, HeadParams hp,
+                                 float* __restrict__ logits, int E, int C, int D) {
+  extern __shared__ float sv[];
+  const int b = blockIdx.x, e = blockIdx.y;
+  const float* v = vec + (static_cast<size_t>(b) * E + e) * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) sv[i] = v[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* W = hp.w[e];
+  for (int c = warp; c < C; c += nw) {
+    float s = 0.f;
+    for (int i = lane * 4; i < D; i += 128) {
+      const float4 w = *reinterpret_cast<const float4*>(W + static_cast<size_t>(c) * D + i);
+      s += (w.x * sv[i] + w.y * sv[i + 1]) + (w.z * sv[i + 2] + w.w * sv[i + 3]);
+    }
+    s = warp_sum(s);
+    if (lane == 0) logits[(static_cast<size_t>(b) * E + e) * C + c] = s + hp.b[e][c];
+  }
+}
+
+__global__ void heads_bwd_dvec_kernel(const float* __restrict__ dlogits, HeadParams hp,
+                                      float* __restrict__ dvec, int E, int C, int D) {
+  extern __shared__ float sdl[];
+  const int b = blockIdx.x, e = blockIdx.y;
+  const float* dl = dlogits + (static_cast<size_t>(b) * E + e) * C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sdl[i] = dl[i];
+  __syncthreads();
+  const float* W = hp.w[e];
+  for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < C; ++c) {
+      const float4 w = *reinterpret_cast<const float4*>(W + static_cast<size_t>(c) * D + d);
+      const float g = sdl[c];
+      s.x += g * w.x; s.y += g * w.y; s.z += g * w.z; s.w += g * w.w;
+    }
+    *reinterpret_cast<float4*>(dvec + (static_cast<size_t>(b) * E + e) * D + d) = s;
+  }
+}
+
+__global__ void heads_bwd_dw_kernel(const float* __restrict__ dlogits, const float* __restrict__ vec,
+                                    HeadParams hp, int B, int E, int C, int D) {
+  const int c = blockIdx.x, e = blockIdx.y;
+  float bsum = 0.f;
+  for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < B; ++b) {
+      const float g = dlogits[(static_cast<size_t>(b) * E + e) * C + c];
+      const float4 v = *reinterpret_cast<const float4*>(vec + (static_cast<size_t>(b) * E + e) * D + d);
+      s.x += g * v.x; s.y += g * v.y; s.z += g * v.z; s.w += g * v.w;
+    }
+    float* dw = hp.dw[e] + static_cast<size_t>(c) * D + d;
+    float4 prev = *reinterpret_cast<float4*>(dw);
+    prev.x += s.x; prev.y += s.y; prev.z += s.z; prev.w += s.w;
+    *reinterpret_cast<float4*>(dw) = prev;
+  }
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < B; ++b) bsum += dlogits[(static_cast<size_t>(b) * E + e) * C + c];
+    hp.db[e][c] += bsum;
+  }
+}
+
+__global__ void cls_fill_kernel(const float* __restrict__ emb, float* __restrict__ mm_x, int B, int L,
+                                int D, int E) {
+  const size_t total = static_cast<size_t>(B) * E * D;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int d = static_cast<int>(i % D);
+    const int e = static_cast<int>((i / D) % E);
+    const int b = static_cast<int>(i / (static_cast<size_t>(D) * E));
+    mm_x[(static_cast<size_t>(b) * L + e) * D + d] = emb[static_cast<size_t>(d) * E + e];
+  }
+}
+
+__global__ void cls_bwd_kernel(const float* __restrict__ dmm, float* __restrict__ demb, int B, int L,
+                               int D, int E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D * E) return;
+  const int d = i % D, e = i / D;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += dmm[(static_cast<size_t>(b) * L + e) * D + d];
+  demb[static_cast<size_t>(d) * E + e] += s;
+}
+
+template <typename T>
+__global__ void split_rows_kernel(const float* __restrict__ dmm, T* __restrict__ dimg,
+                                  T* __restrict__ dtxt, int B, int L, int off_img, int l_img,
+                                  int l_txt, int D) {
+  const int dv = D >> 2;
+  const int ltot = l_img + l_txt;
+  const size_t total = static_cast<size_t>(B) * ltot * dv;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % dv);
+    const size_t r = i / dv;
+    const int l = static_cast<int>(r % ltot);
+    const int b = static_cast<int>(r / ltot);
+    const float4 v =
+        *reinterpret_cast<const float4*>(dmm + (static_cast<size_t>(b) * L + off_img + l) * D + 4 * c);
+    if (l < l_img) Vec4<T>::st(dimg + (static_cast<size_t>(b) * l_img + l) * D + 4 * c, v);
+    else Vec4<T>::st(dtxt + (static_cast<size_t>(b) * l_txt + (l - l_img)) * D + 4 * c, v);
+  }
+}
+
+int nv_for(int D) {
+  if (D % 4 != 0 || D <= 0 || D > 1024) return -1;
+  const int need = (D / 4 + 31) / 32;
+  if (need <= 1) return 1;
+  if (need <= 2) return 2;
+  if (need <= 4) return 4;
+  if (need <= 6) return 6;
+  return 8;
+}
+
+}  // namespace
+
+// ======================================================================= launchers
+int cast_gather(const float* src, void* dst, int dst_dtype, int B, int l_src, int d, const int* idx,
+                int n_sel, const int* keep, int modality, cudaStream_t stream) {
+  if (d % 4 != 0) return MMU_ERR_SHAPE;
+  if (B <= 0 || n_sel <= 0) return 0;
+  const size_t total = static_cast<size_t>(B) * n_sel * (d / 4);
+  const int grid = grid_for(total, 256);
+  if (dst_dtype == DT_BF16)
+    cast_gather_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        src, static_cast<__nv_bfloat16*>(dst), B, l_src, d, idx, n_sel, keep, modality);
+  else
+    cast_gather_kernel<float><<<grid, 256, 0, stream>>>(src, static_cast<float*>(dst), B, l_src, d,
+                                                        idx, n_sel, keep, modality);
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t stream) {
+  if (n % 4 != 0) return MMU_ERR_SHAPE;
+  return cast_gather(src, dst, DT_BF16, 1, static_cast<int>(n / 4), 4, nullptr,
+                     static_cast<int>(n / 4), nullptr, 0, stream);
+}
+
+#define MMU_NV_DISPATCH(nv, CALL) \
+  switch (nv) {                   \
+    case 1: { constexpr int NV = 1; CALL; } break; \
+    case 2: { constexpr int NV = 2; CALL; } break; \
+    case 4: { constexpr int NV = 4; CALL; } break; \
+    case 6: { constexpr int NV = 6; CALL; } break; \
+    case 8: { constexpr int NV = 8; CALL; } break; \
+    default: return MMU_ERR_SHAPE;                   \
+  }
+
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
+                  float* mean, float* rstd, int M, int D, cudaStream_t stream) {
+  const int nv = nv_for(D);
+  if (nv < 0) return MMU_ERR_SHAPE;
+  if (M <= 0) return 0;
+  const int grid = grid_for(M, WARPS);
+  if (y_dtype == DT_BF16) {
+    MMU_NV_DISPATCH(nv, (layernorm_fwd_kernel<NV, __nv_bfloat16><<<grid, THREADS, 0, stream>>>(
+                            x, gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, M, D)));
+  } else {
+    MMU_NV_DISPATCH(nv, (layernorm_fwd_kernel<NV, float><<<grid, THREADS, 0, stream>>>(
+                            x, gamma, beta, static_cast<float*>(y), mean, rstd, M, D)));
+  }
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* mean,
+                  const float* rstd, const float* gamma, float* dx, int accumulate, void* dx_lp,
+                  int lp_dtype, float* dgamma, float* dbeta, float* dcolsum, int M, int D,
+                  cudaStream_t stream) {
+  const int nv = nv_for(D);
+  if (nv < 0) return MMU_ERR_SHAPE;
+  if (M <= 0) return 0;
+  int grid = grid_for(M, WARPS * 4);
+  if (grid > sm_count() * 2) grid = sm_count() * 2;
+  const size_t smem = static_cast<size_t>(WARPS) * D * sizeof(float);
+  using bf = __nv_bfloat16;
+  if (dy_dtype == DT_BF16 && (dx_lp == nullptr || lp_dtype == DT_BF16)) {
+    MMU_NV_DISPATCH(nv, (layernorm_bwd_kernel<NV, bf, bf><<<grid, THREADS, smem, stream>>>(
+                            static_cast<const bf*>(dy), x, mean, rstd, gamma, dx, accumulate,
+                            static_cast<bf*>(dx_lp), dgamma, dbeta, dcolsum, M, D)));
+  } else if (dy_dtype == DT_F32 && (dx_lp == nullptr || lp_dtype == DT_F32)) {
+    // fp32 path: the "low precision" copy would be identical to dx itself
+    MMU_NV_DISPATCH(nv, (layernorm_bwd_kernel<NV, float, float><<<grid, THREADS, smem, stream>>>(
+                            static_cast<const float*>(dy), x, mean, rstd, gamma, dx, accumulate,
+                            static_cast<float*>(dx_lp), dgamma, dbeta, dcolsum, M, D)));
+  } else if (dy_dtype == DT_F32 && lp_dtype == DT_BF16) {
+    MMU_NV_DISPATCH(nv, (layernorm_bwd_kernel<NV, float, bf><<<grid, THREADS, smem, stream>>>(
+                            static_cast<const float*>(dy), x, mean, rstd, gamma, dx, accumulate,
+                            static_cast<bf*>(dx_lp), dgamma, dbeta, dcolsum, M, D)));
+  } else {
+    return MMU_ERR_ARG;
+  }
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int colsum_accumulate(const void* x, int dtype, float* out, int M, int N, cudaStream_t stream) {
+  if (N % 4 != 0) return MMU_ERR_SHAPE;
+  if (M <= 0) return 0;
+  const int threads = 128;
+  const int gx = (N / 4 + threads - 1) / threads;
+  int gy = (sm_count() * 4 + gx - 1) / gx;
+  if (gy > M) gy = M;
+  const int rpb = (M + gy - 1) / gy;
+  gy = (M + rpb - 1) / rpb;
+  dim3 grid(gx, gy);
+  if (dtype == DT_BF16)
+    colsum_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), out, M, N, rpb);
+  else
+    colsum_kernel<float><<<grid, threads, 0, stream>>>(static_cast<const float*>(x), out, M, N, rpb);
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int pool_ln_fwd(const float* x, const float* gamma, const float* beta, const HeadSegments& seg,
+                float* vec, float* mean, float* rstd, int B, int L, int D, cudaStream_t stream) {
+  const int nv = nv_for(D);
+  if (nv < 0 || seg.E < 1 || seg.E > 16) return MMU_ERR_SHAPE;
+  const size_t smem = static_cast<size_t>(WARPS) * D * sizeof(float);
+  dim3 grid(B, seg.E);
+  MMU_NV_DISPATCH(nv, (pool_ln_fwd_kernel<NV><<<grid, THREADS, smem, stream>>>(
+                          x, gamma, beta, seg, vec, mean, rstd, L, D)));
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int pool_ln_bwd(const float* dvec, const float* x, const float* mean, const float* rstd,
+                const float* gamma, const HeadSegments& seg, float* dx, float* dgamma, float* dbeta,
+                int B, int L, int D, cudaStream_t stream) {
+  const int nv = nv_for(D);
+  if (nv < 0 || seg.E < 1 || seg.E > 16) return MMU_ERR_SHAPE;
+  const size_t smem = static_cast<size_t>(WARPS) * D * sizeof(float);
+  dim3 grid(B, seg.E);
+  MMU_NV_DISPATCH(nv, (pool_ln_bwd_kernel<NV><<<grid, THREADS, smem, stream>>>(
+                          dvec, x, mean, rstd, gamma, seg, dx, dgamma, dbeta, L, D)));
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int heads_fwd(const float* vec, const HeadParams& hp, float* logits, int B, int E, int C, int D,
+              cudaStream_t stream) {
+  if (D % 4 != 0 || E > 16) return MMU_ERR_SHAPE;
+  heads_fwd_kernel<<<dim3(B, E), 128, D * sizeof(float), stream>>>(vec, hp, logits, E, C, D);
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int heads_bwd(const float* dlogits, const float* vec, const HeadParams& hp, float* dvec, int B,
+              int E, int C, int D, cudaStream_t stream) {
+  if (D % 4 != 0 || E > 16) return MMU_ERR_SHAPE;
+  heads_bwd_dvec_kernel<<<dim3(B, E), 128, C * sizeof(float), stream>>>(dlogits, hp, dvec, E, C, D);
+  MMU_CHECK_LAUNCH();
+  heads_bwd_dw_kernel<<<dim3(C, E), 128, 0, stream>>>(dlogits, vec, hp, B, E, C, D);
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int cls_fill(const float* class_emb, float* mm_x, int B, int L, int D, int E, cudaStream_t stream) {
+  cls_fill_kernel<<<grid_for(static_cast<size_t>(B) * E * D, 256), 256, 0, stream>>>(class_emb, mm_x,
+                                                                                  B, L, D, E);
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int cls_bwd(const float* dmm, float* dclass_emb, int B, int L, int D, int E, cudaStream_t stream) {
+  cls_bwd_kernel<<<(D * E + 127) / 128, 128, 0, stream>>>(dmm, dclass_emb, B, L, D, E);
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int split_rows(const float* dmm, void* dimg, void* dtxt, int dtype, int B, int L, int off_img,
+               int l_img, int l_txt, int D, cudaStream_t stream) {
+  if (D % 4 != 0) return MMU_ERR_SHAPE;
+  if (l_img + l_txt <= 0) return 0;
+  const size_t total = static_cast<size_t>(B) * (l_img + l_txt) * (D / 4);
+  const int grid = grid_for(total, 256);
+  if (dtype == DT_BF16)
+    split_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        dmm, static_cast<__nv_bfloat16*>(dimg), static_cast<__nv_bfloat16*>(dtxt), B, L, off_img,
+        l_img, l_txt, D);
+  else
+    split_rows_kernel<float><<<grid, 256, 0, stream>>>(dmm, static_cast<float*>(dimg),
+                                                       static_cast<float*>(dtxt), B, L, off_img,
+                                                       l_img, l_txt, D);
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace mmu

@@ -1,0 +1,168 @@
+"""Operator-level Python wrappers over the C ABI (one function per exported kernel family).
+
+These are what the parity tests drive; the model classes in ``src/`` use the engine entry points
+instead.  Every function takes CUDA tensors, enqueues on torch's current stream and raises
+``MMUError`` on failure.  Nothing here computes anything in PyTorch.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, check, lib, ptr, stream_ptr
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise ValueError("mmu ops need contiguous CUDA tensors")
+
+
+def gemm(A, B, *, a_mn_major=False, b_mn_major=False, mode=_lib.EPI_STORE, out=None, out2=None,
+         bias=None, aux=None, alpha=1.0, splits=1, seg=None, out_dtype=None):
+    """C[M,N] = epilogue(sum_k A(m,k) B(n,k)); see ``mmu_gemm`` in include/mmu_b200.h."""
+    _cuda(A, B, out, out2, bias, aux)
+    dt = _dt(A)
+    if a_mn_major:
+        K, M = A.shape
+    else:
+        M, K = A.shape
+    N = B.shape[1] if b_mn_major else B.shape[0]
+    if out is None and mode != _lib.EPI_QUICKGELU:
+        odt = out_dtype or (A.dtype if mode in (_lib.EPI_STORE, _lib.EPI_DGELU) else torch.float32)
+        out = torch.empty(M, N, device=A.device, dtype=odt)
+    ref = out if out is not None else out2
+    e = _lib.GemmEpilogue()
+    e.mode = mode
+    e.out_lp = 1 if ref.dtype == torch.bfloat16 else 0
+    e.out, e.out2, e.bias, e.aux = ptr(out), ptr(out2), ptr(bias), ptr(aux)
+    e.ld_out = out.stride(0) if out is not None else 0
+    e.ld_out2 = out2.stride(0) if out2 is not None else 0
+    e.ld_aux = aux.stride(0) if aux is not None else 0
+    e.seg_len, e.seg_stride, e.seg_off = seg if seg is not None else (0, 0, 0)
+    e.alpha = alpha
+    check(lib.mmu_gemm(dt, ptr(A), A.stride(0), int(a_mn_major), ptr(B), B.stride(0),
+                       int(b_mn_major), M, N, K, splits, C.byref(e), stream_ptr()), "mmu_gemm")
+    return out if out is not None else out2
+
+
+def mask_gather_tokens(src, idx=None, keep=None, modality=0, dtype=torch.float32):
+    _cuda(src, idx, keep)
+    Bn, l_src, d = src.shape
+    n_sel = l_src if idx is None else idx.numel()
+    out = torch.empty(Bn, n_sel, d, device=src.device, dtype=dtype)
+    check(lib.mmu_mask_gather_tokens(ptr(src), ptr(out), BF16 if dtype == torch.bfloat16 else F32,
+                                     Bn, l_src, d, ptr(idx), n_sel, ptr(keep), modality,
+                                     stream_ptr()), "mmu_mask_gather_tokens")
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, out_dtype=torch.float32):
+    _cuda(x, gamma, beta)
+    M, D = x.shape
+    y = torch.empty(M, D, device=x.device, dtype=out_dtype)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    check(lib.mmu_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), _dt(y), ptr(mean), ptr(rstd),
+                                M, D, stream_ptr()), "mmu_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx=None, want_lp=False, want_colsum=False):
+    _cuda(dy, x, mean, rstd, gamma, dx)
+    M, D = x.shape
+    accumulate = dx is not None
+    if dx is None:
+        dx = torch.empty(M, D, device=x.device, dtype=torch.float32)
+    dgamma = torch.zeros(D, device=x.device, dtype=torch.float32)
+    dbeta = torch.zeros(D, device=x.device, dtype=torch.float32)
+    colsum = torch.zeros(D, device=x.device, dtype=torch.float32) if want_colsum else None
+    dx_lp = torch.empty(M, D, device=x.device, dtype=torch.bfloat16) if want_lp else None
+    check(lib.mmu_layernorm_bwd(ptr(dy), _dt(dy), ptr(x), ptr(mean), ptr(rstd), ptr(gamma), ptr(dx),
+                                int(accumulate), ptr(dx_lp), BF16, ptr(dgamma), ptr(dbeta),
+                                ptr(colsum), M, D, stream_ptr()), "mmu_layernorm_bwd")
+    return dx, dgamma, dbeta, dx_lp, colsum
+
+
+def attention_fwd(qkv, B, L, D, H):
+    _cuda(qkv)
+    out = torch.empty(B * L, D, device=qkv.device, dtype=qkv.dtype)
+    lse = torch.empty(L * H * B, device=qkv.device, dtype=torch.float32)
+    check(lib.mmu_batchaxis_attention_fwd(ptr(qkv), ptr(out), ptr(lse), _dt(qkv), B, L, D, H,
+                                          stream_ptr()), "mmu_batchaxis_attention_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, B, L, D, H):
+    _cuda(qkv, out, dout, lse)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(L * H * B, device=qkv.device, dtype=torch.float32)
+    check(lib.mmu_batchaxis_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta),
+                                          ptr(dqkv), _dt(qkv), B, L, D, H, stream_ptr()),
+          "mmu_batchaxis_attention_bwd")
+    return dqkv
+
+
+def new_accum(device):
+    """Zeroed device ``mmu_metric_accum`` as an int64 tensor of ACC_WORDS 8-byte words."""
+    return torch.zeros(_lib.ACC_WORDS, device=device, dtype=torch.int64)
+
+
+def accum_to_dict(accum):
+    """Host copy of an accumulator (ONE device->host transfer) as named numpy arrays."""
+    import numpy as np
+    raw = accum.detach().cpu().numpy()
+    ints, dbl = raw.view(np.uint64), raw.view(np.float64)
+    o = _lib.ACC_OFF
+    return {
+        "conf_count": ints[o["conf_count"]:o["conf_count"] + 15].astype(np.int64),
+        "conf_correct": ints[o["conf_correct"]:o["conf_correct"] + 15].astype(np.int64),
+        "hpred_count": ints[o["hpred_count"]:o["hpred_count"] + 32].astype(np.int64),
+        "mi_count": ints[o["mi_count"]:o["mi_count"] + 32].astype(np.int64),
+        "n_samples": int(ints[o["n_samples"]]), "n_rows": int(ints[o["n_rows"]]),
+        "n_correct_rows": int(ints[o["n_correct_rows"]]),
+        "n_correct_prob": int(ints[o["n_correct_prob"]]),
+        "conf_sum": dbl[o["conf_sum"]:o["conf_sum"] + 15].copy(),
+        "loss_sum": float(dbl[o["loss_sum"]]), "sum_h_pred": float(dbl[o["sum_h_pred"]]),
+        "sum_h_exp": float(dbl[o["sum_h_exp"]]), "sum_mi": float(dbl[o["sum_mi"]]),
+    }
+
+
+def heads_uncertainty_epilogue(logits, labels, mode, *, grad_scale=0.0, want_grad=False,
+                               want_pred=False, want_scores=False, accum=None):
+    """Fused CE / accuracy / uncertainty / histogram epilogue over logits (N, E, C).
+    ``labels``: int64 (N,) or (N, E).  Returns (dlogits, pred[N,2], scores[N,4], accum)."""
+    _cuda(logits, labels)
+    N, E, Cn = logits.shape
+    if labels.dtype != torch.int64:
+        raise TypeError("labels must be int64")
+    if labels.dim() == 1 or labels.shape[1] == 1:
+        ls, les = 1, 0
+    else:
+        ls, les = labels.stride(0), labels.stride(1)
+    dl = torch.empty_like(logits) if want_grad else None
+    pred = torch.empty(N, 2, device=logits.device, dtype=torch.int32) if want_pred else None
+    scores = torch.empty(N, 4, device=logits.device, dtype=torch.float32) if want_scores else None
+    if accum is None:
+        accum = new_accum(logits.device)
+    check(lib.mmu_heads_uncertainty_epilogue(ptr(logits), ptr(labels), ls, les, N, E, Cn, mode,
+                                             grad_scale, ptr(dl), ptr(pred), ptr(scores),
+                                             ptr(accum), stream_ptr()),
+          "mmu_heads_uncertainty_epilogue")
+    return dl, pred, scores, accum
+
+
+def adamw_flat_step(p, g, m, v, step, lr, *, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-3,
+                    grad_scale=1.0, p_bf16=None):
+    _cuda(p, g, m, v, p_bf16)
+    check(lib.mmu_adamw_flat_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), p.numel(), lr,
+                                  betas[0], betas[1], eps, weight_decay, step, grad_scale,
+                                  stream_ptr()), "mmu_adamw_flat_step")

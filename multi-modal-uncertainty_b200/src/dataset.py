@@ -1,0 +1,103 @@
+"""Batch shaping for the hot path (reference ``src/dataset.py:30-101, 216-226``) and synthetic
+stand-ins for the real-data loaders (which are out of scope: SURVEY.md section 2, row 6).
+
+The shuffles use the HOST generator exactly like the reference (``torch.randperm`` on the CPU
+default generator, same calls in the same order) so permutations and tiled labels are
+bit-exact; only the resulting index tensors travel to the GPU.
+"""
+import torch
+from torch.utils.data import Dataset
+
+
+def data_forming_func_transformer(x, y, phase, model_type):
+    """Reference src/dataset.py:30-54.  Vanilla: labels (B,) -> (B, 1); MultiHead: -> (B, 2);
+    MIMO-shuffle-instance: image and text streams permuted independently (image perm drawn
+    first), labels stacked per stream.  Eval phases pass through unchanged."""
+    img, txt = x
+    if phase == "train":
+        if model_type == "Vanilla":
+            y = y.unsqueeze(1).repeat(1, 1)
+        elif model_type == "MultiHead":
+            y = y.unsqueeze(1).repeat(1, 2)
+        elif model_type == "MIMO-shuffle-instance":
+            n = img.size(0)
+            p_img = torch.randperm(n)
+            p_txt = torch.randperm(n)
+            # NB: the reference indexes `txt`/`y` with the second permutation after `img` has
+            # already been permuted; the label pairing below is identical.
+            img, txt = img[p_img], txt[p_txt]
+            y = torch.stack([y[p_img], y[p_txt]], dim=1)
+    return (img, txt), y
+
+
+def data_forming_func(x, y, phase, model_type):
+    """Reference src/dataset.py:56-101: four-view FashionMNIST variants."""
+    b, m, c, h, w = x.shape
+    train = phase == "train"
+    if model_type == "single-model-weight-sharing":
+        return x.reshape(-1, c, h, w), y.unsqueeze(1).repeat(1, m).reshape(-1)
+    if not train:
+        return x, y
+    if model_type == "Vanilla":
+        return x, y.unsqueeze(1).repeat(1, 1)
+    if model_type == "MultiHead":
+        return x, y.unsqueeze(1).repeat(1, m)
+    if model_type == "MIMO-shuffle-view":
+        return x[:, torch.randperm(m)], y.unsqueeze(1).repeat(1, m)
+    if model_type in ("MIMO-shuffle-instance", "MIMO-shuffle-all"):
+        views = 4 if model_type == "MIMO-shuffle-instance" else m
+        perms = [torch.randperm(b) for _ in range(views)]
+        x = torch.stack([x[p, i] for i, p in enumerate(perms)], dim=1)
+        y = torch.stack([y[p] for p in perms], dim=1)
+        if model_type == "MIMO-shuffle-all":
+            vp = torch.randperm(x.size(1))
+            x, y = x[:, vp], y[:, vp]
+    return x, y
+
+
+def collate_fn_flava(batch):
+    """Reference src/dataset.py:216-226: zero-pad ragged (l_i, 768) embeddings to the batch max."""
+    def pad(seqs):
+        out = seqs[0].new_zeros(len(seqs), max(s.shape[0] for s in seqs), seqs[0].shape[1])
+        for i, s in enumerate(seqs):
+            out[i, : s.shape[0]] = s
+        return out
+    imgs = pad([b[0] for b in batch])
+    txts = pad([b[1] for b in batch])
+    labels = torch.tensor([int(b[2]) for b in batch])
+    return (imgs, txts), labels
+
+
+class SyntheticFlavaDataset(Dataset):
+    """Synthetic stand-in for ``FlavaEncodedDataset`` (reference src/dataset.py:196-213): the same
+    item protocol (image_embeddings (l_img, d), text_embeddings (l_txt_i, d), LongTensor([label]))
+    with seeded N(0, 1) features and optionally ragged text lengths."""
+
+    def __init__(self, n, l_img=197, l_txt=40, dim=768, num_classes=101, seed=42, ragged=False):
+        self.n, self.l_img, self.l_txt, self.dim, self.C = n, l_img, l_txt, dim, num_classes
+        self.seed, self.ragged = seed, ragged
+        self.num_classes = num_classes
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, idx):
+        g = torch.Generator().manual_seed(self.seed * 1000003 + idx)
+        l_txt = self.l_txt
+        if self.ragged:
+            l_txt = int(torch.randint(max(1, self.l_txt // 2), self.l_txt + 1, (1,), generator=g))
+        img = torch.randn(self.l_img, self.dim, generator=g)
+        txt = torch.randn(l_txt, self.dim, generator=g)
+        label = torch.randint(0, self.C, (1,), generator=g)
+        return img, txt, label
+
+
+def get_synthetic_flava(batch_size, n_train, n_val, n_test, seed=42, shuffle=True, **kw):
+    """Loaders shaped like reference ``get_dataset`` (src/dataset.py:287-321): DataLoader with
+    ``collate_fn_flava``, workers 0, generator seeded with ``seed``."""
+    from torch.utils.data import DataLoader
+    g = torch.Generator().manual_seed(seed)
+    mk = lambda n, s, sh: DataLoader(SyntheticFlavaDataset(n, seed=s, **kw), batch_size=batch_size,
+                                     shuffle=sh, collate_fn=collate_fn_flava, generator=g,
+                                     drop_last=False)
+    return mk(n_train, seed, shuffle), mk(n_val, seed + 1, False), mk(n_test, seed + 2, False)

@@ -1,0 +1,208 @@
+"""Training / evaluation driver with the reference's ``Model_`` protocol
+(reference ``src/framework.py:35-355``): same constructor, ``to``, ``train_loop`` and
+``eval_loop`` signatures, same callback hooks, same epoch-log keys (``loss, acc, val_loss,
+val_acc, val_auc, test_*, time, epoch``) and the same stopping rules (NaN loss; train accuracy
+== 100 for ``patience`` epochs).
+
+The per-batch body is the hot path: ``data_forming`` (host RNG) -> H2D -> ``model(x)`` ->
+``compute_loss`` -> ``backward`` -> ``optimizer.step`` -> metrics -> ``scheduler.step``.  It is
+exposed on its own as ``train_step`` / ``eval_step`` so it can be benchmarked through the public
+API.  MMBT / ViLT branches of the reference loop are out of scope for this build and raise.
+"""
+import itertools
+import math
+import timeit
+
+import numpy as np
+import torch
+
+from .callbacks import CallbackList, ProgressionCallback, ValidationProgressionCallback
+
+
+def _step_stream(steps, generator):
+    if steps is None:
+        return zip(itertools.count(1), generator)
+
+    def cycle():
+        while True:
+            yield from generator
+    return zip(range(1, steps + 1), cycle())
+
+
+class StepIterator:
+    """Yields ``(step, batch)``; after the body fills ``step['loss'|'metrics'|'size']`` it keeps
+    size-weighted running means and fires the batch callbacks (reference :35-95)."""
+
+    _reserved = ("loss", "metrics", "number", "size")
+
+    def __init__(self, generator, steps_per_epoch, callback, metrics_names):
+        self.generator, self.steps_per_epoch = generator, steps_per_epoch
+        self.callback, self.metrics_names = callback, metrics_names
+        self.losses_sum, self.sizes_sum = 0.0, 0.0
+        self.metrics_sum = np.zeros(len(metrics_names))
+        self.extra_lists = {}
+
+    @property
+    def loss(self):
+        return self.losses_sum / self.sizes_sum if self.sizes_sum else 0
+
+    @property
+    def metrics(self):
+        if not self.sizes_sum:
+            return dict(zip(self.metrics_names, np.zeros(len(self.metrics_names))))
+        return dict(zip(self.metrics_names, self.metrics_sum / self.sizes_sum))
+
+    def __iter__(self):
+        for number, data in _step_stream(self.steps_per_epoch, self.generator):
+            t0 = timeit.default_timer()
+            self.callback.on_batch_begin(number, {})
+            self.callback.on_forward_begin(number, data)
+            step = {"number": number}
+            yield step, data
+            size = step["size"]
+            self.losses_sum += step["loss"] * size
+            self.metrics_sum += step["metrics"] * size
+            self.sizes_sum += size
+            for key, value in step.items():
+                if key not in self._reserved:
+                    self.extra_lists.setdefault(key, []).append(value)
+            logs = {"batch": number, "size": size, "time": timeit.default_timer() - t0,
+                    "batch_begin_time": t0, "loss": step["loss"],
+                    **dict(zip(self.metrics_names, step["metrics"]))}
+            self.callback.on_batch_end(number, logs)
+
+
+class Model_:
+    def __init__(self, model, optimizer, scheduler, data_forming_func, *, metrics=[], verbose=True):
+        self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
+        self.data_forming = data_forming_func
+        self.metrics = metrics
+        self.metrics_names = [m.__name__ for m in metrics]
+        self.device = None
+        self.verbose = verbose
+        self.verbose_logs = {}
+
+    # ---------------------------------------------------------------- plumbing
+    def _compute_metrics(self, pred_y, y, eval, dummy_dim):
+        return np.array([float(m(pred_y, y, eval, dummy_dim)) for m in self.metrics])
+
+    def _transfer_optimizer_state_to_right_device(self):
+        for group in self.optimizer.param_groups:
+            for p in group["params"]:
+                for v in self.optimizer.state.get(p, {}).values():
+                    if torch.is_tensor(v) and v.device != p.device:
+                        v.data = v.data.to(p.device)
+
+    def to(self, device):
+        self.device = device
+        self.model.to(device)
+        for m in self.metrics:
+            if isinstance(m, torch.nn.Module):
+                m.to(device)
+        return self
+
+    def to_device(self, x):
+        if isinstance(x, (tuple, list)):
+            return [None if t is None else t.to(self.device, non_blocking=True) for t in x]
+        return x.to(self.device, non_blocking=True)
+
+    @staticmethod
+    def _reject(mmbt, vilt):
+        if mmbt or vilt:
+            raise NotImplementedError("the MMBT / ViLT branches are outside this build's hot path "
+                                      "(SURVEY.md 8c: third-party arithmetic, parity unpinned)")
+
+    # ---------------------------------------------------------------- hot path
+    def train_step(self, x, y, scheduler_step_on="batch", keep_mask=None):
+        """One optimisation step on a HOST batch; returns (loss: float, metrics: ndarray, size)."""
+        x, y = self.data_forming(x, y, phase="train")
+        x, y = self.to_device(x), self.to_device(y)
+        self.optimizer.zero_grad()
+        y_pred = self.model(x) if keep_mask is None else self.model(x, keep_mask=keep_mask)
+        loss = self.model.compute_loss(y_pred, y)
+        loss.backward()
+        self.optimizer.step()
+        with torch.no_grad():
+            info = self._compute_metrics(y_pred, y, eval=False, dummy_dim=True)
+        if scheduler_step_on == "batch" and self.scheduler is not None:
+            self.scheduler.step()
+        return loss.item(), info, len(y)
+
+    @torch.no_grad()
+    def eval_step(self, x, y):
+        x, y = self.data_forming(x, y, phase="eval")
+        x, y = self.to_device(x), self.to_device(y)
+        outputs = self.model(x)
+        loss = self.model.compute_loss(outputs, y, eval=True)
+        info = self._compute_metrics(outputs, y, eval=True, dummy_dim=True)
+        return float(loss), info, len(y), outputs, y
+
+    # ---------------------------------------------------------------- loops
+    def eval_loop(self, generator, phase, *, steps=None, auc=False, mmbt=False, vilt=False):
+        self._reject(mmbt, vilt)
+        steps = len(generator) if steps is None else steps
+        it = StepIterator(generator, steps,
+                          ValidationProgressionCallback(phase=phase, steps=steps,
+                                                        metrics_names=["loss"] + self.metrics_names),
+                          self.metrics_names)
+        self.model.eval()
+        preds, labels = [], []
+        for step, (x, y) in it:
+            loss, info, size, outputs, y_dev = self.eval_step(x, y)
+            step["size"], step["loss"], step["metrics"] = size, loss, info
+            preds.append(outputs.mean(1))
+            labels.append(y_dev)
+        out = {f"{phase}_loss": it.loss,
+               **{f"{phase}_{k}": v for k, v in it.extra_lists.items()},
+               **{f"{phase}_{k}": v for k, v in it.metrics.items()}}
+        if auc:
+            from sklearn.metrics import roc_auc_score
+            p = torch.cat(preds).cpu().numpy()
+            out[f"{phase}_auc"] = roc_auc_score(torch.cat(labels).cpu().numpy(), p[:, 1])
+        return out
+
+    def train_loop(self, train_generator, test_generator=None, valid_generator=None, *,
+                   epochs=1000, steps_per_epoch=None, validation_steps=None, test_steps=None,
+                   patience=10, callbacks=[], epoch_start=1, scheduler_step_on="epoch", auc=False,
+                   mmbt=False, vilt=False, **kwargs):
+        self._reject(mmbt, vilt)
+        self._transfer_optimizer_state_to_right_device()
+        cbs = CallbackList(callbacks)
+        cbs.append(ProgressionCallback(verbose=self.verbose))
+        cbs.set_params({"epochs": epochs, "steps": steps_per_epoch})
+        cbs.set_model_pytoune(self)
+
+        stop, stopped_epoch, perfect_epochs = False, 0, 0
+        cbs.on_train_begin({})
+        for epoch in range(epoch_start, epochs + 1):
+            cbs.on_epoch_begin(epoch, {})
+            t0 = timeit.default_timer()
+            it = StepIterator(train_generator, steps_per_epoch, cbs, self.metrics_names)
+            self.model.train(True)
+            with torch.enable_grad():
+                for step, (x, y) in it:
+                    loss, info, size = self.train_step(x, y, scheduler_step_on)
+                    cbs.on_backward_end(step["number"])
+                    step["size"], step["loss"], step["metrics"] = size, loss, info
+                    if math.isnan(loss):
+                        stop = True
+            log = {"epoch": epoch, "loss": it.loss,
+                   **{f"train_{k}": v for k, v in it.extra_lists.items()}, **it.metrics}
+            if valid_generator is not None:
+                log.update(self.eval_loop(valid_generator, "val", steps=validation_steps, auc=auc))
+            if test_generator is not None:
+                log.update(self.eval_loop(test_generator, "test", steps=test_steps, auc=auc))
+            log["time"] = timeit.default_timer() - t0
+            log["epoch_begin_time"] = t0
+            if scheduler_step_on == "epoch" and self.scheduler is not None:
+                self.scheduler.step(log[kwargs["scheduler_metric"]])
+            cbs.on_epoch_end(epoch, log)
+            if log.get("acc") == 100:
+                perfect_epochs += 1
+            if perfect_epochs >= patience:
+                stopped_epoch, stop = epoch, True
+            if stop:
+                break
+        cbs.on_train_end({})
+        if stopped_epoch > 0:
+            print("Epoch %05d: completed stopping" % stopped_epoch)

@@ -1,0 +1,353 @@
+"""Fusion models with the reference's names, constructor signatures, state-dict keys and call
+protocol (reference ``src/model.py:225-374``), executed by the sm_100a engine.
+
+``model(x)`` with ``x = (image_features, text_features)`` (either may be ``None`` in eval)
+returns logits ``(B, E, C)``; ``model.compute_loss(y_hat, y, eval=False)`` returns the scalar
+loss.  All parameters are views into ONE flat fp32 buffer (so the fused AdamW and the gradient
+all-reduce see a single contiguous tensor) while staying individually addressable
+``nn.Parameter`` objects under the reference's keys, e.g.
+``mm_encoder.resblocks.0.attn.in_proj_weight`` -- reference checkpoints load with
+``strict=True`` (reference ``src/training_loop.py:72-77``).
+"""
+import ctypes as C
+from typing import Any
+
+import torch
+import torch.nn as nn
+
+from ._backend import _lib, ops
+
+_PREC = {"fp32": _lib.F32, "bf16": _lib.BF16, torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+class _Holder(nn.Module):
+    """Parameter container: only exists so that state-dict keys match the reference's tree."""
+
+
+def _holder_for(root, dotted):
+    mod = root
+    parts = dotted.split(".")
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, _Holder())
+        mod = mod._modules[p]
+    return mod, parts[-1]
+
+
+class _FlavaForward(torch.autograd.Function):
+    """One engine call forward, one (staged) engine call backward.  Parameter gradients are
+    accumulated by the kernels straight into the model's flat gradient buffer (the ``.grad`` of
+    every parameter is a view of it), so backward returns no tensor gradients."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, img, txt, idx_img, idx_txt, keep):
+        ctx.model = model
+        ctx.inputs = model._engine_forward(img, txt, idx_img, idx_txt, keep, training=True)
+        return model._logits_train
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        ctx.model._engine_backward(ctx.inputs, dlogits.contiguous())
+        return (None,) * 7
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_hat, y, model):
+        N, E, _ = y_hat.shape
+        dl, _, _, accum = ops.heads_uncertainty_epilogue(
+            y_hat, y, 0, grad_scale=1.0 / (N * E), want_grad=True)
+        ctx.save_for_backward(dl)
+        model._remember_epilogue(y_hat, 0, accum)
+        return _loss_from_accum(accum)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None, None
+
+
+def _loss_from_accum(accum):
+    o = _lib.ACC_OFF
+    loss_sum = accum[o["loss_sum"]:o["loss_sum"] + 1].view(torch.float64)
+    n_rows = accum[o["n_rows"]:o["n_rows"] + 1].to(torch.float64)
+    return (loss_sum / n_rows).to(torch.float32).reshape(())
+
+
+class FlavaFusionTransfomer(nn.Module):
+    """Drop-in for reference ``FlavaFusionTransfomer`` (src/model.py:225-304).
+
+    One optional keyword beyond the reference: ``precision`` ("bf16" tensor-core path, default,
+    or "fp32" parity path).  ``avg_pool`` is REQUIRED, as in the reference (:256).  Device
+    workspaces are allocated per (batch, token-count) shape on first use and cached.
+    """
+
+    _cls_token = False
+
+    def __init__(self,
+                 out_dim: int = 1,
+                 num_classes: int = 2,
+                 image_hidden_size: int = 768,
+                 text_hidden_size: int = 768,
+                 multimodal_hidden_size: int = 768,
+                 multimodal_num_attention_heads: int = 3,
+                 multimodal_num_hidden_layers: int = 3,
+                 drop: float = 0.0,
+                 **kwargs: Any):
+        super().__init__()
+        self.avg_pool = bool(kwargs["avg_pool"])
+        self.out_dim = out_dim
+        self.num_classes = num_classes
+        self.drop = float(drop)
+        self.precision = _PREC[kwargs.get("precision", "bf16")]
+        self._dims = dict(d_img=image_hidden_size, d_txt=text_hidden_size, D=multimodal_hidden_size,
+                          n_head=multimodal_num_attention_heads,
+                          n_layers=multimodal_num_hidden_layers)
+        self._ws = {}
+        self._cfg_cache = {}
+        self._last_epi = None
+        self._ddp = None
+        self._logits_train = None
+        self.loss = torch.nn.CrossEntropyLoss()  # kept for attribute parity; never called
+
+        cfg = self._config(1, 1, 1)
+        n = int(_lib.lib.mmu_flava_param_count(C.byref(cfg)))
+        _lib.check(n, "mmu_flava_param_count")
+        table = (_lib.ParamEntry * 512)()
+        cnt = _lib.check(_lib.lib.mmu_flava_param_table(C.byref(cfg), table, 512))
+        self._table = [(table[i].name.decode(), int(table[i].offset), int(table[i].numel),
+                        int(table[i].rows), int(table[i].cols), int(table[i].stage))
+                       for i in range(cnt)]
+        self._n_stages = int(_lib.lib.mmu_flava_num_stages(C.byref(cfg)))
+        self._flat = torch.zeros(n, dtype=torch.float32)
+        self._flat_grad = torch.zeros(n, dtype=torch.float32)
+        self._register_views()
+        self._init_like_reference()
+
+    # ------------------------------------------------------------------ parameters
+    def _reference_order(self):
+        d = {name: i for i, (name, *_rest) in enumerate(self._table)}
+        order = []
+        for i in range(self._dims["n_layers"]):
+            pre = f"mm_encoder.resblocks.{i}."
+            order += [pre + s for s in ("attn.in_proj_weight", "attn.in_proj_bias",
+                                        "attn.out_proj.weight", "attn.out_proj.bias",
+                                        "ln_1.weight", "ln_1.bias", "mlp.c_fc.weight",
+                                        "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias",
+                                        "ln_2.weight", "ln_2.bias")]
+        order += ["ln_pre.weight", "ln_pre.bias", "ln_post.weight", "ln_post.bias",
+                  "image_to_mm_projection.weight", "image_to_mm_projection.bias",
+                  "text_to_mm_projection.weight", "text_to_mm_projection.bias"]
+        for e in range(self.out_dim):
+            order += [f"output_layers.{e}.weight", f"output_layers.{e}.bias"]
+        if self._cls_token:
+            order.append("class_embeddings")
+        assert sorted(order) == sorted(d), "engine parameter table and reference key set differ"
+        return [self._table[d[k]] for k in order]
+
+    def _register_views(self):
+        # registration order = the reference's parameters() order (optimizer state-dict parity)
+        for name, off, numel, rows, cols, _stage in self._reference_order():
+            shape = (rows, cols) if cols > 0 else (rows,)
+            p = nn.Parameter(self._flat[off:off + numel].view(shape))
+            p._mmu_owner = self
+            holder, leaf = _holder_for(self, name)
+            holder.register_parameter(leaf, p)
+        self._rebind(self._flat, self._flat_grad)
+
+    def _rebind(self, flat, flat_grad):
+        self._flat, self._flat_grad = flat, flat_grad
+        params = dict(self.named_parameters())
+        for name, off, numel, rows, cols, _stage in self._table:
+            shape = (rows, cols) if cols > 0 else (rows,)
+            p = params[name]
+            p.data = flat[off:off + numel].view(shape)
+            p.grad = flat_grad[off:off + numel].view(shape)
+        self._ws.clear()
+
+    def _apply(self, fn, recurse=True):
+        flat = fn(self._flat)
+        if flat.dtype != torch.float32:
+            raise TypeError("the master parameters are fp32; choose precision='bf16' for the "
+                            "tensor-core path instead of casting the module")
+        grad = fn(self._flat_grad)
+        self._rebind(flat, grad)
+        return self
+
+    @torch.no_grad()
+    def _init_like_reference(self):
+        """Same initialisers, called in the same order as the reference constructor would call
+        them (torch's own module constructors consume the RNG identically), so a seeded
+        construction yields the reference's initial weights."""
+        d = self._dims
+        sd = {}
+        for i in range(d["n_layers"]):
+            pre = f"mm_encoder.resblocks.{i}."
+            attn = nn.MultiheadAttention(d["D"], d["n_head"])
+            sd[pre + "attn.in_proj_weight"] = attn.in_proj_weight
+            sd[pre + "attn.in_proj_bias"] = attn.in_proj_bias
+            sd[pre + "attn.out_proj.weight"] = attn.out_proj.weight
+            sd[pre + "attn.out_proj.bias"] = attn.out_proj.bias
+            ln1 = nn.LayerNorm(d["D"])
+            fc, proj = nn.Linear(d["D"], 4 * d["D"]), nn.Linear(4 * d["D"], d["D"])
+            ln2 = nn.LayerNorm(d["D"])
+            for k, m in (("ln_1", ln1), ("mlp.c_fc", fc), ("mlp.c_proj", proj), ("ln_2", ln2)):
+                sd[pre + k + ".weight"], sd[pre + k + ".bias"] = m.weight, m.bias
+        for k, m in (("ln_pre", nn.LayerNorm(d["D"])), ("ln_post", nn.LayerNorm(d["D"])),
+                     ("image_to_mm_projection", nn.Linear(d["d_img"], d["D"])),
+                     ("text_to_mm_projection", nn.Linear(d["d_txt"], d["D"]))):
+            sd[k + ".weight"], sd[k + ".bias"] = m.weight, m.bias
+        for e in range(self.out_dim):
+            m = nn.Linear(d["D"], self.num_classes)
+            sd[f"output_layers.{e}.weight"], sd[f"output_layers.{e}.bias"] = m.weight, m.bias
+        if self._cls_token:
+            sd["class_embeddings"] = d["D"] ** -0.5 * torch.randn(d["D"], self.out_dim)
+        for name, p in self.named_parameters():
+            p.copy_(sd[name])
+
+    def zero_grad(self, set_to_none: bool = False):
+        self._flat_grad.zero_()
+
+    # ---------------------------------------------------------------------- engine
+    def _config(self, B, l_img, l_txt):
+        key = (B, l_img, l_txt)
+        cfg = self._cfg_cache.get(key)
+        if cfg is None:
+            d = self._dims
+            cfg = _lib.FlavaConfig(B, l_img, l_txt, d["d_img"], d["d_txt"], d["D"], d["n_head"],
+                                   d["n_layers"], self.out_dim, self.num_classes,
+                                   int(self.avg_pool), int(self._cls_token), self.precision)
+            self._cfg_cache[key] = cfg
+        return cfg
+
+    def _workspace(self, cfg, training):
+        key = (cfg.B, cfg.l_img, cfg.l_txt, bool(training))
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = _lib.lib.mmu_flava_workspace_bytes(C.byref(cfg), int(training))
+            _lib.check(nbytes, "mmu_flava_workspace_bytes")
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self._flat.device)
+            self._ws[key] = ws
+        return ws
+
+    def _engine_forward(self, img, txt, idx_img, idx_txt, keep, training):
+        if not self._flat.is_cuda:
+            raise _lib.MMUError("the model lives on the CPU: call .to('cuda') first -- this "
+                                "package has no CPU execution path")
+        if training and self.drop > 0.0:
+            raise NotImplementedError("dropout > 0 is not implemented in the fused engine "
+                                      "(the reference's own runs use --dropout 0, train.py:59)")
+        ref = img if img is not None else txt
+        B = ref.shape[0]
+        dev = self._flat.device
+
+        def prep(t):
+            return None if t is None else t.to(device=dev, dtype=torch.float32).contiguous()
+
+        def prep_idx(i):
+            return None if i is None else i.to(device=dev, dtype=torch.int32).contiguous()
+
+        img, txt, idx_img, idx_txt = prep(img), prep(txt), prep_idx(idx_img), prep_idx(idx_txt)
+        keep = None if keep is None else keep.to(device=dev, dtype=torch.int32).contiguous()
+        l_img = img.shape[1] if img is not None else 0
+        l_txt = txt.shape[1] if txt is not None else 0
+        n_img = (idx_img.numel() if idx_img is not None else l_img) if img is not None else 0
+        n_txt = (idx_txt.numel() if idx_txt is not None else l_txt) if txt is not None else 0
+        cfg = self._config(B, max(l_img, 1), max(l_txt, 1))
+        ws = self._workspace(cfg, training)
+        inp = _lib.FlavaInputs(_lib.ptr(img), _lib.ptr(txt), _lib.ptr(idx_img), _lib.ptr(idx_txt),
+                               n_img, n_txt, _lib.ptr(keep))
+        logits = torch.empty(B, self.out_dim, self.num_classes, device=dev, dtype=torch.float32)
+        _lib.check(_lib.lib.mmu_flava_forward(C.byref(cfg), self._flat.data_ptr(), C.byref(inp),
+                                              ws.data_ptr(), ws.numel(), int(training),
+                                              logits.data_ptr(), _lib.stream_ptr()),
+                   "mmu_flava_forward")
+        if training:
+            self._logits_train = logits
+            return (cfg, inp, ws, (img, txt, idx_img, idx_txt, keep))  # keep inputs alive
+        return logits
+
+    def _engine_backward(self, saved, dlogits):
+        cfg, inp, ws, _alive = saved
+        if self._ddp is not None:
+            self._ddp.backward(self, cfg, inp, ws, dlogits)
+            return
+        _lib.check(_lib.lib.mmu_flava_backward(C.byref(cfg), self._flat.data_ptr(), C.byref(inp),
+                                               ws.data_ptr(), ws.numel(), dlogits.data_ptr(),
+                                               self._flat_grad.data_ptr(), 0, self._n_stages,
+                                               _lib.stream_ptr()), "mmu_flava_backward")
+
+    def backward_stages(self, cfg, inp, ws, dlogits, begin, end):
+        _lib.check(_lib.lib.mmu_flava_backward(C.byref(cfg), self._flat.data_ptr(), C.byref(inp),
+                                               ws.data_ptr(), ws.numel(), dlogits.data_ptr(),
+                                               self._flat_grad.data_ptr(), begin, end,
+                                               _lib.stream_ptr()), "mmu_flava_backward")
+
+    def stage_ranges(self):
+        """[(begin, end)] element ranges of the flat gradient finished by each backward stage."""
+        out = []
+        for st in range(self._n_stages):
+            offs = [(o, o + n) for _nm, o, n, _r, _c, s in self._table if s == st]
+            out.append((min(a for a, _ in offs), max(b for _, b in offs)))
+        return out
+
+    # -------------------------------------------------------------- reference protocol
+    def forward(self, x, token_indices=None, keep_mask=None):
+        """``x = (image_features, text_features)``.  ``token_indices = (idx_img, idx_txt)`` runs
+        the model on token subsets gathered on device (robustness sweeps); ``keep_mask`` is an
+        int (B, 2) modality keep mask (0 zero-fills that modality for that sample)."""
+        img, txt = x
+        idx_img, idx_txt = token_indices if token_indices is not None else (None, None)
+        if self.training and torch.is_grad_enabled():
+            anchor = next(self.parameters())
+            return _FlavaForward.apply(anchor, self, img, txt, idx_img, idx_txt, keep_mask)
+        return self._engine_forward(img, txt, idx_img, idx_txt, keep_mask, training=False)
+
+    def _remember_epilogue(self, y_hat, mode, accum):
+        self._last_epi = (y_hat.data_ptr(), y_hat._version, tuple(y_hat.shape), mode, accum)
+
+    def cached_epilogue(self, y_hat, mode):
+        e = self._last_epi
+        if e is not None and e[0] == y_hat.data_ptr() and e[1] == y_hat._version \
+                and e[2] == tuple(y_hat.shape) and e[3] == mode:
+            return e[4]
+        return None
+
+    def compute_loss(self, y_hat, y, eval=False):
+        """Reference src/model.py:293-304: train -> mean CE over the (B*E) head rows against the
+        tiled labels; eval -> CE on the head-mean logits."""
+        assert y.shape[0] == y_hat.shape[0]
+        y_hat = y_hat if y_hat.is_contiguous() else y_hat.contiguous()
+        if not eval:
+            y2 = y.reshape(y_hat.shape[0], -1)
+            if y2.shape[1] not in (1, y_hat.shape[1]):
+                raise ValueError("labels must be (B,) or (B, E)")
+            if y_hat.requires_grad:
+                return _LossFn.apply(y_hat, y2.contiguous(), self)
+            _, _, _, accum = ops.heads_uncertainty_epilogue(y_hat, y2.contiguous(), 0)
+            self._remember_epilogue(y_hat, 0, accum)
+            return _loss_from_accum(accum)
+        _, _, _, accum = ops.heads_uncertainty_epilogue(y_hat.detach(), y.reshape(-1).contiguous(), 1)
+        self._remember_epilogue(y_hat, 1, accum)
+        return _loss_from_accum(accum)
+
+
+class FlavaFusionTransfomerwithCLSToken(FlavaFusionTransfomer):
+    """Drop-in for reference ``FlavaFusionTransfomerwithCLSToken`` (src/model.py:306-374): E
+    learned class rows are prepended to every sample's sequence and head i reads row i."""
+
+    _cls_token = True
+
+    def __init__(self,
+                 out_dim: int = 1,
+                 num_classes: int = 2,
+                 image_hidden_size: int = 768,
+                 text_hidden_size: int = 768,
+                 multimodal_hidden_size: int = 768,
+                 multimodal_num_attention_heads: int = 3,
+                 multimodal_num_hidden_layers: int = 3,
+                 drop: float = 0.1,
+                 **kwargs: Any):
+        super().__init__(out_dim, num_classes, image_hidden_size, text_hidden_size,
+                         multimodal_hidden_size, multimodal_num_attention_heads,
+                         multimodal_num_hidden_layers, drop, **kwargs)

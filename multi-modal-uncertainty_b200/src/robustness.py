@@ -1,0 +1,109 @@
+"""Robustness sweeps over token subsets / modality masks (reference
+``eval_transformer_robustness.py:37-52, 95-137`` and ``eval_robustness.py:82-121``).
+
+Index sets are drawn on the HOST from the same generators, in the same order, as the reference
+(NumPy global state for n, torch CPU generator for the permutations) so masks are bit-exact;
+the token gather, the forward passes and the scoring run on the GPU.  Instead of dumping
+``(S, 43, K, C)`` logits to ``.npy`` for notebooks, metrics accumulate on device per variant
+(one small all-reduce per sweep); the ``.npy``-shaped array is still returned on request.
+"""
+import numpy as np
+import torch
+
+from .metrics import UncertaintyMeter
+
+
+def input_sampling(l_img, l_txt, type="image"):
+    """Reference eval_transformer_robustness.py:37-52."""
+    assert type in ("image", "text")
+    l = l_img if type == "image" else l_txt
+    n = int(np.random.randint(0, l + 1, size=1)[0])
+    n_img, n_txt = (n, l - n) if type == "image" else (l - n, n)
+    idx_img = torch.sort(torch.randperm(l_img)[:n_img]).values
+    idx_txt = torch.sort(torch.randperm(l_txt)[:n_txt]).values
+    return idx_img, idx_txt
+
+
+def robustness_variants(l_img, l_txt, n_repeats=20):
+    """[(idx_img | None, idx_txt | None)] in the reference's order (:103-121): full, image only,
+    text only, n_repeats image-controlled draws, n_repeats text-controlled draws."""
+    fi, ft = torch.arange(l_img), torch.arange(l_txt)
+    out = [(fi, ft), (fi, None), (None, ft)]
+    for type in ("image", "text"):
+        for _ in range(n_repeats):
+            ii, it = input_sampling(l_img, l_txt, type)
+            out.append((ii if len(ii) else None, it if len(it) else None))
+    return out
+
+
+def mask_level_variant(l_img, l_txt, type, level, levels=10):
+    """North-star config 3 grid: n_k = round(k l / (levels-1)) tokens of the
+    controlled modality, l - n_k of the other; permutations from torch's CPU generator."""
+    l = l_img if type == "image" else l_txt
+    n = int(round(level * l / (levels - 1)))
+    n_img, n_txt = (n, l - n) if type == "image" else (l - n, n)
+    n_img, n_txt = min(n_img, l_img), min(n_txt, l_txt)
+    idx_img = torch.sort(torch.randperm(l_img)[:n_img]).values
+    idx_txt = torch.sort(torch.randperm(l_txt)[:n_txt]).values
+    return (idx_img if n_img else None, idx_txt if n_txt else None)
+
+
+def modality_dropout_mask(batch_size, p_drop, mode="random", scores=None, generator=None):
+    """(B, 2) int32 keep mask over (image, text); guided / random modality dropout.  The
+    reference only names these (configs/training_guided.gin:10-18); the definition is this
+    repo's (see oracle/shaping.py) -- parity unpinned."""
+    u = torch.rand(batch_size, generator=generator)
+    pick = torch.rand(batch_size, generator=generator)
+    keep = torch.ones(batch_size, 2, dtype=torch.int32)
+    if mode == "random":
+        which = (pick >= 0.5).to(torch.int64)
+    elif mode == "guided":
+        which = (scores[:, 1] > scores[:, 0]).to(torch.int64)
+    else:
+        raise ValueError(mode)
+    rows = torch.nonzero(u < p_drop).flatten()
+    keep[rows, which[rows]] = 0
+    return keep
+
+
+@torch.no_grad()
+def forward_variant(model, img, txt, variant, ref_bug_compat=False):
+    """Run one variant.  ``ref_bug_compat`` reproduces reference line 119 (text slot indexed
+    from ``img``); the default follows the evident intent."""
+    ii, it = variant
+    src_txt = img if ref_bug_compat else txt
+    x = (img if ii is not None else None, src_txt if it is not None else None)
+    full_i = ii is None or (len(ii) == img.shape[1] and bool((ii == torch.arange(len(ii))).all()))
+    full_t = it is None or (len(it) == src_txt.shape[1] and bool((it == torch.arange(len(it))).all()))
+    idx = (None if full_i else ii, None if full_t else it)
+    return model(x, token_indices=idx)
+
+
+@torch.no_grad()
+def run_transformer_robustness(model, batches, device, n_repeats=20, ref_bug_compat=False,
+                               collect=True, variants_fn=None):
+    """Sweep every batch through the variant schedule.  Returns (preds (S, V, K, C) numpy or
+    None, labels numpy, [per-variant metric dicts])."""
+    model.eval()
+    meters, preds, labels = None, [], []
+    for (img, txt), y in batches:
+        img, txt, y = img.to(device), txt.to(device), y.to(device).reshape(-1)
+        if variants_fn is None:
+            variants = robustness_variants(img.shape[1], txt.shape[1], n_repeats)
+        else:
+            variants = variants_fn(img.shape[1], txt.shape[1])
+        if meters is None:
+            meters = [UncertaintyMeter(device, model.num_classes, model.out_dim) for _ in variants]
+        outs = []
+        for v, meter in zip(variants, meters):
+            logits = forward_variant(model, img, txt, v, ref_bug_compat)
+            meter.update(logits, y)
+            if collect:
+                outs.append(logits)
+        if collect:
+            preds.append(torch.stack(outs, dim=1).cpu())
+        labels.append(y.cpu())
+    for m in meters or []:
+        m.all_reduce()
+    P = torch.cat(preds).numpy() if collect and preds else None
+    return P, torch.cat(labels).numpy(), [m.compute() for m in meters or []]

@@ -267,6 +267,22 @@ def notebook_case():
                 acc_full=float((pred[:, 0] == labels).mean() * 100))
 
 
+def init_case(ref_model):
+    """Seeded construction of the reference modules: per-parameter checksums of the initial
+    weights (the product constructs torch's own layers in the same order under the same seed)."""
+    out = {}
+    for name, klass, kw in [
+            ("plain", ref_model.FlavaFusionTransfomer, dict(out_dim=2, num_classes=7, avg_pool=False)),
+            ("cls", ref_model.FlavaFusionTransfomerwithCLSToken, dict(out_dim=3, num_classes=5, avg_pool=False))]:
+        torch.manual_seed(123)
+        m = klass(image_hidden_size=32, text_hidden_size=48, multimodal_hidden_size=64,
+                  multimodal_num_attention_heads=2, multimodal_num_hidden_layers=2, drop=0.0, **kw)
+        out[name] = {k: torch.stack([v.double().sum(), v.double().abs().sum()])
+                     for k, v in m.state_dict().items()}
+        out[name + "_param_order"] = [k for k, _ in m.named_parameters()]
+    return out
+
+
 def main():
     torch.set_num_threads(4)
     ref_model, ref_dataset, _ = import_reference()
@@ -288,6 +304,7 @@ def main():
     torch.save(sampling_case(), os.path.join(HERE, "input_sampling.pt"))
     torch.save(optimizer_case(), os.path.join(HERE, "adamw_cosine.pt"))
     torch.save(notebook_case(), os.path.join(HERE, "notebook_scoring.pt"))
+    torch.save(init_case(ref_model), os.path.join(HERE, "init_seed123.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

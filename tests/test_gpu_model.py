@@ -1,0 +1,258 @@
+"""Model-level parity of the CUDA engine (through the reference-shaped Python API) against the
+golden fixtures produced by the unmodified reference and against the CPU oracle.
+
+Tolerances: fp32 path -- 1e-3 relative on logits / loss / gradients (north_star), bit-exact
+argmax; bf16 tensor-core path -- stated separately below (bf16 has 8 mantissa bits: 4e-3 per
+rounding, accumulated over ~20 roundings of O(1) activations)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["plain_E2", "plain_E1", "avgpool_E2", "cls_E3", "plain_E5_h3"]
+BF16_LOGIT_TOL = 6e-2   # relative to max |logit|
+BF16_GRAD_TOL = 0.2     # relative to max |grad| of the tensor
+
+
+@pytest.fixture(scope="module")
+def mmu():
+    import mmu_b200
+    return mmu_b200
+
+
+def build(mmu, cfg, sd, precision):
+    klass = mmu.FlavaFusionTransfomerwithCLSToken if cfg["cls"] else mmu.FlavaFusionTransfomer
+    m = klass(out_dim=cfg["E"], num_classes=cfg["C"], image_hidden_size=cfg["d_img"],
+              text_hidden_size=cfg["d_txt"], multimodal_hidden_size=cfg["D"],
+              multimodal_num_attention_heads=cfg["heads"],
+              multimodal_num_hidden_layers=cfg["layers"], drop=0.0, avg_pool=cfg["avg_pool"],
+              precision=precision)
+    m.load_state_dict(sd, strict=True)  # reference checkpoint keys, strict
+    return m.cuda()
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_fp32_matches_reference_goldens(mmu, golden, name):
+    c = golden("flava_small.pt")[name]
+    cfg = c["cfg"]
+    m = build(mmu, cfg, c["state_dict"], "fp32").train()
+    opt = mmu.FusedAdamW(m.parameters(), lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-3)
+    opt.zero_grad()
+    logits = m((c["img"].cuda(), c["txt"].cuda()))
+    loss = m.compute_loss(logits, c["y_train"].cuda())
+    loss.backward()
+    assert rel(logits.detach().cpu(), c["logits"]) < 1e-3
+    assert abs(float(loss) - float(c["loss"])) < 1e-3 * abs(float(c["loss"]))
+    assert torch.equal(logits.detach().cpu().argmax(-1), c["logits"].argmax(-1))  # bit-exact
+    assert float(mmu.acc(logits, c["y_train"].cuda(), False, True)) == pytest.approx(
+        float(c["train_acc"]), abs=1e-4)
+    for k, p in m.named_parameters():
+        g = c["grads"][k]
+        scale = float(g.abs().max())
+        if scale < 1e-7:
+            assert float(p.grad.abs().max()) < 1e-7, k  # dead text projection stays exactly dead
+        else:
+            assert float((p.grad.cpu() - g).abs().max()) < 1e-3 * scale, k
+    opt.step()
+    for k, p in m.named_parameters():
+        assert float((p.detach().cpu() - c["params_after_adamw"][k]).abs().max()) < 2e-5, k
+    # eval protocol: CE on head-mean logits, acc on the same
+    m.load_state_dict(c["state_dict"])
+    m.eval()
+    with torch.no_grad():
+        le = m((c["img"].cuda(), c["txt"].cuda()))
+        assert rel(le.cpu(), c["logits_eval"]) < 1e-3
+        assert abs(float(m.compute_loss(le, c["y"].cuda(), eval=True)) - float(c["loss_eval"])) < 1e-3
+        assert float(mmu.acc(le, c["y"].cuda(), True, True)) == pytest.approx(float(c["eval_acc"]), abs=1e-4)
+        if cfg["cls"]:
+            assert rel(m((c["img"].cuda(), None)).cpu(), c["logits_img_only"]) < 1e-3
+            assert rel(m((None, c["txt"].cuda())).cpu(), c["logits_txt_only"]) < 1e-3
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_bf16_tensor_core_path(mmu, golden, name):
+    c = golden("flava_small.pt")[name]
+    cfg = c["cfg"]
+    m = build(mmu, cfg, c["state_dict"], "bf16").train()
+    m.zero_grad()
+    logits = m((c["img"].cuda(), c["txt"].cuda()))
+    loss = m.compute_loss(logits, c["y_train"].cuda())
+    loss.backward()
+    assert rel(logits.detach().cpu(), c["logits"]) < BF16_LOGIT_TOL
+    assert abs(float(loss) - float(c["loss"])) < BF16_LOGIT_TOL * max(1.0, abs(float(c["loss"])))
+    for k, p in m.named_parameters():
+        g = c["grads"][k]
+        scale = float(g.abs().max())
+        if scale > 1e-5:
+            assert float((p.grad.cpu() - g).abs().max()) < BF16_GRAD_TOL * scale, k
+
+
+@pytest.mark.parametrize("precision,tol,gtol", [("fp32", 1e-3, 2e-3), ("bf16", BF16_LOGIT_TOL, 0.25)])
+def test_full_width_model(mmu, golden, precision, tol, gtol):
+    """D=768, 3 heads (hd=256), 3 layers, E=5, C=101: the Food-101-shaped model."""
+    from tests.golden.make_golden import det_state_dict
+    c = golden("flava_768.pt")
+    cfg = c["cfg"]
+    m = build(mmu, cfg, det_state_dict(c["shapes"], cfg["seed"]), precision).train()
+    m.zero_grad()
+    logits = m((c["img"].cuda(), c["txt"].cuda()))
+    loss = m.compute_loss(logits, c["y_train"].cuda())
+    loss.backward()
+    assert rel(logits.detach().cpu(), c["logits"]) < tol
+    assert abs(float(loss) - float(c["loss"])) < tol * float(c["loss"])
+    if precision == "fp32":
+        assert torch.equal(logits.detach().cpu().argmax(-1), c["logits"].argmax(-1))
+    for k, p in m.named_parameters():
+        s = c["grad_summaries"][k]
+        if float(s[1]) < 1e-6:
+            continue
+        g = p.grad.double().cpu()
+        assert abs(float(g.abs().sum()) - float(s[1])) < gtol * float(s[1]), k
+        sl = c["grad_slices"][k]
+        scale = max(float(sl.abs().max()), 1e-6)
+        assert float((p.grad.reshape(-1)[:64].cpu() - sl).abs().max()) < max(gtol, 5e-3) * scale + 1e-6, k
+
+
+def test_fp32_vs_oracle_mid_size(mmu):
+    """A shape the fixtures do not cover (ragged l_txt zero padded, B=24, avg_pool)."""
+    from oracle import fusion, shaping
+    torch.manual_seed(5)
+    m = mmu.FlavaFusionTransfomer(out_dim=2, num_classes=13, image_hidden_size=64,
+                                  text_hidden_size=32, multimodal_hidden_size=128,
+                                  multimodal_num_attention_heads=4, multimodal_num_hidden_layers=2,
+                                  avg_pool=True, precision="fp32")
+    P = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(6)
+    items = [(torch.randn(10, 64, generator=g), torch.randn(int(l), 32, generator=g),
+              torch.LongTensor([int(c)])) for l, c in zip(torch.randint(2, 8, (24,), generator=g),
+                                                          torch.randint(0, 13, (24,), generator=g))]
+    (img, txt), y = mmu.dataset.collate_fn_flava(items)
+    (img_o, txt_o), y_o = shaping.collate_fn_flava(items)
+    assert torch.equal(img, img_o) and torch.equal(txt, txt_o) and torch.equal(y, y_o)
+    yt = y.unsqueeze(1).repeat(1, 2)
+    ref_logits, ref_loss, ref_grads = fusion.loss_and_grads(P, (img, txt), yt, 4, True)
+    m.cuda().train()
+    m.zero_grad()
+    logits = m((img.cuda(), txt.cuda()))
+    loss = m.compute_loss(logits, yt.cuda())
+    loss.backward()
+    assert rel(logits.detach().cpu(), ref_logits) < 1e-3
+    assert abs(float(loss) - float(ref_loss)) < 1e-3 * float(ref_loss)
+    for k, p in m.named_parameters():
+        scale = float(ref_grads[k].abs().max())
+        assert float((p.grad.cpu() - ref_grads[k]).abs().max()) < 1e-3 * scale + 1e-8, k
+
+
+def test_robustness_sweep_matches_oracle(mmu):
+    """43-variant schedule (reference eval_transformer_robustness.py:99-121) with the CLS model:
+    bit-exact index sets, fp32 logits within 1e-3, and both line-119 behaviours."""
+    from oracle import fusion, shaping
+    torch.manual_seed(9)
+    m = mmu.FlavaFusionTransfomerwithCLSToken(out_dim=2, num_classes=5, image_hidden_size=32,
+                                              text_hidden_size=32, multimodal_hidden_size=64,
+                                              multimodal_num_attention_heads=2,
+                                              multimodal_num_hidden_layers=2, drop=0.0,
+                                              avg_pool=False, precision="fp32")
+    P = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(10)
+    img, txt = torch.randn(6, 9, 32, generator=g), torch.randn(6, 5, 32, generator=g)
+    y = torch.randint(0, 5, (6,), generator=g)
+    m.cuda().eval()
+    for compat in (False, True):
+        np.random.seed(42); torch.manual_seed(42)
+        variants_o = shaping.robustness_variants(9, 5, n_repeats=4)
+        np.random.seed(42); torch.manual_seed(42)
+        P_gpu, labels, metrics = mmu.robustness.run_transformer_robustness(
+            m, [((img, txt), y)], "cuda", n_repeats=4, ref_bug_compat=compat)
+        assert P_gpu.shape == (6, 11, 2, 5)
+        for vi, v in enumerate(variants_o):
+            if compat and v[1] is not None and int(v[1].max()) >= 9:
+                continue
+            s_img, s_txt = shaping.apply_variant(img, txt, v, ref_bug_compat=compat)
+            ref = fusion.flava_fusion_forward(P, (s_img, s_txt), 2)
+            assert rel(torch.from_numpy(P_gpu[:, vi]), ref) < 1e-3, (compat, vi)
+        assert metrics[0]["n_samples"] == 6
+
+
+def test_state_dict_roundtrip_and_optimizer_checkpoint(mmu, tmp_path, golden):
+    c = golden("flava_small.pt")["plain_E2"]
+    m = build(mmu, c["cfg"], c["state_dict"], "fp32")
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(c["state_dict"].keys()) or set(sd) == set(c["state_dict"])
+    for k in sd:
+        assert torch.equal(sd[k].cpu(), c["state_dict"][k])
+    opt = mmu.FusedAdamW(m.parameters(), lr=1e-3)
+    m.train(); opt.zero_grad()
+    m.compute_loss(m((c["img"].cuda(), c["txt"].cuda())), c["y_train"].cuda()).backward()
+    opt.step()
+    from importlib import import_module
+    utils = import_module("multi-modal-uncertainty_b200.src.utils")
+    tl = import_module("multi-modal-uncertainty_b200.src.training_loop")
+    path = str(tmp_path / "model_last_epoch.pt")
+    utils.save_weights(m, opt, path)
+    ck = torch.load(path, map_location="cpu")
+    assert set(ck) == {"model", "optimizer"}
+    m2 = build(mmu, c["cfg"], c["state_dict"], "fp32")
+    tl._load_pretrained_model(m2, path)
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    # a torch.optim.AdamW built over same-shaped params accepts the optimizer state
+    ref_params = [torch.nn.Parameter(p.detach().cpu().clone()) for p in m.parameters()]
+    torch.optim.AdamW(ref_params, lr=1e-3).load_state_dict(ck["optimizer"])
+
+
+def test_model_trainer_protocol(mmu):
+    """Model_.train_loop / eval_loop over synthetic loaders: finite losses, history keys."""
+    torch.manual_seed(0)
+    m = mmu.FlavaFusionTransfomer(out_dim=2, num_classes=4, image_hidden_size=32,
+                                  text_hidden_size=32, multimodal_hidden_size=64,
+                                  multimodal_num_attention_heads=2, multimodal_num_hidden_layers=1,
+                                  avg_pool=False, precision="bf16")
+    train, val, test = mmu.dataset.get_synthetic_flava(8, 32, 16, 16, l_img=6, l_txt=4, dim=32,
+                                                       num_classes=4, ragged=True)
+    opt = mmu.FusedAdamW(m.parameters(), lr=1e-3)
+    sched = mmu.get_cosine_schedule_with_warmup(opt, 2, 8)
+    from functools import partial
+    trainer = mmu.Model_(m, opt, sched, partial(mmu.dataset.data_forming_func_transformer,
+                                                model_type="MultiHead"),
+                         metrics=[mmu.acc], verbose=False)
+    trainer.to(torch.device("cuda"))
+    logs = []
+    cb = mmu.src.callbacks.LambdaCallback(on_epoch_end=lambda e, l: logs.append(dict(l)))
+    trainer.train_loop(train, valid_generator=val, test_generator=test, epochs=2,
+                       steps_per_epoch=len(train), validation_steps=len(val), test_steps=len(test),
+                       callbacks=[cb], scheduler_step_on="batch", scheduler_metric=None)
+    assert len(logs) == 2
+    for k in ("epoch", "loss", "acc", "val_loss", "val_acc", "test_loss", "test_acc", "time"):
+        assert k in logs[0], k
+    assert np.isfinite(logs[1]["loss"]) and 0 <= logs[1]["acc"] <= 100
+
+
+def test_size_independent_properties(mmu):
+    """Full benchmark width (B=128, D=768, E=5, C=101) where the oracle is too slow:
+    (1) eval logits are identical whether a modality is dropped by index subset or passed whole;
+    (2) the text projection gradient is exactly zero without avg_pool (dead tokens);
+    (3) permuting the samples of a batch permutes the logits (attention is over the batch, so
+        this holds only jointly) -- bit-exact argmax, fp32 tolerance on values."""
+    torch.manual_seed(1)
+    m = mmu.FlavaFusionTransfomer(out_dim=5, num_classes=101, avg_pool=False, precision="bf16").cuda()
+    g = torch.Generator().manual_seed(2)
+    img, txt = torch.randn(128, 12, 768, generator=g).cuda(), torch.randn(128, 7, 768, generator=g).cuda()
+    y = torch.randint(0, 101, (128, 1), generator=g).repeat(1, 5).cuda()
+    m.eval()
+    with torch.no_grad():
+        a = m((img, txt))
+        b = m((img, txt), token_indices=(torch.arange(12), torch.arange(7)))
+        assert torch.equal(a, b)
+        perm = torch.randperm(128, generator=g).cuda()
+        c = m((img[perm], txt[perm]))
+        assert rel(c, a[perm]) < 2e-2
+    m.train(); m.zero_grad()
+    m.compute_loss(m((img, txt)), y).backward()
+    assert float(m.text_to_mm_projection.weight.grad.abs().max()) == 0.0
+    assert float(m.image_to_mm_projection.weight.grad.abs().max()) > 0.0

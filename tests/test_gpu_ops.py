@@ -1,0 +1,195 @@
+"""Operator-level parity: every CUDA kernel family against the CPU oracle / an fp32 torch
+reference on the same seeded inputs.  Everything goes through the C ABI (ctypes)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mmu():
+    import mmu_b200
+    return mmu_b200
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+CASES = [(256, 256, 128), (1000, 520, 200), (72, 104, 96), (136, 768, 3072)]
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("M,N,K", CASES)
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_gemm_store(mmu, dtype, tol, M, N, K, a_mn, b_mn):
+    A = rnd(M, K, seed=1).to(dtype)
+    B = rnd(N, K, seed=2, scale=1 / math.sqrt(K)).to(dtype)
+    bias = rnd(N, seed=3)
+    ref = A.float() @ B.float().t() + bias
+    Ad = (A.t().contiguous() if a_mn else A).cuda()
+    Bd = (B.t().contiguous() if b_mn else B).cuda()
+    out = mmu.ops.gemm(Ad, Bd, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn), bias=bias.cuda(),
+                       out_dtype=torch.float32)
+    assert rel(out.cpu(), ref) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_gemm_epilogues(mmu, dtype, tol):
+    from oracle import fusion
+    M, N, K = 300, 512, 192
+    A, B = rnd(M, K, seed=4).to(dtype), rnd(N, K, seed=5, scale=1 / math.sqrt(K)).to(dtype)
+    bias, resid = rnd(N, seed=6), rnd(M, N, seed=7)
+    z_ref = A.float() @ B.float().t() + bias
+    E = mmu._lib
+    z = torch.empty(M, N, device="cuda", dtype=dtype)
+    u = torch.empty(M, N, device="cuda", dtype=dtype)
+    mmu.ops.gemm(A.cuda(), B.cuda(), mode=E.EPI_QUICKGELU, out=z, out2=u, bias=bias.cuda())
+    assert rel(z.float().cpu(), z_ref) < tol
+    assert rel(u.float().cpu(), fusion.quick_gelu(z_ref)) < tol
+    out = torch.empty(M, N, device="cuda")
+    mmu.ops.gemm(A.cuda(), B.cuda(), mode=E.EPI_RESIDUAL, out=out, bias=bias.cuda(), aux=resid.cuda())
+    assert rel(out.cpu(), z_ref + resid) < tol
+    zz = rnd(M, N, seed=8, scale=2.0).to(dtype)
+    s = torch.sigmoid(1.702 * zz.float())
+    g_ref = (z_ref - bias) * (s * (1 + 1.702 * zz.float() * (1 - s)))
+    out = mmu.ops.gemm(A.cuda(), B.cuda(), mode=E.EPI_DGELU, aux=zz.cuda())
+    assert rel(out.float().cpu(), g_ref) < max(tol, 1e-4)
+    acc = torch.ones(M, N, device="cuda")
+    mmu.ops.gemm(A.cuda(), B.cuda(), mode=E.EPI_ATOMIC, out=acc, splits=3, alpha=0.5)
+    assert rel(acc.cpu(), 1 + 0.5 * (z_ref - bias)) < tol
+    # row remap: rows (b, l < 5) of a (B, 5) block land at b*9 + 2 + l
+    Am = rnd(40, K, seed=9).to(dtype)
+    dst = torch.zeros(8 * 9, N, device="cuda")
+    mmu.ops.gemm(Am.cuda(), B.cuda(), out=dst, seg=(5, 9, 2))
+    full = Am.float() @ B.float().t()
+    got = dst.cpu().view(8, 9, N)[:, 2:7].reshape(40, N)
+    assert rel(got, full) < tol
+    assert float(dst.cpu().view(8, 9, N)[:, :2].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("D", [64, 96, 768, 1024])
+def test_layernorm(mmu, D):
+    from oracle import fusion
+    M = 333
+    x, g, b = rnd(M, D, seed=1, scale=2.0) + 0.5, 1 + 0.1 * rnd(D, seed=2), 0.1 * rnd(D, seed=3)
+    y, mean, rstd = mmu.ops.layernorm_fwd(x.cuda(), g.cuda(), b.cuda())
+    assert rel(y.cpu(), fusion.layer_norm(x, g, b)) < 1e-5
+    ybf, _, _ = mmu.ops.layernorm_fwd(x.cuda(), g.cuda(), b.cuda(), out_dtype=torch.bfloat16)
+    assert rel(ybf.float().cpu(), fusion.layer_norm(x, g, b)) < 1e-2
+    dy = rnd(M, D, seed=4)
+    xr = x.clone().double().requires_grad_(True)
+    gr, br = g.clone().double().requires_grad_(True), b.clone().double().requires_grad_(True)
+    fusion.layer_norm(xr, gr, br).backward(dy.double())
+    prev = rnd(M, D, seed=5)
+    dx, dg, db, dx_lp, cs = mmu.ops.layernorm_bwd(dy.cuda(), x.cuda(), mean, rstd, g.cuda(),
+                                                  dx=prev.clone().cuda(), want_lp=True,
+                                                  want_colsum=True)
+    assert rel(dx.cpu(), prev.double() + xr.grad) < 1e-5
+    assert rel(dg.cpu(), gr.grad) < 1e-4 and rel(db.cpu(), br.grad) < 1e-4
+    assert rel(cs.cpu(), (prev.double() + xr.grad).sum(0)) < 1e-4
+    assert rel(dx_lp.float().cpu(), dx.cpu()) < 1e-2
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("B,L,D,H", [(4, 8, 64, 2), (9, 11, 96, 3), (128, 3, 768, 3), (70, 2, 48, 2)])
+def test_batch_axis_attention(mmu, dtype, tol, B, L, D, H):
+    """Against the oracle's restatement of nn.MultiheadAttention(batch_first=False) on (B, L, D)."""
+    hd = D // H
+    qkv = rnd(B * L, 3 * D, seed=1).to(dtype)
+    out, lse = mmu.ops.attention_fwd(qkv.cuda(), B, L, D, H)
+    q = qkv.double().requires_grad_(True)
+    t = q.view(B, L, 3, H, hd)
+    qq, kk, vv = (t[:, :, i].permute(1, 2, 0, 3) for i in range(3))  # (L, H, B, hd)
+    s = (qq / math.sqrt(hd)) @ kk.transpose(-1, -2)
+    o = (torch.softmax(s, -1) @ vv).permute(2, 0, 1, 3).reshape(B * L, D)
+    assert rel(out.float().cpu(), o) < tol
+    assert rel(lse.cpu().view(L, H, B), torch.logsumexp(s, -1)) < (1e-5 if dtype == torch.float32 else 1e-2)
+    do = rnd(B * L, D, seed=2).to(dtype)
+    o.backward(do.double())
+    dqkv = mmu.ops.attention_bwd(qkv.cuda(), out, do.cuda(), lse, B, L, D, H)
+    assert rel(dqkv.float().cpu(), q.grad) < tol * 2
+
+
+@pytest.mark.parametrize("N,E,C", [(500, 5, 101), (37, 2, 2), (64, 4, 10), (1001, 1, 101), (33, 3, 300)])
+def test_uncertainty_epilogue(mmu, N, E, C):
+    from oracle import fusion, uncertainty
+    logits = rnd(N, E, C, seed=N, scale=3.0)
+    g = torch.Generator().manual_seed(N + 1)
+    y = torch.randint(0, C, (N,), generator=g)
+    yt = torch.stack([torch.roll(y, e) for e in range(E)], 1).contiguous()  # distinct per head
+    # ---- train mode: per-head CE, gradient, per-row accuracy
+    dl, pred, scores, accum = mmu.ops.heads_uncertainty_epilogue(
+        logits.cuda(), yt.cuda(), 0, grad_scale=1.0 / (N * E), want_grad=True, want_pred=True,
+        want_scores=True)
+    a = mmu.ops.accum_to_dict(accum)
+    z = logits.double().requires_grad_(True)
+    loss = fusion.compute_loss(z, yt, eval=False)
+    loss.backward()
+    assert abs(a["loss_sum"] / a["n_rows"] - float(loss)) < 1e-5 * max(1.0, float(loss))
+    assert rel(dl.cpu(), z.grad) < 1e-4
+    assert a["n_rows"] == N * E and a["n_samples"] == N
+    ref_pred_rows = fusion.predictions(logits, eval=False)
+    assert a["n_correct_rows"] == int((ref_pred_rows == yt.reshape(-1)).sum())  # bit-exact
+    # ---- scores / histograms against the fp64 definitions
+    s = uncertainty.ensemble_scores(logits)
+    sc = scores.cpu().double()
+    assert torch.equal(pred[:, 1].cpu().long(), s["pred_prob"])  # bit-exact argmax
+    assert rel(sc[:, 0], s["conf"]) < 1e-5
+    assert float((sc[:, 1] - s["h_pred"]).abs().max()) < 1e-4
+    assert float((sc[:, 2] - s["h_exp"]).abs().max()) < 1e-4
+    assert float((sc[:, 3] - s["mi"]).abs().max()) < 1e-4
+    h = uncertainty.calibration_histograms(logits, y)
+    # the kernel's histogram is exactly the binning of the kernel's own scores ...
+    cb = uncertainty.bin_index(scores[:, 0].cpu(), 15)
+    assert torch.equal(torch.bincount(cb, minlength=15), torch.from_numpy(a["conf_count"]))
+    # ... and equals the oracle's unless a score sits within rounding distance of a bin edge
+    edge = ((s["conf"] * 15) - (s["conf"] * 15).round()).abs().min()
+    if float(edge) > 1e-4:
+        assert torch.equal(h["conf_count"], torch.from_numpy(a["conf_count"]))
+    # ---- eval mode: CE on the head-mean logits, argmax of the same
+    _, pred_e, _, acc_e = mmu.ops.heads_uncertainty_epilogue(logits.cuda(), y.cuda(), 1, want_pred=True)
+    ae = mmu.ops.accum_to_dict(acc_e)
+    assert abs(ae["loss_sum"] / N - float(fusion.compute_loss(logits.double(), y, eval=True))) < 1e-5
+    assert torch.equal(pred_e[:, 0].cpu().long(), s["pred_logit"])
+    assert ae["n_correct_rows"] == int((s["pred_logit"] == y).sum())
+    assert ae["n_correct_prob"] == int((s["pred_prob"] == y).sum())
+    assert torch.equal(torch.from_numpy(ae["conf_correct"]), h["conf_correct"]) or float(edge) <= 1e-4
+    ece = uncertainty.ece_from_bins(h["conf_count"], h["conf_correct"], h["conf_sum"])
+    m = mmu.metrics.UncertaintyMeter("cuda", C, E)
+    m.update(logits.cuda(), y.cuda())
+    assert abs(m.compute()["ece"] - ece) < 1e-4
+
+
+def test_adamw_flat(mmu, golden):
+    from oracle import optim
+    c = golden("adamw_cosine.pt")
+    n = 260  # 257 rounded up to a multiple of 4
+    p = torch.zeros(n); p[:257] = c["p0"]
+    pd, m, v = p.cuda(), torch.zeros(n).cuda(), torch.zeros(n).cuda()
+    shadow = torch.zeros(n, dtype=torch.bfloat16).cuda()
+    for t, g in enumerate(c["grads"]):
+        gg = torch.zeros(n); gg[:257] = g
+        mmu.ops.adamw_flat_step(pd, (gg * 4).cuda(), m, v, t + 1, c["lrs"][t], grad_scale=0.25,
+                                p_bf16=shadow)
+        assert float((pd.cpu()[:257] - c["traj"][t]).abs().max()) < 5e-6  # reference trajectory
+    assert float((m.cpu()[:257] - c["exp_avg"]).abs().max()) < 1e-6
+    assert torch.equal(shadow.cpu(), pd.cpu().to(torch.bfloat16))
+
+
+def test_mask_gather(mmu):
+    src = rnd(6, 9, 16, seed=3)
+    idx = torch.tensor([0, 3, 4, 8], dtype=torch.int32)
+    keep = torch.tensor([[1, 1], [0, 1], [1, 0], [1, 1], [0, 0], [1, 1]], dtype=torch.int32)
+    out = mmu.ops.mask_gather_tokens(src.cuda(), idx.cuda(), keep.cuda(), modality=0)
+    ref = src[:, idx.long()] * keep[:, 0].view(-1, 1, 1)
+    assert torch.equal(out.cpu(), ref)  # bit-exact masks / gather
+    out = mmu.ops.mask_gather_tokens(src.cuda(), None, keep.cuda(), modality=1, dtype=torch.bfloat16)
+    assert torch.equal(out.cpu(), (src * keep[:, 1].view(-1, 1, 1)).to(torch.bfloat16))

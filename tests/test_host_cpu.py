@@ -1,0 +1,251 @@
+"""CPU-side checks (no GPU needed): the C-ABI library loads and exports every declared symbol,
+the Python boundary mirrors the reference (keys, parameter order, seeded init, shaping, index
+sampling, LR schedule), fails loudly without a GPU, and the N>1 helpers work over gloo."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def mmu():
+    import mmu_b200
+    return mmu_b200
+
+
+def test_library_exports_every_declared_symbol(mmu):
+    header = open(os.path.join(ROOT, "include", "mmu_b200.h")).read()
+    declared = re.findall(r"MMU_API[^;(]*?\b(mmu_\w+)\s*\(", header)
+    assert len(declared) >= 16 and len(set(declared)) == len(declared)
+    for name in declared:
+        assert hasattr(mmu._lib.lib, name), name
+    assert sorted(declared) == sorted(mmu._lib.EXPORTS)
+    assert b"sm_100a" in mmu._lib.lib.mmu_version()
+    assert mmu._lib.lib.mmu_error_string(-7) == b"workspace too small"
+
+
+def test_struct_sizes_match_header(mmu):
+    import ctypes as C
+    assert C.sizeof(mmu._lib.MetricAccum) == (15 + 15 + 32 + 32 + 4) * 8 + (15 + 4) * 8
+    assert C.sizeof(mmu._lib.FlavaConfig) == 13 * 4
+    assert C.sizeof(mmu._lib.ParamEntry) == 96 + 8 + 8 + 12 + 4  # padded to 8
+    assert mmu._lib.ACC_OFF["conf_sum"] == 98
+
+
+def small_model(mmu, cls=False, **kw):
+    klass = mmu.FlavaFusionTransfomerwithCLSToken if cls else mmu.FlavaFusionTransfomer
+    args = dict(out_dim=2, num_classes=7, image_hidden_size=32, text_hidden_size=48,
+                multimodal_hidden_size=64, multimodal_num_attention_heads=2,
+                multimodal_num_hidden_layers=2, drop=0.0, avg_pool=False)
+    args.update(kw)
+    return klass(**args)
+
+
+def test_state_dict_keys_and_strict_load(mmu, golden):
+    c = golden("flava_small.pt")["plain_E2"]
+    m = small_model(mmu)
+    assert set(m.state_dict()) == set(c["state_dict"])
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(c["state_dict"][k].shape), k
+    m.load_state_dict(c["state_dict"], strict=True)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, c["state_dict"][k])
+    # parameters are views of one flat buffer, gradients of one flat gradient buffer
+    base = m._flat.data_ptr()
+    for p in m.parameters():
+        assert base <= p.data_ptr() < base + m._flat.numel() * 4
+        assert p.grad is not None and p.grad.shape == p.shape
+    c3 = golden("flava_small.pt")["cls_E3"]
+    m3 = small_model(mmu, cls=True, out_dim=3)
+    m3.load_state_dict(c3["state_dict"], strict=True)
+
+
+def test_seeded_init_and_parameter_order_match_reference(mmu, golden):
+    g = golden("init_seed123.pt")
+    for name, cls, kw in [("plain", False, dict(out_dim=2, num_classes=7)),
+                          ("cls", True, dict(out_dim=3, num_classes=5))]:
+        torch.manual_seed(123)
+        m = small_model(mmu, cls=cls, **kw)
+        assert [k for k, _ in m.named_parameters()] == g[name + "_param_order"]
+        for k, v in m.state_dict().items():
+            got = torch.stack([v.double().sum(), v.double().abs().sum()])
+            assert torch.allclose(got, g[name][k], rtol=1e-12, atol=1e-12), k
+
+
+def test_stage_ranges_partition_the_flat_buffer(mmu):
+    m = small_model(mmu)
+    ranges = m.stage_ranges()
+    assert len(ranges) == 2 + 2  # heads, two blocks, stem
+    order = sorted(ranges)
+    assert order[0][0] == 0
+    for (a0, a1), (b0, b1) in zip(order, order[1:]):
+        assert a1 <= b0
+    assert ranges[0][0] > ranges[-1][0]  # heads live at the end of the buffer, stem at the start
+
+
+def test_no_cpu_fallback(mmu):
+    m = small_model(mmu)
+    with pytest.raises(mmu._lib.MMUError):
+        m((torch.randn(2, 3, 32), torch.randn(2, 2, 48)))
+    with pytest.raises(TypeError):
+        m.half()
+    lin = torch.nn.Linear(4, 4)
+    with pytest.raises(ValueError):
+        mmu.FusedAdamW(lin.parameters())
+
+
+def test_product_shaping_bit_exact(mmu, golden):
+    c = golden("shaping.pt")
+    inp = c["inputs"]
+    ds = mmu.dataset
+    for mt in ["Vanilla", "MultiHead", "MIMO-shuffle-instance"]:
+        for phase in ["train", "eval"]:
+            torch.manual_seed(42)
+            (i2, t2), y2 = ds.data_forming_func_transformer((inp["img"], inp["txt"]), inp["y"], phase, mt)
+            g = c[f"transformer/{mt}/{phase}"]
+            assert torch.equal(i2, g["img"]) and torch.equal(t2, g["txt"]) and torch.equal(y2, g["y"])
+    for mt in ["Vanilla", "single-model-weight-sharing", "MultiHead", "MIMO-shuffle-instance",
+               "MIMO-shuffle-view", "MIMO-shuffle-all"]:
+        for phase in ["train", "eval"]:
+            torch.manual_seed(42)
+            x2, y2 = ds.data_forming_func(inp["x"], inp["yv"], phase, mt)
+            g = c[f"fmnist/{mt}/{phase}"]
+            assert torch.equal(x2, g["x"]) and torch.equal(y2, g["y"]), (mt, phase)
+    (pi, pt), pl = ds.collate_fn_flava(c["collate"]["ragged"])
+    assert torch.equal(pi, c["collate"]["img"]) and torch.equal(pt, c["collate"]["txt"])
+    assert torch.equal(pl, c["collate"]["labels"])
+
+
+def test_product_index_sampling_bit_exact(mmu, golden):
+    c = golden("input_sampling.pt")
+    np.random.seed(c["np_seed"]); torch.manual_seed(c["torch_seed"])
+    variants = mmu.robustness.robustness_variants(c["l_img"], c["l_txt"], c["n_repeats"])
+    assert len(variants) == 43
+    empty = torch.zeros(0, dtype=torch.int64)
+    for (ii, it), (gi, gt) in zip(variants[3:], c["draws"]):
+        assert torch.equal(ii if ii is not None else empty, gi)
+        assert torch.equal(it if it is not None else empty, gt)
+    from oracle import shaping
+    for mode in ("random", "guided"):
+        sc = torch.rand(64, 2, generator=torch.Generator().manual_seed(1))
+        a = mmu.robustness.modality_dropout_mask(64, 0.4, mode, sc, torch.Generator().manual_seed(7))
+        b = shaping.modality_dropout_mask(64, 0.4, mode, sc, torch.Generator().manual_seed(7))
+        assert torch.equal(a, b) and 0 < int((a == 0).sum()) < 64
+    torch.manual_seed(3); a = mmu.robustness.mask_level_variant(197, 40, "image", 4)
+    torch.manual_seed(3); b = shaping.mask_level_variant(197, 40, "image", 4)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and len(a[0]) == round(4 * 197 / 9)
+
+
+def test_cosine_schedule_matches_reference_lrs(mmu, golden):
+    c = golden("adamw_cosine.pt")
+    fn = mmu.optim.cosine_with_warmup_lambda(c["warmup"], c["total"])
+    for t, lr in enumerate(c["lrs"]):
+        assert abs(c["lr"] * fn(t) - lr) < 1e-12
+
+
+def test_fused_adamw_state_dict_layout(mmu):
+    m = small_model(mmu)
+    opt = mmu.FusedAdamW(m.parameters(), lr=3e-4)
+    sd = opt.state_dict()
+    n = len(list(m.parameters()))
+    assert sd["param_groups"][0]["params"] == list(range(n)) and len(sd["state"]) == n
+    assert sd["param_groups"][0]["betas"] == (0.9, 0.98) and sd["param_groups"][0]["eps"] == 1e-9
+    ref = torch.optim.AdamW([torch.nn.Parameter(p.detach().clone()) for p in m.parameters()], lr=3e-4)
+    ref.load_state_dict(sd)  # same layout as torch.optim.AdamW's
+    opt.load_state_dict(sd)
+    m.zero_grad(); opt.zero_grad()
+    assert all(p.grad is not None for p in m.parameters())  # views survive zero_grad
+
+
+def test_trainer_protocol_with_a_plain_torch_model(mmu, tmp_path):
+    """Model_ is model-agnostic host logic: drive it with a CPU nn.Module and torch SGD and
+    check logs, callback order, history.csv / checkpoint artefacts and the stopping rule."""
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = torch.nn.Linear(6, 3 * 2)
+        def forward(self, x):
+            img, txt = x
+            return self.fc(torch.cat([img.mean(1), txt.mean(1)], -1)).view(-1, 2, 3)
+        def compute_loss(self, y_hat, y, eval=False):
+            y_hat = y_hat.mean(1) if eval else y_hat.reshape(-1, 3)
+            return torch.nn.functional.cross_entropy(y_hat, y.reshape(-1))
+    def acc(y_pred, y_true, eval, dummy_dim=False):
+        y_pred = y_pred.mean(1) if eval else y_pred.reshape(-1, 3)
+        return (y_pred.argmax(1) == y_true.reshape(-1)).float().mean() * 100
+    torch.manual_seed(0)
+    from functools import partial
+    train, val, test = mmu.dataset.get_synthetic_flava(4, 12, 8, 8, l_img=3, l_txt=2, dim=3, num_classes=3)
+    net = Tiny()
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0)
+    H, events = {}, []
+    tl = mmu.src.training_loop
+    cbs = tl._construct_default_callbacks(net, opt, H, str(tmp_path), checkpoint_monitor="val_acc")
+    cbs.append(mmu.src.callbacks.LambdaCallback(
+        on_epoch_begin=lambda e, l: events.append(("eb", e)),
+        on_batch_end=lambda b, l: events.append(("be", b, set(l))),
+        on_backward_end=lambda b: events.append(("bw", b))))
+    for cb in cbs:
+        cb.set_save_path(str(tmp_path)); cb.set_model(net, ignore=False); cb.set_optimizer(opt)
+    trainer = mmu.Model_(net, opt, sched, partial(mmu.dataset.data_forming_func_transformer,
+                                                  model_type="MultiHead"), metrics=[acc], verbose=False)
+    trainer.to(torch.device("cpu"))
+    trainer.train_loop(train, valid_generator=val, test_generator=test, epochs=2,
+                       steps_per_epoch=len(train), validation_steps=len(val), test_steps=len(test),
+                       callbacks=cbs, scheduler_step_on="batch", scheduler_metric=None)
+    assert H["epoch"] == [1, 2] and len(H["loss"]) == 2 and "val_acc" in H and "test_loss" in H
+    for f in ("history.csv", "model_epoch_1.pt", "model_last_epoch.pt", "model_best_val.pt"):
+        assert os.path.exists(tmp_path / f), f
+    be = [e for e in events if e[0] == "be"]
+    assert be[0][2] >= {"batch", "size", "time", "batch_begin_time", "loss", "acc"}
+    assert events[0] == ("eb", 1) and events[1] == ("bw", 1)
+    with pytest.raises(NotImplementedError):
+        trainer.eval_loop(val, "val", mmbt=True)
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import mmu_b200
+    par, lib = mmu_b200.parallel, mmu_b200._lib
+    # metric accumulators: integer bins add exactly, doubles add
+    acc = torch.zeros(lib.ACC_WORDS, dtype=torch.int64)
+    acc[lib.ACC_OFF["conf_count"] + 3] = 10 + rank
+    acc[lib.ACC_OFF["n_samples"]] = 100 * (rank + 1)
+    acc[lib.ACC_INT_WORDS:].view(torch.float64)[0] = 0.5 + rank
+    par.all_reduce_accum(acc)
+    assert int(acc[lib.ACC_OFF["conf_count"] + 3]) == 21 and int(acc[lib.ACC_OFF["n_samples"]]) == 300
+    assert float(acc[lib.ACC_INT_WORDS:].view(torch.float64)[0]) == 2.0
+    # bucketed gradient all-reduce over stage ranges + folded 1/world averaging
+    flat = torch.arange(40, dtype=torch.float32) * (rank + 1)
+    works = par.all_reduce_ranges(flat, [(30, 40), (10, 30), (0, 10)], async_op=True)
+    for w in works:
+        w.wait()
+    assert torch.equal(flat * (1.0 / world), torch.arange(40, dtype=torch.float32) * 1.5)
+    p = torch.full((8,), float(rank))
+    par.broadcast_flat(p, 0)
+    assert float(p.abs().sum()) == 0.0
+    # sample sharding: contiguous, disjoint, covering
+    b, e = par.shard_range(1000003, rank, world)
+    t = torch.tensor([b, e])
+    gathered = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    assert int(gathered[0][0]) == 0 and int(gathered[-1][1]) == 1000003
+    assert all(int(gathered[i][1]) == int(gathered[i + 1][0]) for i in range(world - 1))
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")

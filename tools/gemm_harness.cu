@@ -167,7 +167,7 @@ int main(int argc, char** argv) {
       float ref = href[(size_t)m * N + n] + (c.bias ? hbias[n] : 0.f);
       float ref2 = 0.f;
       switch (c.mode) {
-        case EPI_QUICKGELU: ref2 = qgelu(bf16r(ref)); break;
+        case EPI_QUICKGELU: ref2 = qgelu(ref); break;
         case EPI_RESIDUAL: ref += haux_f[(size_t)orow * N + n]; break;
         case EPI_DGELU: ref *= qgelu_grad(__bfloat162float(haux_b[(size_t)m * N + n])); break;
         default: break;
