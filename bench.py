@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Food-101-shaped late fusion over synthetic FLAVA embeddings.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One STEP = one training step (data shaping, forward, CE over the 5 heads, backward, fused AdamW,
+`acc`) on a batch of B = 128 samples per GPU, followed by the robustness sweep of the same batch
+over 10 mask levels (token-subset gather, eval forward, fused uncertainty / ECE-histogram
+epilogue) -- BASELINE.json config[1] with config[2]'s per-batch sweep.  `value` = samples per
+second through that step (each sample is trained on once and swept over 10 levels), whole job
+over N GPUs (weak scaling: B per GPU fixed).  Rank 0 prints ONE JSON line.
+
+* `value`   : inputs resident in HBM when the timed region starts (CUDA events, max over ranks)
+* `e2e`     : same step through the public API (`Model_.train_step`, `robustness` sweep,
+              `UncertaintyMeter.compute`) from pinned HOST buffers: H2D of every batch and the
+              D2H reads of loss / acc / metric accumulators are inside the timed region
+* `roofline`: dominant kernel = gemm_bf16_tcgen05_kernel (tensor bound); achieved = algorithmic
+              FLOPs of the step's GEMM launches / their CUDA-event time, measured live here
+* `cpu_baseline` / `--impl reference`: the oracle port (the reference is pure Python + torch
+  CPU and cannot travel to the GPU box) timed on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(B=128, l_img=197, l_txt=40, D=768, heads=3, layers=3, E=5, C=101, levels=10,
+           lr=1e-3, wd=1e-3)
+CPU_SAMPLE_B = 16
+
+
+# ----------------------------------------------------------------------------- helpers
+def algorithmic_gemm_flops(B, L, D, layers, l_img, l_txt, train=True):
+    """GEMM FLOPs of one forward (2 proj + per layer in/out proj + c_fc + c_proj), x3 for a
+    training step (dgrad + wgrad); BASELINE.md section 4.6 minus attention and heads."""
+    M = B * L
+    fwd = 2 * (B * l_img) * D * D + 2 * (B * l_txt) * D * D + layers * (2 * M * D * 3 * D + 2 * M * D * D
+                                                                     + 2 * 2 * M * D * 4 * D)
+    if not train:
+        return fwd
+    # backward: every GEMM has a dgrad and a wgrad except the projections (no input gradient)
+    bwd = 2 * (fwd - 2 * (B * l_img) * D * D - 2 * (B * l_txt) * D * D) + 2 * (B * l_img) * D * D \
+        + 2 * (B * l_txt) * D * D
+    return fwd + bwd
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor_burst=p["bf16_tflops"],
+                    tensor_sustained=p["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        smax = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_host_batches(n, B, seed, pin):
+    out = []
+    for i in range(n):
+        g = torch.Generator().manual_seed(seed + i)
+        img = torch.randn(B, CFG["l_img"], CFG["D"], generator=g)
+        txt = torch.randn(B, CFG["l_txt"], CFG["D"], generator=g)
+        y = torch.randint(0, CFG["C"], (B,), generator=g)
+        if pin:
+            img, txt, y = img.pin_memory(), txt.pin_memory(), y.pin_memory()
+        out.append(((img, txt), y))
+    return out
+
+
+def level_variants(mmu, seed):
+    """10 mask levels of the image modality, host RNG, drawn per batch."""
+    torch.manual_seed(seed)
+    return [mmu.robustness.mask_level_variant(CFG["l_img"], CFG["l_txt"], "image", k, CFG["levels"])
+            for k in range(CFG["levels"])]
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch.distributed as dist
+    import mmu_b200 as mmu
+    from functools import partial
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = CFG["B"]
+
+    torch.manual_seed(42)
+    model = mmu.FlavaFusionTransfomer(out_dim=CFG["E"], num_classes=CFG["C"],
+                                      multimodal_num_attention_heads=CFG["heads"],
+                                      multimodal_num_hidden_layers=CFG["layers"], drop=0.0,
+                                      avg_pool=False, precision="bf16")
+    opt = mmu.FusedAdamW(model.parameters(), lr=CFG["lr"], betas=(0.9, 0.98), eps=1e-9,
+                         weight_decay=CFG["wd"])
+    sched = mmu.get_cosine_schedule_with_warmup(opt, 3 * 100, 100 * 100)
+    shaping = partial(mmu.dataset.data_forming_func_transformer, model_type="MultiHead")
+
+    def multihead5(x, y, phase):  # config[1] has 5 heads: tile the labels over all of them
+        x, y = shaping(x, y, phase)
+        return x, (y[:, :1].repeat(1, CFG["E"]) if phase == "train" else y)
+
+    trainer = mmu.Model_(model, opt, sched, multihead5, metrics=[mmu.acc], verbose=False)
+    trainer.to(dev)
+    ddp = mmu.parallel.DataParallel(model, opt) if world > 1 else None
+    meter = mmu.metrics.UncertaintyMeter(dev, CFG["C"], CFG["E"])
+
+    nb = 4
+    host = make_host_batches(nb, B, 1000 * (rank + 1), pin=True)
+    resident = [((i.to(dev), t.to(dev)), y.to(dev)) for (i, t), y in host]
+
+    def sweep(img, txt, y, variants):
+        model.eval()
+        with torch.no_grad():
+            for v in variants:
+                logits = mmu.robustness.forward_variant(model, img, txt, v)
+                meter.update(logits, y)
+        model.train()
+
+    def step_resident(i):
+        (img, txt), y = resident[i % nb]
+        yt = y.unsqueeze(1).repeat(1, CFG["E"])
+        opt.zero_grad()
+        logits = model((img, txt))
+        loss = model.compute_loss(logits, yt)
+        loss.backward()
+        opt.step()
+        mmu.acc(logits, yt, False, True)
+        sched.step()
+        sweep(img, txt, y, level_variants(mmu, i))
+
+    def step_e2e(i):
+        (img, txt), y = host[i % nb]
+        loss, info, _ = trainer.train_step((img, txt), y)         # H2D + D2H(loss, acc) inside
+        imgd, txtd, yd = img.to(dev, non_blocking=True), txt.to(dev, non_blocking=True), \
+            y.to(dev, non_blocking=True)                           # the sweep re-reads the host batch
+        sweep(imgd, txtd, yd, level_variants(mmu, i))
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, sampler=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.start()
+        n0 = mmu._lib.lib.mmu_launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        launches = mmu._lib.lib.mmu_launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, launches, clocks
+
+    model.train()
+    for i in range(args.warmup):
+        step_resident(i)
+    ms, launches, clocks = timed(step_resident, args.steps, ClockSampler(local) if rank == 0 else None)
+    meter.all_reduce()
+    summary = meter.compute()
+    for i in range(max(1, args.warmup // 2)):
+        step_e2e(i)
+    meter.reset()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    meter.all_reduce()
+    meter.compute()  # D2H read of the sweep result
+    per_step = ms / args.steps
+    value = world * B / (per_step / 1e3)
+    e2e_value = world * B / (ms_e2e / args.steps / 1e3)
+
+    # ---- roofline of the dominant kernel, measured live: every GEMM launch of one train step
+    roof = cpu = hbm_kernels = None
+    if rank == 0:
+        roof, hbm_kernels = measure_rooflines(mmu, dev)
+        if world == 1:
+            cpu = cpu_reference(steps=1, warmup=1)
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        h2d = sum(t.numel() * t.element_size() for t in (host[0][0][0], host[0][0][1], host[0][1])) * 2
+        line = {
+            "metric": "train+robustness-eval samples/sec", "value": round(value, 2),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(per_step, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1] Food-101-shaped FLAVA late fusion, 5 heads, 101 classes"
+                                   " + configs[2] per-batch 10-level mask sweep",
+                       "per_gpu_batch": B, "global_batch": B * world, "l_img": CFG["l_img"],
+                       "l_txt": CFG["l_txt"], "D": CFG["D"], "layers": CFG["layers"],
+                       "heads": CFG["heads"], "E": CFG["E"], "C": CFG["C"],
+                       "mask_levels": CFG["levels"], "optimizer": "fused AdamW",
+                       "parallelism": f"dp{world}", "dead_tokens": "computed (as written)",
+                       "l2": "working set ~6 GB/step >> 126 MB L2, inputs rotate over 4 batches"},
+            "e2e": {"value": round(e2e_value, 2), "unit": "samples/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "hbm_kernels": hbm_kernels,
+            "cpu_baseline": cpu,
+            "sweep_summary": {k: summary[k] for k in ("acc", "ece", "h_pred", "mi", "n_samples")},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_rooflines(mmu, dev):
+    """Times, with CUDA events on the launching stream, (a) the GEMM launches of one training
+    step in isolation (the dominant kernel, tensor bound) and (b) the two HBM-bound kernels."""
+    pk = peaks()
+    B, L, D = CFG["B"], CFG["l_img"] + CFG["l_txt"], CFG["D"]
+    M = B * L
+    E_ = mmu._lib
+    bf = torch.bfloat16
+    x768 = torch.randn(M, D, device=dev).to(bf)
+    x2304 = torch.randn(M, 3 * D, device=dev).to(bf)
+    x3072 = torch.randn(M, 4 * D, device=dev).to(bf)
+    w = {n: (torch.randn(n, D, device=dev) * 0.02).to(bf) for n in (3 * D, 4 * D, D)}  # keyed by out-features
+    w_proj = (torch.randn(D, 4 * D, device=dev) * 0.02).to(bf)
+    out768f = torch.empty(M, D, device=dev)
+    resid = torch.randn(M, D, device=dev)
+    o2304, o3072, o3072b, o768 = (torch.empty(M, n, device=dev, dtype=bf) for n in (3 * D, 4 * D, 4 * D, D))
+    gw = {s: torch.zeros(*s, device=dev) for s in ((3 * D, D), (4 * D, D), (D, 4 * D), (D, D))}
+    bias = {n: torch.zeros(n, device=dev) for n in (D, 3 * D, 4 * D)}
+    g = mmu.ops.gemm
+
+    def layer_gemms():
+        # forward
+        g(x768, w[3 * D], out=o2304, bias=bias[3 * D])
+        g(x768, w[D], mode=E_.EPI_RESIDUAL, out=out768f, aux=resid, bias=bias[D])
+        g(x768, w[4 * D], mode=E_.EPI_QUICKGELU, out=o3072, out2=o3072b, bias=bias[4 * D])
+        g(x3072, w_proj, mode=E_.EPI_RESIDUAL, out=out768f, aux=resid, bias=bias[D])
+        # backward: dgrad
+        g(x768, w_proj, b_mn_major=True, mode=E_.EPI_DGELU, out=o3072, aux=o3072b)
+        g(x3072, w[4 * D], b_mn_major=True, out=o768)
+        g(x768, w[D], b_mn_major=True, out=o768)
+        g(x2304, w[3 * D], b_mn_major=True, out=o768)
+        # backward: wgrad (split-K atomics)
+        g(x768, x3072, a_mn_major=True, b_mn_major=True, mode=E_.EPI_ATOMIC, out=gw[(D, 4 * D)], splits=8)
+        g(x3072, x768, a_mn_major=True, b_mn_major=True, mode=E_.EPI_ATOMIC, out=gw[(4 * D, D)], splits=2)
+        g(x768, x768, a_mn_major=True, b_mn_major=True, mode=E_.EPI_ATOMIC, out=gw[(D, D)], splits=8)
+        g(x2304, x768, a_mn_major=True, b_mn_major=True, mode=E_.EPI_ATOMIC, out=gw[(3 * D, D)], splits=3)
+
+    flops_layer = 3 * (2 * M * D * 3 * D + 2 * M * D * D + 2 * 2 * M * D * 4 * D)
+    for _ in range(3):
+        layer_gemms()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    n0 = mmu._lib.lib.mmu_launch_count()
+    e0.record()
+    for _ in range(reps):
+        layer_gemms()
+    e1.record()
+    torch.cuda.synchronize()
+    n_launch = mmu._lib.lib.mmu_launch_count() - n0
+    ms = e0.elapsed_time(e1) / reps
+    tf = flops_layer / (ms * 1e-3) / 1e12
+    roof = {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": round(tf, 1),
+            "peak": pk["tensor_sustained"], "unit": "TFLOP/s", "frac": round(tf / pk["tensor_sustained"], 3),
+            "peak_burst": pk["tensor_burst"], "frac_of_burst": round(tf / pk["tensor_burst"], 3),
+            "peak_source": pk["source"] + " (sustained cuBLAS bf16; kernel timed inside a long loop)",
+            "launches_timed": int(n_launch // reps), "avg_launch_us": round(ms * 1e3 / (n_launch / reps), 1),
+            "flops_per_launch_avg": flops_layer / (n_launch / reps), "traffic": None,
+            "note": "12 GEMM launches of one transformer block's fwd+bwd (M=30336), operands > L2"}
+
+    # ---- HBM-bound kernels
+    hbm = []
+    n = 22_843_392 // 4 * 4
+    p, gr, m_, v_ = (torch.randn(n, device=dev) for _ in range(4))
+    v_.abs_()
+    sh = torch.empty(n, device=dev, dtype=bf)
+    for _ in range(3):
+        mmu.ops.adamw_flat_step(p, gr, m_, v_, 1, 1e-3, p_bf16=sh)
+    e0.record()
+    for i in range(20):
+        mmu.ops.adamw_flat_step(p, gr, m_, v_, i + 2, 1e-3, p_bf16=sh)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 20 * 1e3
+    gbs = 28.0 * n / (us * 1e-6) / 1e9
+    hbm.append({"kernel": "adamw_kernel", "bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"],
+                "unit": "GB/s", "frac": round(gbs / pk["hbm"], 3), "bytes_per_param": 28,
+                "us_per_launch": round(us, 1), "note": "22.8 M params (274 MB/launch of p,g,m,v; > L2)"})
+    N = 1 << 20
+    logits = torch.randn(N, CFG["E"], CFG["C"], device=dev)
+    y = torch.randint(0, CFG["C"], (N,), device=dev)
+    acc = mmu.ops.new_accum(dev)
+    for _ in range(2):
+        mmu.ops.heads_uncertainty_epilogue(logits, y, 1, accum=acc)
+    e0.record()
+    for _ in range(5):
+        mmu.ops.heads_uncertainty_epilogue(logits, y, 1, accum=acc)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 5 * 1e3
+    byts = N * (CFG["E"] * CFG["C"] * 4 + 8)
+    gbs = byts / (us * 1e-6) / 1e9
+    hbm.append({"kernel": "ce_uncertainty_kernel", "bound": "hbm", "achieved": round(gbs, 1),
+                "peak": pk["hbm"], "unit": "GB/s", "frac": round(gbs / pk["hbm"], 3),
+                "bytes_per_sample": CFG["E"] * CFG["C"] * 4 + 8, "us_per_launch": round(us, 1),
+                "note": "1 Mi samples x (5 x 101) logits, eval mode (2.1 GB/launch; > L2)"})
+    return roof, hbm
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_reference(steps, warmup):
+    """The oracle port of the reference's CPU path (torch CPU, fp32, all host threads): one step =
+    train step + 10-level sweep on a bounded sample of B=16 (attention cost is ~linear in B at
+    this size).  Returns the cpu_baseline object."""
+    from oracle import fusion, optim, shaping, uncertainty
+    import mmu_b200 as mmu  # only to build the parameter dictionary with the reference's init
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    B = CPU_SAMPLE_B
+    torch.manual_seed(42)
+    model = mmu.FlavaFusionTransfomer(out_dim=CFG["E"], num_classes=CFG["C"], avg_pool=False)
+    P = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    m = {k: torch.zeros_like(v) for k, v in P.items()}
+    v = {k: torch.zeros_like(vv) for k, vv in P.items()}
+    (img, txt), y = make_host_batches(1, B, 7, pin=False)[0]
+    yt = y.unsqueeze(1).repeat(1, CFG["E"])
+
+    def step(i):
+        nonlocal P, m, v
+        logits, loss, grads = fusion.loss_and_grads(P, (img, txt), yt, CFG["heads"], False)
+        for k in P:
+            P[k], m[k], v[k] = optim.adamw_step(P[k], grads[k], m[k], v[k], i + 1, CFG["lr"])
+        fusion.acc(logits, yt, False, True)
+        torch.manual_seed(i)
+        with torch.no_grad():
+            for k in range(CFG["levels"]):
+                var = shaping.mask_level_variant(CFG["l_img"], CFG["l_txt"], "image", k, CFG["levels"])
+                s_img, s_txt = shaping.apply_variant(img, txt, var)
+                lg = fusion.flava_fusion_forward(P, (s_img, s_txt), CFG["heads"], False)
+                uncertainty.calibration_histograms(lg, y)
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(B / dt, 3), "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"B={B} of {CFG['B']} per step, {steps} timed step(s); torch-CPU fp32 oracle "
+                      f"port of the reference modules (reference itself is Python and cannot travel)",
+            "s_per_step": round(dt, 3)}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    cpu = cpu_reference(steps, warm)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    line = {"impl": "reference", "metric": "train+robustness-eval samples/sec", "value": cpu["value"],
+            "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": cpu["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1] train step + configs[2] 10-level mask sweep per batch",
+                       "per_gpu_batch": CPU_SAMPLE_B, "note": "CPU arm: rank 0 only"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,8 @@ extern "C" {
 
 MMU_API const char* mmu_version(void);
 MMU_API const char* mmu_error_string(int code);
+/* Number of CUDA kernels this library has launched so far in this process (host counter). */
+MMU_API long long mmu_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Dense contraction  C[M,N] = epilogue( sum_k A(m,k) B(n,k) )

@@ -15,7 +15,7 @@ F32, BF16 = 0, 1
 EPI_STORE, EPI_QUICKGELU, EPI_RESIDUAL, EPI_DGELU, EPI_ATOMIC = 0, 1, 2, 3, 4
 
 EXPORTS = [
-    "mmu_version", "mmu_error_string", "mmu_gemm", "mmu_mask_gather_tokens", "mmu_layernorm_fwd",
+    "mmu_version", "mmu_error_string", "mmu_launch_count", "mmu_gemm", "mmu_mask_gather_tokens", "mmu_layernorm_fwd",
     "mmu_layernorm_bwd", "mmu_batchaxis_attention_fwd", "mmu_batchaxis_attention_bwd",
     "mmu_heads_uncertainty_epilogue", "mmu_adamw_flat_step", "mmu_flava_param_count",
     "mmu_flava_param_table", "mmu_flava_workspace_bytes", "mmu_flava_num_stages",
@@ -76,6 +76,7 @@ def _load():
     lib.mmu_version.restype = C.c_char_p
     lib.mmu_error_string.restype = C.c_char_p
     lib.mmu_error_string.argtypes = [i]
+    lib.mmu_launch_count.restype = ll
     lib.mmu_gemm.argtypes = [i, vp, ll, i, vp, ll, i, i, i, i, i, C.POINTER(GemmEpilogue), vp]
     lib.mmu_mask_gather_tokens.argtypes = [vp, vp, i, i, i, i, vp, i, vp, i, vp]
     lib.mmu_layernorm_fwd.argtypes = [vp, vp, vp, vp, i, vp, vp, i, i, vp]

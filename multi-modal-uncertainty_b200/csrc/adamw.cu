@@ -93,6 +93,7 @@ int adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, size_
     fprintf(stderr, "mmu: adamw launch failed: %s\n", cudaGetErrorString(err));
     return MMU_ERR_CUDA;
   }
+  count_launch();
   return 0;
 }
 

@@ -370,7 +370,9 @@ int attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int 
     attn_fwd_kernel<float><<<grid, THREADS, smem, stream>>>(static_cast<const float*>(qkv),
                                                             static_cast<float*>(out), lse, B, L, D, H);
   }
-  return cudaGetLastError() == cudaSuccess ? 0 : MMU_ERR_CUDA;
+  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+  count_launch();
+  return 0;
 }
 
 int attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
@@ -401,7 +403,9 @@ int attention_bwd(const void* qkv, const void* out, const void* dout, const floa
         static_cast<const T*>(qkv), static_cast<const T*>(dout), lse, delta_ws,
         static_cast<T*>(dqkv), B, L, D, H);
   }
-  return cudaGetLastError() == cudaSuccess ? 0 : MMU_ERR_CUDA;
+  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+  count_launch(2);
+  return 0;
 }
 
 }  // namespace mmu

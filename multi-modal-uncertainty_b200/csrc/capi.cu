@@ -32,6 +32,8 @@ extern "C" {
 
 const char* mmu_version(void) { return "mmu_b200 0.1 (sm_100a)"; }
 
+long long mmu_launch_count(void) { return launch_count(); }
+
 const char* mmu_error_string(int code) {
   switch (code) {
     case MMU_OK: return "ok";

@@ -14,6 +14,9 @@
 #define MMU_ERR_WORKSPACE (-7)  // workspace too small
 
 namespace mmu {
+// number of kernels this library has launched in this process (host-side counter)
+void count_launch(int n = 1);
+long long launch_count();
 int sm_count();
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, long long inner, long long outer,
                       long long ld, int box_inner, int box_outer);

@@ -344,6 +344,7 @@ int launch(const float* logits, const long long* labels, int ls, int les, int N,
     fprintf(stderr, "mmu: ce_uncertainty launch failed: %s\n", cudaGetErrorString(err));
     return MMU_ERR_CUDA;
   }
+  count_launch();
   return 0;
 }
 

@@ -1,6 +1,7 @@
 // Host side of the tcgen05 GEMM: tensor-map encoding and launch.
 #include "gemm_tcgen05.cuh"
 
+#include <atomic>
 #include <cstdio>
 #include <mutex>
 
@@ -51,6 +52,10 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, long long inner, long 
   return r == CUDA_SUCCESS ? 0 : MMU_ERR_TMAP;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -80,6 +85,7 @@ int launch_mode(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
     fprintf(stderr, "mmu: gemm launch failed: %s\n", cudaGetErrorString(err));
     return MMU_ERR_CUDA;
   }
+  count_launch();
   return 0;
 }
 }  // namespace

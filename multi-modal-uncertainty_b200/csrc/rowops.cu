@@ -25,6 +25,7 @@ constexpr int THREADS = WARPS * 32;
               cudaGetErrorString(err__));                                       \
       return MMU_ERR_CUDA;                                                      \
     }                                                                           \
+    count_launch();                                                             \
   } while (0)
 
 template <typename T>

@@ -162,6 +162,7 @@ int launch(const float* A, long long lda, const float* B, long long ldb, const G
     fprintf(stderr, "mmu: sgemm launch failed: %s\n", cudaGetErrorString(err));
     return MMU_ERR_CUDA;
   }
+  count_launch();
   return 0;
 }
 

@@ -60,7 +60,14 @@ def test_fp32_matches_reference_goldens(mmu, golden, name):
             assert float((p.grad.cpu() - g).abs().max()) < 1e-3 * scale, k
     opt.step()
     for k, p in m.named_parameters():
-        assert float((p.detach().cpu() - c["params_after_adamw"][k]).abs().max()) < 2e-5, k
+        # Adam divides by sqrt(v): where the reference gradient is rounding noise (e.g. the key
+        # bias, whose gradient is analytically zero) the step is +-lr by the SIGN of that noise,
+        # so only well-conditioned elements are comparable.
+        g = c["grads"][k]
+        ok = g.abs() > 1e-3 * g.abs().max().clamp_min(1e-12)
+        d = (p.detach().cpu() - c["params_after_adamw"][k]).abs()
+        assert float(d[ok].max() if ok.any() else 0.0) < 2e-5, k
+        assert float(d.max()) < 2.1e-3, k  # never more than one lr-sized step
     # eval protocol: CE on head-mean logits, acc on the same
     m.load_state_dict(c["state_dict"])
     m.eval()
