@@ -220,6 +220,11 @@ def run_gpu(args):
     ms, launches, clocks = timed(step_resident, args.steps, ClockSampler(local) if rank == 0 else None)
     meter.all_reduce()
     summary = meter.compute()
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps,
+                              "gpu_launches": int(launches)}))
+        return
     for i in range(max(1, args.warmup // 2)):
         step_e2e(i)
     meter.reset()
@@ -437,6 +442,8 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--profile", action="store_true",
+                    help="skip the e2e / roofline / CPU legs (short run for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -110,12 +110,19 @@ MMU_API int mmu_layernorm_bwd(const void* dy, int dy_dtype, const float* x, cons
 
 /* Batch-axis multi-head attention (src/model.py:193,205-207: nn.MultiheadAttention with
  * batch_first=False fed (B, L, D), i.e. attention across the mini-batch, per token position).
- * qkv: [B*L, 3D] packed q|k|v; out: [B*L, D]; lse: fp32[L*H*B]; B <= 256. */
-MMU_API int mmu_batchaxis_attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int L,
-                                int D, int H, void* stream);
+ * qkv: [B*L, 3D] packed q|k|v; out: [B*L, D].
+ * Tensor-core path (dtype MMU_BF16, head_dim % 64 == 0, probs/scores non-NULL): batched tcgen05
+ * GEMMs over the L*H (position, head) problems; probs: bf16 [L*H, B, Bp] written by the forward and
+ * read by the backward, scores: fp32 scratch, dprobs: bf16 scratch of the same shape (Bp = B
+ * rounded up to 8).  Otherwise (fp32, or NULL buffers): fp32 SIMT kernels, B <= 256, which need
+ * lse fp32[L*H*B] (forward output) and delta_ws fp32[L*H*B]. */
+MMU_API int mmu_batchaxis_attention_fwd(const void* qkv, void* out, float* lse, void* probs,
+                                        float* scores, int dtype, int B, int L, int D, int H,
+                                        void* stream);
 MMU_API int mmu_batchaxis_attention_bwd(const void* qkv, const void* out, const void* dout,
-                                const float* lse, float* delta_ws /* fp32[L*H*B] */, void* dqkv,
-                                int dtype, int B, int L, int D, int H, void* stream);
+                                        const float* lse, float* delta_ws, const void* probs,
+                                        float* scores, void* dprobs, void* dqkv, int dtype, int B,
+                                        int L, int D, int H, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused softmax / cross-entropy (+gradient) / accuracy / uncertainty / calibration epilogue.

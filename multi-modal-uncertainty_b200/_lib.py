@@ -81,8 +81,8 @@ def _load():
     lib.mmu_mask_gather_tokens.argtypes = [vp, vp, i, i, i, i, vp, i, vp, i, vp]
     lib.mmu_layernorm_fwd.argtypes = [vp, vp, vp, vp, i, vp, vp, i, i, vp]
     lib.mmu_layernorm_bwd.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, i, vp, vp, vp, i, i, vp]
-    lib.mmu_batchaxis_attention_fwd.argtypes = [vp, vp, vp, i, i, i, i, i, vp]
-    lib.mmu_batchaxis_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]
+    lib.mmu_batchaxis_attention_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, vp]
+    lib.mmu_batchaxis_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]
     lib.mmu_heads_uncertainty_epilogue.argtypes = [vp, vp, i, i, i, i, i, i, f, vp, vp, vp, vp, vp]
     lib.mmu_adamw_flat_step.argtypes = [vp, vp, vp, vp, vp, C.c_size_t, f, f, f, f, f, i, f, vp]
     cfgp = C.POINTER(FlavaConfig)

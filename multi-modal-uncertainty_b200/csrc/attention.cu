@@ -18,6 +18,7 @@
 #include <cstdio>
 
 #include "common.h"
+#include "gemm_api.h"
 #include "kernels.h"
 
 namespace mmu {
@@ -353,11 +354,152 @@ int check(int B, int D, int H) {
   return 0;
 }
 
+
+// ============================================================ tensor-core path (bf16)
+// Each (token position l, head h) pair is one batch entry of the batched tcgen05 GEMM
+// (3-D tensor maps over the packed qkv buffer):
+//   forward : S = (Q K^T)/sqrt(hd) [GEMM, fp32 out] -> row softmax -> P (bf16, kept for the
+//             backward) -> O = P V [GEMM, V as MN-major operand]
+//   backward: dP = dO V^T [GEMM] -> dS = P (dP - <dP,P>) / sqrt(hd) (row kernel) ->
+//             dV = P^T dO, dK = dS^T Q, dQ = dS K  [3 GEMMs, transposes via MN-major descriptors]
+// S/P/dP/dS are only B x B per batch entry (23-47 MB per layer at B = 128), so keeping them in
+// HBM costs far less than the qkv traffic itself.
+namespace tc {
+
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, int rows, int B,
+                    int Bp) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* s = S + static_cast<size_t>(row) * Bp;
+  float m = -INFINITY;
+  for (int c = lane; c < B; c += 32) m = fmaxf(m, s[c]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int c = lane; c < B; c += 32) sum += __expf(s[c] - m);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  __nv_bfloat16* p = P + static_cast<size_t>(row) * Bp;
+  for (int c = lane; c < Bp; c += 32)
+    p[c] = __float2bfloat16_rn(c < B ? __expf(s[c] - m) * inv : 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+softmax_bwd_rows_kernel(const float* __restrict__ dP, const __nv_bfloat16* __restrict__ P,
+                        __nv_bfloat16* __restrict__ dS, int rows, int B, int Bp, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* g = dP + static_cast<size_t>(row) * Bp;
+  const __nv_bfloat16* p = P + static_cast<size_t>(row) * Bp;
+  float delta = 0.f;
+  for (int c = lane; c < B; c += 32) delta += g[c] * __bfloat162float(p[c]);
+  delta = warp_sum(delta);
+  __nv_bfloat16* o = dS + static_cast<size_t>(row) * Bp;
+  for (int c = lane; c < Bp; c += 32)
+    o[c] = __float2bfloat16_rn(c < B ? __bfloat162float(p[c]) * (g[c] - delta) * scale : 0.f);
+}
+
+struct Views {
+  BatchedOperand q_k, k_k, v_k;     // K-major views of the q / k / v thirds (rows = b, K = d)
+  BatchedOperand q_mn, k_mn, v_mn;  // MN-major views (MN = d, K = b)
+};
+
+BatchedOperand qkv_view(const void* qkv, int B, int L, int D, int H, int third, int mn) {
+  BatchedOperand o{};
+  o.base = qkv;
+  o.inner = 3LL * D; o.mid = L; o.outer = B;
+  o.mid_stride = 3LL * D; o.outer_stride = 3LL * D * L;
+  o.mn_major = mn; o.hdiv = H; o.hstride = D / H; o.col0 = third * D;
+  return o;
+}
+BatchedOperand act_view(const void* x, int B, int L, int D, int H, int mn) {  // (B, L, D) tensors
+  BatchedOperand o{};
+  o.base = x;
+  o.inner = D; o.mid = L; o.outer = B;
+  o.mid_stride = D; o.outer_stride = static_cast<long long>(D) * L;
+  o.mn_major = mn; o.hdiv = H; o.hstride = D / H; o.col0 = 0;
+  return o;
+}
+BatchedOperand sq_view(const void* p, int G, int B, int Bp, int mn) {  // [G][B][Bp] matrices
+  BatchedOperand o{};
+  o.base = p;
+  o.inner = Bp; o.mid = G; o.outer = B;
+  o.mid_stride = static_cast<long long>(B) * Bp; o.outer_stride = Bp;
+  o.mn_major = mn; o.hdiv = 1; o.hstride = 0; o.col0 = 0;
+  return o;
+}
+
+GemmEpilogue store_epi(void* out, int bf16, long long ld, float alpha) {
+  GemmEpilogue e{};
+  e.mode = EPI_STORE; e.out_bf16 = bf16; e.out = out; e.ld_out = ld; e.alpha = alpha;
+  return e;
+}
+
+bool eligible(int dtype, int B, int D, int H, const void* probs, const void* scores) {
+  return dtype == DT_BF16 && probs != nullptr && scores != nullptr && (D / H) % 64 == 0 &&
+         D % 8 == 0 && B >= 1;
+}
+
+int fwd(const void* qkv, void* out, void* probs, float* scores, int B, int L, int D, int H,
+        cudaStream_t st) {
+  const int hd = D / H, G = L * H, Bp = (B + 7) / 8 * 8;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  int rc = gemm_bf16_batched_launch(qkv_view(qkv, B, L, D, H, 0, 0), qkv_view(qkv, B, L, D, H, 1, 0),
+                                    G, B, Bp, hd, store_epi(scores, 0, Bp, scale), 1, 0,
+                                    static_cast<long long>(B) * Bp, st);
+  if (rc) return rc;
+  const int rows = G * B;
+  softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(scores, static_cast<__nv_bfloat16*>(probs),
+                                                      rows, B, Bp);
+  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+  count_launch();
+  return gemm_bf16_batched_launch(sq_view(probs, G, B, Bp, 0), qkv_view(qkv, B, L, D, H, 2, 1), G, B,
+                                  hd, B, store_epi(out, 1, static_cast<long long>(L) * D, 1.0f), H,
+                                  hd, D, st);
+}
+
+int bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
+        void* dqkv, int B, int L, int D, int H, cudaStream_t st) {
+  const int hd = D / H, G = L * H, Bp = (B + 7) / 8 * 8;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  // dP = dO V^T
+  int rc = gemm_bf16_batched_launch(act_view(dout, B, L, D, H, 0), qkv_view(qkv, B, L, D, H, 2, 0),
+                                    G, B, Bp, hd, store_epi(scores, 0, Bp, 1.0f), 1, 0,
+                                    static_cast<long long>(B) * Bp, st);
+  if (rc) return rc;
+  const int rows = G * B;
+  softmax_bwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(
+      scores, static_cast<const __nv_bfloat16*>(probs), static_cast<__nv_bfloat16*>(dprobs), rows, B,
+      Bp, scale);
+  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+  count_launch();
+  __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(dqkv);
+  const long long ld = 3LL * D * L;
+  // dV = P^T dO
+  rc = gemm_bf16_batched_launch(sq_view(probs, G, B, Bp, 1), act_view(dout, B, L, D, H, 1), G, B, hd,
+                                B, store_epi(dq + 2 * D, 1, ld, 1.0f), H, hd, 3LL * D, st);
+  if (rc) return rc;
+  // dK = dS^T Q
+  rc = gemm_bf16_batched_launch(sq_view(dprobs, G, B, Bp, 1), qkv_view(qkv, B, L, D, H, 0, 1), G, B,
+                                hd, B, store_epi(dq + D, 1, ld, 1.0f), H, hd, 3LL * D, st);
+  if (rc) return rc;
+  // dQ = dS K
+  return gemm_bf16_batched_launch(sq_view(dprobs, G, B, Bp, 0), qkv_view(qkv, B, L, D, H, 1, 1), G, B,
+                                  hd, B, store_epi(dq, 1, ld, 1.0f), H, hd, 3LL * D, st);
+}
+
+}  // namespace tc
+
 }  // namespace attn
 
-int attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int L, int D, int H,
-                  cudaStream_t stream) {
+int attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* scores, int dtype,
+                  int B, int L, int D, int H, cudaStream_t stream) {
   using namespace attn;
+  if (tc::eligible(dtype, B, D, H, probs, scores))
+    return tc::fwd(qkv, out, probs, scores, B, L, D, H, stream);
+  if (lse == nullptr) return MMU_ERR_ARG;
   if (int rc = check(B, D, H)) return rc;
   const size_t smem = smem_bytes(B);
   dim3 grid(L * H, (B + TQ - 1) / TQ);
@@ -376,9 +518,12 @@ int attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int 
 }
 
 int attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
-                  float* delta_ws, void* dqkv, int dtype, int B, int L, int D, int H,
-                  cudaStream_t stream) {
+                  float* delta_ws, const void* probs, float* scores, void* dprobs, void* dqkv,
+                  int dtype, int B, int L, int D, int H, cudaStream_t stream) {
   using namespace attn;
+  if (tc::eligible(dtype, B, D, H, probs, scores) && dprobs != nullptr)
+    return tc::bwd(qkv, dout, probs, scores, dprobs, dqkv, B, L, D, H, stream);
+  if (lse == nullptr || delta_ws == nullptr) return MMU_ERR_ARG;
   if (int rc = check(B, D, H)) return rc;
   const size_t smem = smem_bytes(B);
   dim3 grid(L * H, (B + TQ - 1) / TQ);

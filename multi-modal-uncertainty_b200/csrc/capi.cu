@@ -98,19 +98,19 @@ int mmu_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float*
                        dbeta, dcolsum, M, D, S(stream));
 }
 
-int mmu_batchaxis_attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int L,
-                                int D, int H, void* stream) {
-  if (qkv == nullptr || out == nullptr || lse == nullptr) return MMU_ERR_ARG;
-  return attention_fwd(qkv, out, lse, dtype, B, L, D, H, S(stream));
+int mmu_batchaxis_attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* scores,
+                                int dtype, int B, int L, int D, int H, void* stream) {
+  if (qkv == nullptr || out == nullptr) return MMU_ERR_ARG;
+  return attention_fwd(qkv, out, lse, probs, scores, dtype, B, L, D, H, S(stream));
 }
 
 int mmu_batchaxis_attention_bwd(const void* qkv, const void* out, const void* dout,
-                                const float* lse, float* delta_ws, void* dqkv, int dtype, int B,
-                                int L, int D, int H, void* stream) {
-  if (qkv == nullptr || out == nullptr || dout == nullptr || lse == nullptr ||
-      delta_ws == nullptr || dqkv == nullptr)
-    return MMU_ERR_ARG;
-  return attention_bwd(qkv, out, dout, lse, delta_ws, dqkv, dtype, B, L, D, H, S(stream));
+                                const float* lse, float* delta_ws, const void* probs, float* scores,
+                                void* dprobs, void* dqkv, int dtype, int B, int L, int D, int H,
+                                void* stream) {
+  if (qkv == nullptr || out == nullptr || dout == nullptr || dqkv == nullptr) return MMU_ERR_ARG;
+  return attention_bwd(qkv, out, dout, lse, delta_ws, probs, scores, dprobs, dqkv, dtype, B, L, D,
+                       H, S(stream));
 }
 
 int mmu_heads_uncertainty_epilogue(const float* logits, const long long* labels, int label_stride,

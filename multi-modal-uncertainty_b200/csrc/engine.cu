@@ -114,6 +114,7 @@ struct LayerWs {
   void* h1;
   void* qkv;
   float* lse;
+  void* probs;     // bf16 [L*H, B, Bp] attention probabilities (tensor-core attention path)
   void* o;
   float* x1;
   float* stats2;
@@ -139,6 +140,8 @@ struct Ws {
   void* dbig;   // dz / dqkv
   void* dh;     // dh2 / do / dh1
   float* delta;
+  float* scores;   // fp32 [L*H, B, Bp] scratch (S / dP)
+  void* dprobs;    // bf16 [L*H, B, Bp] scratch (dS)
   void* dimg;
   void* dtxt;
   long long bytes;
@@ -161,6 +164,8 @@ void carve(const FlavaConfig& c, int training, void* base, const Layout& lay, Ws
   const long long L = (c.cls_token ? c.E : 0) + c.l_img + c.l_txt;
   const long long M = static_cast<long long>(c.B) * L;
   const long long D = c.D;
+  const long long Bp = (c.B + 7) / 8 * 8;
+  const long long sq_elems = L * c.n_head * c.B * Bp;
   w->params_lp = c.precision == PREC_BF16 ? b.take<void>(lay.total * 2) : nullptr;
   w->img_t = b.take<void>(static_cast<long long>(c.B) * c.l_img * c.d_img * s);
   w->txt_t = b.take<void>(static_cast<long long>(c.B) * c.l_txt * c.d_txt * s);
@@ -174,6 +179,7 @@ void carve(const FlavaConfig& c, int training, void* base, const Layout& lay, Ws
     l.h1 = b.take<void>(M * D * s);
     l.qkv = b.take<void>(M * 3 * D * s);
     l.lse = b.take<float>(L * c.n_head * c.B * 4);
+    l.probs = c.precision == PREC_BF16 ? b.take<void>(sq_elems * 2) : nullptr;
     l.o = b.take<void>(M * D * s);
     l.x1 = b.take<float>(M * D * 4);
     l.stats2 = b.take<float>(2 * M * 4);
@@ -187,6 +193,7 @@ void carve(const FlavaConfig& c, int training, void* base, const Layout& lay, Ws
   w->x_final = w->x_out[0];
   w->stats_post = b.take<float>(2 * M * 4);
   w->vec = b.take<float>(static_cast<long long>(c.B) * c.E * D * 4);
+  w->scores = c.precision == PREC_BF16 ? b.take<float>(sq_elems * 4) : nullptr;
   if (training) {
     w->dvec = b.take<float>(static_cast<long long>(c.B) * c.E * D * 4);
     w->dx = b.take<float>(M * D * 4);
@@ -194,11 +201,12 @@ void carve(const FlavaConfig& c, int training, void* base, const Layout& lay, Ws
     w->dbig = b.take<void>(M * 4 * D * s);
     w->dh = b.take<void>(M * D * s);
     w->delta = b.take<float>(L * c.n_head * c.B * 4);
+    w->dprobs = c.precision == PREC_BF16 ? b.take<void>(sq_elems * 2) : nullptr;
     w->dimg = b.take<void>(static_cast<long long>(c.B) * c.l_img * D * s);
     w->dtxt = b.take<void>(static_cast<long long>(c.B) * c.l_txt * D * s);
   } else {
     w->dvec = nullptr; w->dx = nullptr; w->dx_lp = nullptr; w->dbig = nullptr; w->dh = nullptr;
-    w->delta = nullptr; w->dimg = nullptr; w->dtxt = nullptr;
+    w->delta = nullptr; w->dprobs = nullptr; w->dimg = nullptr; w->dtxt = nullptr;
   }
   w->bytes = b.off;
 }
@@ -365,7 +373,7 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
                           M, D, stream));
     MMU_TRY(gemm(l.h1, D, 0, W(p.in_w), D, 0, M, 3 * D, D,
                  epi(EPI_STORE, l.qkv, bf, 3 * D, params + p.in_b)));
-    MMU_TRY(attention_fwd(l.qkv, l.o, l.lse, dt, c.B, s.L, D, c.n_head, stream));
+    MMU_TRY(attention_fwd(l.qkv, l.o, l.lse, l.probs, w.scores, dt, c.B, s.L, D, c.n_head, stream));
     {
       GemmEpilogue e = epi(EPI_RESIDUAL, l.x1, 0, D, params + p.out_b);
       e.aux = x; e.ld_aux = D;
@@ -476,8 +484,8 @@ int flava_backward(const FlavaConfig& c, const float* params, const FlavaInputs&
                    wgrad_splits(D, D, M)));
       MMU_TRY(gemm(w.dx_lp, D, 0, W(p.out_w), D, 1, M, D, D, epi(EPI_STORE, w.dh, bf, D, nullptr)));
       // attention backward: dqkv
-      MMU_TRY(attention_bwd(l.qkv, l.o, w.dh, l.lse, w.delta, w.dbig, dt, c.B, s.L, D, c.n_head,
-                            stream));
+      MMU_TRY(attention_bwd(l.qkv, l.o, w.dh, l.lse, w.delta, l.probs, w.scores, w.dprobs, w.dbig,
+                            dt, c.B, s.L, D, c.n_head, stream));
       // dWin[3D, D] += dqkv^T h1 ; dbin += colsum(dqkv) ; dh1 = dqkv Win
       MMU_TRY(gemm(w.dbig, 3 * D, 1, l.h1, D, 1, 3 * D, D, M,
                    epi(EPI_ATOMIC, grads + p.in_w, 0, D, nullptr), wgrad_splits(3 * D, D, M)));

@@ -31,7 +31,29 @@ struct GemmProblem {
   int M, N, K;
   int a_mn_major, b_mn_major;
   int splits;  // split-K factor (only with EPI_ATOMIC)
+  // Batched mode (batch > 0): `batch` independent M x N x K problems addressed through 3-D tensor
+  // maps (inner, mid, outer).  Batch id g selects mid coordinate g / hdiv and adds
+  // (g % hdiv) * hstride + col0 to the inner coordinate; the output base moves by
+  // (g / out_hdiv) * out_mid_stride + (g % out_hdiv) * out_hstride elements.  This is how the
+  // per-(token position, head) attention problems of the batch-axis MHA are expressed.
+  int batch;
+  int a_hdiv, a_hstride, a_col0;
+  int b_hdiv, b_hstride, b_col0;
+  int out_hdiv, out_hstride;
+  long long out_mid_stride;
 };
+
+// Operand of a batched GEMM: a 3-D view (inner contiguous; strides in elements).
+struct BatchedOperand {
+  const void* base;
+  long long inner, mid, outer;          // extents
+  long long mid_stride, outer_stride;   // element strides (inner stride is 1)
+  int mn_major;                         // 0: rows on `outer`, K on `inner`; 1: K on `outer`
+  int hdiv, hstride, col0;
+};
+int gemm_bf16_batched_launch(const BatchedOperand& A, const BatchedOperand& B, int batch, int M,
+                             int N, int K, const GemmEpilogue& e, int out_hdiv, int out_hstride,
+                             long long out_mid_stride, cudaStream_t stream);
 
 // ---------------------------------------------------------------- host side
 // Returns 0 on success, negative error code otherwise (never throws).

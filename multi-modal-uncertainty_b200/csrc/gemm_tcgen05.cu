@@ -56,6 +56,27 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+// 3-D bf16 tensor map (inner contiguous), 128-byte swizzle, zero fill out of bounds.
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, long long inner, long long mid,
+                      long long outer, long long mid_stride, long long outer_stride, int box_inner,
+                      int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return MMU_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (mid_stride * 2) % 16 != 0 ||
+      (outer_stride * 2) % 16 != 0)
+    return MMU_ERR_ALIGN;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(mid),
+                        static_cast<cuuint64_t>(outer)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(mid_stride) * 2,
+                           static_cast<cuuint64_t>(outer_stride) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_inner), 1u, static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MMU_ERR_TMAP;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -124,6 +145,33 @@ int gemm_bf16_launch(const void* A, long long lda, const void* B, long long ldb,
     case EPI_ATOMIC: return launch_mode<EPI_ATOMIC>(grid, ta, tb, p, e, stream);
     default: return MMU_ERR_ARG;
   }
+}
+
+int gemm_bf16_batched_launch(const BatchedOperand& A, const BatchedOperand& B, int batch, int M,
+                             int N, int K, const GemmEpilogue& e, int out_hdiv, int out_hstride,
+                             long long out_mid_stride, cudaStream_t stream) {
+  using namespace gemm;
+  if (batch <= 0 || M <= 0 || N <= 0 || K <= 0 || N % 4 != 0) return MMU_ERR_SHAPE;
+  if (e.mode != EPI_STORE) return MMU_ERR_ARG;
+  GemmProblem p{};
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn_major = A.mn_major; p.b_mn_major = B.mn_major;
+  p.splits = 1;
+  p.batch = batch;
+  p.a_hdiv = A.hdiv; p.a_hstride = A.hstride; p.a_col0 = A.col0;
+  p.b_hdiv = B.hdiv; p.b_hstride = B.hstride; p.b_col0 = B.col0;
+  p.out_hdiv = out_hdiv; p.out_hstride = out_hstride; p.out_mid_stride = out_mid_stride;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_3d(&ta, A.base, A.inner, A.mid, A.outer, A.mid_stride, A.outer_stride,
+                             A.mn_major ? 64 : BK, A.mn_major ? BK : BM);
+  if (rc != 0) return rc;
+  rc = make_tmap_bf16_3d(&tb, B.base, B.inner, B.mid, B.outer, B.mid_stride, B.outer_stride,
+                         B.mn_major ? 64 : BK, B.mn_major ? BK : BN);
+  if (rc != 0) return rc;
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const long long tiles = 1LL * batch * m_tiles * n_tiles;
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  return launch_mode<EPI_STORE>(grid, ta, tb, p, e, stream);
 }
 
 }  // namespace mmu

@@ -150,7 +150,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   const int n_tiles = (p.N + BN - 1) / BN;
   const int kb_total = (p.K + BK - 1) / BK;
   const int kb_per = (kb_total + p.splits - 1) / p.splits;
-  const int num_tiles = m_tiles * n_tiles * p.splits;
+  const int nbatch = p.batch > 0 ? p.batch : 1;
+  const int num_tiles = nbatch * m_tiles * n_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tma_a);
@@ -184,17 +185,41 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int split = tile % p.splits;
-        const int mn = tile / p.splits;
+        const int mnb = tile / p.splits;
+        const int g = mnb / (m_tiles * n_tiles);
+        const int mn = mnb % (m_tiles * n_tiles);
         const int m0 = (mn / n_tiles) * BM;
         const int n0 = (mn % n_tiles) * BN;
         const int kb0 = split * kb_per;
         const int kb1 = min(kb_total, kb0 + kb_per);
+        const int a_mid = p.batch > 0 ? g / p.a_hdiv : 0;
+        const int a_off = p.batch > 0 ? (g % p.a_hdiv) * p.a_hstride + p.a_col0 : 0;
+        const int b_mid = p.batch > 0 ? g / p.b_hdiv : 0;
+        const int b_off = p.batch > 0 ? (g % p.b_hdiv) * p.b_hstride + p.b_col0 : 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
           const int k0 = kb * BK;
+          if (p.batch > 0) {
+            if (!p.a_mn_major) {
+              ptx::tma_load_3d(sa, &tma_a, &full_bar[stage], a_off + k0, a_mid, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                ptx::tma_load_3d(sa + j * 8192, &tma_a, &full_bar[stage], a_off + m0 + 64 * j, a_mid, k0);
+            }
+            if (!p.b_mn_major) {
+              ptx::tma_load_3d(sb, &tma_b, &full_bar[stage], b_off + k0, b_mid, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                ptx::tma_load_3d(sb + j * 8192, &tma_b, &full_bar[stage], b_off + n0 + 64 * j, b_mid, k0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (!p.a_mn_major) {
             ptx::tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);
           } else {
@@ -265,9 +290,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mn = tile / p.splits;
+      const int mnb = tile / p.splits;
+      const int g = mnb / (m_tiles * n_tiles);
+      const int mn = mnb % (m_tiles * n_tiles);
       const int m0 = (mn / n_tiles) * BM + q * 32;
       const int n0 = (mn % n_tiles) * BN + h * (BN / 2);
+      GemmEpilogue eb = e;
+      if (p.batch > 0) {
+        const long long boff = (long long)(g / p.out_hdiv) * p.out_mid_stride +
+                               (long long)(g % p.out_hdiv) * p.out_hstride;
+        eb.out = e.out_bf16 ? static_cast<void*>(static_cast<__nv_bfloat16*>(e.out) + boff)
+                            : static_cast<void*>(static_cast<float*>(e.out) + boff);
+      }
       int orow[8];
       bool rok[8];
 #pragma unroll
@@ -290,7 +324,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         if (n0 + cc < p.N) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            if (rok[i]) aux[0][i] = load_aux<MODE>(e, orow[i], n0 + cc);
+            if (rok[i]) aux[0][i] = load_aux<MODE>(eb, orow[i], n0 + cc);
         }
       }
 #pragma unroll
@@ -310,7 +344,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             if (col0 + 32 + cc < p.N) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                if (rok[i]) aux[(c + 1) & 1][i] = load_aux<MODE>(e, orow[i], col0 + 32 + cc);
+                if (rok[i]) aux[(c + 1) & 1][i] = load_aux<MODE>(eb, orow[i], col0 + 32 + cc);
             }
           }
           const int gcol = col0 + cc;
@@ -322,7 +356,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
               const int srow = rr + 4 * i;
               const float4 v = *reinterpret_cast<const float4*>(
                   stg + srow * STG_LD + 4 * ((lane & 7) ^ (srow & 7)));
-              if (rok[i]) epi_apply<MODE>(e, orow[i], gcol, v, bias, aux[c & 1][i]);
+              if (rok[i]) epi_apply<MODE>(eb, orow[i], gcol, v, bias, aux[c & 1][i]);
             }
           }
           __syncwarp();

@@ -60,11 +60,15 @@ int split_rows(const float* dmm, void* dimg, void* dtxt, int dtype, int B, int L
 
 // ---- batch-axis attention (src/model.py:193,205-207: MHA with batch_first=False on (B,L,D))
 // qkv (dtype) [B*L, 3D] packed q|k|v; out (dtype) [B*L, D]; lse fp32 [L*H*B].
-int attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int L, int D, int H,
-                  cudaStream_t stream);
+// bf16 with head_dim % 64 == 0 and non-null probs/scores buffers runs on the tensor cores
+// (batched tcgen05 GEMMs): probs bf16 [L*H, B, Bp] (kept for the backward), scores fp32 and dprobs
+// bf16 scratch of the same shape, Bp = B rounded up to 8.  Otherwise the fp32 SIMT kernels run
+// (B <= 256) and need lse / delta_ws.
+int attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* scores, int dtype,
+                  int B, int L, int D, int H, cudaStream_t stream);
 int attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
-                  float* delta_ws, void* dqkv, int dtype, int B, int L, int D, int H,
-                  cudaStream_t stream);
+                  float* delta_ws, const void* probs, float* scores, void* dprobs, void* dqkv,
+                  int dtype, int B, int L, int D, int H, cudaStream_t stream);
 
 // ---- fused softmax-CE / accuracy / uncertainty / calibration-histogram epilogue
 struct MetricAccum {  // lives in device memory; all-reduced (sum) across ranks

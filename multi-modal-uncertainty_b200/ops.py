@@ -92,21 +92,41 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx=None, want_lp=False, want_colsum=
     return dx, dgamma, dbeta, dx_lp, colsum
 
 
+def _tc_attention(qkv, D, H):
+    return qkv.dtype == torch.bfloat16 and (D // H) % 64 == 0
+
+
 def attention_fwd(qkv, B, L, D, H):
+    """Returns (out, saved): saved = lse (SIMT path) or the bf16 probabilities (tensor-core path)."""
     _cuda(qkv)
     out = torch.empty(B * L, D, device=qkv.device, dtype=qkv.dtype)
+    if _tc_attention(qkv, D, H):
+        Bp = (B + 7) // 8 * 8
+        probs = torch.empty(L * H, B, Bp, device=qkv.device, dtype=torch.bfloat16)
+        scores = torch.empty(L * H, B, Bp, device=qkv.device, dtype=torch.float32)
+        check(lib.mmu_batchaxis_attention_fwd(ptr(qkv), ptr(out), 0, ptr(probs), ptr(scores),
+                                              _dt(qkv), B, L, D, H, stream_ptr()),
+              "mmu_batchaxis_attention_fwd")
+        return out, probs
     lse = torch.empty(L * H * B, device=qkv.device, dtype=torch.float32)
-    check(lib.mmu_batchaxis_attention_fwd(ptr(qkv), ptr(out), ptr(lse), _dt(qkv), B, L, D, H,
+    check(lib.mmu_batchaxis_attention_fwd(ptr(qkv), ptr(out), ptr(lse), 0, 0, _dt(qkv), B, L, D, H,
                                           stream_ptr()), "mmu_batchaxis_attention_fwd")
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, B, L, D, H):
-    _cuda(qkv, out, dout, lse)
+def attention_bwd(qkv, out, dout, saved, B, L, D, H):
+    _cuda(qkv, out, dout, saved)
     dqkv = torch.empty_like(qkv)
+    if _tc_attention(qkv, D, H):
+        scores = torch.empty(saved.shape, device=qkv.device, dtype=torch.float32)
+        dprobs = torch.empty_like(saved)
+        check(lib.mmu_batchaxis_attention_bwd(ptr(qkv), ptr(out), ptr(dout), 0, 0, ptr(saved),
+                                              ptr(scores), ptr(dprobs), ptr(dqkv), _dt(qkv), B, L, D,
+                                              H, stream_ptr()), "mmu_batchaxis_attention_bwd")
+        return dqkv
     delta = torch.empty(L * H * B, device=qkv.device, dtype=torch.float32)
-    check(lib.mmu_batchaxis_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(delta),
-                                          ptr(dqkv), _dt(qkv), B, L, D, H, stream_ptr()),
+    check(lib.mmu_batchaxis_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(saved), ptr(delta), 0, 0,
+                                          0, ptr(dqkv), _dt(qkv), B, L, D, H, stream_ptr()),
           "mmu_batchaxis_attention_bwd")
     return dqkv
 
