@@ -140,6 +140,7 @@ struct Ws {
   void* dbig;   // dz / dqkv
   void* dh;     // dh2 / do / dh1
   float* delta;
+  void* ybuf;      // act dtype [M, D]: branch output of out_proj / c_proj before the residual add
   float* scores;   // fp32 [L*H, B, Bp] scratch (S / dP)
   void* dprobs;    // bf16 [L*H, B, Bp] scratch (dS)
   void* dimg;
@@ -193,6 +194,7 @@ void carve(const FlavaConfig& c, int training, void* base, const Layout& lay, Ws
   w->x_final = w->x_out[0];
   w->stats_post = b.take<float>(2 * M * 4);
   w->vec = b.take<float>(static_cast<long long>(c.B) * c.E * D * 4);
+  w->ybuf = b.take<void>(M * D * s);
   w->scores = c.precision == PREC_BF16 ? b.take<float>(sq_elems * 4) : nullptr;
   if (training) {
     w->dvec = b.take<float>(static_cast<long long>(c.B) * c.E * D * 4);
@@ -362,34 +364,40 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
   MMU_TRY(layernorm_fwd(w.mm_x, params + lay.lnpre_w, params + lay.lnpre_b, x, DT_F32, w.stats_pre,
                         w.stats_pre + M, M, D, stream));
 
-  // ---- transformer blocks
+  // ---- transformer blocks.  The projections that close a residual branch (out_proj, c_proj)
+  //      store the branch output y in the activation dtype; the add x + y is fused into the
+  //      LayerNorm kernel that consumes the sum (or into a plain add after the last block).
   for (int i = 0; i < c.n_layers; ++i) {
     const LayerParams& p = lay.layer[i];
     const LayerWs& l = w.layer[i];
     float* x_next;
     if (training) x_next = (i + 1 < c.n_layers) ? w.layer[i + 1].x0 : w.x_final;
     else x_next = w.x_out[(i + 1) & 1];
-    MMU_TRY(layernorm_fwd(x, params + p.ln1_w, params + p.ln1_b, l.h1, dt, l.stats1, l.stats1 + M,
-                          M, D, stream));
+    if (i == 0) {
+      MMU_TRY(layernorm_fwd(x, params + p.ln1_w, params + p.ln1_b, l.h1, dt, l.stats1, l.stats1 + M,
+                            M, D, stream));
+    }  // else: h1 / stats1 of this block were produced by the previous block's closing add+LN
     MMU_TRY(gemm(l.h1, D, 0, W(p.in_w), D, 0, M, 3 * D, D,
                  epi(EPI_STORE, l.qkv, bf, 3 * D, params + p.in_b)));
     MMU_TRY(attention_fwd(l.qkv, l.o, l.lse, l.probs, w.scores, dt, c.B, s.L, D, c.n_head, stream));
-    {
-      GemmEpilogue e = epi(EPI_RESIDUAL, l.x1, 0, D, params + p.out_b);
-      e.aux = x; e.ld_aux = D;
-      MMU_TRY(gemm(l.o, D, 0, W(p.out_w), D, 0, M, D, D, e));
-    }
-    MMU_TRY(layernorm_fwd(l.x1, params + p.ln2_w, params + p.ln2_b, l.h2, dt, l.stats2,
-                          l.stats2 + M, M, D, stream));
+    MMU_TRY(gemm(l.o, D, 0, W(p.out_w), D, 0, M, D, D, epi(EPI_STORE, w.ybuf, bf, D, params + p.out_b)));
+    MMU_TRY(add_layernorm_fwd(x, w.ybuf, l.x1, params + p.ln2_w, params + p.ln2_b, l.h2, dt, l.stats2,
+                              l.stats2 + M, M, D, stream));
     {
       GemmEpilogue e = epi(EPI_QUICKGELU, training ? l.z : nullptr, bf, 4 * D, params + p.fc_b);
       e.out2 = l.u; e.ld_out2 = 4 * D;
       MMU_TRY(gemm(l.h2, D, 0, W(p.fc_w), D, 0, M, 4 * D, D, e));
     }
-    {
-      GemmEpilogue e = epi(EPI_RESIDUAL, x_next, 0, D, params + p.proj_b);
-      e.aux = l.x1; e.ld_aux = D;
-      MMU_TRY(gemm(l.u, 4 * D, 0, W(p.proj_w), 4 * D, 0, M, D, 4 * D, e));
+    MMU_TRY(gemm(l.u, 4 * D, 0, W(p.proj_w), 4 * D, 0, M, D, 4 * D,
+                 epi(EPI_STORE, w.ybuf, bf, D, params + p.proj_b)));
+    if (i + 1 < c.n_layers) {
+      const LayerParams& pn = lay.layer[i + 1];
+      const LayerWs& ln = w.layer[i + 1];
+      MMU_TRY(add_layernorm_fwd(l.x1, w.ybuf, x_next, params + pn.ln1_w, params + pn.ln1_b, ln.h1, dt,
+                                ln.stats1, ln.stats1 + M, M, D, stream));
+    } else {
+      MMU_TRY(add_layernorm_fwd(l.x1, w.ybuf, x_next, nullptr, nullptr, nullptr, dt, nullptr, nullptr,
+                                M, D, stream));
     }
     x = x_next;
   }

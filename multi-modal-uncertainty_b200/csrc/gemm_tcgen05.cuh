@@ -78,14 +78,23 @@ struct AuxT<EPI_RESIDUAL> { using type = float4; };
 template <>
 struct AuxT<EPI_DGELU> { using type = uint2; };
 
+// asm volatile: the prefetch must ISSUE where it is written (ptxas otherwise sinks plain loads
+// towards their first use under register pressure, exposing the full DRAM latency).
 template <int MODE>
 __device__ __forceinline__ typename AuxT<MODE>::type load_aux(const GemmEpilogue& e, long long orow,
                                                               int gcol) {
   if constexpr (MODE == EPI_RESIDUAL) {
-    return *reinterpret_cast<const float4*>(static_cast<const float*>(e.aux) + orow * e.ld_aux + gcol);
+    const float* p = static_cast<const float*>(e.aux) + orow * e.ld_aux + gcol;
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
   } else if constexpr (MODE == EPI_DGELU) {
-    return *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(e.aux) +
-                                           orow * e.ld_aux + gcol);
+    const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(e.aux) + orow * e.ld_aux + gcol;
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
   } else {
     return 0;
   }
@@ -282,11 +291,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     // The TMEM load and the aux (residual / z) loads of chunk c+1 are issued before chunk c is
     // written out, so their latency overlaps the store phase.
     using Aux = typename AuxT<MODE>::type;
+    // aux prefetch depth: 3 chunks for the 8-byte bf16 z (DGELU), 2 for the 16-byte residual
+    constexpr int NBUF = (MODE == EPI_DGELU) ? 3 : 2;
     const int q = warp & 3;
     const int h = (warp - 2) >> 2;
-    float* stg = smem_stg + (warp - 2) * (32 * STG_LD);
+    const uint32_t stg = ptx::smem_u32(smem_stg + (warp - 2) * (32 * STG_LD));
     const int rr = lane >> 3;        // 0..3
     const int cc = (lane & 7) * 4;   // 0..28
+    constexpr int NCHUNK = BN / 2 / 32;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -312,21 +324,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         if (e.seg_len > 0)
           orow[i] = (grow / e.seg_len) * e.seg_stride + e.seg_off + grow % e.seg_len;
       }
+      Aux aux[NBUF][8];
+      auto prefetch_aux = [&](int c) {
+        if (c < NCHUNK && n0 + c * 32 + cc < p.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (rok[i]) aux[c % NBUF][i] = load_aux<MODE>(eb, orow[i], n0 + c * 32 + cc);
+        }
+      };
+      // issued BEFORE waiting for the accumulator: the loads fly while the MMAs finish
+#pragma unroll
+      for (int c = 0; c < NBUF - 1; ++c) prefetch_aux(c);
+
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(as * BN + h * (BN / 2));
-      constexpr int NCHUNK = BN / 2 / 32;
       uint32_t r[32];
-      Aux aux[2][8];
-      if (n0 < p.N) {
-        ptx::tmem_ld_32x32(taddr, r);
-        if (n0 + cc < p.N) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (rok[i]) aux[0][i] = load_aux<MODE>(eb, orow[i], n0 + cc);
-        }
-      }
+      if (n0 < p.N) ptx::tmem_ld_32x32(taddr, r);
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
         const int col0 = n0 + c * 32;
@@ -336,17 +351,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           for (int j = 0; j < 8; ++j) {
             float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                    __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-            *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * (j ^ (lane & 7))) = v;
+            ptx::sts_v4(stg + (lane * STG_LD + 4 * (j ^ (lane & 7))) * 4, v);
           }
           __syncwarp();
-          if (c + 1 < NCHUNK && col0 + 32 < p.N) {
-            ptx::tmem_ld_32x32(taddr + (c + 1) * 32, r);
-            if (col0 + 32 + cc < p.N) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (rok[i]) aux[(c + 1) & 1][i] = load_aux<MODE>(eb, orow[i], col0 + 32 + cc);
-            }
-          }
+          if (c + 1 < NCHUNK && col0 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, r);
+          prefetch_aux(c + NBUF - 1);
           const int gcol = col0 + cc;
           if (gcol < p.N) {
             float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -354,9 +363,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int srow = rr + 4 * i;
-              const float4 v = *reinterpret_cast<const float4*>(
-                  stg + srow * STG_LD + 4 * ((lane & 7) ^ (srow & 7)));
-              if (rok[i]) epi_apply<MODE>(eb, orow[i], gcol, v, bias, aux[c & 1][i]);
+              const float4 v = ptx::lds_v4(stg + (srow * STG_LD + 4 * ((lane & 7) ^ (srow & 7))) * 4);
+              if (rok[i]) epi_apply<MODE>(eb, orow[i], gcol, v, bias, aux[c % NBUF][i]);
             }
           }
           __syncwarp();

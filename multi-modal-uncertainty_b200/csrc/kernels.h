@@ -20,6 +20,10 @@ int cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t stream)
 // ---- LayerNorm (eps 1e-5, biased variance, src/model.py:174-180, :252-253)
 int layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
                   float* mean, float* rstd, int M, int D, cudaStream_t stream);
+// x_out = x_in + y (y and h in `dtype`); h = LN(x_out) unless gamma == nullptr (sum only).
+int add_layernorm_fwd(const float* x_in, const void* y, float* x_out, const float* gamma,
+                      const float* beta, void* h, int dtype, float* mean, float* rstd, int M, int D,
+                      cudaStream_t stream);
 // dx (fp32) = [accumulate ? dx : 0] + LN'(dy); optional low-precision copy of the final dx,
 // optional column sum of the final dx (bias gradient of the layer that produced x).
 int layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* mean,

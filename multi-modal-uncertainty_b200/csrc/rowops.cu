@@ -162,6 +162,53 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   }
 }
 
+
+// x_out = x_in + y (branch output of the preceding projection GEMM, stored in the activation
+// dtype); h = LayerNorm(x_out).  Fusing the residual add here keeps the GEMM epilogues free of the
+// fp32 residual-stream traffic (a streaming row kernel moves those bytes at ~HBM peak; a GEMM
+// epilogue does not).  gamma == nullptr: only the sum is written (last block -> ln_post/heads).
+template <int NV, typename TY, typename TO>
+__global__ void __launch_bounds__(THREADS)
+add_layernorm_fwd_kernel(const float* __restrict__ x_in, const TY* __restrict__ y,
+                         float* __restrict__ x_out, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, TO* __restrict__ h,
+                         float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D >> 2;
+  for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
+    RowRegs<NV> r, ry;
+    r.load(x_in + static_cast<size_t>(row) * D, nvec, lane);
+    ry.load(y + static_cast<size_t>(row) * D, nvec, lane);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      r.v[i].x += ry.v[i].x; r.v[i].y += ry.v[i].y; r.v[i].z += ry.v[i].z; r.v[i].w += ry.v[i].w;
+      const int c = lane + 32 * i;
+      if (c < nvec) *reinterpret_cast<float4*>(x_out + static_cast<size_t>(row) * D + 4 * c) = r.v[i];
+    }
+    if (gamma == nullptr) continue;
+    float mean, rstd;
+    row_stats<NV>(r, nvec, lane, D, mean, rstd);
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c);
+        const float4 b = *reinterpret_cast<const float4*>(beta + 4 * c);
+        float4 o;
+        o.x = (r.v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (r.v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (r.v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (r.v[i].w - mean) * rstd * g.w + b.w;
+        Vec4<TO>::st(h + static_cast<size_t>(row) * D + 4 * c, o);
+      }
+    }
+  }
+}
+
 // Reduce per-warp column partials (acc[NV] float4 per lane) across the block's warps and
 // atomically add into out[D].  `red` is WARPS*D floats of shared memory.
 template <int NV>
@@ -399,23 +446,43 @@ pool_ln_bwd_kernel(const float* __restrict__ dvec, const float* __restrict__ x,
   block_colreduce<NV>(acc_b, red, dbeta, nvec, D);
 }
 
-__global__ void heads_fwd_kernel(const float* __restrict__ vec, HeadParams hp,
-                                 float* __restrict__ logits, int E, int C, int D) {
-  extern __shared__ float sv[];
-  const int b = blockIdx.x, e = blockIdx.y;
-  const float* v = vec + (static_cast<size_t>(b) * E + e) * D;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) sv[i] = v[i];
+// One block = one head x HEADS_TB samples: every weight row is read once per block and reused
+// against all HEADS_TB pooled vectors held in shared memory (the weights are L2 resident, but
+// re-reading the full (C, D) matrix per sample made this tiny op L2-bandwidth bound).
+constexpr int HEADS_TB = 8;
+__global__ void __launch_bounds__(256)
+heads_fwd_kernel(const float* __restrict__ vec, HeadParams hp, float* __restrict__ logits, int B,
+                 int E, int C, int D) {
+  extern __shared__ __align__(16) float sv[];  // [HEADS_TB][D]
+  const int b0 = blockIdx.x * HEADS_TB, e = blockIdx.y;
+  const int nb = min(HEADS_TB, B - b0);
+  for (int i = threadIdx.x * 4; i < HEADS_TB * D; i += blockDim.x * 4) {
+    const int t = i / D, d = i % D;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < nb) v = *reinterpret_cast<const float4*>(vec + (static_cast<size_t>(b0 + t) * E + e) * D + d);
+    *reinterpret_cast<float4*>(sv + i) = v;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const float* W = hp.w[e];
   for (int c = warp; c < C; c += nw) {
-    float s = 0.f;
+    float acc[HEADS_TB];
+#pragma unroll
+    for (int t = 0; t < HEADS_TB; ++t) acc[t] = 0.f;
     for (int i = lane * 4; i < D; i += 128) {
       const float4 w = *reinterpret_cast<const float4*>(W + static_cast<size_t>(c) * D + i);
-      s += (w.x * sv[i] + w.y * sv[i + 1]) + (w.z * sv[i + 2] + w.w * sv[i + 3]);
+#pragma unroll
+      for (int t = 0; t < HEADS_TB; ++t) {
+        const float4 v = *reinterpret_cast<const float4*>(sv + t * D + i);
+        acc[t] += (w.x * v.x + w.y * v.y) + (w.z * v.z + w.w * v.w);
+      }
     }
-    s = warp_sum(s);
-    if (lane == 0) logits[(static_cast<size_t>(b) * E + e) * C + c] = s + hp.b[e][c];
+    const float bias = hp.b[e][c];
+#pragma unroll
+    for (int t = 0; t < HEADS_TB; ++t) {
+      const float sum = warp_sum(acc[t]);
+      if (lane == 0 && t < nb) logits[(static_cast<size_t>(b0 + t) * E + e) * C + c] = sum + bias;
+    }
   }
 }
 
@@ -564,6 +631,27 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y
   return 0;
 }
 
+int add_layernorm_fwd(const float* x_in, const void* y, float* x_out, const float* gamma,
+                      const float* beta, void* h, int dtype, float* mean, float* rstd, int M, int D,
+                      cudaStream_t stream) {
+  const int nv = nv_for(D);
+  if (nv < 0) return MMU_ERR_SHAPE;
+  if (M <= 0) return 0;
+  const int grid = grid_for(M, WARPS);
+  if (dtype == DT_BF16) {
+    using T = __nv_bfloat16;
+    MMU_NV_DISPATCH(nv, (add_layernorm_fwd_kernel<NV, T, T><<<grid, THREADS, 0, stream>>>(
+                            x_in, static_cast<const T*>(y), x_out, gamma, beta, static_cast<T*>(h),
+                            mean, rstd, M, D)));
+  } else {
+    MMU_NV_DISPATCH(nv, (add_layernorm_fwd_kernel<NV, float, float><<<grid, THREADS, 0, stream>>>(
+                            x_in, static_cast<const float*>(y), x_out, gamma, beta,
+                            static_cast<float*>(h), mean, rstd, M, D)));
+  }
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
 int layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* mean,
                   const float* rstd, const float* gamma, float* dx, int accumulate, void* dx_lp,
                   int lp_dtype, float* dgamma, float* dbeta, float* dcolsum, int M, int D,
@@ -642,7 +730,8 @@ int pool_ln_bwd(const float* dvec, const float* x, const float* mean, const floa
 int heads_fwd(const float* vec, const HeadParams& hp, float* logits, int B, int E, int C, int D,
               cudaStream_t stream) {
   if (D % 4 != 0 || E > 16) return MMU_ERR_SHAPE;
-  heads_fwd_kernel<<<dim3(B, E), 128, D * sizeof(float), stream>>>(vec, hp, logits, E, C, D);
+  heads_fwd_kernel<<<dim3((B + HEADS_TB - 1) / HEADS_TB, E), 256, HEADS_TB * D * sizeof(float),
+                     stream>>>(vec, hp, logits, B, E, C, D);
   MMU_CHECK_LAUNCH();
   return 0;
 }
