@@ -180,13 +180,20 @@ def run_gpu(args):
         sched.step()
         sweep(img, txt, y, level_variants(mmu, i))
 
-    def step_e2e(i):
-        (img, txt), y = host[i % nb]
-        loss, info, _ = trainer.train_step((img, txt), y)         # H2D + D2H(loss, acc) inside
-        imgd, txtd, yd = img.to(dev, non_blocking=True), txt.to(dev, non_blocking=True), \
-            y.to(dev, non_blocking=True)                           # the sweep re-reads the host batch
-        sweep(imgd, txtd, yd, level_variants(mmu, i))
-        return loss
+    def step_e2e(batch):
+        (img, txt), y = batch          # device tensors from the prefetcher (copied this step)
+        loss, info, _ = trainer.train_step((img, txt), y, sync=False)
+        sweep(img, txt, y, level_variants(mmu, 0))
+        # D2H read of the step's results (loss, acc) once everything of the step is enqueued
+        return float(loss), [float(v) for v in info]
+
+    def run_e2e(steps):
+        """Public-API loop: pinned host batches -> DevicePrefetcher (H2D of batch i+1 on a side
+        stream while step i runs) -> Model_.train_step -> robustness sweep.  Every step's batch is
+        copied host->device inside the timed region."""
+        loader = [host[i % nb] for i in range(steps)]
+        for batch in mmu.dataset.DevicePrefetcher(loader, dev):
+            step_e2e(batch)
 
     def barrier():
         torch.cuda.synchronize()
@@ -225,10 +232,19 @@ def run_gpu(args):
             print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps,
                               "gpu_launches": int(launches)}))
         return
-    for i in range(max(1, args.warmup // 2)):
-        step_e2e(i)
+    run_e2e(max(1, args.warmup // 2))
     meter.reset()
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_e2e(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t)
     meter.all_reduce()
     meter.compute()  # D2H read of the sweep result
     per_step = ms / args.steps
@@ -245,7 +261,7 @@ def run_gpu(args):
         dist.barrier()
 
     if rank == 0:
-        h2d = sum(t.numel() * t.element_size() for t in (host[0][0][0], host[0][0][1], host[0][1])) * 2
+        h2d = sum(t.numel() * t.element_size() for t in (host[0][0][0], host[0][0][1], host[0][1]))
         line = {
             "metric": "train+robustness-eval samples/sec", "value": round(value, 2),
             "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -260,7 +276,7 @@ def run_gpu(args):
                        "parallelism": f"dp{world}", "dead_tokens": "computed (as written)",
                        "l2": "working set ~6 GB/step >> 126 MB L2, inputs rotate over 4 batches"},
             "e2e": {"value": round(e2e_value, 2), "unit": "samples/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,  # loss + acc, 4 B each
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -287,8 +303,6 @@ def measure_rooflines(mmu, dev):
     x3072 = torch.randn(M, 4 * D, device=dev).to(bf)
     w = {n: (torch.randn(n, D, device=dev) * 0.02).to(bf) for n in (3 * D, 4 * D, D)}  # keyed by out-features
     w_proj = (torch.randn(D, 4 * D, device=dev) * 0.02).to(bf)
-    out768f = torch.empty(M, D, device=dev)
-    resid = torch.randn(M, D, device=dev)
     o2304, o3072, o3072b, o768 = (torch.empty(M, n, device=dev, dtype=bf) for n in (3 * D, 4 * D, 4 * D, D))
     gw = {s: torch.zeros(*s, device=dev) for s in ((3 * D, D), (4 * D, D), (D, 4 * D), (D, D))}
     bias = {n: torch.zeros(n, device=dev) for n in (D, 3 * D, 4 * D)}
@@ -297,9 +311,9 @@ def measure_rooflines(mmu, dev):
     def layer_gemms():
         # forward
         g(x768, w[3 * D], out=o2304, bias=bias[3 * D])
-        g(x768, w[D], mode=E_.EPI_RESIDUAL, out=out768f, aux=resid, bias=bias[D])
+        g(x768, w[D], out=o768, bias=bias[D])
         g(x768, w[4 * D], mode=E_.EPI_QUICKGELU, out=o3072, out2=o3072b, bias=bias[4 * D])
-        g(x3072, w_proj, mode=E_.EPI_RESIDUAL, out=out768f, aux=resid, bias=bias[D])
+        g(x3072, w_proj, out=o768, bias=bias[D])
         # backward: dgrad
         g(x768, w_proj, b_mn_major=True, mode=E_.EPI_DGELU, out=o3072, aux=o3072b)
         g(x3072, w[4 * D], b_mn_major=True, out=o768)

@@ -97,6 +97,9 @@ MMU_API int mmu_gemm(int dtype, const void* A, long long lda, int a_mn_major, co
 MMU_API int mmu_mask_gather_tokens(const float* src, void* dst, int dst_dtype, int B, int l_src, int d,
                            const int* idx, int n_sel, const int* keep, int modality, void* stream);
 
+/* bf16 copy of a flat fp32 buffer (the GEMM-operand shadow of the parameters); n elements. */
+MMU_API int mmu_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
+
 /* LayerNorm, eps 1e-5, biased variance, fp32 statistics (src/model.py:174-180 LayerNorm
  * subclass; :252-253 ln_pre / ln_post).  mean/rstd: fp32[M], saved for the backward. */
 MMU_API int mmu_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
@@ -191,6 +194,8 @@ typedef struct {
   const int* idx_txt;
   int n_img, n_txt;    /* tokens fed to the model (<= l_img / l_txt) */
   const int* keep;     /* int32[B,2] modality keep mask (0: zero-fill) or NULL */
+  const void* params_bf16; /* optional bf16 copy of `params` kept fresh by the caller (the fused
+                              AdamW writes it); NULL: cast from the fp32 master every forward */
 } mmu_flava_inputs;
 
 /* logits: fp32 (B, E, C).  training != 0 keeps the activations the backward needs. */

@@ -19,7 +19,7 @@ EXPORTS = [
     "mmu_layernorm_bwd", "mmu_batchaxis_attention_fwd", "mmu_batchaxis_attention_bwd",
     "mmu_heads_uncertainty_epilogue", "mmu_adamw_flat_step", "mmu_flava_param_count",
     "mmu_flava_param_table", "mmu_flava_workspace_bytes", "mmu_flava_num_stages",
-    "mmu_flava_forward", "mmu_flava_backward",
+    "mmu_flava_forward", "mmu_flava_backward", "mmu_cast_f32_to_bf16",
 ]
 
 
@@ -62,7 +62,7 @@ class ParamEntry(C.Structure):
 class FlavaInputs(C.Structure):
     _fields_ = [("img", C.c_void_p), ("txt", C.c_void_p), ("idx_img", C.c_void_p),
                 ("idx_txt", C.c_void_p), ("n_img", C.c_int), ("n_txt", C.c_int),
-                ("keep", C.c_void_p)]
+                ("keep", C.c_void_p), ("params_bf16", C.c_void_p)]
 
 
 def _load():
@@ -79,6 +79,7 @@ def _load():
     lib.mmu_launch_count.restype = ll
     lib.mmu_gemm.argtypes = [i, vp, ll, i, vp, ll, i, i, i, i, i, C.POINTER(GemmEpilogue), vp]
     lib.mmu_mask_gather_tokens.argtypes = [vp, vp, i, i, i, i, vp, i, vp, i, vp]
+    lib.mmu_cast_f32_to_bf16.argtypes = [vp, vp, C.c_size_t, vp]
     lib.mmu_layernorm_fwd.argtypes = [vp, vp, vp, vp, i, vp, vp, i, i, vp]
     lib.mmu_layernorm_bwd.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, i, vp, vp, vp, i, i, vp]
     lib.mmu_batchaxis_attention_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, vp]

@@ -81,6 +81,11 @@ int mmu_mask_gather_tokens(const float* src, void* dst, int dst_dtype, int B, in
   return cast_gather(src, dst, dst_dtype, B, l_src, d, idx, n_sel, keep, modality, S(stream));
 }
 
+int mmu_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream) {
+  if (src == nullptr || dst == nullptr) return MMU_ERR_ARG;
+  return cast_f32_to_bf16(src, dst, n, S(stream));
+}
+
 int mmu_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
                       float* mean, float* rstd, int M, int D, void* stream) {
   if (x == nullptr || gamma == nullptr || beta == nullptr || y == nullptr) return MMU_ERR_ARG;

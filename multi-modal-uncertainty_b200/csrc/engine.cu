@@ -336,11 +336,13 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
   const int D = c.D, M = s.M;
   const Gemm gemm{c.precision, stream};
   // operand view of the parameters (bf16 shadow refreshed from the fp32 master every forward)
+  const void* shadow = in.params_bf16 != nullptr ? in.params_bf16 : w.params_lp;
   auto W = [&](long long off) -> const void* {
-    return bf ? static_cast<const void*>(static_cast<const uint16_t*>(w.params_lp) + off)
+    return bf ? static_cast<const void*>(static_cast<const uint16_t*>(shadow) + off)
               : static_cast<const void*>(params + off);
   };
-  if (bf) MMU_TRY(cast_f32_to_bf16(params, w.params_lp, static_cast<size_t>(lay.total), stream));
+  if (bf && in.params_bf16 == nullptr)
+    MMU_TRY(cast_f32_to_bf16(params, w.params_lp, static_cast<size_t>(lay.total), stream));
 
   // ---- stem: gather/mask/cast inputs, per-modality projections written straight into the
   //      concatenated (B, L, D) buffer (fuses torch.cat, src/model.py:262-273), CLS rows
@@ -431,8 +433,9 @@ int flava_backward(const FlavaConfig& c, const float* params, const FlavaInputs&
   const int dt = bf ? DT_BF16 : DT_F32;
   const int D = c.D, M = s.M;
   const Gemm gemm{c.precision, stream};
+  const void* shadow = in.params_bf16 != nullptr ? in.params_bf16 : w.params_lp;
   auto W = [&](long long off) -> const void* {
-    return bf ? static_cast<const void*>(static_cast<const uint16_t*>(w.params_lp) + off)
+    return bf ? static_cast<const void*>(static_cast<const uint16_t*>(shadow) + off)
               : static_cast<const void*>(params + off);
   };
   const int n_stages = c.n_layers + 2;

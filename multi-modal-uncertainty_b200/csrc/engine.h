@@ -48,6 +48,9 @@ struct FlavaInputs {
   int n_img;            // tokens used (0: modality absent); <= l_img
   int n_txt;
   const int* keep;      // device int32[B,2] modality keep mask (zero-fill), or null
+  // optional caller-maintained bf16 shadow of `params` (same element offsets).  Null: the engine
+  // casts the fp32 master into the workspace at every forward (22.8 M params = 137 MB of traffic).
+  const void* params_bf16;
 };
 
 int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& in, void* ws,

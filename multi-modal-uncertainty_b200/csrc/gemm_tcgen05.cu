@@ -88,19 +88,49 @@ int sm_count() {
   return n;
 }
 
+// 4-D output / epilogue-operand map: (columns, rows, batch % hdiv, batch / hdiv), element strides
+// (1, ld, hstride, mid_stride); box = 32 rows x 64 bytes, 64-byte swizzle.  Stores clip at the
+// extents, loads zero-fill, so the kernel needs no edge predicates.
+int make_tmap_out_4d(CUtensorMap* out, const void* base, int is_bf16, long long cols, long long rows,
+                     long long ld, long long hdiv, long long hstride, long long nmid,
+                     long long mid_stride) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return MMU_ERR_DRIVER;
+  const long long es = is_bf16 ? 2 : 4;
+  if (hdiv < 1) hdiv = 1;
+  if (nmid < 1) nmid = 1;
+  if (hdiv == 1 || hstride <= 0) hstride = ld;     // size-1 dimensions still need a legal stride
+  if (nmid == 1 || mid_stride <= 0) mid_stride = ld;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * es) % 16 != 0 ||
+      (hstride * es) % 16 != 0 || (mid_stride * es) % 16 != 0)
+    return MMU_ERR_ALIGN;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(hdiv), static_cast<cuuint64_t>(nmid)};
+  cuuint64_t gstride[3] = {static_cast<cuuint64_t>(ld * es), static_cast<cuuint64_t>(hstride * es),
+                           static_cast<cuuint64_t>(mid_stride * es)};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(is_bf16 ? 32 : 16), 32u, 1u, 1u};  // 64-byte rows
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                  4, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MMU_ERR_TMAP;
+}
+
 namespace {
-template <int MODE>
-int launch_mode(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const GemmProblem& p,
-                const GemmEpilogue& e, cudaStream_t stream) {
+template <int MODE, bool OBF>
+int launch_mode(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& c0,
+                const CUtensorMap& c1, const GemmProblem& p, const GemmEpilogue& e,
+                cudaStream_t stream) {
   using namespace gemm;
   static cudaError_t attr_err = cudaFuncSetAttribute(
-      gemm_bf16_tcgen05_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      gemm_bf16_tcgen05_kernel<MODE, OBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (attr_err != cudaSuccess) {
     fprintf(stderr, "mmu: cudaFuncSetAttribute(smem=%d): %s\n", SMEM_BYTES,
             cudaGetErrorString(attr_err));
     return MMU_ERR_CUDA;
   }
-  gemm_bf16_tcgen05_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p, e);
+  gemm_bf16_tcgen05_kernel<MODE, OBF><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, c0, c1, p, e);
   const cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) {
     fprintf(stderr, "mmu: gemm launch failed: %s\n", cudaGetErrorString(err));
@@ -109,6 +139,48 @@ int launch_mode(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   count_launch();
   return 0;
 }
+
+// Output maps + mode dispatch shared by the plain and the batched entry points.  `rows`/`cols`
+// are the per-problem output extents; batch geometry as in GemmProblem.
+int launch_with_epilogue(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const GemmProblem& p,
+                         const GemmEpilogue& e, cudaStream_t stream) {
+  const int obf = e.out_bf16 ? 1 : 0;
+  const long long hdiv = p.batch > 0 ? p.out_hdiv : 1;
+  const long long nmid = p.batch > 0 ? (p.batch + hdiv - 1) / hdiv : 1;
+  auto omap = [&](CUtensorMap* m, const void* base, long long ld) {
+    return make_tmap_out_4d(m, base, obf, p.N, p.M, ld, hdiv, p.out_hstride, nmid, p.out_mid_stride);
+  };
+  CUtensorMap c0, c1;
+  int rc;
+  switch (e.mode) {
+    case EPI_STORE:
+      if (e.out == nullptr) return MMU_ERR_ARG;
+      if ((rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;
+      c1 = c0;
+      return obf ? launch_mode<EPI_STORE, true>(grid, ta, tb, c0, c1, p, e, stream)
+                 : launch_mode<EPI_STORE, false>(grid, ta, tb, c0, c1, p, e, stream);
+    case EPI_QUICKGELU:
+      if (!obf || e.out2 == nullptr) return MMU_ERR_ARG;  // bf16 activations only on this path
+      if ((rc = omap(&c1, e.out2, e.ld_out2)) != 0) return rc;
+      c0 = c1;
+      if (e.out != nullptr && (rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;
+      return launch_mode<EPI_QUICKGELU, true>(grid, ta, tb, c0, c1, p, e, stream);
+    case EPI_DGELU:
+      if (!obf || e.out == nullptr || e.aux == nullptr) return MMU_ERR_ARG;
+      if ((rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;
+      if ((rc = omap(&c1, e.aux, e.ld_aux)) != 0) return rc;
+      return launch_mode<EPI_DGELU, true>(grid, ta, tb, c0, c1, p, e, stream);
+    case EPI_ATOMIC:
+      if (obf || e.out == nullptr) return MMU_ERR_ARG;
+      if ((rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;
+      c1 = c0;
+      return launch_mode<EPI_ATOMIC, false>(grid, ta, tb, c0, c1, p, e, stream);
+    default:
+      // EPI_RESIDUAL exists on the fp32 path only: the bf16 engine fuses the residual add into
+      // the LayerNorm kernel that consumes the sum (rowops.cu add_layernorm_fwd)
+      return MMU_ERR_ARG;
+  }
+}
 }  // namespace
 
 int gemm_bf16_launch(const void* A, long long lda, const void* B, long long ldb,
@@ -116,7 +188,26 @@ int gemm_bf16_launch(const void* A, long long lda, const void* B, long long ldb,
   using namespace gemm;
   GemmProblem p = p_in;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return MMU_ERR_SHAPE;
-  if (p.N % 4 != 0) return MMU_ERR_SHAPE;
+  if (e.seg_len > 0) {
+    // Row remap (fused torch.cat): one batched problem per segment -- batch g holds rows
+    // [g*seg_len, (g+1)*seg_len) of A and writes rows g*seg_stride + seg_off + l of `out`.
+    if (p.a_mn_major || p.b_mn_major || p.splits > 1 || e.mode != EPI_STORE || p.M % e.seg_len != 0)
+      return MMU_ERR_SHAPE;
+    const int nb = p.M / e.seg_len;
+    BatchedOperand a{}, b{};
+    a.base = A; a.inner = p.K; a.mid = nb; a.outer = e.seg_len;
+    a.mid_stride = static_cast<long long>(e.seg_len) * lda; a.outer_stride = lda;
+    a.mn_major = 0; a.hdiv = 1; a.hstride = 0; a.col0 = 0;
+    b.base = B; b.inner = p.K; b.mid = 1; b.outer = p.N;
+    b.mid_stride = static_cast<long long>(p.N) * ldb; b.outer_stride = ldb;
+    b.mn_major = 0; b.hdiv = nb; b.hstride = 0; b.col0 = 0;  // g / nb == 0: every batch reads B
+    GemmEpilogue eb = e;
+    eb.seg_len = 0;
+    const long long es = e.out_bf16 ? 2 : 4;
+    eb.out = static_cast<char*>(e.out) + static_cast<long long>(e.seg_off) * e.ld_out * es;
+    return gemm_bf16_batched_launch(a, b, nb, e.seg_len, p.N, p.K, eb, 1, 0,
+                                    static_cast<long long>(e.seg_stride) * e.ld_out, stream);
+  }
   const int kb_total = (p.K + BK - 1) / BK;
   if (p.splits < 1) p.splits = 1;
   if (p.splits > 1 && e.mode != EPI_ATOMIC) return MMU_ERR_SHAPE;
@@ -125,6 +216,7 @@ int gemm_bf16_launch(const void* A, long long lda, const void* B, long long ldb,
     const int kb_per = (kb_total + p.splits - 1) / p.splits;
     p.splits = (kb_total + kb_per - 1) / kb_per;
   }
+  p.batch = 0;
   CUtensorMap ta, tb;
   int rc;
   if (!p.a_mn_major) rc = make_tmap_bf16_2d(&ta, A, p.K, p.M, lda, BK, BM);
@@ -137,21 +229,14 @@ int gemm_bf16_launch(const void* A, long long lda, const void* B, long long ldb,
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
   const long long tiles = 1LL * m_tiles * n_tiles * p.splits;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  switch (e.mode) {
-    case EPI_STORE: return launch_mode<EPI_STORE>(grid, ta, tb, p, e, stream);
-    case EPI_QUICKGELU: return launch_mode<EPI_QUICKGELU>(grid, ta, tb, p, e, stream);
-    case EPI_RESIDUAL: return launch_mode<EPI_RESIDUAL>(grid, ta, tb, p, e, stream);
-    case EPI_DGELU: return launch_mode<EPI_DGELU>(grid, ta, tb, p, e, stream);
-    case EPI_ATOMIC: return launch_mode<EPI_ATOMIC>(grid, ta, tb, p, e, stream);
-    default: return MMU_ERR_ARG;
-  }
+  return launch_with_epilogue(grid, ta, tb, p, e, stream);
 }
 
 int gemm_bf16_batched_launch(const BatchedOperand& A, const BatchedOperand& B, int batch, int M,
                              int N, int K, const GemmEpilogue& e, int out_hdiv, int out_hstride,
                              long long out_mid_stride, cudaStream_t stream) {
   using namespace gemm;
-  if (batch <= 0 || M <= 0 || N <= 0 || K <= 0 || N % 4 != 0) return MMU_ERR_SHAPE;
+  if (batch <= 0 || M <= 0 || N <= 0 || K <= 0) return MMU_ERR_SHAPE;
   if (e.mode != EPI_STORE) return MMU_ERR_ARG;
   GemmProblem p{};
   p.M = M; p.N = N; p.K = K;
@@ -160,7 +245,8 @@ int gemm_bf16_batched_launch(const BatchedOperand& A, const BatchedOperand& B, i
   p.batch = batch;
   p.a_hdiv = A.hdiv; p.a_hstride = A.hstride; p.a_col0 = A.col0;
   p.b_hdiv = B.hdiv; p.b_hstride = B.hstride; p.b_col0 = B.col0;
-  p.out_hdiv = out_hdiv; p.out_hstride = out_hstride; p.out_mid_stride = out_mid_stride;
+  p.out_hdiv = out_hdiv < 1 ? 1 : out_hdiv; p.out_hstride = out_hstride;
+  p.out_mid_stride = out_mid_stride;
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16_3d(&ta, A.base, A.inner, A.mid, A.outer, A.mid_stride, A.outer_stride,
                              A.mn_major ? 64 : BK, A.mn_major ? BK : BM);
@@ -171,7 +257,7 @@ int gemm_bf16_batched_launch(const BatchedOperand& A, const BatchedOperand& B, i
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
   const long long tiles = 1LL * batch * m_tiles * n_tiles;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  return launch_mode<EPI_STORE>(grid, ta, tb, p, e, stream);
+  return launch_with_epilogue(grid, ta, tb, p, e, stream);
 }
 
 }  // namespace mmu

@@ -1,8 +1,10 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a:
-//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared memory ring (4 stages)
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared memory ring (4 stages of 48 KB)
 //   -> tcgen05.mma (one elected thread, 128x256x16 UMMA, fp32 accumulators in TMEM,
 //      two accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1)
-//   -> tcgen05.ld -> fused epilogue (bias / QuickGELU / residual / dGELU / split-K atomics).
+//   -> tcgen05.ld -> fused epilogue in registers (bias / QuickGELU / dGELU) -> swizzled shared
+//      staging boxes -> TMA tensor stores (cp.async.bulk.tensor store, or cp.reduce .add for the
+//      split-K weight gradients).  The dGELU operand z is TMA-loaded into the same boxes.
 //
 // Computes  C[M,N] = epilogue( sum_k A(m,k) * B(n,k) ).
 // Either operand may be K-major (stored [rows][K], K contiguous) or MN-major (stored
@@ -12,6 +14,16 @@
 // This is the tensor-core path for every dense contraction of the fusion model
 // (reference call sites: src/model.py:262,264 projections; :193 MHA in/out proj;
 // :195-201 MLP c_fc/c_proj) and their backward passes.
+//
+// Epilogue geometry: 8 warps; warp w owns TMEM lanes 32*(w%4).. (hardware rule) and a 128-column
+// half of the 256-column accumulator, i.e. a 32-row x 128-column slab, processed in chunks of 32
+// (bf16 out) or 16 (fp32 out) columns with tcgen05.ld (lane = row, registers = consecutive
+// columns).  A chunk is written as four 16-byte pieces per lane into a [32 rows x 64 B] staging
+// box laid out exactly as TMA's SWIZZLE_64B expects (piece index XOR ((row >> 1) & 3)):
+// conflict-free for the writers, and one TMA store per box then emits full 64-byte row segments
+// -- no per-thread global stores and no edge predicates (the tensor map clips rows >= M and
+// columns >= N).  Each warp alternates between two boxes, so writing chunk c overlaps the drain
+// of chunk c-1; 4 operand stages (192 KB) + 32 KB of boxes fill the SM's shared memory.
 #pragma once
 #include "gemm_api.h"
 #include "ptx.cuh"
@@ -28,14 +40,22 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int STG_LD = 32;                         // staging row (floats), XOR-swizzled 16 B chunks
-constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;    // 4096 B per epilogue warp
 constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = 2 * BN;                       // two accumulator stages (512 = all of TMEM)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * STG_WARP_BYTES + 256 /*barriers*/ +
-                           1024 /*alignment slack*/;
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
+constexpr int BOX_ROWS = 32;
+constexpr int BOX_BYTES = BOX_ROWS * 64;                // 32 rows x 64 B (32 bf16 / 16 fp32 columns)
+constexpr int STG_WARP_BYTES = 2 * BOX_BYTES;           // two boxes per epilogue warp
+constexpr int OFF_STG = STAGES * STAGE_BYTES;           // 1024-aligned
+constexpr int OFF_BIAS = OFF_STG + NUM_EPI_WARPS * STG_WARP_BYTES;
+constexpr int OFF_BARS = OFF_BIAS + 2 * BN * 4;         // bias tile, double buffered
+constexpr int SMEM_USED = OFF_BARS + 256;               // + barriers
+constexpr int SMEM_BYTES = 227 * 1024;                  // everything an SM has; the kernel checks
+                                                        // that SMEM_USED fits behind the 1024-byte
+                                                        // alignment of the dynamic window
+static_assert(OFF_STG % 1024 == 0, "staging boxes must stay aligned for the swizzle pattern");
+static_assert(SMEM_USED <= SMEM_BYTES, "shared memory budget exceeded");
 
 // sigmoid(1.702 z) = 0.5 tanh(0.851 z) + 0.5: ONE MUFU op (tanh.approx, rel. error ~2^-11, far
 // below bf16 resolution) instead of ex2 + rcp -- the GELU epilogues are MUFU-bound otherwise.
@@ -50,107 +70,46 @@ __device__ __forceinline__ float quick_gelu_grad(float z) {
   return s * fmaf(1.702f * z, 1.0f - s, 1.0f);
 }
 
-__device__ __forceinline__ void store4(void* base, int is_bf16, long long off, float4 v) {
-  if (is_bf16) {
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-    __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(base) + off) = pk;
-  } else {
-    *reinterpret_cast<float4*>(static_cast<float*>(base) + off) = v;
-  }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__device__ __forceinline__ float4 load4_bf16(const void* base, long long off) {
-  const uint2 pk = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(base) + off);
-  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
-  const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
-  const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-
-template <int MODE>
-struct AuxT { using type = int; };
-template <>
-struct AuxT<EPI_RESIDUAL> { using type = float4; };
-template <>
-struct AuxT<EPI_DGELU> { using type = uint2; };
-
-// asm volatile: the prefetch must ISSUE where it is written (ptxas otherwise sinks plain loads
-// towards their first use under register pressure, exposing the full DRAM latency).
-template <int MODE>
-__device__ __forceinline__ typename AuxT<MODE>::type load_aux(const GemmEpilogue& e, long long orow,
-                                                              int gcol) {
-  if constexpr (MODE == EPI_RESIDUAL) {
-    const float* p = static_cast<const float*>(e.aux) + orow * e.ld_aux + gcol;
-    float4 v;
-    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p));
-    return v;
-  } else if constexpr (MODE == EPI_DGELU) {
-    const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(e.aux) + orow * e.ld_aux + gcol;
-    uint2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    return v;
-  } else {
-    return 0;
-  }
-}
-
-__device__ __forceinline__ float4 unpack_bf16x4(uint2 pk) {
-  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
-  const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
-  const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-
-template <int MODE>
-__device__ __forceinline__ void epi_apply(const GemmEpilogue& e, long long orow, int gcol, float4 v,
-                                          float4 bias, typename AuxT<MODE>::type aux) {
-  v.x = fmaf(v.x, e.alpha, bias.x); v.y = fmaf(v.y, e.alpha, bias.y);
-  v.z = fmaf(v.z, e.alpha, bias.z); v.w = fmaf(v.w, e.alpha, bias.w);
-  if constexpr (MODE == EPI_STORE) {
-    store4(e.out, e.out_bf16, orow * e.ld_out + gcol, v);
-  } else if constexpr (MODE == EPI_QUICKGELU) {
-    if (e.out != nullptr) store4(e.out, e.out_bf16, orow * e.ld_out + gcol, v);
-    float4 u;
-    u.x = quick_gelu(v.x); u.y = quick_gelu(v.y); u.z = quick_gelu(v.z); u.w = quick_gelu(v.w);
-    store4(e.out2, e.out_bf16, orow * e.ld_out2 + gcol, u);
-  } else if constexpr (MODE == EPI_RESIDUAL) {
-    v.x += aux.x; v.y += aux.y; v.z += aux.z; v.w += aux.w;
-    store4(e.out, e.out_bf16, orow * e.ld_out + gcol, v);
-  } else if constexpr (MODE == EPI_DGELU) {
-    const float4 z = unpack_bf16x4(aux);
-    v.x *= quick_gelu_grad(z.x); v.y *= quick_gelu_grad(z.y);
-    v.z *= quick_gelu_grad(z.z); v.w *= quick_gelu_grad(z.w);
-    store4(e.out, e.out_bf16, orow * e.ld_out + gcol, v);
-  } else if constexpr (MODE == EPI_ATOMIC) {
-    ptx::red_add_v4(static_cast<float*>(e.out) + orow * e.ld_out + gcol, v);
-  }
-}
-
-template <int MODE>
+// MODE: GemmEpiMode; OBF: outputs (and the dGELU operand) are bf16, else fp32.
+// tma_c0: `out`; tma_c1: `out2` (QUICKGELU) or `aux` (DGELU).  Both are 4-D maps
+// (columns, rows, batch % out_hdiv, batch / out_hdiv) with a [32 x 128 B] box.
+template <int MODE, bool OBF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
-                         const __grid_constant__ CUtensorMap tma_b, const GemmProblem p,
+                         const __grid_constant__ CUtensorMap tma_b,
+                         const __grid_constant__ CUtensorMap tma_c0,
+                         const __grid_constant__ CUtensorMap tma_c1, const GemmProblem p,
                          const GemmEpilogue e) {
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operand tiles need 1024-byte alignment.
+  // SWIZZLE_128B operand tiles and staging boxes need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  float* smem_stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES +
-                                               NUM_EPI_WARPS * STG_WARP_BYTES);
-  uint64_t* full_bar = bars;                  // [STAGES]  TMA -> MMA
-  uint64_t* empty_bar = bars + STAGES;        // [STAGES]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]       MMA -> epilogue
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]    epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+  uint64_t* full_bar = bars;                     // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;           // [STAGES]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]       MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA
+  uint64_t* aux_bar = bars + 2 * STAGES + 4;     // [NUM_EPI_WARPS][2] dGELU operand box landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * NUM_EPI_WARPS);
+  if (threadIdx.x == 0 && (smem - smem_raw) + SMEM_USED > SMEM_BYTES) {
+    printf("mmu: dynamic shared memory window is not 1024-byte aligned (offset %d)\n",
+           static_cast<int>(smem - smem_raw));
+    __trap();
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -165,6 +124,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tma_a);
     ptx::prefetch_tmap(&tma_b);
+    ptx::prefetch_tmap(&tma_c0);
+    if (MODE == EPI_QUICKGELU || MODE == EPI_DGELU) ptx::prefetch_tmap(&tma_c1);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -175,6 +136,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], NUM_EPI_WARPS);
     }
+    for (int i = 0; i < 2 * NUM_EPI_WARPS; ++i) ptx::mbar_init(&aux_bar[i], 1);
     ptx::fence_mbar_init();
     ptx::fence_proxy_async();
   }
@@ -286,95 +248,171 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
   } else {
     // ---------------------------------------------------------------- epilogue
-    // 8 warps: TMEM lane quadrant q = warp % 4 (hardware rule), column half h = (warp-2)/4.
-    // Per 32-column chunk: tcgen05.ld -> padded smem transpose -> 128-bit coalesced row stores.
-    // The TMEM load and the aux (residual / z) loads of chunk c+1 are issued before chunk c is
-    // written out, so their latency overlaps the store phase.
-    using Aux = typename AuxT<MODE>::type;
-    // aux prefetch depth: 3 chunks for the 8-byte bf16 z (DGELU), 2 for the 16-byte residual
-    constexpr int NBUF = (MODE == EPI_DGELU) ? 3 : 2;
-    const int q = warp & 3;
-    const int h = (warp - 2) >> 2;
-    const uint32_t stg = ptx::smem_u32(smem_stg + (warp - 2) * (32 * STG_LD));
-    const int rr = lane >> 3;        // 0..3
-    const int cc = (lane & 7) * 4;   // 0..28
-    constexpr int NCHUNK = BN / 2 / 32;
+    const int we = warp - 2;         // 0..7
+    const int q = warp & 3;          // TMEM lane quadrant (hardware: lanes 32*(warp%4)..)
+    const int h = we >> 2;           // which 128-column half of the accumulator
+    const int et = threadIdx.x - 64; // 0..255
+    const uint32_t box0 = ptx::smem_u32(smem + OFF_STG + we * STG_WARP_BYTES);
+    const uint32_t row_off = static_cast<uint32_t>(lane) * 64u;   // this lane's row in a box
+    const uint32_t sw = static_cast<uint32_t>(lane >> 1) & 3u;    // SWIZZLE_64B piece XOR
+    auto piece = [&](int k) { return row_off + ((static_cast<uint32_t>(k) ^ sw) << 4); };
+    float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
+    const uint32_t bias_addr = ptx::smem_u32(bias_s);
+    const bool has_bias = e.bias != nullptr;
+    constexpr int NCOL = OBF ? 32 : 16;         // columns per chunk = per staging box
+    constexpr int NCHUNK = BN / 2 / NCOL;
+    uint64_t* my_aux = aux_bar + 2 * we;
     int as = 0;
-    uint32_t aphase = 0;
+    uint32_t aphase = 0, aux_phase[2] = {0, 0};
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mnb = tile / p.splits;
       const int g = mnb / (m_tiles * n_tiles);
       const int mn = mnb % (m_tiles * n_tiles);
+      const int nt0 = (mn % n_tiles) * BN;
       const int m0 = (mn / n_tiles) * BM + q * 32;
-      const int n0 = (mn % n_tiles) * BN + h * (BN / 2);
-      GemmEpilogue eb = e;
-      if (p.batch > 0) {
-        const long long boff = (long long)(g / p.out_hdiv) * p.out_mid_stride +
-                               (long long)(g % p.out_hdiv) * p.out_hstride;
-        eb.out = e.out_bf16 ? static_cast<void*>(static_cast<__nv_bfloat16*>(e.out) + boff)
-                            : static_cast<void*>(static_cast<float*>(e.out) + boff);
+      const int n0 = nt0 + h * (BN / 2);
+      const int c2 = p.batch > 0 ? g % p.out_hdiv : 0;
+      const int c3 = p.batch > 0 ? g / p.out_hdiv : 0;
+      const bool active = m0 < p.M && n0 < p.N;  // warp-uniform
+
+      // the tile's bias slice, once, into shared memory (double buffered across tiles)
+      if (has_bias) {
+        const int col = nt0 + et;
+        bias_s[as * BN + et] = col < p.N ? e.bias[col] : 0.f;
       }
-      int orow[8];
-      bool rok[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int grow = m0 + rr + 4 * i;
-        rok[i] = grow < p.M;
-        orow[i] = grow;
-        if (e.seg_len > 0)
-          orow[i] = (grow / e.seg_len) * e.seg_stride + e.seg_off + grow % e.seg_len;
-      }
-      Aux aux[NBUF][8];
-      auto prefetch_aux = [&](int c) {
-        if (c < NCHUNK && n0 + c * 32 + cc < p.N) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (rok[i]) aux[c % NBUF][i] = load_aux<MODE>(eb, orow[i], n0 + c * 32 + cc);
-        }
+      named_bar_sync(1, NUM_EPI_THREADS);
+
+      // dGELU: the z boxes of the first two chunks start loading while the MMAs of the tile run
+      auto load_z = [&](int c) {  // lane 0 only; box (c & 1) must be drained
+        ptx::mbar_arrive_expect_tx(&my_aux[c & 1], BOX_BYTES);
+        ptx::tma_load_4d(box0 + (c & 1) * BOX_BYTES, &tma_c1, &my_aux[c & 1], n0 + c * NCOL, m0, c2, c3);
       };
-      // issued BEFORE waiting for the accumulator: the loads fly while the MMAs finish
-#pragma unroll
-      for (int c = 0; c < NBUF - 1; ++c) prefetch_aux(c);
+      if (MODE == EPI_DGELU && active && lane == 0) {
+        ptx::bulk_wait_read<0>();  // the previous tile's stores have drained both boxes
+        load_z(0);
+        if (n0 + NCOL < p.N) load_z(1);
+      }
 
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(as * BN + h * (BN / 2));
-      uint32_t r[32];
-      if (n0 < p.N) ptx::tmem_ld_32x32(taddr, r);
+      uint32_t r[2][NCOL];
+      auto tmem_load = [&](int c) {
+        if constexpr (OBF) ptx::tmem_ld_32x32(taddr + c * NCOL, r[c & 1]);
+        else ptx::tmem_ld_32x16(taddr + c * NCOL, r[c & 1]);
+      };
+      // box `b` may be rewritten once the store issued two boxes ago has read it
+      auto box_free = [&](bool first) {
+        if (lane == 0) {
+          if (first) ptx::bulk_wait_read<0>();
+          else ptx::bulk_wait_read<1>();
+        }
+        __syncwarp();
+      };
+      auto box_store = [&](const CUtensorMap* map, uint32_t box, int col) {
+        ptx::fence_proxy_async();  // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (MODE == EPI_ATOMIC) ptx::tma_reduce_add_4d(map, box, col, m0, c2, c3);
+          else ptx::tma_store_4d(map, box, col, m0, c2, c3);
+          ptx::bulk_commit();
+        }
+      };
+      if (active) tmem_load(0);
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 < p.N) {
+        const int col0 = n0 + c * NCOL;
+        if (active && col0 < p.N) {
           ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-            ptx::sts_v4(stg + (lane * STG_LD + 4 * (j ^ (lane & 7))) * 4, v);
+          if (c + 1 < NCHUNK && col0 + NCOL < p.N) {
+            tmem_load(c + 1);
+          } else {
+            // every accumulator value of this warp is in registers: hand the TMEM stage back
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
           }
-          __syncwarp();
-          if (c + 1 < NCHUNK && col0 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, r);
-          prefetch_aux(c + NBUF - 1);
-          const int gcol = col0 + cc;
-          if (gcol < p.N) {
-            float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e.bias != nullptr) bias = *reinterpret_cast<const float4*>(e.bias + gcol);
+          float v[NCOL];
+          {
+            const uint32_t baddr = bias_addr + static_cast<uint32_t>(as * BN + h * (BN / 2) + c * NCOL) * 4u;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int srow = rr + 4 * i;
-              const float4 v = ptx::lds_v4(stg + (srow * STG_LD + 4 * ((lane & 7) ^ (srow & 7))) * 4);
-              if (rok[i]) epi_apply<MODE>(eb, orow[i], gcol, v, bias, aux[c % NBUF][i]);
+            for (int j = 0; j < NCOL / 4; ++j) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has_bias) b4 = ptx::lds_v4(baddr + 16 * j);
+              v[4 * j + 0] = fmaf(__uint_as_float(r[c & 1][4 * j + 0]), e.alpha, b4.x);
+              v[4 * j + 1] = fmaf(__uint_as_float(r[c & 1][4 * j + 1]), e.alpha, b4.y);
+              v[4 * j + 2] = fmaf(__uint_as_float(r[c & 1][4 * j + 2]), e.alpha, b4.z);
+              v[4 * j + 3] = fmaf(__uint_as_float(r[c & 1][4 * j + 3]), e.alpha, b4.w);
             }
           }
-          __syncwarp();
+          const uint32_t box = box0 + static_cast<uint32_t>(c & 1) * BOX_BYTES;
+          if constexpr (!OBF) {
+            box_free(c == 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::sts_v4(box + piece(k), make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+            box_store(&tma_c0, box, col0);
+          } else if constexpr (MODE == EPI_DGELU) {
+            ptx::mbar_wait(&my_aux[c & 1], aux_phase[c & 1]);
+            aux_phase[c & 1] ^= 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t a = box + piece(k);
+              const uint4 z = ptx::lds_v4u(a);
+              const uint32_t zz[4] = {z.x, z.y, z.z, z.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                o[i] = pack_bf16x2(v[8 * k + 2 * i] * quick_gelu_grad(bf16_lo(zz[i])),
+                                   v[8 * k + 2 * i + 1] * quick_gelu_grad(bf16_hi(zz[i])));
+              ptx::sts_v4u(a, o[0], o[1], o[2], o[3]);
+            }
+            box_store(&tma_c0, box, col0);
+            if (c + 2 < NCHUNK && col0 + 2 * NCOL < p.N && lane == 0) {
+              ptx::bulk_wait_read<0>();  // the store above has read the box: refill it
+              load_z(c + 2);
+            }
+          } else if constexpr (MODE == EPI_QUICKGELU) {
+            if (e.out != nullptr) {  // training: z -> box 0, u -> box 1, each its own bulk group
+              box_free(c == 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::sts_v4u(box0 + piece(k), pack_bf16x2(v[8 * k], v[8 * k + 1]),
+                             pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                             pack_bf16x2(v[8 * k + 4], v[8 * k + 5]),
+                             pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+              box_store(&tma_c0, box0, col0);
+            }
+#pragma unroll
+            for (int i = 0; i < NCOL; ++i) v[i] = quick_gelu(v[i]);
+            const uint32_t ubox = e.out != nullptr ? box0 + BOX_BYTES : box;
+            box_free(e.out == nullptr && c == 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::sts_v4u(ubox + piece(k), pack_bf16x2(v[8 * k], v[8 * k + 1]),
+                           pack_bf16x2(v[8 * k + 2], v[8 * k + 3]), pack_bf16x2(v[8 * k + 4], v[8 * k + 5]),
+                           pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+            box_store(&tma_c1, ubox, col0);
+          } else {
+            box_free(c == 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::sts_v4u(box + piece(k), pack_bf16x2(v[8 * k], v[8 * k + 1]),
+                           pack_bf16x2(v[8 * k + 2], v[8 * k + 3]), pack_bf16x2(v[8 * k + 4], v[8 * k + 5]),
+                           pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+            box_store(&tma_c0, box, col0);
+          }
         }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+      if (!active) {  // nothing to read: still one arrival per warp per tile
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (lane == 0) ptx::bulk_wait<0>();  // all stores of this warp have completed at exit
   }
 
   ptx::tc_fence_before();

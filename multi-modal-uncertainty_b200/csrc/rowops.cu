@@ -446,10 +446,13 @@ pool_ln_bwd_kernel(const float* __restrict__ dvec, const float* __restrict__ x,
   block_colreduce<NV>(acc_b, red, dbeta, nvec, D);
 }
 
-// One block = one head x HEADS_TB samples: every weight row is read once per block and reused
-// against all HEADS_TB pooled vectors held in shared memory (the weights are L2 resident, but
-// re-reading the full (C, D) matrix per sample made this tiny op L2-bandwidth bound).
+// One block = one head x HEADS_TB samples x a slice of the classes: every weight row is read once
+// per block and reused against all HEADS_TB pooled vectors held in shared memory.  The op is tiny
+// (B*E*C*D MACs) but latency bound: the class range is split over blockIdx.z and each warp keeps
+// the weight rows of TWO classes in flight (12 independent 16-byte loads per lane) so the few
+// blocks that exist expose enough memory-level parallelism to pull the weights at speed.
 constexpr int HEADS_TB = 8;
+constexpr int HEADS_ZS = 4;
 __global__ void __launch_bounds__(256)
 heads_fwd_kernel(const float* __restrict__ vec, HeadParams hp, float* __restrict__ logits, int B,
                  int E, int C, int D) {
@@ -465,23 +468,48 @@ heads_fwd_kernel(const float* __restrict__ vec, HeadParams hp, float* __restrict
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const float* W = hp.w[e];
-  for (int c = warp; c < C; c += nw) {
-    float acc[HEADS_TB];
+  const int cper = (C + gridDim.z - 1) / gridDim.z;
+  const int c_begin = blockIdx.z * cper, c_end = min(C, c_begin + cper);
+  for (int c = c_begin + 2 * warp; c < c_end; c += 2 * nw) {
+    const bool two = c + 1 < c_end;
+    const float* w0 = W + static_cast<size_t>(c) * D;
+    const float* w1 = W + static_cast<size_t>(two ? c + 1 : c) * D;
+    float acc0[HEADS_TB], acc1[HEADS_TB];
 #pragma unroll
-    for (int t = 0; t < HEADS_TB; ++t) acc[t] = 0.f;
-    for (int i = lane * 4; i < D; i += 128) {
-      const float4 w = *reinterpret_cast<const float4*>(W + static_cast<size_t>(c) * D + i);
+    for (int t = 0; t < HEADS_TB; ++t) { acc0[t] = 0.f; acc1[t] = 0.f; }
+    for (int i0 = lane * 4; i0 < D; i0 += 128 * 3) {
+      float4 a[3], b[3];
 #pragma unroll
-      for (int t = 0; t < HEADS_TB; ++t) {
-        const float4 v = *reinterpret_cast<const float4*>(sv + t * D + i);
-        acc[t] += (w.x * v.x + w.y * v.y) + (w.z * v.z + w.w * v.w);
+      for (int u = 0; u < 3; ++u) {
+        const int i = i0 + 128 * u;
+        a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < D) {
+          a[u] = *reinterpret_cast<const float4*>(w0 + i);
+          b[u] = *reinterpret_cast<const float4*>(w1 + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int i = i0 + 128 * u;
+        if (i < D) {
+#pragma unroll
+          for (int t = 0; t < HEADS_TB; ++t) {
+            const float4 v = *reinterpret_cast<const float4*>(sv + t * D + i);
+            acc0[t] += (a[u].x * v.x + a[u].y * v.y) + (a[u].z * v.z + a[u].w * v.w);
+            acc1[t] += (b[u].x * v.x + b[u].y * v.y) + (b[u].z * v.z + b[u].w * v.w);
+          }
+        }
       }
     }
-    const float bias = hp.b[e][c];
+    const float bias0 = hp.b[e][c], bias1 = hp.b[e][two ? c + 1 : c];
 #pragma unroll
     for (int t = 0; t < HEADS_TB; ++t) {
-      const float sum = warp_sum(acc[t]);
-      if (lane == 0 && t < nb) logits[(static_cast<size_t>(b0 + t) * E + e) * C + c] = sum + bias;
+      const float s0 = warp_sum(acc0[t]), s1 = warp_sum(acc1[t]);
+      if (lane == 0 && t < nb) {
+        float* o = logits + (static_cast<size_t>(b0 + t) * E + e) * C + c;
+        o[0] = s0 + bias0;
+        if (two) o[1] = s1 + bias1;
+      }
     }
   }
 }
@@ -730,8 +758,8 @@ int pool_ln_bwd(const float* dvec, const float* x, const float* mean, const floa
 int heads_fwd(const float* vec, const HeadParams& hp, float* logits, int B, int E, int C, int D,
               cudaStream_t stream) {
   if (D % 4 != 0 || E > 16) return MMU_ERR_SHAPE;
-  heads_fwd_kernel<<<dim3((B + HEADS_TB - 1) / HEADS_TB, E), 256, HEADS_TB * D * sizeof(float),
-                     stream>>>(vec, hp, logits, B, E, C, D);
+  heads_fwd_kernel<<<dim3((B + HEADS_TB - 1) / HEADS_TB, E, HEADS_ZS), 256,
+                     HEADS_TB * D * sizeof(float), stream>>>(vec, hp, logits, B, E, C, D);
   MMU_CHECK_LAUNCH();
   return 0;
 }

@@ -101,3 +101,71 @@ def get_synthetic_flava(batch_size, n_train, n_val, n_test, seed=42, shuffle=Tru
                                      shuffle=sh, collate_fn=collate_fn_flava, generator=g,
                                      drop_last=False)
     return mk(n_train, seed, shuffle), mk(n_val, seed + 1, False), mk(n_test, seed + 2, False)
+
+
+class DevicePrefetcher:
+    """Iterates a loader of HOST batches ``((img, txt), y)`` and yields them on ``device``:
+    batch i+1 is copied host->device on a side stream (from pinned memory: a true async DMA)
+    while batch i is being consumed, so the copy overlaps the step's kernels instead of
+    preceding them.  Replaces the per-step blocking ``.to(device)`` of the reference loop
+    (src/framework.py:277-279); batches it yields pass through ``Model_.train_step`` /
+    ``eval_step`` unchanged (``.to(device)`` on a resident tensor is a no-op).
+
+    The device side is two persistent slots (no allocation in steady state; a slot is
+    re-filled only after an event recorded behind the consumer's last use of it), so a yielded
+    batch is valid until the consumer asks for the batch after the next one."""
+
+    SLOTS = 2
+
+    def __init__(self, loader, device, pin=True):
+        self.loader, self.device, self.pin = loader, torch.device(device), pin
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._bufs = [dict() for _ in range(self.SLOTS)]
+
+    def _copy(self, obj, slot, path):
+        if obj is None:
+            return None
+        if isinstance(obj, (tuple, list)):
+            return type(obj)(self._copy(o, slot, path + (i,)) for i, o in enumerate(obj))
+        if self.pin and not obj.is_pinned():
+            obj = obj.pin_memory()
+        buf = self._bufs[slot].get(path)
+        if buf is None or buf.shape != obj.shape or buf.dtype != obj.dtype:
+            buf = torch.empty(obj.shape, dtype=obj.dtype, device=self.device)
+            self._bufs[slot][path] = buf
+        with torch.cuda.stream(self.stream):
+            buf.copy_(obj, non_blocking=True)
+        return buf
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        it = iter(self.loader)
+        released = [None] * self.SLOTS  # event behind the consumer's last use of each slot
+        state = {"k": 0}
+
+        def fetch():
+            try:
+                host = next(it)
+            except StopIteration:
+                return None
+            slot = state["k"] % self.SLOTS
+            state["k"] += 1
+            if released[slot] is not None:
+                self.stream.wait_event(released[slot])
+            dev = self._copy(host, slot, ())
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+            return dev, ready, slot
+
+        nxt = fetch()
+        while nxt is not None:
+            batch, ready, slot = nxt
+            cur = torch.cuda.current_stream(self.device)
+            nxt = fetch()            # batch i+1 starts copying now (into the other slot)
+            cur.wait_event(ready)    # batch i has landed before the step touches it
+            yield batch
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            released[slot] = ev

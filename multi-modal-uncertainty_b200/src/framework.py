@@ -113,8 +113,12 @@ class Model_:
                                       "(SURVEY.md 8c: third-party arithmetic, parity unpinned)")
 
     # ---------------------------------------------------------------- hot path
-    def train_step(self, x, y, scheduler_step_on="batch", keep_mask=None):
-        """One optimisation step on a HOST batch; returns (loss: float, metrics: ndarray, size)."""
+    def train_step(self, x, y, scheduler_step_on="batch", keep_mask=None, sync=True):
+        """One optimisation step on a HOST (or prefetched device) batch; returns
+        (loss: float, metrics: ndarray, size).  ``sync=False`` returns the loss and the metrics
+        as 0-dim DEVICE tensors instead, so the caller chooses when to pay the device->host read
+        (the reference reads ``loss.item()`` and every metric right here, src/framework.py:305-312,
+        which drains the GPU queue twice per step)."""
         x, y = self.data_forming(x, y, phase="train")
         x, y = self.to_device(x), self.to_device(y)
         self.optimizer.zero_grad()
@@ -123,10 +127,13 @@ class Model_:
         loss.backward()
         self.optimizer.step()
         with torch.no_grad():
-            info = self._compute_metrics(y_pred, y, eval=False, dummy_dim=True)
+            if sync:
+                info = self._compute_metrics(y_pred, y, eval=False, dummy_dim=True)
+            else:
+                info = [m(y_pred, y, False, True) for m in self.metrics]
         if scheduler_step_on == "batch" and self.scheduler is not None:
             self.scheduler.step()
-        return loss.item(), info, len(y)
+        return (loss.item() if sync else loss.detach()), info, len(y)
 
     @torch.no_grad()
     def eval_step(self, x, y):

@@ -155,7 +155,36 @@ class FlavaFusionTransfomer(nn.Module):
             holder.register_parameter(leaf, p)
         self._rebind(self._flat, self._flat_grad)
 
+    # ---- bf16 shadow of the parameters (tcgen05 GEMM operand), one per model.  It is refreshed
+    #      only when a parameter changed: in-place torch ops on any parameter bump that
+    #      parameter's version counter, and the fused AdamW (which writes through raw pointers)
+    #      updates the shadow itself inside its kernel and re-stamps it.
+    def _param_stamp(self):
+        return self._flat._version + sum(p._version for p in self._param_list)
+
+    def invalidate_shadow(self):
+        """Call after modifying parameters in a way autograd's version counters cannot see
+        (writes through ``p.data`` or a raw device pointer)."""
+        self._shadow_stamp = None
+
+    def _fresh_shadow(self):
+        if self.precision != _PREC["bf16"]:
+            return None
+        stamp = self._param_stamp()
+        if self._shadow is None or self._shadow.device != self._flat.device:
+            self._shadow = torch.empty(self._flat.numel(), dtype=torch.bfloat16,
+                                       device=self._flat.device)
+            self._shadow_stamp = None
+        if stamp != self._shadow_stamp:
+            _lib.check(_lib.lib.mmu_cast_f32_to_bf16(self._flat.data_ptr(), self._shadow.data_ptr(),
+                                                     self._flat.numel(), _lib.stream_ptr()),
+                       "mmu_cast_f32_to_bf16")
+            self._shadow_stamp = stamp
+        return self._shadow
+
     def _rebind(self, flat, flat_grad):
+        self._shadow, self._shadow_stamp = None, None
+        self._param_list = list(self.parameters())
         self._flat, self._flat_grad = flat, flat_grad
         params = dict(self.named_parameters())
         for name, off, numel, rows, cols, _stage in self._table:
@@ -255,8 +284,9 @@ class FlavaFusionTransfomer(nn.Module):
         n_txt = (idx_txt.numel() if idx_txt is not None else l_txt) if txt is not None else 0
         cfg = self._config(B, max(l_img, 1), max(l_txt, 1))
         ws = self._workspace(cfg, training)
+        shadow = self._fresh_shadow()
         inp = _lib.FlavaInputs(_lib.ptr(img), _lib.ptr(txt), _lib.ptr(idx_img), _lib.ptr(idx_txt),
-                               n_img, n_txt, _lib.ptr(keep))
+                               n_img, n_txt, _lib.ptr(keep), _lib.ptr(shadow))
         logits = torch.empty(B, self.out_dim, self.num_classes, device=dev, dtype=torch.float32)
         _lib.check(_lib.lib.mmu_flava_forward(C.byref(cfg), self._flat.data_ptr(), C.byref(inp),
                                               ws.data_ptr(), ws.numel(), int(training),

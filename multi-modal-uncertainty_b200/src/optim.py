@@ -51,9 +51,14 @@ class FusedAdamW(torch.optim.Optimizer):
         g = self.param_groups[0]
         m, v = self._moments()
         self._step += 1
-        ops.adamw_flat_step(self.model._flat, self.model._flat_grad, m, v, self._step, float(g["lr"]),
+        model = self.model
+        shadow = model._shadow if model._shadow is not None and \
+            model._shadow.device == model._flat.device else None
+        ops.adamw_flat_step(model._flat, model._flat_grad, m, v, self._step, float(g["lr"]),
                             betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"],
-                            grad_scale=self.grad_scale)
+                            grad_scale=self.grad_scale, p_bf16=shadow)
+        if shadow is not None:  # the kernel rewrote the bf16 shadow together with the master
+            model._shadow_stamp = model._param_stamp()
 
     # checkpoint format compatible with torch.optim.AdamW's (per-parameter state, reference
     # src/utils.py:98-106 saves {'model', 'optimizer'})

@@ -263,3 +263,46 @@ def test_size_independent_properties(mmu):
     m.compute_loss(m((img, txt)), y).backward()
     assert float(m.text_to_mm_projection.weight.grad.abs().max()) == 0.0
     assert float(m.image_to_mm_projection.weight.grad.abs().max()) > 0.0
+
+
+def test_bf16_shadow_tracks_parameter_updates(mmu, golden):
+    """The bf16 GEMM-operand shadow is refreshed lazily: in-place parameter updates, the fused
+    AdamW step and invalidate_shadow() must all be seen by the next forward."""
+    c = golden("flava_small.pt")["plain_E2"]
+    img, txt, y = c["img"].cuda(), c["txt"].cuda(), c["y_train"].cuda()
+
+    def fresh_copy(model):
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        return build(mmu, c["cfg"], sd, "bf16").eval()
+
+    m = build(mmu, c["cfg"], c["state_dict"], "bf16").eval()
+    with torch.no_grad():
+        base = m((img, txt)).clone()
+        m.image_to_mm_projection.weight.mul_(0.5)          # in-place op: version counter bumps
+        after = m((img, txt))
+        assert not torch.equal(after, base)
+        assert torch.equal(after, fresh_copy(m)((img, txt)))
+        m.text_to_mm_projection.weight.data.mul_(0.5)      # invisible to the version counters
+        m.invalidate_shadow()
+        assert torch.equal(m((img, txt)), fresh_copy(m)((img, txt)))
+    m.train()
+    opt = mmu.FusedAdamW(m.parameters(), lr=1e-2)
+    for _ in range(2):
+        opt.zero_grad()
+        m.compute_loss(m((img, txt)), y).backward()
+        opt.step()                                          # rewrites the shadow in its kernel
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m((img, txt)), fresh_copy(m)((img, txt)))
+
+
+def test_device_prefetcher_yields_host_batches_in_order(mmu):
+    g = torch.Generator().manual_seed(3)
+    host = [((torch.randn(4, 6, 8, generator=g), torch.randn(4, 3, 8, generator=g) if i % 2 else None),
+             torch.randint(0, 5, (4,), generator=g)) for i in range(5)]
+    seen = 0
+    for ((img, txt), y), ((himg, htxt), hy) in zip(mmu.dataset.DevicePrefetcher(host, "cuda"), host):
+        assert img.is_cuda and torch.equal(img.cpu(), himg) and torch.equal(y.cpu(), hy)
+        assert (txt is None) == (htxt is None) and (txt is None or torch.equal(txt.cpu(), htxt))
+        seen += 1
+    assert seen == len(host)

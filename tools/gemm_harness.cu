@@ -36,11 +36,19 @@ static const Case kCases[] = {
     {"proj_bf16_bias", 30336, 768, 768, 0, 0, EPI_STORE, 1, 1, 1, 0, 1},
     {"inproj_bf16", 30336, 2304, 768, 0, 0, EPI_STORE, 1, 1, 1, 0, 1},
     {"cfc_gelu", 30336, 3072, 768, 0, 0, EPI_QUICKGELU, 1, 1, 1, 0, 1},
-    {"cproj_resid", 30336, 768, 3072, 0, 0, EPI_RESIDUAL, 0, 1, 1, 0, 1},
+    {"cproj_bf16", 30336, 768, 3072, 0, 0, EPI_STORE, 1, 1, 1, 0, 1},
     {"dgrad_dgelu", 30336, 3072, 768, 0, 1, EPI_DGELU, 1, 1, 0, 0, 1},
     {"wgrad_split", 3072, 768, 30336, 1, 1, EPI_ATOMIC, 0, 8, 0, 0, 1},
     {"wgrad_sq", 768, 768, 30336, 1, 1, EPI_ATOMIC, 0, 16, 0, 0, 1},
     {"seg_remap", 25216, 768, 768, 0, 0, EPI_STORE, 0, 1, 1, 1, 0},
+    {"tails_bf16", 1000, 520, 200, 0, 0, EPI_STORE, 1, 1, 1, 0, 0},
+    {"gelu_tails", 300, 520, 192, 0, 0, EPI_QUICKGELU, 1, 1, 1, 0, 0},
+    {"dgelu_tails", 300, 520, 192, 0, 1, EPI_DGELU, 1, 1, 0, 0, 0},
+    {"atomic_tails", 304, 520, 1000, 1, 1, EPI_ATOMIC, 0, 3, 0, 0, 0},
+    {"n104_bf16", 72, 104, 96, 0, 0, EPI_STORE, 1, 1, 1, 0, 0},
+    {"dgrad_fc", 30336, 768, 3072, 0, 1, EPI_STORE, 1, 1, 0, 0, 1},
+    {"dgrad_in", 30336, 768, 2304, 0, 1, EPI_STORE, 1, 1, 0, 0, 1},
+    {"wgrad_in", 2304, 768, 30336, 1, 1, EPI_ATOMIC, 0, 3, 0, 0, 1},
 };
 
 __global__ void ref_gemm(const __nv_bfloat16* A, const __nv_bfloat16* B, float* C, int M, int N,

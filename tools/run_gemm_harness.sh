@@ -1,12 +1,7 @@
 #!/bin/bash
-# Runs every harness case in its own process under a timeout; logs to gpurun_out/.
-mkdir -p gpurun_out
-LOG=gpurun_out/gemm_harness.log
-: > $LOG
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv >> $LOG 2>&1
-N=$(./build/gemm_harness)
-for i in $(seq 0 $((N-1))); do
-  timeout 120 ./build/gemm_harness $i >> $LOG 2>&1
-  echo "exit=$?" >> $LOG
+# Runs every case of build/gemm_harness, each under its own timeout (a protocol bug must not hang the box).
+n=$(./build/gemm_harness)
+for i in $(seq 0 $((n-1))); do
+  timeout 60 ./build/gemm_harness $i
+  echo "exit=$?"
 done
-grep -E "RESULT|TIMING|exit=|error|timed out" $LOG
