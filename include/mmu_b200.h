@@ -55,6 +55,10 @@ MMU_API const char* mmu_version(void);
 MMU_API const char* mmu_error_string(int code);
 /* Number of CUDA kernels this library has launched so far in this process (host counter). */
 MMU_API long long mmu_launch_count(void);
+/* sizeof() of the ABI structs as compiled into the library, so a binding can verify its mirror:
+ * 0 mmu_flava_config, 1 mmu_flava_inputs, 2 mmu_gemm_epilogue, 3 mmu_metric_accum,
+ * 4 mmu_param_entry; -1 for anything else. */
+MMU_API int mmu_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
  * Dense contraction  C[M,N] = epilogue( sum_k A(m,k) B(n,k) )
@@ -172,6 +176,7 @@ typedef struct {
   int avg_pool;   /* kwargs["avg_pool"], src/model.py:256,281-284 */
   int cls_token;  /* 1: the CLS-token variant, src/model.py:306-361 */
   int precision;  /* MMU_F32 or MMU_BF16 */
+  int max_variants; /* capacity for packed-variant evaluation (0 or 1: single variant) */
 } mmu_flava_config;
 
 typedef struct {
@@ -196,9 +201,19 @@ typedef struct {
   const int* keep;     /* int32[B,2] modality keep mask (0: zero-fill) or NULL */
   const void* params_bf16; /* optional bf16 copy of `params` kept fresh by the caller (the fused
                               AdamW writes it); NULL: cast from the fp32 master every forward */
+  /* Packed-variant evaluation (replaces the 43 forwards per batch of
+   * eval_transformer_robustness.py:99-125 by one): attention runs over the batch axis and every
+   * other op is row-wise, so token positions never interact and V token-subset variants can be
+   * concatenated along L.  idx_img / idx_txt then hold the concatenated per-variant index lists
+   * (n_img / n_txt are the totals; cfg->l_img / l_txt act as capacities), src_l_* give the token
+   * counts of the source tensors, var_segments the rows [begin, end) feeding head e of variant v. */
+  int src_l_img, src_l_txt;  /* 0: cfg->l_img / cfg->l_txt */
+  int n_variants;            /* 0 or 1: ordinary forward */
+  const int* var_segments;   /* device int32[n_variants][E][2] */
 } mmu_flava_inputs;
 
-/* logits: fp32 (B, E, C).  training != 0 keeps the activations the backward needs. */
+/* logits: fp32 (B, E, C), or (n_variants, B, E, C) for a packed-variant forward (eval only).
+ * training != 0 keeps the activations the backward needs. */
 MMU_API int mmu_flava_forward(const mmu_flava_config* cfg, const float* params, const mmu_flava_inputs* in,
                       void* workspace, long long workspace_bytes, int training, float* logits,
                       void* stream);

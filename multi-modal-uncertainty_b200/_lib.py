@@ -19,7 +19,7 @@ EXPORTS = [
     "mmu_layernorm_bwd", "mmu_batchaxis_attention_fwd", "mmu_batchaxis_attention_bwd",
     "mmu_heads_uncertainty_epilogue", "mmu_adamw_flat_step", "mmu_flava_param_count",
     "mmu_flava_param_table", "mmu_flava_workspace_bytes", "mmu_flava_num_stages",
-    "mmu_flava_forward", "mmu_flava_backward", "mmu_cast_f32_to_bf16",
+    "mmu_flava_forward", "mmu_flava_backward", "mmu_cast_f32_to_bf16", "mmu_struct_size",
 ]
 
 
@@ -51,7 +51,8 @@ ACC_INT_WORDS = ACC_OFF["conf_sum"]  # words [0, ACC_INT_WORDS) are uint64, the 
 
 class FlavaConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("B", "l_img", "l_txt", "d_img", "d_txt", "D", "n_head",
-                                       "n_layers", "E", "C", "avg_pool", "cls_token", "precision")]
+                                       "n_layers", "E", "C", "avg_pool", "cls_token", "precision",
+                                       "max_variants")]
 
 
 class ParamEntry(C.Structure):
@@ -62,7 +63,8 @@ class ParamEntry(C.Structure):
 class FlavaInputs(C.Structure):
     _fields_ = [("img", C.c_void_p), ("txt", C.c_void_p), ("idx_img", C.c_void_p),
                 ("idx_txt", C.c_void_p), ("n_img", C.c_int), ("n_txt", C.c_int),
-                ("keep", C.c_void_p), ("params_bf16", C.c_void_p)]
+                ("keep", C.c_void_p), ("params_bf16", C.c_void_p), ("src_l_img", C.c_int),
+                ("src_l_txt", C.c_int), ("n_variants", C.c_int), ("var_segments", C.c_void_p)]
 
 
 def _load():
@@ -79,6 +81,7 @@ def _load():
     lib.mmu_launch_count.restype = ll
     lib.mmu_gemm.argtypes = [i, vp, ll, i, vp, ll, i, i, i, i, i, C.POINTER(GemmEpilogue), vp]
     lib.mmu_mask_gather_tokens.argtypes = [vp, vp, i, i, i, i, vp, i, vp, i, vp]
+    lib.mmu_struct_size.argtypes = [i]
     lib.mmu_cast_f32_to_bf16.argtypes = [vp, vp, C.c_size_t, vp]
     lib.mmu_layernorm_fwd.argtypes = [vp, vp, vp, vp, i, vp, vp, i, i, vp]
     lib.mmu_layernorm_bwd.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, i, vp, vp, vp, i, i, vp]

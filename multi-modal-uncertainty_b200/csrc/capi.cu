@@ -34,6 +34,17 @@ const char* mmu_version(void) { return "mmu_b200 0.1 (sm_100a)"; }
 
 long long mmu_launch_count(void) { return launch_count(); }
 
+int mmu_struct_size(int which) {
+  switch (which) {
+    case 0: return static_cast<int>(sizeof(mmu_flava_config));
+    case 1: return static_cast<int>(sizeof(mmu_flava_inputs));
+    case 2: return static_cast<int>(sizeof(mmu_gemm_epilogue));
+    case 3: return static_cast<int>(sizeof(mmu_metric_accum));
+    case 4: return static_cast<int>(sizeof(mmu_param_entry));
+    default: return -1;
+  }
+}
+
 const char* mmu_error_string(int code) {
   switch (code) {
     case MMU_OK: return "ok";

@@ -193,7 +193,8 @@ void carve(const FlavaConfig& c, int training, void* base, const Layout& lay, Ws
   w->x_out[1] = training ? nullptr : b.take<float>(M * D * 4);
   w->x_final = w->x_out[0];
   w->stats_post = b.take<float>(2 * M * 4);
-  w->vec = b.take<float>(static_cast<long long>(c.B) * c.E * D * 4);
+  w->vec = b.take<float>(static_cast<long long>(c.max_variants > 1 ? c.max_variants : 1) * c.B *
+                         c.E * D * 4);
   w->ybuf = b.take<void>(M * D * s);
   w->scores = c.precision == PREC_BF16 ? b.take<float>(sq_elems * 4) : nullptr;
   if (training) {
@@ -270,6 +271,10 @@ struct Shape {
   int n_cls, n_img, n_txt, L, M;
 };
 int resolve_shape(const FlavaConfig& c, const FlavaInputs& in, Shape* s) {
+  if (in.n_variants > 1) {  // packed variants: eval only, capacity-checked, no CLS rows
+    if (c.cls_token || in.var_segments == nullptr || in.keep != nullptr) return MMU_ERR_ARG;
+    if (in.n_variants > (c.max_variants > 1 ? c.max_variants : 1)) return MMU_ERR_WORKSPACE;
+  }
   s->n_cls = c.cls_token ? c.E : 0;
   s->n_img = in.img != nullptr ? in.n_img : 0;
   s->n_txt = in.txt != nullptr ? in.n_txt : 0;
@@ -277,7 +282,7 @@ int resolve_shape(const FlavaConfig& c, const FlavaInputs& in, Shape* s) {
   s->L = s->n_cls + s->n_img + s->n_txt;
   s->M = c.B * s->L;
   if (s->n_img + s->n_txt == 0) return MMU_ERR_SHAPE;
-  if (!c.avg_pool || c.cls_token) {
+  if ((!c.avg_pool || c.cls_token) && in.n_variants <= 1) {
     if (c.E > s->L) return MMU_ERR_SHAPE;  // head i reads token position i (src/model.py:286-287)
   }
   return 0;
@@ -331,6 +336,9 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
   if (w.bytes > ws_bytes) return MMU_ERR_WORKSPACE;
   Shape s;
   MMU_TRY(resolve_shape(c, in, &s));
+  if (in.n_variants > 1 && training) return MMU_ERR_ARG;
+  const int src_l_img = in.src_l_img > 0 ? in.src_l_img : c.l_img;
+  const int src_l_txt = in.src_l_txt > 0 ? in.src_l_txt : c.l_txt;
   const int bf = c.precision == PREC_BF16;
   const int dt = bf ? DT_BF16 : DT_F32;
   const int D = c.D, M = s.M;
@@ -347,14 +355,14 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
   // ---- stem: gather/mask/cast inputs, per-modality projections written straight into the
   //      concatenated (B, L, D) buffer (fuses torch.cat, src/model.py:262-273), CLS rows
   if (s.n_img > 0) {
-    MMU_TRY(cast_gather(in.img, w.img_t, dt, c.B, c.l_img, c.d_img, in.idx_img, s.n_img, in.keep, 0,
+    MMU_TRY(cast_gather(in.img, w.img_t, dt, c.B, src_l_img, c.d_img, in.idx_img, s.n_img, in.keep, 0,
                         stream));
     GemmEpilogue e = epi(EPI_STORE, w.mm_x, 0, D, params + lay.img_b);
     e.seg_len = s.n_img; e.seg_stride = s.L; e.seg_off = s.n_cls;
     MMU_TRY(gemm(w.img_t, c.d_img, 0, W(lay.img_w), c.d_img, 0, c.B * s.n_img, D, c.d_img, e));
   }
   if (s.n_txt > 0) {
-    MMU_TRY(cast_gather(in.txt, w.txt_t, dt, c.B, c.l_txt, c.d_txt, in.idx_txt, s.n_txt, in.keep, 1,
+    MMU_TRY(cast_gather(in.txt, w.txt_t, dt, c.B, src_l_txt, c.d_txt, in.idx_txt, s.n_txt, in.keep, 1,
                         stream));
     GemmEpilogue e = epi(EPI_STORE, w.mm_x, 0, D, params + lay.txt_b);
     e.seg_len = s.n_txt; e.seg_stride = s.L; e.seg_off = s.n_cls + s.n_img;
@@ -405,14 +413,20 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
   }
 
   // ---- ln_post + row gather / mean pooling + heads (src/model.py:277-289)
-  const HeadSegments hs = head_segments(c, s);
-  MMU_TRY(pool_ln_fwd(x, params + lay.lnpost_w, params + lay.lnpost_b, hs, w.vec, w.stats_post,
-                      w.stats_post + M, c.B, s.L, D, stream));
   HeadParams hp{};
   for (int e = 0; e < c.E; ++e) {
     hp.w[e] = params + lay.head_w[e];
     hp.b[e] = params + lay.head_b[e];
   }
+  if (in.n_variants > 1) {
+    MMU_TRY(pool_ln_fwd_variants(x, params + lay.lnpost_w, params + lay.lnpost_b, in.var_segments,
+                                 in.n_variants, c.E, w.vec, c.B, s.L, D, stream));
+    MMU_TRY(heads_fwd(w.vec, hp, logits, in.n_variants * c.B, c.E, c.C, D, stream));
+    return 0;
+  }
+  const HeadSegments hs = head_segments(c, s);
+  MMU_TRY(pool_ln_fwd(x, params + lay.lnpost_w, params + lay.lnpost_b, hs, w.vec, w.stats_post,
+                      w.stats_post + M, c.B, s.L, D, stream));
   MMU_TRY(heads_fwd(w.vec, hp, logits, c.B, c.E, c.C, D, stream));
   return 0;
 }
@@ -429,6 +443,7 @@ int flava_backward(const FlavaConfig& c, const float* params, const FlavaInputs&
   if (w.bytes > ws_bytes) return MMU_ERR_WORKSPACE;
   Shape s;
   MMU_TRY(resolve_shape(c, in, &s));
+  if (in.n_variants > 1) return MMU_ERR_ARG;
   const int bf = c.precision == PREC_BF16;
   const int dt = bf ? DT_BF16 : DT_F32;
   const int D = c.D, M = s.M;

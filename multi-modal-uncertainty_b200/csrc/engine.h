@@ -25,6 +25,7 @@ struct FlavaConfig {
   int avg_pool;   // kwargs["avg_pool"]
   int cls_token;  // FlavaFusionTransfomerwithCLSToken
   int precision;  // Precision
+  int max_variants;  // capacity for packed-variant evaluation (0 or 1: single variant)
 };
 
 struct ParamEntry {
@@ -51,6 +52,15 @@ struct FlavaInputs {
   // optional caller-maintained bf16 shadow of `params` (same element offsets).  Null: the engine
   // casts the fp32 master into the workspace at every forward (22.8 M params = 137 MB of traffic).
   const void* params_bf16;
+  // Packed-variant evaluation (robustness sweeps): token positions never interact (attention
+  // runs over the BATCH axis, every other op is row-wise), so V token-subset variants of one
+  // batch are evaluated in ONE pass by concatenating their tokens along L: idx_img / idx_txt
+  // hold the concatenated per-variant index lists (n_img / n_txt = totals, <= config l_img /
+  // l_txt, which act as capacities), and var_segments says which positions feed each head.
+  int src_l_img;            // token count of the `img` source tensor (0: config l_img)
+  int src_l_txt;
+  int n_variants;           // 0 or 1: ordinary forward
+  const int* var_segments;  // device int32 [n_variants][E][2]: rows [begin, end) of head e
 };
 
 int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& in, void* ws,

@@ -147,6 +147,7 @@ struct Args {
   int spc;          // samples per chunk (multiple of 4 and of 32/G)
   int slot_floats;  // floats per shared-memory slot (multiple of 4)
   int nwarps;
+  int bulk_in, bulk_out;  // logits / dlogits base 16-byte aligned: chunks may move by bulk TMA
   float grad_scale;
 };
 
@@ -184,7 +185,7 @@ ce_uncertainty_kernel(const Args a) {
   auto chunk_rows = [&](int ch) { return min(spc, a.N - ch * spc); };
   auto issue = [&](int ch, int b) {  // lane 0 only; a ragged tail chunk is copied by the lanes
     const uint32_t bytes = static_cast<uint32_t>(chunk_rows(ch)) * EC * 4u;
-    if ((bytes & 15u) == 0) {
+    if (a.bulk_in && (bytes & 15u) == 0) {
       ptx::mbar_arrive_expect_tx(&bar[b], bytes);
       bulk_load(slot0 + b * a.slot_floats, a.logits + static_cast<size_t>(ch) * spc * EC, bytes,
                 &bar[b]);
@@ -240,7 +241,7 @@ ce_uncertainty_kernel(const Args a) {
         load_labels(nxt * spc + (g < rows1 ? g : rows1 - 1), g < rows1, ylab_next);
       }
     }
-    if ((bytes & 15u) == 0) {
+    if (a.bulk_in && (bytes & 15u) == 0) {
       ptx::mbar_wait(&bar[cur], (it >> 1) & 1);
     } else {
       const float* src = a.logits + static_cast<size_t>(ch) * spc * EC;
@@ -404,7 +405,7 @@ ce_uncertainty_kernel(const Args a) {
 
     if (GRAD) {
       float* dst = a.dlogits + static_cast<size_t>(ch) * spc * EC;
-      if ((bytes & 15u) == 0) {
+      if (a.bulk_out && (bytes & 15u) == 0) {
         ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the bulk store
         __syncwarp();
         if (lane == 0) bulk_store(dst, tb, bytes);
@@ -518,8 +519,7 @@ int ce_uncertainty(const float* logits, const long long* labels, int label_strid
                    cudaStream_t stream) {
   if (N <= 0) return 0;
   if (E < 1 || E > 16 || C < 1 || (mode != 0 && mode != 1)) return MMU_ERR_ARG;
-  if ((reinterpret_cast<uintptr_t>(logits) & 15) != 0) return MMU_ERR_ALIGN;
-  if (dlogits != nullptr && (reinterpret_cast<uintptr_t>(dlogits) & 15) != 0) return MMU_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(logits) & 3) != 0) return MMU_ERR_ALIGN;
   if (pred_out != nullptr && (reinterpret_cast<uintptr_t>(pred_out) & 7) != 0) return MMU_ERR_ALIGN;
   if (scores_out != nullptr && (reinterpret_cast<uintptr_t>(scores_out) & 15) != 0) return MMU_ERR_ALIGN;
   // the per-block fixed-point confidence sums are exact up to 2^20 samples per block: split
@@ -542,6 +542,10 @@ int ce_uncertainty(const float* logits, const long long* labels, int label_strid
   a.pred_out = pred_out; a.scores_out = scores_out; a.acc = acc;
   a.ls = label_stride; a.les = label_estride; a.N = N; a.E = E; a.C = C;
   a.grad_scale = grad_scale;
+  // slices of a larger logits tensor need not be 16-byte aligned: such calls move their chunks
+  // with ordinary loads / stores instead of bulk TMA copies
+  a.bulk_in = (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
+  a.bulk_out = dlogits == nullptr || (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0;
   // (lanes per sample, class slots per lane): exact fits for the reference's class counts
   // (2: hateful memes, 10: FashionMNIST, 101: Food-101), predicated generic shapes otherwise.
   if (C <= 2) return epi::launch<1, 2, false>(a, mode, stream);

@@ -38,6 +38,9 @@ struct HeadSegments {
   int seg_begin[16];
   int seg_end[16];  // rows [begin, end) of each sample's L rows feed head e
 };
+// Packed-variant pooling: segs = device int32 [V][E][2]; vec out is [V][B][E][D].
+int pool_ln_fwd_variants(const float* x, const float* gamma, const float* beta, const int* segs,
+                         int V, int E, float* vec, int B, int L, int D, cudaStream_t stream);
 struct HeadParams {
   const float* w[16];  // (C, D) each
   const float* b[16];

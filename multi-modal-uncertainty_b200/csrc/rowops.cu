@@ -375,6 +375,55 @@ pool_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   }
 }
 
+// Packed-variant twin of pool_ln_fwd_kernel (eval only: no statistics are kept).  Block
+// (b, e, v) pools the ln_post rows [segs[v][e][0], segs[v][e][1]) of sample b.
+template <int NV>
+__global__ void __launch_bounds__(THREADS)
+pool_ln_fwd_variants_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, const int* __restrict__ segs,
+                            float* __restrict__ vec, int B, int E, int L, int D) {
+  extern __shared__ float red[];
+  const int b = blockIdx.x, e = blockIdx.y, v = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D >> 2;
+  const int s0 = segs[(v * E + e) * 2], s1 = segs[(v * E + e) * 2 + 1];
+  float4 acc[NV];
+  zero_acc<NV>(acc);
+  for (int l = s0 + warp; l < s1; l += WARPS) {
+    const size_t row = static_cast<size_t>(b) * L + l;
+    RowRegs<NV> r;
+    r.load(x + row * D, nvec, lane);
+    float mean, rstd;
+    row_stats<NV>(r, nvec, lane, D, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c);
+        const float4 bb = *reinterpret_cast<const float4*>(beta + 4 * c);
+        acc[i].x += (r.v[i].x - mean) * rstd * g.x + bb.x;
+        acc[i].y += (r.v[i].y - mean) * rstd * g.y + bb.y;
+        acc[i].z += (r.v[i].z - mean) * rstd * g.z + bb.z;
+        acc[i].w += (r.v[i].w - mean) * rstd * g.w + bb.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) *reinterpret_cast<float4*>(red + warp * D + 4 * c) = acc[i];
+  }
+  __syncthreads();
+  const float inv = 1.0f / static_cast<float>(max(1, s1 - s0));
+  float* out = vec + ((static_cast<size_t>(v) * B + b) * E + e) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) s += red[w * D + c];
+    out[c] = s * inv;
+  }
+}
+
 template <int NV>
 __global__ void __launch_bounds__(THREADS)
 pool_ln_bwd_kernel(const float* __restrict__ dvec, const float* __restrict__ x,
@@ -738,6 +787,18 @@ int pool_ln_fwd(const float* x, const float* gamma, const float* beta, const Hea
   dim3 grid(B, seg.E);
   MMU_NV_DISPATCH(nv, (pool_ln_fwd_kernel<NV><<<grid, THREADS, smem, stream>>>(
                           x, gamma, beta, seg, vec, mean, rstd, L, D)));
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int pool_ln_fwd_variants(const float* x, const float* gamma, const float* beta, const int* segs,
+                         int V, int E, float* vec, int B, int L, int D, cudaStream_t stream) {
+  const int nv = nv_for(D);
+  if (nv < 0 || E < 1 || E > 16 || V < 1 || V > 65535 || segs == nullptr) return MMU_ERR_SHAPE;
+  const size_t smem = static_cast<size_t>(WARPS) * D * sizeof(float);
+  dim3 grid(B, E, V);
+  MMU_NV_DISPATCH(nv, (pool_ln_fwd_variants_kernel<NV><<<grid, THREADS, smem, stream>>>(
+                          x, gamma, beta, segs, vec, B, E, L, D)));
   MMU_CHECK_LAUNCH();
   return 0;
 }

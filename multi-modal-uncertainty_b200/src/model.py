@@ -104,6 +104,7 @@ class FlavaFusionTransfomer(nn.Module):
                           n_head=multimodal_num_attention_heads,
                           n_layers=multimodal_num_hidden_layers)
         self._ws = {}
+        self._pack_caps = {}
         self._cfg_cache = {}
         self._last_epi = None
         self._ddp = None
@@ -238,19 +239,20 @@ class FlavaFusionTransfomer(nn.Module):
         self._flat_grad.zero_()
 
     # ---------------------------------------------------------------------- engine
-    def _config(self, B, l_img, l_txt):
-        key = (B, l_img, l_txt)
+    def _config(self, B, l_img, l_txt, max_variants=0):
+        key = (B, l_img, l_txt, max_variants)
         cfg = self._cfg_cache.get(key)
         if cfg is None:
             d = self._dims
             cfg = _lib.FlavaConfig(B, l_img, l_txt, d["d_img"], d["d_txt"], d["D"], d["n_head"],
                                    d["n_layers"], self.out_dim, self.num_classes,
-                                   int(self.avg_pool), int(self._cls_token), self.precision)
+                                   int(self.avg_pool), int(self._cls_token), self.precision,
+                                   max_variants)
             self._cfg_cache[key] = cfg
         return cfg
 
     def _workspace(self, cfg, training):
-        key = (cfg.B, cfg.l_img, cfg.l_txt, bool(training))
+        key = (cfg.B, cfg.l_img, cfg.l_txt, cfg.max_variants, bool(training))
         ws = self._ws.get(key)
         if ws is None:
             nbytes = _lib.lib.mmu_flava_workspace_bytes(C.byref(cfg), int(training))
@@ -295,6 +297,103 @@ class FlavaFusionTransfomer(nn.Module):
         if training:
             self._logits_train = logits
             return (cfg, inp, ws, (img, txt, idx_img, idx_txt, keep))  # keep inputs alive
+        return logits
+
+    # ------------------------------------------------------ packed-variant evaluation
+    PACK_MAX_POSITIONS = 2048  # token positions per packed pass (bounds the workspace)
+
+    def _variant_segments(self, n_img, n_txt, off_img, off_txt):
+        """Rows [begin, end) of the packed sequence feeding each head of one variant: head e
+        reads token e of (image tokens ++ text tokens) (src/model.py:286-287) or, with
+        ``avg_pool``, the mean over the image / the text tokens (:282-284)."""
+        if self.avg_pool:
+            return [(off_img, off_img + n_img), (off_txt, off_txt + n_txt)]
+        if self.out_dim > n_img + n_txt:
+            raise ValueError(f"a variant with {n_img + n_txt} tokens cannot feed {self.out_dim} heads")
+        return [((off_img + e, off_img + e + 1) if e < n_img else
+                 (off_txt + e - n_img, off_txt + e - n_img + 1)) for e in range(self.out_dim)]
+
+    @torch.no_grad()
+    def forward_variants(self, x, variants):
+        """Evaluate V token-subset variants of one batch -- ``variants = [(idx_img | None,
+        idx_txt | None), ...]``, ``None`` = modality absent, as built by
+        ``robustness.robustness_variants`` -- and return logits ``(V, B, E, C)``.
+
+        Equivalent to ``torch.stack([self((img, txt), token_indices=v) for v in variants])``
+        (reference loop eval_transformer_robustness.py:99-125), bit for bit, but token positions
+        never interact in this model (attention runs over the batch axis; every other op is
+        row-wise), so the variants are concatenated along the token axis and evaluated in ONE
+        pass: large GEMMs instead of V small ones and ~V times fewer kernel launches."""
+        img, txt = x
+        if self._cls_token or self.training:
+            return torch.stack([self.forward((img if ii is not None else None,
+                                              txt if it is not None else None),
+                                             token_indices=(ii, it)) for ii, it in variants])
+        out, chunk, pos = [], [], 0
+        for v in variants:
+            n = (len(v[0]) if v[0] is not None else 0) + (len(v[1]) if v[1] is not None else 0)
+            if chunk and pos + n > self.PACK_MAX_POSITIONS:
+                out.append(self._forward_packed(img, txt, chunk))
+                chunk, pos = [], 0
+            chunk.append(v)
+            pos += n
+        out.append(self._forward_packed(img, txt, chunk))
+        return out[0] if len(out) == 1 else torch.cat(out)
+
+    def _forward_packed(self, img, txt, variants):
+        if not self._flat.is_cuda:
+            raise _lib.MMUError("the model lives on the CPU: call .to('cuda') first -- this "
+                                "package has no CPU execution path")
+        dev = self._flat.device
+        V = len(variants)
+        ni = [len(v[0]) if v[0] is not None else 0 for v in variants]
+        nt = [len(v[1]) if v[1] is not None else 0 for v in variants]
+        Ni, Nt = sum(ni), sum(nt)
+        if (Ni and img is None) or (Nt and txt is None) or Ni + Nt == 0:
+            raise ValueError("variants index a modality that was not given")
+        segs, oi, ot = [], 0, Ni
+        for a, b in zip(ni, nt):
+            segs += self._variant_segments(a, b, oi, ot)
+            oi, ot = oi + a, ot + b
+
+        def cat_idx(k, total):
+            if total == 0:
+                return None
+            return torch.cat([v[k].to(torch.int32) for v in variants if v[k] is not None and len(v[k])])
+
+        # one small host tensor -> one H2D copy: [segments | idx_img | idx_txt]
+        seg_t = torch.tensor(segs, dtype=torch.int32).reshape(-1)
+        parts = [seg_t] + [t for t in (cat_idx(0, Ni), cat_idx(1, Nt)) if t is not None]
+        # pinned staging (torch's caching host allocator recycles it behind a stream event): a
+        # pageable source would make cudaMemcpyAsync synchronise the stream first
+        staged = torch.empty(sum(t.numel() for t in parts), dtype=torch.int32, pin_memory=True)
+        torch.cat(parts, out=staged)
+        packed = staged.to(dev, non_blocking=True)
+        seg_d = packed[: seg_t.numel()]
+        idx_img = packed[seg_t.numel(): seg_t.numel() + Ni] if Ni else None
+        idx_txt = packed[seg_t.numel() + Ni:] if Nt else None
+
+        def prep(t):
+            return None if t is None else t.to(device=dev, dtype=torch.float32).contiguous()
+
+        img, txt = prep(img) if Ni else None, prep(txt) if Nt else None
+        B = (img if img is not None else txt).shape[0]
+        # grow-only capacities so that every sweep of this batch size shares one workspace
+        cap = self._pack_caps.get(B, (1, 1, 2))
+        cap = (max(cap[0], Ni, 1), max(cap[1], Nt, 1), max(cap[2], V))
+        self._pack_caps[B] = cap
+        for key in [k for k in self._ws if k[0] == B and k[3] > 1 and k[1:4] != cap]:
+            del self._ws[key]  # superseded by the larger workspace
+        cfg = self._config(B, cap[0], cap[1], cap[2])
+        ws = self._workspace(cfg, False)
+        inp = _lib.FlavaInputs(_lib.ptr(img), _lib.ptr(txt), _lib.ptr(idx_img), _lib.ptr(idx_txt),
+                               Ni, Nt, 0, _lib.ptr(self._fresh_shadow()),
+                               img.shape[1] if img is not None else 0,
+                               txt.shape[1] if txt is not None else 0, V, _lib.ptr(seg_d))
+        logits = torch.empty(V, B, self.out_dim, self.num_classes, device=dev, dtype=torch.float32)
+        _lib.check(_lib.lib.mmu_flava_forward(C.byref(cfg), self._flat.data_ptr(), C.byref(inp),
+                                              ws.data_ptr(), ws.numel(), 0, logits.data_ptr(),
+                                              _lib.stream_ptr()), "mmu_flava_forward")
         return logits
 
     def _engine_backward(self, saved, dlogits):

@@ -80,6 +80,16 @@ def forward_variant(model, img, txt, variant, ref_bug_compat=False):
 
 
 @torch.no_grad()
+def forward_variants(model, img, txt, variants, ref_bug_compat=False):
+    """Logits (V, B, E, C) of every variant of one batch.  Uses the model's packed-variant pass
+    when it has one; ``ref_bug_compat`` as in :func:`forward_variant`."""
+    src_txt = img if ref_bug_compat else txt
+    if hasattr(model, "forward_variants"):
+        return model.forward_variants((img, src_txt), variants)
+    return torch.stack([forward_variant(model, img, txt, v, ref_bug_compat) for v in variants])
+
+
+@torch.no_grad()
 def run_transformer_robustness(model, batches, device, n_repeats=20, ref_bug_compat=False,
                                collect=True, variants_fn=None):
     """Sweep every batch through the variant schedule.  Returns (preds (S, V, K, C) numpy or
@@ -94,14 +104,13 @@ def run_transformer_robustness(model, batches, device, n_repeats=20, ref_bug_com
             variants = variants_fn(img.shape[1], txt.shape[1])
         if meters is None:
             meters = [UncertaintyMeter(device, model.num_classes, model.out_dim) for _ in variants]
-        outs = []
-        for v, meter in zip(variants, meters):
-            logits = forward_variant(model, img, txt, v, ref_bug_compat)
+        # all variants of the batch in one packed pass (model.forward_variants), then one fused
+        # epilogue launch per variant into that variant's accumulator
+        all_logits = forward_variants(model, img, txt, variants, ref_bug_compat)
+        for logits, meter in zip(all_logits, meters):
             meter.update(logits, y)
-            if collect:
-                outs.append(logits)
         if collect:
-            preds.append(torch.stack(outs, dim=1).cpu())
+            preds.append(all_logits.transpose(0, 1).cpu())
         labels.append(y.cpu())
     for m in meters or []:
         m.all_reduce()

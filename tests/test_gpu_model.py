@@ -306,3 +306,34 @@ def test_device_prefetcher_yields_host_batches_in_order(mmu):
         assert (txt is None) == (htxt is None) and (txt is None or torch.equal(txt.cpu(), htxt))
         seen += 1
     assert seen == len(host)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["plain_E2", "avgpool_E2", "plain_E5_h3"])
+def test_packed_variants_equal_per_variant_forwards(mmu, golden, name, precision):
+    """model.forward_variants (all variants concatenated along the token axis, one pass) must
+    give, bit for bit, what one forward per variant gives (the reference's loop,
+    eval_transformer_robustness.py:99-125): token positions never interact in this model."""
+    import numpy as np
+    c = golden("flava_small.pt")[name]
+    cfg = c["cfg"]
+    m = build(mmu, cfg, c["state_dict"], precision).eval()
+    img, txt = c["img"].cuda(), c["txt"].cuda()
+    np.random.seed(5)
+    torch.manual_seed(5)
+    variants = mmu.robustness.robustness_variants(cfg["l_img"], cfg["l_txt"], n_repeats=6)
+    if not cfg["avg_pool"]:  # a variant must hold at least E tokens (head e reads token e)
+        variants = [v for v in variants
+                    if sum(len(i) for i in v if i is not None) >= cfg["E"]]
+    with torch.no_grad():
+        ref = torch.stack([mmu.robustness.forward_variant(m, img, txt, v) for v in variants])
+        got = m.forward_variants((img, txt), variants)
+        assert got.shape == ref.shape and torch.equal(got, ref)
+        m.PACK_MAX_POSITIONS = 9  # force several packed passes
+        assert torch.equal(m.forward_variants((img, txt), variants), ref)
+    P, labels, metrics = mmu.robustness.run_transformer_robustness(
+        m, [((c["img"], c["txt"]), c["y_eval"] if "y_eval" in c else c["y_train"][:, 0])], "cuda",
+        variants_fn=lambda li, lt: variants)
+    assert P.shape[:2] == (img.shape[0], len(variants))
+    assert np.array_equal(P, ref.transpose(0, 1).cpu().numpy())
+    assert all(mt["n_samples"] == img.shape[0] for mt in metrics)
