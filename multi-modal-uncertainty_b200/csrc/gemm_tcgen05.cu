@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -118,20 +119,45 @@ int make_tmap_out_4d(CUtensorMap* out, const void* base, int is_bf16, long long 
 }
 
 namespace {
-template <int MODE, bool OBF>
-int launch_mode(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& c0,
-                const CUtensorMap& c1, const GemmProblem& p, const GemmEpilogue& e,
-                cudaStream_t stream) {
+// MMU_GEMM_NCTA=1 forces the single-CTA kernel (A/B measurements); default: CTA pairs where they fit
+int pair_mode_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("MMU_GEMM_NCTA");
+    v = (s != nullptr && s[0] == '1') ? 0 : 1;
+  }
+  return v;
+}
+
+// CTA pairs (256x256 tiles) for large unbatched problems
+bool use_pair(const GemmProblem& p) { return p.batch == 0 && p.M >= 512 && pair_mode_enabled(); }
+
+template <int MODE, bool OBF, int NCTA>
+int launch_kernel(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& c0,
+                  const CUtensorMap& c1, const GemmProblem& p, const GemmEpilogue& e,
+                  cudaStream_t stream) {
   using namespace gemm;
-  static cudaError_t attr_err = cudaFuncSetAttribute(
-      gemm_bf16_tcgen05_kernel<MODE, OBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  auto kernel = gemm_bf16_tcgen05_kernel<MODE, OBF, NCTA>;
+  static cudaError_t attr_err =
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (attr_err != cudaSuccess) {
     fprintf(stderr, "mmu: cudaFuncSetAttribute(smem=%d): %s\n", SMEM_BYTES,
             cudaGetErrorString(attr_err));
     return MMU_ERR_CUDA;
   }
-  gemm_bf16_tcgen05_kernel<MODE, OBF><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, c0, c1, p, e);
-  const cudaError_t err = cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = NCTA == 2 ? 1 : 0;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, ta, tb, c0, c1, p, e);
   if (err != cudaSuccess) {
     fprintf(stderr, "mmu: gemm launch failed: %s\n", cudaGetErrorString(err));
     return MMU_ERR_CUDA;
@@ -140,9 +166,28 @@ int launch_mode(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const CU
   return 0;
 }
 
+// One CTA per 128x256 tile, or -- for large unbatched problems -- a CTA pair per 256x256 tile.
+template <int MODE, bool OBF>
+int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& c0,
+                const CUtensorMap& c1, const GemmProblem& p, const GemmEpilogue& e,
+                cudaStream_t stream) {
+  using namespace gemm;
+  const int nbatch = p.batch > 0 ? p.batch : 1;
+  const long long n_tiles = (p.N + BN - 1) / BN;
+  if (use_pair(p)) {
+    const long long tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * n_tiles * p.splits;
+    const long long clusters = sm_count() / 2;
+    const int grid = 2 * static_cast<int>(tiles < clusters ? tiles : clusters);
+    return launch_kernel<MODE, OBF, 2>(grid, ta, tb, c0, c1, p, e, stream);
+  }
+  const long long tiles = nbatch * ((p.M + BM - 1) / BM) * n_tiles * p.splits;
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  return launch_kernel<MODE, OBF, 1>(grid, ta, tb, c0, c1, p, e, stream);
+}
+
 // Output maps + mode dispatch shared by the plain and the batched entry points.  `rows`/`cols`
 // are the per-problem output extents; batch geometry as in GemmProblem.
-int launch_with_epilogue(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const GemmProblem& p,
+int launch_with_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const GemmProblem& p,
                          const GemmEpilogue& e, cudaStream_t stream) {
   const int obf = e.out_bf16 ? 1 : 0;
   const long long hdiv = p.batch > 0 ? p.out_hdiv : 1;
@@ -157,24 +202,24 @@ int launch_with_epilogue(int grid, const CUtensorMap& ta, const CUtensorMap& tb,
       if (e.out == nullptr) return MMU_ERR_ARG;
       if ((rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;
       c1 = c0;
-      return obf ? launch_mode<EPI_STORE, true>(grid, ta, tb, c0, c1, p, e, stream)
-                 : launch_mode<EPI_STORE, false>(grid, ta, tb, c0, c1, p, e, stream);
+      return obf ? launch_mode<EPI_STORE, true>(ta, tb, c0, c1, p, e, stream)
+                 : launch_mode<EPI_STORE, false>(ta, tb, c0, c1, p, e, stream);
     case EPI_QUICKGELU:
       if (!obf || e.out2 == nullptr) return MMU_ERR_ARG;  // bf16 activations only on this path
       if ((rc = omap(&c1, e.out2, e.ld_out2)) != 0) return rc;
       c0 = c1;
       if (e.out != nullptr && (rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;
-      return launch_mode<EPI_QUICKGELU, true>(grid, ta, tb, c0, c1, p, e, stream);
+      return launch_mode<EPI_QUICKGELU, true>(ta, tb, c0, c1, p, e, stream);
     case EPI_DGELU:
       if (!obf || e.out == nullptr || e.aux == nullptr) return MMU_ERR_ARG;
       if ((rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;
       if ((rc = omap(&c1, e.aux, e.ld_aux)) != 0) return rc;
-      return launch_mode<EPI_DGELU, true>(grid, ta, tb, c0, c1, p, e, stream);
+      return launch_mode<EPI_DGELU, true>(ta, tb, c0, c1, p, e, stream);
     case EPI_ATOMIC:
       if (obf || e.out == nullptr) return MMU_ERR_ARG;
       if ((rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;
       c1 = c0;
-      return launch_mode<EPI_ATOMIC, false>(grid, ta, tb, c0, c1, p, e, stream);
+      return launch_mode<EPI_ATOMIC, false>(ta, tb, c0, c1, p, e, stream);
     default:
       // EPI_RESIDUAL exists on the fp32 path only: the bf16 engine fuses the residual add into
       // the LayerNorm kernel that consumes the sum (rowops.cu add_layernorm_fwd)
@@ -222,14 +267,13 @@ int gemm_bf16_launch(const void* A, long long lda, const void* B, long long ldb,
   if (!p.a_mn_major) rc = make_tmap_bf16_2d(&ta, A, p.K, p.M, lda, BK, BM);
   else               rc = make_tmap_bf16_2d(&ta, A, p.M, p.K, lda, 64, BK);
   if (rc != 0) return rc;
-  if (!p.b_mn_major) rc = make_tmap_bf16_2d(&tb, B, p.K, p.N, ldb, BK, BN);
+  // a CTA of a pair stages only its half of the B tile: the K-major box shrinks to 128 rows
+  const int b_rows = use_pair(p) ? BN / 2 : BN;
+  if (!p.b_mn_major) rc = make_tmap_bf16_2d(&tb, B, p.K, p.N, ldb, BK, b_rows);
   else               rc = make_tmap_bf16_2d(&tb, B, p.N, p.K, ldb, 64, BK);
   if (rc != 0) return rc;
 
-  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
-  const long long tiles = 1LL * m_tiles * n_tiles * p.splits;
-  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  return launch_with_epilogue(grid, ta, tb, p, e, stream);
+  return launch_with_epilogue(ta, tb, p, e, stream);
 }
 
 int gemm_bf16_batched_launch(const BatchedOperand& A, const BatchedOperand& B, int batch, int M,
@@ -254,10 +298,7 @@ int gemm_bf16_batched_launch(const BatchedOperand& A, const BatchedOperand& B, i
   rc = make_tmap_bf16_3d(&tb, B.base, B.inner, B.mid, B.outer, B.mid_stride, B.outer_stride,
                          B.mn_major ? 64 : BK, B.mn_major ? BK : BN);
   if (rc != 0) return rc;
-  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
-  const long long tiles = 1LL * batch * m_tiles * n_tiles;
-  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  return launch_with_epilogue(grid, ta, tb, p, e, stream);
+  return launch_with_epilogue(ta, tb, p, e, stream);
 }
 
 }  // namespace mmu

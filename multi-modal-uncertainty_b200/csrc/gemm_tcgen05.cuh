@@ -36,10 +36,24 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
-constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+// NCTA = 1: one CTA per 128x256 tile, 4 stages of (A 16 KB + B 32 KB).
+// NCTA = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256x256 tile: each CTA stages its
+//           own 128 rows of A and HALF of B (128 of the 256 n-rows), 6 stages of (16 + 16) KB.
+//           Operand bytes through shared memory per FLOP drop by a third -- the single-CTA
+//           kernel is shared-memory-bandwidth bound (TMA writes + UMMA reads = 192 B/clk of the
+//           SM's 128 B/clk at full tensor rate; ncu: tensor pipe 66 % active, all barriers idle).
+template <int NCTA> struct Geo {
+  static constexpr int STAGES = NCTA == 2 ? 6 : 4;
+  static constexpr int A_STAGE_BYTES = BM * BK * 2;            // 16 KiB
+  static constexpr int B_ROWS = BN / NCTA;                     // n-rows of B staged by this CTA
+  static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;        // 32 / 16 KiB
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int BM_TILE = BM * NCTA;                    // output rows per tile
+};
+constexpr int OPERAND_BYTES = 4 * (BM * BK * 2 + BN * BK * 2);  // 192 KiB in both geometries
+static_assert(Geo<1>::STAGES * Geo<1>::STAGE_BYTES == OPERAND_BYTES, "operand ring size");
+static_assert(Geo<2>::STAGES * Geo<2>::STAGE_BYTES == OPERAND_BYTES, "operand ring size");
+constexpr int MAX_STAGES = 6;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;  // TMA warp, MMA warp, 8 epilogue warps
@@ -47,10 +61,10 @@ constexpr int TMEM_COLS = 2 * BN;                       // two accumulator stage
 constexpr int BOX_ROWS = 32;
 constexpr int BOX_BYTES = BOX_ROWS * 64;                // 32 rows x 64 B (32 bf16 / 16 fp32 columns)
 constexpr int STG_WARP_BYTES = 2 * BOX_BYTES;           // two boxes per epilogue warp
-constexpr int OFF_STG = STAGES * STAGE_BYTES;           // 1024-aligned
+constexpr int OFF_STG = OPERAND_BYTES;                  // 1024-aligned
 constexpr int OFF_BIAS = OFF_STG + NUM_EPI_WARPS * STG_WARP_BYTES;
 constexpr int OFF_BARS = OFF_BIAS + 2 * BN * 4;         // bias tile, double buffered
-constexpr int SMEM_USED = OFF_BARS + 256;               // + barriers
+constexpr int SMEM_USED = OFF_BARS + 320;               // + barriers (32 x 8 B) and the TMEM slot
 constexpr int SMEM_BYTES = 227 * 1024;                  // everything an SM has; the kernel checks
                                                         // that SMEM_USED fits behind the 1024-byte
                                                         // alignment of the dynamic window
@@ -82,29 +96,32 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// MODE: GemmEpiMode; OBF: outputs (and the dGELU operand) are bf16, else fp32.
+// MODE: GemmEpiMode; OBF: outputs (and the dGELU operand) are bf16, else fp32; NCTA: CTAs per
+// tile (2 = cta_group::2 pair, launched as a cluster of 2; not used for batched problems).
 // tma_c0: `out`; tma_c1: `out2` (QUICKGELU) or `aux` (DGELU).  Both are 4-D maps
-// (columns, rows, batch % out_hdiv, batch / out_hdiv) with a [32 x 128 B] box.
-template <int MODE, bool OBF>
+// (columns, rows, batch % out_hdiv, batch / out_hdiv) with a [32 x 64 B] box.
+template <int MODE, bool OBF, int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                          const __grid_constant__ CUtensorMap tma_b,
                          const __grid_constant__ CUtensorMap tma_c0,
                          const __grid_constant__ CUtensorMap tma_c1, const GemmProblem p,
                          const GemmEpilogue e) {
+  using G = Geo<NCTA>;
+  constexpr int STAGES = G::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles and staging boxes need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint8_t* smem_b = smem + STAGES * G::A_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
-  uint64_t* full_bar = bars;                     // [STAGES]  TMA -> MMA
-  uint64_t* empty_bar = bars + STAGES;           // [STAGES]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * STAGES;       // [2]       MMA -> epilogue
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA
-  uint64_t* aux_bar = bars + 2 * STAGES + 4;     // [NUM_EPI_WARPS][2] dGELU operand box landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * NUM_EPI_WARPS);
+  uint64_t* full_bar = bars;                         // [STAGES]  TMA -> MMA (pair: the leader's)
+  uint64_t* empty_bar = bars + MAX_STAGES;           // [STAGES]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;       // [2]       MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;  // [2]       epilogue -> MMA (pair: the leader's)
+  uint64_t* aux_bar = bars + 2 * MAX_STAGES + 4;     // [NUM_EPI_WARPS][2] dGELU operand box landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4 + 2 * NUM_EPI_WARPS);
   if (threadIdx.x == 0 && (smem - smem_raw) + SMEM_USED > SMEM_BYTES) {
     printf("mmu: dynamic shared memory window is not 1024-byte aligned (offset %d)\n",
            static_cast<int>(smem - smem_raw));
@@ -113,8 +130,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = NCTA == 2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;  // CTA within the pair
+  const int tile0 = NCTA == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = NCTA == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
-  const int m_tiles = (p.M + BM - 1) / BM;
+  const int m_tiles = (p.M + G::BM_TILE - 1) / G::BM_TILE;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int kb_total = (p.K + BK - 1) / BK;
   const int kb_per = (kb_total + p.splits - 1) / p.splits;
@@ -134,18 +154,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], NUM_EPI_WARPS);
+      ptx::mbar_init(&tempty_bar[i], NCTA * NUM_EPI_WARPS);  // pair: both CTAs' epilogue warps
     }
     for (int i = 0; i < 2 * NUM_EPI_WARPS; ++i) ptx::mbar_init(&aux_bar[i], 1);
     ptx::fence_mbar_init();
     ptx::fence_proxy_async();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (NCTA == 2) {
+      ptx::tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 2) ptx::cluster_sync_all();  // the peer's barriers are initialised too
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -154,13 +180,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int split = tile % p.splits;
         const int mnb = tile / p.splits;
         const int g = mnb / (m_tiles * n_tiles);
         const int mn = mnb % (m_tiles * n_tiles);
-        const int m0 = (mn / n_tiles) * BM;
-        const int n0 = (mn % n_tiles) * BN;
+        const int m0 = (mn / n_tiles) * G::BM_TILE + rank * BM;   // this CTA's 128 rows of A
+        const int n0 = (mn % n_tiles) * BN + rank * G::B_ROWS;    // pair: this CTA's half of B
         const int kb0 = split * kb_per;
         const int kb1 = min(kb_total, kb0 + kb_per);
         const int a_mid = p.batch > 0 ? g / p.a_hdiv : 0;
@@ -169,10 +195,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         const int b_off = p.batch > 0 ? (g % p.b_hdiv) * p.b_hstride + p.b_col0 : 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-          uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
+          uint8_t* sa = smem_a + stage * G::A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * G::B_STAGE_BYTES;
           const int k0 = kb * BK;
+          if constexpr (NCTA == 2) {
+            // both CTAs' bytes are accounted on the LEADER's barrier (the MMA issuer waits there)
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * G::STAGE_BYTES);
+            if (!p.a_mn_major) {
+              ptx::tma_load_2d_pair(sa, &tma_a, &full_bar[stage], k0, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                ptx::tma_load_2d_pair(sa + j * 8192, &tma_a, &full_bar[stage], m0 + 64 * j, k0);
+            }
+            if (!p.b_mn_major) {
+              ptx::tma_load_2d_pair(sb, &tma_b, &full_bar[stage], k0, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < G::B_ROWS / 64; ++j)
+                ptx::tma_load_2d_pair(sb + j * 8192, &tma_b, &full_bar[stage], n0 + 64 * j, k0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], G::STAGE_BYTES);
           if (p.batch > 0) {
             if (!p.a_mn_major) {
               ptx::tma_load_3d(sa, &tma_a, &full_bar[stage], a_off + k0, a_mid, m0);
@@ -211,8 +257,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(BM, BN, p.a_mn_major, p.b_mn_major);
+    if (lane == 0 && rank == 0) {  // pair: the leader issues for both SMs
+      const uint32_t idesc = ptx::make_idesc_bf16(G::BM_TILE, BN, p.a_mn_major, p.b_mn_major);
       // K-major SW128: 8-row groups 1024 B apart, k advances 32 B inside the swizzle atom.
       // MN-major SW128: 64-element MN groups 8192 B apart (one TMA box), 8-k groups 1024 B apart.
       const uint32_t a_lbo = p.a_mn_major ? 8192u : 16u, a_kstep = p.a_mn_major ? 2048u : 32u;
@@ -221,7 +267,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int split = tile % p.splits;
         const int kb0 = split * kb_per;
         const int kb1 = min(kb_total, kb0 + kb_per);
@@ -231,18 +277,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t sb = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+          const uint32_t sa = ptx::smem_u32(smem_a + stage * G::A_STAGE_BYTES);
+          const uint32_t sb = ptx::smem_u32(smem_b + stage * G::B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = ptx::make_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024u);
             const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024u);
-            ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (NCTA == 2) ptx::umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else ptx::umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if constexpr (NCTA == 2) ptx::umma_commit_pair(&empty_bar[stage]);
+          else ptx::umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (NCTA == 2) ptx::umma_commit_pair(&tfull_bar[as]);
+        else ptx::umma_commit(&tfull_bar[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -264,12 +315,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     uint64_t* my_aux = aux_bar + 2 * we;
     int as = 0;
     uint32_t aphase = 0, aux_phase[2] = {0, 0};
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    auto release_tmem = [&](int stage_idx) {  // one arrival per epilogue warp per tile
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (NCTA == 2) ptx::mbar_arrive_leader(&tempty_bar[stage_idx]);
+        else ptx::mbar_arrive(&tempty_bar[stage_idx]);
+      }
+    };
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int mnb = tile / p.splits;
       const int g = mnb / (m_tiles * n_tiles);
       const int mn = mnb % (m_tiles * n_tiles);
       const int nt0 = (mn % n_tiles) * BN;
-      const int m0 = (mn / n_tiles) * BM + q * 32;
+      const int m0 = (mn / n_tiles) * G::BM_TILE + rank * BM + q * 32;
       const int n0 = nt0 + h * (BN / 2);
       const int c2 = p.batch > 0 ? g % p.out_hdiv : 0;
       const int c3 = p.batch > 0 ? g / p.out_hdiv : 0;
@@ -329,9 +388,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             tmem_load(c + 1);
           } else {
             // every accumulator value of this warp is in registers: hand the TMEM stage back
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+            release_tmem(as);
           }
           float v[NCOL];
           {
@@ -405,21 +462,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           }
         }
       }
-      if (!active) {  // nothing to read: still one arrival per warp per tile
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
-      }
+      if (!active) release_tmem(as);  // nothing to read: still one arrival per warp per tile
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (lane == 0) ptx::bulk_wait<0>();  // all stores of this warp have completed at exit
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 2) ptx::cluster_sync_all();  // neither CTA may leave while its peer works
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (NCTA == 2) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
