@@ -236,8 +236,35 @@ __device__ __forceinline__ void zero_acc(float4 (&a)[NV]) {
   for (int i = 0; i < NV; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// LayerNorm backward.  HBM traffic per row (bf16 path): dy 2D + x 4D + dx 4D read, dx 4D + dx_lp 2D
+// written = 16 B per element.  The three per-column accumulators (dgamma, dbeta, colsum of the
+// final dx) cost 72 registers per thread, so the kernel runs 4-warp blocks (3 per SM) and issues
+// every load of a row -- including the previous dx it accumulates into -- before the first use:
+// one memory round trip per row and ~90 KB in flight per SM.
+constexpr int LNB_WARPS = 4;
+constexpr int LNB_THREADS = LNB_WARPS * 32;
+
+template <int NV, int NW>
+__device__ __forceinline__ void block_colreduce_n(const float4 (&acc)[NV], float* red, float* out,
+                                                  int nvec, int D) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) *reinterpret_cast<float4*>(red + warp * D + 4 * c) = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += red[w * D + c];
+    atomicAdd(out + c, s);
+  }
+}
+
 template <int NV, typename TDY, typename TLP>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(LNB_THREADS, 3)
 layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, float* __restrict__ dx, int accumulate,
@@ -250,31 +277,29 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x,
   zero_acc<NV>(acc_g);
   zero_acc<NV>(acc_b);
   zero_acc<NV>(acc_c);
-  float4 g[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = lane + 32 * i;
-    g[i] = c < nvec ? *reinterpret_cast<const float4*>(gamma + 4 * c) : make_float4(0, 0, 0, 0);
-  }
-  for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
-    RowRegs<NV> rx, rdy;
+  for (int row = blockIdx.x * LNB_WARPS + warp; row < M; row += gridDim.x * LNB_WARPS) {
+    RowRegs<NV> rx, rdy, rp;
     rx.load(x + static_cast<size_t>(row) * D, nvec, lane);
     rdy.load(dy + static_cast<size_t>(row) * D, nvec, lane);
+    if (accumulate) rp.load(dx + static_cast<size_t>(row) * D, nvec, lane);
+    else zero_acc<NV>(rp.v);
     const float mu = mean[row], rs = rstd[row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      if (lane + 32 * i < nvec) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c);  // L1-resident
         float4& xv = rx.v[i];
         xv.x = (xv.x - mu) * rs; xv.y = (xv.y - mu) * rs;
         xv.z = (xv.z - mu) * rs; xv.w = (xv.w - mu) * rs;  // xhat
-        const float4 d = rdy.v[i];
+        float4& d = rdy.v[i];
         acc_g[i].x += d.x * xv.x; acc_g[i].y += d.y * xv.y;
         acc_g[i].z += d.z * xv.z; acc_g[i].w += d.w * xv.w;
         acc_b[i].x += d.x; acc_b[i].y += d.y; acc_b[i].z += d.z; acc_b[i].w += d.w;
-        const float a = d.x * g[i].x, b = d.y * g[i].y, c = d.z * g[i].z, e = d.w * g[i].w;
-        s1 += (a + b) + (c + e);
-        s2 += (a * xv.x + b * xv.y) + (c * xv.z + e * xv.w);
+        d.x *= g.x; d.y *= g.y; d.z *= g.z; d.w *= g.w;  // dy * gamma from here on
+        s1 += (d.x + d.y) + (d.z + d.w);
+        s2 += (d.x * xv.x + d.y * xv.y) + (d.z * xv.z + d.w * xv.w);
       }
     }
     s1 = warp_sum(s1) / D;
@@ -283,26 +308,21 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x,
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
-        const float4 d = rdy.v[i], xv = rx.v[i];
+        const float4 d = rdy.v[i], xv = rx.v[i], prev = rp.v[i];
         float4 o;
-        o.x = rs * (d.x * g[i].x - s1 - xv.x * s2);
-        o.y = rs * (d.y * g[i].y - s1 - xv.y * s2);
-        o.z = rs * (d.z * g[i].z - s1 - xv.z * s2);
-        o.w = rs * (d.w * g[i].w - s1 - xv.w * s2);
-        float* dst = dx + static_cast<size_t>(row) * D + 4 * c;
-        if (accumulate) {
-          const float4 prev = *reinterpret_cast<const float4*>(dst);
-          o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
-        }
-        *reinterpret_cast<float4*>(dst) = o;
+        o.x = prev.x + rs * (d.x - s1 - xv.x * s2);
+        o.y = prev.y + rs * (d.y - s1 - xv.y * s2);
+        o.z = prev.z + rs * (d.z - s1 - xv.z * s2);
+        o.w = prev.w + rs * (d.w - s1 - xv.w * s2);
+        *reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * D + 4 * c) = o;
         if (dx_lp != nullptr) Vec4<TLP>::st(dx_lp + static_cast<size_t>(row) * D + 4 * c, o);
         acc_c[i].x += o.x; acc_c[i].y += o.y; acc_c[i].z += o.z; acc_c[i].w += o.w;
       }
     }
   }
-  block_colreduce<NV>(acc_g, red, dgamma, nvec, D);
-  block_colreduce<NV>(acc_b, red, dbeta, nvec, D);
-  if (dcolsum != nullptr) block_colreduce<NV>(acc_c, red, dcolsum, nvec, D);
+  block_colreduce_n<NV, LNB_WARPS>(acc_g, red, dgamma, nvec, D);
+  block_colreduce_n<NV, LNB_WARPS>(acc_b, red, dbeta, nvec, D);
+  if (dcolsum != nullptr) block_colreduce_n<NV, LNB_WARPS>(acc_c, red, dcolsum, nvec, D);
 }
 
 template <typename T>
@@ -736,21 +756,21 @@ int layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* mea
   const int nv = nv_for(D);
   if (nv < 0) return MMU_ERR_SHAPE;
   if (M <= 0) return 0;
-  int grid = grid_for(M, WARPS * 4);
-  if (grid > sm_count() * 2) grid = sm_count() * 2;
-  const size_t smem = static_cast<size_t>(WARPS) * D * sizeof(float);
+  int grid = (M + LNB_WARPS - 1) / LNB_WARPS;
+  if (grid > sm_count() * 3) grid = sm_count() * 3;
+  const size_t smem = static_cast<size_t>(LNB_WARPS) * D * sizeof(float);
   using bf = __nv_bfloat16;
   if (dy_dtype == DT_BF16 && (dx_lp == nullptr || lp_dtype == DT_BF16)) {
-    MMU_NV_DISPATCH(nv, (layernorm_bwd_kernel<NV, bf, bf><<<grid, THREADS, smem, stream>>>(
+    MMU_NV_DISPATCH(nv, (layernorm_bwd_kernel<NV, bf, bf><<<grid, LNB_THREADS, smem, stream>>>(
                             static_cast<const bf*>(dy), x, mean, rstd, gamma, dx, accumulate,
                             static_cast<bf*>(dx_lp), dgamma, dbeta, dcolsum, M, D)));
   } else if (dy_dtype == DT_F32 && (dx_lp == nullptr || lp_dtype == DT_F32)) {
     // fp32 path: the "low precision" copy would be identical to dx itself
-    MMU_NV_DISPATCH(nv, (layernorm_bwd_kernel<NV, float, float><<<grid, THREADS, smem, stream>>>(
+    MMU_NV_DISPATCH(nv, (layernorm_bwd_kernel<NV, float, float><<<grid, LNB_THREADS, smem, stream>>>(
                             static_cast<const float*>(dy), x, mean, rstd, gamma, dx, accumulate,
                             static_cast<float*>(dx_lp), dgamma, dbeta, dcolsum, M, D)));
   } else if (dy_dtype == DT_F32 && lp_dtype == DT_BF16) {
-    MMU_NV_DISPATCH(nv, (layernorm_bwd_kernel<NV, float, bf><<<grid, THREADS, smem, stream>>>(
+    MMU_NV_DISPATCH(nv, (layernorm_bwd_kernel<NV, float, bf><<<grid, LNB_THREADS, smem, stream>>>(
                             static_cast<const float*>(dy), x, mean, rstd, gamma, dx, accumulate,
                             static_cast<bf*>(dx_lp), dgamma, dbeta, dcolsum, M, D)));
   } else {
