@@ -446,6 +446,20 @@ int fwd(const void* qkv, void* out, void* probs, float* scores, int B, int L, in
         cudaStream_t st) {
   const int hd = D / H, G = L * H, Bp = (B + 7) / 8 * 8;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  if (Bp <= 128) {
+    // P = softmax(Q K^T / sqrt(hd)) in ONE kernel: the row softmax runs in the GEMM epilogue
+    // (a lane owns a whole 128-column row of the accumulator), S never exists in HBM
+    GemmEpilogue e = store_epi(probs, 1, Bp, scale);
+    e.mode = EPI_SOFTMAX;
+    e.n_valid = B;
+    const int rc0 = gemm_bf16_batched_launch(qkv_view(qkv, B, L, D, H, 0, 0),
+                                             qkv_view(qkv, B, L, D, H, 1, 0), G, B, Bp, hd, e, 1, 0,
+                                             static_cast<long long>(B) * Bp, st);
+    if (rc0) return rc0;
+    return gemm_bf16_batched_launch(sq_view(probs, G, B, Bp, 0), qkv_view(qkv, B, L, D, H, 2, 1), G, B,
+                                    hd, B, store_epi(out, 1, static_cast<long long>(L) * D, 1.0f), H,
+                                    hd, D, st);
+  }
   int rc = gemm_bf16_batched_launch(qkv_view(qkv, B, L, D, H, 0, 0), qkv_view(qkv, B, L, D, H, 1, 0),
                                     G, B, Bp, hd, store_epi(scores, 0, Bp, scale), 1, 0,
                                     static_cast<long long>(B) * Bp, st);

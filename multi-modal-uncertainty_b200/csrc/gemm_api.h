@@ -11,6 +11,8 @@ enum GemmEpiMode : int {
   EPI_RESIDUAL = 2,   // out(f32) = aux(f32) + alpha*acc + bias
   EPI_DGELU = 3,      // out = alpha*acc * d/dz[z*sigmoid(1.702 z)] with z = aux (bf16)
   EPI_ATOMIC = 4,     // out(f32) += alpha*acc   (split-K partial sums)
+  EPI_SOFTMAX = 5,    // out(bf16) = softmax over columns [0, n_valid) of alpha*acc, 0 beyond
+                      // (batched bf16 path, N <= 128: the attention probabilities, fused)
 };
 
 struct GemmEpilogue {
@@ -25,6 +27,7 @@ struct GemmEpilogue {
   // out_row = (r / seg_len) * seg_stride + seg_off + r % seg_len      (seg_len <= 0: identity)
   int seg_len, seg_stride, seg_off;
   float alpha;
+  int n_valid;  // EPI_SOFTMAX: number of real columns (N is padded to a multiple of 8)
 };
 
 struct GemmProblem {
@@ -41,6 +44,8 @@ struct GemmProblem {
   int b_hdiv, b_hstride, b_col0;
   int out_hdiv, out_hstride;
   long long out_mid_stride;
+  // single-CTA kernel, N <= 128: the MMA runs at N = 128 and only 128 rows of B are staged
+  int half_n;
 };
 
 // Operand of a batched GEMM: a 3-D view (inner contiguous; strides in elements).

@@ -215,6 +215,13 @@ int launch_with_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
       if ((rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;
       if ((rc = omap(&c1, e.aux, e.ld_aux)) != 0) return rc;
       return launch_mode<EPI_DGELU, true>(ta, tb, c0, c1, p, e, stream);
+    case EPI_SOFTMAX:
+      if (!obf || e.out == nullptr || p.batch <= 0 || p.N > gemm::BN / 2 || e.n_valid < 1 ||
+          e.n_valid > p.N)
+        return MMU_ERR_ARG;
+      if ((rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;
+      c1 = c0;
+      return launch_mode<EPI_SOFTMAX, true>(ta, tb, c0, c1, p, e, stream);
     case EPI_ATOMIC:
       if (obf || e.out == nullptr) return MMU_ERR_ARG;
       if ((rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;
@@ -262,13 +269,14 @@ int gemm_bf16_launch(const void* A, long long lda, const void* B, long long ldb,
     p.splits = (kb_total + kb_per - 1) / kb_per;
   }
   p.batch = 0;
+  p.half_n = !use_pair(p) && p.N <= BN / 2;
   CUtensorMap ta, tb;
   int rc;
   if (!p.a_mn_major) rc = make_tmap_bf16_2d(&ta, A, p.K, p.M, lda, BK, BM);
   else               rc = make_tmap_bf16_2d(&ta, A, p.M, p.K, lda, 64, BK);
   if (rc != 0) return rc;
   // a CTA of a pair stages only its half of the B tile: the K-major box shrinks to 128 rows
-  const int b_rows = use_pair(p) ? BN / 2 : BN;
+  const int b_rows = (use_pair(p) || p.half_n) ? BN / 2 : BN;
   if (!p.b_mn_major) rc = make_tmap_bf16_2d(&tb, B, p.K, p.N, ldb, BK, b_rows);
   else               rc = make_tmap_bf16_2d(&tb, B, p.N, p.K, ldb, 64, BK);
   if (rc != 0) return rc;
@@ -281,7 +289,7 @@ int gemm_bf16_batched_launch(const BatchedOperand& A, const BatchedOperand& B, i
                              long long out_mid_stride, cudaStream_t stream) {
   using namespace gemm;
   if (batch <= 0 || M <= 0 || N <= 0 || K <= 0) return MMU_ERR_SHAPE;
-  if (e.mode != EPI_STORE) return MMU_ERR_ARG;
+  if (e.mode != EPI_STORE && e.mode != EPI_SOFTMAX) return MMU_ERR_ARG;
   GemmProblem p{};
   p.M = M; p.N = N; p.K = K;
   p.a_mn_major = A.mn_major; p.b_mn_major = B.mn_major;
@@ -291,12 +299,13 @@ int gemm_bf16_batched_launch(const BatchedOperand& A, const BatchedOperand& B, i
   p.b_hdiv = B.hdiv; p.b_hstride = B.hstride; p.b_col0 = B.col0;
   p.out_hdiv = out_hdiv < 1 ? 1 : out_hdiv; p.out_hstride = out_hstride;
   p.out_mid_stride = out_mid_stride;
+  p.half_n = N <= BN / 2;  // the MMA runs at N = 128 and only 128 rows of B are staged
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16_3d(&ta, A.base, A.inner, A.mid, A.outer, A.mid_stride, A.outer_stride,
                              A.mn_major ? 64 : BK, A.mn_major ? BK : BM);
   if (rc != 0) return rc;
   rc = make_tmap_bf16_3d(&tb, B.base, B.inner, B.mid, B.outer, B.mid_stride, B.outer_stride,
-                         B.mn_major ? 64 : BK, B.mn_major ? BK : BN);
+                         B.mn_major ? 64 : BK, B.mn_major ? BK : (p.half_n ? BN / 2 : BN));
   if (rc != 0) return rc;
   return launch_with_epilogue(ta, tb, p, e, stream);
 }

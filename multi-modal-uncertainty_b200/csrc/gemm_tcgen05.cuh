@@ -218,7 +218,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], G::STAGE_BYTES);
+          // N <= 128 problems stage (and multiply) only 128 rows of B
+          const int b_boxes = p.half_n ? BN / 128 : BN / 64;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage],
+                                     G::A_STAGE_BYTES + (p.half_n ? G::B_STAGE_BYTES / 2 : G::B_STAGE_BYTES));
           if (p.batch > 0) {
             if (!p.a_mn_major) {
               ptx::tma_load_3d(sa, &tma_a, &full_bar[stage], a_off + k0, a_mid, m0);
@@ -230,8 +233,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             if (!p.b_mn_major) {
               ptx::tma_load_3d(sb, &tma_b, &full_bar[stage], b_off + k0, b_mid, n0);
             } else {
-#pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
+              for (int j = 0; j < b_boxes; ++j)
                 ptx::tma_load_3d(sb + j * 8192, &tma_b, &full_bar[stage], b_off + n0 + 64 * j, b_mid, k0);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -247,8 +249,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           if (!p.b_mn_major) {
             ptx::tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
           } else {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
+            for (int j = 0; j < b_boxes; ++j)
               ptx::tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n0 + 64 * j, k0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -258,7 +259,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0 && rank == 0) {  // pair: the leader issues for both SMs
-      const uint32_t idesc = ptx::make_idesc_bf16(G::BM_TILE, BN, p.a_mn_major, p.b_mn_major);
+      const uint32_t idesc = ptx::make_idesc_bf16(G::BM_TILE, (NCTA == 1 && p.half_n) ? BN / 2 : BN,
+                                                  p.a_mn_major, p.b_mn_major);
       // K-major SW128: 8-row groups 1024 B apart, k advances 32 B inside the swizzle atom.
       // MN-major SW128: 64-element MN groups 8192 B apart (one TMA box), 8-k groups 1024 B apart.
       const uint32_t a_lbo = p.a_mn_major ? 8192u : 16u, a_kstep = p.a_mn_major ? 2048u : 32u;
@@ -378,6 +380,88 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           ptx::bulk_commit();
         }
       };
+      if constexpr (MODE == EPI_SOFTMAX) {
+        // Row softmax of alpha*acc over columns [0, n_valid), N <= 128.  The two warps that share
+        // a TMEM lane quadrant split a row's columns (64 each), run an online max/sum pass over
+        // TMEM, exchange (max, sum) through shared memory, then normalise and store their half:
+        // two TMEM passes, nothing touches HBM but the bf16 probabilities.
+        const int cbase = h * 64;
+        const bool rows_ok = m0 < p.M;
+        const int nloc = min(64, max(0, p.N - cbase));
+        const int nch = rows_ok ? (nloc + NCOL - 1) / NCOL : 0;   // 0, 1 or 2 chunks
+        const float sc = e.alpha * 1.4426950408889634f;
+        const uint32_t tsm = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                             static_cast<uint32_t>(as * BN + cbase);
+        auto ex2 = [](float x) {
+          float y;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+          return y;
+        };
+        auto sm_load = [&](int c) { ptx::tmem_ld_32x32(tsm + c * NCOL, r[c & 1]); };
+        float mx = -INFINITY, sum = 0.f;
+        if (nch > 0) sm_load(0);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c < nch) {
+            ptx::tmem_ld_wait();
+            if (c + 1 < nch) sm_load(c + 1);
+            const int col0 = cbase + c * NCOL;
+            const bool full = col0 + NCOL <= e.n_valid;
+            float cm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < NCOL; ++i)
+              if (full || col0 + i < e.n_valid) cm[i & 3] = fmaxf(cm[i & 3], __uint_as_float(r[c & 1][i]));
+            const float mn = fmaxf(fmaxf(mx, fmaxf(cm[0], cm[1])), fmaxf(cm[2], cm[3]));
+            const float off = -mn * sc;
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < NCOL; ++i)
+              if (full || col0 + i < e.n_valid)
+                part[i & 3] += ex2(fmaf(__uint_as_float(r[c & 1][i]), sc, off));
+            sum = sum * ex2((mx - mn) * sc) + ((part[0] + part[1]) + (part[2] + part[3]));
+            mx = mn;
+          }
+        }
+        {  // exchange with the warp that holds the other 64 columns of the same rows
+          float2* xch = reinterpret_cast<float2*>(bias_s);  // [2][128] (no bias in this mode)
+          xch[h * 128 + q * 32 + lane] = make_float2(mx, sum);
+          named_bar_sync(2 + q, 64);
+          const float2 o = xch[(h ^ 1) * 128 + q * 32 + lane];
+          named_bar_sync(2 + q, 64);  // both have read: the slots may be rewritten next tile
+          const float mn = fmaxf(mx, o.x);
+          sum = sum * ex2((mx - mn) * sc) + o.y * ex2((o.x - mn) * sc);
+          mx = mn;
+        }
+        if (nch > 0) {
+          const float inv = 1.0f / sum, off = -mx * sc;
+          sm_load(0);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (c < nch) {
+              ptx::tmem_ld_wait();
+              if (c + 1 < nch) sm_load(c + 1);
+              else release_tmem(as);
+              const int col0 = cbase + c * NCOL;
+              const bool full = col0 + NCOL <= e.n_valid;
+              float v[NCOL];
+#pragma unroll
+              for (int i = 0; i < NCOL; ++i)
+                v[i] = (full || col0 + i < e.n_valid)
+                           ? ex2(fmaf(__uint_as_float(r[c & 1][i]), sc, off)) * inv : 0.f;
+              const uint32_t box = box0 + static_cast<uint32_t>(c & 1) * BOX_BYTES;
+              box_free(c == 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::sts_v4u(box + piece(k), pack_bf16x2(v[8 * k], v[8 * k + 1]),
+                             pack_bf16x2(v[8 * k + 2], v[8 * k + 3]), pack_bf16x2(v[8 * k + 4], v[8 * k + 5]),
+                             pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+              box_store(&tma_c0, box, col0);
+            }
+          }
+        } else {
+          release_tmem(as);
+        }
+      } else {
       if (active) tmem_load(0);
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
@@ -463,6 +547,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         }
       }
       if (!active) release_tmem(as);  // nothing to read: still one arrival per warp per tile
+      }  // MODE != EPI_SOFTMAX
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (lane == 0) ptx::bulk_wait<0>();  // all stores of this warp have completed at exit
