@@ -177,6 +177,9 @@ typedef struct {
   int cls_token;  /* 1: the CLS-token variant, src/model.py:306-361 */
   int precision;  /* MMU_F32 or MMU_BF16 */
   int max_variants; /* capacity for packed-variant evaluation (0 or 1: single variant) */
+  int group_pool;   /* > 0: MIMOTransfomer head wiring (src/model.py:148-153): head e = mean of
+                       token positions [e*group_pool, (e+1)*group_pool); with d_txt == 0 the text
+                       projection does not exist (single-modality model) */
 } mmu_flava_config;
 
 typedef struct {

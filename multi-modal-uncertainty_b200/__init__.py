@@ -13,8 +13,9 @@ from .src import (callbacks, dataset, framework, metrics, model, optim, parallel
                   robustness, training_loop, utils)
 from .src.framework import Model_  # noqa: F401
 from .src.metrics import acc  # noqa: F401
-from .src.model import FlavaFusionTransfomer, FlavaFusionTransfomerwithCLSToken  # noqa: F401
+from .src.model import (FlavaFusionTransfomer, FlavaFusionTransfomerwithCLSToken,  # noqa: F401
+                        MIMOTransfomer)
 from .src.optim import FusedAdamW, get_cosine_schedule_with_warmup  # noqa: F401
 
-__all__ = ["FlavaFusionTransfomer", "FlavaFusionTransfomerwithCLSToken", "Model_", "FusedAdamW",
+__all__ = ["FlavaFusionTransfomer", "FlavaFusionTransfomerwithCLSToken", "MIMOTransfomer", "Model_", "FusedAdamW",
            "get_cosine_schedule_with_warmup", "acc", "ops"]

@@ -52,7 +52,7 @@ ACC_INT_WORDS = ACC_OFF["conf_sum"]  # words [0, ACC_INT_WORDS) are uint64, the 
 class FlavaConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("B", "l_img", "l_txt", "d_img", "d_txt", "D", "n_head",
                                        "n_layers", "E", "C", "avg_pool", "cls_token", "precision",
-                                       "max_variants")]
+                                       "max_variants", "group_pool")]
 
 
 class ParamEntry(C.Structure):

@@ -69,8 +69,11 @@ int build_layout(const FlavaConfig& c, Layout* L, ParamEntry* out, int max_entri
   char nm[96];
   L->img_w = tb.add("image_to_mm_projection.weight", c.D, c.d_img, stem);
   L->img_b = tb.add("image_to_mm_projection.bias", c.D, 0, stem);
-  L->txt_w = tb.add("text_to_mm_projection.weight", c.D, c.d_txt, stem);
-  L->txt_b = tb.add("text_to_mm_projection.bias", c.D, 0, stem);
+  L->txt_w = L->txt_b = -1;
+  if (c.d_txt > 0) {
+    L->txt_w = tb.add("text_to_mm_projection.weight", c.D, c.d_txt, stem);
+    L->txt_b = tb.add("text_to_mm_projection.bias", c.D, 0, stem);
+  }
   L->cls = -1;
   if (c.cls_token) L->cls = tb.add("class_embeddings", c.D, c.E, stem);
   L->lnpre_w = tb.add("ln_pre.weight", c.D, 0, stem);
@@ -159,17 +162,24 @@ struct Bump {
   }
 };
 
+// The tensor-core path needs 16-byte rows (feature widths % 8): a stem whose input width is not
+// (MIMOTransfomer: 14*14 = 196 pixels per view) runs its small projection GEMMs in fp32 instead.
+bool stem_is_f32(const FlavaConfig& c) {
+  return c.precision != PREC_BF16 || c.d_img % 8 != 0 || c.d_txt % 8 != 0;
+}
+
 void carve(const FlavaConfig& c, int training, void* base, const Layout& lay, Ws* w) {
   Bump b{static_cast<char*>(base), 0};
   const long long s = c.precision == PREC_BF16 ? 2 : 4;
+  const long long ss = stem_is_f32(c) ? 4 : 2;
   const long long L = (c.cls_token ? c.E : 0) + c.l_img + c.l_txt;
   const long long M = static_cast<long long>(c.B) * L;
   const long long D = c.D;
   const long long Bp = (c.B + 7) / 8 * 8;
   const long long sq_elems = L * c.n_head * c.B * Bp;
   w->params_lp = c.precision == PREC_BF16 ? b.take<void>(lay.total * 2) : nullptr;
-  w->img_t = b.take<void>(static_cast<long long>(c.B) * c.l_img * c.d_img * s);
-  w->txt_t = b.take<void>(static_cast<long long>(c.B) * c.l_txt * c.d_txt * s);
+  w->img_t = b.take<void>(static_cast<long long>(c.B) * c.l_img * c.d_img * ss);
+  w->txt_t = b.take<void>(static_cast<long long>(c.B) * c.l_txt * c.d_txt * ss);
   w->mm_x = b.take<float>(M * D * 4);
   w->stats_pre = b.take<float>(2 * M * 4);
   const int slots = training ? c.n_layers : (c.n_layers > 0 ? 1 : 0);
@@ -205,8 +215,8 @@ void carve(const FlavaConfig& c, int training, void* base, const Layout& lay, Ws
     w->dh = b.take<void>(M * D * s);
     w->delta = b.take<float>(L * c.n_head * c.B * 4);
     w->dprobs = c.precision == PREC_BF16 ? b.take<void>(sq_elems * 2) : nullptr;
-    w->dimg = b.take<void>(static_cast<long long>(c.B) * c.l_img * D * s);
-    w->dtxt = b.take<void>(static_cast<long long>(c.B) * c.l_txt * D * s);
+    w->dimg = b.take<void>(static_cast<long long>(c.B) * c.l_img * D * ss);
+    w->dtxt = b.take<void>(static_cast<long long>(c.B) * c.l_txt * D * ss);
   } else {
     w->dvec = nullptr; w->dx = nullptr; w->dx_lp = nullptr; w->dbig = nullptr; w->dh = nullptr;
     w->delta = nullptr; w->dprobs = nullptr; w->dimg = nullptr; w->dtxt = nullptr;
@@ -218,8 +228,9 @@ int check_config(const FlavaConfig& c) {
   if (c.B < 1 || c.D < 4 || c.n_head < 1 || c.E < 1 || c.E > 16 || c.C < 1) return MMU_ERR_SHAPE;
   if (c.D % c.n_head != 0 || (c.D / c.n_head) % 4 != 0) return MMU_ERR_SHAPE;
   if (c.D % 4 != 0 || c.d_img % 4 != 0 || c.d_txt % 4 != 0 || c.D > 1024) return MMU_ERR_SHAPE;
-  if (c.precision == PREC_BF16 && (c.D % 8 != 0 || c.d_img % 8 != 0 || c.d_txt % 8 != 0))
-    return MMU_ERR_SHAPE;
+  if (c.d_img < 4 || c.d_txt < 0 || c.group_pool < 0) return MMU_ERR_SHAPE;
+  if (c.precision == PREC_BF16 && c.D % 8 != 0) return MMU_ERR_SHAPE;
+  if (c.group_pool > 0 && (c.avg_pool || c.cls_token)) return MMU_ERR_ARG;
   if (c.precision != PREC_FP32 && c.precision != PREC_BF16) return MMU_ERR_ARG;
   if (c.avg_pool && !c.cls_token && c.E != 2) return MMU_ERR_SHAPE;  // src/model.py:282-284
   return 0;
@@ -279,11 +290,13 @@ int resolve_shape(const FlavaConfig& c, const FlavaInputs& in, Shape* s) {
   s->n_img = in.img != nullptr ? in.n_img : 0;
   s->n_txt = in.txt != nullptr ? in.n_txt : 0;
   if (s->n_img < 0 || s->n_img > c.l_img || s->n_txt < 0 || s->n_txt > c.l_txt) return MMU_ERR_SHAPE;
+  if (c.d_txt == 0 && s->n_txt > 0) return MMU_ERR_ARG;  // the model has no text projection
   s->L = s->n_cls + s->n_img + s->n_txt;
   s->M = c.B * s->L;
   if (s->n_img + s->n_txt == 0) return MMU_ERR_SHAPE;
   if ((!c.avg_pool || c.cls_token) && in.n_variants <= 1) {
-    if (c.E > s->L) return MMU_ERR_SHAPE;  // head i reads token position i (src/model.py:286-287)
+    // head i reads token position i (src/model.py:286-287) or its group of positions (:148-153)
+    if (c.E * (c.group_pool > 0 ? c.group_pool : 1) > s->L) return MMU_ERR_SHAPE;
   }
   return 0;
 }
@@ -291,7 +304,12 @@ int resolve_shape(const FlavaConfig& c, const FlavaInputs& in, Shape* s) {
 HeadSegments head_segments(const FlavaConfig& c, const Shape& s) {
   HeadSegments hs{};
   hs.E = c.E;
-  if (c.avg_pool && !c.cls_token) {
+  if (c.group_pool > 0) {
+    for (int e = 0; e < c.E; ++e) {
+      hs.seg_begin[e] = e * c.group_pool;
+      hs.seg_end[e] = (e + 1) * c.group_pool;
+    }
+  } else if (c.avg_pool && !c.cls_token) {
     hs.seg_begin[0] = 0; hs.seg_end[0] = s.n_img;
     hs.seg_begin[1] = s.n_img; hs.seg_end[1] = s.n_img + s.n_txt;
   } else {
@@ -354,19 +372,25 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
 
   // ---- stem: gather/mask/cast inputs, per-modality projections written straight into the
   //      concatenated (B, L, D) buffer (fuses torch.cat, src/model.py:262-273), CLS rows
+  const bool stem32 = stem_is_f32(c);  // fp32 stem GEMMs read the fp32 master weights
+  const Gemm gemm_stem{stem32 ? static_cast<int>(PREC_FP32) : c.precision, stream};
+  const int dt_stem = stem32 ? DT_F32 : DT_BF16;
+  auto Wstem = [&](long long off) -> const void* {
+    return stem32 ? static_cast<const void*>(params + off) : W(off);
+  };
   if (s.n_img > 0) {
-    MMU_TRY(cast_gather(in.img, w.img_t, dt, c.B, src_l_img, c.d_img, in.idx_img, s.n_img, in.keep, 0,
-                        stream));
+    MMU_TRY(cast_gather(in.img, w.img_t, dt_stem, c.B, src_l_img, c.d_img, in.idx_img, s.n_img,
+                        in.keep, 0, stream));
     GemmEpilogue e = epi(EPI_STORE, w.mm_x, 0, D, params + lay.img_b);
     e.seg_len = s.n_img; e.seg_stride = s.L; e.seg_off = s.n_cls;
-    MMU_TRY(gemm(w.img_t, c.d_img, 0, W(lay.img_w), c.d_img, 0, c.B * s.n_img, D, c.d_img, e));
+    MMU_TRY(gemm_stem(w.img_t, c.d_img, 0, Wstem(lay.img_w), c.d_img, 0, c.B * s.n_img, D, c.d_img, e));
   }
   if (s.n_txt > 0) {
-    MMU_TRY(cast_gather(in.txt, w.txt_t, dt, c.B, src_l_txt, c.d_txt, in.idx_txt, s.n_txt, in.keep, 1,
-                        stream));
+    MMU_TRY(cast_gather(in.txt, w.txt_t, dt_stem, c.B, src_l_txt, c.d_txt, in.idx_txt, s.n_txt,
+                        in.keep, 1, stream));
     GemmEpilogue e = epi(EPI_STORE, w.mm_x, 0, D, params + lay.txt_b);
     e.seg_len = s.n_txt; e.seg_stride = s.L; e.seg_off = s.n_cls + s.n_img;
-    MMU_TRY(gemm(w.txt_t, c.d_txt, 0, W(lay.txt_w), c.d_txt, 0, c.B * s.n_txt, D, c.d_txt, e));
+    MMU_TRY(gemm_stem(w.txt_t, c.d_txt, 0, Wstem(lay.txt_w), c.d_txt, 0, c.B * s.n_txt, D, c.d_txt, e));
   }
   if (c.cls_token) MMU_TRY(cls_fill(params + lay.cls, w.mm_x, c.B, s.L, D, c.E, stream));
 
@@ -531,20 +555,23 @@ int flava_backward(const FlavaConfig& c, const float* params, const FlavaInputs&
                             dmm, 0, nullptr, DT_F32, grads + lay.lnpre_w, grads + lay.lnpre_b,
                             nullptr, M, D, stream));
       if (c.cls_token) MMU_TRY(cls_bwd(dmm, grads + lay.cls, c.B, s.L, D, c.E, stream));
-      MMU_TRY(split_rows(dmm, w.dimg, w.dtxt, dt, c.B, s.L, s.n_cls, s.n_img, s.n_txt, D, stream));
+      const bool stem32 = stem_is_f32(c);
+      const Gemm gemm_stem{stem32 ? static_cast<int>(PREC_FP32) : c.precision, stream};
+      const int dt_stem = stem32 ? DT_F32 : DT_BF16;
+      MMU_TRY(split_rows(dmm, w.dimg, w.dtxt, dt_stem, c.B, s.L, s.n_cls, s.n_img, s.n_txt, D, stream));
       if (s.n_img > 0) {
         const int Mi = c.B * s.n_img;
-        MMU_TRY(gemm(w.dimg, D, 1, w.img_t, c.d_img, 1, D, c.d_img, Mi,
-                     epi(EPI_ATOMIC, grads + lay.img_w, 0, c.d_img, nullptr),
-                     wgrad_splits(D, c.d_img, Mi)));
-        MMU_TRY(colsum_accumulate(w.dimg, dt, grads + lay.img_b, Mi, D, stream));
+        MMU_TRY(gemm_stem(w.dimg, D, 1, w.img_t, c.d_img, 1, D, c.d_img, Mi,
+                          epi(EPI_ATOMIC, grads + lay.img_w, 0, c.d_img, nullptr),
+                          wgrad_splits(D, c.d_img, Mi)));
+        MMU_TRY(colsum_accumulate(w.dimg, dt_stem, grads + lay.img_b, Mi, D, stream));
       }
       if (s.n_txt > 0) {
         const int Mt = c.B * s.n_txt;
-        MMU_TRY(gemm(w.dtxt, D, 1, w.txt_t, c.d_txt, 1, D, c.d_txt, Mt,
-                     epi(EPI_ATOMIC, grads + lay.txt_w, 0, c.d_txt, nullptr),
-                     wgrad_splits(D, c.d_txt, Mt)));
-        MMU_TRY(colsum_accumulate(w.dtxt, dt, grads + lay.txt_b, Mt, D, stream));
+        MMU_TRY(gemm_stem(w.dtxt, D, 1, w.txt_t, c.d_txt, 1, D, c.d_txt, Mt,
+                          epi(EPI_ATOMIC, grads + lay.txt_w, 0, c.d_txt, nullptr),
+                          wgrad_splits(D, c.d_txt, Mt)));
+        MMU_TRY(colsum_accumulate(w.dtxt, dt_stem, grads + lay.txt_b, Mt, D, stream));
       }
     }
   }

@@ -26,6 +26,10 @@ struct FlavaConfig {
   int cls_token;  // FlavaFusionTransfomerwithCLSToken
   int precision;  // Precision
   int max_variants;  // capacity for packed-variant evaluation (0 or 1: single variant)
+  // MIMOTransfomer (reference src/model.py:114-159): d_txt == 0 means "no text modality" (its
+  // projection does not exist), and head e pools the mean of token positions
+  // [e*group_pool, (e+1)*group_pool) -- the `x.view(b, e, c, -1).mean(2)` of :148-149.
+  int group_pool;    // 0: FLAVA head wiring (token e / avg_pool)
 };
 
 struct ParamEntry {

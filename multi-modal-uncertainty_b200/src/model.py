@@ -103,6 +103,11 @@ class FlavaFusionTransfomer(nn.Module):
         self._dims = dict(d_img=image_hidden_size, d_txt=text_hidden_size, D=multimodal_hidden_size,
                           n_head=multimodal_num_attention_heads,
                           n_layers=multimodal_num_hidden_layers)
+        self._finish_init()
+
+    _group_pool = 0  # MIMOTransfomer: token positions pooled per head
+
+    def _finish_init(self):
         self._ws = {}
         self._pack_caps = {}
         self._cfg_cache = {}
@@ -240,14 +245,14 @@ class FlavaFusionTransfomer(nn.Module):
 
     # ---------------------------------------------------------------------- engine
     def _config(self, B, l_img, l_txt, max_variants=0):
-        key = (B, l_img, l_txt, max_variants)
+        key = (B, l_img, l_txt, max_variants, self._group_pool)
         cfg = self._cfg_cache.get(key)
         if cfg is None:
             d = self._dims
             cfg = _lib.FlavaConfig(B, l_img, l_txt, d["d_img"], d["d_txt"], d["D"], d["n_head"],
                                    d["n_layers"], self.out_dim, self.num_classes,
                                    int(self.avg_pool), int(self._cls_token), self.precision,
-                                   max_variants)
+                                   max_variants, self._group_pool)
             self._cfg_cache[key] = cfg
         return cfg
 
@@ -480,3 +485,93 @@ class FlavaFusionTransfomerwithCLSToken(FlavaFusionTransfomer):
         super().__init__(out_dim, num_classes, image_hidden_size, text_hidden_size,
                          multimodal_hidden_size, multimodal_num_attention_heads,
                          multimodal_num_hidden_layers, drop, **kwargs)
+
+
+class MIMOTransfomer(FlavaFusionTransfomer):
+    """Drop-in for reference ``MIMOTransfomer`` (src/model.py:114-171): the four-view FashionMNIST
+    transformer.  ``x`` is ``(B, E, C, H, W)``; every (view, channel) image is one token of
+    ``H*W`` pixels, projected to ``hidden_size``, run through the same batch-axis-attention blocks
+    as the FLAVA fusion model, and head ``e`` reads the mean over the ``C`` tokens of view ``e``.
+    It runs on the same engine (single modality, ``group_pool`` head wiring); the 196-pixel
+    projection is not 16-byte-row aligned in bf16, so the engine keeps that small stem GEMM in fp32.
+    """
+
+    def __init__(self,
+                 out_dim,
+                 num_classes,
+                 hidden_size,
+                 image_dim=14 * 14,
+                 multimodal_num_hidden_layers=3,
+                 multimodal_num_attention_heads=3,
+                 drop=0,
+                 **kwargs: Any):
+        nn.Module.__init__(self)
+        self.avg_pool = False
+        self.out_dim = out_dim
+        self.num_classes = num_classes
+        self.drop = float(drop)
+        self.precision = _PREC[kwargs.get("precision", "bf16")]
+        self._dims = dict(d_img=image_dim, d_txt=0, D=hidden_size,
+                          n_head=multimodal_num_attention_heads,
+                          n_layers=multimodal_num_hidden_layers)
+        self._group_pool = 1
+        self._finish_init()
+
+    def _block_keys(self, i):
+        pre = f"mm_encoder.resblocks.{i}."
+        return [pre + s for s in ("attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight",
+                                  "attn.out_proj.bias", "ln_1.weight", "ln_1.bias",
+                                  "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight",
+                                  "mlp.c_proj.bias", "ln_2.weight", "ln_2.bias")]
+
+    def _reference_order(self):
+        d = {name: i for i, (name, *_rest) in enumerate(self._table)}
+        order = ["image_to_mm_projection.weight", "image_to_mm_projection.bias"]
+        for i in range(self._dims["n_layers"]):
+            order += self._block_keys(i)
+        for e in range(self.out_dim):
+            order += [f"output_layers.{e}.weight", f"output_layers.{e}.bias"]
+        order += ["ln_pre.weight", "ln_pre.bias", "ln_post.weight", "ln_post.bias"]
+        assert sorted(order) == sorted(d), "engine parameter table and reference key set differ"
+        return [self._table[d[k]] for k in order]
+
+    @torch.no_grad()
+    def _init_like_reference(self):
+        """Initialisers in the reference constructor's order (src/model.py:126-137): projection,
+        blocks, heads; the two LayerNorms consume no random numbers."""
+        d = self._dims
+        sd = {}
+        m = nn.Linear(d["d_img"], d["D"])
+        sd["image_to_mm_projection.weight"], sd["image_to_mm_projection.bias"] = m.weight, m.bias
+        for i in range(d["n_layers"]):
+            pre = f"mm_encoder.resblocks.{i}."
+            attn = nn.MultiheadAttention(d["D"], d["n_head"])
+            sd[pre + "attn.in_proj_weight"] = attn.in_proj_weight
+            sd[pre + "attn.in_proj_bias"] = attn.in_proj_bias
+            sd[pre + "attn.out_proj.weight"] = attn.out_proj.weight
+            sd[pre + "attn.out_proj.bias"] = attn.out_proj.bias
+            ln1 = nn.LayerNorm(d["D"])
+            fc, proj = nn.Linear(d["D"], 4 * d["D"]), nn.Linear(4 * d["D"], d["D"])
+            ln2 = nn.LayerNorm(d["D"])
+            for k, mod in (("ln_1", ln1), ("mlp.c_fc", fc), ("mlp.c_proj", proj), ("ln_2", ln2)):
+                sd[pre + k + ".weight"], sd[pre + k + ".bias"] = mod.weight, mod.bias
+        for e in range(self.out_dim):
+            mod = nn.Linear(d["D"], self.num_classes)
+            sd[f"output_layers.{e}.weight"], sd[f"output_layers.{e}.bias"] = mod.weight, mod.bias
+        for k in ("ln_pre", "ln_post"):
+            mod = nn.LayerNorm(d["D"])
+            sd[k + ".weight"], sd[k + ".bias"] = mod.weight, mod.bias
+        for name, p in self.named_parameters():
+            p.copy_(sd[name])
+
+    def forward(self, x, keep_mask=None):
+        b, e, c, h, w = x.shape
+        if e != self.out_dim or h * w != self._dims["d_img"]:
+            raise ValueError(f"expected (B, {self.out_dim}, C, H, W) with H*W = {self._dims['d_img']}")
+        self._group_pool = c
+        tokens = x.reshape(b, e * c, h * w)
+        return super().forward((tokens, None), keep_mask=keep_mask)
+
+    def forward_variants(self, x, variants):
+        raise NotImplementedError("token-subset variants are a FLAVA-fusion sweep; the FashionMNIST "
+                                  "sweep zero-fills views (robustness.run_view_robustness)")

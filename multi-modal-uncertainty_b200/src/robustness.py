@@ -116,3 +116,28 @@ def run_transformer_robustness(model, batches, device, n_repeats=20, ref_bug_com
         m.all_reduce()
     P = torch.cat(preds).numpy() if collect and preds else None
     return P, torch.cat(labels).numpy(), [m.compute() for m in meters or []]
+
+
+@torch.no_grad()
+def run_view_robustness(model, batches, device, n_views=4, collect=True):
+    """FashionMNIST four-view sweep (reference ``eval_robustness.py:82-121``): for view i, zero-fill
+    view i of every sample, forward, collect the logits.  Returns (outputs (n_views, S, E, C) numpy
+    or None, labels numpy, [per-view metric dicts]) -- the array the reference saves as
+    ``{ckpt}_predictions_robustness.npy``; the metrics accumulate on device per zero-filled view."""
+    model.eval()
+    meters = [UncertaintyMeter(device, model.num_classes, model.out_dim) for _ in range(n_views)]
+    outs, labels = [[] for _ in range(n_views)], []
+    for x, y in batches:
+        x, y = x.to(device), y.to(device).reshape(-1)
+        for i in range(n_views):
+            x_ = x.clone()
+            x_[:, i] = 0  # every other view is kept (reference :92-97 builds the same tensor)
+            logits = model(x_)
+            meters[i].update(logits, y)
+            if collect:
+                outs[i].append(logits.cpu())
+        labels.append(y.cpu())
+    for m in meters:
+        m.all_reduce()
+    P = torch.stack([torch.cat(o) for o in outs]).numpy() if collect and labels else None
+    return P, torch.cat(labels).numpy(), [m.compute() for m in meters]

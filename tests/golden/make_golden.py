@@ -280,6 +280,12 @@ def init_case(ref_model):
         out[name] = {k: torch.stack([v.double().sum(), v.double().abs().sum()])
                      for k, v in m.state_dict().items()}
         out[name + "_param_order"] = [k for k, _ in m.named_parameters()]
+    torch.manual_seed(123)
+    m = ref_model.MIMOTransfomer(out_dim=4, num_classes=10, hidden_size=48,
+                                 multimodal_num_hidden_layers=2, multimodal_num_attention_heads=2)
+    out["mimo"] = {k: torch.stack([v.double().sum(), v.double().abs().sum()])
+                   for k, v in m.state_dict().items()}
+    out["mimo_param_order"] = [k for k, _ in m.named_parameters()]
     return out
 
 

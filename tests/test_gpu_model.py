@@ -337,3 +337,40 @@ def test_packed_variants_equal_per_variant_forwards(mmu, golden, name, precision
     assert P.shape[:2] == (img.shape[0], len(variants))
     assert np.array_equal(P, ref.transpose(0, 1).cpu().numpy())
     assert all(mt["n_samples"] == img.shape[0] for mt in metrics)
+
+
+@pytest.mark.parametrize("precision,tol_l,tol_g", [("fp32", 1e-3, 2e-2), ("bf16", BF16_LOGIT_TOL, 0.25)])
+def test_mimo_transformer_matches_reference_golden(mmu, golden, precision, tol_l, tol_g):
+    """MIMOTransfomer (reference src/model.py:114-171) on the same engine: logits, loss, every
+    gradient against the golden frozen from the unmodified reference module."""
+    c = golden("mimo_transformer.pt")
+    cfg = c["cfg"]
+    m = mmu.MIMOTransfomer(out_dim=cfg["E"], num_classes=cfg["C"], hidden_size=cfg["D"],
+                           multimodal_num_hidden_layers=cfg["layers"],
+                           multimodal_num_attention_heads=cfg["heads"], precision=precision)
+    assert list(m.state_dict().keys()) == list(c["state_dict"].keys())   # reference key ORDER too
+    m.load_state_dict(c["state_dict"], strict=True)
+    m.cuda().train()
+    opt = mmu.FusedAdamW(m.parameters(), lr=1e-3)
+    opt.zero_grad()
+    logits = m(c["x"].cuda())
+    loss = m.compute_loss(logits, c["y_train"].cuda())
+    loss.backward()
+    assert rel(logits.detach().cpu(), c["logits"]) < tol_l
+    assert abs(float(loss.detach()) - float(c["loss"])) < tol_l * max(1.0, abs(float(c["loss"])))
+    if precision == "fp32":
+        assert torch.equal(logits.detach().cpu().argmax(-1), c["logits"].argmax(-1))
+    for k, p in m.named_parameters():
+        g = c["grads"][k]
+        if float(g.abs().max()) > 1e-5:
+            assert float((p.grad.cpu() - g).abs().max() / g.abs().max()) < tol_g, k
+    opt.step()
+    # the four-view zero-fill sweep (eval_robustness.py:82-121) against per-view forwards
+    m.eval()
+    x = c["x"]
+    P, labels, metrics = mmu.robustness.run_view_robustness(m, [(x, c["y"])], "cuda")
+    assert P.shape == (4, x.shape[0], cfg["E"], cfg["C"]) and len(metrics) == 4
+    with torch.no_grad():
+        x0 = x.clone(); x0[:, 2] = 0
+        assert torch.equal(torch.from_numpy(P[2]), m(x0.cuda()).cpu())
+    assert all(mt["n_samples"] == x.shape[0] for mt in metrics)

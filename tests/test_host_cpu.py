@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(mmu):
 def test_struct_sizes_match_header(mmu):
     import ctypes as C
     assert C.sizeof(mmu._lib.MetricAccum) == (15 + 15 + 32 + 32 + 4) * 8 + (15 + 4) * 8
-    assert C.sizeof(mmu._lib.FlavaConfig) == 14 * 4
+    assert C.sizeof(mmu._lib.FlavaConfig) == 15 * 4
     # the ctypes mirrors against sizeof() as compiled into the library
     for which, klass in enumerate((mmu._lib.FlavaConfig, mmu._lib.FlavaInputs, mmu._lib.GemmEpilogue,
                                    mmu._lib.MetricAccum, mmu._lib.ParamEntry)):
@@ -79,6 +79,22 @@ def test_seeded_init_and_parameter_order_match_reference(mmu, golden):
         for k, v in m.state_dict().items():
             got = torch.stack([v.double().sum(), v.double().abs().sum()])
             assert torch.allclose(got, g[name][k], rtol=1e-12, atol=1e-12), k
+
+
+def test_mimo_transformer_seeded_init_and_keys(mmu, golden):
+    """MIMOTransfomer: reference parameter order / state-dict keys and seed-for-seed initial
+    weights (reference src/model.py:114-137)."""
+    g = golden("init_seed123.pt")
+    torch.manual_seed(123)
+    m = mmu.MIMOTransfomer(out_dim=4, num_classes=10, hidden_size=48,
+                           multimodal_num_hidden_layers=2, multimodal_num_attention_heads=2)
+    assert [k for k, _ in m.named_parameters()] == g["mimo_param_order"]
+    assert list(m.state_dict().keys()) == list(g["mimo"].keys())
+    for k, v in m.state_dict().items():
+        got = torch.stack([v.double().sum(), v.double().abs().sum()])
+        assert torch.allclose(got, g["mimo"][k], rtol=1e-12, atol=1e-12), k
+    with pytest.raises(mmu._lib.MMUError):   # no CPU execution path here either
+        m(torch.randn(2, 4, 1, 14, 14))
 
 
 def test_stage_ranges_partition_the_flat_buffer(mmu):
