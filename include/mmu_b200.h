@@ -57,7 +57,7 @@ MMU_API const char* mmu_error_string(int code);
 MMU_API long long mmu_launch_count(void);
 /* sizeof() of the ABI structs as compiled into the library, so a binding can verify its mirror:
  * 0 mmu_flava_config, 1 mmu_flava_inputs, 2 mmu_gemm_epilogue, 3 mmu_metric_accum,
- * 4 mmu_param_entry; -1 for anything else. */
+ * 4 mmu_param_entry, 5 mmu_posthoc_accum; -1 for anything else. */
 MMU_API int mmu_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -164,6 +164,22 @@ MMU_API int mmu_heads_uncertainty_epilogue(const float* logits, const long long*
 /* Fused AdamW over a flat fp32 buffer: torch.optim.AdamW as configured in train.py:196-202.
  * `step` is the 1-based step count; grad_scale multiplies g first (1/world_size for DDP);
  * p_bf16 (may be NULL) receives the bf16 shadow of the updated parameters.  n % 4 == 0. */
+/* ------------------------------------------------------------------------------------------
+ * Post-hoc robustness scoring on device: p(true label) from head-averaged probabilities, the
+ * Pearson statistics of experimental vs mean-control delta-p per modality, and per-variant
+ * accuracy of the head-mean logits -- what notebooks/utils.py:22-34 and
+ * notebooks/food101_robustness.py:24-77 compute on the CPU from the dumped (S, 43, K, C) array.
+ * logits: fp32 (V, B, E, C) with V = 3 + 2*n_repeats in the order of
+ * eval_transformer_robustness.py:103-121; labels int64 (B); p_true_out: fp32 (B, V) or NULL.
+ * The accumulator is += (zero it first; sums all-reduce across ranks). */
+typedef struct {
+  double sx[2], sy[2], sxx[2], syy[2], sxy[2]; /* [image, text]: x = dp(experiment), y = mean dp(controls) */
+  unsigned long long n_samples;
+  unsigned long long correct[128];            /* per variant */
+} mmu_posthoc_accum;
+MMU_API int mmu_posthoc_scoring(const float* logits, const long long* labels, int V, int B, int E, int C,
+                        int n_repeats, float* p_true_out, mmu_posthoc_accum* acc, void* stream);
+
 MMU_API int mmu_adamw_flat_step(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n,
                         float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                         float grad_scale, void* stream);

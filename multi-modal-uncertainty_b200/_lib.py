@@ -20,6 +20,7 @@ EXPORTS = [
     "mmu_heads_uncertainty_epilogue", "mmu_adamw_flat_step", "mmu_flava_param_count",
     "mmu_flava_param_table", "mmu_flava_workspace_bytes", "mmu_flava_num_stages",
     "mmu_flava_forward", "mmu_flava_backward", "mmu_cast_f32_to_bf16", "mmu_struct_size",
+    "mmu_posthoc_scoring",
 ]
 
 
@@ -47,6 +48,12 @@ class MetricAccum(C.Structure):
 ACC_WORDS = C.sizeof(MetricAccum) // 8
 ACC_OFF = {name: getattr(MetricAccum, name).offset // 8 for name, _ in MetricAccum._fields_}
 ACC_INT_WORDS = ACC_OFF["conf_sum"]  # words [0, ACC_INT_WORDS) are uint64, the rest are doubles
+
+
+class PosthocAccum(C.Structure):
+    _fields_ = [("sx", C.c_double * 2), ("sy", C.c_double * 2), ("sxx", C.c_double * 2),
+                ("syy", C.c_double * 2), ("sxy", C.c_double * 2), ("n_samples", C.c_ulonglong),
+                ("correct", C.c_ulonglong * 128)]
 
 
 class FlavaConfig(C.Structure):
@@ -82,6 +89,7 @@ def _load():
     lib.mmu_gemm.argtypes = [i, vp, ll, i, vp, ll, i, i, i, i, i, C.POINTER(GemmEpilogue), vp]
     lib.mmu_mask_gather_tokens.argtypes = [vp, vp, i, i, i, i, vp, i, vp, i, vp]
     lib.mmu_struct_size.argtypes = [i]
+    lib.mmu_posthoc_scoring.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp]
     lib.mmu_cast_f32_to_bf16.argtypes = [vp, vp, C.c_size_t, vp]
     lib.mmu_layernorm_fwd.argtypes = [vp, vp, vp, vp, i, vp, vp, i, i, vp]
     lib.mmu_layernorm_bwd.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, i, vp, vp, vp, i, i, vp]

@@ -11,6 +11,7 @@ using namespace mmu;
 
 static_assert(sizeof(mmu_metric_accum) == sizeof(MetricAccum), "metric accumulator layout");
 static_assert(sizeof(mmu_flava_config) == sizeof(FlavaConfig), "config layout");
+static_assert(sizeof(mmu_posthoc_accum) == sizeof(PosthocAccum), "post-hoc accumulator layout");
 static_assert(sizeof(mmu_param_entry) == sizeof(ParamEntry), "param entry layout");
 static_assert(sizeof(mmu_flava_inputs) == sizeof(FlavaInputs), "inputs layout");
 
@@ -41,6 +42,7 @@ int mmu_struct_size(int which) {
     case 2: return static_cast<int>(sizeof(mmu_gemm_epilogue));
     case 3: return static_cast<int>(sizeof(mmu_metric_accum));
     case 4: return static_cast<int>(sizeof(mmu_param_entry));
+    case 5: return static_cast<int>(sizeof(mmu_posthoc_accum));
     default: return -1;
   }
 }
@@ -159,6 +161,13 @@ long long mmu_flava_workspace_bytes(const mmu_flava_config* cfg, int training) {
 }
 int mmu_flava_num_stages(const mmu_flava_config* cfg) {
   return cfg == nullptr ? MMU_ERR_ARG : flava_num_stages(cfg_of(cfg));
+}
+
+int mmu_posthoc_scoring(const float* logits, const long long* labels, int V, int B, int E, int C,
+                        int n_repeats, float* p_true_out, mmu_posthoc_accum* acc, void* stream) {
+  if (logits == nullptr || labels == nullptr || acc == nullptr) return MMU_ERR_ARG;
+  return posthoc_scoring(logits, labels, V, B, E, C, n_repeats, p_true_out,
+                         reinterpret_cast<PosthocAccum*>(acc), S(stream));
 }
 
 int mmu_flava_forward(const mmu_flava_config* cfg, const float* params, const mmu_flava_inputs* in,

@@ -98,6 +98,16 @@ int ce_uncertainty(const float* logits, const long long* labels, int label_strid
                    float* dlogits, int* pred_out, float* scores_out /*[N,4]*/, MetricAccum* acc,
                    cudaStream_t stream);
 
+// ---- post-hoc robustness scoring (notebooks/utils.py:22-34, food101_robustness.py:24-77)
+struct PosthocAccum {  // device memory; sums are all-reducible
+  double sx[2], sy[2], sxx[2], syy[2], sxy[2];  // [image, text] Pearson sufficient statistics
+  unsigned long long n_samples;
+  unsigned long long correct[128];               // head-mean-logit argmax == label, per variant
+};
+int posthoc_scoring(const float* logits /*(V,B,E,C)*/, const long long* labels /*(B)*/, int V, int B,
+                    int E, int C, int n_repeats, float* p_true_out /*(B,V) or null*/,
+                    PosthocAccum* acc, cudaStream_t stream);
+
 // ---- fused AdamW over the flat parameter buffer (train.py:196-202 hyper-parameters)
 int adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n, float lr,
                float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,

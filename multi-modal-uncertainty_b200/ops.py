@@ -186,3 +186,19 @@ def adamw_flat_step(p, g, m, v, step, lr, *, betas=(0.9, 0.98), eps=1e-9, weight
     check(lib.mmu_adamw_flat_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16), p.numel(), lr,
                                   betas[0], betas[1], eps, weight_decay, step, grad_scale,
                                   stream_ptr()), "mmu_adamw_flat_step")
+
+
+def posthoc_scoring(logits, labels, n_repeats, accum=None, want_p_true=False):
+    """Post-hoc robustness statistics from packed-variant logits (V, B, E, C); see
+    ``mmu_posthoc_scoring``.  Returns (accum uint8 tensor viewing ``mmu_posthoc_accum``, p_true
+    (B, V) or None)."""
+    _cuda(logits, labels)
+    V, B, E, Cn = logits.shape
+    if labels.dtype != torch.int64:
+        raise TypeError("labels must be int64")
+    if accum is None:
+        accum = torch.zeros(C.sizeof(_lib.PosthocAccum), dtype=torch.uint8, device=logits.device)
+    p_true = torch.empty(B, V, device=logits.device) if want_p_true else None
+    check(lib.mmu_posthoc_scoring(ptr(logits), ptr(labels), V, B, E, Cn, n_repeats, ptr(p_true),
+                                  ptr(accum), stream_ptr()), "mmu_posthoc_scoring")
+    return accum, p_true

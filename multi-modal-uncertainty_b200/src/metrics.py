@@ -78,3 +78,53 @@ class UncertaintyMeter:
                  acc_prob=100.0 * d["n_correct_prob"] / n, ece=ece,
                  h_pred=d["sum_h_pred"] / n, h_exp=d["sum_h_exp"] / n, mi=d["sum_mi"] / n)
         return d
+
+
+class PosthocMeter:
+    """Device-side accumulator of the notebooks' post-hoc robustness scores (reference
+    ``notebooks/utils.py:22-34``, ``notebooks/food101_robustness.py:24-77``): fed with the
+    packed-variant logits of each batch, it keeps the Pearson sufficient statistics and the
+    per-variant accuracy counts on the GPU; ``compute()`` reads 1.1 KB back."""
+
+    def __init__(self, device, n_repeats=20):
+        import ctypes as C
+        self.n_repeats = n_repeats
+        self.accum = torch.zeros(C.sizeof(_lib.PosthocAccum), dtype=torch.uint8, device=device)
+
+    def reset(self):
+        self.accum.zero_()
+
+    def update(self, logits_vbec, labels, want_p_true=False):
+        _, p_true = ops.posthoc_scoring(logits_vbec.contiguous(), labels.reshape(-1).contiguous(),
+                                        self.n_repeats, accum=self.accum, want_p_true=want_p_true)
+        return p_true
+
+    def all_reduce(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            words = self.accum.view(torch.int64)
+            dbl = words[:10].view(torch.float64).clone()
+            cnt = words[10:].clone()
+            dist.all_reduce(dbl, group=group)
+            dist.all_reduce(cnt, group=group)
+            words[:10] = dbl.view(torch.int64)
+            words[10:] = cnt
+
+    def compute(self):
+        import ctypes as C
+        raw = self.accum.cpu().numpy().tobytes()
+        a = _lib.PosthocAccum.from_buffer_copy(raw)
+        n = max(int(a.n_samples), 1)
+        out = {"n_samples": int(a.n_samples)}
+        for i, name in enumerate(("image", "text")):
+            cov = a.sxy[i] - a.sx[i] * a.sy[i] / n
+            vx = a.sxx[i] - a.sx[i] ** 2 / n
+            vy = a.syy[i] - a.sy[i] ** 2 / n
+            out["corr_" + name] = float(cov / np.sqrt(vx * vy)) if vx > 0 and vy > 0 else float("nan")
+        r = self.n_repeats
+        acc = np.array([a.correct[v] for v in range(3 + 2 * r)], dtype=np.float64) / n
+        out.update(acc_full=100 * acc[0], acc_image=100 * acc[1], acc_text=100 * acc[2],
+                   acc_image_control=float(acc[3:3 + r].mean()) if r else float("nan"),
+                   acc_text_control=float(acc[3 + r:].mean()) if r else float("nan"),
+                   acc_per_variant=acc)
+        return out

@@ -10,7 +10,7 @@ the token gather, the forward passes and the scoring run on the GPU.  Instead of
 import numpy as np
 import torch
 
-from .metrics import UncertaintyMeter
+from .metrics import PosthocMeter, UncertaintyMeter
 
 
 def input_sampling(l_img, l_txt, type="image"):
@@ -91,11 +91,14 @@ def forward_variants(model, img, txt, variants, ref_bug_compat=False):
 
 @torch.no_grad()
 def run_transformer_robustness(model, batches, device, n_repeats=20, ref_bug_compat=False,
-                               collect=True, variants_fn=None):
+                               collect=True, variants_fn=None, posthoc=False):
     """Sweep every batch through the variant schedule.  Returns (preds (S, V, K, C) numpy or
-    None, labels numpy, [per-variant metric dicts])."""
+    None, labels numpy, [per-variant metric dicts]); with ``posthoc=True`` a fourth element holds
+    the notebooks' scores (Pearson r of experimental vs control delta-p per modality, accuracy
+    table) accumulated on device, so ``collect=False`` runs need no (S, 43, K, C) dump at all."""
     model.eval()
     meters, preds, labels = None, [], []
+    scorer = PosthocMeter(device, n_repeats) if posthoc else None
     for (img, txt), y in batches:
         img, txt, y = img.to(device), txt.to(device), y.to(device).reshape(-1)
         if variants_fn is None:
@@ -109,13 +112,19 @@ def run_transformer_robustness(model, batches, device, n_repeats=20, ref_bug_com
         all_logits = forward_variants(model, img, txt, variants, ref_bug_compat)
         for logits, meter in zip(all_logits, meters):
             meter.update(logits, y)
+        if scorer is not None:
+            scorer.update(all_logits, y)
         if collect:
             preds.append(all_logits.transpose(0, 1).cpu())
         labels.append(y.cpu())
     for m in meters or []:
         m.all_reduce()
     P = torch.cat(preds).numpy() if collect and preds else None
-    return P, torch.cat(labels).numpy(), [m.compute() for m in meters or []]
+    out = (P, torch.cat(labels).numpy(), [m.compute() for m in meters or []])
+    if scorer is not None:
+        scorer.all_reduce()
+        out += (scorer.compute(),)
+    return out
 
 
 @torch.no_grad()

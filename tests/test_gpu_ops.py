@@ -202,3 +202,34 @@ def test_mask_gather(mmu):
     assert torch.equal(out.cpu(), ref)  # bit-exact masks / gather
     out = mmu.ops.mask_gather_tokens(src.cuda(), None, keep.cuda(), modality=1, dtype=torch.bfloat16)
     assert torch.equal(out.cpu(), (src * keep[:, 1].view(-1, 1, 1)).to(torch.bfloat16))
+
+
+def test_posthoc_scoring_matches_notebook_golden(mmu, golden):
+    """Device-side post-hoc scoring against the reference notebooks' own functions
+    (notebooks/utils.py softmax / get_correlation, food101_robustness.py
+    process_predictions_food101) frozen in tests/golden/notebook_scoring.pt."""
+    c = golden("notebook_scoring.pt")
+    preds, labels = c["preds"], c["labels"].long()          # (S, V, K, C)
+    S, V, K, Cn = preds.shape
+    n_rep = (V - 3) // 2
+    meter = mmu.metrics.PosthocMeter("cuda", n_rep)
+    pts = []
+    for lo in range(0, S, 16):                               # several batches: sums accumulate
+        lg = preds[lo:lo + 16].transpose(0, 1).contiguous().cuda()   # (V, B, K, C)
+        pts.append(meter.update(lg, labels[lo:lo + 16].cuda(), want_p_true=True).cpu())
+    pt = torch.cat(pts)
+    assert rel(pt[:, 0], c["ori"]) < 1e-5 and rel(pt[:, 1], c["image"]) < 1e-5
+    assert rel(pt[:, 2], c["text"]) < 1e-5
+    assert rel(pt[:, 3:3 + n_rep], c["image_corr"]) < 1e-5
+    assert rel(pt[:, 3 + n_rep:], c["text_corr"]) < 1e-5
+    out = meter.compute()
+    assert out["n_samples"] == S
+    assert abs(out["corr_image"] - c["corr_image"]) < 1e-3 * max(abs(c["corr_image"]), 1e-2)
+    assert abs(out["corr_text"] - c["corr_text"]) < 1e-3 * max(abs(c["corr_text"]), 1e-2)
+    assert out["acc_full"] == pytest.approx(c["acc_full"], abs=1e-9)   # integer counts: exact
+    from oracle import uncertainty
+    tab = uncertainty.acc_table(preds.numpy(), labels.numpy(), n_rep)
+    assert out["acc_image"] == pytest.approx(tab["image"], abs=1e-9)
+    assert out["acc_text"] == pytest.approx(tab["text"], abs=1e-9)
+    assert out["acc_image_control"] == pytest.approx(float(tab["image_control"].mean()), abs=1e-12)
+    assert out["acc_text_control"] == pytest.approx(float(tab["text_control"].mean()), abs=1e-12)

@@ -35,7 +35,8 @@ def test_struct_sizes_match_header(mmu):
     assert C.sizeof(mmu._lib.FlavaConfig) == 15 * 4
     # the ctypes mirrors against sizeof() as compiled into the library
     for which, klass in enumerate((mmu._lib.FlavaConfig, mmu._lib.FlavaInputs, mmu._lib.GemmEpilogue,
-                                   mmu._lib.MetricAccum, mmu._lib.ParamEntry)):
+                                   mmu._lib.MetricAccum, mmu._lib.ParamEntry,
+                                   mmu._lib.PosthocAccum)):
         assert mmu._lib.lib.mmu_struct_size(which) == C.sizeof(klass), klass.__name__
     assert C.sizeof(mmu._lib.ParamEntry) == 96 + 8 + 8 + 12 + 4  # padded to 8
     assert mmu._lib.ACC_OFF["conf_sum"] == 98
