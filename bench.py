@@ -5,15 +5,17 @@
 
 One STEP = one training step (data shaping, forward, CE over the 5 heads, backward, fused AdamW,
 `acc`) on a batch of B = 128 samples per GPU, followed by the robustness sweep of the same batch
-over 10 mask levels (token-subset gather, eval forward, fused uncertainty / ECE-histogram
+over 10 mask levels (token-subset gather, eval forward of every level -- packed along the token
+axis into one pass, all FLOPs of all levels executed --, fused uncertainty / ECE-histogram
 epilogue) -- BASELINE.json config[1] with config[2]'s per-batch sweep.  `value` = samples per
 second through that step (each sample is trained on once and swept over 10 levels), whole job
 over N GPUs (weak scaling: B per GPU fixed).  Rank 0 prints ONE JSON line.
 
 * `value`   : inputs resident in HBM when the timed region starts (CUDA events, max over ranks)
-* `e2e`     : same step through the public API (`Model_.train_step`, `robustness` sweep,
-              `UncertaintyMeter.compute`) from pinned HOST buffers: H2D of every batch and the
-              D2H reads of loss / acc / metric accumulators are inside the timed region
+* `e2e`     : same step through the public API from pinned HOST buffers: `DevicePrefetcher`
+              (H2D of batch i+1 on a side stream while step i runs) -> `Model_.train_step` ->
+              `model.forward_variants` + `UncertaintyMeter` -> D2H read of loss / acc at the end
+              of the step; every batch is copied host->device inside the timed region
 * `roofline`: dominant kernel = gemm_bf16_tcgen05_kernel (tensor bound); achieved = algorithmic
               FLOPs of the step's GEMM launches / their CUDA-event time, measured live here
 * `cpu_baseline` / `--impl reference`: the oracle port (the reference is pure Python + torch
@@ -69,26 +71,45 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.window = [None, None]  # host-clock bounds of the timed region
 
     def start(self):
+        """Starts sampling (every 20 ms); call mark_begin()/mark_end() around the timed region.
+        The sampler is started before the warm-up so the process is already streaming when the
+        short timed region begins; only samples taken inside the region are reported (all
+        under-load samples if the region was too short to catch three)."""
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.window[0] = time.time()
+
+    def mark_end(self):
+        self.window[1] = time.time()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.thread.join(timeout=2)
+        t0, t1 = self.window
+        inside = [r[1:] for r in self.rows if t0 is not None and t1 is not None and t0 <= r[0] <= t1]
+        scope = "timed region"
+        if len(inside) < 3:
+            inside = [r[1:] for r in self.rows if t0 is None or r[0] >= t0 - 2.0]
+            scope = "warm-up + timed region (region shorter than 3 samples)"
+        self.rows = inside
+        self.scope = scope
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
         reasons = set()
         for r in self.rows:
@@ -99,7 +120,7 @@ class ClockSampler:
                         reasons.add(name)
         smax = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": self.scope}
 
 
 def make_host_batches(n, B, seed, pin):
@@ -207,13 +228,15 @@ def run_gpu(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if sampler:
-            sampler.start()
+            sampler.mark_begin()
         n0 = mmu._lib.lib.mmu_launch_count()
         e0.record()
         for i in range(steps):
             fn(i)
         e1.record()
         barrier()
+        if sampler:
+            sampler.mark_end()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if sampler else None
         launches = mmu._lib.lib.mmu_launch_count() - n0
@@ -224,9 +247,12 @@ def run_gpu(args):
         return ms, launches, clocks
 
     model.train()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for i in range(args.warmup):
         step_resident(i)
-    ms, launches, clocks = timed(step_resident, args.steps, ClockSampler(local) if rank == 0 else None)
+    ms, launches, clocks = timed(step_resident, args.steps, sampler)
     meter.all_reduce()
     summary = meter.compute()
     if args.profile:
@@ -263,7 +289,7 @@ def run_gpu(args):
         dist.barrier()
 
     if rank == 0:
-        h2d = sum(t.numel() * t.element_size() for t in (host[0][0][0], host[0][0][1], host[0][1]))
+        h2d = world * sum(t.numel() * t.element_size() for t in (host[0][0][0], host[0][0][1], host[0][1]))
         line = {
             "metric": "train+robustness-eval samples/sec", "value": round(value, 2),
             "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -278,7 +304,7 @@ def run_gpu(args):
                        "parallelism": f"dp{world}", "dead_tokens": "computed (as written)",
                        "l2": "working set ~6 GB/step >> 126 MB L2, inputs rotate over 4 batches"},
             "e2e": {"value": round(e2e_value, 2), "unit": "samples/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,  # loss + acc, 4 B each
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * world,  # loss + acc, 4 B each, per rank
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -455,9 +481,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rooflines-only", action="store_true",
+                    help="only the per-kernel roofline legs (for ncu --metrics dram__bytes_* captures)")
     ap.add_argument("--profile", action="store_true",
                     help="skip the e2e / roofline / CPU legs (short run for ncu)")
     args = ap.parse_args()
@@ -466,6 +494,12 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+        if args.rooflines_only:
+            import mmu_b200 as mmu
+            torch.cuda.set_device(0)
+            roof, hbm = measure_rooflines(mmu, torch.device("cuda", 0))
+            print(json.dumps({"roofline": roof, "hbm_kernels": hbm}))
+            return
         run_gpu(args)
 
 

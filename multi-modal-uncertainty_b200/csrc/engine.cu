@@ -262,14 +262,28 @@ GemmEpilogue epi(int mode, void* out, int out_bf16, long long ld_out, const floa
   return e;
 }
 
+// Split-K factor of a weight-gradient GEMM (Mg x Ng output, K = tokens): the few output tiles
+// cannot fill the machine, so K is split until the tile count lands just under a whole number of
+// waves (CTA pairs: 256x256 tiles over 74 clusters; small Mg: 128x256 tiles over 148 CTAs).
 int wgrad_splits(int Mg, int Ng, int K) {
-  const int tiles = ((Mg + 127) / 128) * ((Ng + 255) / 256);
-  int s = (sm_count() + tiles - 1) / tiles;
+  const bool pair = Mg >= 512;
+  const int tiles = ((Mg + (pair ? 255 : 127)) / (pair ? 256 : 128)) * ((Ng + 255) / 256);
+  const int units = pair ? sm_count() / 2 : sm_count();
   const int kb = (K + 63) / 64;
-  if (s > kb / 4) s = kb / 4;
-  if (s < 1) s = 1;
-  if (s > 64) s = 64;
-  return s;
+  int smax = kb / 4;
+  if (smax > 16) smax = 16;
+  if (smax < 1) smax = 1;
+  int best_s = 1;
+  double best = 0.0;
+  for (int sp = 1; sp <= smax; ++sp) {
+    const int t = tiles * sp;
+    const double eff = static_cast<double>(t) / (static_cast<double>((t + units - 1) / units) * units);
+    if (eff > best + 0.02) {  // prefer the smaller factor on near-ties: fewer atomic passes
+      best = eff;
+      best_s = sp;
+    }
+  }
+  return best_s;
 }
 
 #define MMU_TRY(x)            \

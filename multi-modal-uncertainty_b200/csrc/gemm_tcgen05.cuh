@@ -139,7 +139,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   const int kb_total = (p.K + BK - 1) / BK;
   const int kb_per = (kb_total + p.splits - 1) / p.splits;
   const int nbatch = p.batch > 0 ? p.batch : 1;
-  const int num_tiles = nbatch * m_tiles * n_tiles * p.splits;
+  const int mn_total = nbatch * m_tiles * n_tiles;
+  const int num_tiles = mn_total * p.splits;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tma_a);
@@ -181,8 +182,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int split = tile % p.splits;
-        const int mnb = tile / p.splits;
+        const int split = tile / mn_total;  // K-split outermost: concurrent CTAs share operand panels
+        const int mnb = tile % mn_total;
         const int g = mnb / (m_tiles * n_tiles);
         const int mn = mnb % (m_tiles * n_tiles);
         const int m0 = (mn / n_tiles) * G::BM_TILE + rank * BM;   // this CTA's 128 rows of A
@@ -270,7 +271,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int split = tile % p.splits;
+        const int split = tile / mn_total;  // K-split outermost: concurrent CTAs share operand panels
         const int kb0 = split * kb_per;
         const int kb1 = min(kb_total, kb0 + kb_per);
         ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -326,7 +327,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       }
     };
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int mnb = tile / p.splits;
+      const int mnb = tile % mn_total;
       const int g = mnb / (m_tiles * n_tiles);
       const int mn = mnb % (m_tiles * n_tiles);
       const int nt0 = (mn % n_tiles) * BN;
