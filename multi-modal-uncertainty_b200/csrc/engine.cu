@@ -409,8 +409,16 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
   if (c.cls_token) MMU_TRY(cls_fill(params + lay.cls, w.mm_x, c.B, s.L, D, c.E, stream));
 
   float* x = training && c.n_layers > 0 ? w.layer[0].x0 : w.x_out[0];
-  MMU_TRY(layernorm_fwd(w.mm_x, params + lay.lnpre_w, params + lay.lnpre_b, x, DT_F32, w.stats_pre,
-                        w.stats_pre + M, M, D, stream));
+  if (c.n_layers > 0) {  // ln_pre chained with the first block's ln_1 in one pass over the rows
+    const LayerParams& p0 = lay.layer[0];
+    const LayerWs& l0 = w.layer[0];
+    MMU_TRY(layernorm2_fwd(w.mm_x, params + lay.lnpre_w, params + lay.lnpre_b, x, w.stats_pre,
+                           w.stats_pre + M, params + p0.ln1_w, params + p0.ln1_b, l0.h1, dt,
+                           l0.stats1, l0.stats1 + M, M, D, stream));
+  } else {
+    MMU_TRY(layernorm_fwd(w.mm_x, params + lay.lnpre_w, params + lay.lnpre_b, x, DT_F32, w.stats_pre,
+                          w.stats_pre + M, M, D, stream));
+  }
 
   // ---- transformer blocks.  The projections that close a residual branch (out_proj, c_proj)
   //      store the branch output y in the activation dtype; the add x + y is fused into the
@@ -421,10 +429,8 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
     float* x_next;
     if (training) x_next = (i + 1 < c.n_layers) ? w.layer[i + 1].x0 : w.x_final;
     else x_next = w.x_out[(i + 1) & 1];
-    if (i == 0) {
-      MMU_TRY(layernorm_fwd(x, params + p.ln1_w, params + p.ln1_b, l.h1, dt, l.stats1, l.stats1 + M,
-                            M, D, stream));
-    }  // else: h1 / stats1 of this block were produced by the previous block's closing add+LN
+    // h1 / stats1 of this block were produced by the stem (block 0) or by the previous block's
+    // closing add+LN
     MMU_TRY(gemm(l.h1, D, 0, W(p.in_w), D, 0, M, 3 * D, D,
                  epi(EPI_STORE, l.qkv, bf, 3 * D, params + p.in_b)));
     MMU_TRY(attention_fwd(l.qkv, l.o, l.lse, l.probs, w.scores, dt, c.B, s.L, D, c.n_head, stream));

@@ -20,6 +20,10 @@ int cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t stream)
 // ---- LayerNorm (eps 1e-5, biased variance, src/model.py:174-180, :252-253)
 int layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,
                   float* mean, float* rstd, int M, int D, cudaStream_t stream);
+// y1 (fp32) = LN(x; g1, b1); y2 (y2_dtype) = LN(y1; g2, b2): ln_pre chained with the first ln_1.
+int layernorm2_fwd(const float* x, const float* g1, const float* b1, float* y1, float* mean1,
+                   float* rstd1, const float* g2, const float* b2, void* y2, int y2_dtype,
+                   float* mean2, float* rstd2, int M, int D, cudaStream_t stream);
 // x_out = x_in + y (y and h in `dtype`); h = LN(x_out) unless gamma == nullptr (sum only).
 int add_layernorm_fwd(const float* x_in, const void* y, float* x_out, const float* gamma,
                       const float* beta, void* h, int dtype, float* mean, float* rstd, int M, int D,

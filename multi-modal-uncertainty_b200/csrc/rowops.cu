@@ -163,6 +163,63 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 }
 
 
+// Two chained LayerNorms in one pass over the row: y1 = LN1(x) (fp32: the residual stream after
+// ln_pre), y2 = LN2(y1) (the first block's ln_1 output, activation dtype).  Saves re-reading y1.
+template <int NV, typename TO>
+__global__ void __launch_bounds__(THREADS)
+layernorm2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g1,
+                      const float* __restrict__ b1, float* __restrict__ y1,
+                      float* __restrict__ mean1, float* __restrict__ rstd1,
+                      const float* __restrict__ g2, const float* __restrict__ b2,
+                      TO* __restrict__ y2, float* __restrict__ mean2, float* __restrict__ rstd2, int M,
+                      int D) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D >> 2;
+  for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
+    RowRegs<NV> r;
+    r.load(x + static_cast<size_t>(row) * D, nvec, lane);
+    float mean, rstd;
+    row_stats<NV>(r, nvec, lane, D, mean, rstd);
+    if (lane == 0) {
+      mean1[row] = mean;
+      rstd1[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 g = *reinterpret_cast<const float4*>(g1 + 4 * c);
+        const float4 b = *reinterpret_cast<const float4*>(b1 + 4 * c);
+        float4& v = r.v[i];
+        v.x = (v.x - mean) * rstd * g.x + b.x;
+        v.y = (v.y - mean) * rstd * g.y + b.y;
+        v.z = (v.z - mean) * rstd * g.z + b.z;
+        v.w = (v.w - mean) * rstd * g.w + b.w;
+        *reinterpret_cast<float4*>(y1 + static_cast<size_t>(row) * D + 4 * c) = v;
+      }
+    }
+    row_stats<NV>(r, nvec, lane, D, mean, rstd);
+    if (lane == 0) {
+      mean2[row] = mean;
+      rstd2[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 g = *reinterpret_cast<const float4*>(g2 + 4 * c);
+        const float4 b = *reinterpret_cast<const float4*>(b2 + 4 * c);
+        float4 o;
+        o.x = (r.v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (r.v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (r.v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (r.v[i].w - mean) * rstd * g.w + b.w;
+        Vec4<TO>::st(y2 + static_cast<size_t>(row) * D + 4 * c, o);
+      }
+    }
+  }
+}
+
 // x_out = x_in + y (branch output of the preceding projection GEMM, stored in the activation
 // dtype); h = LayerNorm(x_out).  Fusing the residual add here keeps the GEMM epilogues free of the
 // fp32 residual-stream traffic (a streaming row kernel moves those bytes at ~HBM peak; a GEMM
@@ -325,15 +382,25 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x,
   if (dcolsum != nullptr) block_colreduce_n<NV, LNB_WARPS>(acc_c, red, dcolsum, nvec, D);
 }
 
+// Column sums (bias gradients).  Each thread owns 4 columns and walks a slab of rows with 8
+// independent 8/16-byte loads in flight (the op is a pure streaming read: 2 B/elem in bf16).
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int M, int N,
-                              int rows_per_block) {
+__global__ void __launch_bounds__(128)
+colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int M, int N, int rows_per_block) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= N) return;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(M, r0 + rows_per_block);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = r0; r < r1; ++r) {
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = Vec4<T>::ld(x + static_cast<size_t>(r + u) * N + c);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+  }
+  for (; r < r1; ++r) {
     const float4 v = Vec4<T>::ld(x + static_cast<size_t>(r) * N + c);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
@@ -728,6 +795,26 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y
   return 0;
 }
 
+int layernorm2_fwd(const float* x, const float* g1, const float* b1, float* y1, float* mean1,
+                   float* rstd1, const float* g2, const float* b2, void* y2, int y2_dtype,
+                   float* mean2, float* rstd2, int M, int D, cudaStream_t stream) {
+  const int nv = nv_for(D);
+  if (nv < 0) return MMU_ERR_SHAPE;
+  if (M <= 0) return 0;
+  const int grid = grid_for(M, WARPS);
+  if (y2_dtype == DT_BF16) {
+    MMU_NV_DISPATCH(nv, (layernorm2_fwd_kernel<NV, __nv_bfloat16><<<grid, THREADS, 0, stream>>>(
+                            x, g1, b1, y1, mean1, rstd1, g2, b2, static_cast<__nv_bfloat16*>(y2),
+                            mean2, rstd2, M, D)));
+  } else {
+    MMU_NV_DISPATCH(nv, (layernorm2_fwd_kernel<NV, float><<<grid, THREADS, 0, stream>>>(
+                            x, g1, b1, y1, mean1, rstd1, g2, b2, static_cast<float*>(y2), mean2,
+                            rstd2, M, D)));
+  }
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
 int add_layernorm_fwd(const float* x_in, const void* y, float* x_out, const float* gamma,
                       const float* beta, void* h, int dtype, float* mean, float* rstd, int M, int D,
                       cudaStream_t stream) {
@@ -785,7 +872,7 @@ int colsum_accumulate(const void* x, int dtype, float* out, int M, int N, cudaSt
   if (M <= 0) return 0;
   const int threads = 128;
   const int gx = (N / 4 + threads - 1) / threads;
-  int gy = (sm_count() * 4 + gx - 1) / gx;
+  int gy = (sm_count() * 8 + gx - 1) / gx;
   if (gy > M) gy = M;
   const int rpb = (M + gy - 1) / gy;
   gy = (M + rpb - 1) / rpb;
