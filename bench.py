@@ -470,8 +470,12 @@ def run_reference(args):
             "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": cpu["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1] train step + configs[2] 10-level mask sweep per batch",
-                       "per_gpu_batch": CPU_SAMPLE_B, "note": "CPU arm: rank 0 only"},
+            "config": {"workload": "configs[1] Food-101-shaped FLAVA late fusion, 5 heads, 101 classes"
+                                   " + configs[2] per-batch 10-level mask sweep",
+                       "per_gpu_batch": CFG["B"], "sample_batch": CPU_SAMPLE_B, "l_img": CFG["l_img"],
+                       "l_txt": CFG["l_txt"], "D": CFG["D"], "layers": CFG["layers"],
+                       "heads": CFG["heads"], "E": CFG["E"], "C": CFG["C"],
+                       "mask_levels": CFG["levels"], "note": "CPU arm: rank 0 only, bounded sample"},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
