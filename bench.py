@@ -203,18 +203,25 @@ def run_gpu(args):
 
     def step_e2e(batch):
         (img, txt), y = batch          # device tensors from the prefetcher (copied this step)
-        loss, info, _ = trainer.train_step((img, txt), y, sync=False)
+        loss, info, _ = trainer.train_step((img, txt), y, sync=False)   # device scalars
         sweep(img, txt, y, level_variants(mmu, 0))
-        # D2H read of the step's results (loss, acc) once everything of the step is enqueued
-        return float(loss), [float(v) for v in info]
+        return loss, info
 
     def run_e2e(steps):
         """Public-API loop: pinned host batches -> DevicePrefetcher (H2D of batch i+1 on a side
-        stream while step i runs) -> Model_.train_step -> robustness sweep.  Every step's batch is
-        copied host->device inside the timed region."""
+        stream while step i runs) -> Model_.train_step -> packed robustness sweep.  Every step's
+        batch is copied host->device and every step's loss / acc is read back device->host inside
+        the timed region; the read of step i happens after step i+1 has been enqueued (one-step
+        lag, the way an asynchronous logger consumes them) so the host never drains the queue."""
         prefetcher.loader = [host[i % nb] for i in range(steps)]
+        pending, history = None, []
         for batch in prefetcher:
-            step_e2e(batch)
+            cur = step_e2e(batch)
+            if pending is not None:
+                history.append((float(pending[0]), [float(v) for v in pending[1]]))
+            pending = cur
+        history.append((float(pending[0]), [float(v) for v in pending[1]]))
+        return history
 
     prefetcher = mmu.dataset.DevicePrefetcher([], dev)  # its two device slots persist across runs
 

@@ -150,13 +150,25 @@ int launch_kernel(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const 
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = NCTA;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  // programmatic dependent launch: the kernel's prologue may overlap the previous kernel's tail
+  // (it calls griddepcontrol.wait before it touches global memory)
+  static const bool pdl = getenv("MMU_GEMM_NO_PDL") == nullptr;  // A/B switch
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (NCTA == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = NCTA;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = NCTA == 2 ? 1 : 0;
+  cfg.numAttrs = na;
   const cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, ta, tb, c0, c1, p, e);
   if (err != cudaSuccess) {
     fprintf(stderr, "mmu: gemm launch failed: %s\n", cudaGetErrorString(err));

@@ -128,6 +128,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     __trap();
   }
 
+  ptx::pdl_trigger();  // the next kernel may start its prologue on SMs this grid has left
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = NCTA == 2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;  // CTA within the pair
@@ -175,6 +176,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the tail of
+  // the previous kernel; its results are needed from here on.
+  ptx::pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer

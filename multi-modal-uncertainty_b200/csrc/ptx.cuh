@@ -108,6 +108,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// ---- programmatic dependent launch: a kernel launched with the programmatic-stream-serialization
+//      attribute may become resident while its predecessor drains; it must not touch memory the
+//      predecessor writes before pdl_wait(); pdl_trigger() lets the NEXT kernel start its prologue.
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- CTA-pair (cta_group::2) variants: the transaction bytes land on the barrier of the pair's
 //      LEADER CTA (bit 24 of a shared::cluster address selects the CTA of the pair; clearing it
 //      addresses the even CTA's copy of the same shared-memory offset).

@@ -9,6 +9,7 @@
 
 #include "common.h"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace mmu {
 
@@ -75,6 +76,7 @@ template <typename T>
 __global__ void cast_gather_kernel(const float* __restrict__ src, T* __restrict__ dst, int B,
                                    int l_src, int d, const int* __restrict__ idx, int n_sel,
                                    const int* __restrict__ keep, int modality) {
+  ptx::pdl_trigger();  // a following tensor-core GEMM may start its prologue early
   const int dv = d >> 2;
   const size_t total = static_cast<size_t>(B) * n_sel * dv;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(THREADS)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, TO* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int M, int D) {
+  ptx::pdl_trigger();  // a following tensor-core GEMM may start its prologue early
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = D >> 2;
   for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
@@ -173,6 +176,7 @@ layernorm2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g1,
                       const float* __restrict__ g2, const float* __restrict__ b2,
                       TO* __restrict__ y2, float* __restrict__ mean2, float* __restrict__ rstd2, int M,
                       int D) {
+  ptx::pdl_trigger();  // a following tensor-core GEMM may start its prologue early
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = D >> 2;
   for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
@@ -230,6 +234,7 @@ add_layernorm_fwd_kernel(const float* __restrict__ x_in, const TY* __restrict__ 
                          float* __restrict__ x_out, const float* __restrict__ gamma,
                          const float* __restrict__ beta, TO* __restrict__ h,
                          float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D) {
+  ptx::pdl_trigger();  // a following tensor-core GEMM may start its prologue early
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = D >> 2;
   for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
@@ -327,6 +332,7 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x,
                      const float* __restrict__ gamma, float* __restrict__ dx, int accumulate,
                      TLP* __restrict__ dx_lp, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ dcolsum, int M, int D) {
+  ptx::pdl_trigger();  // a following tensor-core GEMM may start its prologue early
   extern __shared__ float red[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = D >> 2;

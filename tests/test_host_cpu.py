@@ -254,6 +254,16 @@ def _gloo_worker(rank, world, port, out_dir):
     p = torch.full((8,), float(rank))
     par.broadcast_flat(p, 0)
     assert float(p.abs().sum()) == 0.0
+    # post-hoc scoring accumulator: Pearson sums (doubles) and per-variant counts (uint64) merge
+    ph = mmu_b200.metrics.PosthocMeter("cpu", n_repeats=2)
+    words = ph.accum.view(torch.int64)
+    words[:10].view(torch.float64)[:] = torch.arange(10, dtype=torch.float64) + rank
+    words[10] = 50 * (rank + 1)          # n_samples
+    words[11 + 3] = 7 + rank             # correct[3]
+    ph.all_reduce()
+    assert torch.equal(words[:10].view(torch.float64), 2 * torch.arange(10, dtype=torch.float64) + 1)
+    assert int(words[10]) == 150 and int(words[11 + 3]) == 15
+    assert ph.compute()["n_samples"] == 150
     # sample sharding: contiguous, disjoint, covering
     b, e = par.shard_range(1000003, rank, world)
     t = torch.tensor([b, e])
