@@ -63,6 +63,15 @@ def peaks():
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
 
 
+def gemm_traffic():
+    """Average dram__bytes_read+write per GEMM launch from the committed ncu capture (or None)."""
+    path = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    try:
+        return json.load(open(path))["avg_dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -380,8 +389,10 @@ def measure_rooflines(mmu, dev):
             "peak_burst": pk["tensor_burst"], "frac_of_burst": round(tf / pk["tensor_burst"], 3),
             "peak_source": pk["source"] + " (sustained cuBLAS bf16; kernel timed inside a long loop)",
             "launches_timed": int(n_launch // reps), "avg_launch_us": round(ms * 1e3 / (n_launch / reps), 1),
-            "flops_per_launch_avg": flops_layer / (n_launch / reps), "traffic": None,
-            "note": "12 GEMM launches of one transformer block's fwd+bwd (M=30336), operands > L2"}
+            "flops_per_launch_avg": flops_layer / (n_launch / reps), "traffic": gemm_traffic(),
+            "note": "12 GEMM launches of one transformer block's fwd+bwd (M=30336), operands > L2; "
+                    "traffic = average DRAM bytes per launch from the committed ncu capture "
+                    "profiles/r01_gemm_traffic.json"}
 
     # ---- HBM-bound kernels
     hbm = []
