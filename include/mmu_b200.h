@@ -101,6 +101,12 @@ MMU_API int mmu_gemm(int dtype, const void* A, long long lda, int a_mn_major, co
 MMU_API int mmu_mask_gather_tokens(const float* src, void* dst, int dst_dtype, int B, int l_src, int d,
                            const int* idx, int n_sel, const int* keep, int modality, void* stream);
 
+/* Ragged batch assembly on device: replaces torch pad_sequence(batch_first=True, padding_value=0)
+ * in collate_fn_flava (src/dataset.py:216-226).  packed: fp32 [offsets[B], d] rows of the batch's
+ * samples back to back; offsets: int32[B+1] (device); out: fp32 (B, max_l, d), tails zero-filled. */
+MMU_API int mmu_ragged_pad(const float* packed, const int* offsets, float* out, int B, int max_l, int d,
+                   void* stream);
+
 /* bf16 copy of a flat fp32 buffer (the GEMM-operand shadow of the parameters); n elements. */
 MMU_API int mmu_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
 

@@ -20,7 +20,7 @@ EXPORTS = [
     "mmu_heads_uncertainty_epilogue", "mmu_adamw_flat_step", "mmu_flava_param_count",
     "mmu_flava_param_table", "mmu_flava_workspace_bytes", "mmu_flava_num_stages",
     "mmu_flava_forward", "mmu_flava_backward", "mmu_cast_f32_to_bf16", "mmu_struct_size",
-    "mmu_posthoc_scoring",
+    "mmu_posthoc_scoring", "mmu_ragged_pad",
 ]
 
 
@@ -89,6 +89,7 @@ def _load():
     lib.mmu_gemm.argtypes = [i, vp, ll, i, vp, ll, i, i, i, i, i, C.POINTER(GemmEpilogue), vp]
     lib.mmu_mask_gather_tokens.argtypes = [vp, vp, i, i, i, i, vp, i, vp, i, vp]
     lib.mmu_struct_size.argtypes = [i]
+    lib.mmu_ragged_pad.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.mmu_posthoc_scoring.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp]
     lib.mmu_cast_f32_to_bf16.argtypes = [vp, vp, C.c_size_t, vp]
     lib.mmu_layernorm_fwd.argtypes = [vp, vp, vp, vp, i, vp, vp, i, i, vp]

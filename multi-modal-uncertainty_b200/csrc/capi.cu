@@ -94,6 +94,12 @@ int mmu_mask_gather_tokens(const float* src, void* dst, int dst_dtype, int B, in
   return cast_gather(src, dst, dst_dtype, B, l_src, d, idx, n_sel, keep, modality, S(stream));
 }
 
+int mmu_ragged_pad(const float* packed, const int* offsets, float* out, int B, int max_l, int d,
+                   void* stream) {
+  if (packed == nullptr || offsets == nullptr || out == nullptr) return MMU_ERR_ARG;
+  return ragged_pad(packed, offsets, out, B, max_l, d, S(stream));
+}
+
 int mmu_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream) {
   if (src == nullptr || dst == nullptr) return MMU_ERR_ARG;
   return cast_f32_to_bf16(src, dst, n, S(stream));

@@ -16,6 +16,9 @@ enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
 int cast_gather(const float* src, void* dst, int dst_dtype, int B, int l_src, int d, const int* idx,
                 int n_sel, const int* keep, int modality, cudaStream_t stream);
 int cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t stream);
+// packed ragged rows + int32 offsets[B+1] -> zero-padded (B, max_l, d) (src/dataset.py:216-226)
+int ragged_pad(const float* packed, const int* offsets, float* out, int B, int max_l, int d,
+               cudaStream_t stream);
 
 // ---- LayerNorm (eps 1e-5, biased variance, src/model.py:174-180, :252-253)
 int layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_dtype,

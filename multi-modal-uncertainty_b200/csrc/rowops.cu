@@ -768,6 +768,35 @@ int cast_gather(const float* src, void* dst, int dst_dtype, int B, int l_src, in
   return 0;
 }
 
+// Ragged -> padded: packed rows [offsets[b], offsets[b+1]) of sample b land at out[b, 0..len),
+// the tail of every sample is zero-filled (torch pad_sequence(batch_first=True, padding_value=0)).
+__global__ void ragged_pad_kernel(const float* __restrict__ packed, const int* __restrict__ offsets,
+                                  float* __restrict__ out, int B, int max_l, int d) {
+  const int dv = d >> 2;
+  const size_t total = static_cast<size_t>(B) * max_l * dv;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % dv);
+    const size_t row = i / dv;
+    const int l = static_cast<int>(row % max_l);
+    const int b = static_cast<int>(row / max_l);
+    const int o0 = offsets[b], len = offsets[b + 1] - o0;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l < len) v = *reinterpret_cast<const float4*>(packed + (static_cast<size_t>(o0) + l) * d + 4 * c);
+    *reinterpret_cast<float4*>(out + row * d + 4 * c) = v;
+  }
+}
+
+int ragged_pad(const float* packed, const int* offsets, float* out, int B, int max_l, int d,
+               cudaStream_t stream) {
+  if (d % 4 != 0) return MMU_ERR_SHAPE;
+  if (B <= 0 || max_l <= 0) return 0;
+  const size_t total = static_cast<size_t>(B) * max_l * (d / 4);
+  ragged_pad_kernel<<<grid_for(total, 256), 256, 0, stream>>>(packed, offsets, out, B, max_l, d);
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
 int cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t stream) {
   if (n % 4 != 0) return MMU_ERR_SHAPE;
   return cast_gather(src, dst, DT_BF16, 1, static_cast<int>(n / 4), 4, nullptr,

@@ -202,3 +202,16 @@ def posthoc_scoring(logits, labels, n_repeats, accum=None, want_p_true=False):
     check(lib.mmu_posthoc_scoring(ptr(logits), ptr(labels), V, B, E, Cn, n_repeats, ptr(p_true),
                                   ptr(accum), stream_ptr()), "mmu_posthoc_scoring")
     return accum, p_true
+
+
+def ragged_pad(packed, offsets, max_len):
+    """Zero-padded (B, max_len, d) batch from packed rows (sum_len, d) + int32 offsets (B+1,):
+    the device twin of ``pad_sequence(batch_first=True)`` (reference src/dataset.py:216-226)."""
+    _cuda(packed, offsets)
+    if offsets.dtype != torch.int32 or packed.dtype != torch.float32:
+        raise TypeError("packed must be fp32 and offsets int32")
+    B = offsets.numel() - 1
+    out = torch.empty(B, max_len, packed.shape[1], device=packed.device, dtype=torch.float32)
+    check(lib.mmu_ragged_pad(ptr(packed), ptr(offsets), ptr(out), B, max_len, packed.shape[1],
+                             stream_ptr()), "mmu_ragged_pad")
+    return out

@@ -103,6 +103,93 @@ def get_synthetic_flava(batch_size, n_train, n_val, n_test, seed=42, shuffle=Tru
     return mk(n_train, seed, shuffle), mk(n_val, seed + 1, False), mk(n_test, seed + 2, False)
 
 
+# ------------------------------------------------------------------ packed embedding store
+def pack_flava_encodings(samples, out_dir):
+    """Write an iterable of ``(image_embeddings (l_img_i, d), text_embeddings (l_txt_i, d), label)``
+    -- what ``data/encoding_with_flava.py:38-41`` saves as one ``.img`` + one ``.text`` file per
+    sample -- as ONE packed store: ``image.f32`` / ``text.f32`` (rows back to back),
+    ``image_offsets.npy`` / ``text_offsets.npy`` (int64, N+1) and ``labels.npy``.  Replaces two
+    ``torch.load`` calls per sample (reference src/dataset.py:206-213) by two memory-mapped slices."""
+    import os
+    import numpy as np
+    os.makedirs(out_dir, exist_ok=True)
+    offs = {"image": [0], "text": [0]}
+    labels, dim = [], None
+    with open(os.path.join(out_dir, "image.f32"), "wb") as fi, \
+            open(os.path.join(out_dir, "text.f32"), "wb") as ft:
+        for img, txt, label in samples:
+            img, txt = img.reshape(-1, img.shape[-1]), txt.reshape(-1, txt.shape[-1])
+            dim = dim or img.shape[-1]
+            assert img.shape[-1] == dim and txt.shape[-1] == dim
+            fi.write(img.to(torch.float32).contiguous().numpy().tobytes())
+            ft.write(txt.to(torch.float32).contiguous().numpy().tobytes())
+            offs["image"].append(offs["image"][-1] + img.shape[0])
+            offs["text"].append(offs["text"][-1] + txt.shape[0])
+            labels.append(int(label))
+    np.save(os.path.join(out_dir, "image_offsets.npy"), np.asarray(offs["image"], dtype=np.int64))
+    np.save(os.path.join(out_dir, "text_offsets.npy"), np.asarray(offs["text"], dtype=np.int64))
+    np.save(os.path.join(out_dir, "labels.npy"), np.asarray(labels, dtype=np.int64))
+    np.save(os.path.join(out_dir, "dim.npy"), np.asarray([dim], dtype=np.int64))
+
+
+class PackedFlavaDataset(Dataset):
+    """Reader of :func:`pack_flava_encodings` stores with the item protocol of the reference's
+    ``FlavaEncodedDataset`` (src/dataset.py:196-213): ``(image (l_img, d), text (l_txt_i, d),
+    LongTensor([label]))``, served as views of two memory maps."""
+
+    def __init__(self, store_dir):
+        import os
+        import numpy as np
+        self.dim = int(np.load(os.path.join(store_dir, "dim.npy"))[0])
+        self.off = {k: np.load(os.path.join(store_dir, k + "_offsets.npy")) for k in ("image", "text")}
+        self.labels = np.load(os.path.join(store_dir, "labels.npy"))
+        self.mm = {k: np.memmap(os.path.join(store_dir, k + ".f32"), dtype=np.float32, mode="r",
+                                shape=(int(self.off[k][-1]), self.dim)) for k in ("image", "text")}
+
+    def __len__(self):
+        return len(self.labels)
+
+    def rows(self, key, idx):
+        return self.mm[key][int(self.off[key][idx]):int(self.off[key][idx + 1])]
+
+    def __getitem__(self, idx):
+        import numpy as np
+        return (torch.from_numpy(np.array(self.rows("image", idx))),
+                torch.from_numpy(np.array(self.rows("text", idx))),
+                torch.LongTensor([int(self.labels[idx])]))
+
+
+class RaggedCollator:
+    """``collate_fn`` for :class:`PackedFlavaDataset` index batches: instead of padding on the
+    host (reference ``collate_fn_flava``, src/dataset.py:216-226) it concatenates the samples'
+    rows into one pinned buffer per modality and lets the GPU scatter them into the zero-padded
+    (B, max_len, d) batch (``mmu_ragged_pad``) -- the host never writes a padding byte and the
+    H2D copy moves only real tokens.  Use with ``DataLoader(range(len(ds)), collate_fn=...)``."""
+
+    def __init__(self, dataset, device, pin=True):
+        self.ds, self.device, self.pin = dataset, torch.device(device), pin
+
+    def _modality(self, key, idxs):
+        import numpy as np
+        lens = [int(self.ds.off[key][i + 1] - self.ds.off[key][i]) for i in idxs]
+        host = torch.empty(sum(lens), self.ds.dim, dtype=torch.float32, pin_memory=self.pin)
+        o = 0
+        for i, n in zip(idxs, lens):
+            host[o:o + n] = torch.from_numpy(np.asarray(self.ds.rows(key, i)))
+            o += n
+        offsets = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32)
+        if self.pin:
+            offsets = offsets.pin_memory()
+        from ._backend import ops
+        return ops.ragged_pad(host.to(self.device, non_blocking=True),
+                              offsets.to(self.device, non_blocking=True), max(lens))
+
+    def __call__(self, idxs):
+        idxs = [int(i) for i in idxs]
+        labels = torch.tensor([int(self.ds.labels[i]) for i in idxs])
+        return (self._modality("image", idxs), self._modality("text", idxs)), labels.to(self.device)
+
+
 class DevicePrefetcher:
     """Iterates a loader of HOST batches ``((img, txt), y)`` and yields them on ``device``:
     batch i+1 is copied host->device on a side stream (from pinned memory: a true async DMA)

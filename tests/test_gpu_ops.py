@@ -233,3 +233,17 @@ def test_posthoc_scoring_matches_notebook_golden(mmu, golden):
     assert out["acc_text"] == pytest.approx(tab["text"], abs=1e-9)
     assert out["acc_image_control"] == pytest.approx(float(tab["image_control"].mean()), abs=1e-12)
     assert out["acc_text_control"] == pytest.approx(float(tab["text_control"].mean()), abs=1e-12)
+
+
+def test_ragged_collator_matches_pad_sequence(mmu, tmp_path):
+    """Device-side ragged batch assembly (mmu_ragged_pad via RaggedCollator) against the
+    reference's host collate (pad_sequence, src/dataset.py:216-226): bit-exact, zero tails."""
+    src = mmu.dataset.SyntheticFlavaDataset(11, l_img=6, l_txt=9, dim=16, num_classes=5, seed=8, ragged=True)
+    items = [src[i] for i in range(len(src))]
+    mmu.dataset.pack_flava_encodings(((a, b, int(c)) for a, b, c in items), str(tmp_path / "store"))
+    ds = mmu.dataset.PackedFlavaDataset(str(tmp_path / "store"))
+    collate = mmu.dataset.RaggedCollator(ds, "cuda")
+    for idxs in ([0, 1, 2, 3], [10, 4, 7], [5]):
+        (gi, gt), gy = collate(idxs)
+        (ri, rt), ry = mmu.dataset.collate_fn_flava([items[i] for i in idxs])
+        assert torch.equal(gi.cpu(), ri) and torch.equal(gt.cpu(), rt) and torch.equal(gy.cpu(), ry)

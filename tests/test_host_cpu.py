@@ -280,3 +280,20 @@ def test_world_size_2_gloo(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_packed_store_round_trip(mmu, tmp_path):
+    """pack_flava_encodings / PackedFlavaDataset serve exactly the items the per-sample files
+    of the reference would (src/dataset.py:206-213), ragged text lengths included."""
+    src = mmu.dataset.SyntheticFlavaDataset(9, l_img=5, l_txt=7, dim=8, num_classes=4, seed=3, ragged=True)
+    items = [src[i] for i in range(len(src))]
+    mmu.dataset.pack_flava_encodings(((a, b, int(c)) for a, b, c in items), str(tmp_path / "store"))
+    ds = mmu.dataset.PackedFlavaDataset(str(tmp_path / "store"))
+    assert len(ds) == len(items)
+    for i, (a, b, c) in enumerate(items):
+        ia, ib, ic = ds[i]
+        assert torch.equal(ia, a) and torch.equal(ib, b) and torch.equal(ic, c)
+    # host collate of the packed items == host collate of the originals (reference behaviour)
+    (pi, pt), py = mmu.dataset.collate_fn_flava([ds[i] for i in (0, 3, 4)])
+    (oi, ot), oy = mmu.dataset.collate_fn_flava([items[i] for i in (0, 3, 4)])
+    assert torch.equal(pi, oi) and torch.equal(pt, ot) and torch.equal(py, oy)
