@@ -250,6 +250,28 @@ MMU_API int mmu_flava_backward(const mmu_flava_config* cfg, const float* params,
                        void* workspace, long long workspace_bytes, const float* dlogits,
                        float* grads, int stage_begin, int stage_end, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * MIMOResNet engine: the four-view FashionMNIST ResNet of train_fashionmnist.py (src/model.py:17-100
+ * ResNet / MultiHeadFC / MIMOResNet, src/layers.py:7-38 BasicBlock), fp32.  Same conventions as
+ * the FLAVA engine: flat fp32 parameter / gradient buffers described by a table of reference
+ * state_dict names, a flat buffer for the BatchNorm running statistics (second table), a
+ * caller-owned workspace.  x: fp32 (B, cin, 14, 14); logits: fp32 (B, E, C).  training != 0 uses
+ * batch statistics and moves the running statistics (momentum 0.1, unbiased variance). */
+typedef struct {
+  int B, cin, H, W, E, C;
+} mmu_resnet_config;
+MMU_API long long mmu_resnet_param_count(const mmu_resnet_config* cfg);
+MMU_API long long mmu_resnet_stat_count(const mmu_resnet_config* cfg);
+MMU_API int mmu_resnet_param_table(const mmu_resnet_config* cfg, mmu_param_entry* out /* host */, int max);
+MMU_API int mmu_resnet_stat_table(const mmu_resnet_config* cfg, mmu_param_entry* out /* host */, int max);
+MMU_API long long mmu_resnet_workspace_bytes(const mmu_resnet_config* cfg, int training);
+MMU_API int mmu_resnet_forward(const mmu_resnet_config* cfg, const float* params, float* stats, const float* x,
+                       void* workspace, long long workspace_bytes, int training, float* logits,
+                       void* stream);
+MMU_API int mmu_resnet_backward(const mmu_resnet_config* cfg, const float* params, float* stats, const float* x,
+                        void* workspace, long long workspace_bytes, const float* dlogits,
+                        float* grads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

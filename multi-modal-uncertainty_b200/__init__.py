@@ -15,7 +15,8 @@ from .src.framework import Model_  # noqa: F401
 from .src.metrics import acc  # noqa: F401
 from .src.model import (FlavaFusionTransfomer, FlavaFusionTransfomerwithCLSToken,  # noqa: F401
                         MIMOTransfomer)
+from .src.resnet import MIMOResNet  # noqa: F401
 from .src.optim import FusedAdamW, get_cosine_schedule_with_warmup  # noqa: F401
 
-__all__ = ["FlavaFusionTransfomer", "FlavaFusionTransfomerwithCLSToken", "MIMOTransfomer", "Model_", "FusedAdamW",
+__all__ = ["FlavaFusionTransfomer", "FlavaFusionTransfomerwithCLSToken", "MIMOTransfomer", "MIMOResNet", "Model_", "FusedAdamW",
            "get_cosine_schedule_with_warmup", "acc", "ops"]

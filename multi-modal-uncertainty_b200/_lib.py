@@ -21,6 +21,9 @@ EXPORTS = [
     "mmu_flava_param_table", "mmu_flava_workspace_bytes", "mmu_flava_num_stages",
     "mmu_flava_forward", "mmu_flava_backward", "mmu_cast_f32_to_bf16", "mmu_struct_size",
     "mmu_posthoc_scoring", "mmu_ragged_pad",
+    "mmu_resnet_param_count", "mmu_resnet_stat_count", "mmu_resnet_param_table",
+    "mmu_resnet_stat_table", "mmu_resnet_workspace_bytes", "mmu_resnet_forward",
+    "mmu_resnet_backward",
 ]
 
 
@@ -67,6 +70,10 @@ class ParamEntry(C.Structure):
                 ("rows", C.c_int), ("cols", C.c_int), ("stage", C.c_int)]
 
 
+class ResNetConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("B", "cin", "H", "W", "E", "C")]
+
+
 class FlavaInputs(C.Structure):
     _fields_ = [("img", C.c_void_p), ("txt", C.c_void_p), ("idx_img", C.c_void_p),
                 ("idx_txt", C.c_void_p), ("n_img", C.c_int), ("n_txt", C.c_int),
@@ -89,6 +96,15 @@ def _load():
     lib.mmu_gemm.argtypes = [i, vp, ll, i, vp, ll, i, i, i, i, i, C.POINTER(GemmEpilogue), vp]
     lib.mmu_mask_gather_tokens.argtypes = [vp, vp, i, i, i, i, vp, i, vp, i, vp]
     lib.mmu_struct_size.argtypes = [i]
+    rcfgp = C.POINTER(ResNetConfig)
+    for fn in (lib.mmu_resnet_param_count, lib.mmu_resnet_stat_count):
+        fn.restype, fn.argtypes = ll, [rcfgp]
+    for fn in (lib.mmu_resnet_param_table, lib.mmu_resnet_stat_table):
+        fn.argtypes = [rcfgp, C.POINTER(ParamEntry), i]
+    lib.mmu_resnet_workspace_bytes.restype = ll
+    lib.mmu_resnet_workspace_bytes.argtypes = [rcfgp, i]
+    lib.mmu_resnet_forward.argtypes = [rcfgp, vp, vp, vp, vp, ll, i, vp, vp]
+    lib.mmu_resnet_backward.argtypes = [rcfgp, vp, vp, vp, vp, ll, vp, vp, vp]
     lib.mmu_ragged_pad.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.mmu_posthoc_scoring.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp]
     lib.mmu_cast_f32_to_bf16.argtypes = [vp, vp, C.c_size_t, vp]

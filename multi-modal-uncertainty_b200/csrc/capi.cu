@@ -6,11 +6,13 @@
 #include "engine.h"
 #include "gemm_api.h"
 #include "kernels.h"
+#include "resnet.h"
 
 using namespace mmu;
 
 static_assert(sizeof(mmu_metric_accum) == sizeof(MetricAccum), "metric accumulator layout");
 static_assert(sizeof(mmu_flava_config) == sizeof(FlavaConfig), "config layout");
+static_assert(sizeof(mmu_resnet_config) == sizeof(ResNetConfig), "resnet config layout");
 static_assert(sizeof(mmu_posthoc_accum) == sizeof(PosthocAccum), "post-hoc accumulator layout");
 static_assert(sizeof(mmu_param_entry) == sizeof(ParamEntry), "param entry layout");
 static_assert(sizeof(mmu_flava_inputs) == sizeof(FlavaInputs), "inputs layout");
@@ -190,6 +192,46 @@ int mmu_flava_backward(const mmu_flava_config* cfg, const float* params, const m
   if (cfg == nullptr || in == nullptr) return MMU_ERR_ARG;
   return flava_backward(cfg_of(cfg), params, in_of(in), workspace, workspace_bytes, dlogits, grads,
                         stage_begin, stage_end, S(stream));
+}
+
+namespace {
+inline ResNetConfig rcfg_of(const mmu_resnet_config* c) {
+  ResNetConfig r;
+  std::memcpy(&r, c, sizeof(r));
+  return r;
+}
+}  // namespace
+
+long long mmu_resnet_param_count(const mmu_resnet_config* cfg) {
+  return cfg == nullptr ? MMU_ERR_ARG : resnet_param_count(rcfg_of(cfg));
+}
+long long mmu_resnet_stat_count(const mmu_resnet_config* cfg) {
+  return cfg == nullptr ? MMU_ERR_ARG : resnet_stat_count(rcfg_of(cfg));
+}
+int mmu_resnet_param_table(const mmu_resnet_config* cfg, mmu_param_entry* out, int max) {
+  return cfg == nullptr ? MMU_ERR_ARG
+                        : resnet_param_table(rcfg_of(cfg), reinterpret_cast<ParamEntry*>(out), max);
+}
+int mmu_resnet_stat_table(const mmu_resnet_config* cfg, mmu_param_entry* out, int max) {
+  return cfg == nullptr ? MMU_ERR_ARG
+                        : resnet_stat_table(rcfg_of(cfg), reinterpret_cast<ParamEntry*>(out), max);
+}
+long long mmu_resnet_workspace_bytes(const mmu_resnet_config* cfg, int training) {
+  return cfg == nullptr ? MMU_ERR_ARG : resnet_workspace_bytes(rcfg_of(cfg), training);
+}
+int mmu_resnet_forward(const mmu_resnet_config* cfg, const float* params, float* stats, const float* x,
+                       void* workspace, long long workspace_bytes, int training, float* logits,
+                       void* stream) {
+  if (cfg == nullptr) return MMU_ERR_ARG;
+  return resnet_forward(rcfg_of(cfg), params, stats, x, workspace, workspace_bytes, training, logits,
+                        S(stream));
+}
+int mmu_resnet_backward(const mmu_resnet_config* cfg, const float* params, float* stats, const float* x,
+                        void* workspace, long long workspace_bytes, const float* dlogits,
+                        float* grads, void* stream) {
+  if (cfg == nullptr) return MMU_ERR_ARG;
+  return resnet_backward(rcfg_of(cfg), params, stats, x, workspace, workspace_bytes, dlogits, grads,
+                         S(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,645 @@
+// Four-view FashionMNIST ResNet engine: forward / backward of the reference's MIMOResNet
+// (src/model.py:17-100: conv3x3(4->64) + BN + ReLU, two BasicBlocks(64) at 14x14, two
+// BasicBlocks(128) at 7x7 with a strided 1x1 downsample, AvgPool2d(4), MultiHeadFC) and
+// BasicBlock (src/layers.py:7-38), BatchNorm in batch-statistics mode when training.
+//
+// Layout: activations are NHWC fp32, i.e. row (b, y, x) of a [B*H*W, C] matrix, so that
+//   * a convolution is im2col (columns ordered (ci, ky, kx) = the reference's OIHW weight rows,
+//     so checkpoints need no re-layout) followed by ONE GEMM  out[M, Co] = cols[M, Ci*k*k] W^T,
+//     its input gradient one GEMM + a gather (col2im), its weight gradient one split-K GEMM;
+//   * BatchNorm statistics are column statistics of that matrix.
+// The GEMMs are the library's own (fp32 FFMA path: this model is the reference's fp32,
+// launch-latency-bound configuration); everything else is below.
+// No allocation, no synchronisation: caller-owned flat parameter / gradient / statistics buffers
+// and workspace, everything enqueued on the caller's stream.
+#include "resnet.h"
+
+#include <cstdio>
+#include <cstring>
+
+#include "common.h"
+#include "gemm_api.h"
+
+namespace mmu {
+
+namespace {
+
+#define RN_CHECK_LAUNCH()                                                        \
+  do {                                                                          \
+    const cudaError_t err__ = cudaGetLastError();                               \
+    if (err__ != cudaSuccess) {                                                 \
+      fprintf(stderr, "mmu: launch failed at %s:%d: %s\n", __FILE__, __LINE__, \
+              cudaGetErrorString(err__));                                       \
+      return MMU_ERR_CUDA;                                                      \
+    }                                                                           \
+    count_launch();                                                             \
+  } while (0)
+
+#define RN_TRY(x)               \
+  do {                          \
+    const int rc__ = (x);       \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+int blocks_for(size_t n, int per_block) {
+  size_t b = (n + per_block - 1) / per_block;
+  const size_t cap = static_cast<size_t>(sm_count()) * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+// ------------------------------------------------------------------------- im2col / col2im
+// cols[(b, yo, xo)][ci*k*k + ky*k + kx] = in(b, yo*stride + ky - pad, xo*stride + kx - pad, ci)
+// Threads run over (row, tap, ci) with ci fastest: NHWC reads are coalesced.
+__global__ void im2col_kernel(const float* __restrict__ in, int nchw, int B, int H, int W, int Ci,
+                              int k, int stride, int pad, int Ho, int Wo, float* __restrict__ cols) {
+  const int kk = k * k, K = Ci * kk;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Ci);
+    const int tap = static_cast<int>((i / Ci) % kk);
+    const size_t row = i / K;
+    const int xo = static_cast<int>(row % Wo), yo = static_cast<int>((row / Wo) % Ho);
+    const int b = static_cast<int>(row / (static_cast<size_t>(Wo) * Ho));
+    const int y = yo * stride + tap / k - pad, x = xo * stride + tap % k - pad;
+    float v = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W)
+      v = nchw ? in[((static_cast<size_t>(b) * Ci + ci) * H + y) * W + x]
+               : in[((static_cast<size_t>(b) * H + y) * W + x) * Ci + ci];
+    cols[row * K + static_cast<size_t>(ci) * kk + tap] = v;
+  }
+}
+
+// dx(b, y, x, ci) (+)= sum over taps of dcols[(b, yo, xo)][ci*k*k + tap] with y = yo*stride+ky-pad
+__global__ void col2im_kernel(const float* __restrict__ dcols, int B, int H, int W, int Ci, int k,
+                              int stride, int pad, int Ho, int Wo, float* __restrict__ dx,
+                              int accumulate) {
+  const int kk = k * k, K = Ci * kk;
+  const size_t total = static_cast<size_t>(B) * H * W * Ci;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Ci);
+    const size_t pix = i / Ci;
+    const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+    float s = 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int ty = y + pad - ky;
+      if (ty < 0 || ty % stride != 0) continue;
+      const int yo = ty / stride;
+      if (yo >= Ho) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int tx = x + pad - kx;
+        if (tx < 0 || tx % stride != 0) continue;
+        const int xo = tx / stride;
+        if (xo >= Wo) continue;
+        s += dcols[((static_cast<size_t>(b) * Ho + yo) * Wo + xo) * K + static_cast<size_t>(ci) * kk +
+                   ky * k + kx];
+      }
+    }
+    dx[i] = accumulate ? dx[i] + s : s;
+  }
+}
+
+// ------------------------------------------------------------------------------- BatchNorm
+// Column sums of t and t^2 over the M rows (fp64 partials: E[x^2]-E[x]^2 is then safe).
+// Block = 32 columns x 8 row lanes; grid.y slabs of rows.
+__global__ void __launch_bounds__(256)
+bn_sums_kernel(const float* __restrict__ t, int M, int C, int rows_per_block, double* __restrict__ sums) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  double a = 0.0, b = 0.0;
+  if (c < C)
+    for (int r = r0 + ry; r < r1; r += 8) {
+      const float v = t[static_cast<size_t>(r) * C + c];
+      a += v;
+      b += static_cast<double>(v) * v;
+    }
+  s1[ry][cx] = a;
+  s2[ry][cx] = b;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) { a += s1[j][cx]; b += s2[j][cx]; }
+    atomicAdd(&sums[c], a);
+    atomicAdd(&sums[C + c], b);
+  }
+}
+
+// mean / rstd of the batch (biased variance, eps 1e-5); running statistics move by `momentum`
+// towards the batch mean and the UNBIASED batch variance (torch.nn.BatchNorm2d).
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int M, int C, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = sums[c] / M;
+  double var = sums[C + c] / M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = static_cast<float>(mu);
+  rstd[c] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+  if (running_mean != nullptr) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mu);
+    running_var[c] = (1.f - momentum) * running_var[c] +
+                     momentum * static_cast<float>(var * M / (M > 1 ? M - 1 : 1));
+  }
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean,
+                                     const float* __restrict__ running_var, int C,
+                                     float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = running_mean[c];
+  rstd[c] = 1.0f / sqrtf(running_var[c] + 1e-5f);
+}
+
+// out = [relu]( (t - mean) * rstd * gamma + beta [+ residual] )
+__global__ void bn_apply_kernel(const float* __restrict__ t, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const float* __restrict__ residual,
+                                int relu, float* __restrict__ out, size_t n4, int C) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>((i * 4) % C);
+    const float4 v = reinterpret_cast<const float4*>(t)[i];
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    float4 o;
+    o.x = (v.x - mu.x) * rs.x * g.x + be.x;
+    o.y = (v.y - mu.y) * rs.y * g.y + be.y;
+    o.z = (v.z - mu.z) * rs.z * g.z + be.z;
+    o.w = (v.w - mu.w) * rs.w * g.w + be.w;
+    if (residual != nullptr) {
+      const float4 r = reinterpret_cast<const float4*>(residual)[i];
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    if (relu) {
+      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+// Backward, pass 1: dyb = dout * [out > 0] (ReLU mask from the saved output; out == nullptr: no
+// ReLU), column sums of dyb and dyb * xhat.
+__global__ void __launch_bounds__(256)
+bn_bwd_sums_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                   const float* __restrict__ t, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, int M, int C, int rows_per_block,
+                   float* __restrict__ dyb, double* __restrict__ sums) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    const float mu = mean[c], rs = rstd[c];
+    for (int r = r0 + ry; r < r1; r += 8) {
+      const size_t i = static_cast<size_t>(r) * C + c;
+      float d = dout[i];
+      if (out != nullptr && !(out[i] > 0.f)) d = 0.f;
+      dyb[i] = d;
+      a += d;
+      b += static_cast<double>(d) * ((t[i] - mu) * rs);
+    }
+  }
+  s1[ry][cx] = a;
+  s2[ry][cx] = b;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) { a += s1[j][cx]; b += s2[j][cx]; }
+    atomicAdd(&sums[c], a);
+    atomicAdd(&sums[C + c], b);
+  }
+}
+
+// Backward, pass 2: dt = gamma * rstd * (dyb - mean(dyb) - xhat * mean(dyb * xhat));
+// thread 0..C-1 of block 0 also accumulate dgamma / dbeta.
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dyb, const float* __restrict__ t,
+                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float* __restrict__ gamma, const double* __restrict__ sums,
+                                    int M, int C, float* __restrict__ dt, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta) {
+  const size_t n = static_cast<size_t>(M) * C;
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dbeta[c] += static_cast<float>(sums[c]);
+      dgamma[c] += static_cast<float>(sums[C + c]);
+    }
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const float rs = rstd[c];
+    const float xh = (t[i] - mean[c]) * rs;
+    const float m1 = static_cast<float>(sums[c] / M), m2 = static_cast<float>(sums[C + c] / M);
+    dt[i] = gamma[c] * rs * (dyb[i] - m1 - xh * m2);
+  }
+}
+
+// ------------------------------------------------------------ pooling / elementwise helpers
+// AvgPool2d(4) on the 7x7 map keeps ONE window (rows/cols 0..3): p[b, c] = mean of 16 pixels.
+__global__ void pool_fwd_kernel(const float* __restrict__ a, int B, int H, int W, int C, int win,
+                                float* __restrict__ p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int c = i % C, b = i / C;
+  float s = 0.f;
+  for (int y = 0; y < win; ++y)
+    for (int x = 0; x < win; ++x) s += a[((static_cast<size_t>(b) * H + y) * W + x) * C + c];
+  p[i] = s / (win * win);
+}
+__global__ void pool_bwd_kernel(const float* __restrict__ dp, int B, int H, int W, int C, int win,
+                                float* __restrict__ da) {
+  const size_t total = static_cast<size_t>(B) * H * W * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t pix = i / C;
+    const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+    da[i] = (y < win && x < win) ? dp[static_cast<size_t>(b) * C + c] / (win * win) : 0.f;
+  }
+}
+__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    a[i] += b[i];
+}
+__global__ void colsum_rows_kernel(const float* __restrict__ x, int M, int N, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float s = 0.f;
+  for (int r = 0; r < M; ++r) s += x[static_cast<size_t>(r) * N + c];
+  out[c] += s;
+}
+
+// ------------------------------------------------------------------------------- layout
+struct ConvBn {
+  int ci, co, k, stride, pad, hin, hout;
+  long long w, g, b;  // offsets into the flat parameter buffer: conv weight, BN gain, BN bias
+  long long stat;     // offset into the flat statistics buffer: running_mean[co] | running_var[co]
+};
+struct Net {
+  ConvBn stem;
+  ConvBn c1[4], c2[4], ds;  // four BasicBlocks; ds belongs to block 2 (layer2.0)
+  long long fc_w, fc_b;
+  long long n_params, n_stats;
+};
+
+struct Tab {
+  ParamEntry* out;
+  int max, n;
+  long long cursor;
+  long long add(const char* name, int rows, int cols) {
+    const long long numel = static_cast<long long>(rows) * (cols > 0 ? cols : 1);
+    const long long off = cursor;
+    if (out != nullptr && n < max) {
+      ParamEntry& e = out[n];
+      std::memset(&e, 0, sizeof(e));
+      std::snprintf(e.name, sizeof(e.name), "%s", name);
+      e.offset = off; e.numel = numel; e.rows = rows; e.cols = cols; e.stage = 0;
+    }
+    ++n;
+    cursor = (cursor + numel + 63) / 64 * 64;
+    return off;
+  }
+};
+
+// Parameter order = the reference's named_parameters() order (src/model.py:21-31, layers.py:13-19:
+// a BasicBlock registers bn1, conv1, bn2, conv2, downsample in that order).
+int build(const ResNetConfig& c, Net* net, ParamEntry* ptab, int pmax, ParamEntry* stab, int smax,
+          int* n_ptab, int* n_stab) {
+  if (c.B < 1 || c.cin < 1 || c.H != 14 || c.W != 14 || c.E < 1 || c.E > 16 || c.C < 1) return MMU_ERR_SHAPE;
+  Tab p{ptab, pmax, 0, 0}, s{stab, smax, 0, 0};
+  char nm[96];
+  auto bn = [&](const char* prefix, int ch, ConvBn* cb) {
+    std::snprintf(nm, sizeof(nm), "%s.weight", prefix); cb->g = p.add(nm, ch, 0);
+    std::snprintf(nm, sizeof(nm), "%s.bias", prefix);   cb->b = p.add(nm, ch, 0);
+    std::snprintf(nm, sizeof(nm), "%s.running_mean", prefix); cb->stat = s.add(nm, ch, 0);
+    std::snprintf(nm, sizeof(nm), "%s.running_var", prefix);  s.add(nm, ch, 0);
+  };
+  auto conv = [&](const char* name, int ci, int co, int k, int stride, int hin, ConvBn* cb) {
+    cb->ci = ci; cb->co = co; cb->k = k; cb->stride = stride; cb->pad = k / 2; cb->hin = hin;
+    cb->hout = (hin + 2 * cb->pad - k) / stride + 1;
+    cb->w = p.add(name, co, ci * k * k);
+  };
+  conv("conv1.weight", c.cin, 64, 3, 1, 14, &net->stem);
+  bn("bn1", 64, &net->stem);
+  const int planes[4] = {64, 64, 128, 128}, inpl[4] = {64, 64, 64, 128}, strides[4] = {1, 1, 2, 1};
+  const int hin[4] = {14, 14, 14, 7};
+  const char* names[4] = {"layer1.0", "layer1.1", "layer2.0", "layer2.1"};
+  char pre[64];
+  for (int i = 0; i < 4; ++i) {
+    std::snprintf(pre, sizeof(pre), "%s.bn1", names[i]);
+    ConvBn tmp1{}, tmp2{};
+    bn(pre, planes[i], &tmp1);
+    std::snprintf(pre, sizeof(pre), "%s.conv1.weight", names[i]);
+    conv(pre, inpl[i], planes[i], 3, strides[i], hin[i], &net->c1[i]);
+    net->c1[i].g = tmp1.g; net->c1[i].b = tmp1.b; net->c1[i].stat = tmp1.stat;
+    std::snprintf(pre, sizeof(pre), "%s.bn2", names[i]);
+    bn(pre, planes[i], &tmp2);
+    std::snprintf(pre, sizeof(pre), "%s.conv2.weight", names[i]);
+    conv(pre, planes[i], planes[i], 3, 1, net->c1[i].hout, &net->c2[i]);
+    net->c2[i].g = tmp2.g; net->c2[i].b = tmp2.b; net->c2[i].stat = tmp2.stat;
+    if (i == 2) {
+      std::snprintf(pre, sizeof(pre), "%s.downsample.0.weight", names[i]);
+      conv(pre, inpl[i], planes[i], 1, strides[i], hin[i], &net->ds);
+      net->ds.pad = 0;
+      net->ds.hout = (hin[i] - 1) / strides[i] + 1;
+      std::snprintf(pre, sizeof(pre), "%s.downsample.1", names[i]);
+      ConvBn tmpd{};
+      bn(pre, planes[i], &tmpd);
+      net->ds.g = tmpd.g; net->ds.b = tmpd.b; net->ds.stat = tmpd.stat;
+    }
+  }
+  net->fc_w = p.add("output_layer.fc.weight", c.E * c.C, 128);
+  net->fc_b = p.add("output_layer.fc.bias", c.E * c.C, 0);
+  net->n_params = p.cursor;
+  net->n_stats = s.cursor;
+  if (n_ptab) *n_ptab = p.n;
+  if (n_stab) *n_stab = s.n;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ workspace
+struct CbWs {
+  float* t;     // conv output, pre-BN          [Mout, co]
+  float* mean;  // batch (or running) mean      [co]
+  float* rstd;
+  float* out;   // post BN (+residual) (+ReLU)  [Mout, co]
+};
+struct Ws {
+  CbWs stem, c1[4], c2[4], ds;
+  float* cols;     // im2col scratch (largest layer)
+  float* pooled;   // [B, 128]
+  double* sums;    // [2 * 128] BN reduction scratch
+  // backward
+  float* dcols;
+  float* dyb;      // masked upstream gradient of the BN being differentiated
+  float* dt;       // gradient w.r.t. the conv output
+  float* dact[2];  // gradients w.r.t. activations (ping-pong), largest activation size
+  float* dres;     // gradient flowing along the residual connection
+  float* dpooled;
+  long long bytes;
+};
+struct Bump {
+  char* base;
+  long long off;
+  template <typename T>
+  T* take(long long bytes) {
+    const long long o = off;
+    off = (off + bytes + 255) / 256 * 256;
+    return base != nullptr ? reinterpret_cast<T*>(base + o) : nullptr;
+  }
+};
+long long rows_of(const ResNetConfig& c, int h) { return static_cast<long long>(c.B) * h * h; }
+
+void carve(const ResNetConfig& c, const Net& n, int training, void* base, Ws* w) {
+  Bump b{static_cast<char*>(base), 0};
+  auto cb = [&](const ConvBn& l, CbWs* o) {
+    const long long m = rows_of(c, l.hout);
+    o->t = b.take<float>(m * l.co * 4);
+    o->mean = b.take<float>(l.co * 4);
+    o->rstd = b.take<float>(l.co * 4);
+    o->out = b.take<float>(m * l.co * 4);
+  };
+  cb(n.stem, &w->stem);
+  long long max_cols = rows_of(c, n.stem.hout) * n.stem.ci * 9;
+  for (int i = 0; i < 4; ++i) {
+    cb(n.c1[i], &w->c1[i]);
+    cb(n.c2[i], &w->c2[i]);
+    const long long a = rows_of(c, n.c1[i].hout) * n.c1[i].ci * 9, d = rows_of(c, n.c2[i].hout) * n.c2[i].ci * 9;
+    if (a > max_cols) max_cols = a;
+    if (d > max_cols) max_cols = d;
+  }
+  cb(n.ds, &w->ds);
+  w->cols = b.take<float>(max_cols * 4);
+  w->pooled = b.take<float>(static_cast<long long>(c.B) * 128 * 4);
+  w->sums = b.take<double>(2 * 128 * 8);
+  if (training) {
+    const long long max_act = rows_of(c, 14) * 64;  // == rows_of(7) * 128 * 2: the largest activation
+    w->dcols = b.take<float>(max_cols * 4);
+    w->dyb = b.take<float>(max_act * 4);
+    w->dt = b.take<float>(max_act * 4);
+    w->dact[0] = b.take<float>(max_act * 4);
+    w->dact[1] = b.take<float>(max_act * 4);
+    w->dres = b.take<float>(max_act * 4);
+    w->dpooled = b.take<float>(static_cast<long long>(c.B) * 128 * 4);
+  } else {
+    w->dcols = w->dyb = w->dt = w->dact[0] = w->dact[1] = w->dres = w->dpooled = nullptr;
+  }
+  w->bytes = b.off;
+}
+
+GemmEpilogue store_epi(float* out, long long ld, const float* bias) {
+  GemmEpilogue e{};
+  e.mode = EPI_STORE; e.out_bf16 = 0; e.out = out; e.ld_out = ld; e.bias = bias; e.alpha = 1.0f;
+  return e;
+}
+
+// ------------------------------------------------------------------------- layer helpers
+struct Ctx {
+  const ResNetConfig& c;
+  const float* params;
+  float* stats;      // running statistics (updated in training mode), may be null in eval? no: required
+  float* grads;
+  int training;
+  Ws& w;
+  cudaStream_t st;
+};
+
+int conv_bn_fwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, int in_nchw,
+                const float* residual, int relu) {
+  const int M = static_cast<int>(rows_of(x.c, l.hout)), K = l.ci * l.k * l.k;
+  const size_t ncols = static_cast<size_t>(M) * K;
+  im2col_kernel<<<blocks_for(ncols, 256), 256, 0, x.st>>>(in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k,
+                                                          l.stride, l.pad, l.hout, l.hout, x.w.cols);
+  RN_CHECK_LAUNCH();
+  GemmProblem p{M, l.co, K, 0, 0, 1};
+  RN_TRY(gemm_f32_launch(x.w.cols, K, x.params + l.w, K, p, store_epi(o.t, l.co, nullptr), x.st));
+  if (x.training) {
+    if (cudaMemsetAsync(x.w.sums, 0, 2 * l.co * sizeof(double), x.st) != cudaSuccess) return MMU_ERR_CUDA;
+    const int gy = (M + 511) / 512;
+    bn_sums_kernel<<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(o.t, M, l.co, 512, x.w.sums);
+    RN_CHECK_LAUNCH();
+    bn_finalize_kernel<<<(l.co + 127) / 128, 128, 0, x.st>>>(x.w.sums, M, l.co, 0.1f, o.mean, o.rstd,
+                                                              x.stats + l.stat, x.stats + l.stat + l.co);
+    RN_CHECK_LAUNCH();
+  } else {
+    bn_eval_stats_kernel<<<(l.co + 127) / 128, 128, 0, x.st>>>(x.stats + l.stat, x.stats + l.stat + l.co,
+                                                                l.co, o.mean, o.rstd);
+    RN_CHECK_LAUNCH();
+  }
+  const size_t n4 = static_cast<size_t>(M) * l.co / 4;
+  bn_apply_kernel<<<blocks_for(n4, 256), 256, 0, x.st>>>(o.t, o.mean, o.rstd, x.params + l.g,
+                                                         x.params + l.b, residual, relu, o.out, n4, l.co);
+  RN_CHECK_LAUNCH();
+  return 0;
+}
+
+// dout: gradient w.r.t. this layer's output `o.out`.  relu: the forward applied ReLU.
+// Produces (or accumulates into) din, the gradient w.r.t. the layer input (NHWC); if
+// dres_out != nullptr the masked gradient is also copied there (the residual branch).
+int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, int in_nchw,
+                const float* dout, int relu, float* din, int din_accumulate, float* dres_out) {
+  const int M = static_cast<int>(rows_of(x.c, l.hout)), K = l.ci * l.k * l.k;
+  if (cudaMemsetAsync(x.w.sums, 0, 2 * l.co * sizeof(double), x.st) != cudaSuccess) return MMU_ERR_CUDA;
+  float* dyb = dres_out != nullptr ? dres_out : x.w.dyb;
+  const int gy = (M + 511) / 512;
+  bn_bwd_sums_kernel<<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(
+      dout, relu ? o.out : nullptr, o.t, o.mean, o.rstd, M, l.co, 512, dyb, x.w.sums);
+  RN_CHECK_LAUNCH();
+  const size_t n = static_cast<size_t>(M) * l.co;
+  bn_bwd_apply_kernel<<<blocks_for(n, 256), 256, 0, x.st>>>(dyb, o.t, o.mean, o.rstd, x.params + l.g,
+                                                            x.w.sums, M, l.co, x.w.dt, x.grads + l.g,
+                                                            x.grads + l.b);
+  RN_CHECK_LAUNCH();
+  // weight gradient: dW[co, K] += dt^T cols   (cols recomputed: 9x cheaper than keeping them)
+  const size_t ncols = static_cast<size_t>(M) * K;
+  im2col_kernel<<<blocks_for(ncols, 256), 256, 0, x.st>>>(in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k,
+                                                          l.stride, l.pad, l.hout, l.hout, x.w.cols);
+  RN_CHECK_LAUNCH();
+  {
+    int splits = M / 2048;
+    if (splits < 1) splits = 1;
+    if (splits > 32) splits = 32;
+    GemmProblem p{l.co, K, M, 1, 1, splits};
+    GemmEpilogue e{};
+    e.mode = EPI_ATOMIC; e.out = x.grads + l.w; e.ld_out = K; e.alpha = 1.0f;
+    RN_TRY(gemm_f32_launch(x.w.dt, l.co, x.w.cols, K, p, e, x.st));
+  }
+  if (din != nullptr) {
+    // input gradient: dcols[M, K] = dt W, then gather back to pixels
+    GemmProblem p{M, K, l.co, 0, 1, 1};
+    RN_TRY(gemm_f32_launch(x.w.dt, l.co, x.params + l.w, K, p, store_epi(x.w.dcols, K, nullptr), x.st));
+    const size_t nin = static_cast<size_t>(x.c.B) * l.hin * l.hin * l.ci;
+    col2im_kernel<<<blocks_for(nin, 256), 256, 0, x.st>>>(x.w.dcols, x.c.B, l.hin, l.hin, l.ci, l.k,
+                                                          l.stride, l.pad, l.hout, l.hout, din,
+                                                          din_accumulate);
+    RN_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =========================================================================== public
+int resnet_param_table(const ResNetConfig& c, ParamEntry* out, int max_entries) {
+  Net n;
+  int np = 0;
+  RN_TRY(build(c, &n, out, max_entries, nullptr, 0, &np, nullptr));
+  return np;
+}
+int resnet_stat_table(const ResNetConfig& c, ParamEntry* out, int max_entries) {
+  Net n;
+  int ns = 0;
+  RN_TRY(build(c, &n, nullptr, 0, out, max_entries, nullptr, &ns));
+  return ns;
+}
+long long resnet_param_count(const ResNetConfig& c) {
+  Net n;
+  if (build(c, &n, nullptr, 0, nullptr, 0, nullptr, nullptr) != 0) return MMU_ERR_SHAPE;
+  return n.n_params;
+}
+long long resnet_stat_count(const ResNetConfig& c) {
+  Net n;
+  if (build(c, &n, nullptr, 0, nullptr, 0, nullptr, nullptr) != 0) return MMU_ERR_SHAPE;
+  return n.n_stats;
+}
+long long resnet_workspace_bytes(const ResNetConfig& c, int training) {
+  Net n;
+  if (build(c, &n, nullptr, 0, nullptr, 0, nullptr, nullptr) != 0) return MMU_ERR_SHAPE;
+  Ws w;
+  carve(c, n, training, nullptr, &w);
+  return w.bytes;
+}
+
+int resnet_forward(const ResNetConfig& c, const float* params, float* stats, const float* x_nchw,
+                   void* ws, long long ws_bytes, int training, float* logits, cudaStream_t stream) {
+  if (params == nullptr || stats == nullptr || x_nchw == nullptr || ws == nullptr || logits == nullptr)
+    return MMU_ERR_ARG;
+  Net n;
+  RN_TRY(build(c, &n, nullptr, 0, nullptr, 0, nullptr, nullptr));
+  Ws w;
+  carve(c, n, training, ws, &w);
+  if (w.bytes > ws_bytes) return MMU_ERR_WORKSPACE;
+  const Ctx x{c, params, stats, nullptr, training, w, stream};
+  RN_TRY(conv_bn_fwd(x, n.stem, w.stem, x_nchw, 1, nullptr, 1));
+  const float* a = w.stem.out;
+  for (int i = 0; i < 4; ++i) {
+    RN_TRY(conv_bn_fwd(x, n.c1[i], w.c1[i], a, 0, nullptr, 1));
+    const float* residual = a;
+    if (i == 2) {
+      RN_TRY(conv_bn_fwd(x, n.ds, w.ds, a, 0, nullptr, 0));
+      residual = w.ds.out;
+    }
+    RN_TRY(conv_bn_fwd(x, n.c2[i], w.c2[i], w.c1[i].out, 0, residual, 1));
+    a = w.c2[i].out;
+  }
+  pool_fwd_kernel<<<(c.B * 128 + 255) / 256, 256, 0, stream>>>(a, c.B, 7, 7, 128, 4, w.pooled);
+  RN_CHECK_LAUNCH();
+  GemmProblem p{c.B, c.E * c.C, 128, 0, 0, 1};
+  if ((c.E * c.C) % 4 != 0) return MMU_ERR_SHAPE;
+  RN_TRY(gemm_f32_launch(w.pooled, 128, params + n.fc_w, 128, p,
+                         store_epi(logits, c.E * c.C, params + n.fc_b), stream));
+  return 0;
+}
+
+int resnet_backward(const ResNetConfig& c, const float* params, float* stats, const float* x_nchw,
+                    void* ws, long long ws_bytes, const float* dlogits, float* grads,
+                    cudaStream_t stream) {
+  if (params == nullptr || x_nchw == nullptr || ws == nullptr || dlogits == nullptr || grads == nullptr)
+    return MMU_ERR_ARG;
+  Net n;
+  RN_TRY(build(c, &n, nullptr, 0, nullptr, 0, nullptr, nullptr));
+  Ws w;
+  carve(c, n, 1, ws, &w);
+  if (w.bytes > ws_bytes) return MMU_ERR_WORKSPACE;
+  const Ctx x{c, params, stats, grads, 1, w, stream};
+  const int EC = c.E * c.C;
+  // ---- MultiHeadFC: dWfc += dlogits^T pooled ; dbfc += colsum ; dpooled = dlogits Wfc
+  {
+    GemmProblem p{EC, 128, c.B, 1, 1, 1};
+    GemmEpilogue e{};
+    e.mode = EPI_ATOMIC; e.out = grads + n.fc_w; e.ld_out = 128; e.alpha = 1.0f;
+    RN_TRY(gemm_f32_launch(dlogits, EC, w.pooled, 128, p, e, stream));
+    colsum_rows_kernel<<<(EC + 127) / 128, 128, 0, stream>>>(dlogits, c.B, EC, grads + n.fc_b);
+    RN_CHECK_LAUNCH();
+    GemmProblem q{c.B, 128, EC, 0, 1, 1};
+    RN_TRY(gemm_f32_launch(dlogits, EC, params + n.fc_w, 128, q, store_epi(w.dpooled, 128, nullptr), stream));
+  }
+  float* dcur = w.dact[0];
+  float* dnext = w.dact[1];
+  {
+    const size_t total = static_cast<size_t>(c.B) * 49 * 128;
+    pool_bwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w.dpooled, c.B, 7, 7, 128, 4, dcur);
+    RN_CHECK_LAUNCH();
+  }
+  // ---- BasicBlocks in reverse.  dcur = gradient w.r.t. the block output.
+  for (int i = 3; i >= 0; --i) {
+    const float* blk_in = i == 0 ? w.stem.out : w.c2[i - 1].out;
+    // conv2 + bn2 (+residual) + relu: masked gradient also flows along the residual (w.dres)
+    RN_TRY(conv_bn_bwd(x, n.c2[i], w.c2[i], w.c1[i].out, 0, dcur, 1, dnext, 0, w.dres));
+    // dnext = gradient w.r.t. c1 output (post-ReLU); conv1 + bn1 + relu -> gradient w.r.t. block input
+    RN_TRY(conv_bn_bwd(x, n.c1[i], w.c1[i], blk_in, 0, dnext, 1, dcur, 0, nullptr));
+    if (i == 2) {
+      // downsample branch: conv1x1 + bn, no ReLU; its input gradient adds to dcur
+      RN_TRY(conv_bn_bwd(x, n.ds, w.ds, blk_in, 0, w.dres, 0, dcur, 1, nullptr));
+    } else {
+      const size_t nel = static_cast<size_t>(rows_of(c, n.c1[i].hin)) * n.c1[i].ci;
+      add_inplace_kernel<<<blocks_for(nel, 256), 256, 0, stream>>>(dcur, w.dres, nel);
+      RN_CHECK_LAUNCH();
+    }
+  }
+  // ---- stem: conv1 + bn1 + relu (no input gradient needed)
+  RN_TRY(conv_bn_bwd(x, n.stem, w.stem, x_nchw, 1, dcur, 1, nullptr, 0, nullptr));
+  return 0;
+}
+
+}  // namespace mmu

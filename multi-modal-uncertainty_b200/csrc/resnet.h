@@ -1,0 +1,32 @@
+// Four-view FashionMNIST ResNet engine (reference MIMOResNet, src/model.py:17-100 +
+// src/layers.py:7-38).  See resnet.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "engine.h"  // ParamEntry
+
+namespace mmu {
+
+struct ResNetConfig {
+  int B;     // mini-batch
+  int cin;   // input channels = num_channels * emb_dim (the views become channels, src/model.py:85)
+  int H, W;  // 14 x 14 (quarter crops of FashionMNIST)
+  int E;     // out_dim (heads of MultiHeadFC)
+  int C;     // num_classes
+};
+
+int resnet_param_table(const ResNetConfig& c, ParamEntry* out, int max_entries);  // returns count
+int resnet_stat_table(const ResNetConfig& c, ParamEntry* out, int max_entries);   // BN running stats
+long long resnet_param_count(const ResNetConfig& c);   // padded flat length of params / grads
+long long resnet_stat_count(const ResNetConfig& c);    // padded flat length of the statistics buffer
+long long resnet_workspace_bytes(const ResNetConfig& c, int training);
+// x: fp32 (B, cin, 14, 14) NCHW; logits: fp32 (B, E, C).  training != 0: batch statistics, running
+// statistics updated in `stats`, activations kept for the backward.
+int resnet_forward(const ResNetConfig& c, const float* params, float* stats, const float* x_nchw,
+                   void* ws, long long ws_bytes, int training, float* logits, cudaStream_t stream);
+// grads (same layout as params) are ACCUMULATED.
+int resnet_backward(const ResNetConfig& c, const float* params, float* stats, const float* x_nchw,
+                    void* ws, long long ws_bytes, const float* dlogits, float* grads,
+                    cudaStream_t stream);
+
+}  // namespace mmu

@@ -193,12 +193,26 @@ class FlavaFusionTransfomer(nn.Module):
         self._param_list = list(self.parameters())
         self._flat, self._flat_grad = flat, flat_grad
         params = dict(self.named_parameters())
+        self._grad_views = []
         for name, off, numel, rows, cols, _stage in self._table:
             shape = (rows, cols) if cols > 0 else (rows,)
             p = params[name]
             p.data = flat[off:off + numel].view(shape)
             p.grad = flat_grad[off:off + numel].view(shape)
+            self._grad_views.append((p, p.grad))
         self._ws.clear()
+
+    def _ensure_grad_views(self):
+        """The kernels accumulate into the flat gradient buffer; ``p.grad`` must be its views.
+        ``torch.optim.Optimizer.zero_grad()`` (set_to_none=True, the default) drops them: treat a
+        dropped gradient as the zero it stands for and re-attach the view."""
+        for p, view in self._grad_views:
+            if p.grad is not view:
+                if p.grad is None:
+                    view.zero_()
+                else:
+                    view.copy_(p.grad)
+                p.grad = view
 
     def _apply(self, fn, recurse=True):
         flat = fn(self._flat)
@@ -403,6 +417,7 @@ class FlavaFusionTransfomer(nn.Module):
 
     def _engine_backward(self, saved, dlogits):
         cfg, inp, ws, _alive = saved
+        self._ensure_grad_views()
         if self._ddp is not None:
             self._ddp.backward(self, cfg, inp, ws, dlogits)
             return

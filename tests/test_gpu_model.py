@@ -374,3 +374,42 @@ def test_mimo_transformer_matches_reference_golden(mmu, golden, precision, tol_l
         x0 = x.clone(); x0[:, 2] = 0
         assert torch.equal(torch.from_numpy(P[2]), m(x0.cuda()).cpu())
     assert all(mt["n_samples"] == x.shape[0] for mt in metrics)
+
+
+def test_mimo_resnet_matches_reference_golden(mmu, golden):
+    """MIMOResNet engine (conv = im2col + GEMM, BatchNorm batch statistics, BasicBlocks, pooled
+    MultiHeadFC) against the golden frozen from the unmodified reference module: train-mode
+    logits / loss, every gradient, BatchNorm running statistics, eval-mode logits at <= 1e-3
+    (the golden's seed keeps every ReLU pre-activation >= 2e-5 away from zero, see
+    tests/test_oracle_golden.py::test_mimo_resnet)."""
+    c = golden("mimo_resnet.pt")
+    cfg = c["cfg"]
+    m = mmu.MIMOResNet(num_channels=cfg["num_channels"], emb_dim=cfg["emb_dim"], out_dim=cfg["E"],
+                       num_classes=cfg["C"])
+    m.load_state_dict(c["state_dict"], strict=True)
+    m.cuda().train()
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)          # the reference's optimiser for this model
+    opt.zero_grad()
+    logits = m(c["x"].cuda())
+    loss = m.compute_loss(logits, c["y_train"].cuda())
+    loss.backward()
+    assert rel(logits.detach().cpu(), c["logits"]) < 1e-3
+    assert abs(float(loss.detach()) - float(c["loss"])) < 1e-3 * abs(float(c["loss"]))
+    assert torch.equal(logits.detach().cpu().argmax(-1), c["logits"].argmax(-1))
+    assert float(mmu.acc(logits, c["y_train"].cuda(), False, True)) == pytest.approx(
+        float((c["logits"].argmax(-1) == c["y_train"]).float().mean() * 100), abs=1e-4)
+    for k, p in m.named_parameters():
+        g = c["grads"][k]
+        assert rel(p.grad.cpu(), g) < 1e-3, (k, rel(p.grad.cpu(), g))
+    for k, v in m.state_dict().items():                      # running statistics after the forward
+        if "running" in k or "num_batches" in k:
+            assert rel(v.cpu().double(), c["state_after_forward"][k].double()) < 1e-4, k
+    opt.step()
+    m.load_state_dict(c["state_after_forward"], strict=True)
+    m.eval()
+    with torch.no_grad():
+        ev = m(c["x"].cuda())
+    assert rel(ev.cpu(), c["logits_eval"]) < 1e-3
+    # four-view zero-fill sweep (eval_robustness.py:82-121) runs on this model too
+    P, labels, metrics = mmu.robustness.run_view_robustness(m, [(c["x"], c["y"])], "cuda")
+    assert P.shape == (4, c["x"].shape[0], cfg["E"], cfg["C"])

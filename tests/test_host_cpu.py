@@ -98,6 +98,28 @@ def test_mimo_transformer_seeded_init_and_keys(mmu, golden):
         m(torch.randn(2, 4, 1, 14, 14))
 
 
+def test_mimo_resnet_seeded_init_keys_and_strict_load(mmu, golden):
+    """MIMOResNet: reference parameter order, state-dict keys (BatchNorm buffers included, in the
+    reference's order), seed-for-seed initial weights (src/model.py:17-100), strict checkpoint load."""
+    g, c = golden("init_seed123.pt"), golden("mimo_resnet.pt")
+    torch.manual_seed(123)
+    m = mmu.MIMOResNet(num_channels=1, emb_dim=4, out_dim=4, num_classes=10)
+    assert [k for k, _ in m.named_parameters()] == g["resnet_param_order"] == c["param_order"]
+    assert [k for k, _ in m.named_buffers()] == c["buffer_order"]
+    assert list(m.state_dict().keys()) == list(c["state_dict"].keys())
+    for k, v in m.state_dict().items():
+        got = torch.stack([v.double().sum(), v.double().abs().sum()])
+        assert torch.allclose(got, g["resnet"][k], rtol=1e-12, atol=1e-12), k
+    m.load_state_dict(c["state_dict"], strict=True)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, c["state_dict"][k]), k
+    base = m._flat.data_ptr()
+    for p in m.parameters():
+        assert base <= p.data_ptr() < base + m._flat.numel() * 4 and p.grad is not None
+    with pytest.raises(mmu._lib.MMUError):
+        m(torch.rand(2, 4, 1, 14, 14))
+
+
 def test_stage_ranges_partition_the_flat_buffer(mmu):
     m = small_model(mmu)
     ranges = m.stage_ranges()

@@ -159,3 +159,31 @@ def test_uncertainty_identities():
     assert int(h["conf_correct"].sum()) == h["n_correct_prob"]
     ece = uncertainty.ece_from_bins(h["conf_count"], h["conf_correct"], h["conf_sum"])
     assert 0.0 <= ece <= 1.0
+
+
+def test_mimo_resnet(golden):
+    """oracle/resnet.py against the reference's MIMOResNet (src/model.py:17-100, layers.py:7-38):
+    train-mode logits, loss, every gradient, BatchNorm running statistics, eval-mode logits.
+    The golden's seed was searched (tests/golden/make_golden.py) so that no ReLU pre-activation
+    lies within 2e-5 of zero: a pre-activation within fp32 rounding of zero flips its mask in one
+    implementation and not the other and, with 4 samples, moves BatchNorm gradients by percents."""
+    from oracle import resnet
+    rel = rel_err
+    c = golden("mimo_resnet.pt")
+    C = c["cfg"]["C"]
+    P64 = {k: (v.double() if v.is_floating_point() else v) for k, v in c["state_dict"].items()}
+    logits, loss, grads, buffers = resnet.loss_and_grads(P64, c["x"].double(), c["y_train"], C)
+    assert rel(logits, c["logits"]) < 1e-5 and abs(float(loss) - float(c["loss"])) < 1e-5
+    assert torch.equal(logits.argmax(-1), c["logits"].argmax(-1))
+    for k, g in c["grads"].items():
+        assert rel(grads[k], g) < 5e-5, k
+    for k, v in buffers.items():
+        assert rel(v.double(), c["state_after_forward"][k].double()) < 1e-5, k
+    after64 = {k: (v.double() if v.is_floating_point() else v) for k, v in c["state_after_forward"].items()}
+    ev = resnet.mimo_resnet_forward(after64, c["x"].double(), C, training=False)
+    assert rel(ev, c["logits_eval"]) < 1e-5
+    # fp32 oracle (the dtype the CUDA engine is compared in)
+    l32, loss32, g32, _ = resnet.loss_and_grads(c["state_dict"], c["x"], c["y_train"], C)
+    assert rel(l32, c["logits"]) < 1e-5
+    for k, g in c["grads"].items():
+        assert rel(g32[k], g) < 2e-4, k
