@@ -21,7 +21,18 @@ _PREC = {"fp32": _lib.F32, "bf16": _lib.BF16, torch.float32: _lib.F32, torch.bfl
 
 
 class _Holder(nn.Module):
-    """Parameter container: only exists so that state-dict keys match the reference's tree."""
+    """Parameter container: only exists so that state-dict keys match the reference's tree.
+    Containers with numeric children (the reference's ``nn.ModuleList`` / ``nn.Sequential``:
+    ``output_layers``, ``resblocks``, ``layer1`` ...) index, iterate and ``len()`` like them."""
+
+    def __getitem__(self, i):
+        return self._modules[str(i if i >= 0 else len(self._modules) + i)]
+
+    def __len__(self):
+        return len(self._modules)
+
+    def __iter__(self):
+        return iter(self._modules.values())
 
 
 def _holder_for(root, dotted):

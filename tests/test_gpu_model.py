@@ -413,3 +413,68 @@ def test_mimo_resnet_matches_reference_golden(mmu, golden):
     # four-view zero-fill sweep (eval_robustness.py:82-121) runs on this model too
     P, labels, metrics = mmu.robustness.run_view_robustness(m, [(c["x"], c["y"])], "cuda")
     assert P.shape == (4, c["x"].shape[0], cfg["E"], cfg["C"])
+
+
+def test_full_baseline_size_properties(mmu):
+    """BASELINE.json configs[1]/[2] at full size (B=128, 197 image + 40 text tokens, D=768, E=5,
+    C=101, bf16: M = 30 336 rows -> CTA-pair GEMMs, many tiles per CTA), where the oracle is too
+    slow; size-independent properties instead:
+      (1) the packed 10-level sweep equals one forward per level, bit for bit, and is deterministic;
+      (2) calibration histograms are a partition of the samples, ECE recomputed from the per-sample
+          scores equals the ECE from the bins, accuracy counts match the predictions;
+      (3) softmax-CE gradients sum to zero over the classes => every head-bias gradient sums to 0,
+          and the dead text projection receives exactly zero gradient;
+      (4) a training step is finite and reduces the loss on the same batch."""
+    import numpy as np
+    torch.manual_seed(3)
+    m = mmu.FlavaFusionTransfomer(out_dim=5, num_classes=101, avg_pool=False, precision="bf16").cuda()
+    g = torch.Generator().manual_seed(4)
+    img, txt = torch.randn(128, 197, 768, generator=g).cuda(), torch.randn(128, 40, 768, generator=g).cuda()
+    y = torch.randint(0, 101, (128,), generator=g).cuda()
+    torch.manual_seed(5)
+    variants = [mmu.robustness.mask_level_variant(197, 40, "image", k, 10) for k in range(10)]
+    m.eval()
+    with torch.no_grad():
+        packed = m.forward_variants((img, txt), variants)
+        assert torch.equal(packed, m.forward_variants((img, txt), variants))          # deterministic
+        for k in (0, 4, 9):
+            assert torch.equal(packed[k], mmu.robustness.forward_variant(m, img, txt, variants[k]))
+    assert torch.isfinite(packed).all()
+    # (2) histograms / ECE / accuracy from one epilogue launch over all 1280 (level, sample) pairs
+    flat, labels = packed.view(-1, 5, 101), y.repeat(10)
+    _, pred, scores, accum = mmu.ops.heads_uncertainty_epilogue(flat, labels, 1, want_pred=True,
+                                                                want_scores=True)
+    d = mmu.ops.accum_to_dict(accum)
+    N = flat.shape[0]
+    assert d["n_samples"] == N and int(d["conf_count"].sum()) == N
+    assert int(d["hpred_count"].sum()) == N and int(d["mi_count"].sum()) == N
+    pred, scores = pred.cpu().numpy(), scores.cpu().numpy()
+    lab = labels.cpu().numpy()
+    assert d["n_correct_rows"] == int((pred[:, 0] == lab).sum())
+    assert d["n_correct_prob"] == int((pred[:, 1] == lab).sum())
+    conf = scores[:, 0]
+    bins = np.minimum(np.floor(conf * np.float32(15)).astype(int), 14)
+    assert np.array_equal(np.bincount(bins, minlength=15), d["conf_count"])
+    ece_bins = sum(abs(d["conf_correct"][b] - d["conf_sum"][b]) for b in range(15)) / N
+    ece_direct = sum(abs((pred[bins == b, 1] == lab[bins == b]).sum() - conf[bins == b].astype(np.float64).sum())
+                     for b in range(15)) / N
+    assert abs(ece_bins - ece_direct) < 1e-6
+    assert np.all(scores[:, 3] > -1e-5) and np.all(scores[:, 1] <= np.log(101) + 1e-4)   # MI >= 0, H <= log C
+    # (3) + (4)
+    m.train()
+    opt = mmu.FusedAdamW(m.parameters(), lr=1e-3)
+    yt = y.unsqueeze(1).repeat(1, 5)
+    losses = []
+    for _ in range(2):
+        opt.zero_grad()
+        loss = m.compute_loss(m((img, txt)), yt)
+        loss.backward()
+        if not losses:
+            for e in range(5):
+                gb = m.output_layers[e].bias.grad
+                assert abs(float(gb.sum())) < 1e-5 * max(float(gb.abs().sum()), 1e-12) + 1e-7
+            assert float(m.text_to_mm_projection.weight.grad.abs().max()) == 0.0
+            assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(np.isfinite(losses)) and losses[1] < losses[0]
