@@ -265,12 +265,14 @@ MMU_API long long mmu_resnet_stat_count(const mmu_resnet_config* cfg);
 MMU_API int mmu_resnet_param_table(const mmu_resnet_config* cfg, mmu_param_entry* out /* host */, int max);
 MMU_API int mmu_resnet_stat_table(const mmu_resnet_config* cfg, mmu_param_entry* out /* host */, int max);
 MMU_API long long mmu_resnet_workspace_bytes(const mmu_resnet_config* cfg, int training);
-MMU_API int mmu_resnet_forward(const mmu_resnet_config* cfg, const float* params, float* stats, const float* x,
-                       void* workspace, long long workspace_bytes, int training, float* logits,
-                       void* stream);
-MMU_API int mmu_resnet_backward(const mmu_resnet_config* cfg, const float* params, float* stats, const float* x,
-                        void* workspace, long long workspace_bytes, const float* dlogits,
-                        float* grads, void* stream);
+/* params_bf16: optional bf16 copy of params (mmu_cast_f32_to_bf16): the convolutions then run on
+ * the tcgen05 tensor-core GEMM (bf16 operands, fp32 accumulation); NULL: fp32 parity path. */
+MMU_API int mmu_resnet_forward(const mmu_resnet_config* cfg, const float* params, const void* params_bf16,
+                       float* stats, const float* x, void* workspace, long long workspace_bytes,
+                       int training, float* logits, void* stream);
+MMU_API int mmu_resnet_backward(const mmu_resnet_config* cfg, const float* params, const void* params_bf16,
+                        float* stats, const float* x, void* workspace, long long workspace_bytes,
+                        const float* dlogits, float* grads, void* stream);
 
 #ifdef __cplusplus
 }

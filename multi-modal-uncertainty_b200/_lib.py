@@ -103,8 +103,8 @@ def _load():
         fn.argtypes = [rcfgp, C.POINTER(ParamEntry), i]
     lib.mmu_resnet_workspace_bytes.restype = ll
     lib.mmu_resnet_workspace_bytes.argtypes = [rcfgp, i]
-    lib.mmu_resnet_forward.argtypes = [rcfgp, vp, vp, vp, vp, ll, i, vp, vp]
-    lib.mmu_resnet_backward.argtypes = [rcfgp, vp, vp, vp, vp, ll, vp, vp, vp]
+    lib.mmu_resnet_forward.argtypes = [rcfgp, vp, vp, vp, vp, vp, ll, i, vp, vp]
+    lib.mmu_resnet_backward.argtypes = [rcfgp, vp, vp, vp, vp, vp, ll, vp, vp, vp]
     lib.mmu_ragged_pad.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.mmu_posthoc_scoring.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp]
     lib.mmu_cast_f32_to_bf16.argtypes = [vp, vp, C.c_size_t, vp]

@@ -219,19 +219,19 @@ int mmu_resnet_stat_table(const mmu_resnet_config* cfg, mmu_param_entry* out, in
 long long mmu_resnet_workspace_bytes(const mmu_resnet_config* cfg, int training) {
   return cfg == nullptr ? MMU_ERR_ARG : resnet_workspace_bytes(rcfg_of(cfg), training);
 }
-int mmu_resnet_forward(const mmu_resnet_config* cfg, const float* params, float* stats, const float* x,
-                       void* workspace, long long workspace_bytes, int training, float* logits,
-                       void* stream) {
+int mmu_resnet_forward(const mmu_resnet_config* cfg, const float* params, const void* params_bf16,
+                       float* stats, const float* x, void* workspace, long long workspace_bytes,
+                       int training, float* logits, void* stream) {
   if (cfg == nullptr) return MMU_ERR_ARG;
-  return resnet_forward(rcfg_of(cfg), params, stats, x, workspace, workspace_bytes, training, logits,
-                        S(stream));
+  return resnet_forward(rcfg_of(cfg), params, params_bf16, stats, x, workspace, workspace_bytes,
+                        training, logits, S(stream));
 }
-int mmu_resnet_backward(const mmu_resnet_config* cfg, const float* params, float* stats, const float* x,
-                        void* workspace, long long workspace_bytes, const float* dlogits,
-                        float* grads, void* stream) {
+int mmu_resnet_backward(const mmu_resnet_config* cfg, const float* params, const void* params_bf16,
+                        float* stats, const float* x, void* workspace, long long workspace_bytes,
+                        const float* dlogits, float* grads, void* stream) {
   if (cfg == nullptr) return MMU_ERR_ARG;
-  return resnet_backward(rcfg_of(cfg), params, stats, x, workspace, workspace_bytes, dlogits, grads,
-                         S(stream));
+  return resnet_backward(rcfg_of(cfg), params, params_bf16, stats, x, workspace, workspace_bytes,
+                         dlogits, grads, S(stream));
 }
 
 }  // extern "C"

@@ -130,7 +130,10 @@ int pair_mode_enabled() {
 }
 
 // CTA pairs (256x256 tiles) for large unbatched problems
-bool use_pair(const GemmProblem& p) { return p.batch == 0 && p.M >= 512 && pair_mode_enabled(); }
+// (N <= 128 would waste half of every 256-wide tile: those run the single-CTA kernel at N = 128)
+bool use_pair(const GemmProblem& p) {
+  return p.batch == 0 && p.M >= 512 && p.N > gemm::BN / 2 && pair_mode_enabled();
+}
 
 template <int MODE, bool OBF, int NCTA>
 int launch_kernel(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& c0,

@@ -8,11 +8,15 @@
 //     so checkpoints need no re-layout) followed by ONE GEMM  out[M, Co] = cols[M, Ci*k*k] W^T,
 //     its input gradient one GEMM + a gather (col2im), its weight gradient one split-K GEMM;
 //   * BatchNorm statistics are column statistics of that matrix.
-// The GEMMs are the library's own (fp32 FFMA path: this model is the reference's fp32,
-// launch-latency-bound configuration); everything else is below.
+// The GEMMs are the library's own: the fp32 FFMA path reproduces the reference's arithmetic
+// (this model is its fp32 configuration); given a bf16 copy of the
+// parameters, every layer whose K = ci*k*k keeps 16-byte operand rows (all but the 4-channel
+// stem) runs on the tcgen05 kernel with bf16 columns / gradients and fp32 accumulation.
 // No allocation, no synchronisation: caller-owned flat parameter / gradient / statistics buffers
 // and workspace, everything enqueued on the caller's stream.
 #include "resnet.h"
+
+#include <cuda_bf16.h>
 
 #include <cstdio>
 #include <cstring>
@@ -49,11 +53,17 @@ int blocks_for(size_t n, int per_block) {
   return static_cast<int>(b);
 }
 
+__device__ __forceinline__ void put(float* p, float v) { *p = v; }
+__device__ __forceinline__ void put(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ float get(const float* p) { return *p; }
+__device__ __forceinline__ float get(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
 // ------------------------------------------------------------------------- im2col / col2im
 // cols[(b, yo, xo)][ci*k*k + ky*k + kx] = in(b, yo*stride + ky - pad, xo*stride + kx - pad, ci)
 // Threads run over (row, tap, ci) with ci fastest: NHWC reads are coalesced.
+template <typename TC>
 __global__ void im2col_kernel(const float* __restrict__ in, int nchw, int B, int H, int W, int Ci,
-                              int k, int stride, int pad, int Ho, int Wo, float* __restrict__ cols) {
+                              int k, int stride, int pad, int Ho, int Wo, TC* __restrict__ cols) {
   const int kk = k * k, K = Ci * kk;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * K;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -68,12 +78,13 @@ __global__ void im2col_kernel(const float* __restrict__ in, int nchw, int B, int
     if (y >= 0 && y < H && x >= 0 && x < W)
       v = nchw ? in[((static_cast<size_t>(b) * Ci + ci) * H + y) * W + x]
                : in[((static_cast<size_t>(b) * H + y) * W + x) * Ci + ci];
-    cols[row * K + static_cast<size_t>(ci) * kk + tap] = v;
+    put(cols + row * K + static_cast<size_t>(ci) * kk + tap, v);
   }
 }
 
 // dx(b, y, x, ci) (+)= sum over taps of dcols[(b, yo, xo)][ci*k*k + tap] with y = yo*stride+ky-pad
-__global__ void col2im_kernel(const float* __restrict__ dcols, int B, int H, int W, int Ci, int k,
+template <typename TC>
+__global__ void col2im_kernel(const TC* __restrict__ dcols, int B, int H, int W, int Ci, int k,
                               int stride, int pad, int Ho, int Wo, float* __restrict__ dx,
                               int accumulate) {
   const int kk = k * k, K = Ci * kk;
@@ -95,8 +106,8 @@ __global__ void col2im_kernel(const float* __restrict__ dcols, int B, int H, int
         if (tx < 0 || tx % stride != 0) continue;
         const int xo = tx / stride;
         if (xo >= Wo) continue;
-        s += dcols[((static_cast<size_t>(b) * Ho + yo) * Wo + xo) * K + static_cast<size_t>(ci) * kk +
-                   ky * k + kx];
+        s += get(dcols + ((static_cast<size_t>(b) * Ho + yo) * Wo + xo) * K +
+                 static_cast<size_t>(ci) * kk + ky * k + kx);
       }
     }
     dx[i] = accumulate ? dx[i] + s : s;
@@ -221,10 +232,11 @@ bn_bwd_sums_kernel(const float* __restrict__ dout, const float* __restrict__ out
 
 // Backward, pass 2: dt = gamma * rstd * (dyb - mean(dyb) - xhat * mean(dyb * xhat));
 // thread 0..C-1 of block 0 also accumulate dgamma / dbeta.
+template <typename TD>
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dyb, const float* __restrict__ t,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gamma, const double* __restrict__ sums,
-                                    int M, int C, float* __restrict__ dt, float* __restrict__ dgamma,
+                                    int M, int C, TD* __restrict__ dt, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta) {
   const size_t n = static_cast<size_t>(M) * C;
   if (blockIdx.x == 0)
@@ -238,7 +250,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dyb, const float* 
     const float rs = rstd[c];
     const float xh = (t[i] - mean[c]) * rs;
     const float m1 = static_cast<float>(sums[c] / M), m2 = static_cast<float>(sums[C + c] / M);
-    dt[i] = gamma[c] * rs * (dyb[i] - m1 - xh * m2);
+    put(dt + i, gamma[c] * rs * (dyb[i] - m1 - xh * m2));
   }
 }
 
@@ -446,6 +458,7 @@ GemmEpilogue store_epi(float* out, long long ld, const float* bias) {
 // ------------------------------------------------------------------------- layer helpers
 struct Ctx {
   const ResNetConfig& c;
+  const void* shadow;  // bf16 copy of params (tensor-core path) or null (fp32 path)
   const float* params;
   float* stats;      // running statistics (updated in training mode), may be null in eval? no: required
   float* grads;
@@ -454,15 +467,30 @@ struct Ctx {
   cudaStream_t st;
 };
 
+// A layer runs on the tcgen05 path when a bf16 shadow is given and its GEMM K (= ci*k*k) keeps
+// operand rows 16-byte aligned (every layer but the 4-channel stem, K = 36).
+bool use_tc(const Ctx& x, const ConvBn& l) { return x.shadow != nullptr && (l.ci * l.k * l.k) % 8 == 0; }
+const __nv_bfloat16* wbf(const Ctx& x, const ConvBn& l) {
+  return static_cast<const __nv_bfloat16*>(x.shadow) + l.w;
+}
+
 int conv_bn_fwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, int in_nchw,
                 const float* residual, int relu) {
   const int M = static_cast<int>(rows_of(x.c, l.hout)), K = l.ci * l.k * l.k;
   const size_t ncols = static_cast<size_t>(M) * K;
-  im2col_kernel<<<blocks_for(ncols, 256), 256, 0, x.st>>>(in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k,
-                                                          l.stride, l.pad, l.hout, l.hout, x.w.cols);
-  RN_CHECK_LAUNCH();
   GemmProblem p{M, l.co, K, 0, 0, 1};
-  RN_TRY(gemm_f32_launch(x.w.cols, K, x.params + l.w, K, p, store_epi(o.t, l.co, nullptr), x.st));
+  if (use_tc(x, l)) {
+    __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(x.w.cols);
+    im2col_kernel<__nv_bfloat16><<<blocks_for(ncols, 256), 256, 0, x.st>>>(
+        in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
+    RN_CHECK_LAUNCH();
+    RN_TRY(gemm_bf16_launch(cols, K, wbf(x, l), K, p, store_epi(o.t, l.co, nullptr), x.st));
+  } else {
+    im2col_kernel<float><<<blocks_for(ncols, 256), 256, 0, x.st>>>(
+        in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, x.w.cols);
+    RN_CHECK_LAUNCH();
+    RN_TRY(gemm_f32_launch(x.w.cols, K, x.params + l.w, K, p, store_epi(o.t, l.co, nullptr), x.st));
+  }
   if (x.training) {
     if (cudaMemsetAsync(x.w.sums, 0, 2 * l.co * sizeof(double), x.st) != cudaSuccess) return MMU_ERR_CUDA;
     const int gy = (M + 511) / 512;
@@ -496,32 +524,57 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
       dout, relu ? o.out : nullptr, o.t, o.mean, o.rstd, M, l.co, 512, dyb, x.w.sums);
   RN_CHECK_LAUNCH();
   const size_t n = static_cast<size_t>(M) * l.co;
-  bn_bwd_apply_kernel<<<blocks_for(n, 256), 256, 0, x.st>>>(dyb, o.t, o.mean, o.rstd, x.params + l.g,
-                                                            x.w.sums, M, l.co, x.w.dt, x.grads + l.g,
-                                                            x.grads + l.b);
+  const size_t ncols = static_cast<size_t>(M) * K;
+  const size_t nin = static_cast<size_t>(x.c.B) * l.hin * l.hin * l.ci;
+  GemmEpilogue wg{};
+  wg.mode = EPI_ATOMIC; wg.out = x.grads + l.w; wg.ld_out = K; wg.alpha = 1.0f;
+  if (use_tc(x, l)) {
+    // tensor-core path: dt and the recomputed columns in bf16, fp32 accumulation / outputs
+    __nv_bfloat16* dt = reinterpret_cast<__nv_bfloat16*>(x.w.dt);
+    __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(x.w.cols);
+    __nv_bfloat16* dcols = reinterpret_cast<__nv_bfloat16*>(x.w.dcols);
+    bn_bwd_apply_kernel<__nv_bfloat16><<<blocks_for(n, 256), 256, 0, x.st>>>(
+        dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
+    RN_CHECK_LAUNCH();
+    im2col_kernel<__nv_bfloat16><<<blocks_for(ncols, 256), 256, 0, x.st>>>(
+        in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
+    RN_CHECK_LAUNCH();
+    int splits = M / 4096;
+    if (splits < 1) splits = 1;
+    if (splits > 16) splits = 16;
+    GemmProblem p{l.co, K, M, 1, 1, splits};
+    RN_TRY(gemm_bf16_launch(dt, l.co, cols, K, p, wg, x.st));
+    if (din != nullptr) {
+      GemmProblem q{M, K, l.co, 0, 1, 1};
+      GemmEpilogue e = store_epi(reinterpret_cast<float*>(dcols), K, nullptr);
+      e.out_bf16 = 1;
+      RN_TRY(gemm_bf16_launch(dt, l.co, wbf(x, l), K, q, e, x.st));
+      col2im_kernel<__nv_bfloat16><<<blocks_for(nin, 256), 256, 0, x.st>>>(
+          dcols, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, din, din_accumulate);
+      RN_CHECK_LAUNCH();
+    }
+    return 0;
+  }
+  bn_bwd_apply_kernel<float><<<blocks_for(n, 256), 256, 0, x.st>>>(
+      dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, x.w.dt, x.grads + l.g, x.grads + l.b);
   RN_CHECK_LAUNCH();
   // weight gradient: dW[co, K] += dt^T cols   (cols recomputed: 9x cheaper than keeping them)
-  const size_t ncols = static_cast<size_t>(M) * K;
-  im2col_kernel<<<blocks_for(ncols, 256), 256, 0, x.st>>>(in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k,
-                                                          l.stride, l.pad, l.hout, l.hout, x.w.cols);
+  im2col_kernel<float><<<blocks_for(ncols, 256), 256, 0, x.st>>>(
+      in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, x.w.cols);
   RN_CHECK_LAUNCH();
   {
     int splits = M / 2048;
     if (splits < 1) splits = 1;
     if (splits > 32) splits = 32;
     GemmProblem p{l.co, K, M, 1, 1, splits};
-    GemmEpilogue e{};
-    e.mode = EPI_ATOMIC; e.out = x.grads + l.w; e.ld_out = K; e.alpha = 1.0f;
-    RN_TRY(gemm_f32_launch(x.w.dt, l.co, x.w.cols, K, p, e, x.st));
+    RN_TRY(gemm_f32_launch(x.w.dt, l.co, x.w.cols, K, p, wg, x.st));
   }
   if (din != nullptr) {
     // input gradient: dcols[M, K] = dt W, then gather back to pixels
     GemmProblem p{M, K, l.co, 0, 1, 1};
     RN_TRY(gemm_f32_launch(x.w.dt, l.co, x.params + l.w, K, p, store_epi(x.w.dcols, K, nullptr), x.st));
-    const size_t nin = static_cast<size_t>(x.c.B) * l.hin * l.hin * l.ci;
-    col2im_kernel<<<blocks_for(nin, 256), 256, 0, x.st>>>(x.w.dcols, x.c.B, l.hin, l.hin, l.ci, l.k,
-                                                          l.stride, l.pad, l.hout, l.hout, din,
-                                                          din_accumulate);
+    col2im_kernel<float><<<blocks_for(nin, 256), 256, 0, x.st>>>(
+        x.w.dcols, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, din, din_accumulate);
     RN_CHECK_LAUNCH();
   }
   return 0;
@@ -560,8 +613,9 @@ long long resnet_workspace_bytes(const ResNetConfig& c, int training) {
   return w.bytes;
 }
 
-int resnet_forward(const ResNetConfig& c, const float* params, float* stats, const float* x_nchw,
-                   void* ws, long long ws_bytes, int training, float* logits, cudaStream_t stream) {
+int resnet_forward(const ResNetConfig& c, const float* params, const void* params_bf16, float* stats,
+                   const float* x_nchw, void* ws, long long ws_bytes, int training, float* logits,
+                   cudaStream_t stream) {
   if (params == nullptr || stats == nullptr || x_nchw == nullptr || ws == nullptr || logits == nullptr)
     return MMU_ERR_ARG;
   Net n;
@@ -569,7 +623,7 @@ int resnet_forward(const ResNetConfig& c, const float* params, float* stats, con
   Ws w;
   carve(c, n, training, ws, &w);
   if (w.bytes > ws_bytes) return MMU_ERR_WORKSPACE;
-  const Ctx x{c, params, stats, nullptr, training, w, stream};
+  const Ctx x{c, params_bf16, params, stats, nullptr, training, w, stream};
   RN_TRY(conv_bn_fwd(x, n.stem, w.stem, x_nchw, 1, nullptr, 1));
   const float* a = w.stem.out;
   for (int i = 0; i < 4; ++i) {
@@ -591,9 +645,9 @@ int resnet_forward(const ResNetConfig& c, const float* params, float* stats, con
   return 0;
 }
 
-int resnet_backward(const ResNetConfig& c, const float* params, float* stats, const float* x_nchw,
-                    void* ws, long long ws_bytes, const float* dlogits, float* grads,
-                    cudaStream_t stream) {
+int resnet_backward(const ResNetConfig& c, const float* params, const void* params_bf16, float* stats,
+                    const float* x_nchw, void* ws, long long ws_bytes, const float* dlogits,
+                    float* grads, cudaStream_t stream) {
   if (params == nullptr || x_nchw == nullptr || ws == nullptr || dlogits == nullptr || grads == nullptr)
     return MMU_ERR_ARG;
   Net n;
@@ -601,7 +655,7 @@ int resnet_backward(const ResNetConfig& c, const float* params, float* stats, co
   Ws w;
   carve(c, n, 1, ws, &w);
   if (w.bytes > ws_bytes) return MMU_ERR_WORKSPACE;
-  const Ctx x{c, params, stats, grads, 1, w, stream};
+  const Ctx x{c, params_bf16, params, stats, grads, 1, w, stream};
   const int EC = c.E * c.C;
   // ---- MultiHeadFC: dWfc += dlogits^T pooled ; dbfc += colsum ; dpooled = dlogits Wfc
   {

@@ -22,11 +22,14 @@ long long resnet_stat_count(const ResNetConfig& c);    // padded flat length of 
 long long resnet_workspace_bytes(const ResNetConfig& c, int training);
 // x: fp32 (B, cin, 14, 14) NCHW; logits: fp32 (B, E, C).  training != 0: batch statistics, running
 // statistics updated in `stats`, activations kept for the backward.
-int resnet_forward(const ResNetConfig& c, const float* params, float* stats, const float* x_nchw,
-                   void* ws, long long ws_bytes, int training, float* logits, cudaStream_t stream);
+// params_bf16: optional bf16 copy of `params` (same offsets): every convolution whose GEMM K is a
+// multiple of 8 (all but the stem) then runs on the tcgen05 tensor-core kernel; null = fp32 path.
+int resnet_forward(const ResNetConfig& c, const float* params, const void* params_bf16, float* stats,
+                   const float* x_nchw, void* ws, long long ws_bytes, int training, float* logits,
+                   cudaStream_t stream);
 // grads (same layout as params) are ACCUMULATED.
-int resnet_backward(const ResNetConfig& c, const float* params, float* stats, const float* x_nchw,
-                    void* ws, long long ws_bytes, const float* dlogits, float* grads,
-                    cudaStream_t stream);
+int resnet_backward(const ResNetConfig& c, const float* params, const void* params_bf16, float* stats,
+                    const float* x_nchw, void* ws, long long ws_bytes, const float* dlogits,
+                    float* grads, cudaStream_t stream);
 
 }  // namespace mmu

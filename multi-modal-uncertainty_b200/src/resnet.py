@@ -5,7 +5,9 @@
 As in the fusion models, every parameter is an individually addressable ``nn.Parameter`` that
 views ONE flat fp32 buffer (gradients likewise), and the BatchNorm running statistics are buffer
 views of one flat statistics buffer the kernels update in place; reference checkpoints load with
-``strict=True``.  fp32 only (the reference's configuration for this model); there is no CPU path.
+``strict=True``.  ``precision="fp32"`` (default) is the reference's arithmetic;
+``precision="bf16"`` runs every convolution but the 4-channel stem on the tcgen05 tensor-core GEMM
+(bf16 operands, fp32 accumulation, fp32 BatchNorm).  There is no CPU path.
 """
 import ctypes as C
 import math
@@ -35,8 +37,12 @@ class MIMOResNet(nn.Module):
     ``forward(x)`` takes ``(B, E, C, 14, 14)`` (views become channels, src/model.py:83-86) or
     ``(B, C', 14, 14)`` and returns logits ``(B, out_dim, num_classes)``."""
 
-    def __init__(self, num_channels, emb_dim, out_dim, num_classes):
+    def __init__(self, num_channels, emb_dim, out_dim, num_classes, precision="fp32"):
         super().__init__()
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' (reference arithmetic) or 'bf16' (tensor cores)")
+        self.precision = precision
+        self._shadow, self._shadow_stamp = None, None
         self.out_dim, self.num_classes = out_dim, num_classes
         self._cin = num_channels * emb_dim
         self._ws, self._cfgs = {}, {}
@@ -83,7 +89,27 @@ class MIMOResNet(nn.Module):
         return cfg
 
     # ------------------------------------------------------------------ flat buffers
+    def _fresh_shadow(self):
+        """bf16 copy of the flat parameters for the tensor-core convolutions, re-cast only when a
+        parameter's version counter moved (torch optimisers update the views in place)."""
+        if self.precision != "bf16":
+            return None
+        stamp = self._flat._version + sum(p._version for p, _ in self._grad_views)
+        if self._shadow is None or self._shadow.device != self._flat.device:
+            self._shadow = torch.empty(self._flat.numel(), dtype=torch.bfloat16, device=self._flat.device)
+            self._shadow_stamp = None
+        if stamp != self._shadow_stamp:
+            _lib.check(_lib.lib.mmu_cast_f32_to_bf16(self._flat.data_ptr(), self._shadow.data_ptr(),
+                                                     self._flat.numel(), _lib.stream_ptr()),
+                       "mmu_cast_f32_to_bf16")
+            self._shadow_stamp = stamp
+        return self._shadow
+
+    def invalidate_shadow(self):
+        self._shadow_stamp = None
+
     def _rebind(self, flat, flat_grad, stats):
+        self._shadow, self._shadow_stamp = None, None
         self._flat, self._flat_grad, self._stats = flat, flat_grad, stats
         params = dict(self.named_parameters())
         self._grad_views = []
@@ -181,25 +207,28 @@ class MIMOResNet(nn.Module):
         cfg = self._config(x.shape[0])
         ws = self._workspace(cfg, training)
         logits = torch.empty(x.shape[0], self.out_dim, self.num_classes, device=x.device)
-        _lib.check(_lib.lib.mmu_resnet_forward(C.byref(cfg), self._flat.data_ptr(), self._stats.data_ptr(),
-                                               x.data_ptr(), ws.data_ptr(), ws.numel(), int(training),
-                                               logits.data_ptr(), _lib.stream_ptr()), "mmu_resnet_forward")
+        shadow = self._fresh_shadow()
+        _lib.check(_lib.lib.mmu_resnet_forward(C.byref(cfg), self._flat.data_ptr(), _lib.ptr(shadow),
+                                               self._stats.data_ptr(), x.data_ptr(), ws.data_ptr(),
+                                               ws.numel(), int(training), logits.data_ptr(),
+                                               _lib.stream_ptr()), "mmu_resnet_forward")
         if training:
             for m in self.modules():
                 nb = m._buffers.get("num_batches_tracked")
                 if nb is not None:
                     nb += 1
-        return cfg, ws, x, logits
+        return cfg, ws, x, shadow, logits
 
     _ensure_grad_views = FlavaFusionTransfomer._ensure_grad_views
 
     def _engine_backward(self, saved, dlogits):
-        cfg, ws, x, _ = saved
+        cfg, ws, x, shadow, _ = saved
         self._ensure_grad_views()
-        _lib.check(_lib.lib.mmu_resnet_backward(C.byref(cfg), self._flat.data_ptr(), self._stats.data_ptr(),
-                                                x.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                dlogits.data_ptr(), self._flat_grad.data_ptr(),
-                                                _lib.stream_ptr()), "mmu_resnet_backward")
+        _lib.check(_lib.lib.mmu_resnet_backward(C.byref(cfg), self._flat.data_ptr(), _lib.ptr(shadow),
+                                                self._stats.data_ptr(), x.data_ptr(), ws.data_ptr(),
+                                                ws.numel(), dlogits.data_ptr(),
+                                                self._flat_grad.data_ptr(), _lib.stream_ptr()),
+                   "mmu_resnet_backward")
 
     # -------------------------------------------------------------- reference protocol
     def forward(self, x):

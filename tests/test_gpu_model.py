@@ -478,3 +478,49 @@ def test_full_baseline_size_properties(mmu):
         opt.step()
         losses.append(float(loss.detach()))
     assert all(np.isfinite(losses)) and losses[1] < losses[0]
+
+
+def test_mimo_resnet_tensor_core_path(mmu, golden):
+    """MIMOResNet with precision='bf16': convolutions on the tcgen05 GEMM (bf16 operands, fp32
+    accumulation and BatchNorm).  bf16 tolerance: 6e-2 of max|logit|; 0.35 of max|grad| per tensor
+    on the golden (batch 4-6: bf16 rounding flips ReLU masks the golden's 2e-5 margin protects, and
+    BatchNorm over so few rows amplifies each flip); at batch 64 the gradients are held to the fp32
+    engine by cosine similarity >= 0.98 per tensor.  Batch 64 also exercises the CTA-pair kernel."""
+    c = golden("mimo_resnet.pt")
+    cfg = c["cfg"]
+    m = mmu.MIMOResNet(num_channels=1, emb_dim=4, out_dim=cfg["E"], num_classes=cfg["C"], precision="bf16")
+    m.load_state_dict(c["state_dict"], strict=True)
+    m.cuda().train()
+    m.zero_grad()
+    logits = m(c["x"].cuda())
+    loss = m.compute_loss(logits, c["y_train"].cuda())
+    loss.backward()
+    assert rel(logits.detach().cpu(), c["logits"]) < BF16_LOGIT_TOL
+    assert abs(float(loss.detach()) - float(c["loss"])) < BF16_LOGIT_TOL * abs(float(c["loss"]))
+    for k, p in m.named_parameters():
+        assert rel(p.grad.cpu(), c["grads"][k]) < 0.35, (k, rel(p.grad.cpu(), c["grads"][k]))
+    # batch 64: fp32 engine vs tensor-core engine on the same weights, then a few SGD steps
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(64, 4, 1, 14, 14, generator=g).cuda()
+    y = torch.randint(0, cfg["C"], (64, 1), generator=g).repeat(1, cfg["E"]).cuda()
+    ref = mmu.MIMOResNet(num_channels=1, emb_dim=4, out_dim=cfg["E"], num_classes=cfg["C"])
+    ref.load_state_dict(c["state_dict"], strict=True)
+    ref.cuda().train()
+    m.load_state_dict(c["state_dict"], strict=True)
+    assert rel(m(x).detach(), ref(x).detach()) < BF16_LOGIT_TOL
+    for net in (m, ref):
+        net.zero_grad()
+        net.compute_loss(net(x), y).backward()
+    for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        cos = torch.nn.functional.cosine_similarity(p.grad.flatten().double(), q.grad.flatten().double(), dim=0)
+        assert float(cos) >= 0.98, (k, float(cos))
+    m.load_state_dict(c["state_dict"], strict=True)
+    opt = torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        loss = m.compute_loss(m(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < losses[0]

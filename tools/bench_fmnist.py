@@ -17,6 +17,9 @@ out = {}
 for name, make, opt_fn in (
         ("MIMOResNet", lambda: mmu.MIMOResNet(num_channels=1, emb_dim=4, out_dim=E, num_classes=C),
          lambda m: torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9)),
+        ("MIMOResNet_bf16", lambda: mmu.MIMOResNet(num_channels=1, emb_dim=4, out_dim=E, num_classes=C,
+                                                   precision="bf16"),
+         lambda m: torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9)),
         ("MIMOTransfomer", lambda: mmu.MIMOTransfomer(out_dim=E, num_classes=C, hidden_size=768, precision="bf16"),
          lambda m: mmu.FusedAdamW(m.parameters(), lr=1e-3))):
     torch.manual_seed(42)
