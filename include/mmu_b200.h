@@ -274,6 +274,50 @@ MMU_API int mmu_resnet_backward(const mmu_resnet_config* cfg, const float* param
                         float* stats, const float* x, void* workspace, long long workspace_bytes,
                         const float* dlogits, float* grads, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * MMBT engine: reference src/mmbt.py:47-262 (ImageBertEmbeddings, MultimodalBertEncoder.forward /
+ * forward_img_only / forward_txt_only / forward_control, MultimodalBertClf) from the pooled image
+ * tokens onward.  The BERT arithmetic is that of the reference's un-vendored, unpinned dependency
+ * pytorch_pretrained_bert (call sites src/mmbt.py:13,90-96,124-128): post-LN blocks, LayerNorm
+ * eps 1e-12, erf-GELU, additive mask (1 - m) * -10000 (src/mmbt.py:103-107).  Flat fp32
+ * parameter / gradient buffers described by a table of reference state_dict names; the query /
+ * key / value tensors of a layer are adjacent (one [3D, D] GEMM).  logits: fp32 (B, C). */
+typedef struct {
+  int B, S_txt, n_img, d_img, D, n_head, n_layers, d_ff, vocab, max_pos, n_types, C;
+  int cls_id, sep_id; /* args.vocab.stoi["[CLS]"], ["[SEP]"] (src/mmbt.py:62-66) */
+  int precision;      /* 0 fp32 (parity path), 1 bf16 operands on tcgen05 */
+} mmu_mmbt_config;
+typedef struct {
+  const long long* txt;     /* (B, S_txt) token ids */
+  const long long* mask;    /* (B, S_txt) 1 = attend */
+  const long long* segment; /* (B, S_txt) token types */
+  const float* img;         /* (B, n_img, d_img): ImageEncoder output, src/mmbt.py:40-45 */
+  const int* indices;       /* device int32[n_sel] positions of [CLS img.. SEP | text..] that enter the
+                               encoder; NULL = all (forward).  img_only = first n_img + 2; txt_only =
+                               {0} + text; forward_control = {0} + sorted sample (src/mmbt.py:198-201) */
+  int n_sel;
+  const void* params_bf16;  /* optional bf16 shadow of params */
+  float* dimg;              /* backward: d loss / d img, or NULL */
+} mmu_mmbt_inputs;
+MMU_API long long mmu_mmbt_param_count(const mmu_mmbt_config* cfg);
+MMU_API int mmu_mmbt_param_table(const mmu_mmbt_config* cfg, mmu_param_entry* out /* host */, int max);
+MMU_API long long mmu_mmbt_workspace_bytes(const mmu_mmbt_config* cfg, int training);
+MMU_API int mmu_mmbt_forward(const mmu_mmbt_config* cfg, const float* params, const mmu_mmbt_inputs* in,
+                     void* workspace, long long workspace_bytes, int training, float* logits,
+                     void* stream);
+MMU_API int mmu_mmbt_backward(const mmu_mmbt_config* cfg, const float* params, const mmu_mmbt_inputs* in,
+                      void* workspace, long long workspace_bytes, const float* dlogits, float* grads,
+                      void* stream);
+/* BertAdam step over a flat buffer (pytorch_pretrained_bert.optimization.BertAdam as configured by
+ * train.py:136-147): per-tensor clip_grad_norm_(max_grad_norm) applied to g in place, m/v without
+ * bias correction, update = m / (sqrt(v) + eps) + decay * p, p -= lr * update.  segs: device
+ * int64[n_seg][2] (offset, numel); seg_hyper: device fp32[n_seg][2] = (weight decay, scheduled lr --
+ * the reference keeps state['step'] per tensor); norms: device fp32[n_seg] scratch. */
+MMU_API int mmu_bertadam_flat_step(float* p, float* g, float* m, float* v, void* p_bf16,
+                           const long long* segs, const float* seg_hyper, float* norms, int n_seg,
+                           long long max_seg_numel, float b1, float b2, float eps,
+                           float max_grad_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,14 +9,15 @@ everything numerical runs in ``libmmu_b200.so`` (hand-written CUDA, C ABI in
 """
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is missing)
 from . import ops  # noqa: F401
-from .src import (callbacks, dataset, framework, metrics, model, optim, parallel,  # noqa: F401
+from .src import (callbacks, dataset, framework, metrics, mmbt, model, optim, parallel,  # noqa: F401
                   robustness, training_loop, utils)
 from .src.framework import Model_  # noqa: F401
 from .src.metrics import acc  # noqa: F401
 from .src.model import (FlavaFusionTransfomer, FlavaFusionTransfomerwithCLSToken,  # noqa: F401
                         MIMOTransfomer)
 from .src.resnet import MIMOResNet  # noqa: F401
-from .src.optim import FusedAdamW, get_cosine_schedule_with_warmup  # noqa: F401
+from .src.mmbt import MultimodalBertClf  # noqa: F401
+from .src.optim import BertAdam, FusedAdamW, get_cosine_schedule_with_warmup  # noqa: F401
 
-__all__ = ["FlavaFusionTransfomer", "FlavaFusionTransfomerwithCLSToken", "MIMOTransfomer", "MIMOResNet", "Model_", "FusedAdamW",
+__all__ = ["FlavaFusionTransfomer", "FlavaFusionTransfomerwithCLSToken", "MIMOTransfomer", "MIMOResNet", "MultimodalBertClf", "Model_", "FusedAdamW", "BertAdam",
            "get_cosine_schedule_with_warmup", "acc", "ops"]

@@ -24,6 +24,8 @@ EXPORTS = [
     "mmu_resnet_param_count", "mmu_resnet_stat_count", "mmu_resnet_param_table",
     "mmu_resnet_stat_table", "mmu_resnet_workspace_bytes", "mmu_resnet_forward",
     "mmu_resnet_backward",
+    "mmu_mmbt_param_count", "mmu_mmbt_param_table", "mmu_mmbt_workspace_bytes", "mmu_mmbt_forward",
+    "mmu_mmbt_backward", "mmu_bertadam_flat_step",
 ]
 
 
@@ -72,6 +74,18 @@ class ParamEntry(C.Structure):
 
 class ResNetConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("B", "cin", "H", "W", "E", "C")]
+
+
+class MmbtConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("B", "S_txt", "n_img", "d_img", "D", "n_head", "n_layers",
+                                       "d_ff", "vocab", "max_pos", "n_types", "C", "cls_id",
+                                       "sep_id", "precision")]
+
+
+class MmbtInputs(C.Structure):
+    _fields_ = [("txt", C.c_void_p), ("mask", C.c_void_p), ("segment", C.c_void_p),
+                ("img", C.c_void_p), ("indices", C.c_void_p), ("n_sel", C.c_int),
+                ("params_bf16", C.c_void_p), ("dimg", C.c_void_p)]
 
 
 class FlavaInputs(C.Structure):
@@ -123,6 +137,13 @@ def _load():
     lib.mmu_flava_num_stages.argtypes = [cfgp]
     lib.mmu_flava_forward.argtypes = [cfgp, vp, C.POINTER(FlavaInputs), vp, ll, i, vp, vp]
     lib.mmu_flava_backward.argtypes = [cfgp, vp, C.POINTER(FlavaInputs), vp, ll, vp, vp, i, i, vp]
+    mcfgp, minp = C.POINTER(MmbtConfig), C.POINTER(MmbtInputs)
+    lib.mmu_mmbt_param_count.restype, lib.mmu_mmbt_param_count.argtypes = ll, [mcfgp]
+    lib.mmu_mmbt_param_table.argtypes = [mcfgp, C.POINTER(ParamEntry), i]
+    lib.mmu_mmbt_workspace_bytes.restype, lib.mmu_mmbt_workspace_bytes.argtypes = ll, [mcfgp, i]
+    lib.mmu_mmbt_forward.argtypes = [mcfgp, vp, minp, vp, ll, i, vp, vp]
+    lib.mmu_mmbt_backward.argtypes = [mcfgp, vp, minp, vp, ll, vp, vp, vp]
+    lib.mmu_bertadam_flat_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, ll, f, f, f, f, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:

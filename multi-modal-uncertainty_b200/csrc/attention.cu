@@ -504,9 +504,224 @@ int bwd(const void* qkv, const void* dout, const void* probs, float* scores, voi
                                   hd, B, store_epi(dq, 1, ld, 1.0f), H, hd, 3LL * D, st);
 }
 
+
+// ---------------------------------------------------------------- sequence-axis attention
+// BERT self-attention of the MMBT path (reference call site src/mmbt.py:124-128; arithmetic of
+// pytorch_pretrained_bert's BertSelfAttention): one S x S problem per (sample b, head h) over
+// rows (b, s), with the additive key mask (1 - m)(-10000) of src/mmbt.py:103-107.  Same batched
+// GEMMs as above with the roles of the batch and token axes swapped in the tensor maps.
+__global__ void __launch_bounds__(256)
+softmax_mask_rows_kernel(const float* __restrict__ S, const float* __restrict__ addmask,
+                         __nv_bfloat16* __restrict__ P, int rows, int n, int np, int rows_per_sample) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* s = S + static_cast<size_t>(row) * np;
+  const float* am = addmask + static_cast<size_t>(row / rows_per_sample) * n;
+  float m = -INFINITY;
+  for (int c = lane; c < n; c += 32) m = fmaxf(m, s[c] + am[c]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int c = lane; c < n; c += 32) sum += __expf(s[c] + am[c] - m);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  __nv_bfloat16* p = P + static_cast<size_t>(row) * np;
+  for (int c = lane; c < np; c += 32)
+    p[c] = __float2bfloat16_rn(c < n ? __expf(s[c] + am[c] - m) * inv : 0.f);
+}
+
+BatchedOperand qkv_view_seq(const void* qkv, int B, int S, int D, int H, int third, int mn) {
+  BatchedOperand o{};
+  o.base = qkv;
+  o.inner = 3LL * D; o.mid = B; o.outer = S;
+  o.mid_stride = 3LL * D * S; o.outer_stride = 3LL * D;
+  o.mn_major = mn; o.hdiv = H; o.hstride = D / H; o.col0 = third * D;
+  return o;
+}
+BatchedOperand act_view_seq(const void* x, int B, int S, int D, int H, int mn) {
+  BatchedOperand o{};
+  o.base = x;
+  o.inner = D; o.mid = B; o.outer = S;
+  o.mid_stride = static_cast<long long>(D) * S; o.outer_stride = D;
+  o.mn_major = mn; o.hdiv = H; o.hstride = D / H; o.col0 = 0;
+  return o;
+}
+
+int seq_fwd(const void* qkv, const float* addmask, void* out, void* probs, float* scores, int B, int S,
+            int D, int H, cudaStream_t st) {
+  const int hd = D / H, G = B * H, Sp = (S + 7) / 8 * 8;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  int rc = gemm_bf16_batched_launch(qkv_view_seq(qkv, B, S, D, H, 0, 0), qkv_view_seq(qkv, B, S, D, H, 1, 0),
+                                    G, S, Sp, hd, store_epi(scores, 0, Sp, scale), 1, 0,
+                                    static_cast<long long>(S) * Sp, st);
+  if (rc) return rc;
+  const int rows = G * S;
+  softmax_mask_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(
+      scores, addmask, static_cast<__nv_bfloat16*>(probs), rows, S, Sp, H * S);
+  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+  count_launch();
+  return gemm_bf16_batched_launch(sq_view(probs, G, S, Sp, 0), qkv_view_seq(qkv, B, S, D, H, 2, 1), G, S,
+                                  hd, S, store_epi(out, 1, D, 1.0f), H, hd,
+                                  static_cast<long long>(S) * D, st);
+}
+
+int seq_bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
+            void* dqkv, int B, int S, int D, int H, cudaStream_t st) {
+  const int hd = D / H, G = B * H, Sp = (S + 7) / 8 * 8;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  // dP = dO V^T
+  int rc = gemm_bf16_batched_launch(act_view_seq(dout, B, S, D, H, 0), qkv_view_seq(qkv, B, S, D, H, 2, 0),
+                                    G, S, Sp, hd, store_epi(scores, 0, Sp, 1.0f), 1, 0,
+                                    static_cast<long long>(S) * Sp, st);
+  if (rc) return rc;
+  const int rows = G * S;
+  softmax_bwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(
+      scores, static_cast<const __nv_bfloat16*>(probs), static_cast<__nv_bfloat16*>(dprobs), rows, S,
+      Sp, scale);
+  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+  count_launch();
+  __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(dqkv);
+  const long long ld = 3LL * D, mid = 3LL * D * S;
+  // dV = P^T dO ; dK = dS^T Q ; dQ = dS K
+  rc = gemm_bf16_batched_launch(sq_view(probs, G, S, Sp, 1), act_view_seq(dout, B, S, D, H, 1), G, S, hd,
+                                S, store_epi(dq + 2 * D, 1, ld, 1.0f), H, hd, mid, st);
+  if (rc) return rc;
+  rc = gemm_bf16_batched_launch(sq_view(dprobs, G, S, Sp, 1), qkv_view_seq(qkv, B, S, D, H, 0, 1), G, S,
+                                hd, S, store_epi(dq + D, 1, ld, 1.0f), H, hd, mid, st);
+  if (rc) return rc;
+  return gemm_bf16_batched_launch(sq_view(dprobs, G, S, Sp, 0), qkv_view_seq(qkv, B, S, D, H, 1, 1), G, S,
+                                  hd, S, store_epi(dq, 1, ld, 1.0f), H, hd, mid, st);
+}
+
 }  // namespace tc
 
+// fp32 parity path of the sequence-axis attention: one generic strided batched product
+//   C[g](m, n) = alpha * sum_k A[g](m, k) * B[g](n, k),   g -> (g / H, g % H)
+// (16 x 16 shared-memory tiles) covers S = Q K^T, O = P V and the four backward products.
+namespace seq32 {
+struct Strided {
+  const float* base;
+  long long s0, s1, sm, sk;  // element strides: g / H, g % H, row (m or n), reduction index
+};
+__global__ void __launch_bounds__(256)
+bgemm_kernel(Strided A, Strided Bm, float* __restrict__ C, long long c0, long long c1, long long cm,
+             int M, int N, int K, int H, float alpha) {
+  __shared__ float As[16][17], Bs[16][17];
+  const int g = blockIdx.z;
+  const float* a = A.base + (g / H) * A.s0 + (g % H) * A.s1;
+  const float* b = Bm.base + (g / H) * Bm.s0 + (g % H) * Bm.s1;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 16, n0 = blockIdx.x * 16;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const int ka = k0 + tx;
+    As[ty][tx] = (m0 + ty < M && ka < K) ? a[(m0 + ty) * A.sm + ka * A.sk] : 0.f;
+    Bs[ty][tx] = (n0 + ty < N && ka < K) ? b[(n0 + ty) * Bm.sm + ka * Bm.sk] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(As[ty][k], Bs[tx][k], acc);
+    __syncthreads();
+  }
+  if (m0 + ty < M && n0 + tx < N)
+    C[(g / H) * c0 + (g % H) * c1 + (m0 + ty) * cm + n0 + tx] = alpha * acc;
+}
+int bgemm(const Strided& A, const Strided& B, float* C, long long c0, long long c1, long long cm, int G,
+          int M, int N, int K, int H, float alpha, cudaStream_t st) {
+  dim3 grid((N + 15) / 16, (M + 15) / 16, G);
+  bgemm_kernel<<<grid, 256, 0, st>>>(A, B, C, c0, c1, cm, M, N, K, H, alpha);
+  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+  count_launch();
+  return 0;
+}
+__global__ void __launch_bounds__(256)
+softmax_mask_kernel(float* __restrict__ P, const float* __restrict__ addmask, int rows, int n,
+                    int rows_per_sample) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float* s = P + static_cast<size_t>(row) * n;
+  const float* am = addmask + static_cast<size_t>(row / rows_per_sample) * n;
+  float m = -INFINITY;
+  for (int c = lane; c < n; c += 32) m = fmaxf(m, s[c] + am[c]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int c = lane; c < n; c += 32) sum += expf(s[c] + am[c] - m);
+  sum = warp_sum(sum);
+  for (int c = lane; c < n; c += 32) s[c] = expf(s[c] + am[c] - m) / sum;
+}
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(float* __restrict__ dP, const float* __restrict__ P, int rows, int n, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float* g = dP + static_cast<size_t>(row) * n;
+  const float* p = P + static_cast<size_t>(row) * n;
+  float delta = 0.f;
+  for (int c = lane; c < n; c += 32) delta += g[c] * p[c];
+  delta = warp_sum(delta);
+  for (int c = lane; c < n; c += 32) g[c] = p[c] * (g[c] - delta) * scale;
+}
+}  // namespace seq32
+
 }  // namespace attn
+
+int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, float* scores,
+                      int dtype, int B, int S, int D, int H, cudaStream_t stream) {
+  using namespace attn;
+  if (qkv == nullptr || addmask == nullptr || out == nullptr || probs == nullptr) return MMU_ERR_ARG;
+  if (B < 1 || S < 1 || H < 1 || D % H != 0) return MMU_ERR_SHAPE;
+  if (dtype == DT_BF16) {
+    if ((D / H) % 64 != 0 || scores == nullptr) return MMU_ERR_SHAPE;
+    return tc::seq_fwd(qkv, addmask, out, probs, scores, B, S, D, H, stream);
+  }
+  using seq32::Strided;
+  const int hd = D / H, G = B * H;
+  const float* q = static_cast<const float*>(qkv);
+  float* P = static_cast<float*>(probs);
+  const long long SS = static_cast<long long>(S) * S;
+  const Strided Q{q, 3LL * D * S, hd, 3LL * D, 1}, Kk{q + D, 3LL * D * S, hd, 3LL * D, 1};
+  if (int rc = seq32::bgemm(Q, Kk, P, H * SS, SS, S, G, S, S, hd, H, 1.0f / sqrtf(static_cast<float>(hd)), stream))
+    return rc;
+  const int rows = G * S;
+  seq32::softmax_mask_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(P, addmask, rows, S, H * S);
+  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+  count_launch();
+  const Strided Pm{P, H * SS, SS, S, 1}, V{q + 2 * D, 3LL * D * S, hd, 1, 3LL * D};
+  return seq32::bgemm(Pm, V, static_cast<float*>(out), static_cast<long long>(S) * D, hd, D, G, S, hd, S, H,
+                      1.0f, stream);
+}
+
+int seq_attention_bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
+                      void* dqkv, int dtype, int B, int S, int D, int H, cudaStream_t stream) {
+  using namespace attn;
+  if (qkv == nullptr || dout == nullptr || probs == nullptr || scores == nullptr || dqkv == nullptr)
+    return MMU_ERR_ARG;
+  if (dtype == DT_BF16) {
+    if ((D / H) % 64 != 0 || dprobs == nullptr) return MMU_ERR_SHAPE;
+    return tc::seq_bwd(qkv, dout, probs, scores, dprobs, dqkv, B, S, D, H, stream);
+  }
+  using seq32::Strided;
+  const int hd = D / H, G = B * H;
+  const float* q = static_cast<const float*>(qkv);
+  const float* P = static_cast<const float*>(probs);
+  const float* dO = static_cast<const float*>(dout);
+  float* dq = static_cast<float*>(dqkv);
+  float* dS = scores;  // fp32 [G][S][S] scratch
+  const long long SS = static_cast<long long>(S) * S, q0 = 3LL * D * S;
+  const Strided dOv{dO, static_cast<long long>(S) * D, hd, D, 1}, Vn{q + 2 * D, q0, hd, 3LL * D, 1};
+  if (int rc = seq32::bgemm(dOv, Vn, dS, H * SS, SS, S, G, S, S, hd, H, 1.0f, stream)) return rc;
+  const int rows = G * S;
+  seq32::softmax_bwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(dS, P, rows, S,
+                                                               1.0f / sqrtf(static_cast<float>(hd)));
+  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+  count_launch();
+  const Strided Pt{P, H * SS, SS, 1, S}, dOt{dO, static_cast<long long>(S) * D, hd, 1, D};
+  if (int rc = seq32::bgemm(Pt, dOt, dq + 2 * D, q0, hd, 3LL * D, G, S, hd, S, H, 1.0f, stream)) return rc;
+  const Strided dSt{dS, H * SS, SS, 1, S}, Qt{q, q0, hd, 1, 3LL * D};
+  if (int rc = seq32::bgemm(dSt, Qt, dq + D, q0, hd, 3LL * D, G, S, hd, S, H, 1.0f, stream)) return rc;
+  const Strided dSn{dS, H * SS, SS, S, 1}, Kt{q + D, q0, hd, 1, 3LL * D};
+  return seq32::bgemm(dSn, Kt, dq, q0, hd, 3LL * D, G, S, hd, S, H, 1.0f, stream);
+}
 
 int attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* scores, int dtype,
                   int B, int L, int D, int H, cudaStream_t stream) {

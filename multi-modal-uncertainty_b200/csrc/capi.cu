@@ -6,6 +6,7 @@
 #include "engine.h"
 #include "gemm_api.h"
 #include "kernels.h"
+#include "mmbt.h"
 #include "resnet.h"
 
 using namespace mmu;
@@ -15,6 +16,8 @@ static_assert(sizeof(mmu_flava_config) == sizeof(FlavaConfig), "config layout");
 static_assert(sizeof(mmu_resnet_config) == sizeof(ResNetConfig), "resnet config layout");
 static_assert(sizeof(mmu_posthoc_accum) == sizeof(PosthocAccum), "post-hoc accumulator layout");
 static_assert(sizeof(mmu_param_entry) == sizeof(ParamEntry), "param entry layout");
+static_assert(sizeof(mmu_mmbt_config) == sizeof(MmbtConfig), "mmbt config layout");
+static_assert(sizeof(mmu_mmbt_inputs) == sizeof(MmbtInputs), "mmbt inputs layout");
 static_assert(sizeof(mmu_flava_inputs) == sizeof(FlavaInputs), "inputs layout");
 
 namespace {
@@ -45,6 +48,8 @@ int mmu_struct_size(int which) {
     case 3: return static_cast<int>(sizeof(mmu_metric_accum));
     case 4: return static_cast<int>(sizeof(mmu_param_entry));
     case 5: return static_cast<int>(sizeof(mmu_posthoc_accum));
+    case 6: return static_cast<int>(sizeof(mmu_mmbt_config));
+    case 7: return static_cast<int>(sizeof(mmu_mmbt_inputs));
     default: return -1;
   }
 }
@@ -232,6 +237,50 @@ int mmu_resnet_backward(const mmu_resnet_config* cfg, const float* params, const
   if (cfg == nullptr) return MMU_ERR_ARG;
   return resnet_backward(rcfg_of(cfg), params, params_bf16, stats, x, workspace, workspace_bytes,
                          dlogits, grads, S(stream));
+}
+
+namespace {
+inline MmbtConfig mcfg_of(const mmu_mmbt_config* c) {
+  MmbtConfig r;
+  std::memcpy(&r, c, sizeof(r));
+  return r;
+}
+inline MmbtInputs min_of(const mmu_mmbt_inputs* i) {
+  MmbtInputs r;
+  std::memcpy(&r, i, sizeof(r));
+  return r;
+}
+}  // namespace
+
+long long mmu_mmbt_param_count(const mmu_mmbt_config* cfg) {
+  return cfg == nullptr ? MMU_ERR_ARG : mmbt_param_count(mcfg_of(cfg));
+}
+int mmu_mmbt_param_table(const mmu_mmbt_config* cfg, mmu_param_entry* out, int max) {
+  if (cfg == nullptr) return MMU_ERR_ARG;
+  return mmbt_param_table(mcfg_of(cfg), reinterpret_cast<ParamEntry*>(out), max);
+}
+long long mmu_mmbt_workspace_bytes(const mmu_mmbt_config* cfg, int training) {
+  return cfg == nullptr ? MMU_ERR_ARG : mmbt_workspace_bytes(mcfg_of(cfg), training);
+}
+int mmu_mmbt_forward(const mmu_mmbt_config* cfg, const float* params, const mmu_mmbt_inputs* in,
+                     void* workspace, long long workspace_bytes, int training, float* logits,
+                     void* stream) {
+  if (cfg == nullptr || in == nullptr) return MMU_ERR_ARG;
+  return mmbt_forward(mcfg_of(cfg), params, min_of(in), workspace, workspace_bytes, training, logits,
+                      S(stream));
+}
+int mmu_mmbt_backward(const mmu_mmbt_config* cfg, const float* params, const mmu_mmbt_inputs* in,
+                      void* workspace, long long workspace_bytes, const float* dlogits, float* grads,
+                      void* stream) {
+  if (cfg == nullptr || in == nullptr) return MMU_ERR_ARG;
+  return mmbt_backward(mcfg_of(cfg), params, min_of(in), workspace, workspace_bytes, dlogits, grads,
+                       S(stream));
+}
+int mmu_bertadam_flat_step(float* p, float* g, float* m, float* v, void* p_bf16, const long long* segs,
+                           const float* seg_hyper, float* norms, int n_seg, long long max_seg_numel,
+                           float b1, float b2, float eps, float max_grad_norm, void* stream) {
+  return bertadam_flat(p, g, m, v, p_bf16, segs, seg_hyper, norms, n_seg, max_seg_numel, b1, b2, eps,
+                       max_grad_norm, S(stream));
 }
 
 }  // extern "C"

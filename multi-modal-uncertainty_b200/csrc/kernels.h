@@ -39,6 +39,18 @@ int layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* mea
                   cudaStream_t stream);
 int colsum_accumulate(const void* x, int dtype, float* out, int M, int N, cudaStream_t stream);
 
+// ---- post-LN residual blocks (BERT encoder of the MMBT path, reference src/mmbt.py:90-128;
+// arithmetic of pytorch_pretrained_bert's BertSelfOutput / BertOutput / BertLayerNorm, eps 1e-12)
+// s_out (fp32, may be null) = x_in + y (both `dtype`; y may be null); h = LN(s; gamma, beta, eps).
+int postln_fwd(const void* x_in, const void* y, float* s_out, const float* gamma, const float* beta,
+               void* h, int dtype, float* mean, float* rstd, int M, int D, float eps,
+               cudaStream_t stream);
+// dx (fp32) and dx_lp (`dtype`, may be null; with dtype fp32 pass null) = LN'(dy_branch + dy_res);
+// dy_branch (`dtype`) or dy_res (fp32) may be null.  dgamma / dbeta / dcolsum(dx) accumulate.
+int postln_bwd(const void* dy_branch, const float* dy_res, int dtype, const float* x, const float* mean,
+               const float* rstd, const float* gamma, float* dx, void* dx_lp, float* dgamma,
+               float* dbeta, float* dcolsum, int M, int D, cudaStream_t stream);
+
 // ---- heads: LayerNorm(ln_post) + row gather / segment mean pooling + E small Linears
 struct HeadSegments {
   int E;
@@ -83,6 +95,17 @@ int attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* sc
 int attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                   float* delta_ws, const void* probs, float* scores, void* dprobs, void* dqkv,
                   int dtype, int B, int L, int D, int H, cudaStream_t stream);
+
+// ---- sequence-axis attention (BERT encoder of the MMBT path; reference call site
+// src/mmbt.py:124-128 with the additive mask of :103-107).  qkv (dtype) [B*S, 3D] packed q|k|v,
+// addmask fp32 [B, S] = (1 - mask) * -10000, out (dtype) [B*S, D].
+// bf16 (head_dim % 64 == 0): batched tcgen05 GEMMs; probs bf16 [B*H, S, Sp] kept for the backward,
+// scores fp32 / dprobs bf16 scratch of the same shape (Sp = S rounded up to 8).
+// fp32: probs fp32 [B*H, S, S] kept for the backward, scores fp32 scratch (backward only).
+int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, float* scores,
+                      int dtype, int B, int S, int D, int H, cudaStream_t stream);
+int seq_attention_bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
+                      void* dqkv, int dtype, int B, int S, int D, int H, cudaStream_t stream);
 
 // ---- fused softmax-CE / accuracy / uncertainty / calibration-histogram epilogue
 struct MetricAccum {  // lives in device memory; all-reduced (sum) across ranks

@@ -117,7 +117,7 @@ struct RowRegs {
 
 template <int NV>
 __device__ __forceinline__ void row_stats(const RowRegs<NV>& r, int nvec, int lane, int D,
-                                          float& mean, float& rstd) {
+                                          float& mean, float& rstd, float eps = 1e-5f) {
   mean = warp_sum(r.sum()) / D;
   float ss = 0.f;
 #pragma unroll
@@ -128,7 +128,7 @@ __device__ __forceinline__ void row_stats(const RowRegs<NV>& r, int nvec, int la
       ss += (a * a + b * b) + (c * c + d * d);
     }
   }
-  rstd = rsqrtf(warp_sum(ss) / D + 1e-5f);
+  rstd = rsqrtf(warp_sum(ss) / D + eps);
 }
 
 template <int NV, typename TO>
@@ -271,6 +271,59 @@ add_layernorm_fwd_kernel(const float* __restrict__ x_in, const TY* __restrict__ 
   }
 }
 
+// Post-LN residual (BERT, pytorch_pretrained_bert BertSelfOutput / BertOutput; reference call
+// site src/mmbt.py:124-128): s = x_in + y with x_in the previous LayerNorm output in the ACTIVATION
+// dtype, s kept in fp32 for the backward, h = LayerNorm(s; eps) in the activation dtype.
+// y == nullptr: plain LayerNorm of x_in.
+template <int NV, typename T>
+__global__ void __launch_bounds__(THREADS)
+postln_fwd_kernel(const T* __restrict__ x_in, const T* __restrict__ y, float* __restrict__ s_out,
+                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                  T* __restrict__ h, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                  int M, int D, float eps) {
+  ptx::pdl_trigger();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D >> 2;
+  for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
+    RowRegs<NV> r, ry;
+    r.load(x_in + static_cast<size_t>(row) * D, nvec, lane);
+    if (y != nullptr) {
+      ry.load(y + static_cast<size_t>(row) * D, nvec, lane);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        r.v[i].x += ry.v[i].x; r.v[i].y += ry.v[i].y; r.v[i].z += ry.v[i].z; r.v[i].w += ry.v[i].w;
+      }
+    }
+    if (s_out != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nvec) *reinterpret_cast<float4*>(s_out + static_cast<size_t>(row) * D + 4 * c) = r.v[i];
+      }
+    }
+    float mean, rstd;
+    row_stats<NV>(r, nvec, lane, D, mean, rstd, eps);
+    if (lane == 0 && mean_out != nullptr) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c);
+        const float4 b = *reinterpret_cast<const float4*>(beta + 4 * c);
+        float4 o;
+        o.x = (r.v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (r.v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (r.v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (r.v[i].w - mean) * rstd * g.w + b.w;
+        Vec4<T>::st(h + static_cast<size_t>(row) * D + 4 * c, o);
+      }
+    }
+  }
+}
+
 // Reduce per-warp column partials (acc[NV] float4 per lane) across the block's warps and
 // atomically add into out[D].  `red` is WARPS*D floats of shared memory.
 template <int NV>
@@ -379,6 +432,80 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x,
         o.w = prev.w + rs * (d.w - s1 - xv.w * s2);
         *reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * D + 4 * c) = o;
         if (dx_lp != nullptr) Vec4<TLP>::st(dx_lp + static_cast<size_t>(row) * D + 4 * c, o);
+        acc_c[i].x += o.x; acc_c[i].y += o.y; acc_c[i].z += o.z; acc_c[i].w += o.w;
+      }
+    }
+  }
+  block_colreduce_n<NV, LNB_WARPS>(acc_g, red, dgamma, nvec, D);
+  block_colreduce_n<NV, LNB_WARPS>(acc_b, red, dbeta, nvec, D);
+  if (dcolsum != nullptr) block_colreduce_n<NV, LNB_WARPS>(acc_c, red, dcolsum, nvec, D);
+}
+
+// Post-LN backward: dx = LN'(dy_branch + dy_res) where dy_branch (activation dtype, may be null)
+// is the gradient arriving through the sub-layer's first GEMM and dy_res (fp32, may be null) the
+// gradient arriving through the residual connection -- their sum is never materialised.
+// Writes dx (fp32) and its activation-dtype copy, accumulates dgamma / dbeta and the column sum of
+// dx (= bias gradient of the projection that closed the sub-layer).
+template <int NV, typename T>
+__global__ void __launch_bounds__(LNB_THREADS, 3)
+postln_bwd_kernel(const T* __restrict__ dy_branch, const float* __restrict__ dy_res,
+                  const float* __restrict__ x, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, const float* __restrict__ gamma,
+                  float* __restrict__ dx, T* __restrict__ dx_lp, float* __restrict__ dgamma,
+                  float* __restrict__ dbeta, float* __restrict__ dcolsum, int M, int D) {
+  ptx::pdl_trigger();
+  extern __shared__ float red[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D >> 2;
+  float4 acc_g[NV], acc_b[NV], acc_c[NV];
+  zero_acc<NV>(acc_g);
+  zero_acc<NV>(acc_b);
+  zero_acc<NV>(acc_c);
+  for (int row = blockIdx.x * LNB_WARPS + warp; row < M; row += gridDim.x * LNB_WARPS) {
+    RowRegs<NV> rx, rdy, rr;
+    rx.load(x + static_cast<size_t>(row) * D, nvec, lane);
+    if (dy_branch != nullptr) rdy.load(dy_branch + static_cast<size_t>(row) * D, nvec, lane);
+    else zero_acc<NV>(rdy.v);
+    if (dy_res != nullptr) {
+      rr.load(dy_res + static_cast<size_t>(row) * D, nvec, lane);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        rdy.v[i].x += rr.v[i].x; rdy.v[i].y += rr.v[i].y; rdy.v[i].z += rr.v[i].z; rdy.v[i].w += rr.v[i].w;
+      }
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c);
+        float4& xv = rx.v[i];
+        xv.x = (xv.x - mu) * rs; xv.y = (xv.y - mu) * rs;
+        xv.z = (xv.z - mu) * rs; xv.w = (xv.w - mu) * rs;
+        float4& d = rdy.v[i];
+        acc_g[i].x += d.x * xv.x; acc_g[i].y += d.y * xv.y;
+        acc_g[i].z += d.z * xv.z; acc_g[i].w += d.w * xv.w;
+        acc_b[i].x += d.x; acc_b[i].y += d.y; acc_b[i].z += d.z; acc_b[i].w += d.w;
+        d.x *= g.x; d.y *= g.y; d.z *= g.z; d.w *= g.w;
+        s1 += (d.x + d.y) + (d.z + d.w);
+        s2 += (d.x * xv.x + d.y * xv.y) + (d.z * xv.z + d.w * xv.w);
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 d = rdy.v[i], xv = rx.v[i];
+        float4 o;
+        o.x = rs * (d.x - s1 - xv.x * s2);
+        o.y = rs * (d.y - s1 - xv.y * s2);
+        o.z = rs * (d.z - s1 - xv.z * s2);
+        o.w = rs * (d.w - s1 - xv.w * s2);
+        *reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * D + 4 * c) = o;
+        if (dx_lp != nullptr) Vec4<T>::st(dx_lp + static_cast<size_t>(row) * D + 4 * c, o);
         acc_c[i].x += o.x; acc_c[i].y += o.y; acc_c[i].z += o.z; acc_c[i].w += o.w;
       }
     }
@@ -897,6 +1024,50 @@ int layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* mea
                             static_cast<bf*>(dx_lp), dgamma, dbeta, dcolsum, M, D)));
   } else {
     return MMU_ERR_ARG;
+  }
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int postln_fwd(const void* x_in, const void* y, float* s_out, const float* gamma, const float* beta,
+               void* h, int dtype, float* mean, float* rstd, int M, int D, float eps,
+               cudaStream_t stream) {
+  const int nv = nv_for(D);
+  if (nv < 0) return MMU_ERR_SHAPE;
+  if (M <= 0) return 0;
+  const int grid = grid_for(M, WARPS);
+  if (dtype == DT_BF16) {
+    using T = __nv_bfloat16;
+    MMU_NV_DISPATCH(nv, (postln_fwd_kernel<NV, T><<<grid, THREADS, 0, stream>>>(
+                            static_cast<const T*>(x_in), static_cast<const T*>(y), s_out, gamma, beta,
+                            static_cast<T*>(h), mean, rstd, M, D, eps)));
+  } else {
+    MMU_NV_DISPATCH(nv, (postln_fwd_kernel<NV, float><<<grid, THREADS, 0, stream>>>(
+                            static_cast<const float*>(x_in), static_cast<const float*>(y), s_out, gamma,
+                            beta, static_cast<float*>(h), mean, rstd, M, D, eps)));
+  }
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int postln_bwd(const void* dy_branch, const float* dy_res, int dtype, const float* x, const float* mean,
+               const float* rstd, const float* gamma, float* dx, void* dx_lp, float* dgamma,
+               float* dbeta, float* dcolsum, int M, int D, cudaStream_t stream) {
+  const int nv = nv_for(D);
+  if (nv < 0) return MMU_ERR_SHAPE;
+  if (M <= 0) return 0;
+  int grid = (M + LNB_WARPS - 1) / LNB_WARPS;
+  if (grid > sm_count() * 3) grid = sm_count() * 3;
+  const size_t smem = static_cast<size_t>(LNB_WARPS) * D * sizeof(float);
+  if (dtype == DT_BF16) {
+    using T = __nv_bfloat16;
+    MMU_NV_DISPATCH(nv, (postln_bwd_kernel<NV, T><<<grid, LNB_THREADS, smem, stream>>>(
+                            static_cast<const T*>(dy_branch), dy_res, x, mean, rstd, gamma, dx,
+                            static_cast<T*>(dx_lp), dgamma, dbeta, dcolsum, M, D)));
+  } else {
+    MMU_NV_DISPATCH(nv, (postln_bwd_kernel<NV, float><<<grid, LNB_THREADS, smem, stream>>>(
+                            static_cast<const float*>(dy_branch), dy_res, x, mean, rstd, gamma, dx,
+                            static_cast<float*>(dx_lp), dgamma, dbeta, dcolsum, M, D)));
   }
   MMU_CHECK_LAUNCH();
   return 0;

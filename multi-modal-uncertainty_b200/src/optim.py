@@ -92,6 +92,144 @@ class FusedAdamW(torch.optim.Optimizer):
             self._step = int(float(st["step"]))
 
 
+def warmup_linear(x, warmup=0.002):
+    """pytorch_pretrained_bert.optimization.warmup_linear (the ``schedule`` BertAdam defaults to)."""
+    if x < warmup:
+        return x / warmup
+    return 1.0 - x
+
+
+class BertAdam(torch.optim.Optimizer):
+    """Drop-in for ``pytorch_pretrained_bert.BertAdam`` as the reference configures it for MMBT
+    (``train.py:136-147``: two parameter groups, weight decay 0.01 / 0, ``lr``, ``warmup``,
+    ``t_total``), as ONE fused update per flat buffer (``mmu_bertadam_flat_step``): per-tensor
+    ``clip_grad_norm_(p, max_grad_norm)``, Adam moments without bias correction, weight decay added
+    to the update, ``lr * warmup_linear(step / t_total, warmup)`` with ``state['step']`` kept per
+    tensor.  Parameters with ``requires_grad == False`` are skipped, as tensors whose ``.grad`` is
+    ``None`` are in the reference (the frozen epochs of ``src/framework.py:246-285``).  Every
+    parameter must be flat-buffer backed (an mmu_b200 model); there is no per-tensor fallback."""
+
+    def __init__(self, params, lr, warmup=-1, t_total=-1, schedule="warmup_linear", b1=0.9, b2=0.999,
+                 e=1e-6, weight_decay=0.01, max_grad_norm=1.0):
+        if schedule != "warmup_linear":
+            raise ValueError("only the 'warmup_linear' schedule (the reference's) is implemented")
+        defaults = dict(lr=lr, schedule=schedule, warmup=warmup, t_total=t_total, b1=b1, b2=b2, e=e,
+                        weight_decay=weight_decay, max_grad_norm=max_grad_norm)
+        super().__init__(params, defaults)
+        self._owners = []
+        for g in self.param_groups:
+            for p in g["params"]:
+                owner = getattr(p, "_mmu_owner", None)
+                if owner is None:
+                    raise ValueError("BertAdam needs flat-buffer backed parameters of mmu_b200 models")
+                if not any(owner is o for o in self._owners):
+                    self._owners.append(owner)
+        self._mv = {}
+        self._seg_cache = {}
+        self._steps = {}
+        self.grad_scale = 1.0
+
+    def _moments(self, owner):
+        flat = owner._flat
+        mv = self._mv.get(id(owner))
+        if mv is None or mv[0].device != flat.device:
+            new = (torch.zeros_like(flat), torch.zeros_like(flat))
+            if mv is not None:
+                new[0].copy_(mv[0])
+                new[1].copy_(mv[1])
+            mv = self._mv[id(owner)] = new
+        return mv
+
+    def zero_grad(self, set_to_none: bool = False):
+        for o in self._owners:
+            o._flat_grad.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        import ctypes as C  # noqa: F401
+        from ._backend import _lib
+        for owner in self._owners:
+            flat = owner._flat
+            active = [(p, g) for g in self.param_groups for p in g["params"]
+                      if getattr(p, "_mmu_owner", None) is owner and p.requires_grad]
+            if not active:
+                continue
+            key = (id(owner), flat.data_ptr(), tuple(id(p) for p, _ in active))
+            cached = self._seg_cache.get(key)
+            if cached is None:
+                segs = torch.tensor([[(p.data_ptr() - flat.data_ptr()) // 4, p.numel()] for p, _ in active],
+                                    dtype=torch.int64, device=flat.device)
+                host = torch.empty(len(active), 2, dtype=torch.float32).pin_memory()
+                cached = self._seg_cache[key] = (
+                    segs, host, torch.empty(len(active), 2, dtype=torch.float32, device=flat.device),
+                    torch.empty(len(active), dtype=torch.float32, device=flat.device),
+                    max(p.numel() for p, _ in active))
+            segs, host, hyper, norms, max_numel = cached
+            for i, (p, g) in enumerate(active):
+                st = self._steps.get(id(p), 0)
+                if g["t_total"] != -1:
+                    lr = g["lr"] * warmup_linear(st / g["t_total"], g["warmup"])
+                else:
+                    lr = g["lr"]
+                host[i, 0] = g["weight_decay"]
+                host[i, 1] = lr
+                self._steps[id(p)] = st + 1
+            hyper.copy_(host, non_blocking=True)
+            g0 = self.param_groups[0]
+            m, v = self._moments(owner)
+            shadow = getattr(owner, "_shadow", None)
+            if shadow is not None and shadow.device != flat.device:
+                shadow = None
+            _lib.check(_lib.lib.mmu_bertadam_flat_step(
+                flat.data_ptr(), owner._flat_grad.data_ptr(), m.data_ptr(), v.data_ptr(), _lib.ptr(shadow),
+                segs.data_ptr(), hyper.data_ptr(), norms.data_ptr(), len(active), max_numel,
+                g0["b1"], g0["b2"], g0["e"], g0["max_grad_norm"], _lib.stream_ptr()),
+                "mmu_bertadam_flat_step")
+            if shadow is not None:
+                if len(active) == len(list(owner._param_list)):
+                    owner._shadow_stamp = owner._param_stamp()
+                else:
+                    owner.invalidate_shadow()
+
+    def state_dict(self):
+        state, groups, idx = {}, [], 0
+        for g in self.param_groups:
+            ids = []
+            for p in g["params"]:
+                owner = p._mmu_owner
+                m, v = self._moments(owner)
+                off = (p.data_ptr() - owner._flat.data_ptr()) // 4
+                n = p.numel()
+                state[idx] = {"step": self._steps.get(id(p), 0),
+                              "next_m": m[off:off + n].view(p.shape).clone(),
+                              "next_v": v[off:off + n].view(p.shape).clone()}
+                ids.append(idx)
+                idx += 1
+            gg = {k: val for k, val in g.items() if k != "params"}
+            gg["params"] = ids
+            groups.append(gg)
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        idx = 0
+        for g, sg in zip(self.param_groups, sd["param_groups"]):
+            for k, val in sg.items():
+                if k != "params":
+                    g[k] = val
+            for p in g["params"]:
+                st = sd["state"].get(idx)
+                idx += 1
+                if st is None:
+                    continue
+                owner = p._mmu_owner
+                m, v = self._moments(owner)
+                off = (p.data_ptr() - owner._flat.data_ptr()) // 4
+                n = p.numel()
+                m[off:off + n].view(p.shape).copy_(st["next_m"])
+                v[off:off + n].view(p.shape).copy_(st["next_v"])
+                self._steps[id(p)] = int(st["step"])
+
+
 def cosine_with_warmup_lambda(num_warmup_steps, num_training_steps, num_cycles=0.5):
     def fn(current_step):
         if current_step < num_warmup_steps:

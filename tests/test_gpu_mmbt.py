@@ -1,0 +1,187 @@
+"""MMBT path (reference src/mmbt.py) on the CUDA engine, through the reference-shaped Python API and
+the C ABI, against goldens produced by the UNMODIFIED reference module (tests/golden/
+make_golden_mmbt.py; BERT arithmetic restated from the absent third-party package, see
+oracle/bert_restated.py) and against the CPU oracle.
+
+Tolerances: fp32 path 1e-3 relative on logits / loss / gradients, argmax bit-exact; bf16 tensor-core
+path 6e-2 of max|logit| and 0.2 of max|grad| per tensor (as for the fusion model)."""
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16_LOGIT_TOL = 6e-2
+BF16_GRAD_TOL = 0.2
+
+
+@pytest.fixture(scope="module")
+def mmu():
+    import mmu_b200
+    return mmu_b200
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def make_args(cfg, precision):
+    vocab = types.SimpleNamespace(stoi={"[CLS]": cfg["cls_id"], "[SEP]": cfg["sep_id"], "[PAD]": 0})
+    return types.SimpleNamespace(
+        bert_model="golden", hidden_sz=cfg["D"], img_hidden_sz=cfg["d_img"], num_image_embeds=cfg["n_img"],
+        img_embed_pool_type="avg", dropout=0.0, n_classes=cfg["C"], vocab=vocab, precision=precision,
+        img_encoder=None,
+        bert_config=dict(vocab=cfg["vocab"], D=cfg["D"], n_head=cfg["n_head"], n_layers=cfg["n_layers"],
+                         d_ff=cfg["d_ff"], max_pos=cfg["max_pos"], n_types=cfg["n_types"], init_range=0.02))
+
+
+def build(mmu, c, precision):
+    m = mmu.MultimodalBertClf(make_args(c["cfg"], precision))
+    m.load_state_dict(c["state_dict"], strict=True)  # reference keys incl. the shared embedding aliases
+    return m.cuda()
+
+
+@pytest.mark.parametrize("name", ["fp32_small", "hd64"])
+def test_fp32_forward_variants_match_reference(mmu, golden, name):
+    c = golden("mmbt_small.pt")[name]
+    m = build(mmu, c, "fp32").eval()
+    x = [c[k].cuda() for k in ("txt", "mask", "segment", "img_tokens")]
+    with torch.no_grad():
+        for fn, key in ((m, "logits_full"), (m.forward_img_only, "logits_img_only"),
+                        (m.forward_txt_only, "logits_txt_only")):
+            out = fn(*x).cpu()
+            assert rel(out, c[key]) < 1e-3, key
+            assert torch.equal(out.argmax(-1), c[key].argmax(-1)), key
+        for modal, d in c["control"].items():
+            torch.manual_seed(d["seed"])  # forward_control draws with the host RNG, as the reference
+            out = m.forward_control(*x, modal).cpu()
+            assert rel(out, d["logits"]) < 1e-3, modal
+            out2 = m.forward_indices(*x, [int(i) for i in d["indices"]]).cpu()
+            assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("name", ["fp32_small", "hd64"])
+def test_fp32_loss_and_gradients_match_reference(mmu, golden, name):
+    c = golden("mmbt_small.pt")[name]
+    m = build(mmu, c, "fp32").train()
+    m.zero_grad()
+    tokens = c["img_tokens"].cuda().requires_grad_(True)
+    logits = m(c["txt"].cuda(), c["mask"].cuda(), c["segment"].cuda(), tokens)
+    loss = m.compute_loss(logits, c["y"].cuda())
+    loss.backward()
+    assert rel(logits.detach().cpu(), c["logits_train"]) < 1e-3
+    assert abs(float(loss) - float(c["loss"])) < 1e-3 * abs(float(c["loss"]))
+    assert rel(tokens.grad.cpu(), c["dimg_tokens"]) < 1e-3
+    gmax = max(float(g.abs().max()) for g in c["grads"].values())
+    assert [k for k, _ in m.named_parameters()] == c["named_parameters"]
+    for k, p in m.named_parameters():
+        g = c["grads"][k]
+        scale = float(g.abs().max())
+        if scale < 1e-5 * gmax:  # analytically zero (key bias: softmax is shift invariant)
+            assert float(p.grad.abs().max()) < 1e-4 * gmax, k
+        else:
+            assert float((p.grad.cpu() - g).abs().max()) < 1e-3 * scale, (k, rel(p.grad.cpu(), g))
+
+
+def test_bf16_tensor_core_path(mmu, golden):
+    c = golden("mmbt_small.pt")["hd64"]  # head_dim 64: sequence-axis attention on tcgen05
+    m = build(mmu, c, "bf16").train()
+    m.zero_grad()
+    tokens = c["img_tokens"].cuda().requires_grad_(True)
+    logits = m(c["txt"].cuda(), c["mask"].cuda(), c["segment"].cuda(), tokens)
+    loss = m.compute_loss(logits, c["y"].cuda())
+    loss.backward()
+    assert rel(logits.detach().cpu(), c["logits_train"]) < BF16_LOGIT_TOL
+    assert abs(float(loss) - float(c["loss"])) < BF16_LOGIT_TOL * abs(float(c["loss"]))
+    assert rel(tokens.grad.cpu(), c["dimg_tokens"]) < BF16_GRAD_TOL
+    gmax = max(float(g.abs().max()) for g in c["grads"].values())
+    for k, p in m.named_parameters():
+        g = c["grads"][k]
+        if float(g.abs().max()) < 1e-5 * gmax:
+            continue
+        assert rel(p.grad.cpu(), g) < BF16_GRAD_TOL, (k, rel(p.grad.cpu(), g))
+    m.eval()
+    with torch.no_grad():
+        for modal, d in c["control"].items():
+            out = m.forward_indices(c["txt"].cuda(), c["mask"].cuda(), c["segment"].cuda(), c["img_tokens"].cuda(),
+                                    [int(i) for i in d["indices"]]).cpu()
+            assert rel(out, d["logits"]) < BF16_LOGIT_TOL
+
+
+def test_fp32_vs_oracle_at_seq_above_one_tile(mmu):
+    """A longer ragged batch (S = 3 + 2 + 150 = 155 > 128: several attention tiles) held to the CPU
+    oracle on the same seeded inputs, both precisions."""
+    from oracle import mmbt as O
+    cfg = dict(B=3, S_txt=150, n_img=3, d_img=64, D=128, n_head=2, n_layers=2, d_ff=256, vocab=300,
+               max_pos=160, n_types=2, C=2, cls_id=5, sep_id=6)
+    g = torch.Generator().manual_seed(5)
+    m32 = mmu.MultimodalBertClf(make_args(cfg, "fp32"))
+    with torch.no_grad():
+        for p in m32.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.08)
+    P = {k: v.detach().clone() for k, v in m32.state_dict().items()}
+    txt = torch.randint(7, cfg["vocab"], (3, 150), generator=g)
+    lens = torch.tensor([150, 97, 31])
+    mask = (torch.arange(150)[None] < lens[:, None]).long()
+    txt, segment = txt * mask, mask.clone()
+    tok = torch.randn(3, 3, 64, generator=g)
+    y = torch.tensor([0, 1, 1])
+    ref_logits, ref_loss, ref_grads, ref_dtok = O.loss_and_grads(
+        {k: (v.double() if v.is_floating_point() else v) for k, v in P.items()}, txt, mask, segment,
+        tok.double(), y, cfg)
+    gmax = max(float(v.abs().max()) for v in ref_grads.values())
+    for prec, ltol, gtol in (("fp32", 1e-3, 1e-3), ("bf16", BF16_LOGIT_TOL, BF16_GRAD_TOL)):
+        m = mmu.MultimodalBertClf(make_args(cfg, prec))
+        m.load_state_dict(P, strict=True)
+        m.cuda().train()
+        m.zero_grad()
+        t = tok.cuda().requires_grad_(True)
+        logits = m(txt.cuda(), mask.cuda(), segment.cuda(), t)
+        loss = m.compute_loss(logits, y.cuda())
+        loss.backward()
+        assert rel(logits.detach().cpu(), ref_logits) < ltol, prec
+        assert abs(float(loss) - float(ref_loss)) < ltol * abs(float(ref_loss)), prec
+        assert rel(t.grad.cpu(), ref_dtok) < gtol, prec
+        for k, p in m.named_parameters():
+            if float(ref_grads[k].abs().max()) < 1e-5 * gmax:
+                continue
+            assert rel(p.grad.cpu(), ref_grads[k]) < gtol, (prec, k, rel(p.grad.cpu(), ref_grads[k]))
+
+
+def test_bertadam_matches_reference_optimizer(mmu, golden):
+    """Fused BertAdam on a real flat-buffer model against oracle.mmbt.bertadam_step (itself pinned to
+    the restated reference optimizer in tests/test_oracle_golden.py), incl. clipping and frozen
+    tensors."""
+    from oracle import mmbt as O
+    cfg = dict(B=2, S_txt=4, n_img=2, d_img=16, D=64, n_head=1, n_layers=1, d_ff=64, vocab=30, max_pos=16,
+               n_types=2, C=2, cls_id=1, sep_id=2)
+    m = mmu.MultimodalBertClf(make_args(cfg, "fp32")).cuda()
+    named = list(m.named_parameters())
+    no_decay = ["bias", "LayerNorm.bias", "LayerNorm.weight"]
+    groups = [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
+              {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+    opt = mmu.BertAdam(groups, lr=5e-2, warmup=0.1, t_total=40)
+    g = torch.Generator().manual_seed(3)
+    ref = {n: dict(p=p.detach().cpu().double(), m=torch.zeros(p.shape, dtype=torch.float64),
+                   v=torch.zeros(p.shape, dtype=torch.float64), step=0) for n, p in named}
+    frozen = "enc.encoder.layer.0.intermediate.dense.weight"
+    for it in range(5):
+        opt.zero_grad()
+        dict(named)[frozen].requires_grad = it != 2  # frozen for one step
+        for n, p in named:
+            gr = torch.randn(p.shape, generator=g) * (4.0 if "query.weight" in n else 0.02)
+            p.grad.copy_(gr.cuda())
+            if n == frozen and it == 2:
+                continue
+            r = ref[n]
+            wd = 0.0 if any(nd in n for nd in no_decay) else 0.01
+            r["p"], r["m"], r["v"] = O.bertadam_step(r["p"], gr.double(), r["m"], r["v"], r["step"], lr=5e-2,
+                                                     warmup=0.1, t_total=40, weight_decay=wd)
+            r["step"] += 1
+        opt.step()
+    for n, p in named:
+        assert rel(p.detach().cpu(), ref[n]["p"]) < 1e-5, n

@@ -38,6 +38,8 @@ def test_struct_sizes_match_header(mmu):
                                    mmu._lib.MetricAccum, mmu._lib.ParamEntry,
                                    mmu._lib.PosthocAccum)):
         assert mmu._lib.lib.mmu_struct_size(which) == C.sizeof(klass), klass.__name__
+    assert mmu._lib.lib.mmu_struct_size(6) == C.sizeof(mmu._lib.MmbtConfig) == 15 * 4
+    assert mmu._lib.lib.mmu_struct_size(7) == C.sizeof(mmu._lib.MmbtInputs)
     assert C.sizeof(mmu._lib.ParamEntry) == 96 + 8 + 8 + 12 + 4  # padded to 8
     assert mmu._lib.ACC_OFF["conf_sum"] == 98
 
@@ -319,3 +321,27 @@ def test_packed_store_round_trip(mmu, tmp_path):
     (pi, pt), py = mmu.dataset.collate_fn_flava([ds[i] for i in (0, 3, 4)])
     (oi, ot), oy = mmu.dataset.collate_fn_flava([items[i] for i in (0, 3, 4)])
     assert torch.equal(pi, oi) and torch.equal(pt, ot) and torch.equal(py, oy)
+
+
+def test_mmbt_state_dict_keys_order_and_strict_load(mmu, golden):
+    """MultimodalBertClf: the reference's state_dict keys (incl. the embedding tensors
+    ImageBertEmbeddings shares with the text side, src/mmbt.py:51-55), named_parameters() order and
+    a strict load of a reference checkpoint; host-side index lists of the forward variants."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_mmbt import make_args
+    c = golden("mmbt_small.pt")["fp32_small"]
+    m = mmu.MultimodalBertClf(make_args(c["cfg"], "fp32"))
+    assert sorted(m.state_dict()) == sorted(c["state_dict_keys_all"])
+    assert [k for k, _ in m.named_parameters()] == c["named_parameters"]
+    m.load_state_dict(c["state_dict"], strict=True)
+    assert m.enc.img_embeddings.word_embeddings.weight is m.enc.txt_embeddings.word_embeddings.weight
+    w = m.enc.encoder.layer[0].attention.self.query.weight
+    assert torch.equal(w, c["state_dict"]["enc.encoder.layer.0.attention.self.query.weight"])
+    for modal, d in c["control"].items():
+        torch.manual_seed(d["seed"])
+        num = c["cfg"]["n_img"] + 1 if modal == "image" else c["cfg"]["S_txt"]
+        ind = m.control_indices(c["cfg"]["S_txt"] + c["cfg"]["n_img"] + 2, num)
+        assert ind == [int(i) for i in d["indices"]]  # bit-exact with the reference's draw
+    with pytest.raises(mmu._lib.MMUError):  # no CPU path
+        m(c["txt"], c["mask"], c["segment"], c["img_tokens"])

@@ -187,3 +187,51 @@ def test_mimo_resnet(golden):
     assert rel(l32, c["logits"]) < 1e-5
     for k, g in c["grads"].items():
         assert rel(g32[k], g) < 2e-4, k
+
+
+# ------------------------------------------------------------------------------- MMBT path
+@pytest.mark.parametrize("name", ["fp32_small", "hd64"])
+def test_mmbt_oracle_matches_reference(golden, name):
+    """oracle/mmbt.py against the UNMODIFIED reference src/mmbt.py (run on the restated third-party
+    BERT, tests/golden/make_golden_mmbt.py): all four forward entry points, the index draw of
+    forward_control, loss, every gradient and the gradient of the pooled image tokens."""
+    from oracle import mmbt as O
+    c = golden("mmbt_small.pt")[name]
+    cfg = c["cfg"]
+    P = {k: (v.double() if v.is_floating_point() else v) for k, v in c["state_dict"].items()}
+    tok = c["img_tokens"].double()
+    x = (c["txt"], c["mask"], c["segment"], tok, cfg)
+    assert rel_err(O.forward(P, *x), c["logits_full"]) < 1e-5
+    for mode in ("img_only", "txt_only"):
+        idx = O.mode_indices(mode, cfg["n_img"], cfg["S_txt"])
+        assert rel_err(O.forward(P, *x, idx), c["logits_" + mode]) < 1e-5, mode
+    for modal, d in c["control"].items():
+        torch.manual_seed(d["seed"])
+        num = cfg["n_img"] + 1 if modal == "image" else cfg["S_txt"]
+        ind = O.control_indices(cfg["S_txt"] + cfg["n_img"] + 2, num)
+        assert torch.equal(ind, d["indices"])  # bit-exact index draw
+        assert rel_err(O.forward(P, *x, ind), d["logits"]) < 1e-5, modal
+    logits, loss, grads, dtok = O.loss_and_grads(P, c["txt"], c["mask"], c["segment"], tok, c["y"], cfg)
+    assert abs(float(loss) - float(c["loss"])) < 1e-6
+    assert rel_err(dtok, c["dimg_tokens"]) < 1e-4
+    gmax = max(float(g.abs().max()) for g in c["grads"].values())
+    for k, g in c["grads"].items():
+        if float(g.abs().max()) < 1e-5 * gmax:  # analytically zero (key bias); fp32 rounding noise
+            assert float(grads[k].abs().max()) < 1e-5 * gmax, k
+        else:
+            assert rel_err(grads[k], g) < 2e-4, k
+
+
+def test_bertadam_oracle_matches_restated_reference_optimizer(golden):
+    from oracle import mmbt as O
+    c = golden("bertadam.pt")
+    h = c["hyper"]
+    st = {k: dict(p=v.double(), m=torch.zeros_like(v).double(), v=torch.zeros_like(v).double())
+          for k, v in c["init"].items()}
+    for step, (gr, after) in enumerate(zip(c["grads"], c["after"])):
+        for k, s in st.items():
+            s["p"], s["m"], s["v"] = O.bertadam_step(
+                s["p"], gr[k].double(), s["m"], s["v"], step, lr=h["lr"], warmup=h["warmup"],
+                t_total=h["t_total"], weight_decay=c["decay"][k], b1=h["b1"], b2=h["b2"], e=h["e"],
+                max_grad_norm=h["max_grad_norm"])
+            assert rel_err(s["p"], after[k]) < 1e-5, (step, k)
