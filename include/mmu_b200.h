@@ -308,6 +308,29 @@ MMU_API int mmu_mmbt_forward(const mmu_mmbt_config* cfg, const float* params, co
 MMU_API int mmu_mmbt_backward(const mmu_mmbt_config* cfg, const float* params, const mmu_mmbt_inputs* in,
                       void* workspace, long long workspace_bytes, const float* dlogits, float* grads,
                       void* stream);
+/* MMBT image encoder (reference src/mmbt.py:15-45 ImageEncoder): torchvision Bottleneck ResNet trunk
+ * (resnet152: layers {3, 8, 36, 3}, children()[:-2]) + AdaptiveAvg/MaxPool2d to num_image_embeds
+ * cells, flattened to (B, N, 2048) tokens.  Parameter names are the nn.Sequential keys
+ * ("model.0.weight", "model.1.weight", "model.4.0.conv1.weight", ...); BatchNorm running statistics
+ * live in a second flat buffer (second table), updated in training mode as torch does. */
+typedef struct {
+  int B, H;             /* images, square input size */
+  int layers[4];        /* {3, 8, 36, 3} */
+  int width_per_group;  /* 64 */
+  int pool_h, pool_w;   /* src/mmbt.py:28-37 */
+  int pool_max;         /* img_embed_pool_type != "avg" */
+} mmu_imgenc_config;
+MMU_API long long mmu_imgenc_param_count(const mmu_imgenc_config* cfg);
+MMU_API long long mmu_imgenc_stat_count(const mmu_imgenc_config* cfg);
+MMU_API int mmu_imgenc_param_table(const mmu_imgenc_config* cfg, mmu_param_entry* out /* host */, int max);
+MMU_API int mmu_imgenc_stat_table(const mmu_imgenc_config* cfg, mmu_param_entry* out /* host */, int max);
+MMU_API long long mmu_imgenc_workspace_bytes(const mmu_imgenc_config* cfg, int training);
+MMU_API int mmu_imgenc_forward(const mmu_imgenc_config* cfg, const float* params, const void* params_bf16,
+                       float* stats, const float* x /* (B,3,H,H) */, void* workspace,
+                       long long workspace_bytes, int training, float* tokens, void* stream);
+MMU_API int mmu_imgenc_backward(const mmu_imgenc_config* cfg, const float* params, const void* params_bf16,
+                        float* stats, const float* x, void* workspace, long long workspace_bytes,
+                        const float* dtokens, float* grads, void* stream);
 /* BertAdam step over a flat buffer (pytorch_pretrained_bert.optimization.BertAdam as configured by
  * train.py:136-147): per-tensor clip_grad_norm_(max_grad_norm) applied to g in place, m/v without
  * bias correction, update = m / (sqrt(v) + eps) + decay * p, p -= lr * update.  segs: device

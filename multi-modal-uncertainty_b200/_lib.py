@@ -26,6 +26,8 @@ EXPORTS = [
     "mmu_resnet_backward",
     "mmu_mmbt_param_count", "mmu_mmbt_param_table", "mmu_mmbt_workspace_bytes", "mmu_mmbt_forward",
     "mmu_mmbt_backward", "mmu_bertadam_flat_step",
+    "mmu_imgenc_param_count", "mmu_imgenc_stat_count", "mmu_imgenc_param_table", "mmu_imgenc_stat_table",
+    "mmu_imgenc_workspace_bytes", "mmu_imgenc_forward", "mmu_imgenc_backward",
 ]
 
 
@@ -74,6 +76,11 @@ class ParamEntry(C.Structure):
 
 class ResNetConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("B", "cin", "H", "W", "E", "C")]
+
+
+class ImgEncConfig(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("layers", C.c_int * 4), ("width_per_group", C.c_int),
+                ("pool_h", C.c_int), ("pool_w", C.c_int), ("pool_max", C.c_int)]
 
 
 class MmbtConfig(C.Structure):
@@ -137,6 +144,14 @@ def _load():
     lib.mmu_flava_num_stages.argtypes = [cfgp]
     lib.mmu_flava_forward.argtypes = [cfgp, vp, C.POINTER(FlavaInputs), vp, ll, i, vp, vp]
     lib.mmu_flava_backward.argtypes = [cfgp, vp, C.POINTER(FlavaInputs), vp, ll, vp, vp, i, i, vp]
+    icfgp = C.POINTER(ImgEncConfig)
+    for fn in (lib.mmu_imgenc_param_count, lib.mmu_imgenc_stat_count):
+        fn.restype, fn.argtypes = ll, [icfgp]
+    for fn in (lib.mmu_imgenc_param_table, lib.mmu_imgenc_stat_table):
+        fn.argtypes = [icfgp, C.POINTER(ParamEntry), i]
+    lib.mmu_imgenc_workspace_bytes.restype, lib.mmu_imgenc_workspace_bytes.argtypes = ll, [icfgp, i]
+    lib.mmu_imgenc_forward.argtypes = [icfgp, vp, vp, vp, vp, vp, ll, i, vp, vp]
+    lib.mmu_imgenc_backward.argtypes = [icfgp, vp, vp, vp, vp, vp, ll, vp, vp, vp]
     mcfgp, minp = C.POINTER(MmbtConfig), C.POINTER(MmbtInputs)
     lib.mmu_mmbt_param_count.restype, lib.mmu_mmbt_param_count.argtypes = ll, [mcfgp]
     lib.mmu_mmbt_param_table.argtypes = [mcfgp, C.POINTER(ParamEntry), i]

@@ -17,6 +17,7 @@ static_assert(sizeof(mmu_resnet_config) == sizeof(ResNetConfig), "resnet config 
 static_assert(sizeof(mmu_posthoc_accum) == sizeof(PosthocAccum), "post-hoc accumulator layout");
 static_assert(sizeof(mmu_param_entry) == sizeof(ParamEntry), "param entry layout");
 static_assert(sizeof(mmu_mmbt_config) == sizeof(MmbtConfig), "mmbt config layout");
+static_assert(sizeof(mmu_imgenc_config) == sizeof(ImgEncConfig), "image encoder config layout");
 static_assert(sizeof(mmu_mmbt_inputs) == sizeof(MmbtInputs), "mmbt inputs layout");
 static_assert(sizeof(mmu_flava_inputs) == sizeof(FlavaInputs), "inputs layout");
 
@@ -50,6 +51,7 @@ int mmu_struct_size(int which) {
     case 5: return static_cast<int>(sizeof(mmu_posthoc_accum));
     case 6: return static_cast<int>(sizeof(mmu_mmbt_config));
     case 7: return static_cast<int>(sizeof(mmu_mmbt_inputs));
+    case 8: return static_cast<int>(sizeof(mmu_imgenc_config));
     default: return -1;
   }
 }
@@ -281,6 +283,45 @@ int mmu_bertadam_flat_step(float* p, float* g, float* m, float* v, void* p_bf16,
                            float b1, float b2, float eps, float max_grad_norm, void* stream) {
   return bertadam_flat(p, g, m, v, p_bf16, segs, seg_hyper, norms, n_seg, max_seg_numel, b1, b2, eps,
                        max_grad_norm, S(stream));
+}
+
+namespace {
+inline ImgEncConfig icfg_of(const mmu_imgenc_config* c) {
+  ImgEncConfig r;
+  std::memcpy(&r, c, sizeof(r));
+  return r;
+}
+}  // namespace
+long long mmu_imgenc_param_count(const mmu_imgenc_config* cfg) {
+  return cfg == nullptr ? MMU_ERR_ARG : imgenc_param_count(icfg_of(cfg));
+}
+long long mmu_imgenc_stat_count(const mmu_imgenc_config* cfg) {
+  return cfg == nullptr ? MMU_ERR_ARG : imgenc_stat_count(icfg_of(cfg));
+}
+int mmu_imgenc_param_table(const mmu_imgenc_config* cfg, mmu_param_entry* out, int max) {
+  if (cfg == nullptr) return MMU_ERR_ARG;
+  return imgenc_param_table(icfg_of(cfg), reinterpret_cast<ParamEntry*>(out), max);
+}
+int mmu_imgenc_stat_table(const mmu_imgenc_config* cfg, mmu_param_entry* out, int max) {
+  if (cfg == nullptr) return MMU_ERR_ARG;
+  return imgenc_stat_table(icfg_of(cfg), reinterpret_cast<ParamEntry*>(out), max);
+}
+long long mmu_imgenc_workspace_bytes(const mmu_imgenc_config* cfg, int training) {
+  return cfg == nullptr ? MMU_ERR_ARG : imgenc_workspace_bytes(icfg_of(cfg), training);
+}
+int mmu_imgenc_forward(const mmu_imgenc_config* cfg, const float* params, const void* params_bf16,
+                       float* stats, const float* x, void* workspace, long long workspace_bytes,
+                       int training, float* tokens, void* stream) {
+  if (cfg == nullptr) return MMU_ERR_ARG;
+  return imgenc_forward(icfg_of(cfg), params, params_bf16, stats, x, workspace, workspace_bytes, training,
+                        tokens, S(stream));
+}
+int mmu_imgenc_backward(const mmu_imgenc_config* cfg, const float* params, const void* params_bf16,
+                        float* stats, const float* x, void* workspace, long long workspace_bytes,
+                        const float* dtokens, float* grads, void* stream) {
+  if (cfg == nullptr) return MMU_ERR_ARG;
+  return imgenc_backward(icfg_of(cfg), params, params_bf16, stats, x, workspace, workspace_bytes, dtokens,
+                         grads, S(stream));
 }
 
 }  // extern "C"

@@ -28,6 +28,9 @@ struct GemmEpilogue {
   int seg_len, seg_stride, seg_off;
   float alpha;
   int n_valid;  // EPI_SOFTMAX: number of real columns (N is padded to a multiple of 8)
+  // EPI_QUICKGELU / EPI_DGELU (bf16 kernel): 0 = QuickGELU z*sigmoid(1.702 z) (src/model.py:185),
+  // 1 = erf-GELU z*Phi(z) (BERT's gelu of the MMBT path, src/mmbt.py:124-128)
+  int act;
 };
 
 struct GemmProblem {

@@ -84,6 +84,31 @@ __device__ __forceinline__ float quick_gelu_grad(float z) {
   return s * fmaf(1.702f * z, 1.0f - s, 1.0f);
 }
 
+// erf-GELU z*Phi(z) and its derivative Phi(z) + z*phi(z).  Phi through Abramowitz-Stegun 7.1.25
+// (erf(x) = 1 - (a1 t + a2 t^2 + a3 t^3) exp(-x^2), t = 1/(1 + 0.47047 x), |error| <= 2.5e-5 --
+// far below bf16 resolution): one rcp + one ex2 + ~10 FMAs, where erff() would make the epilogue
+// of a K = 768 tile longer than its main loop.  exp(-x^2) = exp(-z^2/2) is shared with phi(z).
+__device__ __forceinline__ void gelu_erf_terms(float z, float& cdf, float& pdf) {
+  const float x = fabsf(z) * 0.70710678118654752f;
+  float t, ex;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.47047f, x, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950408889634f * x * x));
+  const float poly = t * fmaf(t, fmaf(t, 0.7478556f, -0.0958798f), 0.3480242f);
+  const float half_erfc = 0.5f * poly * ex;             // 0.5 * erfc(|z| / sqrt 2)
+  cdf = z >= 0.f ? 1.0f - half_erfc : half_erfc;
+  pdf = 0.3989422804014327f * ex;
+}
+__device__ __forceinline__ float erf_gelu(float z) {
+  float cdf, pdf;
+  gelu_erf_terms(z, cdf, pdf);
+  return z * cdf;
+}
+__device__ __forceinline__ float erf_gelu_grad(float z) {
+  float cdf, pdf;
+  gelu_erf_terms(z, cdf, pdf);
+  return fmaf(z, pdf, cdf);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -508,10 +533,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
               const uint4 z = ptx::lds_v4u(a);
               const uint32_t zz[4] = {z.x, z.y, z.z, z.w};
               uint32_t o[4];
+              if (e.act == 1) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                o[i] = pack_bf16x2(v[8 * k + 2 * i] * quick_gelu_grad(bf16_lo(zz[i])),
-                                   v[8 * k + 2 * i + 1] * quick_gelu_grad(bf16_hi(zz[i])));
+                for (int i = 0; i < 4; ++i)
+                  o[i] = pack_bf16x2(v[8 * k + 2 * i] * erf_gelu_grad(bf16_lo(zz[i])),
+                                     v[8 * k + 2 * i + 1] * erf_gelu_grad(bf16_hi(zz[i])));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  o[i] = pack_bf16x2(v[8 * k + 2 * i] * quick_gelu_grad(bf16_lo(zz[i])),
+                                     v[8 * k + 2 * i + 1] * quick_gelu_grad(bf16_hi(zz[i])));
+              }
               ptx::sts_v4u(a, o[0], o[1], o[2], o[3]);
             }
             box_store(&tma_c0, box, col0);
@@ -530,8 +562,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                              pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
               box_store(&tma_c0, box0, col0);
             }
+            if (e.act == 1) {
 #pragma unroll
-            for (int i = 0; i < NCOL; ++i) v[i] = quick_gelu(v[i]);
+              for (int i = 0; i < NCOL; ++i) v[i] = erf_gelu(v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < NCOL; ++i) v[i] = quick_gelu(v[i]);
+            }
             const uint32_t ubox = e.out != nullptr ? box0 + BOX_BYTES : box;
             box_free(e.out == nullptr && c == 0);
 #pragma unroll

@@ -593,15 +593,15 @@ int mmbt_forward(const MmbtConfig& c, const float* params, const MmbtInputs& in,
     MB_TRY(postln_fwd(h, w.ybuf, training ? l.s1 : nullptr, params + p.ln1_w, params + p.ln1_b, l.a, dt,
                       training ? l.st1 : nullptr, training ? l.st1 + M : nullptr, M, D, BERT_LN_EPS,
                       stream));
-    MB_TRY(gemm(l.a, D, 0, W(p.i_w), D, 0, M, F, D, epi(EPI_STORE, l.z, bf, F, params + p.i_b)));
-    {
+    if (bf) {  // u = gelu_erf(a Wi^T + b) in the GEMM epilogue (z kept only for the backward)
+      GemmEpilogue e = epi(EPI_QUICKGELU, training ? l.z : nullptr, 1, F, params + p.i_b);
+      e.out2 = l.u; e.ld_out2 = F; e.act = 1;
+      MB_TRY(gemm(l.a, D, 0, W(p.i_w), D, 0, M, F, D, e));
+    } else {
+      MB_TRY(gemm(l.a, D, 0, W(p.i_w), D, 0, M, F, D, epi(EPI_STORE, l.z, 0, F, params + p.i_b)));
       const long long n = static_cast<long long>(M) * F;
-      if (bf)
-        gelu_fwd_kernel<__nv_bfloat16><<<grid1d(n, 256), 256, 0, stream>>>(
-            static_cast<const __nv_bfloat16*>(l.z), static_cast<__nv_bfloat16*>(l.u), n);
-      else
-        gelu_fwd_kernel<float><<<grid1d(n, 256), 256, 0, stream>>>(static_cast<const float*>(l.z),
-                                                                  static_cast<float*>(l.u), n);
+      gelu_fwd_kernel<float><<<grid1d(n, 256), 256, 0, stream>>>(static_cast<const float*>(l.z),
+                                                                static_cast<float*>(l.u), n);
       MB_CHECK_LAUNCH();
     }
     MB_TRY(gemm(l.u, F, 0, W(p.o_w), F, 0, M, D, F, epi(EPI_STORE, w.ybuf, bf, D, params + p.o_b)));
@@ -693,15 +693,15 @@ int mmbt_backward(const MmbtConfig& c, const float* params, const MmbtInputs& in
                       bf ? w.g_lp : nullptr, grads + p.ln2_w, grads + p.ln2_b, grads + p.o_b, M, D,
                       stream));
     // s2 = a + u Wo2^T + b:  du = ds2 Wo2 -> dz = du * gelu'(z)
-    MB_TRY(gemm(LP(w.gA), D, 0, W(p.o_w), F, 1, M, F, D, epi(EPI_STORE, w.dbig, bf, F, nullptr)));
-    {
+    if (bf) {  // dGELU fused into the dgrad GEMM epilogue (z arrives by TMA)
+      GemmEpilogue e = epi(EPI_DGELU, w.dbig, 1, F, nullptr);
+      e.aux = l.z; e.ld_aux = F; e.act = 1;
+      MB_TRY(gemm(LP(w.gA), D, 0, W(p.o_w), F, 1, M, F, D, e));
+    } else {
+      MB_TRY(gemm(LP(w.gA), D, 0, W(p.o_w), F, 1, M, F, D, epi(EPI_STORE, w.dbig, 0, F, nullptr)));
       const long long n = static_cast<long long>(M) * F;
-      if (bf)
-        gelu_bwd_kernel<__nv_bfloat16><<<grid1d(n, 256), 256, 0, stream>>>(
-            static_cast<const __nv_bfloat16*>(l.z), static_cast<__nv_bfloat16*>(w.dbig), n);
-      else
-        gelu_bwd_kernel<float><<<grid1d(n, 256), 256, 0, stream>>>(static_cast<const float*>(l.z),
-                                                                  static_cast<float*>(w.dbig), n);
+      gelu_bwd_kernel<float><<<grid1d(n, 256), 256, 0, stream>>>(static_cast<const float*>(l.z),
+                                                                static_cast<float*>(w.dbig), n);
       MB_CHECK_LAUNCH();
     }
     // dWo2[D, F] += ds2^T u ; dWi[F, D] += dz^T a ; dbi += colsum(dz) ; da_branch = dz Wi

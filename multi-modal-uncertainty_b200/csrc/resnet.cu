@@ -497,10 +497,10 @@ int conv_bn_fwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
     bn_sums_kernel<<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(o.t, M, l.co, 512, x.w.sums);
     RN_CHECK_LAUNCH();
     bn_finalize_kernel<<<(l.co + 127) / 128, 128, 0, x.st>>>(x.w.sums, M, l.co, 0.1f, o.mean, o.rstd,
-                                                              x.stats + l.stat, x.stats + l.stat + l.co);
+                                                              x.stats + l.stat, x.stats + l.stat + (l.co + 63) / 64 * 64);
     RN_CHECK_LAUNCH();
   } else {
-    bn_eval_stats_kernel<<<(l.co + 127) / 128, 128, 0, x.st>>>(x.stats + l.stat, x.stats + l.stat + l.co,
+    bn_eval_stats_kernel<<<(l.co + 127) / 128, 128, 0, x.st>>>(x.stats + l.stat, x.stats + l.stat + (l.co + 63) / 64 * 64,
                                                                 l.co, o.mean, o.rstd);
     RN_CHECK_LAUNCH();
   }
@@ -694,6 +694,415 @@ int resnet_backward(const ResNetConfig& c, const float* params, const void* para
   // ---- stem: conv1 + bn1 + relu (no input gradient needed)
   RN_TRY(conv_bn_bwd(x, n.stem, w.stem, x_nchw, 1, dcur, 1, nullptr, 0, nullptr));
   return 0;
+}
+
+
+// ===========================================================================================
+// MMBT image encoder (reference src/mmbt.py:15-45 ImageEncoder): torchvision's Bottleneck ResNet
+// trunk (resnet152 = layers [3, 8, 36, 3]; children()[:-2], i.e. up to layer4) followed by an
+// adaptive average / max pool to num_image_embeds cells, flattened to (B, N, 2048) tokens.
+// Built from the same conv + BatchNorm helpers as the FashionMNIST ResNet above (NHWC fp32
+// activations, im2col + GEMM; tcgen05 for every conv but the 3-channel stem when a bf16 shadow of
+// the parameters is given).
+namespace {
+
+constexpr int IE_MAX_CONVS = 208;   // 1 stem + 3 per block + 4 downsamples (resnet152: 155)
+constexpr int IE_MAX_BLOCKS = 64;
+
+struct IeBlock { int c1, c2, c3, ds; };  // indices into IeNet::conv (ds = -1: identity shortcut)
+struct IeNet {
+  ConvBn conv[IE_MAX_CONVS];
+  int n_conv;
+  IeBlock block[IE_MAX_BLOCKS];
+  int n_block;
+  int h_pool_in;   // spatial size after the stem's max pool
+  int h_out;       // spatial size of the layer4 output
+  int c_out;       // 2048
+  long long n_params, n_stats;
+};
+
+int ie_build(const ImgEncConfig& c, IeNet* net, ParamEntry* ptab, int pmax, ParamEntry* stab, int smax,
+             int* n_ptab, int* n_stab) {
+  if (c.B < 1 || c.H < 32 || c.pool_h < 1 || c.pool_w < 1 || c.width_per_group < 8 ||
+      c.width_per_group % 8 != 0)
+    return MMU_ERR_SHAPE;
+  int nb = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (c.layers[i] < 1) return MMU_ERR_SHAPE;
+    nb += c.layers[i];
+  }
+  if (nb > IE_MAX_BLOCKS || 1 + 3 * nb + 4 > IE_MAX_CONVS) return MMU_ERR_SHAPE;
+  Tab p{ptab, pmax, 0, 0}, s{stab, smax, 0, 0};
+  char nm[96];
+  auto bn = [&](const char* prefix, int ch, ConvBn* cb) {
+    std::snprintf(nm, sizeof(nm), "%s.weight", prefix); cb->g = p.add(nm, ch, 0);
+    std::snprintf(nm, sizeof(nm), "%s.bias", prefix);   cb->b = p.add(nm, ch, 0);
+    std::snprintf(nm, sizeof(nm), "%s.running_mean", prefix); cb->stat = s.add(nm, ch, 0);
+    std::snprintf(nm, sizeof(nm), "%s.running_var", prefix);  s.add(nm, ch, 0);
+  };
+  auto conv = [&](const char* name, int ci, int co, int k, int stride, int hin, ConvBn* cb) {
+    cb->ci = ci; cb->co = co; cb->k = k; cb->stride = stride; cb->pad = k / 2; cb->hin = hin;
+    cb->hout = (hin + 2 * cb->pad - k) / stride + 1;
+    cb->w = p.add(name, co, ci * k * k);
+  };
+  int nc = 0;
+  // nn.Sequential(conv1, bn1, relu, maxpool, layer1..layer4): keys model.0, model.1, model.4..7
+  conv("model.0.weight", 3, 64, 7, 2, c.H, &net->conv[nc]);
+  bn("model.1", 64, &net->conv[nc]);
+  ++nc;
+  const int h_stem = net->conv[0].hout;
+  net->h_pool_in = (h_stem + 2 - 3) / 2 + 1;  // MaxPool2d(3, stride 2, padding 1)
+  int h = net->h_pool_in, inpl = 64, blk = 0;
+  char pre[80], key[96];
+  for (int li = 0; li < 4; ++li) {
+    const int planes = 64 << li, width = planes * c.width_per_group / 64, outp = planes * 4;
+    for (int bi = 0; bi < c.layers[li]; ++bi) {
+      const int stride = (bi == 0 && li > 0) ? 2 : 1;
+      std::snprintf(pre, sizeof(pre), "model.%d.%d", 4 + li, bi);
+      IeBlock& B = net->block[blk++];
+      B.c1 = nc;
+      std::snprintf(key, sizeof(key), "%s.conv1.weight", pre); conv(key, inpl, width, 1, 1, h, &net->conv[nc]);
+      std::snprintf(key, sizeof(key), "%s.bn1", pre);          bn(key, width, &net->conv[nc]);
+      ++nc;
+      B.c2 = nc;
+      std::snprintf(key, sizeof(key), "%s.conv2.weight", pre); conv(key, width, width, 3, stride, h, &net->conv[nc]);
+      std::snprintf(key, sizeof(key), "%s.bn2", pre);          bn(key, width, &net->conv[nc]);
+      const int h2 = net->conv[nc].hout;
+      ++nc;
+      B.c3 = nc;
+      std::snprintf(key, sizeof(key), "%s.conv3.weight", pre); conv(key, width, outp, 1, 1, h2, &net->conv[nc]);
+      std::snprintf(key, sizeof(key), "%s.bn3", pre);          bn(key, outp, &net->conv[nc]);
+      ++nc;
+      B.ds = -1;
+      if (bi == 0 && (stride != 1 || inpl != outp)) {
+        B.ds = nc;
+        std::snprintf(key, sizeof(key), "%s.downsample.0.weight", pre);
+        conv(key, inpl, outp, 1, stride, h, &net->conv[nc]);
+        std::snprintf(key, sizeof(key), "%s.downsample.1", pre);
+        bn(key, outp, &net->conv[nc]);
+        ++nc;
+      }
+      inpl = outp;
+      h = h2;
+    }
+  }
+  net->n_conv = nc;
+  net->n_block = blk;
+  net->h_out = h;
+  net->c_out = inpl;
+  // (an adaptive pool grid larger than the map is legal: cells then repeat pixels, as in torch)
+  net->n_params = p.cursor;
+  net->n_stats = s.cursor;
+  if (n_ptab) *n_ptab = p.n;
+  if (n_stab) *n_stab = s.n;
+  return 0;
+}
+
+struct IeWs {
+  CbWs cb[IE_MAX_CONVS];
+  float* mp;            // max-pooled stem output [B*hp*hp, 64]
+  unsigned char* mp_idx;  // window position (0..8) of each maximum
+  int* pool_idx;        // adaptive max pool: flat pixel index of each maximum
+  float* dact[2];
+  Ws shared;            // cols / sums / dcols / dyb / dt / dres used by conv_bn_fwd / conv_bn_bwd
+  long long bytes;
+};
+
+void ie_carve(const ImgEncConfig& c, const IeNet& n, int training, void* base, IeWs* w) {
+  Bump b{static_cast<char*>(base), 0};
+  long long max_cols = 0, max_act = 0;
+  int max_co = 64;
+  for (int i = 0; i < n.n_conv; ++i) {
+    const ConvBn& l = n.conv[i];
+    const long long m = static_cast<long long>(c.B) * l.hout * l.hout;
+    CbWs& o = w->cb[i];
+    o.t = b.take<float>(m * l.co * 4);
+    o.mean = b.take<float>(l.co * 4);
+    o.rstd = b.take<float>(l.co * 4);
+    o.out = b.take<float>(m * l.co * 4);
+    const long long cols = m * l.ci * l.k * l.k;
+    if (cols > max_cols) max_cols = cols;
+    if (m * l.co > max_act) max_act = m * l.co;
+    const long long min_ = static_cast<long long>(c.B) * l.hin * l.hin * l.ci;
+    if (min_ > max_act) max_act = min_;
+    if (l.co > max_co) max_co = l.co;
+  }
+  const long long mp_el = static_cast<long long>(c.B) * n.h_pool_in * n.h_pool_in * 64;
+  w->mp = b.take<float>(mp_el * 4);
+  w->mp_idx = b.take<unsigned char>(mp_el);
+  w->pool_idx = b.take<int>(static_cast<long long>(c.B) * c.pool_h * c.pool_w * n.c_out * 4);
+  std::memset(&w->shared, 0, sizeof(w->shared));
+  w->shared.cols = b.take<float>(max_cols * 4);
+  w->shared.sums = b.take<double>(2LL * max_co * 8);
+  if (training) {
+    w->shared.dcols = b.take<float>(max_cols * 4);
+    w->shared.dyb = b.take<float>(max_act * 4);
+    w->shared.dt = b.take<float>(max_act * 4);
+    w->shared.dres = b.take<float>(max_act * 4);
+    w->dact[0] = b.take<float>(max_act * 4);
+    w->dact[1] = b.take<float>(max_act * 4);
+  } else {
+    w->dact[0] = w->dact[1] = nullptr;
+  }
+  w->bytes = b.off;
+}
+
+// MaxPool2d(kernel 3, stride 2, padding 1) on NHWC; idx = window tap (ky*3+kx) of the maximum
+// (first maximum in scan order, like torch's CPU kernel).
+__global__ void maxpool_fwd_kernel(const float* __restrict__ a, int B, int H, int Ho, int C,
+                                   float* __restrict__ out, unsigned char* __restrict__ idx) {
+  const size_t total = static_cast<size_t>(B) * Ho * Ho * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t pix = i / C;
+    const int xo = static_cast<int>(pix % Ho), yo = static_cast<int>((pix / Ho) % Ho);
+    const int b = static_cast<int>(pix / (static_cast<size_t>(Ho) * Ho));
+    float best = -INFINITY;
+    int tap = 0;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int y = yo * 2 + ky - 1;
+      if (y < 0 || y >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int x = xo * 2 + kx - 1;
+        if (x < 0 || x >= H) continue;
+        const float v = a[((static_cast<size_t>(b) * H + y) * H + x) * C + c];
+        if (v > best) { best = v; tap = ky * 3 + kx; }
+      }
+    }
+    out[i] = best;
+    idx[i] = static_cast<unsigned char>(tap);
+  }
+}
+// gather form (no atomics): an input pixel collects from the <= 4 windows that contain it
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const unsigned char* __restrict__ idx,
+                                   int B, int H, int Ho, int C, float* __restrict__ da) {
+  const size_t total = static_cast<size_t>(B) * H * H * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t pix = i / C;
+    const int x = static_cast<int>(pix % H), y = static_cast<int>((pix / H) % H);
+    const int b = static_cast<int>(pix / (static_cast<size_t>(H) * H));
+    float s = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = y + 1 - ky;
+      if (ty < 0 || (ty & 1)) continue;
+      const int yo = ty >> 1;
+      if (yo >= Ho) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = x + 1 - kx;
+        if (tx < 0 || (tx & 1)) continue;
+        const int xo = tx >> 1;
+        if (xo >= Ho) continue;
+        const size_t o = ((static_cast<size_t>(b) * Ho + yo) * Ho + xo) * C + c;
+        if (idx[o] == ky * 3 + kx) s += dout[o];
+      }
+    }
+    da[i] = s;
+  }
+}
+// AdaptiveAvgPool2d / AdaptiveMaxPool2d((ph, pw)) on the (B, H, H, C) NHWC map, written as tokens
+// (B, ph*pw, C): cell (i, j) covers rows [floor(i H / ph), ceil((i+1) H / ph)), likewise columns.
+__global__ void adaptive_pool_fwd_kernel(const float* __restrict__ a, int B, int H, int C, int ph, int pw,
+                                         int is_max, float* __restrict__ tok, int* __restrict__ arg) {
+  const size_t total = static_cast<size_t>(B) * ph * pw * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int cell = static_cast<int>((i / C) % (ph * pw));
+    const int b = static_cast<int>(i / (static_cast<size_t>(C) * ph * pw));
+    const int ci = cell / pw, cj = cell % pw;
+    const int y0 = (ci * H) / ph, y1 = ((ci + 1) * H + ph - 1) / ph;
+    const int x0 = (cj * H) / pw, x1 = ((cj + 1) * H + pw - 1) / pw;
+    float s = is_max ? -INFINITY : 0.f;
+    int best = 0;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        const float v = a[((static_cast<size_t>(b) * H + y) * H + x) * C + c];
+        if (is_max) { if (v > s) { s = v; best = y * H + x; } }
+        else s += v;
+      }
+    tok[i] = is_max ? s : s / ((y1 - y0) * (x1 - x0));
+    if (is_max) arg[i] = best;
+  }
+}
+__global__ void adaptive_pool_bwd_kernel(const float* __restrict__ dtok, const int* __restrict__ arg, int B,
+                                         int H, int C, int ph, int pw, int is_max, float* __restrict__ da) {
+  const size_t total = static_cast<size_t>(B) * H * H * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t pix = i / C;
+    const int x = static_cast<int>(pix % H), y = static_cast<int>((pix / H) % H);
+    const int b = static_cast<int>(pix / (static_cast<size_t>(H) * H));
+    float s = 0.f;
+    for (int ci = 0; ci < ph; ++ci) {
+      const int y0 = (ci * H) / ph, y1 = ((ci + 1) * H + ph - 1) / ph;
+      if (y < y0 || y >= y1) continue;
+      for (int cj = 0; cj < pw; ++cj) {
+        const int x0 = (cj * H) / pw, x1 = ((cj + 1) * H + pw - 1) / pw;
+        if (x < x0 || x >= x1) continue;
+        const size_t o = ((static_cast<size_t>(b) * ph + ci) * pw + cj) * C + c;
+        if (is_max) { if (arg[o] == y * H + x) s += dtok[o]; }
+        else s += dtok[o] / ((y1 - y0) * (x1 - x0));
+      }
+    }
+    da[i] = s;
+  }
+}
+
+ResNetConfig ie_rc(const ImgEncConfig& c) { return ResNetConfig{c.B, 3, c.H, c.H, 1, 1}; }
+
+}  // namespace
+
+int imgenc_param_table(const ImgEncConfig& c, ParamEntry* out, int max_entries) {
+  IeNet* n = new IeNet;
+  int np = 0;
+  const int rc = ie_build(c, n, out, max_entries, nullptr, 0, &np, nullptr);
+  delete n;
+  return rc != 0 ? rc : np;
+}
+int imgenc_stat_table(const ImgEncConfig& c, ParamEntry* out, int max_entries) {
+  IeNet* n = new IeNet;
+  int ns = 0;
+  const int rc = ie_build(c, n, nullptr, 0, out, max_entries, nullptr, &ns);
+  delete n;
+  return rc != 0 ? rc : ns;
+}
+long long imgenc_param_count(const ImgEncConfig& c) {
+  IeNet* n = new IeNet;
+  const int rc = ie_build(c, n, nullptr, 0, nullptr, 0, nullptr, nullptr);
+  const long long r = rc != 0 ? rc : n->n_params;
+  delete n;
+  return r;
+}
+long long imgenc_stat_count(const ImgEncConfig& c) {
+  IeNet* n = new IeNet;
+  const int rc = ie_build(c, n, nullptr, 0, nullptr, 0, nullptr, nullptr);
+  const long long r = rc != 0 ? rc : n->n_stats;
+  delete n;
+  return r;
+}
+long long imgenc_workspace_bytes(const ImgEncConfig& c, int training) {
+  IeNet* n = new IeNet;
+  IeWs* w = new IeWs;
+  long long r = ie_build(c, n, nullptr, 0, nullptr, 0, nullptr, nullptr);
+  if (r == 0) {
+    ie_carve(c, *n, training, nullptr, w);
+    r = w->bytes;
+  }
+  delete n;
+  delete w;
+  return r;
+}
+
+namespace {
+int ie_forward(const ImgEncConfig& c, const IeNet& n, IeWs& w, const float* params, const void* shadow,
+               float* stats, const float* x_nchw, int training, float* tokens, cudaStream_t stream) {
+  const ResNetConfig rc = ie_rc(c);
+  const Ctx x{rc, shadow, params, stats, nullptr, training, w.shared, stream};
+  RN_TRY(conv_bn_fwd(x, n.conv[0], w.cb[0], x_nchw, 1, nullptr, 1));
+  {
+    const size_t total = static_cast<size_t>(c.B) * n.h_pool_in * n.h_pool_in * 64;
+    maxpool_fwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w.cb[0].out, c.B, n.conv[0].hout,
+                                                                    n.h_pool_in, 64, w.mp, w.mp_idx);
+    RN_CHECK_LAUNCH();
+  }
+  const float* a = w.mp;
+  for (int bi = 0; bi < n.n_block; ++bi) {
+    const IeBlock& B = n.block[bi];
+    RN_TRY(conv_bn_fwd(x, n.conv[B.c1], w.cb[B.c1], a, 0, nullptr, 1));
+    RN_TRY(conv_bn_fwd(x, n.conv[B.c2], w.cb[B.c2], w.cb[B.c1].out, 0, nullptr, 1));
+    const float* residual = a;
+    if (B.ds >= 0) {
+      RN_TRY(conv_bn_fwd(x, n.conv[B.ds], w.cb[B.ds], a, 0, nullptr, 0));
+      residual = w.cb[B.ds].out;
+    }
+    RN_TRY(conv_bn_fwd(x, n.conv[B.c3], w.cb[B.c3], w.cb[B.c2].out, 0, residual, 1));
+    a = w.cb[B.c3].out;
+  }
+  const size_t total = static_cast<size_t>(c.B) * c.pool_h * c.pool_w * n.c_out;
+  adaptive_pool_fwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(a, c.B, n.h_out, n.c_out, c.pool_h,
+                                                                        c.pool_w, c.pool_max, tokens, w.pool_idx);
+  RN_CHECK_LAUNCH();
+  return 0;
+}
+
+int ie_backward(const ImgEncConfig& c, const IeNet& n, IeWs& w, const float* params, const void* shadow,
+                float* stats, const float* x_nchw, const float* dtokens, float* grads, cudaStream_t stream) {
+  const ResNetConfig rc = ie_rc(c);
+  const Ctx x{rc, shadow, params, stats, grads, 1, w.shared, stream};
+  float* dcur = w.dact[0];
+  float* dnext = w.dact[1];
+  {
+    const size_t total = static_cast<size_t>(c.B) * n.h_out * n.h_out * n.c_out;
+    adaptive_pool_bwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(
+        dtokens, w.pool_idx, c.B, n.h_out, n.c_out, c.pool_h, c.pool_w, c.pool_max, dcur);
+    RN_CHECK_LAUNCH();
+  }
+  for (int bi = n.n_block - 1; bi >= 0; --bi) {
+    const IeBlock& B = n.block[bi];
+    const float* blk_in = bi == 0 ? w.mp : w.cb[n.block[bi - 1].c3].out;
+    // conv3 + bn3 + shortcut + relu: the masked gradient also flows along the shortcut (dres)
+    RN_TRY(conv_bn_bwd(x, n.conv[B.c3], w.cb[B.c3], w.cb[B.c2].out, 0, dcur, 1, dnext, 0, w.shared.dres));
+    RN_TRY(conv_bn_bwd(x, n.conv[B.c2], w.cb[B.c2], w.cb[B.c1].out, 0, dnext, 1, dcur, 0, nullptr));
+    RN_TRY(conv_bn_bwd(x, n.conv[B.c1], w.cb[B.c1], blk_in, 0, dcur, 1, dnext, 0, nullptr));
+    if (B.ds >= 0) {
+      RN_TRY(conv_bn_bwd(x, n.conv[B.ds], w.cb[B.ds], blk_in, 0, w.shared.dres, 0, dnext, 1, nullptr));
+    } else {
+      const ConvBn& l = n.conv[B.c1];
+      const size_t nel = static_cast<size_t>(c.B) * l.hin * l.hin * l.ci;
+      add_inplace_kernel<<<blocks_for(nel, 256), 256, 0, stream>>>(dnext, w.shared.dres, nel);
+      RN_CHECK_LAUNCH();
+    }
+    float* t = dcur; dcur = dnext; dnext = t;
+  }
+  {
+    const int hs = n.conv[0].hout;
+    const size_t total = static_cast<size_t>(c.B) * hs * hs * 64;
+    maxpool_bwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(dcur, w.mp_idx, c.B, hs, n.h_pool_in, 64,
+                                                                    dnext);
+    RN_CHECK_LAUNCH();
+  }
+  return conv_bn_bwd(x, n.conv[0], w.cb[0], x_nchw, 1, dnext, 1, nullptr, 0, nullptr);
+}
+}  // namespace
+
+int imgenc_forward(const ImgEncConfig& c, const float* params, const void* params_bf16, float* stats,
+                   const float* x_nchw, void* ws, long long ws_bytes, int training, float* tokens,
+                   cudaStream_t stream) {
+  if (params == nullptr || stats == nullptr || x_nchw == nullptr || ws == nullptr || tokens == nullptr)
+    return MMU_ERR_ARG;
+  IeNet* n = new IeNet;
+  IeWs* w = new IeWs;
+  int rc = ie_build(c, n, nullptr, 0, nullptr, 0, nullptr, nullptr);
+  if (rc == 0) {
+    ie_carve(c, *n, training, ws, w);
+    rc = w->bytes > ws_bytes ? MMU_ERR_WORKSPACE
+                             : ie_forward(c, *n, *w, params, params_bf16, stats, x_nchw, training, tokens, stream);
+  }
+  delete n;
+  delete w;
+  return rc;
+}
+
+int imgenc_backward(const ImgEncConfig& c, const float* params, const void* params_bf16, float* stats,
+                    const float* x_nchw, void* ws, long long ws_bytes, const float* dtokens, float* grads,
+                    cudaStream_t stream) {
+  if (params == nullptr || x_nchw == nullptr || ws == nullptr || dtokens == nullptr || grads == nullptr)
+    return MMU_ERR_ARG;
+  IeNet* n = new IeNet;
+  IeWs* w = new IeWs;
+  int rc = ie_build(c, n, nullptr, 0, nullptr, 0, nullptr, nullptr);
+  if (rc == 0) {
+    ie_carve(c, *n, 1, ws, w);
+    rc = w->bytes > ws_bytes ? MMU_ERR_WORKSPACE
+                             : ie_backward(c, *n, *w, params, params_bf16, stats, x_nchw, dtokens, grads, stream);
+  }
+  delete n;
+  delete w;
+  return rc;
 }
 
 }  // namespace mmu

@@ -32,4 +32,26 @@ int resnet_backward(const ResNetConfig& c, const float* params, const void* para
                     const float* x_nchw, void* ws, long long ws_bytes, const float* dlogits,
                     float* grads, cudaStream_t stream);
 
+// ---- MMBT image encoder (reference src/mmbt.py:15-45): Bottleneck ResNet trunk + adaptive pool.
+struct ImgEncConfig {
+  int B;                // images
+  int H;                // square input size (224)
+  int layers[4];        // resnet152: {3, 8, 36, 3}
+  int width_per_group;  // 64 (torchvision's base width; thinner nets for tests)
+  int pool_h, pool_w;   // adaptive pool grid: num_image_embeds cells (src/mmbt.py:28-37)
+  int pool_max;         // args.img_embed_pool_type != "avg"
+};
+int imgenc_param_table(const ImgEncConfig& c, ParamEntry* out, int max_entries);
+int imgenc_stat_table(const ImgEncConfig& c, ParamEntry* out, int max_entries);
+long long imgenc_param_count(const ImgEncConfig& c);
+long long imgenc_stat_count(const ImgEncConfig& c);
+long long imgenc_workspace_bytes(const ImgEncConfig& c, int training);
+// x: fp32 (B, 3, H, H) NCHW; tokens: fp32 (B, pool_h * pool_w, 2048).
+int imgenc_forward(const ImgEncConfig& c, const float* params, const void* params_bf16, float* stats,
+                   const float* x_nchw, void* ws, long long ws_bytes, int training, float* tokens,
+                   cudaStream_t stream);
+int imgenc_backward(const ImgEncConfig& c, const float* params, const void* params_bf16, float* stats,
+                    const float* x_nchw, void* ws, long long ws_bytes, const float* dtokens, float* grads,
+                    cudaStream_t stream);
+
 }  // namespace mmu

@@ -108,9 +108,9 @@ class Model_:
 
     @staticmethod
     def _reject(mmbt, vilt):
-        if mmbt or vilt:
-            raise NotImplementedError("the MMBT / ViLT branches are outside this build's hot path "
-                                      "(SURVEY.md 8c: third-party arithmetic, parity unpinned)")
+        if vilt:
+            raise NotImplementedError("the ViLT branch wraps a third-party pretrained model whose "
+                                      "weights are unavailable offline (SURVEY.md 8c): not built")
 
     # ---------------------------------------------------------------- hot path
     def train_step(self, x, y, scheduler_step_on="batch", keep_mask=None, sync=True):
@@ -135,6 +135,45 @@ class Model_:
             self.scheduler.step()
         return (loss.item() if sync else loss.detach()), info, len(y)
 
+    def train_step_mmbt(self, x, y, global_step, *, freeze_img=False, freeze_txt=False,
+                        gradient_accumulation_steps=1, scheduler_step_on="epoch"):
+        """The ``mmbt`` branch of the reference's step body (src/framework.py:277-304): freeze
+        flags re-applied every step, ``model(*x)``, loss divided by the accumulation factor,
+        optimizer step + zero_grad every ``gradient_accumulation_steps`` batches.  (The
+        reference also zeroes the gradients at the START of every batch, :279 -- so its
+        accumulation only ever sees the last micro-batch; reproduced as is.)"""
+        x, y = self.data_forming(x, y, phase="train")
+        x, y = self.to_device(x), self.to_device(y)
+        self.optimizer.zero_grad()
+        ie = getattr(self.model.enc, "img_encoder", None)
+        if ie is not None:
+            for p in ie.parameters():
+                p.requires_grad = not freeze_img
+        for p in self.model.enc.encoder.parameters():
+            p.requires_grad = not freeze_txt
+        y_pred = self.model(*x)
+        loss = self.model.compute_loss(y_pred, y)
+        if gradient_accumulation_steps > 1:
+            loss = loss / gradient_accumulation_steps
+        loss.backward()
+        if global_step % gradient_accumulation_steps == 0:
+            self.optimizer.step()
+            self.optimizer.zero_grad()
+        with torch.no_grad():
+            info = self._compute_metrics(y_pred, y, eval=False, dummy_dim=False)
+        if scheduler_step_on == "batch" and self.scheduler is not None:
+            self.scheduler.step()
+        return loss.item(), info, len(y)
+
+    @torch.no_grad()
+    def eval_step_mmbt(self, x, y):
+        x, y = self.data_forming(x, y, phase="eval")
+        x, y = self.to_device(x), self.to_device(y)
+        outputs = self.model(*x)
+        loss = self.model.compute_loss(outputs, y, eval=True)
+        info = self._compute_metrics(outputs, y, eval=True, dummy_dim=False)
+        return float(loss), info, len(y), outputs, y
+
     @torch.no_grad()
     def eval_step(self, x, y):
         x, y = self.data_forming(x, y, phase="eval")
@@ -155,9 +194,12 @@ class Model_:
         self.model.eval()
         preds, labels = [], []
         for step, (x, y) in it:
-            loss, info, size, outputs, y_dev = self.eval_step(x, y)
+            loss, info, size, outputs, y_dev = self.eval_step_mmbt(x, y) if mmbt else self.eval_step(x, y)
             step["size"], step["loss"], step["metrics"] = size, loss, info
-            preds.append(outputs.mean(1))
+            # (B, E, C) -> head-mean logits.  The reference applies the same .mean(1) to MMBT's
+            # (B, C) logits (src/framework.py:191), which collapses the class axis and cannot feed
+            # its own AUROC line (:198); the (B, C) logits are kept instead.
+            preds.append(outputs if mmbt else outputs.mean(1))
             labels.append(y_dev)
         out = {f"{phase}_loss": it.loss,
                **{f"{phase}_{k}": v for k, v in it.extra_lists.items()},
@@ -179,7 +221,7 @@ class Model_:
         cbs.set_params({"epochs": epochs, "steps": steps_per_epoch})
         cbs.set_model_pytoune(self)
 
-        stop, stopped_epoch, perfect_epochs = False, 0, 0
+        stop, stopped_epoch, perfect_epochs, global_step = False, 0, 0, 0
         cbs.on_train_begin({})
         for epoch in range(epoch_start, epochs + 1):
             cbs.on_epoch_begin(epoch, {})
@@ -188,7 +230,15 @@ class Model_:
             self.model.train(True)
             with torch.enable_grad():
                 for step, (x, y) in it:
-                    loss, info, size = self.train_step(x, y, scheduler_step_on)
+                    if mmbt:
+                        global_step += 1
+                        loss, info, size = self.train_step_mmbt(
+                            x, y, global_step, freeze_img=epoch < kwargs["freeze_img"],
+                            freeze_txt=epoch < kwargs["freeze_txt"],
+                            gradient_accumulation_steps=kwargs["gradient_accumulation_steps"],
+                            scheduler_step_on=scheduler_step_on)
+                    else:
+                        loss, info, size = self.train_step(x, y, scheduler_step_on)
                     cbs.on_backward_end(step["number"])
                     step["size"], step["loss"], step["metrics"] = size, loss, info
                     if math.isnan(loss):
@@ -196,9 +246,9 @@ class Model_:
             log = {"epoch": epoch, "loss": it.loss,
                    **{f"train_{k}": v for k, v in it.extra_lists.items()}, **it.metrics}
             if valid_generator is not None:
-                log.update(self.eval_loop(valid_generator, "val", steps=validation_steps, auc=auc))
+                log.update(self.eval_loop(valid_generator, "val", steps=validation_steps, auc=auc, mmbt=mmbt))
             if test_generator is not None:
-                log.update(self.eval_loop(test_generator, "test", steps=test_steps, auc=auc))
+                log.update(self.eval_loop(test_generator, "test", steps=test_steps, auc=auc, mmbt=mmbt))
             log["time"] = timeit.default_timer() - t0
             log["epoch_begin_time"] = t0
             if scheduler_step_on == "epoch" and self.scheduler is not None:

@@ -150,3 +150,34 @@ def run_view_robustness(model, batches, device, n_views=4, collect=True):
         m.all_reduce()
     P = torch.stack([torch.cat(o) for o in outs]).numpy() if collect and labels else None
     return P, torch.cat(labels).numpy(), [m.compute() for m in meters]
+
+
+@torch.no_grad()
+def run_mmbt_robustness(model, generator, n_repeats=20, device=None, posthoc=None):
+    """The MMBT sweep of reference ``eval_mmbt_robustness.py:76-96``: per batch the full forward,
+    ``forward_img_only``, ``forward_txt_only`` and ``n_repeats`` ``forward_control`` draws for
+    "image" then "text" -> ``(S, 3 + 2 n_repeats, C)`` logits and ``(S,)`` labels (the arrays the
+    reference saves as ``robustness_{ckpt}_predictions_{phase}.npy`` / ``..._labels_...``).
+
+    The reference re-runs the ResNet-152 image encoder inside every one of the 43 forwards; in
+    eval mode its output does not depend on the variant, so the pooled image tokens are computed
+    ONCE per batch and every variant is an index list over the same embedded sequence
+    (``MultimodalBertClf.forward_indices``).  The ``forward_control`` draws consume the host
+    ``torch.randperm`` stream exactly like the reference (src/mmbt.py:198-201)."""
+    model.eval()
+    device = device if device is not None else next(model.parameters()).device
+    preds, labels = [], []
+    for x, y in generator:
+        txt, mask, segment, img = (t.to(device, non_blocking=True) for t in x)
+        tokens = model._tokens(img)
+        outs = [model(txt, mask, segment, tokens), model.forward_img_only(txt, mask, segment, tokens),
+                model.forward_txt_only(txt, mask, segment, tokens)]
+        for type in ("image", "text"):
+            for _ in range(n_repeats):
+                outs.append(model.forward_control(txt, mask, segment, tokens, type))
+        y_hat = torch.stack(outs, dim=1)  # (B, V, C)
+        if posthoc is not None:
+            posthoc.update(y_hat.transpose(0, 1).unsqueeze(2).contiguous(), y.to(device))
+        preds.append(y_hat.cpu())
+        labels.append(y.cpu())
+    return torch.cat(preds).numpy(), torch.cat(labels).numpy()

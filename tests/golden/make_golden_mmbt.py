@@ -21,6 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference"
 sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
 
 from oracle import bert_restated  # noqa: E402
 
@@ -134,6 +135,44 @@ def mmbt_case(ref_mmbt, *, seed, B, S_txt, n_img, D, heads, layers, d_ff, vocab,
     return out
 
 
+def image_encoder_case(ref_mmbt, *, seed, layers, width, n_img, pool, B, hw):
+    """The reference's ImageEncoder class, unmodified, over a thin torchvision Bottleneck ResNet
+    (``resnet152`` itself is ResNet(Bottleneck, [3, 8, 36, 3]); same class, fewer / thinner blocks
+    so that the fixture stays small).  Train-mode tokens + running statistics, eval-mode tokens and
+    the gradients of sum(tokens * r)."""
+    import torchvision
+    from torchvision.models.resnet import Bottleneck, ResNet
+    saved = torchvision.models.resnet152
+    torchvision.models.resnet152 = lambda pretrained=False, **kw: ResNet(Bottleneck, list(layers),
+                                                                         width_per_group=width)
+    try:
+        torch.manual_seed(seed)
+        enc = ref_mmbt.ImageEncoder(types.SimpleNamespace(num_image_embeds=n_img, img_embed_pool_type=pool))
+    finally:
+        torchvision.models.resnet152 = saved
+    from det_params import det_image_encoder_state, grad_digest
+    enc.load_state_dict(det_image_encoder_state({k: v.shape for k, v in enc.state_dict().items()}, seed),
+                        strict=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, 3, hw, hw, generator=g)
+    r = torch.randn(B, n_img, 2048, generator=g)
+    out = {"cfg": dict(layers=list(layers), width=width, n_img=n_img, pool=pool, B=B, hw=hw, seed=seed),
+           "state_dict_shapes": {k: tuple(v.shape) for k, v in enc.state_dict().items()},
+           "named_parameters": [k for k, _ in enc.named_parameters()], "x": x, "r": r}
+    enc.eval()
+    with torch.no_grad():
+        out["tokens_eval"] = enc(x).clone()
+    enc.train()
+    enc.zero_grad()
+    tok = enc(x)
+    (tok * r).sum().backward()
+    out["tokens_train"] = tok.detach().clone()
+    out["grads"] = {k: grad_digest(p.grad) for k, p in enc.named_parameters()}
+    out["buffers_after"] = {k: v.detach().clone() for k, v in enc.state_dict().items()
+                            if "running" in k or "num_batches" in k}
+    return out
+
+
 def bertadam_case():
     """The reference's optimizer configuration for MMBT (train.py:136-147) on a few small tensors,
     several steps, including a tensor whose gradient norm exceeds max_grad_norm."""
@@ -160,16 +199,22 @@ def bertadam_case():
 def main():
     torch.set_num_threads(4)
     ref_mmbt = import_reference_mmbt()
-    cases = {
+    cases = {} if "--only-image-encoder" in sys.argv else {
         "fp32_small": mmbt_case(ref_mmbt, seed=31, B=3, S_txt=11, n_img=3, D=128, heads=2, layers=2, d_ff=256,
                                 vocab=120, max_pos=32, C=2, img_hw=64),
         # head_dim 64 (the tensor-core path's geometry), longer ragged text, 3 classes
         "hd64": mmbt_case(ref_mmbt, seed=32, B=4, S_txt=27, n_img=3, D=128, heads=2, layers=3, d_ff=512,
                           vocab=200, max_pos=64, C=3, img_hw=64),
     }
-    torch.save(cases, os.path.join(HERE, "mmbt_small.pt"))
-    torch.save(bertadam_case(), os.path.join(HERE, "bertadam.pt"))
-    for f in ("mmbt_small.pt", "bertadam.pt"):
+    if "--only-image-encoder" not in sys.argv:
+        torch.save(cases, os.path.join(HERE, "mmbt_small.pt"))
+        torch.save(bertadam_case(), os.path.join(HERE, "bertadam.pt"))
+    enc_cases = {
+        "avg3": image_encoder_case(ref_mmbt, seed=41, layers=(1, 2, 1, 1), width=16, n_img=3, pool="avg", B=4, hw=64),
+        "max4": image_encoder_case(ref_mmbt, seed=43, layers=(1, 1, 1, 1), width=8, n_img=4, pool="max", B=3, hw=96),
+    }
+    torch.save(enc_cases, os.path.join(HERE, "image_encoder.pt"))
+    for f in ("mmbt_small.pt", "bertadam.pt", "image_encoder.pt"):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 
 

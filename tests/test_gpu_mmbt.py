@@ -5,10 +5,15 @@ oracle/bert_restated.py) and against the CPU oracle.
 
 Tolerances: fp32 path 1e-3 relative on logits / loss / gradients, argmax bit-exact; bf16 tensor-core
 path 6e-2 of max|logit| and 0.2 of max|grad| per tensor (as for the fusion model)."""
+import os
+import sys
 import types
 
 import pytest
 import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from det_params import det_image_encoder_state, digest_error  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -185,3 +190,82 @@ def test_bertadam_matches_reference_optimizer(mmu, golden):
         opt.step()
     for n, p in named:
         assert rel(p.detach().cpu(), ref[n]["p"]) < 1e-5, n
+
+
+# ------------------------------------------------------------------ image encoder (ResNet trunk)
+def _encoder(mmu, c, precision):
+    import importlib
+    ie = importlib.import_module("multi-modal-uncertainty_b200.src.image_encoder")
+    cfg = c["cfg"]
+    args = types.SimpleNamespace(num_image_embeds=cfg["n_img"], img_embed_pool_type=cfg["pool"],
+                                 precision=precision, img_encoder_layers=tuple(cfg["layers"]),
+                                 img_encoder_width=cfg["width"])
+    enc = ie.ImageEncoder(args)
+    assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == c["state_dict_shapes"]
+    assert [k for k, _ in enc.named_parameters()] == c["named_parameters"]
+    enc.load_state_dict(det_image_encoder_state(c["state_dict_shapes"], cfg["seed"]), strict=True)
+    return enc.cuda()
+
+
+@pytest.mark.parametrize("name", ["avg3", "max4"])
+def test_image_encoder_fp32_matches_reference(mmu, golden, name):
+    c = golden("image_encoder.pt")[name]
+    enc = _encoder(mmu, c, "fp32")
+    enc.eval()
+    with torch.no_grad():
+        assert rel(enc(c["x"].cuda()).cpu(), c["tokens_eval"]) < 1e-3
+    enc.train()
+    enc.zero_grad()
+    tok = enc(c["x"].cuda())
+    (tok * c["r"].cuda()).sum().backward()
+    assert rel(tok.detach().cpu(), c["tokens_train"]) < 1e-3
+    for k, p in enc.named_parameters():
+        assert digest_error(c["grads"][k], p.grad) < 2e-3, (k, digest_error(c["grads"][k], p.grad))
+    sd = enc.state_dict()
+    for k, v in c["buffers_after"].items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+        else:
+            assert rel(sd[k].cpu(), v) < 1e-4, k
+
+
+def test_image_encoder_bf16_and_full_mmbt_from_images(mmu, golden):
+    """Tensor-core convolutions (bf16 operands) against the golden tokens, then the whole
+    MultimodalBertClf from raw images: image encoder -> tokens -> BERT trunk, gradients reaching the
+    ResNet stem."""
+    c = golden("image_encoder.pt")["avg3"]
+    enc = _encoder(mmu, c, "bf16").eval()
+    with torch.no_grad():
+        tok = enc(c["x"].cuda()).cpu()
+    assert rel(tok, c["tokens_eval"]) < BF16_LOGIT_TOL
+    cos = torch.nn.functional.cosine_similarity(tok.flatten().double(), c["tokens_eval"].flatten().double(), dim=0)
+    assert float(cos) > 0.999
+    # full model from images (fp32): tokens produced by the engine feed the trunk, backward reaches conv1
+    g = golden("mmbt_small.pt")["fp32_small"]
+    cfg = g["cfg"]
+    args = make_args(cfg, "fp32")
+    args.img_encoder = "native"
+    args.img_encoder_layers, args.img_encoder_width = (1, 1, 1, 1), 8
+    m = mmu.MultimodalBertClf(args).cuda().train()
+    keys = set(m.state_dict())
+    assert "enc.img_encoder.model.0.weight" in keys and "enc.img_encoder.model.7.0.bn3.running_var" in keys
+    x = [g[k].cuda() for k in ("txt", "mask", "segment", "img")]
+    named = list(m.named_parameters())
+    opt = mmu.BertAdam([{"params": [p for _, p in named], "weight_decay": 0.01}], lr=1e-3, warmup=0.1, t_total=100)
+    losses = []
+    for _ in range(8):
+        opt.zero_grad()
+        loss = m.compute_loss(m(*x), g["y"].cuda())
+        loss.backward()
+        if not losses:
+            stem = dict(named)["enc.img_encoder.model.0.weight"].grad
+            assert float(stem.abs().max()) > 0 and bool(torch.isfinite(stem).all())
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(l == l for l in losses) and losses[-1] < losses[0]
+    # frozen image encoder (src/framework.py:281-282): no gradient, still runs
+    for p in m.enc.img_encoder.parameters():
+        p.requires_grad = False
+    m.zero_grad()
+    m.compute_loss(m(*x), g["y"].cuda()).backward()
+    assert float(dict(named)["enc.img_encoder.model.0.weight"].grad.abs().max()) == 0.0

@@ -251,7 +251,54 @@ def test_trainer_protocol_with_a_plain_torch_model(mmu, tmp_path):
     assert be[0][2] >= {"batch", "size", "time", "batch_begin_time", "loss", "acc"}
     assert events[0] == ("eb", 1) and events[1] == ("bw", 1)
     with pytest.raises(NotImplementedError):
-        trainer.eval_loop(val, "val", mmbt=True)
+        trainer.eval_loop(val, "val", vilt=True)
+
+
+def test_trainer_mmbt_branch_with_a_plain_torch_model(mmu):
+    """The ``mmbt`` branches of Model_ (reference src/framework.py:246-304, :172-176): ``model(*x)``,
+    per-epoch freeze flags on ``enc.img_encoder`` / ``enc.encoder``, gradient-accumulation stepping,
+    (B, C) logits with ``dummy_dim=False`` metrics, epoch-wise scheduler on ``val_acc``."""
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.img_encoder = torch.nn.Linear(4, 4)
+            self.encoder = torch.nn.Linear(8, 8)
+    class TinyMM(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.enc = Enc()
+            self.emb = torch.nn.Embedding(20, 4)
+            self.clf = torch.nn.Linear(8, 2)
+        def forward(self, txt, mask, segment, img):
+            t = (self.emb(txt) * mask[..., None]).sum(1)
+            return self.clf(self.enc.encoder(torch.cat([t, self.enc.img_encoder(img)], -1)))
+        def compute_loss(self, y_hat, y, eval=False):
+            return torch.nn.functional.cross_entropy(y_hat, y)
+    def acc(y_pred, y_true, eval, dummy_dim=False):
+        assert dummy_dim is False and y_pred.dim() == 2
+        return (y_pred.argmax(1) == y_true).float().mean() * 100
+    torch.manual_seed(0)
+    def batches(n):
+        return [((torch.randint(0, 20, (4, 5)), torch.ones(4, 5, dtype=torch.long),
+                  torch.ones(4, 5, dtype=torch.long), torch.randn(4, 4)), torch.randint(0, 2, (4,)))
+                for _ in range(n)]
+    net = TinyMM()
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, "max", patience=1, factor=0.5)
+    seen = []
+    step = opt.step
+    opt.step = lambda *a, **k: (seen.append((net.enc.img_encoder.weight.requires_grad,
+                                             net.enc.encoder.weight.requires_grad)), step(*a, **k))[1]
+    trainer = mmu.Model_(net, opt, sched, lambda x, y, phase="train": (x, y), metrics=[acc], verbose=False)
+    trainer.to(torch.device("cpu"))
+    H = {}
+    cbs = [mmu.src.callbacks.LambdaCallback(on_epoch_end=lambda e, l: H.setdefault("logs", []).append(dict(l)))]
+    trainer.train_loop(batches(4), valid_generator=batches(2), epochs=2, steps_per_epoch=4, validation_steps=2,
+                       callbacks=cbs, scheduler_step_on="epoch", scheduler_metric="val_acc", mmbt=True,
+                       freeze_img=2, freeze_txt=0, gradient_accumulation_steps=2, auc=True)
+    # 4 batches / accumulation 2 -> 2 optimizer steps per epoch; image encoder frozen in epoch 1 only
+    assert seen == [(False, True)] * 2 + [(True, True)] * 2
+    assert len(H["logs"]) == 2 and {"loss", "acc", "val_loss", "val_acc", "val_auc"} <= set(H["logs"][0])
 
 
 def _gloo_worker(rank, world, port, out_dir):

@@ -235,3 +235,30 @@ def test_bertadam_oracle_matches_restated_reference_optimizer(golden):
                 t_total=h["t_total"], weight_decay=c["decay"][k], b1=h["b1"], b2=h["b2"], e=h["e"],
                 max_grad_norm=h["max_grad_norm"])
             assert rel_err(s["p"], after[k]) < 1e-5, (step, k)
+
+
+@pytest.mark.parametrize("name", ["avg3", "max4"])
+def test_image_encoder_oracle_matches_reference(golden, name):
+    """oracle/image_encoder.py against the reference's unmodified ImageEncoder class
+    (src/mmbt.py:15-45) over a thin torchvision Bottleneck ResNet: eval tokens, train-mode tokens,
+    running statistics and every gradient (large tensors through a strided digest).  The seeds
+    were chosen so that no ReLU / max-pool decision sits within fp32 rounding of a tie."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from det_params import det_image_encoder_state, digest_error
+    from oracle import image_encoder as IE
+    c = golden("image_encoder.pt")[name]
+    cfg = c["cfg"]
+    sd = det_image_encoder_state(c["state_dict_shapes"], cfg["seed"])
+    P = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    pool = {3: (3, 1), 4: (2, 2)}[cfg["n_img"]]
+    is_max = cfg["pool"] != "avg"
+    te = IE.image_encoder_forward(P, c["x"].double(), cfg["layers"], pool, is_max, False)
+    assert rel_err(te, c["tokens_eval"]) < 1e-5
+    tt, grads, buf = IE.tokens_and_grads(P, c["x"].double(), c["r"].double(), cfg["layers"], pool, is_max)
+    assert rel_err(tt, c["tokens_train"]) < 5e-5
+    for k, d in c["grads"].items():
+        assert digest_error(d, grads[k]) < 1e-4, k
+    for k, v in c["buffers_after"].items():
+        assert rel_err(buf[k], v) < 1e-5, k
