@@ -15,6 +15,7 @@
 // No allocation, no synchronisation: caller-owned flat parameter / gradient / statistics buffers
 // and workspace, everything enqueued on the caller's stream.
 #include "resnet.h"
+#include "kernels.h"
 
 #include <cuda_bf16.h>
 
@@ -79,6 +80,39 @@ __global__ void im2col_kernel(const float* __restrict__ in, int nchw, int B, int
       v = nchw ? in[((static_cast<size_t>(b) * Ci + ci) * H + y) * W + x]
                : in[((static_cast<size_t>(b) * H + y) * W + x) * Ci + ci];
     put(cols + row * K + static_cast<size_t>(ci) * kk + tap, v);
+  }
+}
+
+// bf16 columns, NHWC input, K % 8 == 0: one thread writes 8 consecutive columns of a row as one
+// 16-byte store (the scalar kernel above scatters 2-byte stores 2*k*k bytes apart); the reads are
+// 3x3 neighbourhoods that overlap between rows and stay in L1 / L2.
+__global__ void __launch_bounds__(256)
+im2col_bf16x8_kernel(const float* __restrict__ in, int B, int H, int W, int Ci, int k, int stride, int pad,
+                     int Ho, int Wo, __nv_bfloat16* __restrict__ cols) {
+  const int kk = k * k, K = Ci * kk, K8 = K >> 3;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * K8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % K8);
+    const size_t row = i / K8;
+    const int xo = static_cast<int>(row % Wo), yo = static_cast<int>((row / Wo) % Ho);
+    const int b = static_cast<int>(row / (static_cast<size_t>(Wo) * Ho));
+    const float* base = in + static_cast<size_t>(b) * H * W * Ci;
+    int ci = (c8 * 8) / kk, tap = (c8 * 8) % kk;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ky = tap / k, kx = tap - ky * k;
+      const int y = yo * stride + ky - pad, x = xo * stride + kx - pad;
+      v[j] = (y >= 0 && y < H && x >= 0 && x < W) ? base[(static_cast<size_t>(y) * W + x) * Ci + ci] : 0.f;
+      if (++tap == kk) { tap = 0; ++ci; }
+    }
+    uint4 pk;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+    *reinterpret_cast<uint4*>(cols + row * K + static_cast<size_t>(c8) * 8) = pk;
   }
 }
 
@@ -474,6 +508,24 @@ const __nv_bfloat16* wbf(const Ctx& x, const ConvBn& l) {
   return static_cast<const __nv_bfloat16*>(x.shadow) + l.w;
 }
 
+// bf16 columns of a layer for the tensor-core path: a 1x1 stride-1 convolution's columns ARE its
+// NHWC input (one vectorised cast); otherwise 8 columns per thread.
+int tc_columns(const Ctx& x, const ConvBn& l, const float* in, int in_nchw, __nv_bfloat16* cols) {
+  const size_t M = static_cast<size_t>(rows_of(x.c, l.hout));
+  const int K = l.ci * l.k * l.k;
+  if (l.k == 1 && l.stride == 1 && !in_nchw) return cast_f32_to_bf16(in, cols, M * K, x.st);
+  if (!in_nchw && K % 8 == 0) {
+    im2col_bf16x8_kernel<<<blocks_for(M * (K / 8), 256), 256, 0, x.st>>>(
+        in, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
+    RN_CHECK_LAUNCH();
+    return 0;
+  }
+  im2col_kernel<__nv_bfloat16><<<blocks_for(M * K, 256), 256, 0, x.st>>>(
+      in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
+  RN_CHECK_LAUNCH();
+  return 0;
+}
+
 int conv_bn_fwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, int in_nchw,
                 const float* residual, int relu) {
   const int M = static_cast<int>(rows_of(x.c, l.hout)), K = l.ci * l.k * l.k;
@@ -481,9 +533,7 @@ int conv_bn_fwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
   GemmProblem p{M, l.co, K, 0, 0, 1};
   if (use_tc(x, l)) {
     __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(x.w.cols);
-    im2col_kernel<__nv_bfloat16><<<blocks_for(ncols, 256), 256, 0, x.st>>>(
-        in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
-    RN_CHECK_LAUNCH();
+    RN_TRY(tc_columns(x, l, in, in_nchw, cols));
     RN_TRY(gemm_bf16_launch(cols, K, wbf(x, l), K, p, store_epi(o.t, l.co, nullptr), x.st));
   } else {
     im2col_kernel<float><<<blocks_for(ncols, 256), 256, 0, x.st>>>(
@@ -536,15 +586,19 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
     bn_bwd_apply_kernel<__nv_bfloat16><<<blocks_for(n, 256), 256, 0, x.st>>>(
         dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
     RN_CHECK_LAUNCH();
-    im2col_kernel<__nv_bfloat16><<<blocks_for(ncols, 256), 256, 0, x.st>>>(
-        in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
-    RN_CHECK_LAUNCH();
+    RN_TRY(tc_columns(x, l, in, in_nchw, cols));
     int splits = M / 4096;
     if (splits < 1) splits = 1;
     if (splits > 16) splits = 16;
     GemmProblem p{l.co, K, M, 1, 1, splits};
     RN_TRY(gemm_bf16_launch(dt, l.co, cols, K, p, wg, x.st));
-    if (din != nullptr) {
+    if (din != nullptr && l.k == 1 && l.stride == 1) {
+      // 1x1 stride-1: the input gradient IS dt W -- written (or TMA-reduce-added) straight to din
+      GemmProblem q{M, K, l.co, 0, 1, 1};
+      GemmEpilogue e = store_epi(din, K, nullptr);
+      if (din_accumulate) e.mode = EPI_ATOMIC;
+      RN_TRY(gemm_bf16_launch(dt, l.co, wbf(x, l), K, q, e, x.st));
+    } else if (din != nullptr) {
       GemmProblem q{M, K, l.co, 0, 1, 1};
       GemmEpilogue e = store_epi(reinterpret_cast<float*>(dcols), K, nullptr);
       e.out_bf16 = 1;
