@@ -308,6 +308,18 @@ MMU_API int mmu_mmbt_forward(const mmu_mmbt_config* cfg, const float* params, co
 MMU_API int mmu_mmbt_backward(const mmu_mmbt_config* cfg, const float* params, const mmu_mmbt_inputs* in,
                       void* workspace, long long workspace_bytes, const float* dlogits, float* grads,
                       void* stream);
+/* Sequence-axis self-attention of the MMBT path's BERT encoder (pytorch_pretrained_bert
+ * BertSelfAttention as called from src/mmbt.py:124-128, additive mask of :103-107).
+ * qkv (dtype) [B*S, 3D] packed q|k|v; addmask fp32 [B, S]; out (dtype) [B*S, D].
+ * dtype 1 (bf16, head_dim % 64 == 0): tcgen05; probs bf16 [B*H, S, Sp] (Sp = S rounded up to 8),
+ * scores fp32 / dprobs bf16 scratch of that shape.  dtype 0: fp32 SIMT parity path, probs fp32
+ * [B*H, S, S].  flags bit 0: keep the probabilities for the backward; bit 1: do NOT use the fused
+ * one-kernel forward (head_dim 64, S <= 512) -- A/B and test switch. */
+MMU_API int mmu_seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs,
+                          float* scores, int dtype, int B, int S, int D, int H, int flags, void* stream);
+MMU_API int mmu_seq_attention_bwd(const void* qkv, const void* dout, const void* probs, float* scores,
+                          void* dprobs, void* dqkv, int dtype, int B, int S, int D, int H, void* stream);
+
 /* MMBT image encoder (reference src/mmbt.py:15-45 ImageEncoder): torchvision Bottleneck ResNet trunk
  * (resnet152: layers {3, 8, 36, 3}, children()[:-2]) + AdaptiveAvg/MaxPool2d to num_image_embeds
  * cells, flattened to (B, N, 2048) tokens.  Parameter names are the nn.Sequential keys

@@ -28,6 +28,7 @@ EXPORTS = [
     "mmu_mmbt_backward", "mmu_bertadam_flat_step",
     "mmu_imgenc_param_count", "mmu_imgenc_stat_count", "mmu_imgenc_param_table", "mmu_imgenc_stat_table",
     "mmu_imgenc_workspace_bytes", "mmu_imgenc_forward", "mmu_imgenc_backward",
+    "mmu_seq_attention_fwd", "mmu_seq_attention_bwd",
 ]
 
 
@@ -144,6 +145,8 @@ def _load():
     lib.mmu_flava_num_stages.argtypes = [cfgp]
     lib.mmu_flava_forward.argtypes = [cfgp, vp, C.POINTER(FlavaInputs), vp, ll, i, vp, vp]
     lib.mmu_flava_backward.argtypes = [cfgp, vp, C.POINTER(FlavaInputs), vp, ll, vp, vp, i, i, vp]
+    lib.mmu_seq_attention_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    lib.mmu_seq_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]
     icfgp = C.POINTER(ImgEncConfig)
     for fn in (lib.mmu_imgenc_param_count, lib.mmu_imgenc_stat_count):
         fn.restype, fn.argtypes = ll, [icfgp]

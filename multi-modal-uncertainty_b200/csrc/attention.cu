@@ -666,12 +666,17 @@ softmax_bwd_kernel(float* __restrict__ dP, const float* __restrict__ P, int rows
 }  // namespace attn
 
 int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, float* scores,
-                      int dtype, int B, int S, int D, int H, cudaStream_t stream) {
+                      int dtype, int B, int S, int D, int H, cudaStream_t stream, int keep_probs,
+                      int allow_fused) {
   using namespace attn;
   if (qkv == nullptr || addmask == nullptr || out == nullptr || probs == nullptr) return MMU_ERR_ARG;
   if (B < 1 || S < 1 || H < 1 || D % H != 0) return MMU_ERR_SHAPE;
   if (dtype == DT_BF16) {
     if ((D / H) % 64 != 0 || scores == nullptr) return MMU_ERR_SHAPE;
+    if (allow_fused) {  // one fused kernel when it applies (head_dim 64, S <= 512)
+      const int rc = fused_seq_attention_fwd(qkv, addmask, out, keep_probs ? probs : nullptr, B, S, D, H, stream);
+      if (rc <= 0) return rc;
+    }
     return tc::seq_fwd(qkv, addmask, out, probs, scores, B, S, D, H, stream);
   }
   using seq32::Strided;

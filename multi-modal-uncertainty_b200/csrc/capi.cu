@@ -324,4 +324,14 @@ int mmu_imgenc_backward(const mmu_imgenc_config* cfg, const float* params, const
                          grads, S(stream));
 }
 
+int mmu_seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, float* scores,
+                          int dtype, int B, int seq, int D, int H, int flags, void* stream) {
+  return seq_attention_fwd(qkv, addmask, out, probs, scores, dtype, B, seq, D, H, S(stream), flags & 1,
+                           (flags & 2) ? 0 : 1);
+}
+int mmu_seq_attention_bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
+                          void* dqkv, int dtype, int B, int seq, int D, int H, void* stream) {
+  return seq_attention_bwd(qkv, dout, probs, scores, dprobs, dqkv, dtype, B, seq, D, H, S(stream));
+}
+
 }  // extern "C"

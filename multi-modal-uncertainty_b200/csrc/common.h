@@ -20,4 +20,8 @@ long long launch_count();
 int sm_count();
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, long long inner, long long outer,
                       long long ld, int box_inner, int box_outer);
+// 3-D (inner contiguous, mid, outer; element strides), box = box_inner x 1 x box_outer, SWIZZLE_128B
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, long long inner, long long mid,
+                      long long outer, long long mid_stride, long long outer_stride, int box_inner,
+                      int box_outer);
 }  // namespace mmu

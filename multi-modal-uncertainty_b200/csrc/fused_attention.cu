@@ -1,0 +1,337 @@
+// Fused sequence-axis attention forward for the BERT encoder of the MMBT path (head_dim 64,
+// S <= 512): ONE kernel per layer instead of  scores GEMM -> masked softmax -> P V GEMM, and the
+// fp32 score matrix (B*H*S*S*4 bytes = 402 MB per layer at B = 32, S = 512) never exists in HBM.
+//
+// One CTA per (sample b, head h, 128-query tile):
+//   TMA : Q tile [128 x 64], K [S x 64] (K-major, 128-key boxes), V [S x 64] (MN-major, 64-key
+//         boxes) from the packed qkv buffer -> shared memory (144 KB)
+//   MMA1: S = Q K^T, one tcgen05.mma group per 128-key block -> ALL of TMEM (128 lanes x 512 fp32
+//         columns hold the whole score tile)
+//   softmax: 8 warps; warp w owns TMEM lane quadrant w % 4 (a thread = one query row) and one half
+//         of the key columns; pass 1 row max, (pass 2 row sum when P is kept,) last pass
+//         p = exp2(s * scale * log2e + mask - max) [* 1/sum] -> bf16 -> a [128 x 64] SWIZZLE_128B
+//         K-major tile in shared memory (two buffers per column half); the two halves exchange
+//         (max, sum) through shared memory
+//   MMA2: O += P_chunk V_chunk as soon as a chunk is staged; the accumulator reuses TMEM columns
+//         0..63, which chunk 0's last pass has already drained (chunk 0 is always issued first)
+//   TMA store of every P chunk to the probs tensor when the backward needs it (training)
+//   epilogue: O (x 1/sum in the 2-pass variant) -> bf16 -> out[b, s, h*64 ...]
+// Reference: pytorch_pretrained_bert BertSelfAttention as called from src/mmbt.py:124-128, with the
+// additive mask of src/mmbt.py:103-107.
+#include <cuda_bf16.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace mmu {
+namespace fattn {
+
+constexpr int HD = 64;
+constexpr int BQ = 128;          // queries per CTA
+constexpr int SMAX = 512;        // keys: the whole row of scores lives in TMEM
+constexpr int KB = 128;          // keys per MMA1 block / K box
+constexpr int CH = 64;           // keys per P chunk / V box
+constexpr int THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 softmax
+constexpr int OFF_Q = 0;                          // 16 KB
+constexpr int OFF_K = OFF_Q + BQ * HD * 2;        // 4 x 16 KB
+constexpr int OFF_V = OFF_K + SMAX * HD * 2;      // 8 x 8 KB
+constexpr int OFF_P = OFF_V + SMAX * HD * 2;      // 2 halves x 2 buffers x 16 KB
+constexpr int P_BYTES = BQ * CH * 2;
+constexpr int OFF_MASK = OFF_P + 4 * P_BYTES;     // 512 floats
+constexpr int OFF_XCH = OFF_MASK + SMAX * 4;      // float2 [2][128]
+constexpr int OFF_BARS = OFF_XCH + 2 * BQ * 8;
+constexpr int SMEM_USED = OFF_BARS + 16 * 8 + 16;
+constexpr int SMEM_BYTES = SMEM_USED + 1024;      // slack for the 1024-byte alignment
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void nbar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <bool SAVE_P>
+__global__ void __launch_bounds__(THREADS, 1)
+fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_v,
+                 const __grid_constant__ CUtensorMap tm_p, const float* __restrict__ addmask,
+                 __nv_bfloat16* __restrict__ out, int B, int S, int D, int H, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+  uint64_t* qk_full = bars;        // Q + K landed
+  uint64_t* v_full = bars + 1;     // V landed
+  uint64_t* s_full = bars + 2;     // scores complete in TMEM
+  uint64_t* o_full = bars + 3;     // O complete in TMEM
+  uint64_t* p_full = bars + 4;     // [2 halves][2 buffers]
+  uint64_t* p_empty = bars + 8;    // [2][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* mask_s = reinterpret_cast<float*>(smem + OFF_MASK);
+  float2* xch = reinterpret_cast<float2*>(smem + OFF_XCH);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tiles = (S + BQ - 1) / BQ;
+  const int g = blockIdx.x / q_tiles, qt = blockIdx.x % q_tiles;
+  const int b = g / H, h = g % H;
+  const int q0 = qt * BQ;
+  const int n_kb = (S + KB - 1) / KB;   // MMA1 blocks
+  const int n_ch = (S + CH - 1) / CH;   // P / V chunks
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_qk);
+    ptx::prefetch_tmap(&tm_v);
+    if (SAVE_P) ptx::prefetch_tmap(&tm_p);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&p_full[i], 1);
+      ptx::mbar_init(&p_empty[i], 1);
+    }
+    ptx::fence_mbar_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  // additive mask of this sample, pre-multiplied by log2(e); keys >= S are excluded outright
+  for (int k = threadIdx.x; k < SMAX; k += THREADS)
+    mask_s[k] = k < S ? addmask[static_cast<size_t>(b) * S + k] * 1.4426950408889634f : -INFINITY;
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(qk_full, BQ * HD * 2 + n_kb * KB * HD * 2);
+      ptx::tma_load_3d(smem + OFF_Q, &tm_qk, qk_full, h * HD, b, q0);
+      for (int kb = 0; kb < n_kb; ++kb)
+        ptx::tma_load_3d(smem + OFF_K + kb * KB * HD * 2, &tm_qk, qk_full, D + h * HD, b, kb * KB);
+      ptx::mbar_arrive_expect_tx(v_full, n_ch * CH * HD * 2);
+      for (int c = 0; c < n_ch; ++c)
+        ptx::tma_load_3d(smem + OFF_V + c * CH * HD * 2, &tm_v, v_full, 2 * D + h * HD, b, c * CH);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA1: S[128 x 128*n_kb] = Q K^T
+      ptx::mbar_wait(qk_full, 0);
+      ptx::tc_fence_after();
+      const uint32_t id1 = ptx::make_idesc_bf16(BQ, KB, 0, 0);
+      const uint32_t sq = ptx::smem_u32(smem + OFF_Q);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const uint32_t sk = ptx::smem_u32(smem + OFF_K + kb * KB * HD * 2);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          ptx::umma_bf16(tmem + kb * KB, ptx::make_smem_desc_sw128(sq + k * 32, 16u, 1024u),
+                         ptx::make_smem_desc_sw128(sk + k * 32, 16u, 1024u), id1, k > 0 ? 1u : 0u);
+      }
+      ptx::umma_commit(s_full);
+      // ---- MMA2: O[128 x 64] += P_chunk V_chunk, chunk 0 first (its columns become the accumulator)
+      ptx::mbar_wait(v_full, 0);
+      const uint32_t id2 = ptx::make_idesc_bf16(BQ, HD, 0, 1);
+      const int per_half = 4;
+      bool first = true;
+      for (int i = 0; i < per_half; ++i) {
+        for (int hh = 0; hh < 2; ++hh) {
+          const int c = hh * per_half + i;
+          if (c >= n_ch) continue;
+          const int buf = i & 1;
+          ptx::mbar_wait(&p_full[hh * 2 + buf], (i >> 1) & 1);
+          ptx::tc_fence_after();
+          const uint32_t sp = ptx::smem_u32(smem + OFF_P + (hh * 2 + buf) * P_BYTES);
+          const uint32_t sv = ptx::smem_u32(smem + OFF_V + c * CH * HD * 2);
+#pragma unroll
+          for (int k = 0; k < CH / 16; ++k) {
+            ptx::umma_bf16(tmem, ptx::make_smem_desc_sw128(sp + k * 32, 16u, 1024u),
+                           ptx::make_smem_desc_sw128(sv + k * 2048, 8192u, 1024u), id2,
+                           (first && k == 0) ? 0u : 1u);
+          }
+          first = false;
+          ptx::umma_commit(&p_empty[hh * 2 + buf]);
+        }
+      }
+      ptx::umma_commit(o_full);
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax warps
+    const int we = warp - 2;
+    const int q = warp & 3;            // TMEM lane quadrant (hardware: lanes 32*(warp % 4)..)
+    const int hh = we >> 2;            // which half of the key columns
+    const int row = q * 32 + lane;     // query row within the tile
+    const float sc = scale * 1.4426950408889634f;
+    const int c_begin = hh * 4, c_end = min(n_ch, hh * 4 + 4);   // this half's chunks
+    const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    ptx::mbar_wait(s_full, 0);
+    ptx::tc_fence_after();
+    uint32_t r[32];
+    // pass 1: row maximum over this half's columns
+    float mx = -INFINITY;
+    for (int c = c_begin; c < c_end; ++c) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
+        ptx::tmem_ld_wait();
+        const float* ms = mask_s + c * CH + j * 32;
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], fmaf(__uint_as_float(r[i]), sc, ms[i]));
+        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      }
+    }
+    float sum = 0.f;
+    if (SAVE_P) {  // pass 2: row sum, so that the NORMALISED probabilities can be stored
+      xch[hh * BQ + row] = make_float2(mx, 0.f);
+      nbar(3 + q, 64);
+      mx = fmaxf(mx, xch[(hh ^ 1) * BQ + row].x);
+      nbar(3 + q, 64);
+      for (int c = c_begin; c < c_end; ++c) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
+          ptx::tmem_ld_wait();
+          const float* ms = mask_s + c * CH + j * 32;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s4[i & 3] += ex2f(fmaf(__uint_as_float(r[i]), sc, ms[i]) - mx);
+          sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        }
+      }
+      xch[hh * BQ + row] = make_float2(mx, sum);
+      nbar(3 + q, 64);
+      sum += xch[(hh ^ 1) * BQ + row].y;
+      nbar(3 + q, 64);
+    } else {
+      xch[hh * BQ + row] = make_float2(mx, 0.f);
+      nbar(3 + q, 64);
+      mx = fmaxf(mx, xch[(hh ^ 1) * BQ + row].x);
+      nbar(3 + q, 64);
+    }
+    const float inv = SAVE_P ? 1.0f / sum : 1.0f;
+    // last pass: probabilities -> bf16 -> swizzled K-major tile -> MMA2 (and the probs tensor)
+    const uint32_t prow = static_cast<uint32_t>(row >> 3) * 1024u + static_cast<uint32_t>(row & 7) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    const bool issuer = (q == 2 && lane == 0);  // warp 2 / warp 6: first warp of each half
+    for (int c = c_begin; c < c_end; ++c) {
+      const int i = c - c_begin, buf = i & 1;
+      const uint32_t pbuf = ptx::smem_u32(smem + OFF_P + (hh * 2 + buf) * P_BYTES);
+      if (i >= 2) {
+        ptx::mbar_wait(&p_empty[hh * 2 + buf], 0);     // MMA2 has consumed the previous tile
+        if (SAVE_P) {
+          if (issuer) ptx::bulk_wait_read<1>();        // ... and so has its TMA store
+          nbar(1 + hh, 128);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
+        ptx::tmem_ld_wait();
+        const float* ms = mask_s + c * CH + j * 32;
+        float v[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] = ex2f(fmaf(__uint_as_float(r[t]), sc, ms[t]) - mx) * inv;
+        if (!SAVE_P) {
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int t = 0; t < 32; ++t) s4[t & 3] += v[t];
+          sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t piece = static_cast<uint32_t>(j * 4 + k);
+          ptx::sts_v4u(pbuf + prow + ((piece ^ sw) << 4), pack2(v[8 * k], v[8 * k + 1]),
+                       pack2(v[8 * k + 2], v[8 * k + 3]), pack2(v[8 * k + 4], v[8 * k + 5]),
+                       pack2(v[8 * k + 6], v[8 * k + 7]));
+        }
+      }
+      if (c == 0) ptx::tc_fence_before();  // columns 0..63 are drained before MMA2 overwrites them
+      ptx::fence_proxy_async();
+      nbar(1 + hh, 128);
+      if (issuer) {
+        ptx::mbar_arrive(&p_full[hh * 2 + buf]);
+        if (SAVE_P) {
+          ptx::tma_store_3d(&tm_p, pbuf, c * CH, g, q0);
+          ptx::bulk_commit();
+        }
+      }
+    }
+    float inv_o = 1.0f;
+    if (!SAVE_P) {
+      xch[hh * BQ + row] = make_float2(mx, sum);
+      nbar(3 + q, 64);
+      sum += xch[(hh ^ 1) * BQ + row].y;
+      inv_o = 1.0f / sum;
+    }
+    // ---- epilogue: this warp's 32 rows x 32 of the 64 output columns
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    ptx::tmem_ld_32x32(trow + hh * 32, r);
+    ptx::tmem_ld_wait();
+    if (q0 + row < S) {
+      __nv_bfloat16* o = out + (static_cast<size_t>(b) * S + q0 + row) * D + h * HD + hh * 32;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint4 pk;
+        pk.x = pack2(__uint_as_float(r[8 * k]) * inv_o, __uint_as_float(r[8 * k + 1]) * inv_o);
+        pk.y = pack2(__uint_as_float(r[8 * k + 2]) * inv_o, __uint_as_float(r[8 * k + 3]) * inv_o);
+        pk.z = pack2(__uint_as_float(r[8 * k + 4]) * inv_o, __uint_as_float(r[8 * k + 5]) * inv_o);
+        pk.w = pack2(__uint_as_float(r[8 * k + 6]) * inv_o, __uint_as_float(r[8 * k + 7]) * inv_o);
+        *reinterpret_cast<uint4*>(o + 8 * k) = pk;
+      }
+    }
+    if (SAVE_P && issuer) ptx::bulk_wait<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace fattn
+
+// Returns 1 when the fused kernel does not apply (caller falls back to the three-kernel path).
+int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, int B, int S,
+                            int D, int H, cudaStream_t stream) {
+  using namespace fattn;
+  static const bool disabled = getenv("MMU_ATTN_UNFUSED") != nullptr;  // A/B switch
+  if (disabled || D / H != HD || D % H != 0 || S > SMAX || S < 1) return 1;
+  const int Sp = (S + 7) / 8 * 8;
+  CUtensorMap tq, tv, tp;
+  int rc = make_tmap_bf16_3d(&tq, qkv, 3LL * D, B, S, 3LL * D * S, 3LL * D, HD, KB);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tv, qkv, 3LL * D, B, S, 3LL * D * S, 3LL * D, HD, CH);
+  if (rc) return rc;
+  tp = tq;
+  if (probs != nullptr) {
+    rc = make_tmap_bf16_3d(&tp, probs, Sp, static_cast<long long>(B) * H, S, static_cast<long long>(S) * Sp,
+                           Sp, CH, BQ);
+    if (rc) return rc;
+  }
+  const int grid = B * H * ((S + BQ - 1) / BQ);
+  const float scale = 1.0f / sqrtf(static_cast<float>(HD));
+  auto launch = [&](auto kernel) -> int {
+    static cudaError_t attr = cudaSuccess;
+    attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (attr != cudaSuccess) return MMU_ERR_CUDA;
+    kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tq, tv, tp, addmask, static_cast<__nv_bfloat16*>(out), B, S,
+                                                  D, H, scale);
+    if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+    count_launch();
+    return 0;
+  };
+  return probs != nullptr ? launch(fattn_fwd_kernel<true>) : launch(fattn_fwd_kernel<false>);
+}
+
+}  // namespace mmu

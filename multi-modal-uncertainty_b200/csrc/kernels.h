@@ -102,8 +102,14 @@ int attention_bwd(const void* qkv, const void* out, const void* dout, const floa
 // bf16 (head_dim % 64 == 0): batched tcgen05 GEMMs; probs bf16 [B*H, S, Sp] kept for the backward,
 // scores fp32 / dprobs bf16 scratch of the same shape (Sp = S rounded up to 8).
 // fp32: probs fp32 [B*H, S, S] kept for the backward, scores fp32 scratch (backward only).
+// keep_probs == 0 (inference): the fused bf16 kernel does not write the probabilities at all.
 int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, float* scores,
-                      int dtype, int B, int S, int D, int H, cudaStream_t stream);
+                      int dtype, int B, int S, int D, int H, cudaStream_t stream, int keep_probs = 1,
+                      int allow_fused = 1);
+// Fused forward (fused_attention.cu): head_dim 64, S <= 512; probs may be null (inference: nothing
+// but O is written).  Returns 1 when it does not apply, 0 on success, < 0 on error.
+int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, int B, int S,
+                            int D, int H, cudaStream_t stream);
 int seq_attention_bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
                       void* dqkv, int dtype, int B, int S, int D, int H, cudaStream_t stream);
 

@@ -588,7 +588,8 @@ int mmbt_forward(const MmbtConfig& c, const float* params, const MmbtInputs& in,
     const LayerP& p = lay.layer[i];
     const LayerWs& l = w.layer[i];
     MB_TRY(gemm(h, D, 0, W(p.q_w), D, 0, M, 3 * D, D, epi(EPI_STORE, l.qkv, bf, 3 * D, params + p.q_b)));
-    MB_TRY(seq_attention_fwd(l.qkv, w.addmask, l.ctx, l.probs, w.scores, dt, c.B, S, D, c.n_head, stream));
+    MB_TRY(seq_attention_fwd(l.qkv, w.addmask, l.ctx, l.probs, w.scores, dt, c.B, S, D, c.n_head, stream,
+                             training));
     MB_TRY(gemm(l.ctx, D, 0, W(p.ao_w), D, 0, M, D, D, epi(EPI_STORE, w.ybuf, bf, D, params + p.ao_b)));
     MB_TRY(postln_fwd(h, w.ybuf, training ? l.s1 : nullptr, params + p.ln1_w, params + p.ln1_b, l.a, dt,
                       training ? l.st1 : nullptr, training ? l.st1 + M : nullptr, M, D, BERT_LN_EPS,

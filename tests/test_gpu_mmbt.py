@@ -269,3 +269,56 @@ def test_image_encoder_bf16_and_full_mmbt_from_images(mmu, golden):
     m.zero_grad()
     m.compute_loss(m(*x), g["y"].cuda()).backward()
     assert float(dict(named)["enc.img_encoder.model.0.weight"].grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,S,H", [(2, 512, 12), (3, 333, 2), (2, 64, 1), (1, 130, 3), (2, 8, 2)])
+def test_fused_attention_matches_three_kernel_path_and_fp64(mmu, B, S, H):
+    """The fused one-kernel attention forward (TMEM-resident scores) against the three-kernel
+    tensor-core path and an fp64 softmax(QK^T/8 + mask)V on the same bf16 inputs: context within
+    bf16 rounding, saved probabilities within bf16 resolution, padded keys exactly zero; the
+    backward run from the fused kernel's probabilities matches the fp64 gradients."""
+    lib, L = mmu._lib.lib, mmu._lib
+    D, hd = 64 * H, 64
+    g = torch.Generator().manual_seed(S)
+    qkv = (torch.randn(B * S, 3 * D, generator=g) * 1.5).bfloat16().cuda()
+    lens = torch.randint(S // 2, S + 1, (B,), generator=g)
+    lens[0] = S
+    keep = (torch.arange(S)[None] < lens[:, None])
+    addmask = ((1.0 - keep.float()) * -10000.0).cuda()
+    Sp = (S + 7) // 8 * 8
+    G = B * H
+    outs = {}
+    for flags in (1, 3, 0):  # fused + probs, unfused + probs, fused inference (no probs)
+        out = torch.zeros(B * S, D, dtype=torch.bfloat16, device="cuda")
+        probs = torch.full((G, S, Sp), 7.0, dtype=torch.bfloat16, device="cuda")
+        scores = torch.empty(G, S, Sp, dtype=torch.float32, device="cuda")
+        L.check(lib.mmu_seq_attention_fwd(qkv.data_ptr(), addmask.data_ptr(), out.data_ptr(), probs.data_ptr(),
+                                          scores.data_ptr(), 1, B, S, D, H, flags, L.stream_ptr()))
+        torch.cuda.synchronize()
+        outs[flags] = (out.float().cpu(), probs.float().cpu())
+    q, k, v = (qkv.float().cpu().double().view(B, S, 3, H, hd)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    sc = q @ k.transpose(-1, -2) / 8.0 + addmask.cpu().double()[:, None, None, :]
+    P = torch.softmax(sc, -1)
+    ctx = (P @ v).permute(0, 2, 1, 3).reshape(B * S, D)
+    for flags in (1, 3, 0):
+        assert rel(outs[flags][0], ctx) < 2e-2, flags
+    for flags in (1, 3):
+        pr = outs[flags][1]
+        assert float((pr[:, :, :S].double() - P.reshape(G, S, S)).abs().max()) < 8e-3, flags
+        if Sp > S:
+            assert float(pr[:, :, S:].abs().max()) == 0.0
+    assert float((outs[1][0] - outs[3][0]).abs().max()) < 2e-2 * float(ctx.abs().max())
+    assert torch.equal(outs[0][1], torch.full((G, S, Sp), 7.0))  # inference writes no probabilities
+    # backward from the fused forward's probabilities
+    dout = (torch.randn(B * S, D, generator=g)).bfloat16().cuda()
+    probs = outs[1][1].bfloat16().cuda()
+    scores = torch.empty(G, S, Sp, dtype=torch.float32, device="cuda")
+    dprobs = torch.empty(G, S, Sp, dtype=torch.bfloat16, device="cuda")
+    dqkv = torch.zeros_like(qkv)
+    L.check(lib.mmu_seq_attention_bwd(qkv.data_ptr(), dout.data_ptr(), probs.data_ptr(), scores.data_ptr(),
+                                      dprobs.data_ptr(), dqkv.data_ptr(), 1, B, S, D, H, L.stream_ptr()))
+    x = qkv.float().cpu().double().requires_grad_(True)
+    q, k, v = (x.view(B, S, 3, H, hd)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    P = torch.softmax(q @ k.transpose(-1, -2) / 8.0 + addmask.cpu().double()[:, None, None, :], -1)
+    ((P @ v).permute(0, 2, 1, 3).reshape(B * S, D) * dout.float().cpu().double()).sum().backward()
+    assert rel(dqkv.float().cpu(), x.grad) < 4e-2
