@@ -351,7 +351,8 @@ MMU_API int mmu_imgenc_backward(const mmu_imgenc_config* cfg, const float* param
 MMU_API int mmu_bertadam_flat_step(float* p, float* g, float* m, float* v, void* p_bf16,
                            const long long* segs, const float* seg_hyper, float* norms, int n_seg,
                            long long max_seg_numel, float b1, float b2, float eps,
-                           float max_grad_norm, void* stream);
+                           float max_grad_norm, float grad_scale /* applied to g first: 1/world */,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -161,7 +161,7 @@ def _load():
     lib.mmu_mmbt_workspace_bytes.restype, lib.mmu_mmbt_workspace_bytes.argtypes = ll, [mcfgp, i]
     lib.mmu_mmbt_forward.argtypes = [mcfgp, vp, minp, vp, ll, i, vp, vp]
     lib.mmu_mmbt_backward.argtypes = [mcfgp, vp, minp, vp, ll, vp, vp, vp]
-    lib.mmu_bertadam_flat_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, ll, f, f, f, f, vp]
+    lib.mmu_bertadam_flat_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, ll, f, f, f, f, f, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int:

@@ -280,9 +280,10 @@ int mmu_mmbt_backward(const mmu_mmbt_config* cfg, const float* params, const mmu
 }
 int mmu_bertadam_flat_step(float* p, float* g, float* m, float* v, void* p_bf16, const long long* segs,
                            const float* seg_hyper, float* norms, int n_seg, long long max_seg_numel,
-                           float b1, float b2, float eps, float max_grad_norm, void* stream) {
+                           float b1, float b2, float eps, float max_grad_norm, float grad_scale,
+                           void* stream) {
   return bertadam_flat(p, g, m, v, p_bf16, segs, seg_hyper, norms, n_seg, max_seg_numel, b1, b2, eps,
-                       max_grad_norm, S(stream));
+                       max_grad_norm, grad_scale, S(stream));
 }
 
 namespace {

@@ -787,17 +787,19 @@ __global__ void __launch_bounds__(256)
 bertadam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 __nv_bfloat16* __restrict__ p_lp, const long long* __restrict__ segs,
                 const float* __restrict__ seg_hyper, const float* __restrict__ norms, int chunk,
-                float b1, float b2, float eps, float max_norm) {
+                float b1, float b2, float eps, float max_norm, float grad_scale) {
   const int sgi = blockIdx.y;
   const long long off = segs[2 * sgi], numel = segs[2 * sgi + 1];
   const long long c0 = static_cast<long long>(blockIdx.x) * chunk;
   if (c0 >= numel) return;
   const long long c1 = min(numel, c0 + chunk);
   // torch.nn.utils.clip_grad_norm_(p, max_norm): coef = max_norm / (||g|| + 1e-6), applied if < 1
-  float coef = 1.0f;
+  // grad_scale (1 / world size after a sum-all-reduce) is applied before the clip, as if the
+  // averaged gradient had been stored: ||s g|| = s ||g||
+  float coef = grad_scale;
   if (max_norm > 0.f) {
-    const float cc = max_norm / (sqrtf(norms[sgi]) + 1e-6f);
-    coef = cc < 1.0f ? cc : 1.0f;
+    const float cc = max_norm / (grad_scale * sqrtf(norms[sgi]) + 1e-6f);
+    coef = cc < 1.0f ? cc * grad_scale : grad_scale;
   }
   const float wd = seg_hyper[2 * sgi], lr = seg_hyper[2 * sgi + 1];
   for (long long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
@@ -820,7 +822,7 @@ bertadam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict_
 
 int bertadam_flat(float* p, float* g, float* m, float* v, void* p_bf16, const long long* segs,
                   const float* seg_hyper, float* norms, int n_seg, long long max_seg_numel, float b1,
-                  float b2, float eps, float max_grad_norm, cudaStream_t stream) {
+                  float b2, float eps, float max_grad_norm, float grad_scale, cudaStream_t stream) {
   if (p == nullptr || g == nullptr || m == nullptr || v == nullptr || segs == nullptr ||
       seg_hyper == nullptr || norms == nullptr)
     return MMU_ERR_ARG;
@@ -835,7 +837,7 @@ int bertadam_flat(float* p, float* g, float* m, float* v, void* p_bf16, const lo
     MB_CHECK_LAUNCH();
   }
   bertadam_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p_bf16), segs,
-                                            seg_hyper, norms, chunk, b1, b2, eps, max_grad_norm);
+                                            seg_hyper, norms, chunk, b1, b2, eps, max_grad_norm, grad_scale);
   MB_CHECK_LAUNCH();
   return 0;
 }

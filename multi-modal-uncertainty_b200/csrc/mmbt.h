@@ -63,9 +63,10 @@ int mmbt_backward(const MmbtConfig& c, const float* params, const MmbtInputs& in
 // the caller supplies it per tensor.
 // segs: device int64 [n_seg][2] = (offset, numel) of every tensor in the flat buffer;
 // seg_hyper: device float [n_seg][2] = (weight_decay, scheduled lr) per tensor; norms: device float
-// [n_seg] scratch; max_seg_numel: the largest tensor's element count (sizes the grid).
+// [n_seg] scratch; max_seg_numel: the largest tensor's element count (sizes the grid); grad_scale:
+// factor applied to g before everything else (1 / world size after a sum-all-reduce).
 int bertadam_flat(float* p, float* g, float* m, float* v, void* p_bf16, const long long* segs,
                   const float* seg_hyper, float* norms, int n_seg, long long max_seg_numel, float b1,
-                  float b2, float eps, float max_grad_norm, cudaStream_t stream);
+                  float b2, float eps, float max_grad_norm, float grad_scale, cudaStream_t stream);
 
 }  // namespace mmu

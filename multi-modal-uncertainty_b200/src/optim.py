@@ -148,6 +148,9 @@ class BertAdam(torch.optim.Optimizer):
     def step(self, closure=None):
         import ctypes as C  # noqa: F401
         from ._backend import _lib
+        sync = getattr(self, "_flat_sync", None)
+        if sync is not None:
+            sync.all_reduce_grads()  # sum over ranks; 1/world is folded into the kernel (grad_scale)
         for owner in self._owners:
             flat = owner._flat
             active = [(p, g) for g in self.param_groups for p in g["params"]
@@ -183,7 +186,8 @@ class BertAdam(torch.optim.Optimizer):
             _lib.check(_lib.lib.mmu_bertadam_flat_step(
                 flat.data_ptr(), owner._flat_grad.data_ptr(), m.data_ptr(), v.data_ptr(), _lib.ptr(shadow),
                 segs.data_ptr(), hyper.data_ptr(), norms.data_ptr(), len(active), max_numel,
-                g0["b1"], g0["b2"], g0["e"], g0["max_grad_norm"], _lib.stream_ptr()),
+                g0["b1"], g0["b2"], g0["e"], g0["max_grad_norm"], float(self.grad_scale),
+                _lib.stream_ptr()),
                 "mmu_bertadam_flat_step")
             if shadow is not None:
                 if len(active) == len(list(owner._param_list)):

@@ -98,3 +98,35 @@ class DataParallel:
         self._works = []
         if self._comm is not None:
             torch.cuda.current_stream().wait_stream(self._comm)
+
+
+class FlatGradSync:
+    """Data parallelism for models made of several flat-buffer owners (the MMBT path: BERT trunk +
+    image encoder) with the fused ``BertAdam``: parameters (and BatchNorm running statistics) are
+    broadcast from rank 0 once; ``optimizer.step()`` then sum-all-reduces every owner's flat
+    gradient buffer (one collective per owner) and the 1/world factor is folded into the update
+    kernel.  BatchNorm batch statistics stay rank-local, as under ``DistributedDataParallel``
+    without SyncBN.  ``attach(model, optimizer)`` wires it up."""
+
+    def __init__(self, owners, group=None):
+        self.owners, self.group = list(owners), group
+        self.rank, self.world = world(group)
+        for o in self.owners:
+            broadcast_flat(o._flat, 0, group)
+            stats = getattr(o, "_stats", None)
+            if stats is not None:
+                broadcast_flat(stats, 0, group)
+            if hasattr(o, "invalidate_shadow"):
+                o.invalidate_shadow()
+
+    def all_reduce_grads(self):
+        if self.world > 1:
+            for o in self.owners:
+                dist.all_reduce(o._flat_grad, group=self.group)
+
+    @classmethod
+    def attach(cls, optimizer, group=None):
+        sync = cls(optimizer._owners, group)
+        optimizer._flat_sync = sync
+        optimizer.grad_scale = 1.0 / sync.world
+        return sync

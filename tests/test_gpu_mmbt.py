@@ -322,3 +322,28 @@ def test_fused_attention_matches_three_kernel_path_and_fp64(mmu, B, S, H):
     P = torch.softmax(q @ k.transpose(-1, -2) / 8.0 + addmask.cpu().double()[:, None, None, :], -1)
     ((P @ v).permute(0, 2, 1, 3).reshape(B * S, D) * dout.float().cpu().double()).sum().backward()
     assert rel(dqkv.float().cpu(), x.grad) < 4e-2
+
+
+def test_mmbt_robustness_sweep_matches_reference_variants(mmu, golden):
+    """run_mmbt_robustness (reference eval_mmbt_robustness.py:76-96): variants 0..2 are the golden
+    full / img_only / txt_only logits, the forward_control draws consume the host RNG exactly like a
+    loop of reference calls, image tokens are computed once per batch."""
+    c = golden("mmbt_small.pt")["hd64"]
+    cfg = c["cfg"]
+    m = build(mmu, c, "fp32").eval()
+    x = (c["txt"], c["mask"], c["segment"], c["img_tokens"])
+    gen = [(x, c["y"]), (tuple(t.flip(0) for t in x), c["y"].flip(0))]
+    torch.manual_seed(123)
+    preds, labels = mmu.robustness.run_mmbt_robustness(m, gen, n_repeats=3, device="cuda")
+    assert preds.shape == (2 * cfg["B"], 3 + 2 * 3, cfg["C"]) and labels.shape == (2 * cfg["B"],)
+    B = cfg["B"]
+    for v, key in enumerate(("logits_full", "logits_img_only", "logits_txt_only")):
+        assert rel(torch.from_numpy(preds[:B, v]), c[key]) < 1e-3, key
+        assert rel(torch.from_numpy(preds[B:, v]), c[key].flip(0)) < 1e-3, key
+    # the same host-RNG stream, replayed by hand
+    torch.manual_seed(123)
+    xd = [t.cuda() for t in x]
+    with torch.no_grad():
+        for v, modal in enumerate(["image"] * 3 + ["text"] * 3):
+            out = m.forward_control(*xd, modal).cpu()
+            assert torch.equal(out, torch.from_numpy(preds[:B, 3 + v])), (v, modal)

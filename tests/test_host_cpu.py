@@ -335,6 +335,19 @@ def _gloo_worker(rank, world, port, out_dir):
     assert torch.equal(words[:10].view(torch.float64), 2 * torch.arange(10, dtype=torch.float64) + 1)
     assert int(words[10]) == 150 and int(words[11 + 3]) == 15
     assert ph.compute()["n_samples"] == 150
+    # flat-buffer owners of the MMBT path (trunk + image encoder): broadcast + gradient sum
+    class Owner:
+        def __init__(self, n):
+            self._flat = torch.full((n,), float(rank + 1))
+            self._flat_grad = torch.arange(n, dtype=torch.float32) * (rank + 1)
+            self._stats = torch.full((3,), float(rank))
+    class Opt:
+        _owners = [Owner(5), Owner(7)]
+    sync = par.FlatGradSync.attach(Opt)
+    assert Opt.grad_scale == 0.5 and all(float(o._flat.sum()) == o._flat.numel() for o in Opt._owners)
+    assert all(float(o._stats.abs().sum()) == 0.0 for o in Opt._owners)
+    sync.all_reduce_grads()
+    assert torch.equal(Opt._owners[1]._flat_grad, torch.arange(7, dtype=torch.float32) * 3)
     # sample sharding: contiguous, disjoint, covering
     b, e = par.shard_range(1000003, rank, world)
     t = torch.tensor([b, e])

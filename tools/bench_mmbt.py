@@ -19,7 +19,15 @@ ap.add_argument("--precision", default="bf16")
 ap.add_argument("--images", action="store_true")
 ap.add_argument("--no-cpu", action="store_true")
 a = ap.parse_args()
-dev = torch.device("cuda:0")
+# one process per GPU under torchrun (weak scaling: `--batch` samples per rank, no data-path
+# collective but the gradient all-reduce inside optimizer.step())
+RANK, WORLD = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+LOCAL = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(LOCAL)
+if WORLD > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+dev = torch.device("cuda", LOCAL)
 B, S_txt, n_img, C = a.batch, a.s_txt, 3, 2
 vocab = types.SimpleNamespace(stoi={"[CLS]": 101, "[SEP]": 102, "[PAD]": 0})
 args = types.SimpleNamespace(bert_model="bert-base-uncased", hidden_sz=768, img_hidden_sz=2048,
@@ -32,7 +40,9 @@ no_decay = ["bias", "LayerNorm.bias", "LayerNorm.weight"]
 opt = mmu.BertAdam([{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
                     {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}],
                    lr=5e-5, warmup=0.1, t_total=1000)
-g = torch.Generator().manual_seed(42)
+if WORLD > 1:
+    mmu.parallel.FlatGradSync.attach(opt)
+g = torch.Generator().manual_seed(42 + RANK)
 txt = torch.randint(1000, 30522, (B, S_txt), generator=g)
 lens = torch.randint(S_txt // 2, S_txt + 1, (B,), generator=g)
 mask = (torch.arange(S_txt)[None] < lens[:, None]).long()
@@ -55,6 +65,8 @@ def timed(fn, n):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    if WORLD > 1:
+        dist.barrier()
     l0 = mmu._lib.lib.mmu_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -62,25 +74,31 @@ def timed(fn, n):
         r = fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n, r, (mmu._lib.lib.mmu_launch_count() - l0) // n
+    ms = e0.elapsed_time(e1) / n
+    if WORLD > 1:  # max over ranks, on the device clock
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return ms, r, (mmu._lib.lib.mmu_launch_count() - l0) // n
 
 
 S, D, L = n_img + 2 + S_txt, 768, 12
 flops_fwd = L * (24 * S * D * D + 4 * S * S * D) * B
 out = {"config": {"workload": "MMBT bert-base, seq %d, batch %d, %s, %s" % (S, B, a.precision, "images" if a.images else "pooled image tokens")}}
 ms, loss, nl = timed(train_step, a.steps)
-out["train"] = {"ms_per_step": round(ms, 3), "samples_per_s": round(B / ms * 1e3, 1), "loss": float(loss.detach()),
+out["n_gpus"] = WORLD
+out["train"] = {"ms_per_step": round(ms, 3), "samples_per_s": round(WORLD * B / ms * 1e3, 1), "loss": float(loss.detach()),
                 "tflops": round(3 * flops_fwd / ms / 1e9, 1), "gpu_launches": int(nl)}
 m.eval()
 with torch.no_grad():
     ms, _, nl = timed(lambda: m(txt, mask, segment, img), a.steps)
-    out["eval_forward"] = {"ms_per_step": round(ms, 3), "samples_per_s": round(B / ms * 1e3, 1),
+    out["eval_forward"] = {"ms_per_step": round(ms, 3), "samples_per_s": round(WORLD * B / ms * 1e3, 1),
                            "tflops": round(flops_fwd / ms / 1e9, 1), "gpu_launches": int(nl)}
     torch.manual_seed(0)
     ms, _, nl = timed(lambda: m.forward_control(txt, mask, segment, img, "text"), a.steps)
-    out["forward_control_text"] = {"ms_per_step": round(ms, 3), "samples_per_s": round(B / ms * 1e3, 1)}
+    out["forward_control_text"] = {"ms_per_step": round(ms, 3), "samples_per_s": round(WORLD * B / ms * 1e3, 1)}
 
-if not a.no_cpu and not a.images:
+if not a.no_cpu and not a.images and RANK == 0:
     # CPU oracle port, fp32, all host threads, bounded sample: batch 2 of the same shape, 1 train step
     from oracle import mmbt as O
     cores = len(os.sched_getaffinity(0))
@@ -93,4 +111,7 @@ if not a.no_cpu and not a.images:
     dt = time.perf_counter() - t0
     out["cpu_port_train"] = {"s_per_step": round(dt, 3), "samples_per_s": round(2 / dt, 2), "cores": cores,
                              "sample": "batch 2 of the same sequence length, 1 step (oracle/mmbt.py, fp32)"}
-print(json.dumps(out))
+if RANK == 0:
+    print(json.dumps(out))
+if WORLD > 1:
+    dist.destroy_process_group()
