@@ -20,8 +20,12 @@ Parity status
   and guided / random modality dropout have NO reference implementation
   (SURVEY.md section 0): **parity unpinned** for those; the definitions in
   ``oracle/uncertainty.py`` are the repo's own, written out in fp64.
-* MMBT / ViLT arithmetic lives in un-vendored third-party packages
-  (``pytorch_pretrained_bert``, unpinned): not restated here, **parity unpinned**.
+* MMBT: ``oracle/mmbt.py`` and ``oracle/image_encoder.py`` restate ``src/mmbt.py`` and are PINNED
+  to goldens from the unmodified reference module (``tests/golden/make_golden_mmbt.py``).  The
+  BERT layer arithmetic itself lives in the un-vendored, unpinned third-party
+  ``pytorch_pretrained_bert``; ``oracle/bert_restated.py`` restates its published definitions so
+  that the reference module can run here -- with respect to the absent package that part is
+  **parity unpinned (third-party)**.  ViLT: not restated.
 """
 
 from . import fusion, optim, shaping, uncertainty  # noqa: F401
