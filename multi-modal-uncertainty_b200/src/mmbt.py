@@ -289,6 +289,9 @@ class MultimodalBertClf(nn.Module):
         """General entry: ``indices`` (sequence of ints over ``[CLS] img.. [SEP] | text..``, or None
         for all positions) selects what enters the encoder."""
         tokens = self._tokens(img)
+        if self.training and float(getattr(self.args, "dropout", 0.0) or 0.0) > 0.0:
+            raise _lib.MMUError("dropout > 0 in training is not implemented (the engine computes the "
+                                "dropout-free network); train with args.dropout = 0 or call .eval()")
         if self.training and torch.is_grad_enabled():
             if tokens.requires_grad:
                 return _MmbtForward.apply(tokens, self, txt, mask, segment, indices)

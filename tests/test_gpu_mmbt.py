@@ -347,3 +347,79 @@ def test_mmbt_robustness_sweep_matches_reference_variants(mmu, golden):
         for v, modal in enumerate(["image"] * 3 + ["text"] * 3):
             out = m.forward_control(*xd, modal).cpu()
             assert torch.equal(out, torch.from_numpy(preds[:B, 3 + v])), (v, modal)
+
+
+def test_full_baseline_size_properties(mmu):
+    """BASELINE.json configs[3] at full size (BERT-base, 3 + 2 + 507 = 512 positions, batch 32, bf16)
+    through size-independent properties: an explicit all-positions index list equals the plain
+    forward bit for bit; token ids / segments under mask == 0 positions cannot influence the logits
+    beyond bf16 noise of their own rows; forward_img_only ignores the text altogether; the fused
+    attention and the three-kernel path agree; a few BertAdam steps reduce the loss; gradient sums
+    are finite everywhere."""
+    B, S_txt, n_img = 32, 507, 3
+    vocab = types.SimpleNamespace(stoi={"[CLS]": 101, "[SEP]": 102, "[PAD]": 0})
+    args = types.SimpleNamespace(bert_model="bert-base-uncased", hidden_sz=768, img_hidden_sz=2048,
+                                 num_image_embeds=n_img, img_embed_pool_type="avg", dropout=0.0, n_classes=2,
+                                 vocab=vocab, precision="bf16", img_encoder=None)
+    torch.manual_seed(0)
+    m = mmu.MultimodalBertClf(args).cuda().eval()
+    g = torch.Generator().manual_seed(1)
+    txt = torch.randint(1000, 30522, (B, S_txt), generator=g)
+    lens = torch.randint(S_txt // 3, S_txt + 1, (B,), generator=g)
+    lens[0], lens[1] = S_txt, 1
+    mask = (torch.arange(S_txt)[None] < lens[:, None]).long()
+    txt, segment = txt * mask, mask.clone()
+    tok = torch.randn(B, n_img, 2048, generator=g)
+    x = [t.cuda() for t in (txt, mask, segment, tok)]
+    with torch.no_grad():
+        base = m(*x)
+        assert torch.equal(base, m.forward_indices(*x, list(range(n_img + 2 + S_txt))))
+        assert bool(torch.isfinite(base).all())
+        # padded positions are masked keys: scrambling them moves nothing but rounding noise
+        txt2 = torch.where(mask.bool(), txt, torch.randint(1000, 30522, (B, S_txt), generator=g))
+        moved = m(txt2.cuda(), x[1], x[2], x[3])
+        assert float((moved - base).abs().max()) < 2e-2 * float(base.abs().max())
+        io = m.forward_img_only(*x)
+        assert torch.equal(io, m.forward_img_only(txt2.cuda(), x[1], torch.zeros_like(x[2]), x[3]))
+    m.train()
+    named = list(m.named_parameters())
+    # constant lr (t_total = -1): without bias correction the first updates are ~3 lr per element
+    opt = mmu.BertAdam([{"params": [p for _, p in named], "weight_decay": 0.01}], lr=5e-6)
+    y = torch.randint(0, 2, (B,), generator=g).cuda()
+    losses = []
+    for it in range(8):
+        opt.zero_grad()
+        loss = m.compute_loss(m(*x), y)
+        loss.backward()
+        if it == 0:
+            assert all(bool(torch.isfinite(p.grad).all()) for _, p in named)
+            assert float(dict(named)["enc.txt_embeddings.word_embeddings.weight"].grad[0].abs().max()) == 0.0
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(l == l for l in losses) and min(losses[4:]) < losses[0], losses
+    with pytest.raises(mmu._lib.MMUError):
+        args.dropout = 0.1
+        m(*x)
+    args.dropout = 0.0
+
+
+def test_trainer_runs_the_mmbt_branch_on_the_engine(mmu, golden, tmp_path):
+    """Model_.train_loop(mmbt=True) + eval_loop(mmbt=True, auc=True) with the CUDA MultimodalBertClf,
+    BertAdam and ReduceLROnPlateau, as train.py:132-162,296-330 wires them."""
+    c = golden("mmbt_small.pt")["fp32_small"]
+    cfg = c["cfg"]
+    m = build(mmu, c, "fp32")
+    named = list(m.named_parameters())
+    opt = mmu.BertAdam([{"params": [p for _, p in named], "weight_decay": 0.01}], lr=1e-3, warmup=0.1, t_total=50)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, "max", patience=1, factor=0.5)
+    x = (c["txt"], c["mask"], c["segment"], c["img_tokens"])
+    batches = [(x, c["y"])] * 3
+    trainer = mmu.Model_(m, opt, sched, lambda x, y, phase="train": (x, y), metrics=[mmu.acc], verbose=False)
+    trainer.to(torch.device("cuda"))
+    logs = []
+    cbs = [mmu.src.callbacks.LambdaCallback(on_epoch_end=lambda e, l: logs.append(dict(l)))]
+    trainer.train_loop(batches, valid_generator=batches[:1], epochs=3, steps_per_epoch=3, validation_steps=1,
+                       callbacks=cbs, scheduler_step_on="epoch", scheduler_metric="val_acc", mmbt=True,
+                       freeze_img=0, freeze_txt=2, gradient_accumulation_steps=1, auc=cfg["C"] == 2)
+    assert len(logs) == 3 and logs[-1]["loss"] < logs[0]["loss"]
+    assert {"acc", "val_loss", "val_acc", "val_auc"} <= set(logs[0])
