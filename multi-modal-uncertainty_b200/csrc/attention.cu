@@ -569,17 +569,22 @@ int seq_bwd(const void* qkv, const void* dout, const void* probs, float* scores,
             void* dqkv, int B, int S, int D, int H, cudaStream_t st) {
   const int hd = D / H, G = B * H, Sp = (S + 7) / 8 * 8;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
-  // dP = dO V^T
-  int rc = gemm_bf16_batched_launch(act_view_seq(dout, B, S, D, H, 0), qkv_view_seq(qkv, B, S, D, H, 2, 0),
-                                    G, S, Sp, hd, store_epi(scores, 0, Sp, 1.0f), 1, 0,
-                                    static_cast<long long>(S) * Sp, st);
-  if (rc) return rc;
-  const int rows = G * S;
-  softmax_bwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(
-      scores, static_cast<const __nv_bfloat16*>(probs), static_cast<__nv_bfloat16*>(dprobs), rows, S,
-      Sp, scale);
-  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
-  count_launch();
+  // dS = P o (dP - delta) / sqrt(hd), dP = dO V^T: one fused kernel (dP stays in TMEM) when it
+  // applies, else the dP GEMM (fp32 to HBM) + the row kernel
+  int rc = fused_seq_attention_bwd_ds(qkv, dout, probs, dprobs, B, S, D, H, st);
+  if (rc < 0) return rc;
+  if (rc > 0) {
+    rc = gemm_bf16_batched_launch(act_view_seq(dout, B, S, D, H, 0), qkv_view_seq(qkv, B, S, D, H, 2, 0),
+                                  G, S, Sp, hd, store_epi(scores, 0, Sp, 1.0f), 1, 0,
+                                  static_cast<long long>(S) * Sp, st);
+    if (rc) return rc;
+    const int rows = G * S;
+    softmax_bwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(
+        scores, static_cast<const __nv_bfloat16*>(probs), static_cast<__nv_bfloat16*>(dprobs), rows, S,
+        Sp, scale);
+    if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+    count_launch();
+  }
   __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(dqkv);
   const long long ld = 3LL * D, mid = 3LL * D * S;
   // dV = P^T dO ; dK = dS^T Q ; dQ = dS K

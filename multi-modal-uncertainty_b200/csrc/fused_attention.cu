@@ -299,6 +299,170 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Backward, first half, fused: dS = P o (dP - delta) / sqrt(hd) with dP = dO V^T and
+// delta_i = sum_j dP_ij P_ij -- replaces the dP GEMM (fp32 [G, S, S] written to HBM) + the row kernel
+// that read it back.  Same CTA geometry as the forward: dP of a 128-query tile is accumulated
+// straight into TMEM (512 columns), the saved probabilities of the tile arrive by TMA as eight
+// [128 x 64] SWIZZLE_128B chunks, the eight softmax warps make two passes (delta, then dS written
+// IN PLACE over P in shared memory) and every finished chunk leaves by one TMA store.
+constexpr int B_OFF_DO = 0;                           // 16 KB
+constexpr int B_OFF_V = B_OFF_DO + BQ * HD * 2;       // 4 x 16 KB (K-major boxes of 128 keys)
+constexpr int B_OFF_P = B_OFF_V + SMAX * HD * 2;      // 8 x 16 KB
+constexpr int B_OFF_XCH = B_OFF_P + 8 * P_BYTES;      // float [2][128]
+constexpr int B_OFF_BARS = B_OFF_XCH + 2 * BQ * 4;
+constexpr int B_SMEM_BYTES = B_OFF_BARS + 8 * 8 + 16 + 1024;
+
+__global__ void __launch_bounds__(THREADS, 1)
+fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_v,
+                    const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_ds,
+                    int S, int D, int H, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BARS);
+  uint64_t* in_full = bars;       // dO + V landed
+  uint64_t* p_full = bars + 1;    // P tile landed
+  uint64_t* s_full = bars + 2;    // dP complete in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xch = reinterpret_cast<float*>(smem + B_OFF_XCH);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tiles = (S + BQ - 1) / BQ;
+  const int g = blockIdx.x / q_tiles, qt = blockIdx.x % q_tiles;
+  const int b = g / H, h = g % H;
+  const int q0 = qt * BQ;
+  const int n_kb = (S + KB - 1) / KB, n_ch = (S + CH - 1) / CH;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_do);
+    ptx::prefetch_tmap(&tm_v);
+    ptx::prefetch_tmap(&tm_p);
+    ptx::prefetch_tmap(&tm_ds);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 3; ++i) ptx::mbar_init(&bars[i], 1);
+    ptx::fence_mbar_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(in_full, BQ * HD * 2 + n_kb * KB * HD * 2);
+      ptx::tma_load_3d(smem + B_OFF_DO, &tm_do, in_full, h * HD, b, q0);
+      for (int kb = 0; kb < n_kb; ++kb)
+        ptx::tma_load_3d(smem + B_OFF_V + kb * KB * HD * 2, &tm_v, in_full, 2 * D + h * HD, b, kb * KB);
+      ptx::mbar_arrive_expect_tx(p_full, n_ch * P_BYTES);
+      for (int c = 0; c < n_ch; ++c)
+        ptx::tma_load_3d(smem + B_OFF_P + c * P_BYTES, &tm_p, p_full, c * CH, g, q0);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      ptx::mbar_wait(in_full, 0);
+      ptx::tc_fence_after();
+      const uint32_t id1 = ptx::make_idesc_bf16(BQ, KB, 0, 0);
+      const uint32_t sa = ptx::smem_u32(smem + B_OFF_DO);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const uint32_t sb = ptx::smem_u32(smem + B_OFF_V + kb * KB * HD * 2);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          ptx::umma_bf16(tmem + kb * KB, ptx::make_smem_desc_sw128(sa + k * 32, 16u, 1024u),
+                         ptx::make_smem_desc_sw128(sb + k * 32, 16u, 1024u), id1, k > 0 ? 1u : 0u);
+      }
+      ptx::umma_commit(s_full);
+    }
+  } else {
+    const int we = warp - 2;
+    const int q = warp & 3;
+    const int hh = we >> 2;
+    const int row = q * 32 + lane;
+    const int c_begin = hh * 4, c_end = min(n_ch, hh * 4 + 4);
+    const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t prow = static_cast<uint32_t>(row >> 3) * 1024u + static_cast<uint32_t>(row & 7) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    const uint32_t pbase = ptx::smem_u32(smem + B_OFF_P);
+    const bool issuer = (q == 2 && lane == 0);
+    ptx::mbar_wait(p_full, 0);
+    ptx::mbar_wait(s_full, 0);
+    ptx::tc_fence_after();
+    uint32_t r[32];
+    // pass 1: delta = sum_j dP_ij P_ij
+    float delta = 0.f;
+    for (int c = c_begin; c < c_end; ++c) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint4 pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          pk[k] = ptx::lds_v4u(pbase + c * P_BYTES + prow + ((static_cast<uint32_t>(j * 4 + k) ^ sw) << 4));
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t w[4] = {pk[k].x, pk[k].y, pk[k].z, pk[k].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            d4[t] = fmaf(__uint_as_float(r[8 * k + 2 * t]), __uint_as_float(w[t] << 16), d4[t]);
+            d4[t] = fmaf(__uint_as_float(r[8 * k + 2 * t + 1]), __uint_as_float(w[t] & 0xffff0000u), d4[t]);
+          }
+        }
+        delta += (d4[0] + d4[1]) + (d4[2] + d4[3]);
+      }
+    }
+    xch[hh * BQ + row] = delta;
+    nbar(3 + q, 64);
+    delta += xch[(hh ^ 1) * BQ + row];
+    // pass 2: dS = P (dP - delta) * scale, in place over P, chunk by chunk -> TMA store
+    for (int c = c_begin; c < c_end; ++c) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
+        uint4 pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          pk[k] = ptx::lds_v4u(pbase + c * P_BYTES + prow + ((static_cast<uint32_t>(j * 4 + k) ^ sw) << 4));
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t w[4] = {pk[k].x, pk[k].y, pk[k].z, pk[k].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float lo = __uint_as_float(w[t] << 16) * (__uint_as_float(r[8 * k + 2 * t]) - delta) * scale;
+            const float hi = __uint_as_float(w[t] & 0xffff0000u) * (__uint_as_float(r[8 * k + 2 * t + 1]) - delta) * scale;
+            o[t] = pack2(lo, hi);
+          }
+          ptx::sts_v4u(pbase + c * P_BYTES + prow + ((static_cast<uint32_t>(j * 4 + k) ^ sw) << 4), o[0], o[1],
+                       o[2], o[3]);
+        }
+      }
+      ptx::fence_proxy_async();
+      nbar(1 + hh, 128);
+      if (issuer) {
+        ptx::tma_store_3d(&tm_ds, pbase + c * P_BYTES, c * CH, g, q0);
+        ptx::bulk_commit();
+      }
+    }
+    if (issuer) ptx::bulk_wait<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
 }  // namespace fattn
 
 // Returns 1 when the fused kernel does not apply (caller falls back to the three-kernel path).
@@ -332,6 +496,34 @@ int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, vo
     return 0;
   };
   return probs != nullptr ? launch(fattn_fwd_kernel<true>) : launch(fattn_fwd_kernel<false>);
+}
+
+// dprobs (bf16 [G, S, Sp]) = dS.  Returns 1 when the fused kernel does not apply.
+int fused_seq_attention_bwd_ds(const void* qkv, const void* dout, const void* probs, void* dprobs, int B, int S,
+                               int D, int H, cudaStream_t stream) {
+  using namespace fattn;
+  static const bool disabled = getenv("MMU_ATTN_UNFUSED") != nullptr;
+  if (disabled || D / H != HD || D % H != 0 || S > SMAX || S < 1) return 1;
+  const int Sp = (S + 7) / 8 * 8;
+  const long long G = static_cast<long long>(B) * H;
+  CUtensorMap tdo, tv, tp, tds;
+  int rc = make_tmap_bf16_3d(&tdo, dout, D, B, S, static_cast<long long>(D) * S, D, HD, BQ);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tv, qkv, 3LL * D, B, S, 3LL * D * S, 3LL * D, HD, KB);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tp, probs, Sp, G, S, static_cast<long long>(S) * Sp, Sp, CH, BQ);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tds, dprobs, Sp, G, S, static_cast<long long>(S) * Sp, Sp, CH, BQ);
+  if (rc) return rc;
+  static cudaError_t attr =
+      cudaFuncSetAttribute(fattn_bwd_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM_BYTES);
+  if (attr != cudaSuccess) return MMU_ERR_CUDA;
+  const int grid = static_cast<int>(G) * ((S + BQ - 1) / BQ);
+  fattn_bwd_ds_kernel<<<grid, THREADS, B_SMEM_BYTES, stream>>>(tdo, tv, tp, tds, S, D, H,
+                                                               1.0f / sqrtf(static_cast<float>(HD)));
+  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+  count_launch();
+  return 0;
 }
 
 }  // namespace mmu
