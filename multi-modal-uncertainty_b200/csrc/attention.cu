@@ -571,8 +571,9 @@ int seq_bwd(const void* qkv, const void* dout, const void* probs, float* scores,
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   // dS = P o (dP - delta) / sqrt(hd), dP = dO V^T: one fused kernel (dP stays in TMEM) when it
   // applies, else the dP GEMM (fp32 to HBM) + the row kernel
-  int rc = fused_seq_attention_bwd_ds(qkv, dout, probs, dprobs, B, S, D, H, st);
+  int rc = fused_seq_attention_bwd_ds(qkv, dout, probs, dprobs, dqkv, B, S, D, H, st);
   if (rc < 0) return rc;
+  const bool dq_done = rc == 0;  // the fused kernel also produced dQ = dS K
   if (rc > 0) {
     rc = gemm_bf16_batched_launch(act_view_seq(dout, B, S, D, H, 0), qkv_view_seq(qkv, B, S, D, H, 2, 0),
                                   G, S, Sp, hd, store_epi(scores, 0, Sp, 1.0f), 1, 0,
@@ -593,7 +594,7 @@ int seq_bwd(const void* qkv, const void* dout, const void* probs, float* scores,
   if (rc) return rc;
   rc = gemm_bf16_batched_launch(sq_view(dprobs, G, S, Sp, 1), qkv_view_seq(qkv, B, S, D, H, 0, 1), G, S,
                                 hd, S, store_epi(dq + D, 1, ld, 1.0f), H, hd, mid, st);
-  if (rc) return rc;
+  if (rc || dq_done) return rc;
   return gemm_bf16_batched_launch(sq_view(dprobs, G, S, Sp, 0), qkv_view_seq(qkv, B, S, D, H, 1, 1), G, S,
                                   hd, S, store_epi(dq, 1, ld, 1.0f), H, hd, mid, st);
 }

@@ -306,18 +306,22 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
 // that read it back.  Same CTA geometry as the forward: dP of a 128-query tile is accumulated
 // straight into TMEM (512 columns), the saved probabilities of the tile arrive by TMA as eight
 // [128 x 64] SWIZZLE_128B chunks, the eight softmax warps make two passes (delta, then dS written
-// IN PLACE over P in shared memory) and every finished chunk leaves by one TMA store.
+// IN PLACE over P in shared memory) and every finished chunk leaves by one TMA store.  The staged
+// dS chunks are K-major UMMA operands as they stand, so dQ = dS K is accumulated right here too
+// (K reloaded MN-major over the V tile once MMA1 has retired; accumulator = TMEM columns 0..63,
+// drained by chunk 0's second pass before the first MMA2) -- the separate dQ GEMM disappears.
 constexpr int B_OFF_DO = 0;                           // 16 KB
 constexpr int B_OFF_V = B_OFF_DO + BQ * HD * 2;       // 4 x 16 KB (K-major boxes of 128 keys)
 constexpr int B_OFF_P = B_OFF_V + SMAX * HD * 2;      // 8 x 16 KB
 constexpr int B_OFF_XCH = B_OFF_P + 8 * P_BYTES;      // float [2][128]
 constexpr int B_OFF_BARS = B_OFF_XCH + 2 * BQ * 4;
-constexpr int B_SMEM_BYTES = B_OFF_BARS + 8 * 8 + 16 + 1024;
+constexpr int B_SMEM_BYTES = B_OFF_BARS + 16 * 8 + 16 + 1024;
 
 __global__ void __launch_bounds__(THREADS, 1)
 fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_v,
                     const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_ds,
-                    int S, int D, int H, float scale) {
+                    const __grid_constant__ CUtensorMap tm_k, __nv_bfloat16* __restrict__ dqkv, int S, int D,
+                    int H, float scale) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -325,7 +329,10 @@ fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_cons
   uint64_t* in_full = bars;       // dO + V landed
   uint64_t* p_full = bars + 1;    // P tile landed
   uint64_t* s_full = bars + 2;    // dP complete in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 3;    // K (MN-major) landed over the V tile
+  uint64_t* o_full = bars + 4;    // dQ complete in TMEM
+  uint64_t* ds_full = bars + 8;   // [8] dS chunk staged
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   float* xch = reinterpret_cast<float*>(smem + B_OFF_XCH);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -340,9 +347,10 @@ fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_cons
     ptx::prefetch_tmap(&tm_v);
     ptx::prefetch_tmap(&tm_p);
     ptx::prefetch_tmap(&tm_ds);
+    ptx::prefetch_tmap(&tm_k);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 3; ++i) ptx::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 16; ++i) ptx::mbar_init(&bars[i], 1);
     ptx::fence_mbar_init();
     ptx::fence_proxy_async();
   }
@@ -364,6 +372,11 @@ fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_cons
       ptx::mbar_arrive_expect_tx(p_full, n_ch * P_BYTES);
       for (int c = 0; c < n_ch; ++c)
         ptx::tma_load_3d(smem + B_OFF_P + c * P_BYTES, &tm_p, p_full, c * CH, g, q0);
+      // MMA1 has retired -> the V tile is dead: K arrives over it, MN-major, for dQ = dS K
+      ptx::mbar_wait(s_full, 0);
+      ptx::mbar_arrive_expect_tx(k_full, n_ch * CH * HD * 2);
+      for (int c = 0; c < n_ch; ++c)
+        ptx::tma_load_3d(smem + B_OFF_V + c * CH * HD * 2, &tm_k, k_full, D + h * HD, b, c * CH);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -379,6 +392,27 @@ fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_cons
                          ptx::make_smem_desc_sw128(sb + k * 32, 16u, 1024u), id1, k > 0 ? 1u : 0u);
       }
       ptx::umma_commit(s_full);
+      // ---- MMA2: dQ[128 x 64] += dS_chunk K_chunk, chunk 0 first (its columns become the accumulator)
+      ptx::mbar_wait(k_full, 0);
+      const uint32_t id2 = ptx::make_idesc_bf16(BQ, HD, 0, 1);
+      bool first = true;
+      for (int i = 0; i < 4; ++i) {
+        for (int hh = 0; hh < 2; ++hh) {
+          const int c = hh * 4 + i;
+          if (c >= n_ch) continue;
+          ptx::mbar_wait(&ds_full[c], 0);
+          ptx::tc_fence_after();
+          const uint32_t sp = ptx::smem_u32(smem + B_OFF_P + c * P_BYTES);
+          const uint32_t sk = ptx::smem_u32(smem + B_OFF_V + c * CH * HD * 2);
+#pragma unroll
+          for (int k = 0; k < CH / 16; ++k)
+            ptx::umma_bf16(tmem, ptx::make_smem_desc_sw128(sp + k * 32, 16u, 1024u),
+                           ptx::make_smem_desc_sw128(sk + k * 2048, 8192u, 1024u), id2,
+                           (first && k == 0) ? 0u : 1u);
+          first = false;
+        }
+      }
+      ptx::umma_commit(o_full);
     }
   } else {
     const int we = warp - 2;
@@ -446,11 +480,30 @@ fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_cons
                        o[2], o[3]);
         }
       }
+      if (c == 0) ptx::tc_fence_before();  // columns 0..63 are drained before MMA2 overwrites them
       ptx::fence_proxy_async();
       nbar(1 + hh, 128);
       if (issuer) {
+        ptx::mbar_arrive(&ds_full[c]);
         ptx::tma_store_3d(&tm_ds, pbase + c * P_BYTES, c * CH, g, q0);
         ptx::bulk_commit();
+      }
+    }
+    // ---- dQ tile: this warp's 32 rows x 32 of the 64 columns -> dqkv[b, s, h*64 ...] (the q third)
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    ptx::tmem_ld_32x32(trow + hh * 32, r);
+    ptx::tmem_ld_wait();
+    if (q0 + row < S) {
+      __nv_bfloat16* o = dqkv + (static_cast<size_t>(b) * S + q0 + row) * (3 * static_cast<size_t>(D)) + h * HD + hh * 32;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint4 pk4;
+        pk4.x = pack2(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1]));
+        pk4.y = pack2(__uint_as_float(r[8 * k + 2]), __uint_as_float(r[8 * k + 3]));
+        pk4.z = pack2(__uint_as_float(r[8 * k + 4]), __uint_as_float(r[8 * k + 5]));
+        pk4.w = pack2(__uint_as_float(r[8 * k + 6]), __uint_as_float(r[8 * k + 7]));
+        *reinterpret_cast<uint4*>(o + 8 * k) = pk4;
       }
     }
     if (issuer) ptx::bulk_wait<0>();
@@ -498,15 +551,16 @@ int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, vo
   return probs != nullptr ? launch(fattn_fwd_kernel<true>) : launch(fattn_fwd_kernel<false>);
 }
 
-// dprobs (bf16 [G, S, Sp]) = dS.  Returns 1 when the fused kernel does not apply.
-int fused_seq_attention_bwd_ds(const void* qkv, const void* dout, const void* probs, void* dprobs, int B, int S,
-                               int D, int H, cudaStream_t stream) {
+// dprobs (bf16 [G, S, Sp]) = dS and the q third of dqkv = dS K.  Returns 1 when the fused kernel
+// does not apply.
+int fused_seq_attention_bwd_ds(const void* qkv, const void* dout, const void* probs, void* dprobs, void* dqkv,
+                               int B, int S, int D, int H, cudaStream_t stream) {
   using namespace fattn;
   static const bool disabled = getenv("MMU_ATTN_UNFUSED") != nullptr;
   if (disabled || D / H != HD || D % H != 0 || S > SMAX || S < 1) return 1;
   const int Sp = (S + 7) / 8 * 8;
   const long long G = static_cast<long long>(B) * H;
-  CUtensorMap tdo, tv, tp, tds;
+  CUtensorMap tdo, tv, tp, tds, tk;
   int rc = make_tmap_bf16_3d(&tdo, dout, D, B, S, static_cast<long long>(D) * S, D, HD, BQ);
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&tv, qkv, 3LL * D, B, S, 3LL * D * S, 3LL * D, HD, KB);
@@ -515,11 +569,14 @@ int fused_seq_attention_bwd_ds(const void* qkv, const void* dout, const void* pr
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&tds, dprobs, Sp, G, S, static_cast<long long>(S) * Sp, Sp, CH, BQ);
   if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tk, qkv, 3LL * D, B, S, 3LL * D * S, 3LL * D, HD, CH);
+  if (rc) return rc;
   static cudaError_t attr =
       cudaFuncSetAttribute(fattn_bwd_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM_BYTES);
   if (attr != cudaSuccess) return MMU_ERR_CUDA;
   const int grid = static_cast<int>(G) * ((S + BQ - 1) / BQ);
-  fattn_bwd_ds_kernel<<<grid, THREADS, B_SMEM_BYTES, stream>>>(tdo, tv, tp, tds, S, D, H,
+  fattn_bwd_ds_kernel<<<grid, THREADS, B_SMEM_BYTES, stream>>>(tdo, tv, tp, tds, tk,
+                                                               static_cast<__nv_bfloat16*>(dqkv), S, D, H,
                                                                1.0f / sqrtf(static_cast<float>(HD)));
   if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
   count_launch();

@@ -110,8 +110,8 @@ int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* pr
 // but O is written).  Returns 1 when it does not apply, 0 on success, < 0 on error.
 int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, int B, int S,
                             int D, int H, cudaStream_t stream);
-int fused_seq_attention_bwd_ds(const void* qkv, const void* dout, const void* probs, void* dprobs, int B, int S,
-                               int D, int H, cudaStream_t stream);
+int fused_seq_attention_bwd_ds(const void* qkv, const void* dout, const void* probs, void* dprobs, void* dqkv,
+                               int B, int S, int D, int H, cudaStream_t stream);
 int seq_attention_bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
                       void* dqkv, int dtype, int B, int S, int D, int H, cudaStream_t stream);
 
