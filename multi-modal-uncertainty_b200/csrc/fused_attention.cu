@@ -63,26 +63,32 @@ template <bool SAVE_P>
 __global__ void __launch_bounds__(THREADS, 1)
 fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_v,
                  const __grid_constant__ CUtensorMap tm_p, const float* __restrict__ addmask,
-                 __nv_bfloat16* __restrict__ out, int B, int S, int D, int H, float scale) {
+                 __nv_bfloat16* __restrict__ out, int B, int S, int D, int H, float scale, int tiles_per_cta) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
-  uint64_t* qk_full = bars;        // Q + K landed
-  uint64_t* v_full = bars + 1;     // V landed
+  uint64_t* kv_full = bars;        // K + V of this (sample, head) landed (once per CTA)
+  uint64_t* q_full = bars + 1;     // Q tile landed                       (once per query tile)
   uint64_t* s_full = bars + 2;     // scores complete in TMEM
   uint64_t* o_full = bars + 3;     // O complete in TMEM
   uint64_t* p_full = bars + 4;     // [2 halves][2 buffers]
   uint64_t* p_empty = bars + 8;    // [2][2]
+  uint64_t* t_empty = bars + 12;   // TMEM drained by the 8 softmax warps (count 8)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   float* mask_s = reinterpret_cast<float*>(smem + OFF_MASK);
   float2* xch = reinterpret_cast<float2*>(smem + OFF_XCH);
 
+  // A CTA owns `tiles_per_cta` consecutive 128-query tiles of one (sample b, head h): K and V are
+  // loaded ONCE per CTA and shared by its tiles (a CTA per tile re-reads 128 KB of K/V for every
+  // 16 KB of Q; a CTA per head leaves 2.6 waves on 148 SMs -- the host picks the split).
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tiles = (S + BQ - 1) / BQ;
-  const int g = blockIdx.x / q_tiles, qt = blockIdx.x % q_tiles;
+  const int all_tiles = (S + BQ - 1) / BQ;
+  const int splits = (all_tiles + tiles_per_cta - 1) / tiles_per_cta;
+  const int g = blockIdx.x / splits;
+  const int tile0 = (blockIdx.x % splits) * tiles_per_cta;
+  const int q_tiles = min(tiles_per_cta, all_tiles - tile0);
   const int b = g / H, h = g % H;
-  const int q0 = qt * BQ;
   const int n_kb = (S + KB - 1) / KB;   // MMA1 blocks
   const int n_ch = (S + CH - 1) / CH;   // P / V chunks
 
@@ -92,11 +98,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
     if (SAVE_P) ptx::prefetch_tmap(&tm_p);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 4; ++i) ptx::mbar_init(&bars[i], 1);
-    for (int i = 0; i < 4; ++i) {
-      ptx::mbar_init(&p_full[i], 1);
-      ptx::mbar_init(&p_empty[i], 1);
-    }
+    for (int i = 0; i < 12; ++i) ptx::mbar_init(&bars[i], 1);
+    ptx::mbar_init(t_empty, 8);
     ptx::fence_mbar_init();
     ptx::fence_proxy_async();
   }
@@ -114,54 +117,66 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(qk_full, BQ * HD * 2 + n_kb * KB * HD * 2);
-      ptx::tma_load_3d(smem + OFF_Q, &tm_qk, qk_full, h * HD, b, q0);
+      ptx::mbar_arrive_expect_tx(q_full, BQ * HD * 2);
+      ptx::tma_load_3d(smem + OFF_Q, &tm_qk, q_full, h * HD, b, tile0 * BQ);
+      ptx::mbar_arrive_expect_tx(kv_full, n_kb * KB * HD * 2 + n_ch * CH * HD * 2);
       for (int kb = 0; kb < n_kb; ++kb)
-        ptx::tma_load_3d(smem + OFF_K + kb * KB * HD * 2, &tm_qk, qk_full, D + h * HD, b, kb * KB);
-      ptx::mbar_arrive_expect_tx(v_full, n_ch * CH * HD * 2);
+        ptx::tma_load_3d(smem + OFF_K + kb * KB * HD * 2, &tm_qk, kv_full, D + h * HD, b, kb * KB);
       for (int c = 0; c < n_ch; ++c)
-        ptx::tma_load_3d(smem + OFF_V + c * CH * HD * 2, &tm_v, v_full, 2 * D + h * HD, b, c * CH);
+        ptx::tma_load_3d(smem + OFF_V + c * CH * HD * 2, &tm_v, kv_full, 2 * D + h * HD, b, c * CH);
+      // the next Q tile is fetched as soon as MMA1 of the current one has retired
+      for (int qt = 1; qt < q_tiles; ++qt) {
+        ptx::mbar_wait(s_full, (qt - 1) & 1);
+        ptx::mbar_arrive_expect_tx(q_full, BQ * HD * 2);
+        ptx::tma_load_3d(smem + OFF_Q, &tm_qk, q_full, h * HD, b, (tile0 + qt) * BQ);
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ---- MMA1: S[128 x 128*n_kb] = Q K^T
-      ptx::mbar_wait(qk_full, 0);
-      ptx::tc_fence_after();
       const uint32_t id1 = ptx::make_idesc_bf16(BQ, KB, 0, 0);
-      const uint32_t sq = ptx::smem_u32(smem + OFF_Q);
-      for (int kb = 0; kb < n_kb; ++kb) {
-        const uint32_t sk = ptx::smem_u32(smem + OFF_K + kb * KB * HD * 2);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ptx::umma_bf16(tmem + kb * KB, ptx::make_smem_desc_sw128(sq + k * 32, 16u, 1024u),
-                         ptx::make_smem_desc_sw128(sk + k * 32, 16u, 1024u), id1, k > 0 ? 1u : 0u);
-      }
-      ptx::umma_commit(s_full);
-      // ---- MMA2: O[128 x 64] += P_chunk V_chunk, chunk 0 first (its columns become the accumulator)
-      ptx::mbar_wait(v_full, 0);
       const uint32_t id2 = ptx::make_idesc_bf16(BQ, HD, 0, 1);
-      const int per_half = 4;
-      bool first = true;
-      for (int i = 0; i < per_half; ++i) {
-        for (int hh = 0; hh < 2; ++hh) {
-          const int c = hh * per_half + i;
-          if (c >= n_ch) continue;
-          const int buf = i & 1;
-          ptx::mbar_wait(&p_full[hh * 2 + buf], (i >> 1) & 1);
-          ptx::tc_fence_after();
-          const uint32_t sp = ptx::smem_u32(smem + OFF_P + (hh * 2 + buf) * P_BYTES);
-          const uint32_t sv = ptx::smem_u32(smem + OFF_V + c * CH * HD * 2);
+      const uint32_t sq = ptx::smem_u32(smem + OFF_Q);
+      ptx::mbar_wait(kv_full, 0);
+      for (int qt = 0; qt < q_tiles; ++qt) {
+        // ---- MMA1: S[128 x 128*n_kb] = Q K^T  (TMEM must have been drained by the previous tile)
+        ptx::mbar_wait(q_full, qt & 1);
+        if (qt > 0) ptx::mbar_wait(t_empty, (qt - 1) & 1);
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < n_kb; ++kb) {
+          const uint32_t sk = ptx::smem_u32(smem + OFF_K + kb * KB * HD * 2);
 #pragma unroll
-          for (int k = 0; k < CH / 16; ++k) {
-            ptx::umma_bf16(tmem, ptx::make_smem_desc_sw128(sp + k * 32, 16u, 1024u),
-                           ptx::make_smem_desc_sw128(sv + k * 2048, 8192u, 1024u), id2,
-                           (first && k == 0) ? 0u : 1u);
-          }
-          first = false;
-          ptx::umma_commit(&p_empty[hh * 2 + buf]);
+          for (int k = 0; k < HD / 16; ++k)
+            ptx::umma_bf16(tmem + kb * KB, ptx::make_smem_desc_sw128(sq + k * 32, 16u, 1024u),
+                           ptx::make_smem_desc_sw128(sk + k * 32, 16u, 1024u), id1, k > 0 ? 1u : 0u);
         }
+        ptx::umma_commit(s_full);
+        // ---- MMA2: O[128 x 64] += P_chunk V_chunk, chunk 0 first (its columns become the accumulator)
+        bool first = true;
+        for (int i = 0; i < 4; ++i) {
+          for (int hh = 0; hh < 2; ++hh) {
+            const int c = hh * 4 + i;
+            if (c >= n_ch) continue;
+            const int buf = i & 1;
+            // global use index of this P buffer (a half with n chunks uses buffer 0 ceil(n/2) and
+            // buffer 1 floor(n/2) times per query tile): the barrier phase is its parity
+            const int n_half = max(0, min(n_ch, hh * 4 + 4) - hh * 4);
+            const int use = qt * ((n_half - buf + 1) / 2) + (i >> 1);
+            ptx::mbar_wait(&p_full[hh * 2 + buf], use & 1);
+            ptx::tc_fence_after();
+            const uint32_t sp = ptx::smem_u32(smem + OFF_P + (hh * 2 + buf) * P_BYTES);
+            const uint32_t sv = ptx::smem_u32(smem + OFF_V + c * CH * HD * 2);
+#pragma unroll
+            for (int k = 0; k < CH / 16; ++k) {
+              ptx::umma_bf16(tmem, ptx::make_smem_desc_sw128(sp + k * 32, 16u, 1024u),
+                             ptx::make_smem_desc_sw128(sv + k * 2048, 8192u, 1024u), id2,
+                             (first && k == 0) ? 0u : 1u);
+            }
+            first = false;
+            ptx::umma_commit(&p_empty[hh * 2 + buf]);
+          }
+        }
+        ptx::umma_commit(o_full);
       }
-      ptx::umma_commit(o_full);
     }
   } else {
     // ---------------------------------------------------------------- softmax warps
@@ -171,122 +186,131 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
     const int row = q * 32 + lane;     // query row within the tile
     const float sc = scale * 1.4426950408889634f;
     const int c_begin = hh * 4, c_end = min(n_ch, hh * 4 + 4);   // this half's chunks
+    const int n_mine = c_end - c_begin;                           // 0..4 (uniform over the half)
     const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
-    ptx::mbar_wait(s_full, 0);
-    ptx::tc_fence_after();
+    const uint32_t prow = static_cast<uint32_t>(row >> 3) * 1024u + static_cast<uint32_t>(row & 7) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    const bool issuer = (q == 2 && lane == 0);  // warp 2 / warp 6: first warp of each half
     uint32_t r[32];
-    // pass 1: row maximum over this half's columns
-    float mx = -INFINITY;
-    for (int c = c_begin; c < c_end; ++c) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
-        ptx::tmem_ld_wait();
-        const float* ms = mask_s + c * CH + j * 32;
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], fmaf(__uint_as_float(r[i]), sc, ms[i]));
-        mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-      }
-    }
-    float sum = 0.f;
-    if (SAVE_P) {  // pass 2: row sum, so that the NORMALISED probabilities can be stored
-      xch[hh * BQ + row] = make_float2(mx, 0.f);
-      nbar(3 + q, 64);
-      mx = fmaxf(mx, xch[(hh ^ 1) * BQ + row].x);
-      nbar(3 + q, 64);
+    for (int qt = 0; qt < q_tiles; ++qt) {
+      const int q0 = (tile0 + qt) * BQ;
+      ptx::mbar_wait(s_full, qt & 1);
+      ptx::tc_fence_after();
+      // pass 1: row maximum over this half's columns
+      float mx = -INFINITY;
       for (int c = c_begin; c < c_end; ++c) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
           ptx::tmem_ld_wait();
           const float* ms = mask_s + c * CH + j * 32;
-          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int i = 0; i < 32; ++i) s4[i & 3] += ex2f(fmaf(__uint_as_float(r[i]), sc, ms[i]) - mx);
-          sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], fmaf(__uint_as_float(r[i]), sc, ms[i]));
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
         }
       }
-      xch[hh * BQ + row] = make_float2(mx, sum);
-      nbar(3 + q, 64);
-      sum += xch[(hh ^ 1) * BQ + row].y;
-      nbar(3 + q, 64);
-    } else {
       xch[hh * BQ + row] = make_float2(mx, 0.f);
       nbar(3 + q, 64);
       mx = fmaxf(mx, xch[(hh ^ 1) * BQ + row].x);
       nbar(3 + q, 64);
-    }
-    const float inv = SAVE_P ? 1.0f / sum : 1.0f;
-    // last pass: probabilities -> bf16 -> swizzled K-major tile -> MMA2 (and the probs tensor)
-    const uint32_t prow = static_cast<uint32_t>(row >> 3) * 1024u + static_cast<uint32_t>(row & 7) * 128u;
-    const uint32_t sw = static_cast<uint32_t>(row & 7);
-    const bool issuer = (q == 2 && lane == 0);  // warp 2 / warp 6: first warp of each half
-    for (int c = c_begin; c < c_end; ++c) {
-      const int i = c - c_begin, buf = i & 1;
-      const uint32_t pbuf = ptx::smem_u32(smem + OFF_P + (hh * 2 + buf) * P_BYTES);
-      if (i >= 2) {
-        ptx::mbar_wait(&p_empty[hh * 2 + buf], 0);     // MMA2 has consumed the previous tile
-        if (SAVE_P) {
-          if (issuer) ptx::bulk_wait_read<1>();        // ... and so has its TMA store
-          nbar(1 + hh, 128);
+      float sum = 0.f;
+      if (SAVE_P) {  // pass 2: row sum, so that the NORMALISED probabilities can be stored
+        for (int c = c_begin; c < c_end; ++c) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
+            ptx::tmem_ld_wait();
+            const float* ms = mask_s + c * CH + j * 32;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s4[i & 3] += ex2f(fmaf(__uint_as_float(r[i]), sc, ms[i]) - mx);
+            sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          }
+        }
+        xch[hh * BQ + row] = make_float2(mx, sum);
+        nbar(3 + q, 64);
+        sum += xch[(hh ^ 1) * BQ + row].y;
+        nbar(3 + q, 64);
+      }
+      const float inv = SAVE_P ? 1.0f / sum : 1.0f;
+      // last pass: probabilities -> bf16 -> swizzled K-major tile -> MMA2 (and the probs tensor)
+      for (int c = c_begin; c < c_end; ++c) {
+        const int i = c - c_begin, buf = i & 1;
+        const uint32_t pbuf = ptx::smem_u32(smem + OFF_P + (hh * 2 + buf) * P_BYTES);
+        // buffer reuse: its previous tile (this query tile's use i - 2, or the previous query
+        // tile's last use of this buffer) must have been consumed by MMA2 and by its TMA store.
+        // Completions of p_empty[buf] come in use order, 2 (or 1) per query tile.
+        const int uses_per_tile = (n_mine - buf + 1) / 2;           // uses of this buffer per tile
+        const int use = qt * uses_per_tile + (i >> 1);              // global use index of this write
+        if (use > 0) {
+          ptx::mbar_wait(&p_empty[hh * 2 + buf], (use - 1) & 1);
+          if (SAVE_P) {
+            if (issuer) ptx::bulk_wait_read<1>();
+            nbar(1 + hh, 128);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
+          ptx::tmem_ld_wait();
+          const float* ms = mask_s + c * CH + j * 32;
+          float v[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = ex2f(fmaf(__uint_as_float(r[t]), sc, ms[t]) - mx) * inv;
+          if (!SAVE_P) {
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < 32; ++t) s4[t & 3] += v[t];
+            sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t piece = static_cast<uint32_t>(j * 4 + k);
+            ptx::sts_v4u(pbuf + prow + ((piece ^ sw) << 4), pack2(v[8 * k], v[8 * k + 1]),
+                         pack2(v[8 * k + 2], v[8 * k + 3]), pack2(v[8 * k + 4], v[8 * k + 5]),
+                         pack2(v[8 * k + 6], v[8 * k + 7]));
+          }
+        }
+        if (c == 0) ptx::tc_fence_before();  // columns 0..63 are drained before MMA2 overwrites them
+        ptx::fence_proxy_async();
+        nbar(1 + hh, 128);
+        if (issuer) {
+          ptx::mbar_arrive(&p_full[hh * 2 + buf]);
+          if (SAVE_P) {
+            ptx::tma_store_3d(&tm_p, pbuf, c * CH, g, q0);
+            ptx::bulk_commit();
+          }
         }
       }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
-        ptx::tmem_ld_wait();
-        const float* ms = mask_s + c * CH + j * 32;
-        float v[32];
-#pragma unroll
-        for (int t = 0; t < 32; ++t) v[t] = ex2f(fmaf(__uint_as_float(r[t]), sc, ms[t]) - mx) * inv;
-        if (!SAVE_P) {
-          float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int t = 0; t < 32; ++t) s4[t & 3] += v[t];
-          sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-        }
+      float inv_o = 1.0f;
+      if (!SAVE_P) {
+        xch[hh * BQ + row] = make_float2(mx, sum);
+        nbar(3 + q, 64);
+        sum += xch[(hh ^ 1) * BQ + row].y;
+        nbar(3 + q, 64);
+        inv_o = 1.0f / sum;
+      }
+      // ---- epilogue: this warp's 32 rows x 32 of the 64 output columns
+      ptx::mbar_wait(o_full, qt & 1);
+      ptx::tc_fence_after();
+      ptx::tmem_ld_32x32(trow + hh * 32, r);
+      ptx::tmem_ld_wait();
+      // TMEM is free for the next tile's MMA1 once all 8 warps have their O values in registers
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(t_empty);
+      if (q0 + row < S) {
+        __nv_bfloat16* o = out + (static_cast<size_t>(b) * S + q0 + row) * D + h * HD + hh * 32;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t piece = static_cast<uint32_t>(j * 4 + k);
-          ptx::sts_v4u(pbuf + prow + ((piece ^ sw) << 4), pack2(v[8 * k], v[8 * k + 1]),
-                       pack2(v[8 * k + 2], v[8 * k + 3]), pack2(v[8 * k + 4], v[8 * k + 5]),
-                       pack2(v[8 * k + 6], v[8 * k + 7]));
+          uint4 pk;
+          pk.x = pack2(__uint_as_float(r[8 * k]) * inv_o, __uint_as_float(r[8 * k + 1]) * inv_o);
+          pk.y = pack2(__uint_as_float(r[8 * k + 2]) * inv_o, __uint_as_float(r[8 * k + 3]) * inv_o);
+          pk.z = pack2(__uint_as_float(r[8 * k + 4]) * inv_o, __uint_as_float(r[8 * k + 5]) * inv_o);
+          pk.w = pack2(__uint_as_float(r[8 * k + 6]) * inv_o, __uint_as_float(r[8 * k + 7]) * inv_o);
+          *reinterpret_cast<uint4*>(o + 8 * k) = pk;
         }
-      }
-      if (c == 0) ptx::tc_fence_before();  // columns 0..63 are drained before MMA2 overwrites them
-      ptx::fence_proxy_async();
-      nbar(1 + hh, 128);
-      if (issuer) {
-        ptx::mbar_arrive(&p_full[hh * 2 + buf]);
-        if (SAVE_P) {
-          ptx::tma_store_3d(&tm_p, pbuf, c * CH, g, q0);
-          ptx::bulk_commit();
-        }
-      }
-    }
-    float inv_o = 1.0f;
-    if (!SAVE_P) {
-      xch[hh * BQ + row] = make_float2(mx, sum);
-      nbar(3 + q, 64);
-      sum += xch[(hh ^ 1) * BQ + row].y;
-      inv_o = 1.0f / sum;
-    }
-    // ---- epilogue: this warp's 32 rows x 32 of the 64 output columns
-    ptx::mbar_wait(o_full, 0);
-    ptx::tc_fence_after();
-    ptx::tmem_ld_32x32(trow + hh * 32, r);
-    ptx::tmem_ld_wait();
-    if (q0 + row < S) {
-      __nv_bfloat16* o = out + (static_cast<size_t>(b) * S + q0 + row) * D + h * HD + hh * 32;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint4 pk;
-        pk.x = pack2(__uint_as_float(r[8 * k]) * inv_o, __uint_as_float(r[8 * k + 1]) * inv_o);
-        pk.y = pack2(__uint_as_float(r[8 * k + 2]) * inv_o, __uint_as_float(r[8 * k + 3]) * inv_o);
-        pk.z = pack2(__uint_as_float(r[8 * k + 4]) * inv_o, __uint_as_float(r[8 * k + 5]) * inv_o);
-        pk.w = pack2(__uint_as_float(r[8 * k + 6]) * inv_o, __uint_as_float(r[8 * k + 7]) * inv_o);
-        *reinterpret_cast<uint4*>(o + 8 * k) = pk;
       }
     }
     if (SAVE_P && issuer) ptx::bulk_wait<0>();
@@ -536,14 +560,23 @@ int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, vo
                            Sp, CH, BQ);
     if (rc) return rc;
   }
-  const int grid = B * H * ((S + BQ - 1) / BQ);
+  // query tiles per CTA (K / V staged once per CTA).  Measured on B200 at B*H = 384, S = 512
+  // (MMBT train step / eval forward, ms): 1 tile per CTA 15.6 / 4.45, 2 tiles 15.5 / 4.30, all 4
+  // tiles (a CTA per head) 15.3 / 4.05 -- staging K/V once beats the 2.6-wave grid's quantisation
+  static const int tpc_env_eval = getenv("MMU_FATTN_TPC_EVAL") ? atoi(getenv("MMU_FATTN_TPC_EVAL")) : 0;
+  static const int tpc_env_train = getenv("MMU_FATTN_TPC_TRAIN") ? atoi(getenv("MMU_FATTN_TPC_TRAIN")) : 0;
+  const int all_tiles = (S + BQ - 1) / BQ;
+  int tpc = probs != nullptr ? (tpc_env_train > 0 ? tpc_env_train : all_tiles)
+                             : (tpc_env_eval > 0 ? tpc_env_eval : all_tiles);
+  if (tpc > all_tiles) tpc = all_tiles;
+  const int grid = B * H * ((all_tiles + tpc - 1) / tpc);
   const float scale = 1.0f / sqrtf(static_cast<float>(HD));
   auto launch = [&](auto kernel) -> int {
     static cudaError_t attr = cudaSuccess;
     attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (attr != cudaSuccess) return MMU_ERR_CUDA;
     kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tq, tv, tp, addmask, static_cast<__nv_bfloat16*>(out), B, S,
-                                                  D, H, scale);
+                                                  D, H, scale, tpc);
     if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
     count_launch();
     return 0;
