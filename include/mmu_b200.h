@@ -286,6 +286,7 @@ typedef struct {
   int B, S_txt, n_img, d_img, D, n_head, n_layers, d_ff, vocab, max_pos, n_types, C;
   int cls_id, sep_id; /* args.vocab.stoi["[CLS]"], ["[SEP]"] (src/mmbt.py:62-66) */
   int precision;      /* 0 fp32 (parity path), 1 bf16 operands on tcgen05 */
+  int max_seq;        /* workspace capacity in sequence positions; 0 = n_img + 2 + S_txt */
 } mmu_mmbt_config;
 typedef struct {
   const long long* txt;     /* (B, S_txt) token ids */
@@ -296,6 +297,8 @@ typedef struct {
                                encoder; NULL = all (forward).  img_only = first n_img + 2; txt_only =
                                {0} + text; forward_control = {0} + sorted sample (src/mmbt.py:198-201) */
   int n_sel;
+  int indices_per_sample;   /* 1: indices is int32[B][n_sel], one list per sample (equally long robustness
+                               variants of a batch packed along the batch axis into one forward) */
   const void* params_bf16;  /* optional bf16 shadow of params */
   float* dimg;              /* backward: d loss / d img, or NULL */
 } mmu_mmbt_inputs;

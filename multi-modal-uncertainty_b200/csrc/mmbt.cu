@@ -91,6 +91,7 @@ int check_config(const MmbtConfig& c) {
   if (c.cls_id < 0 || c.cls_id >= c.vocab || c.sep_id < 0 || c.sep_id >= c.vocab) return MMU_ERR_ARG;
   if (c.precision != PREC_FP32 && c.precision != PREC_BF16) return MMU_ERR_ARG;
   if (c.precision == PREC_BF16 && (c.D / c.n_head) % 64 != 0) return MMU_ERR_SHAPE;
+  if (c.max_seq < 0) return MMU_ERR_SHAPE;
   return 0;
 }
 
@@ -198,7 +199,7 @@ void carve(const MmbtConfig& c, int training, void* base, const Layout& lay, Ws*
   Bump b{static_cast<char*>(base), 0};
   const bool bf = c.precision == PREC_BF16;
   const long long s = bf ? 2 : 4;
-  const long long S = c.n_img + 2 + c.S_txt;  // capacity: every subset is shorter
+  const long long S = c.max_seq > 0 ? c.max_seq : c.n_img + 2 + c.S_txt;  // capacity
   const long long M = static_cast<long long>(c.B) * S, D = c.D, F = c.d_ff;
   const long long G = static_cast<long long>(c.B) * c.n_head, Sp = (S + 7) / 8 * 8;
   const long long sq = bf ? G * S * Sp : G * S * S;
@@ -273,7 +274,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 embed_fwd_kernel(const long long* __restrict__ txt, const long long* __restrict__ mask,
                  const long long* __restrict__ segment, const float* __restrict__ imgp,
-                 const int* __restrict__ indices, const float* __restrict__ word,
+                 const int* __restrict__ indices, int idx_stride, const float* __restrict__ word,
                  const float* __restrict__ pos, const float* __restrict__ type,
                  const float* __restrict__ gamma, const float* __restrict__ beta, int B, int S,
                  int S_txt, int n_img, int D, int cls_id, int sep_id, int vocab, int n_types,
@@ -285,7 +286,7 @@ embed_fwd_kernel(const long long* __restrict__ txt, const long long* __restrict_
   const int M = B * S;
   if (r >= M) return;
   const int b = r / S, j = r % S;
-  const int p = indices != nullptr ? indices[j] : j;
+  const int p = indices != nullptr ? indices[static_cast<long long>(b) * idx_stride + j] : j;
   const int n2 = n_img + 2;
   int wid = -1, pid, tid = 0, iid = -1;
   float m = 1.f;
@@ -503,9 +504,10 @@ int wsplits(int Mg, int Ng, int K) {
 
 int resolve_S(const MmbtConfig& c, const MmbtInputs& in) {
   const int full = c.n_img + 2 + c.S_txt;
-  if (in.indices == nullptr) return full;
+  const int cap = c.max_seq > 0 ? c.max_seq : full;
+  if (in.indices == nullptr) return full <= cap ? full : MMU_ERR_WORKSPACE;
   if (in.n_sel < 1 || in.n_sel > full) return MMU_ERR_SHAPE;
-  return in.n_sel;
+  return in.n_sel <= cap ? in.n_sel : MMU_ERR_WORKSPACE;
 }
 
 }  // namespace
@@ -570,14 +572,14 @@ int mmbt_forward(const MmbtConfig& c, const float* params, const MmbtInputs& in,
     float* st0 = training ? w.st0 : nullptr;
     if (bf)
       embed_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
-          in.txt, in.mask, in.segment, w.imgp, in.indices, params + lay.word, params + lay.pos,
-          params + lay.type, params + lay.eln_w, params + lay.eln_b, c.B, S, c.S_txt, c.n_img, D,
+          in.txt, in.mask, in.segment, w.imgp, in.indices, in.indices_per_sample ? S : 0, params + lay.word,
+          params + lay.pos, params + lay.type, params + lay.eln_w, params + lay.eln_b, c.B, S, c.S_txt, c.n_img, D,
           c.cls_id, c.sep_id, c.vocab, c.n_types, s0, st0, static_cast<__nv_bfloat16*>(w.h0),
           w.addmask, w.row_word, w.row_pos, w.row_type, w.row_img);
     else
       embed_fwd_kernel<float><<<grid, 256, 0, stream>>>(
-          in.txt, in.mask, in.segment, w.imgp, in.indices, params + lay.word, params + lay.pos,
-          params + lay.type, params + lay.eln_w, params + lay.eln_b, c.B, S, c.S_txt, c.n_img, D,
+          in.txt, in.mask, in.segment, w.imgp, in.indices, in.indices_per_sample ? S : 0, params + lay.word,
+          params + lay.pos, params + lay.type, params + lay.eln_w, params + lay.eln_b, c.B, S, c.S_txt, c.n_img, D,
           c.cls_id, c.sep_id, c.vocab, c.n_types, s0, st0, static_cast<float*>(w.h0), w.addmask,
           w.row_word, w.row_pos, w.row_type, w.row_img);
     MB_CHECK_LAUNCH();

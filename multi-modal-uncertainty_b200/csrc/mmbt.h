@@ -30,6 +30,8 @@ struct MmbtConfig {
   int cls_id;    // args.vocab.stoi["[CLS]"]
   int sep_id;    // args.vocab.stoi["[SEP]"]
   int precision; // Precision
+  int max_seq;   // workspace capacity in sequence positions; 0 = n_img + 2 + S_txt.  A caller that
+                 // only ever runs short index lists (packed robustness variants) sizes it to n_sel.
 };
 
 struct MmbtInputs {
@@ -43,6 +45,9 @@ struct MmbtInputs {
   // forward_control (:186-234) = {0} + the sampled subset.
   const int* indices;
   int n_sel;
+  // 0: one index list shared by the batch; 1: `indices` is int32[B][n_sel], one list per sample
+  // (packs several equally long robustness variants of a batch into ONE forward along the batch axis)
+  int indices_per_sample;
   const void* params_bf16;   // optional caller-maintained bf16 shadow of params
   float* dimg;               // backward only: d loss / d img (B, n_img, d_img) fp32, or null
 };

@@ -146,15 +146,15 @@ class MultimodalBertClf(nn.Module):
     def _shape(rows, cols):
         return (rows, cols) if cols > 0 else (rows,)
 
-    def _config(self, B, S_txt):
-        key = (B, S_txt)
+    def _config(self, B, S_txt, max_seq=0):
+        key = (B, S_txt, max_seq)
         cfg = self._cfgs.get(key)
         if cfg is None:
             bc = self._bc
             cfg = self._cfgs[key] = _lib.MmbtConfig(
                 B, S_txt, self._n_img, self._d_img, bc["D"], bc["n_head"], bc["n_layers"], bc["d_ff"],
                 bc["vocab"], bc["max_pos"], bc["n_types"], int(self.args.n_classes), self._cls_id,
-                self._sep_id, self.precision)
+                self._sep_id, self.precision, max_seq)
         return cfg
 
     def _own_parameters(self):
@@ -222,7 +222,7 @@ class MultimodalBertClf(nn.Module):
 
     # ------------------------------------------------------------------------ engine
     def _workspace(self, cfg, training):
-        key = (cfg.B, cfg.S_txt, bool(training))
+        key = (cfg.B, cfg.S_txt, cfg.max_seq, bool(training))
         ws = self._ws.get(key)
         if ws is None:
             nbytes = _lib.check(int(_lib.lib.mmu_mmbt_workspace_bytes(C.byref(cfg), int(training))),
@@ -233,6 +233,8 @@ class MultimodalBertClf(nn.Module):
     def _device_indices(self, indices):
         if indices is None:
             return None
+        if torch.is_tensor(indices) and indices.dim() == 2:  # one list per sample
+            return indices.to(device=self._flat.device, dtype=torch.int32).contiguous()
         key = tuple(int(i) for i in indices)
         t = self._idx_cache.get(key)
         if t is None:
@@ -251,12 +253,18 @@ class MultimodalBertClf(nn.Module):
             raise ValueError(f"image tokens must be (B, {self._n_img}, {self._d_img})")
         tokens = tokens.detach().to(device=dev, dtype=torch.float32).contiguous()
         txt, mask, segment = (t.to(device=dev, dtype=torch.int64).contiguous() for t in (txt, mask, segment))
-        cfg = self._config(B, S_txt)
-        ws = self._workspace(cfg, training)
         idx = self._device_indices(indices)
+        # per-sample lists (packed short variants): the workspace is sized to the lists, not to the
+        # full sequence of the replicated batch
+        cfg = self._config(B, S_txt, int(idx.shape[-1]) if (idx is not None and idx.dim() == 2) else 0)
+        ws = self._workspace(cfg, training)
         shadow = self._fresh_shadow()
+        per_sample = int(idx is not None and idx.dim() == 2)
+        if per_sample and idx.shape[0] != B:
+            raise ValueError("per-sample index lists must be (B, S)")
         inp = _lib.MmbtInputs(txt.data_ptr(), mask.data_ptr(), segment.data_ptr(), tokens.data_ptr(),
-                              _lib.ptr(idx), 0 if idx is None else idx.numel(), _lib.ptr(shadow), None)
+                              _lib.ptr(idx), 0 if idx is None else idx.shape[-1], per_sample,
+                              _lib.ptr(shadow), None)
         logits = torch.empty(B, int(self.args.n_classes), device=dev, dtype=torch.float32)
         _lib.check(_lib.lib.mmu_mmbt_forward(C.byref(cfg), self._flat.data_ptr(), C.byref(inp),
                                              ws.data_ptr(), ws.numel(), int(training), logits.data_ptr(),
@@ -268,8 +276,8 @@ class MultimodalBertClf(nn.Module):
         self._ensure_grad_views()
         dimg = torch.empty_like(tokens) if need_dimg else None
         inp = _lib.MmbtInputs(txt.data_ptr(), mask.data_ptr(), segment.data_ptr(), tokens.data_ptr(),
-                              _lib.ptr(idx), 0 if idx is None else idx.numel(), _lib.ptr(shadow),
-                              _lib.ptr(dimg))
+                              _lib.ptr(idx), 0 if idx is None else idx.shape[-1],
+                              int(idx is not None and idx.dim() == 2), _lib.ptr(shadow), _lib.ptr(dimg))
         _lib.check(_lib.lib.mmu_mmbt_backward(C.byref(cfg), self._flat.data_ptr(), C.byref(inp),
                                               ws.data_ptr(), ws.numel(), dlogits.data_ptr(),
                                               self._flat_grad.data_ptr(), _lib.stream_ptr()),
@@ -300,6 +308,23 @@ class MultimodalBertClf(nn.Module):
             anchor = next(p for p in self._param_list if p.requires_grad)
             return _MmbtForwardAnchored.apply(anchor, self, tokens, txt, mask, segment, indices)
         return self._engine_forward(tokens, txt, mask, segment, indices, training=False)[-1]
+
+    @torch.no_grad()
+    def forward_index_lists(self, txt, mask, segment, img, index_lists):
+        """Several EQUALLY LONG index lists (robustness variants) evaluated in one pass: the batch is
+        replicated along the batch axis and every replica gets its own list
+        (``mmu_mmbt_inputs.indices_per_sample``).  Inference only.  Returns ``(V, B, C)``; row v is
+        what ``forward_indices(..., index_lists[v])`` returns."""
+        V, B = len(index_lists), txt.shape[0]
+        idx = torch.tensor([list(map(int, il)) for il in index_lists], dtype=torch.int32)
+        idx = idx.repeat_interleave(B, 0)
+        tokens = self._tokens(img)
+
+        def rep(t):
+            return t.repeat(V, *([1] * (t.dim() - 1)))
+
+        logits = self._engine_forward(rep(tokens), rep(txt), rep(mask), rep(segment), idx, training=False)[-1]
+        return logits.view(V, B, -1)
 
     def forward(self, txt, mask, segment, img):
         return self.forward_indices(txt, mask, segment, img, None)

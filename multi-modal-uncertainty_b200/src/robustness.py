@@ -170,11 +170,33 @@ def run_mmbt_robustness(model, generator, n_repeats=20, device=None, posthoc=Non
     for x, y in generator:
         txt, mask, segment, img = (t.to(device, non_blocking=True) for t in x)
         tokens = model._tokens(img)
-        outs = [model(txt, mask, segment, tokens), model.forward_img_only(txt, mask, segment, tokens),
-                model.forward_txt_only(txt, mask, segment, tokens)]
+        n_img, s_txt = model._n_img, txt.shape[1]
+        total = s_txt + n_img + 2
+        # index lists of the 43 variants in the reference's order; the forward_control draws come
+        # from the host RNG in the order the reference's calls would make them
+        lists = [list(range(total)), list(range(n_img + 2)), [0] + list(range(n_img + 2, total))]
         for type in ("image", "text"):
+            num = n_img + 1 if type == "image" else s_txt
             for _ in range(n_repeats):
-                outs.append(model.forward_control(txt, mask, segment, tokens, type))
+                lists.append(model.control_indices(total, num))
+        if hasattr(model, "forward_index_lists"):
+            # equally long variants share ONE pass (the 21 five-token variants -- img_only and the
+            # "image" controls -- would otherwise be 21 launch-bound forwards)
+            outs = [None] * len(lists)
+            by_len = {}
+            for v, il in enumerate(lists):
+                by_len.setdefault(len(il), []).append(v)
+            for length, vs in by_len.items():
+                if len(vs) > 1 and length * len(vs) <= total:
+                    packed = model.forward_index_lists(txt, mask, segment, tokens, [lists[v] for v in vs])
+                    for k, v in enumerate(vs):
+                        outs[v] = packed[k]
+                else:
+                    for v in vs:
+                        outs[v] = model.forward_indices(txt, mask, segment, tokens,
+                                                        None if length == total else lists[v])
+        else:
+            outs = [model.forward_indices(txt, mask, segment, tokens, il) for il in lists]
         y_hat = torch.stack(outs, dim=1)  # (B, V, C)
         if posthoc is not None:
             posthoc.update(y_hat.transpose(0, 1).unsqueeze(2).contiguous(), y.to(device))

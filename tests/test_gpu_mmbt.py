@@ -423,3 +423,21 @@ def test_trainer_runs_the_mmbt_branch_on_the_engine(mmu, golden, tmp_path):
                        freeze_img=0, freeze_txt=2, gradient_accumulation_steps=1, auc=cfg["C"] == 2)
     assert len(logs) == 3 and logs[-1]["loss"] < logs[0]["loss"]
     assert {"acc", "val_loss", "val_acc", "val_auc"} <= set(logs[0])
+
+
+def test_packed_index_lists_equal_one_forward_per_list(mmu, golden):
+    """forward_index_lists (equally long robustness variants packed along the batch axis, per-sample
+    index lists, workspace sized to the lists) against one forward per list, both precisions."""
+    c = golden("mmbt_small.pt")["hd64"]
+    cfg = c["cfg"]
+    total = cfg["S_txt"] + cfg["n_img"] + 2
+    torch.manual_seed(5)
+    for prec in ("fp32", "bf16"):
+        m = build(mmu, c, prec).eval()
+        x = [c[k].cuda() for k in ("txt", "mask", "segment", "img_tokens")]
+        lists = [list(range(cfg["n_img"] + 2))] + [m.control_indices(total, cfg["n_img"] + 1) for _ in range(6)]
+        with torch.no_grad():
+            packed = m.forward_index_lists(*x, lists)
+            for v, il in enumerate(lists):
+                one = m.forward_indices(*x, il)
+                assert torch.equal(packed[v], one), (prec, v)

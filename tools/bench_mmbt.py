@@ -98,6 +98,14 @@ with torch.no_grad():
     ms, _, nl = timed(lambda: m.forward_control(txt, mask, segment, img, "text"), a.steps)
     out["forward_control_text"] = {"ms_per_step": round(ms, 3), "samples_per_s": round(WORLD * B / ms * 1e3, 1)}
 
+    # the whole robustness sweep of one batch (eval_mmbt_robustness.py:76-96): full + img_only + txt_only +
+    # 20 + 20 forward_control draws = 43 variants; image tokens computed once per batch
+    torch.manual_seed(0)
+    batch = [((txt, mask, segment, img), y)]
+    ms, _, nl = timed(lambda: mmu.robustness.run_mmbt_robustness(m, batch, n_repeats=20, device=dev), max(2, a.steps // 3))
+    out["robustness_sweep_43"] = {"ms_per_batch": round(ms, 2), "samples_per_s": round(WORLD * B / ms * 1e3, 1),
+                                  "variant_forwards_per_s": round(WORLD * 43 * B / ms * 1e3, 1), "gpu_launches": int(nl)}
+
 if not a.no_cpu and not a.images and RANK == 0:
     # CPU oracle port, fp32, all host threads, bounded sample: batch 2 of the same shape, 1 train step
     from oracle import mmbt as O
