@@ -158,12 +158,21 @@ bn_sums_kernel(const float* __restrict__ t, int M, int C, int rows_per_block, do
   const int c = blockIdx.x * 32 + cx;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
   double a = 0.0, b = 0.0;
-  if (c < C)
-    for (int r = r0 + ry; r < r1; r += 8) {
+  if (c < C) {
+    int r = r0 + ry;
+    for (; r + 24 < r1; r += 32) {  // four independent loads in flight per thread
+      const float v0 = t[static_cast<size_t>(r) * C + c], v1 = t[static_cast<size_t>(r + 8) * C + c];
+      const float v2 = t[static_cast<size_t>(r + 16) * C + c], v3 = t[static_cast<size_t>(r + 24) * C + c];
+      a += (static_cast<double>(v0) + v1) + (static_cast<double>(v2) + v3);
+      b += (static_cast<double>(v0) * v0 + static_cast<double>(v1) * v1) +
+           (static_cast<double>(v2) * v2 + static_cast<double>(v3) * v3);
+    }
+    for (; r < r1; r += 8) {
       const float v = t[static_cast<size_t>(r) * C + c];
       a += v;
       b += static_cast<double>(v) * v;
     }
+  }
   s1[ry][cx] = a;
   s2[ry][cx] = b;
   __syncthreads();
@@ -245,7 +254,22 @@ bn_bwd_sums_kernel(const float* __restrict__ dout, const float* __restrict__ out
   double a = 0.0, b = 0.0;
   if (c < C) {
     const float mu = mean[c], rs = rstd[c];
-    for (int r = r0 + ry; r < r1; r += 8) {
+    int r = r0 + ry;
+    for (; r + 8 < r1; r += 16) {  // two rows per iteration: six independent loads in flight
+      const size_t i0 = static_cast<size_t>(r) * C + c, i1 = static_cast<size_t>(r + 8) * C + c;
+      float d0 = dout[i0], d1 = dout[i1];
+      const float t0 = t[i0], t1 = t[i1];
+      if (out != nullptr) {
+        const float o0 = out[i0], o1 = out[i1];
+        if (!(o0 > 0.f)) d0 = 0.f;
+        if (!(o1 > 0.f)) d1 = 0.f;
+      }
+      dyb[i0] = d0;
+      dyb[i1] = d1;
+      a += static_cast<double>(d0) + d1;
+      b += static_cast<double>(d0) * ((t0 - mu) * rs) + static_cast<double>(d1) * ((t1 - mu) * rs);
+    }
+    for (; r < r1; r += 8) {
       const size_t i = static_cast<size_t>(r) * C + c;
       float d = dout[i];
       if (out != nullptr && !(out[i] > 0.f)) d = 0.f;
@@ -587,9 +611,22 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
         dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
     RN_CHECK_LAUNCH();
     RN_TRY(tc_columns(x, l, in, in_nchw, cols));
-    int splits = M / 4096;
-    if (splits < 1) splits = 1;
-    if (splits > 16) splits = 16;
+    // Split-K so that the few [co x K] output tiles fill the machine: a layer3 convolution has 18
+    // tiles and 98 k-blocks (an eighth of the SMs busy without a split).  Wave-aware choice as in
+    // engine.cu: the tile count x split lands just under a whole number of waves.
+    const bool pair = l.co >= 512 && K > 128;
+    const int tiles = ((l.co + (pair ? 255 : 127)) / (pair ? 256 : 128)) * ((K + 255) / 256);
+    const int units = pair ? sm_count() / 2 : sm_count();
+    int smax = ((M + 63) / 64) / 4;
+    if (smax > 48) smax = 48;
+    if (smax < 1) smax = 1;
+    int splits = 1;
+    double best = 0.0;
+    for (int sp = 1; sp <= smax; ++sp) {
+      const int t = tiles * sp;
+      const double eff = static_cast<double>(t) / (static_cast<double>((t + units - 1) / units) * units);
+      if (eff > best + 0.02) { best = eff; splits = sp; }
+    }
     GemmProblem p{l.co, K, M, 1, 1, splits};
     RN_TRY(gemm_bf16_launch(dt, l.co, cols, K, p, wg, x.st));
     if (din != nullptr && l.k == 1 && l.stride == 1) {
