@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -114,6 +115,53 @@ im2col_bf16x8_kernel(const float* __restrict__ in, int B, int H, int W, int Ci, 
     pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
     *reinterpret_cast<uint4*>(cols + row * K + static_cast<size_t>(c8) * 8) = pk;
   }
+}
+
+// Padded-K variant for an NCHW input (the image encoder's 7x7 stem): columns [K, Kp) are zero.
+__global__ void __launch_bounds__(256)
+im2col_nchw_pad_bf16x8_kernel(const float* __restrict__ in, int B, int H, int W, int Ci, int k, int stride,
+                              int pad, int Ho, int Wo, int Kp, __nv_bfloat16* __restrict__ cols) {
+  const int kk = k * k, K = Ci * kk, K8 = Kp >> 3;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * K8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % K8);
+    const size_t row = i / K8;
+    const int xo = static_cast<int>(row % Wo), yo = static_cast<int>((row / Wo) % Ho);
+    const int b = static_cast<int>(row / (static_cast<size_t>(Wo) * Ho));
+    const float* base = in + static_cast<size_t>(b) * Ci * H * W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      float val = 0.f;
+      if (c < K) {
+        const int ci = c / kk, tap = c - ci * kk;
+        const int ky = tap / k, kx = tap - ky * k;
+        const int y = yo * stride + ky - pad, x = xo * stride + kx - pad;
+        if (y >= 0 && y < H && x >= 0 && x < W) val = base[(static_cast<size_t>(ci) * H + y) * W + x];
+      }
+      v[j] = val;
+    }
+    uint4 pk;
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+    pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+    *reinterpret_cast<uint4*>(cols + row * Kp + static_cast<size_t>(c8) * 8) = pk;
+  }
+}
+__global__ void pad_weights_bf16_kernel(const float* __restrict__ w, int co, int K, int Kp,
+                                        __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= co * Kp) return;
+  const int r = i / Kp, c = i % Kp;
+  out[i] = __float2bfloat16_rn(c < K ? w[r * K + c] : 0.f);
+}
+__global__ void unpad_add_kernel(const float* __restrict__ dwp, int co, int K, int Kp, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= co * K) return;
+  dw[i] += dwp[(i / K) * Kp + i % K];
 }
 
 // dx(b, y, x, ci) (+)= sum over taps of dcols[(b, yo, xo)][ci*k*k + tap] with y = yo*stride+ky-pad
@@ -456,6 +504,11 @@ struct Ws {
   float* dact[2];  // gradients w.r.t. activations (ping-pong), largest activation size
   float* dres;     // gradient flowing along the residual connection
   float* dpooled;
+  // tensor-core path of a convolution whose K = ci*k*k is not a multiple of 8 (the 7x7x3 stem of
+  // the MMBT image encoder, K = 147): K padded with zero columns to Kp = 152 -- a padded bf16
+  // copy of the weights and an fp32 [co x Kp] scratch for the weight gradient.  Null: disabled.
+  void* pad_w;
+  float* pad_dw;
   long long bytes;
 };
 struct Bump {
@@ -504,6 +557,8 @@ void carve(const ResNetConfig& c, const Net& n, int training, void* base, Ws* w)
   } else {
     w->dcols = w->dyb = w->dt = w->dact[0] = w->dact[1] = w->dres = w->dpooled = nullptr;
   }
+  w->pad_w = nullptr;
+  w->pad_dw = nullptr;
   w->bytes = b.off;
 }
 
@@ -528,6 +583,10 @@ struct Ctx {
 // A layer runs on the tcgen05 path when a bf16 shadow is given and its GEMM K (= ci*k*k) keeps
 // operand rows 16-byte aligned (every layer but the 4-channel stem, K = 36).
 bool use_tc(const Ctx& x, const ConvBn& l) { return x.shadow != nullptr && (l.ci * l.k * l.k) % 8 == 0; }
+// ... or, with K padded to a multiple of 8, when the padded scratch exists (image-encoder stem)
+bool use_tc_padded(const Ctx& x, const ConvBn& l, int in_nchw) {
+  return x.shadow != nullptr && (l.ci * l.k * l.k) % 8 != 0 && in_nchw && x.w.pad_w != nullptr;
+}
 const __nv_bfloat16* wbf(const Ctx& x, const ConvBn& l) {
   return static_cast<const __nv_bfloat16*>(x.shadow) + l.w;
 }
@@ -555,7 +614,18 @@ int conv_bn_fwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
   const int M = static_cast<int>(rows_of(x.c, l.hout)), K = l.ci * l.k * l.k;
   const size_t ncols = static_cast<size_t>(M) * K;
   GemmProblem p{M, l.co, K, 0, 0, 1};
-  if (use_tc(x, l)) {
+  if (use_tc_padded(x, l, in_nchw)) {
+    const int Kp = (K + 7) / 8 * 8;
+    __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(x.w.cols);
+    __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(x.w.pad_w);
+    pad_weights_bf16_kernel<<<(l.co * Kp + 255) / 256, 256, 0, x.st>>>(x.params + l.w, l.co, K, Kp, wp);
+    RN_CHECK_LAUNCH();
+    im2col_nchw_pad_bf16x8_kernel<<<blocks_for(static_cast<size_t>(M) * (Kp / 8), 256), 256, 0, x.st>>>(
+        in, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, Kp, cols);
+    RN_CHECK_LAUNCH();
+    GemmProblem pp{M, l.co, Kp, 0, 0, 1};
+    RN_TRY(gemm_bf16_launch(cols, Kp, wp, Kp, pp, store_epi(o.t, l.co, nullptr), x.st));
+  } else if (use_tc(x, l)) {
     __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(x.w.cols);
     RN_TRY(tc_columns(x, l, in, in_nchw, cols));
     RN_TRY(gemm_bf16_launch(cols, K, wbf(x, l), K, p, store_epi(o.t, l.co, nullptr), x.st));
@@ -602,6 +672,31 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
   const size_t nin = static_cast<size_t>(x.c.B) * l.hin * l.hin * l.ci;
   GemmEpilogue wg{};
   wg.mode = EPI_ATOMIC; wg.out = x.grads + l.w; wg.ld_out = K; wg.alpha = 1.0f;
+  if (use_tc_padded(x, l, in_nchw) && din == nullptr) {
+    // padded-K tensor-core weight gradient (7x7x3 stem): dW_p[co, Kp] in a scratch, then += into dW
+    const int Kp = (K + 7) / 8 * 8;
+    __nv_bfloat16* dt = reinterpret_cast<__nv_bfloat16*>(x.w.dt);
+    __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(x.w.cols);
+    bn_bwd_apply_kernel<__nv_bfloat16><<<blocks_for(n, 256), 256, 0, x.st>>>(
+        dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
+    RN_CHECK_LAUNCH();
+    im2col_nchw_pad_bf16x8_kernel<<<blocks_for(static_cast<size_t>(M) * (Kp / 8), 256), 256, 0, x.st>>>(
+        in, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, Kp, cols);
+    RN_CHECK_LAUNCH();
+    if (cudaMemsetAsync(x.w.pad_dw, 0, static_cast<size_t>(l.co) * Kp * 4, x.st) != cudaSuccess) return MMU_ERR_CUDA;
+    GemmEpilogue wgp{};
+    wgp.mode = EPI_ATOMIC; wgp.out = x.w.pad_dw; wgp.ld_out = Kp; wgp.alpha = 1.0f;
+    int splits = sm_count() / ((Kp + 255) / 256);
+    if (const char* e = getenv("MMU_STEM_SPLITS")) splits = atoi(e);
+    const int kb = (M + 63) / 64;
+    if (splits > kb / 4) splits = kb / 4;
+    if (splits < 1) splits = 1;
+    GemmProblem p{l.co, Kp, M, 1, 1, splits};
+    RN_TRY(gemm_bf16_launch(dt, l.co, cols, Kp, p, wgp, x.st));
+    unpad_add_kernel<<<(l.co * K + 255) / 256, 256, 0, x.st>>>(x.w.pad_dw, l.co, K, Kp, x.grads + l.w);
+    RN_CHECK_LAUNCH();
+    return 0;
+  }
   if (use_tc(x, l)) {
     // tensor-core path: dt and the recomputed columns in bf16, fp32 accumulation / outputs
     __nv_bfloat16* dt = reinterpret_cast<__nv_bfloat16*>(x.w.dt);
@@ -923,6 +1018,14 @@ void ie_carve(const ImgEncConfig& c, const IeNet& n, int training, void* base, I
   w->mp_idx = b.take<unsigned char>(mp_el);
   w->pool_idx = b.take<int>(static_cast<long long>(c.B) * c.pool_h * c.pool_w * n.c_out * 4);
   std::memset(&w->shared, 0, sizeof(w->shared));
+  {  // padded stem operands (K = 147 -> 152)
+    const ConvBn& st = n.conv[0];
+    const long long Kp = (st.ci * st.k * st.k + 7) / 8 * 8;
+    w->shared.pad_w = b.take<void>(st.co * Kp * 2);
+    w->shared.pad_dw = b.take<float>(st.co * Kp * 4);
+    const long long m0 = static_cast<long long>(c.B) * st.hout * st.hout;
+    if (m0 * Kp > max_cols) max_cols = m0 * Kp;
+  }
   w->shared.cols = b.take<float>(max_cols * 4);
   w->shared.sums = b.take<double>(2LL * max_co * 8);
   if (training) {
