@@ -60,6 +60,22 @@ __device__ __forceinline__ void put(__nv_bfloat16* p, float v) { *p = __float2bf
 __device__ __forceinline__ float get(const float* p) { return *p; }
 __device__ __forceinline__ float get(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 pk = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
 // ------------------------------------------------------------------------- im2col / col2im
 // cols[(b, yo, xo)][ci*k*k + ky*k + kx] = in(b, yo*stride + ky - pad, xo*stride + kx - pad, ci)
 // Threads run over (row, tap, ci) with ci fastest: NHWC reads are coalesced.
@@ -87,8 +103,9 @@ __global__ void im2col_kernel(const float* __restrict__ in, int nchw, int B, int
 // bf16 columns, NHWC input, K % 8 == 0: one thread writes 8 consecutive columns of a row as one
 // 16-byte store (the scalar kernel above scatters 2-byte stores 2*k*k bytes apart); the reads are
 // 3x3 neighbourhoods that overlap between rows and stay in L1 / L2.
+template <typename TA>
 __global__ void __launch_bounds__(256)
-im2col_bf16x8_kernel(const float* __restrict__ in, int B, int H, int W, int Ci, int k, int stride, int pad,
+im2col_bf16x8_kernel(const TA* __restrict__ in, int B, int H, int W, int Ci, int k, int stride, int pad,
                      int Ho, int Wo, __nv_bfloat16* __restrict__ cols) {
   const int kk = k * k, K = Ci * kk, K8 = K >> 3;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * K8;
@@ -98,14 +115,14 @@ im2col_bf16x8_kernel(const float* __restrict__ in, int B, int H, int W, int Ci, 
     const size_t row = i / K8;
     const int xo = static_cast<int>(row % Wo), yo = static_cast<int>((row / Wo) % Ho);
     const int b = static_cast<int>(row / (static_cast<size_t>(Wo) * Ho));
-    const float* base = in + static_cast<size_t>(b) * H * W * Ci;
+    const TA* base = in + static_cast<size_t>(b) * H * W * Ci;
     int ci = (c8 * 8) / kk, tap = (c8 * 8) % kk;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int ky = tap / k, kx = tap - ky * k;
       const int y = yo * stride + ky - pad, x = xo * stride + kx - pad;
-      v[j] = (y >= 0 && y < H && x >= 0 && x < W) ? base[(static_cast<size_t>(y) * W + x) * Ci + ci] : 0.f;
+      v[j] = (y >= 0 && y < H && x >= 0 && x < W) ? get(base + (static_cast<size_t>(y) * W + x) * Ci + ci) : 0.f;
       if (++tap == kk) { tap = 0; ++ci; }
     }
     uint4 pk;
@@ -199,8 +216,9 @@ __global__ void col2im_kernel(const TC* __restrict__ dcols, int B, int H, int W,
 // ------------------------------------------------------------------------------- BatchNorm
 // Column sums of t and t^2 over the M rows (fp64 partials: E[x^2]-E[x]^2 is then safe).
 // Block = 32 columns x 8 row lanes; grid.y slabs of rows.
+template <typename TA>
 __global__ void __launch_bounds__(256)
-bn_sums_kernel(const float* __restrict__ t, int M, int C, int rows_per_block, double* __restrict__ sums) {
+bn_sums_kernel(const TA* __restrict__ t, int M, int C, int rows_per_block, double* __restrict__ sums) {
   __shared__ double s1[8][33], s2[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -209,14 +227,14 @@ bn_sums_kernel(const float* __restrict__ t, int M, int C, int rows_per_block, do
   if (c < C) {
     int r = r0 + ry;
     for (; r + 24 < r1; r += 32) {  // four independent loads in flight per thread
-      const float v0 = t[static_cast<size_t>(r) * C + c], v1 = t[static_cast<size_t>(r + 8) * C + c];
-      const float v2 = t[static_cast<size_t>(r + 16) * C + c], v3 = t[static_cast<size_t>(r + 24) * C + c];
+      const float v0 = get(t + static_cast<size_t>(r) * C + c), v1 = get(t + static_cast<size_t>(r + 8) * C + c);
+      const float v2 = get(t + static_cast<size_t>(r + 16) * C + c), v3 = get(t + static_cast<size_t>(r + 24) * C + c);
       a += (static_cast<double>(v0) + v1) + (static_cast<double>(v2) + v3);
       b += (static_cast<double>(v0) * v0 + static_cast<double>(v1) * v1) +
            (static_cast<double>(v2) * v2 + static_cast<double>(v3) * v3);
     }
     for (; r < r1; r += 8) {
-      const float v = t[static_cast<size_t>(r) * C + c];
+      const float v = get(t + static_cast<size_t>(r) * C + c);
       a += v;
       b += static_cast<double>(v) * v;
     }
@@ -260,14 +278,15 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean,
 }
 
 // out = [relu]( (t - mean) * rstd * gamma + beta [+ residual] )
-__global__ void bn_apply_kernel(const float* __restrict__ t, const float* __restrict__ mean,
+template <typename TA>
+__global__ void bn_apply_kernel(const TA* __restrict__ t, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const float* __restrict__ residual,
-                                int relu, float* __restrict__ out, size_t n4, int C) {
+                                const float* __restrict__ beta, const TA* __restrict__ residual,
+                                int relu, TA* __restrict__ out, size_t n4, int C) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>((i * 4) % C);
-    const float4 v = reinterpret_cast<const float4*>(t)[i];
+    const float4 v = ld4(t + 4 * i);
     const float4 mu = *reinterpret_cast<const float4*>(mean + c);
     const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
     const float4 g = *reinterpret_cast<const float4*>(gamma + c);
@@ -278,21 +297,22 @@ __global__ void bn_apply_kernel(const float* __restrict__ t, const float* __rest
     o.z = (v.z - mu.z) * rs.z * g.z + be.z;
     o.w = (v.w - mu.w) * rs.w * g.w + be.w;
     if (residual != nullptr) {
-      const float4 r = reinterpret_cast<const float4*>(residual)[i];
+      const float4 r = ld4(residual + 4 * i);
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
     if (relu) {
       o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
     }
-    reinterpret_cast<float4*>(out)[i] = o;
+    st4(out + 4 * i, o);
   }
 }
 
 // Backward, pass 1: dyb = dout * [out > 0] (ReLU mask from the saved output; out == nullptr: no
 // ReLU), column sums of dyb and dyb * xhat.
+template <typename TA>
 __global__ void __launch_bounds__(256)
-bn_bwd_sums_kernel(const float* __restrict__ dout, const float* __restrict__ out,
-                   const float* __restrict__ t, const float* __restrict__ mean,
+bn_bwd_sums_kernel(const float* __restrict__ dout, const TA* __restrict__ out,
+                   const TA* __restrict__ t, const float* __restrict__ mean,
                    const float* __restrict__ rstd, int M, int C, int rows_per_block,
                    float* __restrict__ dyb, double* __restrict__ sums) {
   __shared__ double s1[8][33], s2[8][33];
@@ -306,9 +326,9 @@ bn_bwd_sums_kernel(const float* __restrict__ dout, const float* __restrict__ out
     for (; r + 8 < r1; r += 16) {  // two rows per iteration: six independent loads in flight
       const size_t i0 = static_cast<size_t>(r) * C + c, i1 = static_cast<size_t>(r + 8) * C + c;
       float d0 = dout[i0], d1 = dout[i1];
-      const float t0 = t[i0], t1 = t[i1];
+      const float t0 = get(t + i0), t1 = get(t + i1);
       if (out != nullptr) {
-        const float o0 = out[i0], o1 = out[i1];
+        const float o0 = get(out + i0), o1 = get(out + i1);
         if (!(o0 > 0.f)) d0 = 0.f;
         if (!(o1 > 0.f)) d1 = 0.f;
       }
@@ -320,10 +340,10 @@ bn_bwd_sums_kernel(const float* __restrict__ dout, const float* __restrict__ out
     for (; r < r1; r += 8) {
       const size_t i = static_cast<size_t>(r) * C + c;
       float d = dout[i];
-      if (out != nullptr && !(out[i] > 0.f)) d = 0.f;
+      if (out != nullptr && !(get(out + i) > 0.f)) d = 0.f;
       dyb[i] = d;
       a += d;
-      b += static_cast<double>(d) * ((t[i] - mu) * rs);
+      b += static_cast<double>(d) * ((get(t + i) - mu) * rs);
     }
   }
   s1[ry][cx] = a;
@@ -338,8 +358,8 @@ bn_bwd_sums_kernel(const float* __restrict__ dout, const float* __restrict__ out
 
 // Backward, pass 2: dt = gamma * rstd * (dyb - mean(dyb) - xhat * mean(dyb * xhat));
 // thread 0..C-1 of block 0 also accumulate dgamma / dbeta.
-template <typename TD>
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dyb, const float* __restrict__ t,
+template <typename TD, typename TA>
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dyb, const TA* __restrict__ t,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gamma, const double* __restrict__ sums,
                                     int M, int C, TD* __restrict__ dt, float* __restrict__ dgamma,
@@ -354,7 +374,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dyb, const float* 
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C);
     const float rs = rstd[c];
-    const float xh = (t[i] - mean[c]) * rs;
+    const float xh = (get(t + i) - mean[c]) * rs;
     const float m1 = static_cast<float>(sums[c] / M), m2 = static_cast<float>(sums[C + c] / M);
     put(dt + i, gamma[c] * rs * (dyb[i] - m1 - xh * m2));
   }
@@ -578,7 +598,14 @@ struct Ctx {
   int training;
   Ws& w;
   cudaStream_t st;
+  // 1: the activations (conv outputs t, BatchNorm outputs, pooled maps) are bf16 -- the MMBT image
+  // encoder's tensor-core mode; the buffers are still declared float* and reinterpreted.  An NCHW
+  // input (the images) is always fp32.  0: fp32 activations (FashionMNIST engine, parity paths).
+  int act16 = 0;
 };
+using bf16_t = __nv_bfloat16;
+inline const bf16_t* as16(const float* p) { return reinterpret_cast<const bf16_t*>(p); }
+inline bf16_t* as16(float* p) { return reinterpret_cast<bf16_t*>(p); }
 
 // A layer runs on the tcgen05 path when a bf16 shadow is given and its GEMM K (= ci*k*k) keeps
 // operand rows 16-byte aligned (every layer but the 4-channel stem, K = 36).
@@ -591,18 +618,32 @@ const __nv_bfloat16* wbf(const Ctx& x, const ConvBn& l) {
   return static_cast<const __nv_bfloat16*>(x.shadow) + l.w;
 }
 
-// bf16 columns of a layer for the tensor-core path: a 1x1 stride-1 convolution's columns ARE its
-// NHWC input (one vectorised cast); otherwise 8 columns per thread.
-int tc_columns(const Ctx& x, const ConvBn& l, const float* in, int in_nchw, __nv_bfloat16* cols) {
+// bf16 columns of a layer for the tensor-core path (*cols_out = the GEMM operand): a 1x1 stride-1
+// convolution's columns ARE its NHWC input -- used in place when the activations are bf16, one
+// vectorised cast otherwise; other shapes: 8 columns per thread.
+int tc_columns(const Ctx& x, const ConvBn& l, const float* in, int in_nchw, __nv_bfloat16* cols,
+               const __nv_bfloat16** cols_out) {
   const size_t M = static_cast<size_t>(rows_of(x.c, l.hout));
   const int K = l.ci * l.k * l.k;
-  if (l.k == 1 && l.stride == 1 && !in_nchw) return cast_f32_to_bf16(in, cols, M * K, x.st);
+  *cols_out = cols;
+  if (l.k == 1 && l.stride == 1 && !in_nchw) {
+    if (x.act16) {
+      *cols_out = as16(in);
+      return 0;
+    }
+    return cast_f32_to_bf16(in, cols, M * K, x.st);
+  }
   if (!in_nchw && K % 8 == 0) {
-    im2col_bf16x8_kernel<<<blocks_for(M * (K / 8), 256), 256, 0, x.st>>>(
-        in, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
+    if (x.act16)
+      im2col_bf16x8_kernel<bf16_t><<<blocks_for(M * (K / 8), 256), 256, 0, x.st>>>(
+          as16(in), x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
+    else
+      im2col_bf16x8_kernel<float><<<blocks_for(M * (K / 8), 256), 256, 0, x.st>>>(
+          in, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
     RN_CHECK_LAUNCH();
     return 0;
   }
+  if (x.act16 && !in_nchw) return MMU_ERR_SHAPE;  // bf16 activations need K % 8 == 0 everywhere
   im2col_kernel<__nv_bfloat16><<<blocks_for(M * K, 256), 256, 0, x.st>>>(
       in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
   RN_CHECK_LAUNCH();
@@ -624,12 +665,17 @@ int conv_bn_fwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
         in, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, Kp, cols);
     RN_CHECK_LAUNCH();
     GemmProblem pp{M, l.co, Kp, 0, 0, 1};
-    RN_TRY(gemm_bf16_launch(cols, Kp, wp, Kp, pp, store_epi(o.t, l.co, nullptr), x.st));
+    GemmEpilogue e = store_epi(o.t, l.co, nullptr);
+    e.out_bf16 = x.act16;
+    RN_TRY(gemm_bf16_launch(cols, Kp, wp, Kp, pp, e, x.st));
   } else if (use_tc(x, l)) {
-    __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(x.w.cols);
-    RN_TRY(tc_columns(x, l, in, in_nchw, cols));
-    RN_TRY(gemm_bf16_launch(cols, K, wbf(x, l), K, p, store_epi(o.t, l.co, nullptr), x.st));
+    const __nv_bfloat16* cols = nullptr;
+    RN_TRY(tc_columns(x, l, in, in_nchw, reinterpret_cast<__nv_bfloat16*>(x.w.cols), &cols));
+    GemmEpilogue e = store_epi(o.t, l.co, nullptr);
+    e.out_bf16 = x.act16;
+    RN_TRY(gemm_bf16_launch(cols, K, wbf(x, l), K, p, e, x.st));
   } else {
+    if (x.act16) return MMU_ERR_SHAPE;
     im2col_kernel<float><<<blocks_for(ncols, 256), 256, 0, x.st>>>(
         in, in_nchw, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, x.w.cols);
     RN_CHECK_LAUNCH();
@@ -638,7 +684,8 @@ int conv_bn_fwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
   if (x.training) {
     if (cudaMemsetAsync(x.w.sums, 0, 2 * l.co * sizeof(double), x.st) != cudaSuccess) return MMU_ERR_CUDA;
     const int gy = (M + 511) / 512;
-    bn_sums_kernel<<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(o.t, M, l.co, 512, x.w.sums);
+    if (x.act16) bn_sums_kernel<bf16_t><<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(as16(o.t), M, l.co, 512, x.w.sums);
+    else bn_sums_kernel<float><<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(o.t, M, l.co, 512, x.w.sums);
     RN_CHECK_LAUNCH();
     bn_finalize_kernel<<<(l.co + 127) / 128, 128, 0, x.st>>>(x.w.sums, M, l.co, 0.1f, o.mean, o.rstd,
                                                               x.stats + l.stat, x.stats + l.stat + (l.co + 63) / 64 * 64);
@@ -649,8 +696,12 @@ int conv_bn_fwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
     RN_CHECK_LAUNCH();
   }
   const size_t n4 = static_cast<size_t>(M) * l.co / 4;
-  bn_apply_kernel<<<blocks_for(n4, 256), 256, 0, x.st>>>(o.t, o.mean, o.rstd, x.params + l.g,
-                                                         x.params + l.b, residual, relu, o.out, n4, l.co);
+  if (x.act16)
+    bn_apply_kernel<bf16_t><<<blocks_for(n4, 256), 256, 0, x.st>>>(
+        as16(o.t), o.mean, o.rstd, x.params + l.g, x.params + l.b, as16(residual), relu, as16(o.out), n4, l.co);
+  else
+    bn_apply_kernel<float><<<blocks_for(n4, 256), 256, 0, x.st>>>(o.t, o.mean, o.rstd, x.params + l.g,
+                                                                  x.params + l.b, residual, relu, o.out, n4, l.co);
   RN_CHECK_LAUNCH();
   return 0;
 }
@@ -664,8 +715,12 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
   if (cudaMemsetAsync(x.w.sums, 0, 2 * l.co * sizeof(double), x.st) != cudaSuccess) return MMU_ERR_CUDA;
   float* dyb = dres_out != nullptr ? dres_out : x.w.dyb;
   const int gy = (M + 511) / 512;
-  bn_bwd_sums_kernel<<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(
-      dout, relu ? o.out : nullptr, o.t, o.mean, o.rstd, M, l.co, 512, dyb, x.w.sums);
+  if (x.act16)
+    bn_bwd_sums_kernel<bf16_t><<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(
+        dout, relu ? as16(o.out) : nullptr, as16(o.t), o.mean, o.rstd, M, l.co, 512, dyb, x.w.sums);
+  else
+    bn_bwd_sums_kernel<float><<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(
+        dout, relu ? o.out : nullptr, o.t, o.mean, o.rstd, M, l.co, 512, dyb, x.w.sums);
   RN_CHECK_LAUNCH();
   const size_t n = static_cast<size_t>(M) * l.co;
   const size_t ncols = static_cast<size_t>(M) * K;
@@ -677,8 +732,12 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
     const int Kp = (K + 7) / 8 * 8;
     __nv_bfloat16* dt = reinterpret_cast<__nv_bfloat16*>(x.w.dt);
     __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(x.w.cols);
-    bn_bwd_apply_kernel<__nv_bfloat16><<<blocks_for(n, 256), 256, 0, x.st>>>(
-        dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
+    if (x.act16)
+      bn_bwd_apply_kernel<bf16_t, bf16_t><<<blocks_for(n, 256), 256, 0, x.st>>>(
+          dyb, as16(o.t), o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
+    else
+      bn_bwd_apply_kernel<bf16_t, float><<<blocks_for(n, 256), 256, 0, x.st>>>(
+          dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
     RN_CHECK_LAUNCH();
     im2col_nchw_pad_bf16x8_kernel<<<blocks_for(static_cast<size_t>(M) * (Kp / 8), 256), 256, 0, x.st>>>(
         in, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, Kp, cols);
@@ -702,10 +761,15 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
     __nv_bfloat16* dt = reinterpret_cast<__nv_bfloat16*>(x.w.dt);
     __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(x.w.cols);
     __nv_bfloat16* dcols = reinterpret_cast<__nv_bfloat16*>(x.w.dcols);
-    bn_bwd_apply_kernel<__nv_bfloat16><<<blocks_for(n, 256), 256, 0, x.st>>>(
-        dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
+    if (x.act16)
+      bn_bwd_apply_kernel<bf16_t, bf16_t><<<blocks_for(n, 256), 256, 0, x.st>>>(
+          dyb, as16(o.t), o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
+    else
+      bn_bwd_apply_kernel<bf16_t, float><<<blocks_for(n, 256), 256, 0, x.st>>>(
+          dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
     RN_CHECK_LAUNCH();
-    RN_TRY(tc_columns(x, l, in, in_nchw, cols));
+    const __nv_bfloat16* wcols = nullptr;
+    RN_TRY(tc_columns(x, l, in, in_nchw, cols, &wcols));
     // Split-K so that the few [co x K] output tiles fill the machine: a layer3 convolution has 18
     // tiles and 98 k-blocks (an eighth of the SMs busy without a split).  Wave-aware choice as in
     // engine.cu: the tile count x split lands just under a whole number of waves.
@@ -723,7 +787,7 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
       if (eff > best + 0.02) { best = eff; splits = sp; }
     }
     GemmProblem p{l.co, K, M, 1, 1, splits};
-    RN_TRY(gemm_bf16_launch(dt, l.co, cols, K, p, wg, x.st));
+    RN_TRY(gemm_bf16_launch(dt, l.co, wcols, K, p, wg, x.st));
     if (din != nullptr && l.k == 1 && l.stride == 1) {
       // 1x1 stride-1: the input gradient IS dt W -- written (or TMA-reduce-added) straight to din
       GemmProblem q{M, K, l.co, 0, 1, 1};
@@ -741,7 +805,8 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
     }
     return 0;
   }
-  bn_bwd_apply_kernel<float><<<blocks_for(n, 256), 256, 0, x.st>>>(
+  if (x.act16) return MMU_ERR_SHAPE;
+  bn_bwd_apply_kernel<float, float><<<blocks_for(n, 256), 256, 0, x.st>>>(
       dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, x.w.dt, x.grads + l.g, x.grads + l.b);
   RN_CHECK_LAUNCH();
   // weight gradient: dW[co, K] += dt^T cols   (cols recomputed: 9x cheaper than keeping them)
@@ -1043,8 +1108,9 @@ void ie_carve(const ImgEncConfig& c, const IeNet& n, int training, void* base, I
 
 // MaxPool2d(kernel 3, stride 2, padding 1) on NHWC; idx = window tap (ky*3+kx) of the maximum
 // (first maximum in scan order, like torch's CPU kernel).
-__global__ void maxpool_fwd_kernel(const float* __restrict__ a, int B, int H, int Ho, int C,
-                                   float* __restrict__ out, unsigned char* __restrict__ idx) {
+template <typename TA>
+__global__ void maxpool_fwd_kernel(const TA* __restrict__ a, int B, int H, int Ho, int C,
+                                   TA* __restrict__ out, unsigned char* __restrict__ idx) {
   const size_t total = static_cast<size_t>(B) * Ho * Ho * C;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -1060,11 +1126,11 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ a, int B, int H, in
       for (int kx = 0; kx < 3; ++kx) {
         const int x = xo * 2 + kx - 1;
         if (x < 0 || x >= H) continue;
-        const float v = a[((static_cast<size_t>(b) * H + y) * H + x) * C + c];
+        const float v = get(a + ((static_cast<size_t>(b) * H + y) * H + x) * C + c);
         if (v > best) { best = v; tap = ky * 3 + kx; }
       }
     }
-    out[i] = best;
+    put(out + i, best);
     idx[i] = static_cast<unsigned char>(tap);
   }
 }
@@ -1098,7 +1164,8 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const unsigne
 }
 // AdaptiveAvgPool2d / AdaptiveMaxPool2d((ph, pw)) on the (B, H, H, C) NHWC map, written as tokens
 // (B, ph*pw, C): cell (i, j) covers rows [floor(i H / ph), ceil((i+1) H / ph)), likewise columns.
-__global__ void adaptive_pool_fwd_kernel(const float* __restrict__ a, int B, int H, int C, int ph, int pw,
+template <typename TA>
+__global__ void adaptive_pool_fwd_kernel(const TA* __restrict__ a, int B, int H, int C, int ph, int pw,
                                          int is_max, float* __restrict__ tok, int* __restrict__ arg) {
   const size_t total = static_cast<size_t>(B) * ph * pw * C;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -1113,7 +1180,7 @@ __global__ void adaptive_pool_fwd_kernel(const float* __restrict__ a, int B, int
     int best = 0;
     for (int y = y0; y < y1; ++y)
       for (int x = x0; x < x1; ++x) {
-        const float v = a[((static_cast<size_t>(b) * H + y) * H + x) * C + c];
+        const float v = get(a + ((static_cast<size_t>(b) * H + y) * H + x) * C + c);
         if (is_max) { if (v > s) { s = v; best = y * H + x; } }
         else s += v;
       }
@@ -1195,12 +1262,19 @@ namespace {
 int ie_forward(const ImgEncConfig& c, const IeNet& n, IeWs& w, const float* params, const void* shadow,
                float* stats, const float* x_nchw, int training, float* tokens, cudaStream_t stream) {
   const ResNetConfig rc = ie_rc(c);
-  const Ctx x{rc, shadow, params, stats, nullptr, training, w.shared, stream};
+  // tensor-core mode keeps every activation in bf16 (halves the BatchNorm / column traffic, and a
+  // 1x1 convolution reads its input in place)
+  const int act16 = shadow != nullptr;
+  const Ctx x{rc, shadow, params, stats, nullptr, training, w.shared, stream, act16};
   RN_TRY(conv_bn_fwd(x, n.conv[0], w.cb[0], x_nchw, 1, nullptr, 1));
   {
     const size_t total = static_cast<size_t>(c.B) * n.h_pool_in * n.h_pool_in * 64;
-    maxpool_fwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w.cb[0].out, c.B, n.conv[0].hout,
-                                                                    n.h_pool_in, 64, w.mp, w.mp_idx);
+    if (act16)
+      maxpool_fwd_kernel<bf16_t><<<blocks_for(total, 256), 256, 0, stream>>>(
+          as16(w.cb[0].out), c.B, n.conv[0].hout, n.h_pool_in, 64, as16(w.mp), w.mp_idx);
+    else
+      maxpool_fwd_kernel<float><<<blocks_for(total, 256), 256, 0, stream>>>(w.cb[0].out, c.B, n.conv[0].hout,
+                                                                           n.h_pool_in, 64, w.mp, w.mp_idx);
     RN_CHECK_LAUNCH();
   }
   const float* a = w.mp;
@@ -1217,8 +1291,12 @@ int ie_forward(const ImgEncConfig& c, const IeNet& n, IeWs& w, const float* para
     a = w.cb[B.c3].out;
   }
   const size_t total = static_cast<size_t>(c.B) * c.pool_h * c.pool_w * n.c_out;
-  adaptive_pool_fwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(a, c.B, n.h_out, n.c_out, c.pool_h,
-                                                                        c.pool_w, c.pool_max, tokens, w.pool_idx);
+  if (act16)
+    adaptive_pool_fwd_kernel<bf16_t><<<blocks_for(total, 256), 256, 0, stream>>>(
+        as16(a), c.B, n.h_out, n.c_out, c.pool_h, c.pool_w, c.pool_max, tokens, w.pool_idx);
+  else
+    adaptive_pool_fwd_kernel<float><<<blocks_for(total, 256), 256, 0, stream>>>(
+        a, c.B, n.h_out, n.c_out, c.pool_h, c.pool_w, c.pool_max, tokens, w.pool_idx);
   RN_CHECK_LAUNCH();
   return 0;
 }
@@ -1226,7 +1304,7 @@ int ie_forward(const ImgEncConfig& c, const IeNet& n, IeWs& w, const float* para
 int ie_backward(const ImgEncConfig& c, const IeNet& n, IeWs& w, const float* params, const void* shadow,
                 float* stats, const float* x_nchw, const float* dtokens, float* grads, cudaStream_t stream) {
   const ResNetConfig rc = ie_rc(c);
-  const Ctx x{rc, shadow, params, stats, grads, 1, w.shared, stream};
+  const Ctx x{rc, shadow, params, stats, grads, 1, w.shared, stream, shadow != nullptr};
   float* dcur = w.dact[0];
   float* dnext = w.dact[1];
   {
