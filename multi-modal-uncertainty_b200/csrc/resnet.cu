@@ -216,36 +216,71 @@ __global__ void col2im_kernel(const TC* __restrict__ dcols, int B, int H, int W,
 // ------------------------------------------------------------------------------- BatchNorm
 // Column sums of t and t^2 over the M rows (fp64 partials: E[x^2]-E[x]^2 is then safe).
 // Block = 32 columns x 8 row lanes; grid.y slabs of rows.
+// Geometry of the column-statistics kernels: a thread owns 4 adjacent columns (one 16- / 8-byte
+// load per row), TX threads across the columns (a power of two, <= 32, i.e. up to 128 columns per
+// block) and 256 / TX row lanes; per-thread fp32 partial sums over short row runs are folded into
+// fp64 accumulators, reduced through shared memory, then added atomically (fp64).
+struct ColGeo { int tx, ty, gx; };
+inline int stat_rows_per_block(int M, const ColGeo& g);
+inline ColGeo col_geo(int C) {
+  int tx = 1;
+  while (tx < 32 && tx * 2 <= C / 4) tx *= 2;
+  return ColGeo{tx, 256 / tx, (C / 4 + tx - 1) / tx};
+}
+
+// rows per block: enough blocks to fill the machine a few times over, at least 4 row steps each
+inline int stat_rows_per_block(int M, const ColGeo& g) {
+  const int target_blocks = 148 * 6;
+  int gy = (target_blocks + g.gx - 1) / g.gx;
+  int rpb = (M + gy - 1) / gy;
+  const int min_rows = 8 * g.ty;
+  if (rpb < min_rows) rpb = min_rows;
+  return (rpb + g.ty - 1) / g.ty * g.ty;
+}
+
 template <typename TA>
 __global__ void __launch_bounds__(256)
-bn_sums_kernel(const TA* __restrict__ t, int M, int C, int rows_per_block, double* __restrict__ sums) {
-  __shared__ double s1[8][33], s2[8][33];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
+bn_sums_kernel(const TA* __restrict__ t, int M, int C, int rows_per_block, int TX, double* __restrict__ sums) {
+  __shared__ double red[256][8];
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = 256 / TX;
+  const int c = (blockIdx.x * TX + tx) * 4;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
-  double a = 0.0, b = 0.0;
+  double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
   if (c < C) {
-    int r = r0 + ry;
-    for (; r + 24 < r1; r += 32) {  // four independent loads in flight per thread
-      const float v0 = get(t + static_cast<size_t>(r) * C + c), v1 = get(t + static_cast<size_t>(r + 8) * C + c);
-      const float v2 = get(t + static_cast<size_t>(r + 16) * C + c), v3 = get(t + static_cast<size_t>(r + 24) * C + c);
-      a += (static_cast<double>(v0) + v1) + (static_cast<double>(v2) + v3);
-      b += (static_cast<double>(v0) * v0 + static_cast<double>(v1) * v1) +
-           (static_cast<double>(v2) * v2 + static_cast<double>(v3) * v3);
+    int r = r0 + ty;
+    for (; r + 3 * TY < r1; r += 4 * TY) {  // four independent vector loads in flight
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ld4(t + static_cast<size_t>(r + u * TY) * C + c);
+      float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s1.x += v[u].x; s1.y += v[u].y; s1.z += v[u].z; s1.w += v[u].w;
+        s2.x = fmaf(v[u].x, v[u].x, s2.x); s2.y = fmaf(v[u].y, v[u].y, s2.y);
+        s2.z = fmaf(v[u].z, v[u].z, s2.z); s2.w = fmaf(v[u].w, v[u].w, s2.w);
+      }
+      a[0] += s1.x; a[1] += s1.y; a[2] += s1.z; a[3] += s1.w;
+      b[0] += s2.x; b[1] += s2.y; b[2] += s2.z; b[3] += s2.w;
     }
-    for (; r < r1; r += 8) {
-      const float v = get(t + static_cast<size_t>(r) * C + c);
-      a += v;
-      b += static_cast<double>(v) * v;
+    for (; r < r1; r += TY) {
+      const float4 v = ld4(t + static_cast<size_t>(r) * C + c);
+      a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+      b[0] += static_cast<double>(v.x) * v.x; b[1] += static_cast<double>(v.y) * v.y;
+      b[2] += static_cast<double>(v.z) * v.z; b[3] += static_cast<double>(v.w) * v.w;
     }
   }
-  s1[ry][cx] = a;
-  s2[ry][cx] = b;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[threadIdx.x][j] = a[j]; red[threadIdx.x][4 + j] = b[j]; }
   __syncthreads();
-  if (ry == 0 && c < C) {
-    for (int j = 1; j < 8; ++j) { a += s1[j][cx]; b += s2[j][cx]; }
-    atomicAdd(&sums[c], a);
-    atomicAdd(&sums[C + c], b);
+  if (ty == 0 && c < C) {
+    for (int y = 1; y < TY; ++y)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[j] += red[y * TX + tx][j]; b[j] += red[y * TX + tx][4 + j]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&sums[c + j], a[j]);
+      atomicAdd(&sums[C + c + j], b[j]);
+    }
   }
 }
 
@@ -313,46 +348,69 @@ template <typename TA>
 __global__ void __launch_bounds__(256)
 bn_bwd_sums_kernel(const float* __restrict__ dout, const TA* __restrict__ out,
                    const TA* __restrict__ t, const float* __restrict__ mean,
-                   const float* __restrict__ rstd, int M, int C, int rows_per_block,
+                   const float* __restrict__ rstd, int M, int C, int rows_per_block, int TX,
                    float* __restrict__ dyb, double* __restrict__ sums) {
-  __shared__ double s1[8][33], s2[8][33];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
+  __shared__ double red[256][8];
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = 256 / TX;
+  const int c = (blockIdx.x * TX + tx) * 4;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
-  double a = 0.0, b = 0.0;
+  double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
   if (c < C) {
-    const float mu = mean[c], rs = rstd[c];
-    int r = r0 + ry;
-    for (; r + 8 < r1; r += 16) {  // two rows per iteration: six independent loads in flight
-      const size_t i0 = static_cast<size_t>(r) * C + c, i1 = static_cast<size_t>(r + 8) * C + c;
-      float d0 = dout[i0], d1 = dout[i1];
-      const float t0 = get(t + i0), t1 = get(t + i1);
-      if (out != nullptr) {
-        const float o0 = get(out + i0), o1 = get(out + i1);
-        if (!(o0 > 0.f)) d0 = 0.f;
-        if (!(o1 > 0.f)) d1 = 0.f;
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    int r = r0 + ty;
+    for (; r + TY < r1; r += 2 * TY) {  // two rows per iteration: six independent vector loads
+      float4 d[2], tv[2], ov[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const size_t i = static_cast<size_t>(r + u * TY) * C + c;
+        d[u] = *reinterpret_cast<const float4*>(dout + i);
+        tv[u] = ld4(t + i);
+        ov[u] = out != nullptr ? ld4(out + i) : make_float4(1.f, 1.f, 1.f, 1.f);
       }
-      dyb[i0] = d0;
-      dyb[i1] = d1;
-      a += static_cast<double>(d0) + d1;
-      b += static_cast<double>(d0) * ((t0 - mu) * rs) + static_cast<double>(d1) * ((t1 - mu) * rs);
+      float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!(ov[u].x > 0.f)) d[u].x = 0.f;
+        if (!(ov[u].y > 0.f)) d[u].y = 0.f;
+        if (!(ov[u].z > 0.f)) d[u].z = 0.f;
+        if (!(ov[u].w > 0.f)) d[u].w = 0.f;
+        *reinterpret_cast<float4*>(dyb + static_cast<size_t>(r + u * TY) * C + c) = d[u];
+        s1.x += d[u].x; s1.y += d[u].y; s1.z += d[u].z; s1.w += d[u].w;
+        s2.x = fmaf(d[u].x, (tv[u].x - mu.x) * rs.x, s2.x); s2.y = fmaf(d[u].y, (tv[u].y - mu.y) * rs.y, s2.y);
+        s2.z = fmaf(d[u].z, (tv[u].z - mu.z) * rs.z, s2.z); s2.w = fmaf(d[u].w, (tv[u].w - mu.w) * rs.w, s2.w);
+      }
+      a[0] += s1.x; a[1] += s1.y; a[2] += s1.z; a[3] += s1.w;
+      b[0] += s2.x; b[1] += s2.y; b[2] += s2.z; b[3] += s2.w;
     }
-    for (; r < r1; r += 8) {
+    for (; r < r1; r += TY) {
       const size_t i = static_cast<size_t>(r) * C + c;
-      float d = dout[i];
-      if (out != nullptr && !(get(out + i) > 0.f)) d = 0.f;
-      dyb[i] = d;
-      a += d;
-      b += static_cast<double>(d) * ((get(t + i) - mu) * rs);
+      float4 d = *reinterpret_cast<const float4*>(dout + i);
+      const float4 tv = ld4(t + i);
+      if (out != nullptr) {
+        const float4 ov = ld4(out + i);
+        if (!(ov.x > 0.f)) d.x = 0.f;
+        if (!(ov.y > 0.f)) d.y = 0.f;
+        if (!(ov.z > 0.f)) d.z = 0.f;
+        if (!(ov.w > 0.f)) d.w = 0.f;
+      }
+      *reinterpret_cast<float4*>(dyb + i) = d;
+      a[0] += d.x; a[1] += d.y; a[2] += d.z; a[3] += d.w;
+      b[0] += static_cast<double>(d.x) * ((tv.x - mu.x) * rs.x); b[1] += static_cast<double>(d.y) * ((tv.y - mu.y) * rs.y);
+      b[2] += static_cast<double>(d.z) * ((tv.z - mu.z) * rs.z); b[3] += static_cast<double>(d.w) * ((tv.w - mu.w) * rs.w);
     }
   }
-  s1[ry][cx] = a;
-  s2[ry][cx] = b;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[threadIdx.x][j] = a[j]; red[threadIdx.x][4 + j] = b[j]; }
   __syncthreads();
-  if (ry == 0 && c < C) {
-    for (int j = 1; j < 8; ++j) { a += s1[j][cx]; b += s2[j][cx]; }
-    atomicAdd(&sums[c], a);
-    atomicAdd(&sums[C + c], b);
+  if (ty == 0 && c < C) {
+    for (int y = 1; y < TY; ++y)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[j] += red[y * TX + tx][j]; b[j] += red[y * TX + tx][4 + j]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&sums[c + j], a[j]);
+      atomicAdd(&sums[C + c + j], b[j]);
+    }
   }
 }
 
@@ -364,19 +422,32 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dyb, const TA* __r
                                     const float* __restrict__ gamma, const double* __restrict__ sums,
                                     int M, int C, TD* __restrict__ dt, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta) {
-  const size_t n = static_cast<size_t>(M) * C;
+  const size_t n4 = static_cast<size_t>(M) * C / 4;
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       dbeta[c] += static_cast<float>(sums[c]);
       dgamma[c] += static_cast<float>(sums[C + c]);
     }
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+  const double invM = 1.0 / M;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    const float rs = rstd[c];
-    const float xh = (get(t + i) - mean[c]) * rs;
-    const float m1 = static_cast<float>(sums[c] / M), m2 = static_cast<float>(sums[C + c] / M);
-    put(dt + i, gamma[c] * rs * (dyb[i] - m1 - xh * m2));
+    const int c = static_cast<int>((i * 4) % C);
+    const float4 d = *reinterpret_cast<const float4*>(dyb + 4 * i);
+    const float4 tv = ld4(t + 4 * i);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const double2 sa = *reinterpret_cast<const double2*>(sums + c), sb = *reinterpret_cast<const double2*>(sums + c + 2);
+    const double2 qa = *reinterpret_cast<const double2*>(sums + C + c), qb = *reinterpret_cast<const double2*>(sums + C + c + 2);
+    const float m1[4] = {static_cast<float>(sa.x * invM), static_cast<float>(sa.y * invM),
+                         static_cast<float>(sb.x * invM), static_cast<float>(sb.y * invM)};
+    const float m2[4] = {static_cast<float>(qa.x * invM), static_cast<float>(qa.y * invM),
+                         static_cast<float>(qb.x * invM), static_cast<float>(qb.y * invM)};
+    float4 o;
+    o.x = g.x * rs.x * (d.x - m1[0] - (tv.x - mu.x) * rs.x * m2[0]);
+    o.y = g.y * rs.y * (d.y - m1[1] - (tv.y - mu.y) * rs.y * m2[1]);
+    o.z = g.z * rs.z * (d.z - m1[2] - (tv.z - mu.z) * rs.z * m2[2]);
+    o.w = g.w * rs.w * (d.w - m1[3] - (tv.w - mu.w) * rs.w * m2[3]);
+    st4(dt + 4 * i, o);
   }
 }
 
@@ -683,9 +754,11 @@ int conv_bn_fwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
   }
   if (x.training) {
     if (cudaMemsetAsync(x.w.sums, 0, 2 * l.co * sizeof(double), x.st) != cudaSuccess) return MMU_ERR_CUDA;
-    const int gy = (M + 511) / 512;
-    if (x.act16) bn_sums_kernel<bf16_t><<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(as16(o.t), M, l.co, 512, x.w.sums);
-    else bn_sums_kernel<float><<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(o.t, M, l.co, 512, x.w.sums);
+    const ColGeo cg = col_geo(l.co);
+    const int rpb = stat_rows_per_block(M, cg);
+    const int gy = (M + rpb - 1) / rpb;
+    if (x.act16) bn_sums_kernel<bf16_t><<<dim3(cg.gx, gy), 256, 0, x.st>>>(as16(o.t), M, l.co, rpb, cg.tx, x.w.sums);
+    else bn_sums_kernel<float><<<dim3(cg.gx, gy), 256, 0, x.st>>>(o.t, M, l.co, rpb, cg.tx, x.w.sums);
     RN_CHECK_LAUNCH();
     bn_finalize_kernel<<<(l.co + 127) / 128, 128, 0, x.st>>>(x.w.sums, M, l.co, 0.1f, o.mean, o.rstd,
                                                               x.stats + l.stat, x.stats + l.stat + (l.co + 63) / 64 * 64);
@@ -714,13 +787,15 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
   const int M = static_cast<int>(rows_of(x.c, l.hout)), K = l.ci * l.k * l.k;
   if (cudaMemsetAsync(x.w.sums, 0, 2 * l.co * sizeof(double), x.st) != cudaSuccess) return MMU_ERR_CUDA;
   float* dyb = dres_out != nullptr ? dres_out : x.w.dyb;
-  const int gy = (M + 511) / 512;
+  const ColGeo cg = col_geo(l.co);
+  const int rpb = stat_rows_per_block(M, cg);
+  const int gy = (M + rpb - 1) / rpb;
   if (x.act16)
-    bn_bwd_sums_kernel<bf16_t><<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(
-        dout, relu ? as16(o.out) : nullptr, as16(o.t), o.mean, o.rstd, M, l.co, 512, dyb, x.w.sums);
+    bn_bwd_sums_kernel<bf16_t><<<dim3(cg.gx, gy), 256, 0, x.st>>>(
+        dout, relu ? as16(o.out) : nullptr, as16(o.t), o.mean, o.rstd, M, l.co, rpb, cg.tx, dyb, x.w.sums);
   else
-    bn_bwd_sums_kernel<float><<<dim3((l.co + 31) / 32, gy), 256, 0, x.st>>>(
-        dout, relu ? o.out : nullptr, o.t, o.mean, o.rstd, M, l.co, 512, dyb, x.w.sums);
+    bn_bwd_sums_kernel<float><<<dim3(cg.gx, gy), 256, 0, x.st>>>(
+        dout, relu ? o.out : nullptr, o.t, o.mean, o.rstd, M, l.co, rpb, cg.tx, dyb, x.w.sums);
   RN_CHECK_LAUNCH();
   const size_t n = static_cast<size_t>(M) * l.co;
   const size_t ncols = static_cast<size_t>(M) * K;
@@ -733,10 +808,10 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
     __nv_bfloat16* dt = reinterpret_cast<__nv_bfloat16*>(x.w.dt);
     __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(x.w.cols);
     if (x.act16)
-      bn_bwd_apply_kernel<bf16_t, bf16_t><<<blocks_for(n, 256), 256, 0, x.st>>>(
+      bn_bwd_apply_kernel<bf16_t, bf16_t><<<blocks_for(n / 4, 256), 256, 0, x.st>>>(
           dyb, as16(o.t), o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
     else
-      bn_bwd_apply_kernel<bf16_t, float><<<blocks_for(n, 256), 256, 0, x.st>>>(
+      bn_bwd_apply_kernel<bf16_t, float><<<blocks_for(n / 4, 256), 256, 0, x.st>>>(
           dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
     RN_CHECK_LAUNCH();
     im2col_nchw_pad_bf16x8_kernel<<<blocks_for(static_cast<size_t>(M) * (Kp / 8), 256), 256, 0, x.st>>>(
@@ -762,10 +837,10 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
     __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(x.w.cols);
     __nv_bfloat16* dcols = reinterpret_cast<__nv_bfloat16*>(x.w.dcols);
     if (x.act16)
-      bn_bwd_apply_kernel<bf16_t, bf16_t><<<blocks_for(n, 256), 256, 0, x.st>>>(
+      bn_bwd_apply_kernel<bf16_t, bf16_t><<<blocks_for(n / 4, 256), 256, 0, x.st>>>(
           dyb, as16(o.t), o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
     else
-      bn_bwd_apply_kernel<bf16_t, float><<<blocks_for(n, 256), 256, 0, x.st>>>(
+      bn_bwd_apply_kernel<bf16_t, float><<<blocks_for(n / 4, 256), 256, 0, x.st>>>(
           dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, dt, x.grads + l.g, x.grads + l.b);
     RN_CHECK_LAUNCH();
     const __nv_bfloat16* wcols = nullptr;
@@ -806,7 +881,7 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
     return 0;
   }
   if (x.act16) return MMU_ERR_SHAPE;
-  bn_bwd_apply_kernel<float, float><<<blocks_for(n, 256), 256, 0, x.st>>>(
+  bn_bwd_apply_kernel<float, float><<<blocks_for(n / 4, 256), 256, 0, x.st>>>(
       dyb, o.t, o.mean, o.rstd, x.params + l.g, x.w.sums, M, l.co, x.w.dt, x.grads + l.g, x.grads + l.b);
   RN_CHECK_LAUNCH();
   // weight gradient: dW[co, K] += dt^T cols   (cols recomputed: 9x cheaper than keeping them)

@@ -11,7 +11,7 @@ import mmu_b200 as mmu
 ie = importlib.import_module("multi-modal-uncertainty_b200.src.image_encoder")
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
-ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--precision", default="bf16")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -23,7 +23,7 @@ r = torch.randn(a.batch, 3, 2048, device=dev)
 
 
 def timed(fn, n):
-    for _ in range(2):
+    for _ in range(3):
         fn()
     torch.cuda.synchronize()
     l0 = mmu._lib.lib.mmu_launch_count()
