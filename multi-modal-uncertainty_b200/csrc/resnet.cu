@@ -181,6 +181,92 @@ __global__ void unpad_add_kernel(const float* __restrict__ dwp, int co, int K, i
   dw[i] += dwp[(i / K) * Kp + i % K];
 }
 
+// ---- tap-major columns: cols[row][tap * Ci + ci].  A thread moves 8 consecutive channels of one
+// tap: one 16-byte load from the bf16 NHWC input, one 16-byte store (both fully coalesced).
+__global__ void __launch_bounds__(256)
+im2col_tm_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int Ci, int k, int stride, int pad,
+                 int Ho, int Wo, __nv_bfloat16* __restrict__ cols) {
+  const int kk = k * k, C8 = Ci >> 3;
+  const size_t K = static_cast<size_t>(Ci) * kk;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * kk * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    const int tap = static_cast<int>((i / C8) % kk);
+    const size_t row = i / (static_cast<size_t>(C8) * kk);
+    const int xo = static_cast<int>(row % Wo), yo = static_cast<int>((row / Wo) % Ho);
+    const int b = static_cast<int>(row / (static_cast<size_t>(Wo) * Ho));
+    const int ky = tap / k, kx = tap - ky * k;
+    const int y = yo * stride + ky - pad, x = xo * stride + kx - pad;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H && x >= 0 && x < W)
+      v = *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + y) * W + x) * Ci + c8 * 8);
+    *reinterpret_cast<uint4*>(cols + row * K + static_cast<size_t>(tap) * Ci + c8 * 8) = v;
+  }
+}
+// din[pixel][ci .. ci+8) (+)= sum over the taps that reach the pixel of dcols[row][tap * Ci + ci ..]
+__global__ void __launch_bounds__(256)
+col2im_tm_kernel(const __nv_bfloat16* __restrict__ dcols, int B, int H, int W, int Ci, int k, int stride,
+                 int pad, int Ho, int Wo, float* __restrict__ dx, int accumulate) {
+  const int kk = k * k, C8 = Ci >> 3;
+  const size_t K = static_cast<size_t>(Ci) * kk;
+  const size_t total = static_cast<size_t>(B) * H * W * C8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    const size_t pix = i / C8;
+    const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int ky = 0; ky < k; ++ky) {
+      const int ty = y + pad - ky;
+      if (ty < 0 || ty % stride != 0) continue;
+      const int yo = ty / stride;
+      if (yo >= Ho) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int tx = x + pad - kx;
+        if (tx < 0 || tx % stride != 0) continue;
+        const int xo = tx / stride;
+        if (xo >= Wo) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(
+            dcols + ((static_cast<size_t>(b) * Ho + yo) * Wo + xo) * K + static_cast<size_t>(ky * k + kx) * Ci + c8 * 8);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[2 * j] += __uint_as_float(w[j] << 16);
+          acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+        }
+      }
+    }
+    float* o = dx + pix * Ci + c8 * 8;
+    float4 lo = make_float4(acc[0], acc[1], acc[2], acc[3]), hi = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    if (accumulate) {
+      const float4 a = *reinterpret_cast<const float4*>(o), c = *reinterpret_cast<const float4*>(o + 4);
+      lo.x += a.x; lo.y += a.y; lo.z += a.z; lo.w += a.w;
+      hi.x += c.x; hi.y += c.y; hi.z += c.z; hi.w += c.w;
+    }
+    *reinterpret_cast<float4*>(o) = lo;
+    *reinterpret_cast<float4*>(o + 4) = hi;
+  }
+}
+// wperm[co][tap * Ci + ci] = bf16(w[(co * Ci + ci) * kk + tap])   (OIHW -> tap-major rows)
+__global__ void permute_weights_kernel(const float* __restrict__ w, int co, int Ci, int kk,
+                                       __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = Ci * kk;
+  if (i >= co * K) return;
+  const int o = i / K, r = i % K, tap = r / Ci, ci = r % Ci;
+  out[i] = __float2bfloat16_rn(w[(static_cast<size_t>(o) * Ci + ci) * kk + tap]);
+}
+// dW[(co * Ci + ci) * kk + tap] += dwp[co][tap * Ci + ci]
+__global__ void unpermute_add_kernel(const float* __restrict__ dwp, int co, int Ci, int kk, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = Ci * kk;
+  if (i >= co * K) return;
+  const int o = i / K, r = i % K, ci = r / kk, tap = r % kk;
+  dw[i] += dwp[static_cast<size_t>(o) * K + static_cast<size_t>(tap) * Ci + ci];
+}
+
 // dx(b, y, x, ci) (+)= sum over taps of dcols[(b, yo, xo)][ci*k*k + tap] with y = yo*stride+ky-pad
 template <typename TC>
 __global__ void col2im_kernel(const TC* __restrict__ dcols, int B, int H, int W, int Ci, int k,
@@ -493,6 +579,7 @@ struct ConvBn {
   int ci, co, k, stride, pad, hin, hout;
   long long w, g, b;  // offsets into the flat parameter buffer: conv weight, BN gain, BN bias
   long long stat;     // offset into the flat statistics buffer: running_mean[co] | running_var[co]
+  long long wp = -1;  // offset (elements) of this layer's tap-major bf16 weight copy, or -1
 };
 struct Net {
   ConvBn stem;
@@ -600,6 +687,11 @@ struct Ws {
   // copy of the weights and an fp32 [co x Kp] scratch for the weight gradient.  Null: disabled.
   void* pad_w;
   float* pad_dw;
+  // tap-major 3x3 convolutions (image encoder, bf16 activations): columns ordered (tap, ci) so that
+  // im2col / col2im move 16-byte vectors; the weights are re-ordered into `wperm` (bf16, all 3x3
+  // layers) by the forward, the weight gradient goes through the fp32 scratch `dwperm`.
+  void* wperm;
+  float* dwperm;
   long long bytes;
 };
 struct Bump {
@@ -650,6 +742,8 @@ void carve(const ResNetConfig& c, const Net& n, int training, void* base, Ws* w)
   }
   w->pad_w = nullptr;
   w->pad_dw = nullptr;
+  w->wperm = nullptr;
+  w->dwperm = nullptr;
   w->bytes = b.off;
 }
 
@@ -685,7 +779,12 @@ bool use_tc(const Ctx& x, const ConvBn& l) { return x.shadow != nullptr && (l.ci
 bool use_tc_padded(const Ctx& x, const ConvBn& l, int in_nchw) {
   return x.shadow != nullptr && (l.ci * l.k * l.k) % 8 != 0 && in_nchw && x.w.pad_w != nullptr;
 }
+// tap-major layer: 3x3 (or larger) convolution with bf16 activations and a re-ordered weight copy
+bool use_tm(const Ctx& x, const ConvBn& l) {
+  return x.act16 && l.k > 1 && l.wp >= 0 && x.w.wperm != nullptr && l.ci % 8 == 0;
+}
 const __nv_bfloat16* wbf(const Ctx& x, const ConvBn& l) {
+  if (use_tm(x, l)) return static_cast<const __nv_bfloat16*>(x.w.wperm) + l.wp;
   return static_cast<const __nv_bfloat16*>(x.shadow) + l.w;
 }
 
@@ -703,6 +802,12 @@ int tc_columns(const Ctx& x, const ConvBn& l, const float* in, int in_nchw, __nv
       return 0;
     }
     return cast_f32_to_bf16(in, cols, M * K, x.st);
+  }
+  if (!in_nchw && use_tm(x, l)) {
+    im2col_tm_kernel<<<blocks_for(M * (K / 8), 256), 256, 0, x.st>>>(
+        as16(in), x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
+    RN_CHECK_LAUNCH();
+    return 0;
   }
   if (!in_nchw && K % 8 == 0) {
     if (x.act16)
@@ -740,6 +845,11 @@ int conv_bn_fwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
     e.out_bf16 = x.act16;
     RN_TRY(gemm_bf16_launch(cols, Kp, wp, Kp, pp, e, x.st));
   } else if (use_tc(x, l)) {
+    if (use_tm(x, l)) {  // tap-major weight copy (kept for the backward of the same step)
+      permute_weights_kernel<<<(l.co * K + 255) / 256, 256, 0, x.st>>>(
+          x.params + l.w, l.co, l.ci, l.k * l.k, static_cast<__nv_bfloat16*>(x.w.wperm) + l.wp);
+      RN_CHECK_LAUNCH();
+    }
     const __nv_bfloat16* cols = nullptr;
     RN_TRY(tc_columns(x, l, in, in_nchw, reinterpret_cast<__nv_bfloat16*>(x.w.cols), &cols));
     GemmEpilogue e = store_epi(o.t, l.co, nullptr);
@@ -862,7 +972,17 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
       if (eff > best + 0.02) { best = eff; splits = sp; }
     }
     GemmProblem p{l.co, K, M, 1, 1, splits};
-    RN_TRY(gemm_bf16_launch(dt, l.co, wcols, K, p, wg, x.st));
+    if (use_tm(x, l)) {  // dW in tap-major order into the scratch, then += into the OIHW gradient
+      if (cudaMemsetAsync(x.w.dwperm, 0, static_cast<size_t>(l.co) * K * 4, x.st) != cudaSuccess) return MMU_ERR_CUDA;
+      GemmEpilogue wgp = wg;
+      wgp.out = x.w.dwperm;
+      RN_TRY(gemm_bf16_launch(dt, l.co, wcols, K, p, wgp, x.st));
+      unpermute_add_kernel<<<(l.co * K + 255) / 256, 256, 0, x.st>>>(x.w.dwperm, l.co, l.ci, l.k * l.k,
+                                                                      x.grads + l.w);
+      RN_CHECK_LAUNCH();
+    } else {
+      RN_TRY(gemm_bf16_launch(dt, l.co, wcols, K, p, wg, x.st));
+    }
     if (din != nullptr && l.k == 1 && l.stride == 1) {
       // 1x1 stride-1: the input gradient IS dt W -- written (or TMA-reduce-added) straight to din
       GemmProblem q{M, K, l.co, 0, 1, 1};
@@ -874,8 +994,12 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
       GemmEpilogue e = store_epi(reinterpret_cast<float*>(dcols), K, nullptr);
       e.out_bf16 = 1;
       RN_TRY(gemm_bf16_launch(dt, l.co, wbf(x, l), K, q, e, x.st));
-      col2im_kernel<__nv_bfloat16><<<blocks_for(nin, 256), 256, 0, x.st>>>(
-          dcols, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, din, din_accumulate);
+      if (use_tm(x, l))
+        col2im_tm_kernel<<<blocks_for(nin / 8, 256), 256, 0, x.st>>>(
+            dcols, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, din, din_accumulate);
+      else
+        col2im_kernel<__nv_bfloat16><<<blocks_for(nin, 256), 256, 0, x.st>>>(
+            dcols, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, din, din_accumulate);
       RN_CHECK_LAUNCH();
     }
     return 0;
@@ -1041,6 +1165,8 @@ struct IeNet {
   int n_conv;
   IeBlock block[IE_MAX_BLOCKS];
   int n_block;
+  long long n_wperm;  // elements of the tap-major weight copies (all 3x3 layers)
+  long long max_wk;   // largest co * K among them (weight-gradient scratch)
   int h_pool_in;   // spatial size after the stem's max pool
   int h_out;       // spatial size of the layer4 output
   int c_out;       // 2048
@@ -1114,6 +1240,17 @@ int ie_build(const ImgEncConfig& c, IeNet* net, ParamEntry* ptab, int pmax, Para
   }
   net->n_conv = nc;
   net->n_block = blk;
+  net->n_wperm = 0;
+  net->max_wk = 0;
+  for (int i = 1; i < nc; ++i) {
+    ConvBn& l = net->conv[i];
+    if (l.k > 1) {
+      const long long wk = static_cast<long long>(l.co) * l.ci * l.k * l.k;
+      l.wp = net->n_wperm;
+      net->n_wperm += (wk + 63) / 64 * 64;
+      if (wk > net->max_wk) net->max_wk = wk;
+    }
+  }
   net->h_out = h;
   net->c_out = inpl;
   // (an adaptive pool grid larger than the map is legal: cells then repeat pixels, as in torch)
@@ -1168,6 +1305,8 @@ void ie_carve(const ImgEncConfig& c, const IeNet& n, int training, void* base, I
   }
   w->shared.cols = b.take<float>(max_cols * 4);
   w->shared.sums = b.take<double>(2LL * max_co * 8);
+  w->shared.wperm = b.take<void>(n.n_wperm * 2);
+  w->shared.dwperm = training ? b.take<float>(n.max_wk * 4) : nullptr;
   if (training) {
     w->shared.dcols = b.take<float>(max_cols * 4);
     w->shared.dyb = b.take<float>(max_act * 4);
