@@ -196,19 +196,35 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
       const int q0 = (tile0 + qt) * BQ;
       ptx::mbar_wait(s_full, qt & 1);
       ptx::tc_fence_after();
+      // Passes 1 and 2 stream this half's columns 16 at a time through two register buffers: the
+      // tcgen05.ld of step i + 1 is in flight while step i is reduced (TMEM load latency, not
+      // arithmetic, bounded these passes).
+      const int n16 = n_mine * (CH / 16);
+      const uint32_t tcol0 = trow + c_begin * CH;
+      const float* ms0 = mask_s + c_begin * CH;
+      uint32_t ra[16], rb[16];
+      auto stream16 = [&](auto&& body) {
+        if (n16 > 0) ptx::tmem_ld_32x16(tcol0, ra);
+        for (int i = 0; i < n16; i += 2) {
+          ptx::tmem_ld_wait();
+          if (i + 1 < n16) ptx::tmem_ld_32x16(tcol0 + (i + 1) * 16, rb);
+          body(ra, ms0 + i * 16);
+          if (i + 1 < n16) {
+            ptx::tmem_ld_wait();
+            if (i + 2 < n16) ptx::tmem_ld_32x16(tcol0 + (i + 2) * 16, ra);
+            body(rb, ms0 + (i + 1) * 16);
+          }
+        }
+      };
       // pass 1: row maximum over this half's columns
       float mx = -INFINITY;
-      for (int c = c_begin; c < c_end; ++c) {
+      {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        stream16([&](const uint32_t (&v)[16], const float* ms) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
-          ptx::tmem_ld_wait();
-          const float* ms = mask_s + c * CH + j * 32;
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], fmaf(__uint_as_float(r[i]), sc, ms[i]));
-          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-        }
+          for (int i = 0; i < 16; ++i) m4[i & 3] = fmaxf(m4[i & 3], fmaf(__uint_as_float(v[i]), sc, ms[i]));
+        });
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
       xch[hh * BQ + row] = make_float2(mx, 0.f);
       nbar(3 + q, 64);
@@ -216,18 +232,12 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
       nbar(3 + q, 64);
       float sum = 0.f;
       if (SAVE_P) {  // pass 2: row sum, so that the NORMALISED probabilities can be stored
-        for (int c = c_begin; c < c_end; ++c) {
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        stream16([&](const uint32_t (&v)[16], const float* ms) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
-            ptx::tmem_ld_wait();
-            const float* ms = mask_s + c * CH + j * 32;
-            float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < 32; ++i) s4[i & 3] += ex2f(fmaf(__uint_as_float(r[i]), sc, ms[i]) - mx);
-            sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-          }
-        }
+          for (int i = 0; i < 16; ++i) s4[i & 3] += ex2f(fmaf(__uint_as_float(v[i]), sc, ms[i]) - mx);
+        });
+        sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         xch[hh * BQ + row] = make_float2(mx, sum);
         nbar(3 + q, 64);
         sum += xch[(hh ^ 1) * BQ + row].y;
@@ -250,27 +260,39 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
             nbar(1 + hh, 128);
           }
         }
+        {  // four 16-column steps, the next step's TMEM load in flight behind the current one
+          auto emit = [&](const uint32_t (&tv)[16], int step) {
+            const float* ms = mask_s + c * CH + step * 16;
+            float v[16];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          ptx::tmem_ld_32x32(trow + c * CH + j * 32, r);
+            for (int t = 0; t < 16; ++t) v[t] = ex2f(fmaf(__uint_as_float(tv[t]), sc, ms[t]) - mx) * inv;
+            if (!SAVE_P) {
+              float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int t = 0; t < 16; ++t) s4[t & 3] += v[t];
+              sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint32_t piece = static_cast<uint32_t>(step * 2 + k);
+              ptx::sts_v4u(pbuf + prow + ((piece ^ sw) << 4), pack2(v[8 * k], v[8 * k + 1]),
+                           pack2(v[8 * k + 2], v[8 * k + 3]), pack2(v[8 * k + 4], v[8 * k + 5]),
+                           pack2(v[8 * k + 6], v[8 * k + 7]));
+            }
+          };
+          const uint32_t tc = trow + c * CH;
+          ptx::tmem_ld_32x16(tc, ra);
           ptx::tmem_ld_wait();
-          const float* ms = mask_s + c * CH + j * 32;
-          float v[32];
-#pragma unroll
-          for (int t = 0; t < 32; ++t) v[t] = ex2f(fmaf(__uint_as_float(r[t]), sc, ms[t]) - mx) * inv;
-          if (!SAVE_P) {
-            float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int t = 0; t < 32; ++t) s4[t & 3] += v[t];
-            sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t piece = static_cast<uint32_t>(j * 4 + k);
-            ptx::sts_v4u(pbuf + prow + ((piece ^ sw) << 4), pack2(v[8 * k], v[8 * k + 1]),
-                         pack2(v[8 * k + 2], v[8 * k + 3]), pack2(v[8 * k + 4], v[8 * k + 5]),
-                         pack2(v[8 * k + 6], v[8 * k + 7]));
-          }
+          ptx::tmem_ld_32x16(tc + 16, rb);
+          emit(ra, 0);
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld_32x16(tc + 32, ra);
+          emit(rb, 1);
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld_32x16(tc + 48, rb);
+          emit(ra, 2);
+          ptx::tmem_ld_wait();
+          emit(rb, 3);
         }
         if (c == 0) ptx::tc_fence_before();  // columns 0..63 are drained before MMA2 overwrites them
         ptx::fence_proxy_async();
