@@ -474,3 +474,87 @@ def test_image_encoder_bf16_gradients(mmu, golden, name):
             continue
         bound = 0.95 if k.startswith("model.7") else 0.85
         assert cos > bound and 0.7 < ratio < 1.4, (k, cos, ratio)
+
+
+@pytest.mark.parametrize("B,S_txt,n_img,C", [(1, 1, 1, 2), (2, 9, 7, 5), (5, 40, 2, 3), (2, 64, 9, 2)])
+def test_fp32_edge_shapes_vs_oracle(mmu, B, S_txt, n_img, C):
+    """Edge shapes against the CPU oracle (fp32 path, 1e-3): a single sample with a single text token,
+    every supported num_image_embeds family, more than two classes, fully padded tails, and the
+    forward_control / img_only / txt_only index lists on each."""
+    from oracle import mmbt as O
+    cfg = dict(B=B, S_txt=S_txt, n_img=n_img, d_img=32, D=64, n_head=2, n_layers=2, d_ff=128, vocab=50,
+               max_pos=max(S_txt, n_img + 2) + 3, n_types=2, C=C, cls_id=3, sep_id=4)
+    g = torch.Generator().manual_seed(100 * B + S_txt)
+    m = mmu.MultimodalBertClf(make_args(cfg, "fp32"))
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.1 if p.dim() == 1 else 0.15))
+            if p.dim() == 1 and p.numel() == cfg["D"]:
+                p.add_(0.5)
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    txt = torch.randint(5, cfg["vocab"], (B, S_txt), generator=g)
+    lens = torch.randint(1, S_txt + 1, (B,), generator=g)
+    mask = (torch.arange(S_txt)[None] < lens[:, None]).long()
+    txt, segment = txt * mask, mask.clone()
+    tok = torch.randn(B, n_img, 32, generator=g)
+    y = torch.randint(0, C, (B,), generator=g)
+    Pd = {k: (v.double() if v.is_floating_point() else v) for k, v in P.items()}
+    ref_logits, ref_loss, ref_grads, ref_dtok = O.loss_and_grads(Pd, txt, mask, segment, tok.double(), y, cfg)
+    m.cuda().train()
+    m.zero_grad()
+    t = tok.cuda().requires_grad_(True)
+    logits = m(txt.cuda(), mask.cuda(), segment.cuda(), t)
+    loss = m.compute_loss(logits, y.cuda())
+    loss.backward()
+    assert rel(logits.detach().cpu(), ref_logits) < 1e-3
+    assert abs(float(loss.detach()) - float(ref_loss)) < 1e-3 * abs(float(ref_loss))
+    assert torch.equal(logits.detach().cpu().argmax(-1), ref_logits.argmax(-1))
+    assert rel(t.grad.cpu(), ref_dtok) < 1e-3
+    gmax = max(float(v.abs().max()) for v in ref_grads.values())
+    for k, p in m.named_parameters():
+        if float(ref_grads[k].abs().max()) < 1e-5 * gmax:
+            continue
+        assert rel(p.grad.cpu(), ref_grads[k]) < 1e-3, (k, rel(p.grad.cpu(), ref_grads[k]))
+    m.eval()
+    total = S_txt + n_img + 2
+    x = [v.cuda() for v in (txt, mask, segment, tok)]
+    with torch.no_grad():
+        for mode, fn in (("img_only", m.forward_img_only), ("txt_only", m.forward_txt_only)):
+            ref = O.forward(Pd, txt, mask, segment, tok.double(), cfg, O.mode_indices(mode, n_img, S_txt))
+            assert rel(fn(*x).cpu(), ref) < 1e-3, mode
+        torch.manual_seed(9)
+        ind = O.control_indices(total, n_img + 1)
+        torch.manual_seed(9)
+        out = m.forward_control(*x, "image").cpu()
+        assert rel(out, O.forward(Pd, txt, mask, segment, tok.double(), cfg, ind)) < 1e-3
+
+
+@pytest.mark.parametrize("n_img,pool", [(1, "avg"), (2, "max"), (5, "avg"), (6, "max"), (8, "avg"), (9, "max"), (7, "avg")])
+def test_image_encoder_pool_grids_vs_oracle(mmu, n_img, pool):
+    """Every num_image_embeds grid of src/mmbt.py:28-37 (incl. grids larger than the 2x2 final map),
+    avg and max pooling, forward and the gradient of the pooled tokens w.r.t. the last BatchNorm, fp32
+    engine against the oracle."""
+    import importlib
+    from oracle import image_encoder as IE
+    ie = importlib.import_module("multi-modal-uncertainty_b200.src.image_encoder")
+    args = types.SimpleNamespace(num_image_embeds=n_img, img_embed_pool_type=pool, precision="fp32",
+                                 img_encoder_layers=(1, 1, 1, 1), img_encoder_width=8)
+    enc = ie.ImageEncoder(args)
+    sd = det_image_encoder_state({k: tuple(v.shape) for k, v in enc.state_dict().items()}, 7)
+    enc.load_state_dict(sd, strict=True)
+    enc.cuda().eval()
+    g = torch.Generator().manual_seed(n_img)
+    x = torch.randn(2, 3, 96, 96, generator=g)
+    P = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    ref = IE.image_encoder_forward(P, x.double(), (1, 1, 1, 1), ie.POOL_GRID[n_img], pool != "avg", False)
+    with torch.no_grad():
+        tok = enc(x.cuda()).cpu()
+    assert tok.shape == (2, n_img, 2048) and rel(tok, ref) < 1e-3
+    enc.train()
+    enc.zero_grad()
+    r = torch.randn(2, n_img, 2048, generator=g)
+    (enc(x.cuda()) * r.cuda()).sum().backward()
+    _, grads, _ = IE.tokens_and_grads(P, x.double(), r.double(), (1, 1, 1, 1), ie.POOL_GRID[n_img], pool != "avg")
+    for k in ("model.7.0.bn3.weight", "model.7.0.bn3.bias", "model.7.0.conv3.weight"):
+        got = dict(enc.named_parameters())[k].grad.cpu()
+        assert rel(got, grads[k]) < 5e-3, (k, rel(got, grads[k]))
