@@ -167,6 +167,9 @@ class ImageEncoder(nn.Module):
                                                 ws.numel(), dtokens.data_ptr(),
                                                 self._flat_grad.data_ptr(), _lib.stream_ptr()),
                    "mmu_imgenc_backward")
+        sync = getattr(self, "_flat_sync", None)
+        if sync is not None:
+            sync.launch(self)
 
     def forward(self, x):
         anchor = next((p for p, _ in self._grad_views if p.requires_grad), None)

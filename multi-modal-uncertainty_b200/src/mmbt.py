@@ -282,6 +282,9 @@ class MultimodalBertClf(nn.Module):
                                               ws.data_ptr(), ws.numel(), dlogits.data_ptr(),
                                               self._flat_grad.data_ptr(), _lib.stream_ptr()),
                    "mmu_mmbt_backward")
+        sync = getattr(self, "_flat_sync", None)
+        if sync is not None:
+            sync.launch(self)  # gradient all-reduce overlaps the image encoder's backward
         return dimg
 
     # -------------------------------------------------------------- reference protocol

@@ -108,9 +108,11 @@ class FlatGradSync:
     kernel.  BatchNorm batch statistics stay rank-local, as under ``DistributedDataParallel``
     without SyncBN.  ``attach(model, optimizer)`` wires it up."""
 
-    def __init__(self, owners, group=None):
-        self.owners, self.group = list(owners), group
+    def __init__(self, owners, group=None, overlap=False):
+        self.owners, self.group, self.overlap = list(owners), group, overlap
         self.rank, self.world = world(group)
+        self._pending = {}
+        self._comm = None
         for o in self.owners:
             broadcast_flat(o._flat, 0, group)
             stats = getattr(o, "_stats", None)
@@ -118,15 +120,40 @@ class FlatGradSync:
                 broadcast_flat(stats, 0, group)
             if hasattr(o, "invalidate_shadow"):
                 o.invalidate_shadow()
+            o._flat_sync = self if overlap else None
+
+    def launch(self, owner):
+        """Called by an owner at the end of its backward (``overlap=True`` only -- one backward per
+        optimizer step, i.e. no gradient accumulation): its gradient all-reduce starts on a side
+        stream and overlaps whatever backward work is still queued (the image encoder's backward
+        runs after the trunk's)."""
+        if self.world == 1 or id(owner) in self._pending:
+            return
+        if self._comm is None and owner._flat_grad.is_cuda:
+            self._comm = torch.cuda.Stream()
+        if self._comm is None:
+            self._pending[id(owner)] = dist.all_reduce(owner._flat_grad, group=self.group, async_op=True)
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ev)
+            self._pending[id(owner)] = dist.all_reduce(owner._flat_grad, group=self.group, async_op=True)
 
     def all_reduce_grads(self):
         if self.world > 1:
             for o in self.owners:
-                dist.all_reduce(o._flat_grad, group=self.group)
+                w = self._pending.pop(id(o), None)
+                if w is not None:
+                    w.wait()
+                else:
+                    dist.all_reduce(o._flat_grad, group=self.group)
+            if self._comm is not None:
+                torch.cuda.current_stream().wait_stream(self._comm)
 
     @classmethod
-    def attach(cls, optimizer, group=None):
-        sync = cls(optimizer._owners, group)
+    def attach(cls, optimizer, group=None, overlap=False):
+        sync = cls(optimizer._owners, group, overlap)
         optimizer._flat_sync = sync
         optimizer.grad_scale = 1.0 / sync.world
         return sync
