@@ -75,11 +75,17 @@ class ImageEncoder(nn.Module):
             p._mmu_owner = self
             holder, leaf = _holder_for(self, name)
             holder.register_parameter(leaf, p)
+        # every BatchNorm's num_batches_tracked is a 0-dim view of ONE int64 buffer: the forward bumps
+        # all of them with a single in-place add instead of 155 tiny launches
+        n_bn = sum(1 for name, *_ in self._stat_table if name.endswith("running_var"))
+        self._nbt = torch.zeros(n_bn, dtype=torch.long)
+        self._nbt_holders = []
         for name, off, numel, rows, cols in self._stat_table:
             holder, leaf = _holder_for(self, name)
             holder.register_buffer(leaf, self._stats[off:off + numel])
             if leaf == "running_var":
-                holder.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+                holder.register_buffer("num_batches_tracked", self._nbt[len(self._nbt_holders)])
+                self._nbt_holders.append(holder)
         self._rebind(self._flat, self._flat_grad, self._stats)
         self._init_weights()
 
@@ -103,7 +109,18 @@ class ImageEncoder(nn.Module):
     _fresh_shadow = MIMOResNet._fresh_shadow
     invalidate_shadow = MIMOResNet.invalidate_shadow
     _rebind = MIMOResNet._rebind
-    _apply = MIMOResNet._apply
+
+    def _apply(self, fn, recurse=True):
+        flat = fn(self._flat)
+        if flat.dtype != torch.float32:
+            raise TypeError("the image encoder's master parameters are fp32; choose precision='bf16' "
+                            "for the tensor-core path instead of casting the module")
+        self._rebind(flat, fn(self._flat_grad), fn(self._stats))
+        self._nbt = fn(self._nbt)
+        for i, holder in enumerate(self._nbt_holders):
+            holder._buffers["num_batches_tracked"] = self._nbt[i]
+        return self
+
     zero_grad = MIMOResNet.zero_grad
     _ensure_grad_views = FlavaFusionTransfomer._ensure_grad_views
 
@@ -153,10 +170,7 @@ class ImageEncoder(nn.Module):
                                                ws.numel(), int(bn_training), tokens.data_ptr(),
                                                _lib.stream_ptr()), "mmu_imgenc_forward")
         if bn_training:
-            for m in self.modules():
-                nb = m._buffers.get("num_batches_tracked")
-                if nb is not None:
-                    nb += 1
+            self._nbt += 1
         return cfg, ws, x, shadow, tokens
 
     def _engine_backward(self, saved, dtokens):

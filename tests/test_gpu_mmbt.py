@@ -271,7 +271,7 @@ def test_image_encoder_bf16_and_full_mmbt_from_images(mmu, golden):
     assert float(dict(named)["enc.img_encoder.model.0.weight"].grad.abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("B,S,H", [(2, 512, 12), (3, 333, 2), (2, 64, 1), (1, 130, 3), (2, 8, 2)])
+@pytest.mark.parametrize("B,S,H", [(2, 512, 12), (3, 333, 2), (2, 64, 1), (1, 130, 3), (2, 8, 2), (2, 300, 2), (1, 420, 3), (2, 257, 1), (1, 449, 2)])
 def test_fused_attention_matches_three_kernel_path_and_fp64(mmu, B, S, H):
     """The fused one-kernel attention forward (TMEM-resident scores) against the three-kernel
     tensor-core path and an fp64 softmax(QK^T/8 + mask)V on the same bf16 inputs: context within
