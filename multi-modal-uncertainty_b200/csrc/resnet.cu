@@ -432,10 +432,13 @@ __global__ void bn_apply_kernel(const TA* __restrict__ t, const float* __restric
 // ReLU), column sums of dyb and dyb * xhat.
 template <typename TA>
 __global__ void __launch_bounds__(256)
-bn_bwd_sums_kernel(const float* __restrict__ dout, const TA* __restrict__ out,
+bn_bwd_sums_kernel(const float* __restrict__ dout, const float* dout2, const TA* __restrict__ out,
                    const TA* __restrict__ t, const float* __restrict__ mean,
                    const float* __restrict__ rstd, int M, int C, int rows_per_block, int TX,
-                   float* __restrict__ dyb, double* __restrict__ sums) {
+                   float* dyb, double* __restrict__ sums) {
+  // dout2 (nullable): a second gradient term added on the fly -- the identity-shortcut gradient of
+  // the NEXT residual block, which would otherwise cost a separate add pass.  It may alias dyb
+  // (element i is read before element i is written, by the same thread).
   __shared__ double red[256][8];
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = 256 / TX;
   const int c = (blockIdx.x * TX + tx) * 4;
@@ -450,6 +453,10 @@ bn_bwd_sums_kernel(const float* __restrict__ dout, const TA* __restrict__ out,
       for (int u = 0; u < 2; ++u) {
         const size_t i = static_cast<size_t>(r + u * TY) * C + c;
         d[u] = *reinterpret_cast<const float4*>(dout + i);
+        if (dout2 != nullptr) {
+          const float4 e = *reinterpret_cast<const float4*>(dout2 + i);
+          d[u].x += e.x; d[u].y += e.y; d[u].z += e.z; d[u].w += e.w;
+        }
         tv[u] = ld4(t + i);
         ov[u] = out != nullptr ? ld4(out + i) : make_float4(1.f, 1.f, 1.f, 1.f);
       }
@@ -471,6 +478,10 @@ bn_bwd_sums_kernel(const float* __restrict__ dout, const TA* __restrict__ out,
     for (; r < r1; r += TY) {
       const size_t i = static_cast<size_t>(r) * C + c;
       float4 d = *reinterpret_cast<const float4*>(dout + i);
+      if (dout2 != nullptr) {
+        const float4 e = *reinterpret_cast<const float4*>(dout2 + i);
+        d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
+      }
       const float4 tv = ld4(t + i);
       if (out != nullptr) {
         const float4 ov = ld4(out + i);
@@ -893,7 +904,8 @@ int conv_bn_fwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
 // Produces (or accumulates into) din, the gradient w.r.t. the layer input (NHWC); if
 // dres_out != nullptr the masked gradient is also copied there (the residual branch).
 int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, int in_nchw,
-                const float* dout, int relu, float* din, int din_accumulate, float* dres_out) {
+                const float* dout, int relu, float* din, int din_accumulate, float* dres_out,
+                const float* dout2 = nullptr) {
   const int M = static_cast<int>(rows_of(x.c, l.hout)), K = l.ci * l.k * l.k;
   if (cudaMemsetAsync(x.w.sums, 0, 2 * l.co * sizeof(double), x.st) != cudaSuccess) return MMU_ERR_CUDA;
   float* dyb = dres_out != nullptr ? dres_out : x.w.dyb;
@@ -902,10 +914,10 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
   const int gy = (M + rpb - 1) / rpb;
   if (x.act16)
     bn_bwd_sums_kernel<bf16_t><<<dim3(cg.gx, gy), 256, 0, x.st>>>(
-        dout, relu ? as16(o.out) : nullptr, as16(o.t), o.mean, o.rstd, M, l.co, rpb, cg.tx, dyb, x.w.sums);
+        dout, dout2, relu ? as16(o.out) : nullptr, as16(o.t), o.mean, o.rstd, M, l.co, rpb, cg.tx, dyb, x.w.sums);
   else
     bn_bwd_sums_kernel<float><<<dim3(cg.gx, gy), 256, 0, x.st>>>(
-        dout, relu ? o.out : nullptr, o.t, o.mean, o.rstd, M, l.co, rpb, cg.tx, dyb, x.w.sums);
+        dout, dout2, relu ? o.out : nullptr, o.t, o.mean, o.rstd, M, l.co, rpb, cg.tx, dyb, x.w.sums);
   RN_CHECK_LAUNCH();
   const size_t n = static_cast<size_t>(M) * l.co;
   const size_t ncols = static_cast<size_t>(M) * K;
@@ -1527,22 +1539,29 @@ int ie_backward(const ImgEncConfig& c, const IeNet& n, IeWs& w, const float* par
         dtokens, w.pool_idx, c.B, n.h_out, n.c_out, c.pool_h, c.pool_w, c.pool_max, dcur);
     RN_CHECK_LAUNCH();
   }
+  // `pending` = identity-shortcut gradient of the block processed last, still to be added to dcur:
+  // it is folded into the next conv3's BatchNorm-backward pass instead of a separate add.
+  const float* pending = nullptr;
   for (int bi = n.n_block - 1; bi >= 0; --bi) {
     const IeBlock& B = n.block[bi];
     const float* blk_in = bi == 0 ? w.mp : w.cb[n.block[bi - 1].c3].out;
     // conv3 + bn3 + shortcut + relu: the masked gradient also flows along the shortcut (dres)
-    RN_TRY(conv_bn_bwd(x, n.conv[B.c3], w.cb[B.c3], w.cb[B.c2].out, 0, dcur, 1, dnext, 0, w.shared.dres));
+    RN_TRY(conv_bn_bwd(x, n.conv[B.c3], w.cb[B.c3], w.cb[B.c2].out, 0, dcur, 1, dnext, 0, w.shared.dres, pending));
+    pending = nullptr;
     RN_TRY(conv_bn_bwd(x, n.conv[B.c2], w.cb[B.c2], w.cb[B.c1].out, 0, dnext, 1, dcur, 0, nullptr));
     RN_TRY(conv_bn_bwd(x, n.conv[B.c1], w.cb[B.c1], blk_in, 0, dcur, 1, dnext, 0, nullptr));
     if (B.ds >= 0) {
       RN_TRY(conv_bn_bwd(x, n.conv[B.ds], w.cb[B.ds], blk_in, 0, w.shared.dres, 0, dnext, 1, nullptr));
     } else {
-      const ConvBn& l = n.conv[B.c1];
-      const size_t nel = static_cast<size_t>(c.B) * l.hin * l.hin * l.ci;
-      add_inplace_kernel<<<blocks_for(nel, 256), 256, 0, stream>>>(dnext, w.shared.dres, nel);
-      RN_CHECK_LAUNCH();
+      pending = w.shared.dres;
     }
     float* t = dcur; dcur = dnext; dnext = t;
+  }
+  if (pending != nullptr) {  // only if the very first block had an identity shortcut
+    const ConvBn& l = n.conv[n.block[0].c1];
+    const size_t nel = static_cast<size_t>(c.B) * l.hin * l.hin * l.ci;
+    add_inplace_kernel<<<blocks_for(nel, 256), 256, 0, stream>>>(dcur, pending, nel);
+    RN_CHECK_LAUNCH();
   }
   {
     const int hs = n.conv[0].hout;
