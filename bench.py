@@ -18,6 +18,9 @@ over N GPUs (weak scaling: B per GPU fixed).  Rank 0 prints ONE JSON line.
               of the step; every batch is copied host->device inside the timed region
 * `roofline`: dominant kernel = gemm_bf16_tcgen05_kernel (tensor bound); achieved = algorithmic
               FLOPs of the step's GEMM launches / their CUDA-event time, measured live here
+* `other_configs`: short device-timed side measurements of the BASELINE.json configs the headline
+              does not cover (configs[3] MMBT from pooled tokens and from raw images, configs[0]
+              FashionMNIST ResNet); reported next to the headline, never part of `value`
 * `cpu_baseline` / `--impl reference`: the oracle port (the reference is pure Python + torch
   CPU and cannot travel to the GPU box) timed on the host cores on a bounded sample.
 """
@@ -297,10 +300,13 @@ def run_gpu(args):
 
     # ---- roofline of the dominant kernel, measured live: every GEMM launch of one train step
     roof = cpu = hbm_kernels = None
+    other = None
     if rank == 0:
         roof, hbm_kernels = measure_rooflines(mmu, dev)
         if world == 1:
             cpu = cpu_reference(steps=1, warmup=1)
+            if not args.no_other_configs:
+                other = other_configs(mmu, dev)
     if world > 1:
         dist.barrier()
 
@@ -328,10 +334,101 @@ def run_gpu(args):
             "hbm_kernels": hbm_kernels,
             "cpu_baseline": cpu,
             "sweep_summary": {k: summary[k] for k in ("acc", "ece", "h_pred", "mi", "n_samples")},
+            "other_configs": other,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(mmu, dev):
+    """Short device-timed measurements (CUDA events, 3 warm-up + 5 steps) of the BASELINE.json configs
+    the headline does not cover -- reported next to it, never part of `value`: configs[3] MMBT
+    (BERT-base + ResNet-152 image tokens, 512 positions, batch 32, bf16: train step from pooled
+    tokens and from raw images, robustness forward) and configs[0] (four-view FashionMNIST ResNet,
+    batch 256).  N = 1 only; any failure is reported as a string instead of breaking the line."""
+    import types
+    out = {}
+
+    def timed(fn, n=5):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    try:
+        Bm, S_txt, n_img = 32, 507, 3
+        vocab = types.SimpleNamespace(stoi={"[CLS]": 101, "[SEP]": 102, "[PAD]": 0})
+        g = torch.Generator().manual_seed(42)
+        txt = torch.randint(1000, 30522, (Bm, S_txt), generator=g)
+        lens = torch.randint(S_txt // 2, S_txt + 1, (Bm,), generator=g)
+        mask = (torch.arange(S_txt)[None] < lens[:, None]).long()
+        txt, segment = (txt * mask).to(dev), mask.clone().to(dev)
+        mask = mask.to(dev)
+        y = torch.randint(0, 2, (Bm,), generator=g).to(dev)
+        S, D, L = n_img + 2 + S_txt, 768, 12
+        flops_fwd = L * (24 * S * D * D + 4 * S * S * D) * Bm
+        for images in (False, True):
+            args = types.SimpleNamespace(bert_model="bert-base-uncased", hidden_sz=768, img_hidden_sz=2048,
+                                         num_image_embeds=n_img, img_embed_pool_type="avg", dropout=0.0,
+                                         n_classes=2, vocab=vocab, precision="bf16",
+                                         img_encoder="native" if images else None)
+            torch.manual_seed(42)
+            m = mmu.MultimodalBertClf(args).to(dev).train()
+            named = list(m.named_parameters())
+            nd = ["bias", "LayerNorm.bias", "LayerNorm.weight"]
+            opt = mmu.BertAdam([{"params": [p for n, p in named if not any(k in n for k in nd)], "weight_decay": 0.01},
+                                {"params": [p for n, p in named if any(k in n for k in nd)], "weight_decay": 0.0}],
+                               lr=5e-5, warmup=0.1, t_total=1000)
+            img = (torch.randn(Bm, 3, 224, 224, generator=g) if images
+                   else torch.randn(Bm, n_img, 2048, generator=g)).to(dev)
+
+            def train_step():
+                opt.zero_grad()
+                loss = m.compute_loss(m(txt, mask, segment, img), y)
+                loss.backward()
+                opt.step()
+
+            ms = timed(train_step)
+            key = "mmbt_images" if images else "mmbt_tokens"
+            out[key] = {"train_ms": round(ms, 2), "train_samples_per_s": round(Bm / ms * 1e3, 1)}
+            if not images:
+                out[key]["train_tflops_trunk"] = round(3 * flops_fwd / ms / 1e9, 1)
+            m.eval()
+            with torch.no_grad():
+                ms = timed(lambda: m(txt, mask, segment, img))
+            out[key].update(eval_forward_ms=round(ms, 2), eval_samples_per_s=round(Bm / ms * 1e3, 1))
+            del m, opt
+            torch.cuda.empty_cache()
+        out["mmbt_config"] = "BERT-base, 3 + 2 + 507 = 512 positions, batch 32, bf16, BertAdam, binary head"
+    except Exception as e:  # noqa: BLE001 -- a side measurement must never break the headline line
+        out["mmbt_error"] = repr(e)[:200]
+    try:
+        Bf, E, C = 256, 4, 10
+        g = torch.Generator().manual_seed(42)
+        x = torch.rand(Bf, 4, 1, 14, 14, generator=g).to(dev)
+        yt = torch.randint(0, C, (Bf,), generator=g).unsqueeze(1).repeat(1, E).to(dev)
+        for prec in ("fp32", "bf16"):
+            torch.manual_seed(42)
+            m = mmu.MIMOResNet(num_channels=1, emb_dim=4, out_dim=E, num_classes=C, precision=prec).to(dev).train()
+            opt = torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9)
+
+            def step():
+                opt.zero_grad()
+                m.compute_loss(m(x), yt).backward()
+                opt.step()
+
+            ms = timed(step, 10)
+            out["fmnist_mimo_resnet_" + prec] = {"train_ms": round(ms, 3), "train_samples_per_s": round(Bf / ms * 1e3, 1)}
+    except Exception as e:  # noqa: BLE001
+        out["fmnist_error"] = repr(e)[:200]
+    return out
 
 
 def measure_rooflines(mmu, dev):
@@ -506,6 +603,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short side measurements of configs[0] / configs[3] (N = 1 only)")
     ap.add_argument("--rooflines-only", action="store_true",
                     help="only the per-kernel roofline legs (for ncu --metrics dram__bytes_* captures)")
     ap.add_argument("--profile", action="store_true",
