@@ -186,6 +186,28 @@ typedef struct {
 MMU_API int mmu_posthoc_scoring(const float* logits, const long long* labels, int V, int B, int E, int C,
                         int n_repeats, float* p_true_out, mmu_posthoc_accum* acc, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Rank statistics of the post-hoc analysis, as exact integer pair counts.
+ * mmu_pair_concordance: for each of `batch` problems b, over all unordered pairs {i, j} of
+ *   xb = x + b*x_batch_stride, yb = y + b*y_batch_stride (fp32, n elements each; a stride of 0
+ *   shares one vector between the problems), counts[4*b + 0..3] = { concordant, discordant,
+ *   tied in x, tied in y } (both tie counts include the jointly tied pairs; joint =
+ *   conc + disc + tx + ty - n(n-1)/2).  counts is overwritten.  NaNs compare as ties.
+ *   - AUROC (sklearn.metrics.roc_auc_score as called at src/framework.py:195-198 and
+ *     notebooks/hatefulmeme_robustness.py:22-41): x = labels as 0/1 floats, y = scores;
+ *     AUROC = (conc + (ty - joint)/2) / (conc + disc + ty - joint).
+ *   - Kendall tau-b (scipy.stats.kendalltau as called at notebooks/analysis_round_1.py:87-90):
+ *     (conc - disc) / sqrt((T - tx)(T - ty)), T = n(n-1)/2.
+ * mmu_top_truncate: notebooks/analysis_round_1.py:74-85 `trunk_pred_top` on device -- per row of
+ *   pred (N, C): threshold = the top-th largest value of the original row, the true class zeroed
+ *   first when mute_true (labels int64 (N), may be NULL otherwise), entries below the threshold
+ *   zeroed; out (N, C). */
+MMU_API int mmu_pair_concordance(const float* x, const float* y, long long n, int batch,
+                         long long x_batch_stride, long long y_batch_stride,
+                         unsigned long long* counts, void* stream);
+MMU_API int mmu_top_truncate(const float* pred, const long long* labels, int N, int C, int top,
+                     int mute_true, float* out, void* stream);
+
 MMU_API int mmu_adamw_flat_step(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n,
                         float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                         float grad_scale, void* stream);

@@ -20,7 +20,7 @@ EXPORTS = [
     "mmu_heads_uncertainty_epilogue", "mmu_adamw_flat_step", "mmu_flava_param_count",
     "mmu_flava_param_table", "mmu_flava_workspace_bytes", "mmu_flava_num_stages",
     "mmu_flava_forward", "mmu_flava_backward", "mmu_cast_f32_to_bf16", "mmu_struct_size",
-    "mmu_posthoc_scoring", "mmu_ragged_pad",
+    "mmu_posthoc_scoring", "mmu_ragged_pad", "mmu_pair_concordance", "mmu_top_truncate",
     "mmu_resnet_param_count", "mmu_resnet_stat_count", "mmu_resnet_param_table",
     "mmu_resnet_stat_table", "mmu_resnet_workspace_bytes", "mmu_resnet_forward",
     "mmu_resnet_backward",
@@ -129,6 +129,8 @@ def _load():
     lib.mmu_resnet_backward.argtypes = [rcfgp, vp, vp, vp, vp, vp, ll, vp, vp, vp]
     lib.mmu_ragged_pad.argtypes = [vp, vp, vp, i, i, i, vp]
     lib.mmu_posthoc_scoring.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp]
+    lib.mmu_pair_concordance.argtypes = [vp, vp, ll, i, ll, ll, vp, vp]
+    lib.mmu_top_truncate.argtypes = [vp, vp, i, i, i, i, vp, vp]
     lib.mmu_cast_f32_to_bf16.argtypes = [vp, vp, C.c_size_t, vp]
     lib.mmu_layernorm_fwd.argtypes = [vp, vp, vp, vp, i, vp, vp, i, i, vp]
     lib.mmu_layernorm_bwd.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, i, vp, vp, vp, i, i, vp]

@@ -185,6 +185,19 @@ int mmu_posthoc_scoring(const float* logits, const long long* labels, int V, int
                          reinterpret_cast<PosthocAccum*>(acc), S(stream));
 }
 
+int mmu_pair_concordance(const float* x, const float* y, long long n, int batch,
+                         long long x_batch_stride, long long y_batch_stride,
+                         unsigned long long* counts, void* stream) {
+  if (x == nullptr || y == nullptr || counts == nullptr) return MMU_ERR_ARG;
+  return pair_concordance(x, y, n, batch, x_batch_stride, y_batch_stride, counts, S(stream));
+}
+
+int mmu_top_truncate(const float* pred, const long long* labels, int N, int C, int top, int mute_true,
+                     float* out, void* stream) {
+  if (pred == nullptr || out == nullptr || (mute_true && labels == nullptr)) return MMU_ERR_ARG;
+  return top_truncate(pred, labels, N, C, top, mute_true, out, S(stream));
+}
+
 int mmu_flava_forward(const mmu_flava_config* cfg, const float* params, const mmu_flava_inputs* in,
                       void* workspace, long long workspace_bytes, int training, float* logits,
                       void* stream) {

@@ -146,6 +146,16 @@ int posthoc_scoring(const float* logits /*(V,B,E,C)*/, const long long* labels /
                     int E, int C, int n_repeats, float* p_true_out /*(B,V) or null*/,
                     PosthocAccum* acc, cudaStream_t stream);
 
+// ---- rank statistics (AUROC: notebooks/hatefulmeme_robustness.py:22-41, src/framework.py:195-198;
+// Kendall tau-b @ top-k: notebooks/analysis_round_1.py:74-113).  counts[b] = {concordant,
+// discordant, tied in x (joint ties included), tied in y (joint ties included)} over all unordered
+// pairs of (x + b*x_batch_stride, y + b*y_batch_stride)[0..n); overwritten, exact integers.
+int pair_concordance(const float* x, const float* y, long long n, int batch, long long x_batch_stride,
+                     long long y_batch_stride, unsigned long long* counts /*[batch][4]*/,
+                     cudaStream_t stream);
+int top_truncate(const float* pred /*(N,C)*/, const long long* labels /*(N) or null*/, int N, int C,
+                 int top, int mute_true, float* out /*(N,C)*/, cudaStream_t stream);
+
 // ---- fused AdamW over the flat parameter buffer (train.py:196-202 hyper-parameters)
 int adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n, float lr,
                float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,

@@ -204,6 +204,39 @@ def posthoc_scoring(logits, labels, n_repeats, accum=None, want_p_true=False):
     return accum, p_true
 
 
+def pair_concordance(x, y):
+    """Exact pair counts of (x, y): x (n,) or (batch, n), y likewise (a 1-D argument is shared by
+    every problem of the batch).  Returns int64 (batch, 4) = concordant, discordant, tied in x,
+    tied in y; see ``mmu_pair_concordance``."""
+    _cuda(x, y)
+    if x.dtype != torch.float32 or y.dtype != torch.float32:
+        raise TypeError("x and y must be fp32")
+    n = x.shape[-1]
+    if y.shape[-1] != n:
+        raise ValueError("x and y differ in length")
+    batch = max(x.shape[0] if x.dim() == 2 else 1, y.shape[0] if y.dim() == 2 else 1)
+    for t in (x, y):
+        if t.dim() == 2 and t.shape[0] != batch:
+            raise ValueError("batch sizes differ")
+    counts = torch.empty(batch, 4, dtype=torch.int64, device=x.device)
+    check(lib.mmu_pair_concordance(ptr(x), ptr(y), n, batch, n if x.dim() == 2 else 0,
+                                   n if y.dim() == 2 else 0, ptr(counts), stream_ptr()),
+          "mmu_pair_concordance")
+    return counts
+
+
+def top_truncate(pred, labels=None, top=5, mute_true=False):
+    """``trunk_pred_top`` of notebooks/analysis_round_1.py:74-85 on device; pred fp32 (N, C)."""
+    _cuda(pred, labels)
+    if pred.dtype != torch.float32 or (labels is not None and labels.dtype != torch.int64):
+        raise TypeError("pred must be fp32 and labels int64")
+    N, Cn = pred.shape
+    out = torch.empty_like(pred)
+    check(lib.mmu_top_truncate(ptr(pred), ptr(labels), N, Cn, top, int(bool(mute_true)), ptr(out),
+                               stream_ptr()), "mmu_top_truncate")
+    return out
+
+
 def ragged_pad(packed, offsets, max_len):
     """Zero-padded (B, max_len, d) batch from packed rows (sum_len, d) + int32 offsets (B+1,):
     the device twin of ``pad_sequence(batch_first=True)`` (reference src/dataset.py:216-226)."""

@@ -205,9 +205,10 @@ class Model_:
                **{f"{phase}_{k}": v for k, v in it.extra_lists.items()},
                **{f"{phase}_{k}": v for k, v in it.metrics.items()}}
         if auc:
-            from sklearn.metrics import roc_auc_score
-            p = torch.cat(preds).cpu().numpy()
-            out[f"{phase}_auc"] = roc_auc_score(torch.cat(labels).cpu().numpy(), p[:, 1])
+            # reference src/framework.py:195-198 (sklearn roc_auc_score on the host copy of every
+            # logit): exact pair counting on the device instead, 32 bytes read back
+            from . import metrics as _metrics
+            out[f"{phase}_auc"] = _metrics.auroc(torch.cat(labels), torch.cat(preds)[:, 1].contiguous())
         return out
 
     def train_loop(self, train_generator, test_generator=None, valid_generator=None, *,

@@ -99,6 +99,17 @@ class PosthocMeter:
                                         self.n_repeats, accum=self.accum, want_p_true=want_p_true)
         return p_true
 
+    def class_prob(self, logits_vbec, cls=1):
+        """Head-mean probability of class ``cls`` per (sample, variant), (B, V): the scores of
+        ``process_predictions_hatefulmeme`` (reference ``notebooks/hatefulmeme_robustness.py:
+        105-112``) that ``metrics.auc_table`` ranks.  Same kernel as ``update`` with every label
+        set to ``cls``; the accumulator of this meter is not touched."""
+        B = logits_vbec.shape[1]
+        lab = torch.full((B,), int(cls), dtype=torch.int64, device=logits_vbec.device)
+        _, p = ops.posthoc_scoring(logits_vbec.contiguous(), lab, self.n_repeats, accum=None,
+                                   want_p_true=True)
+        return p
+
     def all_reduce(self, group=None):
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -128,3 +139,76 @@ class PosthocMeter:
                    acc_text_control=float(acc[3 + r:].mean()) if r else float("nan"),
                    acc_per_variant=acc)
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Rank statistics of the post-hoc analysis, from exact device-side pair counts
+# (``mmu_pair_concordance``).  Nothing is sorted and nothing leaves the GPU but 32 bytes per problem.
+def _as_f32_rows(t, device):
+    t = torch.as_tensor(t)
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def pair_counts(x, y):
+    """int64 numpy (batch, 4): concordant, discordant, tied in x, tied in y (joint ties in both)."""
+    if not torch.cuda.is_available():
+        raise _lib.MMUError("rank statistics run on the GPU only (no CUDA device, no CPU fallback)")
+    dev = y.device if isinstance(y, torch.Tensor) and y.is_cuda else torch.device("cuda")
+    return ops.pair_concordance(_as_f32_rows(x, dev), _as_f32_rows(y, dev)).cpu().numpy()
+
+
+def auroc(labels, scores):
+    """Area under the ROC curve of binary ``labels`` (N,) against ``scores`` (N,) or (V, N): what
+    ``sklearn.metrics.roc_auc_score`` returns at reference ``src/framework.py:195-198`` and
+    ``notebooks/hatefulmeme_robustness.py:22-41``, as the Mann-Whitney ratio of exact pair counts.
+    Returns a float (1-D scores) or a float64 array (V,).  Raises ValueError when only one class
+    is present, like sklearn."""
+    scores_t = torch.as_tensor(scores)
+    n = scores_t.shape[-1]
+    cnt = pair_counts(torch.as_tensor(labels).reshape(-1), scores_t)
+    conc, disc, tx, ty = (cnt[:, k].astype(object) for k in range(4))   # Python ints: no overflow
+    joint = conc + disc + tx + ty - n * (n - 1) // 2
+    ty_only = ty - joint
+    den = conc + disc + ty_only
+    if (den == 0).any():
+        raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
+    out = np.array([float((c + 0.5 * t) / d) for c, t, d in zip(conc, ty_only, den)])
+    return float(out[0]) if scores_t.dim() == 1 else out
+
+
+def kendalltau(x, y):
+    """Kendall tau-b of the flattened inputs (``scipy.stats.kendalltau`` as called at reference
+    ``notebooks/analysis_round_1.py:87-90``); nan when one side is constant."""
+    x, y = torch.as_tensor(x).reshape(-1), torch.as_tensor(y).reshape(-1)
+    n = x.numel()
+    conc, disc, tx, ty = (int(v) for v in pair_counts(x, y)[0])
+    tot = n * (n - 1) // 2
+    if tot - tx == 0 or tot - ty == 0:
+        return float("nan")
+    return (conc - disc) / np.sqrt(float(tot - tx)) / np.sqrt(float(tot - ty))
+
+
+def head_diversity_kendalltau(predictions, labels, top=5, mute_true=True):
+    """Prediction-diversity score of reference ``notebooks/analysis_round_1.py:74-113``: per head,
+    ``trunk_pred_top`` (keep the top-``top`` entries of each row, true class muted), then tau-b
+    between every pair of heads (``itertools.combinations`` order) on the flattened arrays.
+    predictions: CUDA fp32 (S, E, C); labels int64 (S).  Returns float64 (E(E-1)/2,); the notebook
+    prints the mean."""
+    import itertools
+    S, E, C = predictions.shape
+    labels = labels.reshape(-1).to(predictions.device, torch.int64).contiguous()
+    muted = [ops.top_truncate(predictions[:, k, :].contiguous().float(), labels, top, mute_true)
+             for k in range(E)]
+    return np.array([kendalltau(a, b) for a, b in itertools.combinations(muted, 2)])
+
+
+def auc_table(labels, scores):
+    """``AUC_table`` of reference ``notebooks/hatefulmeme_robustness.py:22-41``: scores (S, V) of
+    p(class 1) per variant (full, image, text, n image controls, n text controls) -> AUROC per
+    variant (V,) plus the notebook's group means."""
+    scores = torch.as_tensor(scores)
+    auc = auroc(labels, scores.t().contiguous())
+    n = (len(auc) - 3) // 2
+    return {"AUC": auc, "full": auc[0], "image": auc[1], "text": auc[2],
+            "image_control": float(auc[3:3 + n].mean()) if n else float("nan"),
+            "text_control": float(auc[3 + n:].mean()) if n else float("nan")}

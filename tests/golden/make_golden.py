@@ -335,6 +335,55 @@ def notebook_case():
                 acc_full=float((pred[:, 0] == labels).mean() * 100))
 
 
+def rank_case():
+    """Rank statistics of the notebooks, computed by the reference's own functions:
+    `trunk_pred_top` / `subnetwork_wise_kendalltau` (notebooks/analysis_round_1.py:74-90) and
+    `process_predictions_hatefulmeme` / `AUC_table` (notebooks/hatefulmeme_robustness.py:22-41,
+    105-112), extracted from the unmodified sources with ast and executed on seeded arrays."""
+    import itertools
+    import pandas as pd
+    import scipy.stats as stats
+    from sklearn.metrics import roc_auc_score
+    ns = {"np": np, "stats": stats, "itertools": itertools}
+    tree = ast.parse(open(os.path.join(REF, "notebooks", "analysis_round_1.py")).read())
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef)
+           and n.name in ("trunk_pred_top", "subnetwork_wise_kendalltau")]
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "nb_round1", "exec"), ns)
+    rng = np.random.RandomState(31)
+    S, E, C, top = 300, 4, 10, 5
+    predictions = rng.randn(S, E, C).astype(np.float32)
+    predictions[::7, :, 3] = predictions[::7, :, 5]          # ties inside rows
+    predictions[5] = np.round(predictions[5])                # many equal entries
+    labels = rng.randint(0, C, size=S)
+    muted = [ns["trunk_pred_top"](predictions[:, i, :], labels, top, mute_true=True)
+             for i in range(E)]
+    plain = ns["trunk_pred_top"](predictions[:, 0, :], labels, 3, mute_true=False)
+    taus = ns["subnetwork_wise_kendalltau"](muted)
+
+    ns2 = {"np": np, "pd": pd, "roc_auc_score": roc_auc_score}
+    src_u = open(os.path.join(REF, "notebooks", "utils.py")).read()
+    fn_u = [n for n in ast.parse(src_u).body if isinstance(n, ast.FunctionDef) and n.name == "softmax"]
+    exec(compile(ast.Module(body=fn_u, type_ignores=[]), "nb_utils", "exec"), ns2)
+    tree2 = ast.parse(open(os.path.join(REF, "notebooks", "hatefulmeme_robustness.py")).read())
+    fns2 = [n for n in tree2.body if isinstance(n, ast.FunctionDef)
+            and n.name in ("AUC_table", "process_predictions_hatefulmeme")]
+    exec(compile(ast.Module(body=fns2, type_ignores=[]), "nb_hateful", "exec"), ns2)
+    S2, V, K = 400, 43, 2
+    preds = (rng.randn(S2, V, K, 2) * 1.5).astype(np.float32)
+    preds[::5] = np.round(preds[::5])                        # tied scores across samples
+    lab2 = rng.randint(0, 2, size=S2)
+    args = ns2["process_predictions_hatefulmeme"](preds, lab2)
+    df = ns2["AUC_table"](*args)
+    return dict(predictions=torch.from_numpy(predictions), labels=torch.from_numpy(labels), top=top,
+                muted=torch.from_numpy(np.stack(muted).astype(np.float64)),
+                plain_top3=torch.from_numpy(plain.astype(np.float64)),
+                taus=torch.from_numpy(np.asarray(taus, dtype=np.float64)),
+                hm_preds=torch.from_numpy(preds), hm_labels=torch.from_numpy(lab2),
+                hm_scores=torch.from_numpy(np.concatenate(
+                    [np.stack(args[1:4], 1), args[4], args[5]], 1).astype(np.float32)),
+                hm_auc=torch.from_numpy(df["AUC"].to_numpy(dtype=np.float64)))
+
+
 def init_case(ref_model):
     """Seeded construction of the reference modules: per-parameter checksums of the initial
     weights (the product constructs torch's own layers in the same order under the same seed)."""
@@ -364,6 +413,9 @@ def init_case(ref_model):
 
 def main():
     torch.set_num_threads(4)
+    if sys.argv[1:] == ["rank"]:   # only the rank-statistics fixture (no model import needed)
+        torch.save(rank_case(), os.path.join(HERE, "rank_stats.pt"))
+        return
     ref_model, ref_dataset, _ = import_reference()
     small = dict(C=7, D=64, heads=2, layers=2, d_img=32, d_txt=48, l_img=5, l_txt=3, B=4)
     cases = {
@@ -385,6 +437,7 @@ def main():
     torch.save(optimizer_case(), os.path.join(HERE, "adamw_cosine.pt"))
     torch.save(notebook_case(), os.path.join(HERE, "notebook_scoring.pt"))
     torch.save(init_case(ref_model), os.path.join(HERE, "init_seed123.pt"))
+    torch.save(rank_case(), os.path.join(HERE, "rank_stats.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -247,3 +247,75 @@ def test_ragged_collator_matches_pad_sequence(mmu, tmp_path):
         (gi, gt), gy = collate(idxs)
         (ri, rt), ry = mmu.dataset.collate_fn_flava([items[i] for i in idxs])
         assert torch.equal(gi.cpu(), ri) and torch.equal(gt.cpu(), rt) and torch.equal(gy.cpu(), ry)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 1023, 1024, 1025, 2047, 2049, 4097, 6000])
+def test_pair_concordance_counts_bit_exact(mmu, n):
+    """mmu_pair_concordance against the oracle's integer pair counts: sizes straddle the 1024-row
+    tile, the 2048-column chunk and the diagonal blocks; values are tie-heavy."""
+    import numpy as np
+    from oracle import rank_stats
+    rng = np.random.RandomState(n)
+    x = rng.randint(0, 6, size=n).astype(np.float32)
+    ys = np.stack([rng.randint(0, 40, size=n).astype(np.float32),
+                   rng.randn(n).astype(np.float32), x.copy()])
+    got = mmu.ops.pair_concordance(torch.from_numpy(x).cuda(), torch.from_numpy(ys).cuda()).cpu()
+    for b in range(3):                                   # x shared by the batch (stride 0)
+        assert tuple(int(v) for v in got[b]) == rank_stats.pair_counts(x, ys[b])
+    got2 = mmu.ops.pair_concordance(torch.from_numpy(ys).cuda(), torch.from_numpy(ys[[2, 0, 1]].copy()).cuda())
+    for b in range(3):
+        assert tuple(int(v) for v in got2[b].cpu()) == rank_stats.pair_counts(ys[b], ys[[2, 0, 1][b]])
+
+
+def test_rank_statistics_match_reference_notebooks(mmu, golden):
+    """Device top-5 truncation, Kendall tau-b between heads and AUROC per variant against the
+    reference's own notebook functions frozen in tests/golden/rank_stats.pt
+    (notebooks/analysis_round_1.py:74-113, notebooks/hatefulmeme_robustness.py:22-41,105-112)."""
+    import numpy as np
+    c = golden("rank_stats.pt")
+    preds, labels = c["predictions"].cuda(), c["labels"].long().cuda()
+    for k in range(preds.shape[1]):
+        got = mmu.ops.top_truncate(preds[:, k].contiguous(), labels, c["top"], True)
+        assert torch.equal(got.cpu().double(), c["muted"][k])                      # bit-exact
+    got = mmu.ops.top_truncate(preds[:, 0].contiguous(), None, 3, False)
+    assert torch.equal(got.cpu().double(), c["plain_top3"])
+    taus = mmu.metrics.head_diversity_kendalltau(preds, labels, top=c["top"])
+    assert np.allclose(taus, c["taus"].numpy(), rtol=0, atol=1e-12)
+    # AUROC of the notebook's own scores: exact counts -> equal to sklearn's up to its last ulp
+    tab = mmu.metrics.auc_table(c["hm_labels"], c["hm_scores"])
+    assert np.allclose(tab["AUC"], c["hm_auc"].numpy(), rtol=0, atol=1e-12)
+    n = (len(tab["AUC"]) - 3) // 2
+    assert tab["image_control"] == pytest.approx(float(c["hm_auc"][3:3 + n].mean()), abs=1e-12)
+    # scores computed on device from the (S, V, K, 2) logits: fp32 softmax (max-subtracted) vs the
+    # notebook's naive fp32 softmax -> 1e-5 on the scores, AUROC within the reach of re-broken ties
+    lg = c["hm_preds"].transpose(0, 1).contiguous().cuda()                         # (V, S, K, 2)
+    meter = mmu.metrics.PosthocMeter("cuda", n)
+    p1 = meter.class_prob(lg, 1)
+    assert rel(p1.cpu(), c["hm_scores"]) < 1e-5
+    tab2 = mmu.metrics.auc_table(c["hm_labels"], p1)
+    assert np.abs(tab2["AUC"] - c["hm_auc"].numpy()).max() < 2e-3
+    assert mmu.metrics.auroc(c["hm_labels"], p1[:, 0].contiguous()) == pytest.approx(tab2["AUC"][0], abs=0)
+    with pytest.raises(ValueError):
+        mmu.metrics.auroc(torch.zeros(8), torch.rand(8))
+
+
+def test_rank_statistics_full_size_properties(mmu):
+    """At evaluation-set sizes (200k scores: O(n^2) = 2e10 pairs on device) the counts obey their
+    identities and the AUROC equals sklearn's rank-based value."""
+    import numpy as np
+    from sklearn.metrics import roc_auc_score
+    n = 200_000
+    g = torch.Generator().manual_seed(5)
+    lab = torch.randint(0, 2, (n,), generator=g)
+    sc = (torch.randn(n, generator=g) + 0.5 * lab).mul(64).round().div(64)          # ties
+    a = mmu.metrics.auroc(lab, sc)
+    assert abs(a - roc_auc_score(lab.numpy(), sc.numpy())) < 1e-12
+    assert abs(mmu.metrics.auroc(lab, -sc) - (1.0 - a)) < 1e-15
+    cnt = mmu.metrics.pair_counts(lab, sc)[0]
+    n_pos = int(lab.sum())
+    tot = n * (n - 1) // 2
+    joint = int(cnt.sum()) - tot
+    assert int(cnt[2]) == n_pos * (n_pos - 1) // 2 + (n - n_pos) * (n - n_pos - 1) // 2
+    assert int(cnt[0]) + int(cnt[1]) + int(cnt[3]) - joint == n_pos * (n - n_pos)
+    assert mmu.metrics.kendalltau(sc, sc) == pytest.approx(1.0, abs=1e-15)
+    assert mmu.metrics.kendalltau(sc, -sc) == pytest.approx(-1.0, abs=1e-15)

@@ -254,7 +254,7 @@ def test_trainer_protocol_with_a_plain_torch_model(mmu, tmp_path):
         trainer.eval_loop(val, "val", vilt=True)
 
 
-def test_trainer_mmbt_branch_with_a_plain_torch_model(mmu):
+def test_trainer_mmbt_branch_with_a_plain_torch_model(mmu, monkeypatch):
     """The ``mmbt`` branches of Model_ (reference src/framework.py:246-304, :172-176): ``model(*x)``,
     per-epoch freeze flags on ``enc.img_encoder`` / ``enc.encoder``, gradient-accumulation stepping,
     (B, C) logits with ``dummy_dim=False`` metrics, epoch-wise scheduler on ``val_acc``."""
@@ -291,6 +291,14 @@ def test_trainer_mmbt_branch_with_a_plain_torch_model(mmu):
                                              net.enc.encoder.weight.requires_grad)), step(*a, **k))[1]
     trainer = mmu.Model_(net, opt, sched, lambda x, y, phase="train": (x, y), metrics=[acc], verbose=False)
     trainer.to(torch.device("cpu"))
+    # the product's AUROC counts pairs on the GPU and refuses to run without one; this host-logic
+    # test stands the oracle in for it
+    from oracle import rank_stats
+    if not torch.cuda.is_available():
+        with pytest.raises(mmu._lib.MMUError):
+            mmu.src.metrics.auroc(torch.tensor([0, 1]), torch.tensor([0.2, 0.7]))
+    monkeypatch.setattr(mmu.src.metrics, "auroc",
+                        lambda lab, sc: rank_stats.auroc(lab.numpy(), sc.numpy()))
     H = {}
     cbs = [mmu.src.callbacks.LambdaCallback(on_epoch_end=lambda e, l: H.setdefault("logs", []).append(dict(l)))]
     trainer.train_loop(batches(4), valid_generator=batches(2), epochs=2, steps_per_epoch=4, validation_steps=2,

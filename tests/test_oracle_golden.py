@@ -262,3 +262,43 @@ def test_image_encoder_oracle_matches_reference(golden, name):
         assert digest_error(d, grads[k]) < 1e-4, k
     for k, v in c["buffers_after"].items():
         assert rel_err(buf[k], v) < 1e-5, k
+
+
+def test_rank_stats_against_reference_notebooks(golden):
+    """oracle/rank_stats.py against the reference's own trunk_pred_top / subnetwork_wise_kendalltau
+    (notebooks/analysis_round_1.py:74-90) and AUC_table (notebooks/hatefulmeme_robustness.py:22-41),
+    executed unmodified by tests/golden/make_golden.py::rank_case."""
+    from oracle import rank_stats
+    c = golden("rank_stats.pt")
+    preds, labels = c["predictions"].numpy(), c["labels"].numpy()
+    for k in range(preds.shape[1]):
+        got = rank_stats.trunk_pred_top(preds[:, k], labels, c["top"], mute_true=True)
+        assert np.array_equal(got.astype(np.float64), c["muted"][k].numpy())      # bit-exact
+    got = rank_stats.trunk_pred_top(preds[:, 0], labels, 3, mute_true=False)
+    assert np.array_equal(got.astype(np.float64), c["plain_top3"].numpy())
+    taus = rank_stats.subnetwork_wise_kendalltau(preds, labels, c["top"])
+    assert np.allclose(taus, c["taus"].numpy(), rtol=0, atol=1e-12)
+    auc = rank_stats.auc_table(c["hm_labels"].numpy(), c["hm_scores"].numpy())
+    assert np.allclose(auc, c["hm_auc"].numpy(), rtol=0, atol=1e-12)
+    # the scores themselves: head-mean probability of class 1 (process_predictions_hatefulmeme)
+    p1 = uncertainty.notebook_softmax(c["hm_preds"].numpy()).mean(2)[..., 1]
+    assert np.allclose(p1, c["hm_scores"].numpy(), rtol=1e-6)
+
+
+def test_rank_stats_against_scipy_and_sklearn():
+    """The third-party definitions the reference calls, live, on vectors with heavy ties."""
+    import scipy.stats as stats
+    from sklearn.metrics import roc_auc_score
+    from oracle import rank_stats
+    rng = np.random.RandomState(4)
+    for n, levels in [(2, 2), (3, 50), (257, 4), (1500, 1000), (2500, 7)]:
+        x = rng.randint(0, levels, size=n).astype(np.float32)
+        y = rng.randint(0, levels, size=n).astype(np.float32) + (x > levels // 2)
+        if len(set(x)) > 1 and len(set(y)) > 1:
+            assert abs(rank_stats.kendalltau(x, y) - stats.kendalltau(x, y)[0]) < 1e-12
+        lab = rng.randint(0, 2, size=n)
+        if 0 < lab.sum() < n:
+            assert abs(rank_stats.auroc(lab, y) - roc_auc_score(lab, y)) < 1e-12
+    assert np.isnan(rank_stats.kendalltau(np.ones(5), np.arange(5)))
+    conc, disc, tx, ty = rank_stats.pair_counts([1, 2, 2, 3], [1, 3, 3, 2])
+    assert (conc, disc, tx, ty) == (3, 2, 1, 1)
