@@ -319,3 +319,28 @@ def test_rank_statistics_full_size_properties(mmu):
     assert int(cnt[0]) + int(cnt[1]) + int(cnt[3]) - joint == n_pos * (n - n_pos)
     assert mmu.metrics.kendalltau(sc, sc) == pytest.approx(1.0, abs=1e-15)
     assert mmu.metrics.kendalltau(sc, -sc) == pytest.approx(-1.0, abs=1e-15)
+
+
+@pytest.mark.parametrize("N,E,C", [(777, 5, 101), (130, 4, 10), (64, 6, 101), (99, 3, 2), (50, 2, 60)])
+def test_uncertainty_epilogue_batched_heads_bit_identical(mmu, N, E, C, monkeypatch):
+    """Eval mode reduces HB heads together (ce_uncertainty_kernel<..., HB>); every HB that divides E
+    must give the head-by-head kernel's results bit for bit (scores, predictions, every bin)."""
+    logits = rnd(N, E, C, seed=N + E, scale=4.0).cuda()
+    g = torch.Generator().manual_seed(N)
+    y = torch.randint(0, C, (N,), generator=g).cuda()
+    outs = {}
+    for hb in [h for h in (1, 2, 3, 4, 5) if E % h == 0]:
+        monkeypatch.setenv("MMU_CE_HB", str(hb))
+        _, pred, scores, accum = mmu.ops.heads_uncertainty_epilogue(logits, y, 1, want_pred=True,
+                                                                    want_scores=True)
+        outs[hb] = (pred.cpu(), scores.cpu(), accum.cpu())
+    monkeypatch.delenv("MMU_CE_HB")
+    _, pred, scores, accum = mmu.ops.heads_uncertainty_epilogue(logits, y, 1, want_pred=True,
+                                                                want_scores=True)
+    outs["default"] = (pred.cpu(), scores.cpu(), accum.cpu())
+    assert len(outs) >= 3
+    for hb, (p, s, a) in outs.items():
+        assert torch.equal(p, outs[1][0]) and torch.equal(s, outs[1][1]), hb
+        # integer words of the accumulator are order independent; the fp64 sums are atomics
+        ia = a.view(torch.int64)[:mmu._lib.ACC_INT_WORDS]
+        assert torch.equal(ia, outs[1][2].view(torch.int64)[:mmu._lib.ACC_INT_WORDS]), hb

@@ -16,7 +16,12 @@ yt = y.unsqueeze(1).repeat(1, E).contiguous()
 acc = mmu.ops.new_accum(dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 out = {}
+def eval_hb1():
+    os.environ["MMU_CE_HB"] = "1"
+    mmu.ops.heads_uncertainty_epilogue(logits, y, 1, accum=acc)
+    del os.environ["MMU_CE_HB"]
 for name, fn, byts in (
+        ("eval_head_by_head", eval_hb1, N * (E * C * 4 + 8)),
         ("eval", lambda: mmu.ops.heads_uncertainty_epilogue(logits, y, 1, accum=acc), N * (E * C * 4 + 8)),
         ("train_grad", lambda: mmu.ops.heads_uncertainty_epilogue(logits, yt, 0, grad_scale=1.0 / (N * E),
                                                                   want_grad=True, accum=acc),
