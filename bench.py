@@ -426,8 +426,28 @@ def other_configs(mmu, dev):
 
             ms = timed(step, 10)
             out["fmnist_mimo_resnet_" + prec] = {"train_ms": round(ms, 3), "train_samples_per_s": round(Bf / ms * 1e3, 1)}
+            # the same step replayed from a CUDA graph through the trainer (graphs.GraphedTrainStep)
+            tr = mmu.Model_(m, opt, None, lambda a, b, phase="train": (a, b), metrics=[mmu.acc], verbose=False)
+            tr.to(dev)
+            ms = timed(lambda: tr.train_step(x, yt, sync=False, cuda_graph=True), 10)
+            out["fmnist_mimo_resnet_" + prec].update(graph_train_ms=round(ms, 3),
+                                                     graph_train_samples_per_s=round(Bf / ms * 1e3, 1))
     except Exception as e:  # noqa: BLE001
         out["fmnist_error"] = repr(e)[:200]
+    try:
+        # post-hoc rank statistics (exact pair counting, compute bound): AUROC of 43 variants of a
+        # 10 000-sample evaluation set in one batched launch, and one 200 000-score vector
+        g = torch.Generator().manual_seed(42)
+        lab = torch.randint(0, 2, (10000,), generator=g).float().to(dev)
+        sc = torch.randn(43, 10000, generator=g).to(dev)
+        ms = timed(lambda: mmu.ops.pair_concordance(lab, sc))
+        big_l = torch.randint(0, 2, (200000,), generator=g).float().to(dev)
+        big_s = torch.randn(200000, generator=g).to(dev)
+        ms2 = timed(lambda: mmu.ops.pair_concordance(big_l, big_s), 3)
+        out["rank_stats"] = {"auroc_43x10k_ms": round(ms, 3), "pairs_per_s_43x10k": round(43 * 10000 * 9999 / 2 / ms * 1e3),
+                             "auroc_200k_ms": round(ms2, 3), "pairs_per_s_200k": round(200000 * 199999 / 2 / ms2 * 1e3)}
+    except Exception as e:  # noqa: BLE001
+        out["rank_stats_error"] = repr(e)[:200]
     return out
 
 

@@ -9,7 +9,7 @@ everything numerical runs in ``libmmu_b200.so`` (hand-written CUDA, C ABI in
 """
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is missing)
 from . import ops  # noqa: F401
-from .src import (callbacks, dataset, framework, metrics, mmbt, model, optim, parallel,  # noqa: F401
+from .src import (callbacks, dataset, framework, graphs, metrics, mmbt, model, optim, parallel,  # noqa: F401
                   robustness, training_loop, utils)
 from .src.framework import Model_  # noqa: F401
 from .src.metrics import acc  # noqa: F401

@@ -113,13 +113,27 @@ class Model_:
                                       "weights are unavailable offline (SURVEY.md 8c): not built")
 
     # ---------------------------------------------------------------- hot path
-    def train_step(self, x, y, scheduler_step_on="batch", keep_mask=None, sync=True):
+    def train_step(self, x, y, scheduler_step_on="batch", keep_mask=None, sync=True, cuda_graph=False):
         """One optimisation step on a HOST (or prefetched device) batch; returns
         (loss: float, metrics: ndarray, size).  ``sync=False`` returns the loss and the metrics
         as 0-dim DEVICE tensors instead, so the caller chooses when to pay the device->host read
         (the reference reads ``loss.item()`` and every metric right here, src/framework.py:305-312,
-        which drains the GPU queue twice per step)."""
+        which drains the GPU queue twice per step).  ``cuda_graph=True`` replays the whole step
+        body from a CUDA graph captured per batch shape (``graphs.GraphedTrainStep``: the
+        launch-bound FashionMNIST configuration; bit-identical to the eager step)."""
         x, y = self.data_forming(x, y, phase="train")
+        if cuda_graph:
+            if keep_mask is not None:
+                raise ValueError("keep_mask batches are not replayed from a CUDA graph")
+            if getattr(self, "_graphed", None) is None:
+                from .graphs import GraphedTrainStep
+                self._graphed = GraphedTrainStep(self)
+            loss, info = self._graphed.step(x, y)
+            if scheduler_step_on == "batch" and self.scheduler is not None:
+                self.scheduler.step()
+            if sync:
+                return loss.item(), np.array([float(m) for m in info]), len(y)
+            return loss, info, len(y)
         x, y = self.to_device(x), self.to_device(y)
         self.optimizer.zero_grad()
         y_pred = self.model(x) if keep_mask is None else self.model(x, keep_mask=keep_mask)
@@ -239,7 +253,8 @@ class Model_:
                             gradient_accumulation_steps=kwargs["gradient_accumulation_steps"],
                             scheduler_step_on=scheduler_step_on)
                     else:
-                        loss, info, size = self.train_step(x, y, scheduler_step_on)
+                        loss, info, size = self.train_step(x, y, scheduler_step_on,
+                                                           cuda_graph=bool(kwargs.get("cuda_graph", False)))
                     cbs.on_backward_end(step["number"])
                     step["size"], step["loss"], step["metrics"] = size, loss, info
                     if math.isnan(loss):

@@ -1,0 +1,106 @@
+"""CUDA-graph capture of a whole training step for the launch-bound configurations.
+
+The FashionMNIST models (reference ``train_fashionmnist.py``: four 14x14 views, batch 256,
+``torch.optim.SGD``) spend 110 MFLOP per sample in ~200 small kernels: neither roofline is
+reachable, the step is bounded by launch latency and by the Python / autograd dispatch between the
+launches.  ``GraphedTrainStep`` records the step body of
+``Model_.train_step`` -- ``optimizer.zero_grad()``, forward, ``compute_loss``, ``backward()``,
+``optimizer.step()``, metrics (reference ``src/framework.py:262-312``) -- once per batch shape into
+a ``torch.cuda.CUDAGraph`` and replays it with one launch per step (forward, loss and backward go
+through ``model.forward_backward``, which makes the same engine calls without the autograd
+engine); the host only copies the batch into the graph's static input buffers.  Results are bit-identical to the eager step: the same
+kernels run in the same order on the same addresses.
+
+What is baked into a captured graph, and therefore part of its cache key: the batch shapes /
+dtypes and every scalar hyper-parameter of the optimiser's ``param_groups`` (a scheduler that moves
+the learning rate -- ``ReduceLROnPlateau`` in ``train_fashionmnist.py:118`` -- triggers one
+re-capture).  Optimisers that compute per-step scalars on the HOST from a step counter
+(``FusedAdamW`` / ``BertAdam`` bias corrections and warm-up, ``torch.optim.Adam`` without
+``capturable=True``) cannot be replayed and are rejected.  The very first step always runs eagerly:
+it creates the optimiser state (momentum buffers) the captured step updates in place.
+"""
+import torch
+
+
+def _flatten(x):
+    if isinstance(x, (tuple, list)):
+        return list(x), True
+    return [x], False
+
+
+class GraphedTrainStep:
+    def __init__(self, trainer):
+        self.trainer = trainer
+        self.entries = {}
+        self._warm = False
+        if not hasattr(trainer.model, "forward_backward"):
+            raise TypeError("the model must provide forward_backward(x, y) (the fusion / FashionMNIST "
+                            "models do) to be replayed from a CUDA graph")
+        opt = trainer.optimizer
+        name = type(opt).__name__
+        if name in ("FusedAdamW", "BertAdam"):
+            raise ValueError(f"{name} derives per-step scalars from a host-side step counter; a "
+                             "replayed graph would freeze them -- use the eager step")
+        for g in opt.param_groups:
+            if "capturable" in g and not g["capturable"] and name != "SGD":
+                raise ValueError(f"{name} must be built with capturable=True to be replayed from a CUDA graph")
+
+    def _key(self, xs, y):
+        shapes = tuple(None if t is None else (tuple(t.shape), t.dtype) for t in xs)
+        hyper = tuple(tuple(sorted((k, v) for k, v in g.items()
+                                   if isinstance(v, (int, float, bool)) or v is None))
+                      for g in self.trainer.optimizer.param_groups)
+        return shapes, tuple(y.shape), y.dtype, hyper
+
+    def _body(self, x, y):
+        tr = self.trainer
+        tr.optimizer.zero_grad()
+        # forward + loss + backward through the model's autograd-free entry point: the autograd
+        # engine's stream bookkeeping makes the capture depend on uncaptured work
+        # (cudaErrorStreamCaptureIsolation), the engine calls themselves are plain launches
+        y_pred, loss = tr.model.forward_backward(x, y)
+        tr.optimizer.step()
+        with torch.no_grad():
+            mets = [m(y_pred, y, False, True) for m in tr.metrics]
+        return loss, mets
+
+    def _capture(self, xs, is_seq, y):
+        dev = self.trainer.device
+        sx = [None if t is None else torch.empty_like(t, device=dev) for t in xs]
+        sy = torch.empty_like(y, device=dev)
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        try:
+            with torch.cuda.graph(graph):
+                loss, mets = self._body(sx if is_seq else sx[0], sy)
+        except RuntimeError as e:  # a metric / model that reads back to the host under capture
+            raise RuntimeError("the training step cannot be captured in a CUDA graph (a host "
+                               f"read-back or allocation inside the step?): {e}") from e
+        bad = [m for m in mets if not torch.is_tensor(m)]
+        if bad:
+            raise TypeError("metrics must return device tensors to be replayed from a CUDA graph")
+        return graph, sx, sy, loss, mets
+
+    def step(self, x, y):
+        """x, y: the shaped batch (host or device tensors).  Returns (loss, metrics) as 0-dim
+        device tensors that the NEXT replay overwrites: read them before calling again."""
+        xs, is_seq = _flatten(x)
+        if not self._warm:  # first step: eager (creates the optimiser state)
+            self._warm = True
+            tr = self.trainer
+            return self._body(tr.to_device(x), tr.to_device(y))
+        key = self._key(xs, y)
+        ent = self.entries.get(key)
+        if ent is None:
+            ent = self.entries[key] = self._capture(xs, is_seq, y)
+        graph, sx, sy, loss, mets = ent
+        for dst, src in zip(sx, xs):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        sy.copy_(y, non_blocking=True)
+        graph.replay()
+        # replays do not move tensor version counters: caches keyed on them are stale now
+        inval = getattr(self.trainer.model, "invalidate_shadow", None)
+        if inval is not None:
+            inval()
+        return loss, mets

@@ -12,6 +12,9 @@ from ._backend import _lib, ops
 
 
 def _owner_of(y_pred):
+    owner = getattr(y_pred, "_mmu_owner", None)   # set by model.forward_backward (no autograd graph)
+    if owner is not None:
+        return owner
     fn = getattr(y_pred, "grad_fn", None)
     return getattr(fn, "model", None) if fn is not None else None
 

@@ -463,6 +463,31 @@ class FlavaFusionTransfomer(nn.Module):
             return _FlavaForward.apply(anchor, self, img, txt, idx_img, idx_txt, keep_mask)
         return self._engine_forward(img, txt, idx_img, idx_txt, keep_mask, training=False)
 
+    def _train_engine(self, x):
+        img, txt = x
+        saved = self._engine_forward(img, txt, None, None, None, training=True)
+        return saved, self._logits_train
+
+    @torch.no_grad()
+    def forward_backward(self, x, y):
+        """``y_hat = model(x); loss = model.compute_loss(y_hat, y); loss.backward()`` of a training
+        step in one call that bypasses the autograd engine: engine forward, fused CE + gradient
+        epilogue, engine backward into the flat gradient buffer -- the same kernels in the same
+        order.  This is the form a CUDA graph can capture (``graphs.GraphedTrainStep``): the
+        autograd engine's cross-stream bookkeeping creates dependencies on uncaptured work.
+        Returns (logits, loss)."""
+        saved, logits = self._train_engine(x)
+        y2 = y.reshape(logits.shape[0], -1)
+        if y2.shape[1] not in (1, logits.shape[1]):
+            raise ValueError("labels must be (B,) or (B, E)")
+        N, E, _ = logits.shape
+        dl, _, _, accum = ops.heads_uncertainty_epilogue(logits, y2.contiguous(), 0,
+                                                         grad_scale=1.0 / (N * E), want_grad=True)
+        self._remember_epilogue(logits, 0, accum)
+        self._engine_backward(saved, dl)
+        logits._mmu_owner = self   # lets metrics.acc reuse this epilogue's accumulator
+        return logits, _loss_from_accum(accum)
+
     def _remember_epilogue(self, y_hat, mode, accum):
         self._last_epi = (y_hat.data_ptr(), y_hat._version, tuple(y_hat.shape), mode, accum)
 
@@ -597,6 +622,13 @@ class MIMOTransfomer(FlavaFusionTransfomer):
         self._group_pool = c
         tokens = x.reshape(b, e * c, h * w)
         return super().forward((tokens, None), keep_mask=keep_mask)
+
+    def _train_engine(self, x):
+        b, e, c, h, w = x.shape
+        if e != self.out_dim or h * w != self._dims["d_img"]:
+            raise ValueError(f"expected (B, {self.out_dim}, C, H, W) with H*W = {self._dims['d_img']}")
+        self._group_pool = c
+        return super()._train_engine((x.reshape(b, e * c, h * w), None))
 
     def forward_variants(self, x, variants):
         raise NotImplementedError("token-subset variants are a FLAVA-fusion sweep; the FashionMNIST "

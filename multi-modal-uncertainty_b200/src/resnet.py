@@ -236,6 +236,12 @@ class MIMOResNet(nn.Module):
             return _ResNetForward.apply(next(self.parameters()), self, x)
         return self._engine_forward(x, training=self.training)[-1]
 
+    def _train_engine(self, x):
+        saved = self._engine_forward(x, training=True)
+        return saved, saved[-1]
+
+    forward_backward = FlavaFusionTransfomer.forward_backward
+
     # loss / metric plumbing is the fusion models' (identical semantics, src/model.py:102-112)
     _remember_epilogue = FlavaFusionTransfomer._remember_epilogue
     cached_epilogue = FlavaFusionTransfomer.cached_epilogue

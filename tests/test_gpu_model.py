@@ -524,3 +524,64 @@ def test_mimo_resnet_tensor_core_path(mmu, golden):
         opt.step()
         losses.append(float(loss.detach()))
     assert losses[-1] < losses[0]
+
+
+def _graph_vs_eager(mmu, precision, steps=5):
+    g = torch.Generator().manual_seed(7)
+    B, E, C = 64, 4, 10
+    batches = [(torch.rand(B, 4, 1, 14, 14, generator=g), torch.randint(0, C, (B,), generator=g))
+               for _ in range(steps)]
+    out = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(11)
+        m = mmu.MIMOResNet(num_channels=1, emb_dim=4, out_dim=E, num_classes=C, precision=precision)
+        opt = torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+        tr = mmu.Model_(m, opt, None, lambda x, y, phase="train": (x, y.unsqueeze(1).repeat(1, E)),
+                        metrics=[mmu.acc], verbose=False)
+        tr.to(torch.device("cuda"))
+        m.train()
+        logs = []
+        for i, (x, y) in enumerate(batches):
+            if i == 3:
+                for grp in opt.param_groups:          # what ReduceLROnPlateau does between epochs
+                    grp["lr"] = 0.01
+            loss, info, size = tr.train_step(x, y, cuda_graph=(mode == "graph"))
+            logs.append((loss, float(info[0]), size))
+        m.eval()
+        with torch.no_grad():
+            ev = m(batches[0][0].cuda()).cpu()         # eval forward right after the last replay
+        out[mode] = (logs, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}, ev,
+                     getattr(tr, "_graphed", None))
+    return out
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_train_step_equals_eager(mmu, precision):
+    """Model_.train_step(cuda_graph=True) (graphs.GraphedTrainStep: zero_grad, forward, loss,
+    backward, SGD step and metrics replayed from one CUDA graph per batch shape) against the eager
+    step on the FashionMNIST configuration (four views, SGD momentum 0.9 as in
+    train_fashionmnist.py:113): same losses / accuracies, same parameters and BatchNorm statistics
+    after several steps, one re-capture when the learning rate moves, and an eval forward after the
+    last replay that sees the updated weights."""
+    out = _graph_vs_eager(mmu, precision)
+    (le, sde, eve, _), (lg, sdg, evg, graphed) = out["eager"], out["graph"]
+    assert graphed is not None and len(graphed.entries) == 2       # lr 0.05 and lr 0.01
+    # the weight-gradient GEMMs are split-K with atomic accumulation: runs agree to rounding
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    for (l0, a0, s0), (l1, a1, s1) in zip(le, lg):
+        assert s0 == s1 and abs(l0 - l1) <= tol * max(1.0, abs(l0)) and abs(a0 - a1) <= (0.5 if precision == "fp32" else 2.0)
+    for k in sde:   # absolute on small tensors (BatchNorm biases are ~1e-4 after five steps)
+        a, b = sdg[k].double(), sde[k].double()
+        assert float((a - b).abs().max()) <= tol * 10 * max(1.0, float(b.abs().max())), k
+    assert int(sdg["bn1.num_batches_tracked"]) == len(le)
+    assert float((evg.double() - eve.double()).abs().max()) <= tol * 10 * max(1.0, float(eve.abs().max()))
+
+
+def test_cuda_graph_rejects_host_stepped_optimizers(mmu):
+    m = mmu.MIMOTransfomer(out_dim=2, num_classes=3, hidden_size=48, multimodal_num_hidden_layers=1,
+                           multimodal_num_attention_heads=2).cuda()
+    tr = mmu.Model_(m, mmu.FusedAdamW(m.parameters(), lr=1e-3), None, lambda x, y, phase="train": (x, y),
+                    verbose=False)
+    tr.to(torch.device("cuda"))
+    with pytest.raises(ValueError):
+        tr.train_step(torch.rand(4, 4, 1, 14, 14), torch.randint(0, 3, (4, 2)), cuda_graph=True)

@@ -46,6 +46,25 @@ for name, make, opt_fn in (
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 30
     out[name] = {"ms_per_step": round(ms, 3), "samples_per_s": round(B / ms * 1e3, 1), "loss": float(loss.detach())}
+    if isinstance(opt, torch.optim.SGD):
+        # the same step through the reference-protocol trainer, replayed from a CUDA graph
+        # (graphs.GraphedTrainStep); inputs come from pinned host memory every step
+        tr = mmu.Model_(m, opt, None, lambda a, b, phase="train": (a, b), metrics=[mmu.acc], verbose=False)
+        tr.to(dev)
+        xh, yh = x.pin_memory(), yt.pin_memory()
+        for mode in (False, True):
+            for _ in range(5):
+                tr.train_step(xh, yh, sync=False, cuda_graph=mode)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(30):
+                l, info, _ = tr.train_step(xh, yh, sync=False, cuda_graph=mode)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 30
+            out[name + ("_trainer_graph" if mode else "_trainer_eager")] = {
+                "ms_per_step": round(ms, 3), "samples_per_s": round(B / ms * 1e3, 1), "loss": float(l),
+                "acc": float(info[0])}
 
 # CPU oracle port of the ResNet train step (fp32, all host threads), bounded: 2 steps
 from oracle import resnet
