@@ -182,9 +182,11 @@ __global__ void unpad_add_kernel(const float* __restrict__ dwp, int co, int K, i
 }
 
 // ---- tap-major columns: cols[row][tap * Ci + ci].  A thread moves 8 consecutive channels of one
-// tap: one 16-byte load from the bf16 NHWC input, one 16-byte store (both fully coalesced).
+// tap: one 16-byte load from the bf16 NHWC input (two from an fp32 input, rounded here), one
+// 16-byte store (all fully coalesced).
+template <typename TA>
 __global__ void __launch_bounds__(256)
-im2col_tm_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int Ci, int k, int stride, int pad,
+im2col_tm_kernel(const TA* __restrict__ in, int B, int H, int W, int Ci, int k, int stride, int pad,
                  int Ho, int Wo, __nv_bfloat16* __restrict__ cols) {
   const int kk = k * k, C8 = Ci >> 3;
   const size_t K = static_cast<size_t>(Ci) * kk;
@@ -199,8 +201,18 @@ im2col_tm_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int 
     const int ky = tap / k, kx = tap - ky * k;
     const int y = yo * stride + ky - pad, x = xo * stride + kx - pad;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (y >= 0 && y < H && x >= 0 && x < W)
-      v = *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + y) * W + x) * Ci + c8 * 8);
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const TA* src = in + ((static_cast<size_t>(b) * H + y) * W + x) * Ci + c8 * 8;
+      if constexpr (sizeof(TA) == 2) {
+        v = *reinterpret_cast<const uint4*>(src);
+      } else {
+        const float4 lo = *reinterpret_cast<const float4*>(src), hi = *reinterpret_cast<const float4*>(src + 4);
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(lo.x, lo.y), t1 = __floats2bfloat162_rn(lo.z, lo.w);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(hi.x, hi.y), t3 = __floats2bfloat162_rn(hi.z, hi.w);
+        v.x = *reinterpret_cast<uint32_t*>(&t0); v.y = *reinterpret_cast<uint32_t*>(&t1);
+        v.z = *reinterpret_cast<uint32_t*>(&t2); v.w = *reinterpret_cast<uint32_t*>(&t3);
+      }
+    }
     *reinterpret_cast<uint4*>(cols + row * K + static_cast<size_t>(tap) * Ci + c8 * 8) = v;
   }
 }
@@ -597,6 +609,8 @@ struct Net {
   ConvBn c1[4], c2[4], ds;  // four BasicBlocks; ds belongs to block 2 (layer2.0)
   long long fc_w, fc_b;
   long long n_params, n_stats;
+  long long n_wperm = 0;  // elements of the tap-major bf16 weight copies (3x3 layers with ci % 8 == 0)
+  long long max_wk = 0;   // largest co * K among them (weight-gradient scratch)
 };
 
 struct Tab {
@@ -663,6 +677,18 @@ int build(const ResNetConfig& c, Net* net, ParamEntry* ptab, int pmax, ParamEntr
       ConvBn tmpd{};
       bn(pre, planes[i], &tmpd);
       net->ds.g = tmpd.g; net->ds.b = tmpd.b; net->ds.stat = tmpd.stat;
+    }
+  }
+  // tap-major copies for the tensor-core mode (every 3x3 layer but the 4-channel stem)
+  net->n_wperm = 0;
+  net->max_wk = 0;
+  for (int i = 0; i < 4; ++i) {
+    for (ConvBn* l : {&net->c1[i], &net->c2[i]}) {
+      if (l->ci % 8 != 0) continue;
+      const long long wk = static_cast<long long>(l->co) * l->ci * l->k * l->k;
+      l->wp = net->n_wperm;
+      net->n_wperm += (wk + 63) / 64 * 64;
+      if (wk > net->max_wk) net->max_wk = wk;
     }
   }
   net->fc_w = p.add("output_layer.fc.weight", c.E * c.C, 128);
@@ -753,8 +779,8 @@ void carve(const ResNetConfig& c, const Net& n, int training, void* base, Ws* w)
   }
   w->pad_w = nullptr;
   w->pad_dw = nullptr;
-  w->wperm = nullptr;
-  w->dwperm = nullptr;
+  w->wperm = n.n_wperm > 0 ? b.take<void>(n.n_wperm * 2) : nullptr;
+  w->dwperm = (training && n.max_wk > 0) ? b.take<float>(n.max_wk * 4) : nullptr;
   w->bytes = b.off;
 }
 
@@ -790,9 +816,10 @@ bool use_tc(const Ctx& x, const ConvBn& l) { return x.shadow != nullptr && (l.ci
 bool use_tc_padded(const Ctx& x, const ConvBn& l, int in_nchw) {
   return x.shadow != nullptr && (l.ci * l.k * l.k) % 8 != 0 && in_nchw && x.w.pad_w != nullptr;
 }
-// tap-major layer: 3x3 (or larger) convolution with bf16 activations and a re-ordered weight copy
+// tap-major layer: 3x3 (or larger) convolution on the tensor-core path with a re-ordered weight
+// copy (bf16 activations in the image encoder, fp32 activations in the FashionMNIST engine)
 bool use_tm(const Ctx& x, const ConvBn& l) {
-  return x.act16 && l.k > 1 && l.wp >= 0 && x.w.wperm != nullptr && l.ci % 8 == 0;
+  return x.shadow != nullptr && l.k > 1 && l.wp >= 0 && x.w.wperm != nullptr && l.ci % 8 == 0;
 }
 const __nv_bfloat16* wbf(const Ctx& x, const ConvBn& l) {
   if (use_tm(x, l)) return static_cast<const __nv_bfloat16*>(x.w.wperm) + l.wp;
@@ -815,8 +842,12 @@ int tc_columns(const Ctx& x, const ConvBn& l, const float* in, int in_nchw, __nv
     return cast_f32_to_bf16(in, cols, M * K, x.st);
   }
   if (!in_nchw && use_tm(x, l)) {
-    im2col_tm_kernel<<<blocks_for(M * (K / 8), 256), 256, 0, x.st>>>(
-        as16(in), x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
+    if (x.act16)
+      im2col_tm_kernel<bf16_t><<<blocks_for(M * (K / 8), 256), 256, 0, x.st>>>(
+          as16(in), x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
+    else
+      im2col_tm_kernel<float><<<blocks_for(M * (K / 8), 256), 256, 0, x.st>>>(
+          in, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
     RN_CHECK_LAUNCH();
     return 0;
   }
