@@ -89,17 +89,29 @@ class PosthocMeter:
     packed-variant logits of each batch, it keeps the Pearson sufficient statistics and the
     per-variant accuracy counts on the GPU; ``compute()`` reads 1.1 KB back."""
 
-    def __init__(self, device, n_repeats=20):
+    def __init__(self, device, n_repeats=20, auc=False):
+        """``auc=True`` (binary heads: hateful memes) also keeps every sample's head-mean p(class 1)
+        per variant on the device -- 4 bytes per sample-variant -- so that ``compute()`` can rank
+        them: the ``AUC_table`` of reference ``notebooks/hatefulmeme_robustness.py:22-41``."""
         import ctypes as C
         self.n_repeats = n_repeats
         self.accum = torch.zeros(C.sizeof(_lib.PosthocAccum), dtype=torch.uint8, device=device)
+        self.auc = auc
+        self._p1, self._labels = [], []
 
     def reset(self):
         self.accum.zero_()
+        self._p1, self._labels = [], []
 
     def update(self, logits_vbec, labels, want_p_true=False):
-        _, p_true = ops.posthoc_scoring(logits_vbec.contiguous(), labels.reshape(-1).contiguous(),
-                                        self.n_repeats, accum=self.accum, want_p_true=want_p_true)
+        logits_vbec, labels = logits_vbec.contiguous(), labels.reshape(-1).contiguous()
+        _, p_true = ops.posthoc_scoring(logits_vbec, labels, self.n_repeats, accum=self.accum,
+                                        want_p_true=want_p_true)
+        if self.auc:
+            if logits_vbec.shape[-1] != 2:
+                raise ValueError("the AUROC table is defined for binary heads (C = 2)")
+            self._p1.append(self.class_prob(logits_vbec, 1))
+            self._labels.append(labels)
         return p_true
 
     def class_prob(self, logits_vbec, cls=1):
@@ -123,6 +135,10 @@ class PosthocMeter:
             dist.all_reduce(cnt, group=group)
             words[:10] = dbl.view(torch.int64)
             words[10:] = cnt
+            if self.auc and self._p1:   # rank statistics need every sample: gather the scores
+                from .parallel import all_gather_rows
+                self._p1 = [all_gather_rows(torch.cat(self._p1), group)]
+                self._labels = [all_gather_rows(torch.cat(self._labels), group)]
 
     def compute(self):
         import ctypes as C
@@ -141,6 +157,11 @@ class PosthocMeter:
                    acc_image_control=float(acc[3:3 + r].mean()) if r else float("nan"),
                    acc_text_control=float(acc[3 + r:].mean()) if r else float("nan"),
                    acc_per_variant=acc)
+        if self.auc and self._p1:
+            tab = auc_table(torch.cat(self._labels), torch.cat(self._p1))
+            out.update(auc_per_variant=tab["AUC"], auc_full=tab["full"], auc_image=tab["image"],
+                       auc_text=tab["text"], auc_image_control=tab["image_control"],
+                       auc_text_control=tab["text_control"])
         return out
 
 

@@ -43,6 +43,25 @@ def all_reduce_accum(accum, group=None):
     return accum
 
 
+def all_gather_rows(t, group=None):
+    """Concatenation over ranks (rank order) of per-rank tensors that differ in their number of
+    rows: what a rank statistic over the whole evaluation set needs (AUROC / Kendall tau do not
+    decompose over sample shards, unlike the histogram accumulators).  Rows are padded to the
+    longest shard for one ``all_gather``; 4 bytes per sample-variant cross NVLink."""
+    _, nranks = world(group)
+    if nranks == 1:
+        return t
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(nranks)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s) for s in sizes]
+    pad = torch.zeros((max(sizes),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    parts = [torch.empty_like(pad) for _ in sizes]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:k] for p, k in zip(parts, sizes)])
+
+
 def all_reduce_ranges(flat, ranges, group=None, async_op=False):
     """Sum-all-reduce the element ranges [(b, e), ...] of a flat buffer; returns work handles."""
     works = []

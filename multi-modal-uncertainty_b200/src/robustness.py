@@ -98,7 +98,8 @@ def run_transformer_robustness(model, batches, device, n_repeats=20, ref_bug_com
     table) accumulated on device, so ``collect=False`` runs need no (S, 43, K, C) dump at all."""
     model.eval()
     meters, preds, labels = None, [], []
-    scorer = PosthocMeter(device, n_repeats) if posthoc else None
+    # binary heads also get the notebooks' AUROC table (hatefulmeme_robustness.py:22-41)
+    scorer = PosthocMeter(device, n_repeats, auc=model.num_classes == 2) if posthoc else None
     for (img, txt), y in batches:
         img, txt, y = img.to(device), txt.to(device), y.to(device).reshape(-1)
         if variants_fn is None:

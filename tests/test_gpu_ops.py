@@ -295,6 +295,12 @@ def test_rank_statistics_match_reference_notebooks(mmu, golden):
     tab2 = mmu.metrics.auc_table(c["hm_labels"], p1)
     assert np.abs(tab2["AUC"] - c["hm_auc"].numpy()).max() < 2e-3
     assert mmu.metrics.auroc(c["hm_labels"], p1[:, 0].contiguous()) == pytest.approx(tab2["AUC"][0], abs=0)
+    # the same table accumulated batch by batch by the sweep's meter (PosthocMeter(auc=True))
+    acc_meter = mmu.metrics.PosthocMeter("cuda", n, auc=True)
+    for lo in range(0, lg.shape[1], 96):
+        acc_meter.update(lg[:, lo:lo + 96].contiguous(), c["hm_labels"][lo:lo + 96].long().cuda())
+    res = acc_meter.compute()
+    assert np.array_equal(res["auc_per_variant"], tab2["AUC"]) and res["auc_full"] == tab2["full"]
     with pytest.raises(ValueError):
         mmu.metrics.auroc(torch.zeros(8), torch.rand(8))
 

@@ -343,6 +343,14 @@ def _gloo_worker(rank, world, port, out_dir):
     assert torch.equal(words[:10].view(torch.float64), 2 * torch.arange(10, dtype=torch.float64) + 1)
     assert int(words[10]) == 150 and int(words[11 + 3]) == 15
     assert ph.compute()["n_samples"] == 150
+    # rank statistics need every sample's score: uneven shards are gathered in rank order
+    mine = torch.arange((3 + 2 * rank) * 4, dtype=torch.float32).reshape(3 + 2 * rank, 4) + 100 * rank
+    full = par.all_gather_rows(mine)
+    want = torch.cat([torch.arange((3 + 2 * r) * 4, dtype=torch.float32).reshape(3 + 2 * r, 4) + 100 * r
+                      for r in range(world)])
+    assert torch.equal(full, want)
+    lab = par.all_gather_rows(torch.full((2 + rank,), rank, dtype=torch.int64))
+    assert lab.tolist() == [0, 0, 1, 1, 1]
     # flat-buffer owners of the MMBT path (trunk + image encoder): broadcast + gradient sum
     class Owner:
         def __init__(self, n):
