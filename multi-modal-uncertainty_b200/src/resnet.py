@@ -6,8 +6,9 @@ As in the fusion models, every parameter is an individually addressable ``nn.Par
 views ONE flat fp32 buffer (gradients likewise), and the BatchNorm running statistics are buffer
 views of one flat statistics buffer the kernels update in place; reference checkpoints load with
 ``strict=True``.  ``precision="fp32"`` (default) is the reference's arithmetic;
-``precision="bf16"`` runs every convolution but the 4-channel stem on the tcgen05 tensor-core GEMM
-(bf16 operands, fp32 accumulation, fp32 BatchNorm).  There is no CPU path.
+``precision="bf16"`` runs every convolution on the tcgen05 tensor-core GEMM (bf16 operands, fp32
+accumulation, fp32 activations and BatchNorm; 3x3 layers with tap-major columns, the 4-channel
+stem with K padded 36 -> 40).  There is no CPU path.
 """
 import ctypes as C
 import math
