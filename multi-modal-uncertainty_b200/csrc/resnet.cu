@@ -232,20 +232,25 @@ __global__ void unpad_add_kernel(const float* __restrict__ dwp, int co, int K, i
 // ---- tap-major columns: cols[row][tap * Ci + ci].  A thread moves 8 consecutive channels of one
 // tap: one 16-byte load from the bf16 NHWC input (two from an fp32 input, rounded here), one
 // 16-byte store (all fully coalesced).
-template <typename TA>
+// I: index type of the flat work index -- unsigned when it fits (every shape of the two networks):
+// the decode is six divisions per 16 bytes moved, and a 64-bit division is ~5x a 32-bit one (ncu:
+// these kernels are issue bound on exactly that, not on memory).
+template <typename TA, typename I>
 __global__ void __launch_bounds__(256)
 im2col_tm_kernel(const TA* __restrict__ in, int B, int H, int W, int Ci, int k, int stride, int pad,
                  int Ho, int Wo, __nv_bfloat16* __restrict__ cols) {
   const int kk = k * k, C8 = Ci >> 3;
   const size_t K = static_cast<size_t>(Ci) * kk;
-  const size_t total = static_cast<size_t>(B) * Ho * Wo * kk * C8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c8 = static_cast<int>(i % C8);
-    const int tap = static_cast<int>((i / C8) % kk);
-    const size_t row = i / (static_cast<size_t>(C8) * kk);
-    const int xo = static_cast<int>(row % Wo), yo = static_cast<int>((row / Wo) % Ho);
-    const int b = static_cast<int>(row / (static_cast<size_t>(Wo) * Ho));
+  const I total = static_cast<I>(B) * Ho * Wo * kk * C8;
+  for (I i = blockIdx.x * static_cast<I>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<I>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % static_cast<I>(C8));
+    const I t = i / static_cast<I>(C8);
+    const int tap = static_cast<int>(t % static_cast<I>(kk));
+    const I row = t / static_cast<I>(kk);
+    const I rowy = row / static_cast<I>(Wo);
+    const int xo = static_cast<int>(row - rowy * Wo), yo = static_cast<int>(rowy % static_cast<I>(Ho));
+    const int b = static_cast<int>(rowy / static_cast<I>(Ho));
     const int ky = tap / k, kx = tap - ky * k;
     const int y = yo * stride + ky - pad, x = xo * stride + kx - pad;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -261,22 +266,24 @@ im2col_tm_kernel(const TA* __restrict__ in, int B, int H, int W, int Ci, int k, 
         v.z = *reinterpret_cast<uint32_t*>(&t2); v.w = *reinterpret_cast<uint32_t*>(&t3);
       }
     }
-    *reinterpret_cast<uint4*>(cols + row * K + static_cast<size_t>(tap) * Ci + c8 * 8) = v;
+    *reinterpret_cast<uint4*>(cols + static_cast<size_t>(row) * K + static_cast<size_t>(tap) * Ci + c8 * 8) = v;
   }
 }
 // din[pixel][ci .. ci+8) (+)= sum over the taps that reach the pixel of dcols[row][tap * Ci + ci ..]
+template <typename I>
 __global__ void __launch_bounds__(256)
 col2im_tm_kernel(const __nv_bfloat16* __restrict__ dcols, int B, int H, int W, int Ci, int k, int stride,
                  int pad, int Ho, int Wo, float* __restrict__ dx, int accumulate) {
   const int kk = k * k, C8 = Ci >> 3;
   const size_t K = static_cast<size_t>(Ci) * kk;
-  const size_t total = static_cast<size_t>(B) * H * W * C8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c8 = static_cast<int>(i % C8);
-    const size_t pix = i / C8;
-    const int x = static_cast<int>(pix % W), y = static_cast<int>((pix / W) % H);
-    const int b = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+  const I total = static_cast<I>(B) * H * W * C8;
+  for (I i = blockIdx.x * static_cast<I>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<I>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % static_cast<I>(C8));
+    const I pix = i / static_cast<I>(C8);
+    const I pixy = pix / static_cast<I>(W);
+    const int x = static_cast<int>(pix - pixy * W), y = static_cast<int>(pixy % static_cast<I>(H));
+    const int b = static_cast<int>(pixy / static_cast<I>(H));
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int ky = 0; ky < k; ++ky) {
       const int ty = y + pad - ky;
@@ -298,7 +305,7 @@ col2im_tm_kernel(const __nv_bfloat16* __restrict__ dcols, int B, int H, int W, i
         }
       }
     }
-    float* o = dx + pix * Ci + c8 * 8;
+    float* o = dx + static_cast<size_t>(pix) * Ci + c8 * 8;
     float4 lo = make_float4(acc[0], acc[1], acc[2], acc[3]), hi = make_float4(acc[4], acc[5], acc[6], acc[7]);
     if (accumulate) {
       const float4 a = *reinterpret_cast<const float4*>(o), c = *reinterpret_cast<const float4*>(o + 4);
@@ -914,11 +921,19 @@ int tc_columns(const Ctx& x, const ConvBn& l, const float* in, int in_nchw, __nv
     return cast_f32_to_bf16(in, cols, M * K, x.st);
   }
   if (!in_nchw && use_tm(x, l)) {
-    if (x.act16)
-      im2col_tm_kernel<bf16_t><<<blocks_for(M * (K / 8), 256), 256, 0, x.st>>>(
+    const bool small = M * (K / 8) + 256ull * 16 * sm_count() < (1ull << 32);  // grid-stride overshoot included
+    const int nb = blocks_for(M * (K / 8), 256);
+    if (x.act16 && small)
+      im2col_tm_kernel<bf16_t, unsigned><<<nb, 256, 0, x.st>>>(
           as16(in), x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
+    else if (x.act16)
+      im2col_tm_kernel<bf16_t, size_t><<<nb, 256, 0, x.st>>>(
+          as16(in), x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
+    else if (small)
+      im2col_tm_kernel<float, unsigned><<<nb, 256, 0, x.st>>>(
+          in, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
     else
-      im2col_tm_kernel<float><<<blocks_for(M * (K / 8), 256), 256, 0, x.st>>>(
+      im2col_tm_kernel<float, size_t><<<nb, 256, 0, x.st>>>(
           in, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, cols);
     RN_CHECK_LAUNCH();
     return 0;
@@ -1105,8 +1120,11 @@ int conv_bn_bwd(const Ctx& x, const ConvBn& l, const CbWs& o, const float* in, i
       GemmEpilogue e = store_epi(reinterpret_cast<float*>(dcols), K, nullptr);
       e.out_bf16 = 1;
       RN_TRY(gemm_bf16_launch(dt, l.co, wbf(x, l), K, q, e, x.st));
-      if (use_tm(x, l))
-        col2im_tm_kernel<<<blocks_for(nin / 8, 256), 256, 0, x.st>>>(
+      if (use_tm(x, l) && nin / 8 + 256ull * 16 * sm_count() < (1ull << 32))
+        col2im_tm_kernel<unsigned><<<blocks_for(nin / 8, 256), 256, 0, x.st>>>(
+            dcols, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, din, din_accumulate);
+      else if (use_tm(x, l))
+        col2im_tm_kernel<size_t><<<blocks_for(nin / 8, 256), 256, 0, x.st>>>(
             dcols, x.c.B, l.hin, l.hin, l.ci, l.k, l.stride, l.pad, l.hout, l.hout, din, din_accumulate);
       else
         col2im_kernel<__nv_bfloat16><<<blocks_for(nin, 256), 256, 0, x.st>>>(
