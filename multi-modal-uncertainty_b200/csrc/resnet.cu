@@ -473,7 +473,10 @@ __global__ void bn_apply_kernel(const TA* __restrict__ t, const float* __restric
                                 int relu, TA* __restrict__ out, size_t n4, int C) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>((i * 4) % C);
+    // channel of the vector: a 32-bit modulo when the element index fits (a 64-bit one costs more
+    // instructions than the rest of the iteration)
+    const int c = n4 < (1ull << 30) ? static_cast<int>((static_cast<unsigned>(i) * 4u) % static_cast<unsigned>(C))
+                                    : static_cast<int>((i * 4) % C);
     const float4 v = ld4(t + 4 * i);
     const float4 mu = *reinterpret_cast<const float4*>(mean + c);
     const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
@@ -595,7 +598,10 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dyb, const TA* __r
   const double invM = 1.0 / M;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>((i * 4) % C);
+    // channel of the vector: a 32-bit modulo when the element index fits (a 64-bit one costs more
+    // instructions than the rest of the iteration)
+    const int c = n4 < (1ull << 30) ? static_cast<int>((static_cast<unsigned>(i) * 4u) % static_cast<unsigned>(C))
+                                    : static_cast<int>((i * 4) % C);
     const float4 d = *reinterpret_cast<const float4*>(dyb + 4 * i);
     const float4 tv = ld4(t + 4 * i);
     const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
