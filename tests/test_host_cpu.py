@@ -421,3 +421,38 @@ def test_mmbt_state_dict_keys_order_and_strict_load(mmu, golden):
         assert ind == [int(i) for i in d["indices"]]  # bit-exact with the reference's draw
     with pytest.raises(mmu._lib.MMUError):  # no CPU path
         m(c["txt"], c["mask"], c["segment"], c["img_tokens"])
+
+
+def test_graphed_train_step_host_logic(mmu):
+    """graphs.GraphedTrainStep without a GPU: what it refuses to capture and what re-captures.
+    (The capture itself is exercised by tests/test_gpu_model.py::test_cuda_graph_train_step_equals_eager.)"""
+    import types
+    G = mmu.graphs.GraphedTrainStep
+
+    class WithFB(torch.nn.Linear):
+        def forward_backward(self, x, y):
+            raise AssertionError("not reached")
+
+    net = WithFB(3, 2)
+    sgd = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9)
+    tr = types.SimpleNamespace(model=net, optimizer=sgd, metrics=[], device=torch.device("cpu"))
+    g = G(tr)
+    x, y = torch.zeros(4, 3), torch.zeros(4, dtype=torch.long)
+    k0 = g._key([x], y)
+    assert g._key([x], y) == k0
+    assert g._key([torch.zeros(5, 3)], torch.zeros(5, dtype=torch.long)) != k0      # batch shape
+    assert g._key([x.double()], y) != k0                                              # dtype
+    sgd.param_groups[0]["lr"] = 0.05                                                  # ReduceLROnPlateau
+    assert g._key([x], y) != k0
+    assert g._key([x, None], y)[0][1] is None                                         # absent modality
+    # a model without the autograd-free entry point, optimisers with host-side step scalars
+    with pytest.raises(TypeError):
+        G(types.SimpleNamespace(model=torch.nn.Linear(3, 2), optimizer=sgd, metrics=[], device=None))
+    FusedAdamW = type("FusedAdamW", (), {"param_groups": []})
+    with pytest.raises(ValueError):
+        G(types.SimpleNamespace(model=net, optimizer=FusedAdamW(), metrics=[], device=None))
+    adam = torch.optim.Adam(net.parameters(), lr=1e-3)           # capturable=False by default
+    with pytest.raises(ValueError):
+        G(types.SimpleNamespace(model=net, optimizer=adam, metrics=[], device=None))
+    G(types.SimpleNamespace(model=net, optimizer=torch.optim.Adam(net.parameters(), capturable=True),
+                            metrics=[], device=None))
