@@ -302,3 +302,28 @@ def test_rank_stats_against_scipy_and_sklearn():
     assert np.isnan(rank_stats.kendalltau(np.ones(5), np.arange(5)))
     conc, disc, tx, ty = rank_stats.pair_counts([1, 2, 2, 3], [1, 3, 3, 2])
     assert (conc, disc, tx, ty) == (3, 2, 1, 1)
+
+
+def test_rank_stats_count_identities():
+    """Size-independent properties of the pair counts the device kernel is held to: the five
+    classes partition the n(n-1)/2 pairs, swapping the arguments swaps the tie counts, negating one
+    argument swaps concordant and discordant, a strictly monotone map changes nothing."""
+    from oracle import rank_stats
+    rng = np.random.RandomState(11)
+    for n in (1, 2, 5, 64, 700):
+        x = rng.randint(0, 5, size=n).astype(np.float32)
+        y = rng.randint(0, 9, size=n).astype(np.float32)
+        c, d, tx, ty = rank_stats.pair_counts(x, y)
+        tot = n * (n - 1) // 2
+        joint = c + d + tx + ty - tot
+        assert 0 <= joint <= min(tx, ty)
+        ux, cx = np.unique(x, return_counts=True)
+        assert tx == int((cx * (cx - 1) // 2).sum())                     # ties in x from multiplicities
+        assert rank_stats.pair_counts(y, x) == (c, d, ty, tx)
+        assert rank_stats.pair_counts(x, -y) == (d, c, tx, ty)
+        assert rank_stats.pair_counts(3 * x + 1, np.exp(y / 4)) == (c, d, tx, ty)
+    # AUROC is 1/2 for constant scores and 1 for a perfect ranking
+    lab = np.array([0, 1, 1, 0, 1])
+    assert rank_stats.auroc(lab, np.zeros(5)) == 0.5
+    assert rank_stats.auroc(lab, lab + 0.0) == 1.0
+    assert np.isnan(rank_stats.auroc(np.ones(4), np.arange(4.0)))        # one class only
