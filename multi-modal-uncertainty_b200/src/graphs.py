@@ -66,6 +66,8 @@ class GraphedTrainStep:
 
     def _capture(self, xs, is_seq, y):
         dev = self.trainer.device
+        if dev is None or torch.device(dev).type != "cuda":
+            raise RuntimeError("CUDA-graph capture needs the trainer on a CUDA device: call Model_.to(device) first")
         sx = [None if t is None else torch.empty_like(t, device=dev) for t in xs]
         sy = torch.empty_like(y, device=dev)
         graph = torch.cuda.CUDAGraph()
