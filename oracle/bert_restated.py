@@ -10,8 +10,12 @@ definitions -- release 0.6.2, the last one -- of exactly the classes those call 
 so that ``tests/golden/make_golden.py`` can run the UNMODIFIED reference ``src/mmbt.py`` on top
 of it and freeze golden vectors.  Parity for the MMBT path is therefore anchored on the
 reference's own call sites (embedding assembly, mask construction, ``forward_control`` index
-sampling, classifier, loss) while the BERT arithmetic is **pinned to this restatement, not to
-the absent package**: DESIGN.md says "parity unpinned (third-party)" for that part.
+sampling, classifier, loss) while the BERT arithmetic is pinned to this restatement, not to
+the absent package.  The restatement itself is held, in fp64 and to 1e-12, to
+``transformers.BertModel`` (5.5.0, installed here: the maintained successor of the absent package,
+same authors, same state-dict keys -- strict load) by
+``tests/test_oracle_golden.py::test_restated_bert_matches_transformers_bertmodel``; ``BertAdam`` has
+no surviving counterpart and stays pinned to its published definition only.
 
 Facts restated (pytorch_pretrained_bert 0.6.2, modeling.py / optimization.py):
 * ``gelu(x) = x * 0.5 * (1 + erf(x / sqrt(2)))``;

@@ -327,3 +327,37 @@ def test_rank_stats_count_identities():
     assert rank_stats.auroc(lab, np.zeros(5)) == 0.5
     assert rank_stats.auroc(lab, lab + 0.0) == 1.0
     assert np.isnan(rank_stats.auroc(np.ones(4), np.arange(4.0)))        # one class only
+
+
+def test_restated_bert_matches_transformers_bertmodel():
+    """oracle/bert_restated.py (the absent ``pytorch_pretrained_bert`` 0.6.2 restated) against the
+    maintained successor of that package, ``transformers.BertModel`` (installed: 5.5.0): same
+    state-dict keys (strict load), same embeddings / encoder / pooler arithmetic to 1e-12 in fp64
+    on a padded batch.  This pins the BERT layer arithmetic the MMBT goldens are built on to an
+    independent implementation; the call sequence on the restated side is the reference's own
+    (src/mmbt.py:103-128: additive mask (1 - m) * -10000, ``bert.encoder(..., output_all_encoded_layers
+    =False)``, ``bert.pooler``)."""
+    tf = pytest.importorskip("transformers")
+    from oracle import bert_restated as R
+    kw = dict(vocab_size=97, hidden_size=48, num_hidden_layers=3, num_attention_heads=4,
+              intermediate_size=80, max_position_embeddings=40)
+    torch.manual_seed(0)
+    m = R.BertModel(R.BertConfig(**kw)).double().eval()
+    for p in m.parameters():          # move biases / LayerNorm parameters off their trivial initial values
+        p.data.add_(torch.randn_like(p) * 0.05)
+    hf = tf.BertModel(tf.BertConfig(hidden_act="gelu", layer_norm_eps=1e-12, **kw)).double().eval()
+    missing, unexpected = hf.load_state_dict(m.state_dict(), strict=False)
+    assert not missing and not unexpected
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(1, 97, (3, 17), generator=g)
+    ids[1, 12:] = 0
+    tt = torch.randint(0, 2, (3, 17), generator=g)
+    mask = (ids != 0).long()
+    with torch.no_grad():
+        o = hf(input_ids=ids, token_type_ids=tt, attention_mask=mask)
+        ext = (1.0 - mask[:, None, None, :].double()) * -10000.0
+        last = m.encoder(m.embeddings(ids, tt), ext, output_all_encoded_layers=False)[-1]
+        pooled = m.pooler(last)
+    keep = mask.bool()
+    assert float((o.last_hidden_state - last)[keep].abs().max()) < 1e-12
+    assert float((o.pooler_output - pooled).abs().max()) < 1e-12
