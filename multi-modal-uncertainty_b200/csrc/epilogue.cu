@@ -12,7 +12,8 @@
 //    two private shared-memory slots with 1-D bulk TMA copies (cp.async.bulk + mbarrier), so every
 //    DRAM access is a full-width burst regardless of the 2020-byte sample pitch, and no
 //    block-wide barrier exists anywhere in the main loop (12 warps x 2 slots x 8 KB per SM keep
-//    ~100 KB in flight per SM);
+//    ~100 KB in flight per SM; the eval-mode kernels for E <= 5 heads hold a whole pass in
+//    registers and run 16 warps x 1 slot instead -- see HB / SS at the kernel);
 //  * G lanes cooperate on one sample (G*CPL >= C class slots; G=8, CPL=13 wastes 3 % at C=101),
 //    reductions are G-wide warp shuffles;
 //  * in train mode the gradient overwrites the slot in place and leaves through a bulk TMA store;
