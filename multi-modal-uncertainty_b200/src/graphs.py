@@ -14,7 +14,9 @@ kernels run in the same order on the same addresses.
 What is baked into a captured graph, and therefore part of its cache key: the batch shapes /
 dtypes and every scalar hyper-parameter of the optimiser's ``param_groups`` (a scheduler that moves
 the learning rate -- ``ReduceLROnPlateau`` in ``train_fashionmnist.py:118`` -- triggers one
-re-capture).  Optimisers that compute per-step scalars on the HOST from a step counter
+re-capture; after ``MAX_GRAPHS`` distinct sets new ones run eagerly, so a per-batch scheduler
+degrades to the eager step instead of capturing a graph per batch).  Optimisers that compute
+per-step scalars on the HOST from a step counter
 (``FusedAdamW`` / ``BertAdam`` bias corrections and warm-up, ``torch.optim.Adam`` without
 ``capturable=True``) cannot be replayed and are rejected.  The very first step always runs eagerly:
 it creates the optimiser state (momentum buffers) the captured step updates in place.
@@ -29,10 +31,13 @@ def _flatten(x):
 
 
 class GraphedTrainStep:
+    MAX_GRAPHS = 8  # captured graphs kept (each owns its static buffers and a memory pool)
+
     def __init__(self, trainer):
         self.trainer = trainer
         self.entries = {}
         self._warm = False
+        self._warned = False
         if not hasattr(trainer.model, "forward_backward"):
             raise TypeError("the model must provide forward_backward(x, y) (the fusion / FashionMNIST "
                             "models do) to be replayed from a CUDA graph")
@@ -94,6 +99,16 @@ class GraphedTrainStep:
         key = self._key(xs, y)
         ent = self.entries.get(key)
         if ent is None:
+            if len(self.entries) >= self.MAX_GRAPHS:
+                # a scheduler that moves the learning rate every batch (or ever-changing batch
+                # shapes) would capture a new graph per step: run such steps eagerly instead
+                if not self._warned:
+                    self._warned = True
+                    import warnings
+                    warnings.warn(f"more than {self.MAX_GRAPHS} distinct (shape, hyper-parameter) sets: "
+                                  "further new ones run eagerly instead of being captured")
+                tr = self.trainer
+                return self._body(tr.to_device(x), tr.to_device(y))
             ent = self.entries[key] = self._capture(xs, is_seq, y)
         graph, sx, sy, loss, mets = ent
         for dst, src in zip(sx, xs):
