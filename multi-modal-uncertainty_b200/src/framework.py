@@ -120,7 +120,7 @@ class Model_:
         (the reference reads ``loss.item()`` and every metric right here, src/framework.py:305-312,
         which drains the GPU queue twice per step).  ``cuda_graph=True`` replays the whole step
         body from a CUDA graph captured per batch shape (``graphs.GraphedTrainStep``: the
-        launch-bound FashionMNIST configuration; bit-identical to the eager step)."""
+        FashionMNIST configuration; same kernels, same order as the eager step)."""
         x, y = self.data_forming(x, y, phase="train")
         if cuda_graph:
             if keep_mask is not None:
