@@ -569,7 +569,7 @@ def test_cuda_graph_train_step_equals_eager(mmu, precision):
     (le, sde, eve, _), (lg, sdg, evg, graphed) = out["eager"], out["graph"]
     assert graphed is not None and len(graphed.entries) == 2       # lr 0.05 and lr 0.01
     # the weight-gradient GEMMs are split-K with atomic accumulation: runs agree to rounding
-    tol = 1e-5 if precision == "fp32" else 2e-2
+    tol = 5e-5 if precision == "fp32" else 2e-2   # fp32: ~1e-6 observed (atomic order), margin for other boxes
     for (l0, a0, s0), (l1, a1, s1) in zip(le, lg):
         assert s0 == s1 and abs(l0 - l1) <= tol * max(1.0, abs(l0)) and abs(a0 - a1) <= (0.5 if precision == "fp32" else 2.0)
     for k in sde:   # absolute on small tensors (BatchNorm biases are ~1e-4 after five steps)
