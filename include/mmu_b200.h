@@ -71,7 +71,9 @@ MMU_API int mmu_struct_size(int which);
  *   STORE      out = alpha*acc + bias                      (out: dtype if out_lp else fp32)
  *   QUICKGELU  z = alpha*acc + bias; out = z (may be NULL); out2 = z*sigmoid(1.702 z)
  *              (src/model.py:183-185 QuickGELU fused behind c_fc)
- *   RESIDUAL   out(fp32) = aux(fp32) + alpha*acc + bias    (src/model.py:210-211)
+ *   RESIDUAL   out(fp32) = aux(fp32) + alpha*acc + bias    (src/model.py:210-211); dtype MMU_F32
+ *              only -- the bf16 path returns MMU_ERR_ARG: its residual add is fused into the
+ *              LayerNorm kernel that consumes the sum
  *   DGELU      out = alpha*acc * d/dz QuickGELU(z), z = aux (dtype)
  *   ATOMIC     out(fp32) += alpha*acc, split-K `splits` ways (weight gradients)
  * seg_len > 0 remaps output rows r -> (r/seg_len)*seg_stride + seg_off + r%seg_len, which writes
@@ -100,6 +102,19 @@ MMU_API int mmu_gemm(int dtype, const void* A, long long lda, int a_mn_major, co
  * keep: int32[B,2] or NULL; `modality` (0 image, 1 text) selects the keep column. */
 MMU_API int mmu_mask_gather_tokens(const float* src, void* dst, int dst_dtype, int B, int l_src, int d,
                            const int* idx, int n_sel, const int* keep, int modality, void* stream);
+
+/* Guided / random modality dropout (BASELINE.json configs[1]; the reference only NAMES it --
+ * configs/training_guided.gin:10-18 -- so the definition is this repo's, oracle/shaping.py
+ * modality_dropout_mask): keep int32[B,2] over (image, text) for mmu_mask_gather_tokens /
+ * mmu_flava_inputs.keep.  u, r: fp32[B] uniform draws of the HOST generator (device copies).
+ * Sample b keeps both modalities unless u[b] < p_drop; then mode 0 (random) drops image when
+ * r[b] < 0.5 else text; mode 1 (guided) drops the modality with the HIGHER score
+ * (score_img[b*score_stride] vs score_txt[b*score_stride], device fp32, ties -> image) -- the
+ * scores stay on the device, e.g. the confidence column of mmu_heads_uncertainty_epilogue's
+ * scores_out for the image-only / text-only variants of the batch. */
+MMU_API int mmu_modality_keep_mask(const float* u, const float* r, const float* score_img,
+                                   const float* score_txt, int score_stride, int B, float p_drop,
+                                   int mode, int* keep, void* stream);
 
 /* Ragged batch assembly on device: replaces torch pad_sequence(batch_first=True, padding_value=0)
  * in collate_fn_flava (src/dataset.py:216-226).  packed: fp32 [offsets[B], d] rows of the batch's
@@ -167,9 +182,6 @@ MMU_API int mmu_heads_uncertainty_epilogue(const float* logits, const long long*
                                    float grad_scale, float* dlogits, int* pred_out,
                                    float* scores_out, mmu_metric_accum* accum, void* stream);
 
-/* Fused AdamW over a flat fp32 buffer: torch.optim.AdamW as configured in train.py:196-202.
- * `step` is the 1-based step count; grad_scale multiplies g first (1/world_size for DDP);
- * p_bf16 (may be NULL) receives the bf16 shadow of the updated parameters.  n % 4 == 0. */
 /* ------------------------------------------------------------------------------------------
  * Post-hoc robustness scoring on device: p(true label) from head-averaged probabilities, the
  * Pearson statistics of experimental vs mean-control delta-p per modality, and per-variant
@@ -208,6 +220,9 @@ MMU_API int mmu_pair_concordance(const float* x, const float* y, long long n, in
 MMU_API int mmu_top_truncate(const float* pred, const long long* labels, int N, int C, int top,
                      int mute_true, float* out, void* stream);
 
+/* Fused AdamW over a flat fp32 buffer: torch.optim.AdamW as configured in train.py:196-202.
+ * `step` is the 1-based step count; grad_scale multiplies g first (1/world_size for DDP);
+ * p_bf16 (may be NULL) receives the bf16 shadow of the updated parameters.  n % 4 == 0. */
 MMU_API int mmu_adamw_flat_step(float* p, const float* g, float* m, float* v, void* p_bf16, size_t n,
                         float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                         float grad_scale, void* stream);

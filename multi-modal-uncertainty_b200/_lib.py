@@ -28,7 +28,7 @@ EXPORTS = [
     "mmu_mmbt_backward", "mmu_bertadam_flat_step",
     "mmu_imgenc_param_count", "mmu_imgenc_stat_count", "mmu_imgenc_param_table", "mmu_imgenc_stat_table",
     "mmu_imgenc_workspace_bytes", "mmu_imgenc_forward", "mmu_imgenc_backward",
-    "mmu_seq_attention_fwd", "mmu_seq_attention_bwd",
+    "mmu_seq_attention_fwd", "mmu_seq_attention_bwd", "mmu_modality_keep_mask",
 ]
 
 
@@ -128,6 +128,7 @@ def _load():
     lib.mmu_resnet_forward.argtypes = [rcfgp, vp, vp, vp, vp, vp, ll, i, vp, vp]
     lib.mmu_resnet_backward.argtypes = [rcfgp, vp, vp, vp, vp, vp, ll, vp, vp, vp]
     lib.mmu_ragged_pad.argtypes = [vp, vp, vp, i, i, i, vp]
+    lib.mmu_modality_keep_mask.argtypes = [vp, vp, vp, vp, i, i, f, i, vp, vp]
     lib.mmu_posthoc_scoring.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp]
     lib.mmu_pair_concordance.argtypes = [vp, vp, ll, i, ll, ll, vp, vp]
     lib.mmu_top_truncate.argtypes = [vp, vp, i, i, i, i, vp, vp]

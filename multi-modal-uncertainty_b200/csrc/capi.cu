@@ -103,6 +103,12 @@ int mmu_mask_gather_tokens(const float* src, void* dst, int dst_dtype, int B, in
   return cast_gather(src, dst, dst_dtype, B, l_src, d, idx, n_sel, keep, modality, S(stream));
 }
 
+int mmu_modality_keep_mask(const float* u, const float* r, const float* score_img,
+                           const float* score_txt, int score_stride, int B, float p_drop, int mode,
+                           int* keep, void* stream) {
+  return modality_keep_mask(u, r, score_img, score_txt, score_stride, B, p_drop, mode, keep, S(stream));
+}
+
 int mmu_ragged_pad(const float* packed, const int* offsets, float* out, int B, int max_l, int d,
                    void* stream) {
   if (packed == nullptr || offsets == nullptr || out == nullptr) return MMU_ERR_ARG;

@@ -16,6 +16,10 @@ enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
 int cast_gather(const float* src, void* dst, int dst_dtype, int B, int l_src, int d, const int* idx,
                 int n_sel, const int* keep, int modality, cudaStream_t stream);
 int cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t stream);
+// guided / random modality-dropout keep mask int32[B,2] from host-drawn uniforms u, r (fp32[B]) and,
+// for mode 1 (guided), device-resident per-sample scores (element b at score_*[b*score_stride])
+int modality_keep_mask(const float* u, const float* r, const float* score_img, const float* score_txt,
+                       int score_stride, int B, float p_drop, int mode, int* keep, cudaStream_t stream);
 // packed ragged rows + int32 offsets[B+1] -> zero-padded (B, max_l, d) (src/dataset.py:216-226)
 int ragged_pad(const float* packed, const int* offsets, float* out, int B, int max_l, int d,
                cudaStream_t stream);

@@ -94,6 +94,29 @@ __global__ void cast_gather_kernel(const float* __restrict__ src, T* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ modality-dropout keep mask
+// Guided / random modality dropout (north-star extension; definition: oracle/shaping.py
+// modality_dropout_mask).  u, r: fp32[B] uniform draws made by the HOST generator; sample b keeps
+// both modalities unless u[b] < p_drop; then it drops image / text by r[b] < 0.5 (mode 0, random)
+// or the modality whose device-resident score is higher, ties -> image (mode 1, guided).  The
+// guided scores never leave the device, so the training step does not wait on a host read.
+__global__ void modality_keep_mask_kernel(const float* __restrict__ u, const float* __restrict__ r,
+                                          const float* __restrict__ score_img,
+                                          const float* __restrict__ score_txt, int score_stride, int B,
+                                          float p_drop, int mode, int* __restrict__ keep) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int ki = 1, kt = 1;
+  if (u[b] < p_drop) {
+    const bool drop_text = mode == 0 ? !(r[b] < 0.5f)
+                                     : score_txt[static_cast<size_t>(b) * score_stride] >
+                                           score_img[static_cast<size_t>(b) * score_stride];
+    if (drop_text) kt = 0; else ki = 0;
+  }
+  keep[2 * b] = ki;
+  keep[2 * b + 1] = kt;
+}
+
 // ----------------------------------------------------------------------- LayerNorm
 // Row held in registers: NV float4 per lane (D <= 128*NV).
 template <int NV>
@@ -891,6 +914,18 @@ int cast_gather(const float* src, void* dst, int dst_dtype, int B, int l_src, in
   else
     cast_gather_kernel<float><<<grid, 256, 0, stream>>>(src, static_cast<float*>(dst), B, l_src, d,
                                                         idx, n_sel, keep, modality);
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int modality_keep_mask(const float* u, const float* r, const float* score_img, const float* score_txt,
+                       int score_stride, int B, float p_drop, int mode, int* keep, cudaStream_t stream) {
+  if (u == nullptr || keep == nullptr || (mode != 0 && mode != 1)) return MMU_ERR_ARG;
+  if (mode == 0 && r == nullptr) return MMU_ERR_ARG;
+  if (mode == 1 && (score_img == nullptr || score_txt == nullptr)) return MMU_ERR_ARG;
+  if (B <= 0) return 0;
+  modality_keep_mask_kernel<<<(B + 127) / 128, 128, 0, stream>>>(u, r, score_img, score_txt, score_stride,
+                                                                 B, p_drop, mode, keep);
   MMU_CHECK_LAUNCH();
   return 0;
 }

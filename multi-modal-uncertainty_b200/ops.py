@@ -248,3 +248,24 @@ def ragged_pad(packed, offsets, max_len):
     check(lib.mmu_ragged_pad(ptr(packed), ptr(offsets), ptr(out), B, max_len, packed.shape[1],
                              stream_ptr()), "mmu_ragged_pad")
     return out
+
+
+def modality_keep_mask(u, r, p_drop, mode="random", score_img=None, score_txt=None):
+    """Keep mask int32 (B, 2) on device from host-drawn uniforms ``u``, ``r`` (fp32 (B,), already
+    on the device) and -- ``mode='guided'`` -- device-resident per-sample scores (1-D views with
+    any equal stride, e.g. ``scores[:, 0]`` of the epilogue's per-sample output); see
+    ``mmu_modality_keep_mask``."""
+    if not (u.is_cuda and u.dtype == torch.float32 and u.is_contiguous()):
+        raise ValueError("u must be a contiguous fp32 CUDA vector")
+    B = u.numel()
+    m = {"random": 0, "guided": 1}[mode]
+    stride = 1
+    if m == 1:
+        if score_img.dtype != torch.float32 or score_txt.dtype != torch.float32 or \
+                score_img.stride(0) != score_txt.stride(0) or score_img.numel() != B or score_txt.numel() != B:
+            raise ValueError("guided scores must be fp32 (B,) views with equal strides")
+        stride = score_img.stride(0)
+    keep = torch.empty(B, 2, dtype=torch.int32, device=u.device)
+    check(lib.mmu_modality_keep_mask(ptr(u), ptr(r), ptr(score_img), ptr(score_txt), stride, B,
+                                     float(p_drop), m, ptr(keep), stream_ptr()), "mmu_modality_keep_mask")
+    return keep

@@ -66,6 +66,22 @@ def modality_dropout_mask(batch_size, p_drop, mode="random", scores=None, genera
     return keep
 
 
+def modality_dropout_mask_device(batch_size, p_drop, mode, device, score_img=None, score_txt=None,
+                                 generator=None):
+    """The same keep mask as :func:`modality_dropout_mask`, built ON THE DEVICE: the two uniform
+    vectors come from the host generator (same draws, same order), are uploaded from pinned
+    memory, and ``mmu_modality_keep_mask`` combines them with device-resident guided scores
+    (``score_img`` / ``score_txt``: fp32 (B,) views of equal stride, e.g. the confidence column of
+    the uncertainty epilogue's per-sample output for the image-only / text-only variants of the
+    batch) -- a guided training step never waits for a device->host read."""
+    from ._backend import ops
+    staged = torch.empty(2, batch_size, dtype=torch.float32, pin_memory=True)
+    torch.rand(batch_size, generator=generator, out=staged[0])
+    torch.rand(batch_size, generator=generator, out=staged[1])
+    ur = staged.to(device, non_blocking=True)
+    return ops.modality_keep_mask(ur[0], ur[1], p_drop, mode, score_img, score_txt)
+
+
 @torch.no_grad()
 def forward_variant(model, img, txt, variant, ref_bug_compat=False):
     """Run one variant.  ``ref_bug_compat`` reproduces reference line 119 (text slot indexed

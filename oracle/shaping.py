@@ -140,22 +140,37 @@ def leave_one_view_out(x, i):
 def modality_dropout_mask(batch_size, p_drop, mode="random", scores=None, generator=None):
     """Per-sample keep mask (B, 2) int32 over (image, text).  NO REFERENCE IMPLEMENTATION
     (only stale gin names, configs/training_guided.gin:10-18) -- parity unpinned; this is the
-    repo's definition.  One uniform draw u_b per sample decides whether a modality is dropped
-    (u_b < p_drop).  ``random``: a second draw picks which (image if < 0.5).  ``guided``: drop
-    the modality whose head is currently the more confident one (scores[b, m], ties -> image).
-    A dropped modality is zero-filled on device, as eval_robustness.py:92-97 zero-fills views."""
-    g = generator
-    u = torch.rand(batch_size, generator=g)
-    pick = torch.rand(batch_size, generator=g)
-    keep = torch.ones(batch_size, 2, dtype=torch.int32)
-    drop = u < p_drop
-    if mode == "random":
-        which = (pick >= 0.5).to(torch.int64)  # 0 = image, 1 = text
-    elif mode == "guided":
-        assert scores is not None and tuple(scores.shape) == (batch_size, 2)
-        which = (scores[:, 1] > scores[:, 0]).to(torch.int64)
-    else:
+    repo's DEFINITION, written sample by sample (the product computes it vectorised / on device):
+
+      draw u_0..u_{B-1}, then r_0..r_{B-1}, uniform in [0, 1) from ``generator`` (two vector draws);
+      sample b keeps both modalities unless u_b < p_drop; if it drops one,
+        "random": image when r_b < 0.5, else text;
+        "guided": the modality whose score is currently HIGHER (scores[b] = (image, text);
+                  ties -> image), i.e. the one the model leans on.
+    A dropped modality is zero-filled (``apply_keep_mask``), as eval_robustness.py:92-97
+    zero-fills views."""
+    if mode not in ("random", "guided"):
         raise ValueError(mode)
-    rows = torch.nonzero(drop).flatten()
-    keep[rows, which[rows]] = 0
-    return keep
+    u = torch.rand(batch_size, generator=generator).tolist()
+    r = torch.rand(batch_size, generator=generator).tolist()
+    rows = []
+    for b in range(batch_size):
+        keep_img, keep_txt = 1, 1
+        if u[b] < p_drop:
+            if mode == "random":
+                drop_text = not (r[b] < 0.5)
+            else:
+                assert scores is not None and tuple(scores.shape) == (batch_size, 2)
+                drop_text = bool(float(scores[b, 1]) > float(scores[b, 0]))
+            if drop_text:
+                keep_txt = 0
+            else:
+                keep_img = 0
+        rows.append([keep_img, keep_txt])
+    return torch.tensor(rows, dtype=torch.int32).reshape(batch_size, 2)
+
+
+def apply_keep_mask(img, txt, keep):
+    """Zero-fill the dropped modality of each sample (keep (B, 2) over (image, text))."""
+    k = keep.to(img.dtype)
+    return img * k[:, 0].view(-1, 1, 1), txt * k[:, 1].view(-1, 1, 1)

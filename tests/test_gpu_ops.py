@@ -80,6 +80,53 @@ def test_gemm_epilogues(mmu, dtype, tol):
     assert float(dst.cpu().view(8, 9, N)[:, :2].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 520, 192), (2304, 768, 320), (640, 3072, 768)])
+def test_gemm_epilogues_cta_pair_kernel(mmu, M, N, K):
+    """The same epilogue modes on the CTA-PAIR kernel (gemm_bf16_tcgen05_kernel<MODE, OBF, 2>,
+    tcgen05 cta_group::2, 256x256 tiles): dispatched for unbatched problems with M >= 512 and
+    N > 128 (gemm_tcgen05.cu use_pair) -- every big GEMM of the headline configuration.  Shapes
+    cover ragged M / N edges (clipped by the output tensor maps), several tiles per cluster and
+    both MN-major operand layouts; the reference is fp32 matmul of the bf16-rounded operands, so
+    the tolerance only has to cover the bf16 rounding of the OUTPUT (2^-9) and the tanh.approx
+    sigmoid (2^-11)."""
+    from oracle import fusion
+    E = mmu._lib
+    dt = torch.bfloat16
+    A, B = rnd(M, K, seed=4).to(dt), rnd(N, K, seed=5, scale=1 / math.sqrt(K)).to(dt)
+    bias = rnd(N, seed=6)
+    acc_ref = A.float() @ B.float().t()
+    z_ref = acc_ref + bias
+    # QUICKGELU, training form (z and u) and eval form (u only)
+    z = torch.empty(M, N, device="cuda", dtype=dt)
+    u = torch.empty(M, N, device="cuda", dtype=dt)
+    mmu.ops.gemm(A.cuda(), B.cuda(), mode=E.EPI_QUICKGELU, out=z, out2=u, bias=bias.cuda())
+    assert rel(z.float().cpu(), z_ref) < 4e-3
+    assert rel(u.float().cpu(), fusion.quick_gelu(z_ref)) < 5e-3
+    u2 = torch.empty(M, N, device="cuda", dtype=dt)
+    mmu.ops.gemm(A.cuda(), B.cuda(), mode=E.EPI_QUICKGELU, out2=u2, bias=bias.cuda())
+    assert torch.equal(u2, u)
+    # DGELU with the MN-major weight operand the dgrad GEMM uses (dz = (dx W) * gelu'(z))
+    zz = rnd(M, N, seed=8, scale=2.0).to(dt)
+    s = torch.sigmoid(1.702 * zz.float())
+    g_ref = acc_ref * (s * (1 + 1.702 * zz.float() * (1 - s)))
+    out = mmu.ops.gemm(A.cuda(), B.t().contiguous().cuda(), b_mn_major=True, mode=E.EPI_DGELU, aux=zz.cuda())
+    assert rel(out.float().cpu(), g_ref) < 5e-3
+    out = mmu.ops.gemm(A.cuda(), B.cuda(), mode=E.EPI_DGELU, aux=zz.cuda())
+    assert rel(out.float().cpu(), g_ref) < 5e-3
+    # ATOMIC: split-K accumulation on top of existing contents (fp32, no output rounding), in the
+    # wgrad layout (both operands MN-major)
+    for splits in (1, 3):
+        acc = torch.ones(M, N, device="cuda")
+        mmu.ops.gemm(A.t().contiguous().cuda(), B.t().contiguous().cuda(), a_mn_major=True,
+                     b_mn_major=True, mode=E.EPI_ATOMIC, out=acc, splits=splits, alpha=0.5)
+        assert rel(acc.cpu(), 1 + 0.5 * acc_ref) < 2e-5
+    # plain store, fp32 and bf16 outputs
+    o32 = mmu.ops.gemm(A.cuda(), B.cuda(), bias=bias.cuda(), out_dtype=torch.float32)
+    assert rel(o32.cpu(), z_ref) < 2e-5
+    o16 = mmu.ops.gemm(A.cuda(), B.cuda(), bias=bias.cuda())
+    assert rel(o16.float().cpu(), z_ref) < 4e-3
+
+
 @pytest.mark.parametrize("D", [64, 96, 768, 1024])
 def test_layernorm(mmu, D):
     from oracle import fusion
@@ -350,3 +397,23 @@ def test_uncertainty_epilogue_batched_heads_bit_identical(mmu, N, E, C, monkeypa
         # integer words of the accumulator are order independent; the fp64 sums are atomics
         ia = a.view(torch.int64)[:mmu._lib.ACC_INT_WORDS]
         assert torch.equal(ia, outs[1][2].view(torch.int64)[:mmu._lib.ACC_INT_WORDS]), hb
+
+
+@pytest.mark.parametrize("mode", ["random", "guided"])
+@pytest.mark.parametrize("B,p", [(128, 0.5), (77, 0.25), (300, 1.0), (16, 0.0)])
+def test_modality_keep_mask_device_equals_oracle(mmu, mode, B, p):
+    """mmu_modality_keep_mask (device, scores never leave the GPU) against the oracle's
+    sample-by-sample definition (oracle/shaping.py) under the same host generator: bit-exact."""
+    from oracle import shaping
+    g = torch.Generator().manual_seed(B)
+    scores = torch.rand(B, 4, generator=g)
+    scores[::7, 1] = scores[::7, 0]                       # exact ties -> image is dropped
+    ref = shaping.modality_dropout_mask(B, p, mode, scores[:, :2], torch.Generator().manual_seed(11))
+    sd = scores.cuda()
+    got = mmu.robustness.modality_dropout_mask_device(B, p, mode, "cuda", sd[:, 0], sd[:, 1],
+                                                      torch.Generator().manual_seed(11))
+    assert got.dtype == torch.int32 and torch.equal(got.cpu(), ref)
+    host = mmu.robustness.modality_dropout_mask(B, p, mode, scores[:, :2], torch.Generator().manual_seed(11))
+    assert torch.equal(host, ref)
+    if p == 1.0:
+        assert int((ref.sum(1) == 1).sum()) == B           # every sample lost exactly one modality
