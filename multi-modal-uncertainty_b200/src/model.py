@@ -88,12 +88,23 @@ def _loss_from_accum(accum):
 class FlavaFusionTransfomer(nn.Module):
     """Drop-in for reference ``FlavaFusionTransfomer`` (src/model.py:225-304).
 
-    One optional keyword beyond the reference: ``precision`` ("bf16" tensor-core path, default,
-    or "fp32" parity path).  ``avg_pool`` is REQUIRED, as in the reference (:256).  Device
-    workspaces are allocated per (batch, token-count) shape on first use and cached.
+    Two optional keywords beyond the reference: ``precision`` ("bf16" tensor-core path, default,
+    or "fp32" parity path) and ``live_tokens`` (default False = every token position is computed,
+    as written).  ``avg_pool`` is REQUIRED, as in the reference (:256).  Device workspaces are
+    allocated per (batch, token-count) shape on first use and cached.
+
+    ``live_tokens=True``: without ``avg_pool`` head ``i`` reads token position ``i`` of the
+    concatenated sequence (:286-287) and token positions never interact (attention runs over the
+    BATCH axis, every other op is row-wise), so positions >= E cannot reach the logits or any
+    gradient (~97 % of the as-written step at 197 + 40 tokens).  The
+    live-token path gathers only the first E positions of (image ++ text) -- same kernels, same
+    rows, bit-identical logits; gradients identical up to the summation order of the split-K
+    weight-gradient atomics (the skipped rows contribute exact zeros).  Ignored with ``avg_pool``
+    / the CLS variant / ``MIMOTransfomer``, where every position is live.
     """
 
     _cls_token = False
+    live_tokens = False
 
     def __init__(self,
                  out_dim: int = 1,
@@ -111,6 +122,7 @@ class FlavaFusionTransfomer(nn.Module):
         self.num_classes = num_classes
         self.drop = float(drop)
         self.precision = _PREC[kwargs.get("precision", "bf16")]
+        self.live_tokens = bool(kwargs.get("live_tokens", False))
         self._dims = dict(d_img=image_hidden_size, d_txt=text_hidden_size, D=multimodal_hidden_size,
                           n_head=multimodal_num_attention_heads,
                           n_layers=multimodal_num_hidden_layers)
@@ -120,6 +132,7 @@ class FlavaFusionTransfomer(nn.Module):
 
     def _finish_init(self):
         self._ws = {}
+        self._live_idx = {}
         self._pack_caps = {}
         self._cfg_cache = {}
         self._last_epi = None
@@ -212,6 +225,7 @@ class FlavaFusionTransfomer(nn.Module):
             p.grad = flat_grad[off:off + numel].view(shape)
             self._grad_views.append((p, p.grad))
         self._ws.clear()
+        self._live_idx = {}
 
     def _ensure_grad_views(self):
         """The kernels accumulate into the flat gradient buffer; ``p.grad`` must be its views.
@@ -359,6 +373,13 @@ class FlavaFusionTransfomer(nn.Module):
             return torch.stack([self.forward((img if ii is not None else None,
                                               txt if it is not None else None),
                                              token_indices=(ii, it)) for ii, it in variants])
+        if self._skips_dead_tokens():
+            live = []
+            for ii, it in variants:
+                _, _, li, lt = self._live_subset(img if ii is not None else None,
+                                                 txt if it is not None else None, ii, it)
+                live.append((li, lt))
+            variants = live
         out, chunk, pos = [], [], 0
         for v in variants:
             n = (len(v[0]) if v[0] is not None else 0) + (len(v[1]) if v[1] is not None else 0)
@@ -451,6 +472,32 @@ class FlavaFusionTransfomer(nn.Module):
             out.append((min(a for a, _ in offs), max(b for _, b in offs)))
         return out
 
+    # ------------------------------------------------------------------ live-token path
+    def _skips_dead_tokens(self):
+        return self.live_tokens and not self.avg_pool and not self._cls_token and self._group_pool == 0
+
+    def _live_subset(self, img, txt, idx_img, idx_txt):
+        """(img, txt, idx_img, idx_txt) restricted to the first E positions of (image ++ text):
+        the only ones head i = 0..E-1 reads (src/model.py:286-287)."""
+        E = self.out_dim
+        n_img = (len(idx_img) if idx_img is not None else img.shape[1]) if img is not None else 0
+        n_txt = (len(idx_txt) if idx_txt is not None else txt.shape[1]) if txt is not None else 0
+        if n_img + n_txt < E:
+            raise ValueError(f"{n_img + n_txt} tokens cannot feed {E} heads")
+        k_img = min(E, n_img)
+        k_txt = E - k_img
+        dev = self._flat.device
+
+        def head(idx, k):
+            if idx is not None:
+                return idx[:k]
+            t = self._live_idx.get(k)
+            if t is None:
+                t = self._live_idx[k] = torch.arange(k, dtype=torch.int32, device=dev)
+            return t
+        return (img if k_img else None, txt if k_txt else None,
+                head(idx_img, k_img) if k_img else None, head(idx_txt, k_txt) if k_txt else None)
+
     # -------------------------------------------------------------- reference protocol
     def forward(self, x, token_indices=None, keep_mask=None):
         """``x = (image_features, text_features)``.  ``token_indices = (idx_img, idx_txt)`` runs
@@ -458,6 +505,8 @@ class FlavaFusionTransfomer(nn.Module):
         int (B, 2) modality keep mask (0 zero-fills that modality for that sample)."""
         img, txt = x
         idx_img, idx_txt = token_indices if token_indices is not None else (None, None)
+        if self._skips_dead_tokens():
+            img, txt, idx_img, idx_txt = self._live_subset(img, txt, idx_img, idx_txt)
         if self.training and torch.is_grad_enabled():
             anchor = next(self.parameters())
             return _FlavaForward.apply(anchor, self, img, txt, idx_img, idx_txt, keep_mask)
@@ -465,7 +514,10 @@ class FlavaFusionTransfomer(nn.Module):
 
     def _train_engine(self, x):
         img, txt = x
-        saved = self._engine_forward(img, txt, None, None, None, training=True)
+        idx_img = idx_txt = None
+        if self._skips_dead_tokens():
+            img, txt, idx_img, idx_txt = self._live_subset(img, txt, None, None)
+        saved = self._engine_forward(img, txt, idx_img, idx_txt, None, training=True)
         return saved, self._logits_train
 
     @torch.no_grad()

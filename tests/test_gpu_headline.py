@@ -305,3 +305,46 @@ def test_headline_avg_pool_all_tokens_live(mmu):
         for k, (e, scale) in errs.items():
             assert scale > 0 and e < tg, (k, e)      # nothing is dead with avg_pool
     del c
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_headline_live_token_path_is_bit_identical(mmu, case, precision):
+    """``live_tokens=True`` computes only the token positions that can reach a head (positions
+    < E without avg_pool, src/model.py:286-287) -- 5 of 237 here.  Same kernels on the same rows:
+    train-mode logits, eval logits and the packed 10-level sweep are BIT-identical to the
+    as-written path; every gradient agrees to the summation order of the split-K weight-gradient
+    atomics (the skipped rows contribute exact zeros), and the dead text projection stays at 0."""
+    outs = {}
+    variants = sweep_variants(mmu)
+    for live in (False, True):
+        torch.manual_seed(42)
+        m = mmu.FlavaFusionTransfomer(out_dim=CFG["E"], num_classes=CFG["C"],
+                                      multimodal_num_attention_heads=CFG["heads"],
+                                      multimodal_num_hidden_layers=CFG["layers"], drop=0.0,
+                                      avg_pool=False, precision=precision, live_tokens=live)
+        m.load_state_dict(case["P"], strict=True)
+        m.cuda().train()
+        m.zero_grad()
+        x = (case["img"].cuda(), case["txt"].cuda())
+        logits = m(x)
+        m.compute_loss(logits, case["yt"].cuda()).backward()
+        grads = {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters()}
+        m.eval()
+        with torch.no_grad():
+            ev = m(x).cpu()
+            sw = m.forward_variants(x, variants).cpu()
+            keep = torch.ones(CFG["B"], 2, dtype=torch.int32)
+            keep[::3, 0] = 0
+            km = m(x, keep_mask=keep.cuda()).cpu()
+        outs[live] = (logits.detach().cpu(), grads, ev, sw, km)
+    a, b = outs[False], outs[True]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    worst = 0.0
+    for k in a[1]:
+        scale = float(a[1][k].abs().max())
+        if scale == 0.0:
+            assert float(b[1][k].abs().max()) == 0.0, k
+        else:
+            worst = max(worst, float((a[1][k] - b[1][k]).abs().max()) / scale)
+    print(f"\n[headline live tokens {precision}] logits bit-identical; worst gradient difference {worst:.2e} of max|g|")
+    assert worst < 2e-5

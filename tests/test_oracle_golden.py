@@ -34,6 +34,32 @@ def test_flava_forward_loss_grads(golden, name):
     assert float(fusion.acc(logits, c["y_train"], False, True)) == float(c["train_acc"])
 
 
+@pytest.mark.parametrize("name", ["plain_E2", "avgpool_E2", "plain_E5_h3"])
+def test_eager_incumbent_matches_reference_goldens(golden, name):
+    """oracle/eager.py -- the fused-ATen form that bench.py times on `cuda` as the PyTorch-eager
+    incumbent -- computes the reference's function: logits, loss, every gradient and one
+    torch.optim.AdamW step against the goldens of the unmodified reference."""
+    from oracle import eager
+    c = golden("flava_small.pt")[name]
+    cfg = c["cfg"]
+    tr = eager.EagerTrainer(c["state_dict"], cfg["heads"], cfg["layers"], cfg["E"], lr=1e-3, wd=1e-3)
+    logits = eager.forward(tr.P, (c["img"], c["txt"]), cfg["heads"], cfg["layers"], cfg["E"], cfg["avg_pool"])
+    assert rel_err(logits.detach(), c["logits"]) < 1e-5
+    loss = eager.compute_loss(logits, c["y_train"])
+    assert abs(float(loss) - float(c["loss"])) < 1e-5 * max(1.0, abs(float(c["loss"])))
+    loss.backward()
+    for k, g in c["grads"].items():
+        got = tr.P[k].grad if tr.P[k].grad is not None else torch.zeros_like(g)
+        assert float((got - g).abs().max()) <= 2e-4 * max(float(g.abs().max()), 1e-6) + 1e-7, k
+    if not cfg["avg_pool"]:
+        tr2 = eager.EagerTrainer(c["state_dict"], cfg["heads"], cfg["layers"], cfg["E"], lr=1e-3, wd=1e-3)
+        tr2.train_step((c["img"], c["txt"]), c["y_train"])
+        for k, g in c["grads"].items():
+            ok = g.abs() > 1e-3 * g.abs().max().clamp_min(1e-12)
+            d = (tr2.P[k].detach() - c["params_after_adamw"][k]).abs()
+            assert float(d[ok].max() if ok.any() else 0.0) < 2e-5, k
+
+
 def test_flava_missing_modality(golden):
     c = golden("flava_small.pt")["cls_E3"]
     P, h = c["state_dict"], c["cfg"]["heads"]
