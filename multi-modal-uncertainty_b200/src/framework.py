@@ -31,23 +31,57 @@ def _step_stream(steps, generator):
 
 class StepIterator:
     """Yields ``(step, batch)``; after the body fills ``step['loss'|'metrics'|'size']`` it keeps
-    size-weighted running means and fires the batch callbacks (reference :35-95)."""
+    size-weighted running means and fires the batch callbacks (reference :35-95).
+
+    Deferred read-back (``read_every`` > 1): when the body hands over the loss /
+    metrics as 0-dim DEVICE tensors, the size-weighted sums are accumulated ON THE DEVICE and read
+    back once every ``read_every`` steps and at the end of the epoch (one small D2H copy) instead
+    of the reference's two queue-draining ``.item()`` reads per step (src/framework.py:305-312).
+    The epoch means are the same numbers; a NaN loss is detected at the next read (``saw_nan``);
+    per-batch logs carry the running mean of the last read."""
 
     _reserved = ("loss", "metrics", "number", "size")
 
-    def __init__(self, generator, steps_per_epoch, callback, metrics_names):
+    def __init__(self, generator, steps_per_epoch, callback, metrics_names, read_every=1):
         self.generator, self.steps_per_epoch = generator, steps_per_epoch
         self.callback, self.metrics_names = callback, metrics_names
         self.losses_sum, self.sizes_sum = 0.0, 0.0
         self.metrics_sum = np.zeros(len(metrics_names))
         self.extra_lists = {}
+        self.read_every = max(1, int(read_every))
+        self._dev, self._pending, self._pending_sizes = None, 0, 0.0
+        self.saw_nan = False
+
+    def _defer(self, loss, metrics, size):
+        vec = torch.stack([loss.detach().reshape(()).float()] +
+                          [torch.as_tensor(m, device=loss.device).reshape(()).float() for m in metrics])
+        if self._dev is None:
+            self._dev = torch.zeros_like(vec, dtype=torch.float64)
+        self._dev.add_(vec, alpha=float(size))
+        self._pending += 1
+        self._pending_sizes += size
+        if self._pending >= self.read_every:
+            self.flush()
+
+    def flush(self):
+        """One device->host read of the pending size-weighted sums."""
+        if self._pending:
+            vals = self._dev.tolist()
+            self._dev.zero_()
+            self.losses_sum += vals[0]
+            self.metrics_sum += np.asarray(vals[1:])
+            self.sizes_sum += self._pending_sizes
+            self.saw_nan = self.saw_nan or math.isnan(vals[0])
+            self._pending, self._pending_sizes = 0, 0.0
 
     @property
     def loss(self):
+        self.flush()
         return self.losses_sum / self.sizes_sum if self.sizes_sum else 0
 
     @property
     def metrics(self):
+        self.flush()
         if not self.sizes_sum:
             return dict(zip(self.metrics_names, np.zeros(len(self.metrics_names))))
         return dict(zip(self.metrics_names, self.metrics_sum / self.sizes_sum))
@@ -60,15 +94,25 @@ class StepIterator:
             step = {"number": number}
             yield step, data
             size = step["size"]
-            self.losses_sum += step["loss"] * size
-            self.metrics_sum += step["metrics"] * size
-            self.sizes_sum += size
+            if torch.is_tensor(step["loss"]):      # deferred read-back: accumulate on the device
+                self._defer(step["loss"], step["metrics"], size)
+                mean_loss = self.losses_sum / self.sizes_sum if self.sizes_sum else float("nan")
+                mean_mets = (self.metrics_sum / self.sizes_sum if self.sizes_sum
+                             else np.full(len(self.metrics_names), np.nan))
+                logs = {"batch": number, "size": size, "time": timeit.default_timer() - t0,
+                        "batch_begin_time": t0, "loss": mean_loss,
+                        **dict(zip(self.metrics_names, mean_mets)), "deferred": True}
+            else:
+                self.losses_sum += step["loss"] * size
+                self.metrics_sum += step["metrics"] * size
+                self.sizes_sum += size
+                self.saw_nan = self.saw_nan or math.isnan(step["loss"])
+                logs = {"batch": number, "size": size, "time": timeit.default_timer() - t0,
+                        "batch_begin_time": t0, "loss": step["loss"],
+                        **dict(zip(self.metrics_names, step["metrics"]))}
             for key, value in step.items():
                 if key not in self._reserved:
                     self.extra_lists.setdefault(key, []).append(value)
-            logs = {"batch": number, "size": size, "time": timeit.default_timer() - t0,
-                    "batch_begin_time": t0, "loss": step["loss"],
-                    **dict(zip(self.metrics_names, step["metrics"]))}
             self.callback.on_batch_end(number, logs)
 
 
@@ -241,7 +285,10 @@ class Model_:
         for epoch in range(epoch_start, epochs + 1):
             cbs.on_epoch_begin(epoch, {})
             t0 = timeit.default_timer()
-            it = StepIterator(train_generator, steps_per_epoch, cbs, self.metrics_names)
+            # metrics_every=N (N > 1): loss / metrics stay on the device and are read back every N
+            # steps and at the end of the epoch (StepIterator) -- same epoch means, no per-step sync
+            read_every = 1 if mmbt else int(kwargs.get("metrics_every", 1))
+            it = StepIterator(train_generator, steps_per_epoch, cbs, self.metrics_names, read_every)
             self.model.train(True)
             with torch.enable_grad():
                 for step, (x, y) in it:
@@ -253,12 +300,13 @@ class Model_:
                             gradient_accumulation_steps=kwargs["gradient_accumulation_steps"],
                             scheduler_step_on=scheduler_step_on)
                     else:
-                        loss, info, size = self.train_step(x, y, scheduler_step_on,
+                        loss, info, size = self.train_step(x, y, scheduler_step_on, sync=read_every == 1,
                                                            cuda_graph=bool(kwargs.get("cuda_graph", False)))
                     cbs.on_backward_end(step["number"])
                     step["size"], step["loss"], step["metrics"] = size, loss, info
-                    if math.isnan(loss):
-                        stop = True
+            it.flush()
+            if it.saw_nan:      # reference src/framework.py:319 (checked at every read-back)
+                stop = True
             log = {"epoch": epoch, "loss": it.loss,
                    **{f"train_{k}": v for k, v in it.extra_lists.items()}, **it.metrics}
             if valid_generator is not None:

@@ -59,6 +59,26 @@ class GraphedTrainStep:
                       for g in self.trainer.optimizer.param_groups)
         return shapes, tuple(y.shape), y.dtype, hyper
 
+    def _baked(self):
+        """Every tensor whose ADDRESS a captured step bakes in: the model's flat parameter /
+        gradient / statistics buffers, the bf16 shadow, the cached workspaces and the optimiser
+        state.  An entry keeps strong references to them (a freed workspace can therefore never be
+        recycled under a live graph) and is dropped as soon as one of the model- or
+        optimiser-owned buffers is no longer the current one (``model.to()``, ``_rebind``,
+        ``optimizer.load_state_dict`` ...)."""
+        m, opt = self.trainer.model, self.trainer.optimizer
+        owned = [getattr(m, n, None) for n in ("_flat", "_flat_grad", "_stats", "_shadow")]
+        for st in opt.state.values():
+            owned += [v for v in st.values() if torch.is_tensor(v)]
+        owned = [t for t in owned if t is not None]
+        ws = getattr(m, "_ws", None)
+        scratch = list(ws.values()) if isinstance(ws, dict) else []
+        return owned, scratch
+
+    @staticmethod
+    def _ident(tensors):
+        return tuple((t.data_ptr(), t.numel(), t.dtype) for t in tensors)
+
     def _body(self, x, y):
         tr = self.trainer
         tr.optimizer.zero_grad()
@@ -88,7 +108,8 @@ class GraphedTrainStep:
         bad = [m for m in mets if not torch.is_tensor(m)]
         if bad:
             raise TypeError("metrics must return device tensors to be replayed from a CUDA graph")
-        return graph, sx, sy, loss, mets
+        owned, scratch = self._baked()
+        return graph, sx, sy, loss, mets, self._ident(owned), owned + scratch
 
     def step(self, x, y):
         """x, y: the shaped batch (host or device tensors).  Returns (loss, metrics) as 0-dim
@@ -100,6 +121,9 @@ class GraphedTrainStep:
             return self._body(tr.to_device(x), tr.to_device(y))
         key = self._key(xs, y)
         ent = self.entries.get(key)
+        if ent is not None and ent[5] != self._ident(self._baked()[0]):
+            del self.entries[key]      # a baked-in buffer was replaced: the graph is stale
+            ent = None
         if ent is None:
             if len(self.entries) >= self.MAX_GRAPHS:
                 # a scheduler that moves the learning rate every batch (or ever-changing batch
@@ -112,7 +136,7 @@ class GraphedTrainStep:
                 tr = self.trainer
                 return self._body(tr.to_device(x), tr.to_device(y))
             ent = self.entries[key] = self._capture(xs, is_seq, y)
-        graph, sx, sy, loss, mets = ent
+        graph, sx, sy, loss, mets = ent[:5]
         for dst, src in zip(sx, xs):
             if dst is not None:
                 dst.copy_(src, non_blocking=True)

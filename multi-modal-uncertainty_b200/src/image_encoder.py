@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from ._backend import _lib
-from .model import FlavaFusionTransfomer, _holder_for
+from .model import FlavaFusionTransfomer, _holder_for, check_workspace, stamp_workspace
 from .resnet import MIMOResNet
 
 #: reference src/mmbt.py:28-37: num_image_embeds -> adaptive pool grid
@@ -171,10 +171,12 @@ class ImageEncoder(nn.Module):
                                                _lib.stream_ptr()), "mmu_imgenc_forward")
         if bn_training:
             self._nbt += 1
-        return cfg, ws, x, shadow, tokens
+        saved = (cfg, ws, x, shadow, tokens)
+        return stamp_workspace(self, ws, saved) if training else saved
 
     def _engine_backward(self, saved, dtokens):
         cfg, ws, x, shadow, _ = saved
+        check_workspace(self, ws, saved)
         self._ensure_grad_views()
         _lib.check(_lib.lib.mmu_imgenc_backward(C.byref(cfg), self._flat.data_ptr(), _lib.ptr(shadow),
                                                 self._stats.data_ptr(), x.data_ptr(), ws.data_ptr(),

@@ -33,9 +33,10 @@ def acc(y_pred, y_true, eval, dummy_dim=False, model=None):
     y_pred = y_pred.detach()
     if not y_pred.is_contiguous():
         y_pred = y_pred.contiguous()
-    accum = model.cached_epilogue(y_pred, mode) if model is not None else None
+    labels = y_true.reshape(y_pred.shape[0], -1) if mode == 0 else y_true.reshape(-1)
+    # the loss epilogue already counted the correct rows of exactly these logits AND labels
+    accum = model.cached_epilogue(y_pred, mode, labels) if model is not None else None
     if accum is None:
-        labels = y_true.reshape(y_pred.shape[0], -1) if mode == 0 else y_true.reshape(-1)
         _, _, _, accum = ops.heads_uncertainty_epilogue(y_pred, labels.contiguous(), mode)
     o = _lib.ACC_OFF
     correct = accum[o["n_correct_rows"]].to(torch.float32)

@@ -24,7 +24,8 @@ import torch
 import torch.nn as nn
 
 from ._backend import _lib, ops
-from .model import FlavaFusionTransfomer, _Holder, _holder_for, _loss_from_accum
+from .model import (FlavaFusionTransfomer, _Holder, _holder_for, _loss_from_accum, check_workspace,
+                    stamp_workspace)
 
 _PREC = {"fp32": 0, "bf16": 1}
 
@@ -198,6 +199,8 @@ class MultimodalBertClf(nn.Module):
     _fresh_shadow = FlavaFusionTransfomer._fresh_shadow
     _remember_epilogue = FlavaFusionTransfomer._remember_epilogue
     cached_epilogue = FlavaFusionTransfomer.cached_epilogue
+    _labels_key = staticmethod(FlavaFusionTransfomer._labels_key)
+    _new_forward = FlavaFusionTransfomer._new_forward
 
     @torch.no_grad()
     def _init_like_reference(self):
@@ -244,6 +247,7 @@ class MultimodalBertClf(nn.Module):
         return t
 
     def _engine_forward(self, tokens, txt, mask, segment, indices, training):
+        self._new_forward()
         if not self._flat.is_cuda:
             raise _lib.MMUError("the model lives on the CPU: call .to('cuda') first -- this "
                                 "package has no CPU execution path")
@@ -269,10 +273,12 @@ class MultimodalBertClf(nn.Module):
         _lib.check(_lib.lib.mmu_mmbt_forward(C.byref(cfg), self._flat.data_ptr(), C.byref(inp),
                                              ws.data_ptr(), ws.numel(), int(training), logits.data_ptr(),
                                              _lib.stream_ptr()), "mmu_mmbt_forward")
-        return cfg, ws, (tokens, txt, mask, segment, idx, shadow), logits
+        saved = (cfg, ws, (tokens, txt, mask, segment, idx, shadow), logits)
+        return stamp_workspace(self, ws, saved) if training else saved
 
     def _engine_backward(self, saved, dlogits, need_dimg):
         cfg, ws, (tokens, txt, mask, segment, idx, shadow), _ = saved
+        check_workspace(self, ws, saved)
         self._ensure_grad_views()
         dimg = torch.empty_like(tokens) if need_dimg else None
         inp = _lib.MmbtInputs(txt.data_ptr(), mask.data_ptr(), segment.data_ptr(), tokens.data_ptr(),

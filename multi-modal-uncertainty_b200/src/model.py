@@ -45,6 +45,30 @@ def _holder_for(root, dotted):
     return mod, parts[-1]
 
 
+class _Saved(tuple):
+    """What a training-mode engine forward hands to its backward, plus the workspace stamp."""
+    stamp = 0
+
+
+def stamp_workspace(model, ws, saved):
+    """The activations a backward needs live in `ws` (ONE workspace per shape): stamp it so that a
+    backward whose activations were overwritten by a LATER training-mode forward at the same
+    shape fails loudly (``check_workspace``) instead of producing wrong gradients."""
+    stamps = model.__dict__.setdefault("_ws_stamp", {})
+    out = _Saved(saved)
+    out.stamp = stamps[ws.data_ptr()] = stamps.get(ws.data_ptr(), 0) + 1
+    return out
+
+
+def check_workspace(model, ws, saved):
+    if model.__dict__.get("_ws_stamp", {}).get(ws.data_ptr()) != getattr(saved, "stamp", None):
+        raise _lib.MMUError(
+            "backward() of a forward whose saved activations were overwritten: a later "
+            "training-mode forward at the same shape ran before this backward (the engine keeps "
+            "ONE workspace per shape).  Call backward() before the next training-mode forward, or "
+            "run the extra forward after model.eval()")
+
+
 class _FlavaForward(torch.autograd.Function):
     """One engine call forward, one (staged) engine call backward.  Parameter gradients are
     accumulated by the kernels straight into the model's flat gradient buffer (the ``.grad`` of
@@ -69,7 +93,7 @@ class _LossFn(torch.autograd.Function):
         dl, _, _, accum = ops.heads_uncertainty_epilogue(
             y_hat, y, 0, grad_scale=1.0 / (N * E), want_grad=True)
         ctx.save_for_backward(dl)
-        model._remember_epilogue(y_hat, 0, accum)
+        model._remember_epilogue(y_hat, 0, accum, y)
         return _loss_from_accum(accum)
 
     @staticmethod
@@ -312,6 +336,7 @@ class FlavaFusionTransfomer(nn.Module):
         if training and self.drop > 0.0:
             raise NotImplementedError("dropout > 0 is not implemented in the fused engine "
                                       "(the reference's own runs use --dropout 0, train.py:59)")
+        self._new_forward()
         ref = img if img is not None else txt
         B = ref.shape[0]
         dev = self._flat.device
@@ -340,7 +365,7 @@ class FlavaFusionTransfomer(nn.Module):
                    "mmu_flava_forward")
         if training:
             self._logits_train = logits
-            return (cfg, inp, ws, (img, txt, idx_img, idx_txt, keep))  # keep inputs alive
+            return stamp_workspace(self, ws, (cfg, inp, ws, (img, txt, idx_img, idx_txt, keep)))  # keeps inputs alive
         return logits
 
     # ------------------------------------------------------ packed-variant evaluation
@@ -392,6 +417,7 @@ class FlavaFusionTransfomer(nn.Module):
         return out[0] if len(out) == 1 else torch.cat(out)
 
     def _forward_packed(self, img, txt, variants):
+        self._new_forward()
         if not self._flat.is_cuda:
             raise _lib.MMUError("the model lives on the CPU: call .to('cuda') first -- this "
                                 "package has no CPU execution path")
@@ -449,6 +475,7 @@ class FlavaFusionTransfomer(nn.Module):
 
     def _engine_backward(self, saved, dlogits):
         cfg, inp, ws, _alive = saved
+        check_workspace(self, ws, saved)
         self._ensure_grad_views()
         if self._ddp is not None:
             self._ddp.backward(self, cfg, inp, ws, dlogits)
@@ -535,20 +562,34 @@ class FlavaFusionTransfomer(nn.Module):
         N, E, _ = logits.shape
         dl, _, _, accum = ops.heads_uncertainty_epilogue(logits, y2.contiguous(), 0,
                                                          grad_scale=1.0 / (N * E), want_grad=True)
-        self._remember_epilogue(logits, 0, accum)
+        self._remember_epilogue(logits, 0, accum, y2)
         self._engine_backward(saved, dl)
         logits._mmu_owner = self   # lets metrics.acc reuse this epilogue's accumulator
         return logits, _loss_from_accum(accum)
 
-    def _remember_epilogue(self, y_hat, mode, accum):
-        self._last_epi = (y_hat.data_ptr(), y_hat._version, tuple(y_hat.shape), mode, accum)
+    # The loss epilogue's accumulator is reused by ``metrics.acc`` for the SAME logits and labels.
+    # The engine writes logits through raw pointers (version counters do not move) and the caching
+    # allocator recycles addresses, so the cache entry is also tied to a forward GENERATION: every
+    # engine forward bumps ``_fwd_gen`` and drops the entry.
+    @staticmethod
+    def _labels_key(labels):
+        return None if labels is None else (labels.data_ptr(), labels.numel(), labels._version)
 
-    def cached_epilogue(self, y_hat, mode):
+    def _remember_epilogue(self, y_hat, mode, accum, labels=None):
+        self._last_epi = (y_hat.data_ptr(), y_hat._version, tuple(y_hat.shape), mode,
+                          getattr(self, "_fwd_gen", 0), self._labels_key(labels), accum)
+
+    def cached_epilogue(self, y_hat, mode, labels=None):
         e = self._last_epi
         if e is not None and e[0] == y_hat.data_ptr() and e[1] == y_hat._version \
-                and e[2] == tuple(y_hat.shape) and e[3] == mode:
-            return e[4]
+                and e[2] == tuple(y_hat.shape) and e[3] == mode and e[4] == getattr(self, "_fwd_gen", 0) \
+                and e[5] == self._labels_key(labels):
+            return e[6]
         return None
+
+    def _new_forward(self):
+        self._fwd_gen = getattr(self, "_fwd_gen", 0) + 1
+        self._last_epi = None
 
     def compute_loss(self, y_hat, y, eval=False):
         """Reference src/model.py:293-304: train -> mean CE over the (B*E) head rows against the
@@ -562,10 +603,10 @@ class FlavaFusionTransfomer(nn.Module):
             if y_hat.requires_grad:
                 return _LossFn.apply(y_hat, y2.contiguous(), self)
             _, _, _, accum = ops.heads_uncertainty_epilogue(y_hat, y2.contiguous(), 0)
-            self._remember_epilogue(y_hat, 0, accum)
+            self._remember_epilogue(y_hat, 0, accum, y2)
             return _loss_from_accum(accum)
         _, _, _, accum = ops.heads_uncertainty_epilogue(y_hat.detach(), y.reshape(-1).contiguous(), 1)
-        self._remember_epilogue(y_hat, 1, accum)
+        self._remember_epilogue(y_hat, 1, accum, y)
         return _loss_from_accum(accum)
 
 

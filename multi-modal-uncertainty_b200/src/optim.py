@@ -162,12 +162,17 @@ class BertAdam(torch.optim.Optimizer):
             if cached is None:
                 segs = torch.tensor([[(p.data_ptr() - flat.data_ptr()) // 4, p.numel()] for p, _ in active],
                                     dtype=torch.int64, device=flat.device)
-                host = torch.empty(len(active), 2, dtype=torch.float32).pin_memory()
+                # pinned staging of the per-tensor (weight decay, lr) rows: a RING of buffers, each
+                # guarded by an event recorded behind its upload, so that a host that runs ahead of
+                # the GPU (gradient accumulation, no .item() per step) never rewrites rows whose DMA
+                # is still pending
+                host = _PinnedRing((len(active), 2))
                 cached = self._seg_cache[key] = (
                     segs, host, torch.empty(len(active), 2, dtype=torch.float32, device=flat.device),
                     torch.empty(len(active), dtype=torch.float32, device=flat.device),
                     max(p.numel() for p, _ in active))
-            segs, host, hyper, norms, max_numel = cached
+            segs, ring, hyper, norms, max_numel = cached
+            host = ring.acquire()
             for i, (p, g) in enumerate(active):
                 st = self._steps.get(id(p), 0)
                 if g["t_total"] != -1:
@@ -178,6 +183,7 @@ class BertAdam(torch.optim.Optimizer):
                 host[i, 1] = lr
                 self._steps[id(p)] = st + 1
             hyper.copy_(host, non_blocking=True)
+            ring.release()
             g0 = self.param_groups[0]
             m, v = self._moments(owner)
             shadow = getattr(owner, "_shadow", None)
@@ -232,6 +238,30 @@ class BertAdam(torch.optim.Optimizer):
                 m[off:off + n].view(p.shape).copy_(st["next_m"])
                 v[off:off + n].view(p.shape).copy_(st["next_v"])
                 self._steps[id(p)] = int(st["step"])
+
+
+class _PinnedRing:
+    """``slots`` pinned host buffers handed out round-robin; ``release()`` records a CUDA event on
+    the current stream behind the asynchronous upload that read the buffer, ``acquire()`` waits for
+    that event before the buffer is rewritten."""
+
+    def __init__(self, shape, dtype=torch.float32, slots=4):
+        self.bufs = [torch.empty(shape, dtype=dtype).pin_memory() for _ in range(slots)]
+        self.events = [None] * slots
+        self.k = -1
+
+    def acquire(self):
+        self.k = (self.k + 1) % len(self.bufs)
+        ev = self.events[self.k]
+        if ev is not None:
+            ev.synchronize()
+        return self.bufs[self.k]
+
+    def release(self):
+        ev = self.events[self.k]
+        if ev is None:
+            ev = self.events[self.k] = torch.cuda.Event()
+        ev.record()
 
 
 def cosine_with_warmup_lambda(num_warmup_steps, num_training_steps, num_cycles=0.5):

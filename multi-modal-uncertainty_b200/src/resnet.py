@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from ._backend import _lib
-from .model import FlavaFusionTransfomer, _holder_for
+from .model import FlavaFusionTransfomer, _holder_for, check_workspace, stamp_workspace
 
 
 class _ResNetForward(torch.autograd.Function):
@@ -197,6 +197,7 @@ class MIMOResNet(nn.Module):
         return ws
 
     def _engine_forward(self, x, training):
+        self._new_forward()
         if not self._flat.is_cuda:
             raise _lib.MMUError("the model lives on the CPU: call .to('cuda') first -- this "
                                 "package has no CPU execution path")
@@ -218,12 +219,16 @@ class MIMOResNet(nn.Module):
                 nb = m._buffers.get("num_batches_tracked")
                 if nb is not None:
                     nb += 1
-        return cfg, ws, x, shadow, logits
+        saved = (cfg, ws, x, shadow, logits)
+        return stamp_workspace(self, ws, saved) if training else saved
 
     _ensure_grad_views = FlavaFusionTransfomer._ensure_grad_views
+    _labels_key = staticmethod(FlavaFusionTransfomer._labels_key)
+    _new_forward = FlavaFusionTransfomer._new_forward
 
     def _engine_backward(self, saved, dlogits):
         cfg, ws, x, shadow, _ = saved
+        check_workspace(self, ws, saved)
         self._ensure_grad_views()
         _lib.check(_lib.lib.mmu_resnet_backward(C.byref(cfg), self._flat.data_ptr(), _lib.ptr(shadow),
                                                 self._stats.data_ptr(), x.data_ptr(), ws.data_ptr(),

@@ -579,6 +579,69 @@ def test_cuda_graph_train_step_equals_eager(mmu, precision):
     assert float((evg.double() - eve.double()).abs().max()) <= tol * 10 * max(1.0, float(eve.abs().max()))
 
 
+def test_overwritten_activations_fail_loudly_and_metric_cache_is_per_forward(mmu, golden):
+    """One workspace per shape holds the activations a backward needs: a second training-mode
+    forward at the same shape overwrites them, so the first forward's backward must raise instead
+    of returning wrong gradients.  And ``acc`` may reuse the loss epilogue's accumulator only for
+    the same forward AND the same labels."""
+    c = golden("flava_small.pt")["plain_E2"]
+    m = build(mmu, c["cfg"], c["state_dict"], "fp32").train()
+    x = (c["img"].cuda(), c["txt"].cuda())
+    y = c["y_train"].cuda()
+    m.zero_grad()
+    first = m.compute_loss(m(x), y)
+    second = m.compute_loss(m((x[0] * 2, x[1])), y)
+    with pytest.raises(mmu._lib.MMUError):
+        first.backward()
+    second.backward()                                    # the latest forward is intact
+    # metric cache: same logits, other labels -> recomputed, not the cached accumulator
+    logits = m(x)
+    loss = m.compute_loss(logits, y)
+    a_same = float(mmu.acc(logits, y, False, True))
+    y_other = (y + 1) % c["cfg"]["C"]
+    a_other = float(mmu.acc(logits, y_other, False, True))
+    ref_same = float((logits.detach().argmax(-1) == y).float().mean() * 100)
+    ref_other = float((logits.detach().argmax(-1) == y_other).float().mean() * 100)
+    assert a_same == pytest.approx(ref_same, abs=1e-4) and a_other == pytest.approx(ref_other, abs=1e-4)
+    loss.backward()
+
+
+def test_cuda_graph_dropped_when_baked_buffers_change(mmu):
+    """A captured step bakes in the addresses of the flat buffers, workspaces and optimiser state.
+    ``model.to()`` re-binds the parameter views and frees the cached workspaces; an optimiser
+    ``load_state_dict`` replaces the momentum tensors.  The graph entry must keep the old
+    workspace alive and must be re-captured when an owned buffer was replaced -- results stay
+    those of the eager step."""
+    import copy
+    g = torch.Generator().manual_seed(3)
+    B, E, C = 32, 4, 10
+    batches = [(torch.rand(B, 4, 1, 14, 14, generator=g), torch.randint(0, C, (B,), generator=g))
+               for _ in range(6)]
+    res = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(5)
+        m = mmu.MIMOResNet(num_channels=1, emb_dim=4, out_dim=E, num_classes=C)
+        opt = torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9)
+        tr = mmu.Model_(m, opt, None, lambda x, y, phase="train": (x, y.unsqueeze(1).repeat(1, E)),
+                        metrics=[mmu.acc], verbose=False)
+        tr.to(torch.device("cuda"))
+        m.train()
+        losses = []
+        for i, (x, y) in enumerate(batches):
+            if i == 3:
+                m.to("cuda")                                            # _rebind: workspaces freed
+                junk = torch.full((1 << 22,), float("nan"), device="cuda")  # recycle freed blocks
+                opt.load_state_dict(copy.deepcopy(opt.state_dict()))    # new momentum tensors
+                del junk
+            losses.append(float(tr.train_step(x, y, cuda_graph=(mode == "graph"))[0]))
+        res[mode] = (losses, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()},
+                     getattr(tr, "_graphed", None))
+    assert all(abs(a - b) <= 5e-5 * max(1.0, abs(a)) for a, b in zip(res["eager"][0], res["graph"][0]))
+    for k, v in res["eager"][1].items():
+        assert float((v.double() - res["graph"][1][k].double()).abs().max()) <= 5e-4 * max(1.0, float(v.abs().max())), k
+    assert all(torch.isfinite(v.double()).all() for v in res["graph"][1].values())
+
+
 def test_cuda_graph_rejects_host_stepped_optimizers(mmu):
     m = mmu.MIMOTransfomer(out_dim=2, num_classes=3, hidden_size=48, multimodal_num_hidden_layers=1,
                            multimodal_num_attention_heads=2).cuda()

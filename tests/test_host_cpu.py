@@ -254,6 +254,65 @@ def test_trainer_protocol_with_a_plain_torch_model(mmu, tmp_path):
         trainer.eval_loop(val, "val", vilt=True)
 
 
+def test_train_loop_deferred_readback_gives_the_same_epoch_logs(mmu):
+    """``train_loop(..., metrics_every=N)`` keeps loss / metrics on the device and reads the
+    size-weighted sums back every N steps and at epoch end: same epoch means as the reference's
+    per-step ``.item()`` protocol (src/framework.py:305-312), NaN stop rule kept."""
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = torch.nn.Linear(6, 3 * 2)
+            self.poison = False
+        def forward(self, x):
+            img, txt = x
+            return self.fc(torch.cat([img.mean(1), txt.mean(1)], -1)).view(-1, 2, 3)
+        def compute_loss(self, y_hat, y, eval=False):
+            y_hat = y_hat.mean(1) if eval else y_hat.reshape(-1, 3)
+            loss = torch.nn.functional.cross_entropy(y_hat, y.reshape(-1))
+            return loss * float("nan") if self.poison else loss
+    def acc(y_pred, y_true, eval, dummy_dim=False):
+        y_pred = y_pred.mean(1) if eval else y_pred.reshape(-1, 3)
+        return (y_pred.argmax(1) == y_true.reshape(-1)).float().mean() * 100
+    from functools import partial
+    logs = {}
+    for every in (1, 3, 100):
+        torch.manual_seed(0)
+        train, val, _ = mmu.dataset.get_synthetic_flava(4, 28, 8, 8, l_img=3, l_txt=2, dim=3, num_classes=3)
+        net = Tiny()
+        opt = torch.optim.SGD(net.parameters(), lr=0.1)
+        trainer = mmu.Model_(net, opt, None, partial(mmu.dataset.data_forming_func_transformer,
+                                                     model_type="MultiHead"), metrics=[acc], verbose=False)
+        trainer.to(torch.device("cpu"))
+        out, batch_logs = [], []
+        cb = mmu.src.callbacks.LambdaCallback(on_epoch_end=lambda e, l: out.append(dict(l)),
+                                              on_batch_end=lambda b, l: batch_logs.append(dict(l)))
+        trainer.train_loop(train, valid_generator=val, epochs=2, steps_per_epoch=len(train),
+                           validation_steps=len(val), callbacks=[cb], scheduler_step_on="batch",
+                           metrics_every=every)
+        logs[every] = out
+        assert len(out) == 2 and len(batch_logs) == 2 * len(train)
+        assert ("deferred" in batch_logs[0]) == (every > 1)
+    for every in (3, 100):
+        for a, b in zip(logs[1], logs[every]):
+            assert a["loss"] == pytest.approx(b["loss"], rel=1e-6) and a["acc"] == pytest.approx(b["acc"], abs=1e-4)
+            assert a["val_loss"] == pytest.approx(b["val_loss"], rel=1e-6)
+    # NaN loss stops training at the end of the epoch in both protocols
+    for every in (1, 4):
+        torch.manual_seed(0)
+        train, _, _ = mmu.dataset.get_synthetic_flava(4, 12, 8, 8, l_img=3, l_txt=2, dim=3, num_classes=3)
+        net = Tiny()
+        net.poison = True
+        trainer = mmu.Model_(net, torch.optim.SGD(net.parameters(), lr=0.1), None,
+                             partial(mmu.dataset.data_forming_func_transformer, model_type="MultiHead"),
+                             metrics=[acc], verbose=False)
+        trainer.to(torch.device("cpu"))
+        seen = []
+        trainer.train_loop(train, epochs=5, steps_per_epoch=len(train), scheduler_step_on="batch",
+                           callbacks=[mmu.src.callbacks.LambdaCallback(on_epoch_end=lambda e, l: seen.append(e))],
+                           metrics_every=every)
+        assert seen == [1]
+
+
 def test_trainer_mmbt_branch_with_a_plain_torch_model(mmu, monkeypatch):
     """The ``mmbt`` branches of Model_ (reference src/framework.py:246-304, :172-176): ``model(*x)``,
     per-epoch freeze flags on ``enc.img_encoder`` / ``enc.encoder``, gradient-accumulation stepping,
