@@ -30,12 +30,15 @@ pytestmark = pytest.mark.gpu
 CFG = dict(B=128, l_img=197, l_txt=40, D=768, heads=3, layers=3, E=5, C=101)
 
 # bf16 path at this size: bounds (<= 3x the measured values printed by the tests)
-BF16_LOGIT_TOL = 1.5e-2      # max |dlogit| / max |logit|
-BF16_LOSS_TOL = 3e-3         # relative
+# measured on a B200 (round 2): logits 2.9e-3 .. 3.0e-3, loss 8.4e-5, worst gradient 7.4e-3 (1.28e-2
+# with a modality mask), 2 of 640 per-head argmax flips, 7 / 6 of 1 280 sweep predictions (mean
+# logits / mean probabilities), 5 of 1 280 confidence bins moved, ECE 0.17927 vs 0.17929
+BF16_LOGIT_TOL = 9e-3        # max |dlogit| / max |logit|
+BF16_LOSS_TOL = 2.5e-4       # relative
 BF16_GRAD_TOL = 3e-2         # max |dg| / max |g| per tensor
-BF16_MAX_ROW_FLIPS = 16      # of B*E = 640 per-head argmax rows (train protocol)
-BF16_MAX_SWEEP_FLIPS = 40    # of 1 280 (level, sample) head-mean predictions
-BF16_MAX_BIN_MOVES = 64      # samples whose confidence bin differs, of 1 280
+BF16_MAX_ROW_FLIPS = 6       # of B*E = 640 per-head argmax rows (train protocol)
+BF16_MAX_SWEEP_FLIPS = 20    # of 1 280 (level, sample) head-mean predictions
+BF16_MAX_BIN_MOVES = 15      # samples whose confidence bin differs, of 1 280
 
 
 @pytest.fixture(scope="module")
@@ -240,7 +243,7 @@ def test_headline_packed_sweep_bf16_vs_oracle(mmu, case, sweep_oracle):
     assert r["e_logit"] < BF16_LOGIT_TOL
     assert r["flips_logit"] <= BF16_MAX_SWEEP_FLIPS and r["flips_prob"] <= BF16_MAX_SWEEP_FLIPS
     assert r["moved"] <= BF16_MAX_BIN_MOVES
-    assert abs(r["ece"][0] - r["ece"][1]) < 5e-3
+    assert abs(r["ece"][0] - r["ece"][1]) < 1e-3
 
 
 @pytest.mark.parametrize("mode", ["random", "guided"])
@@ -264,7 +267,7 @@ def test_headline_keep_mask_vs_oracle(mmu, case, mode):
         errs = grad_errors(m, ref_grads)
         worst = max((v[0], k) for k, v in errs.items() if v[1] > 0)
         print(f"\n[headline keep_mask {mode} {precision}] logits {e_logit:.2e}  worst grad {worst[0]:.2e} ({worst[1]})")
-        assert e_logit < tl and abs(loss - float(ref_loss)) < max(tl, 3e-3) * abs(float(ref_loss))
+        assert e_logit < tl and abs(loss - float(ref_loss)) < (1e-3 if precision == "fp32" else BF16_LOSS_TOL) * abs(float(ref_loss))
         if precision == "fp32":
             assert torch.equal(logits.argmax(-1), ref_logits.argmax(-1))
         for k, (e, scale) in errs.items():
@@ -299,7 +302,7 @@ def test_headline_avg_pool_all_tokens_live(mmu):
         print(f"\n[headline avg_pool {precision}] logits {e_logit:.2e}  loss "
               f"{abs(float(loss.detach()) - float(ref_loss)) / float(ref_loss):.2e}  worst grad {worst[0]:.2e} ({worst[1]})")
         assert e_logit < tl
-        assert abs(float(loss.detach()) - float(ref_loss)) < max(tl, 3e-3) * float(ref_loss)
+        assert abs(float(loss.detach()) - float(ref_loss)) < (1e-3 if precision == "fp32" else BF16_LOSS_TOL) * float(ref_loss)
         if precision == "fp32":
             assert torch.equal(logits.detach().cpu().argmax(-1), ref_logits.argmax(-1))
         for k, (e, scale) in errs.items():

@@ -4,7 +4,7 @@ make_golden_mmbt.py; BERT arithmetic restated from the absent third-party packag
 oracle/bert_restated.py) and against the CPU oracle.
 
 Tolerances: fp32 path 1e-3 relative on logits / loss / gradients, argmax bit-exact; bf16 tensor-core
-path 6e-2 of max|logit| and 0.2 of max|grad| per tensor (as for the fusion model)."""
+path 1.6e-2 of max|logit| and 5e-2 of max|grad| per tensor (<= 3x what a B200 measures)."""
 import os
 import sys
 import types
@@ -17,8 +17,10 @@ from det_params import det_image_encoder_state, digest_error  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-BF16_LOGIT_TOL = 6e-2
-BF16_GRAD_TOL = 0.2
+# <= 3x the errors measured on a B200 (gpurun_out/measured_errors.json):
+# logits 2.5e-3 .. 5.4e-3, image-encoder tokens 6.6e-3, gradients 1.67e-2, d loss / d tokens 1.1e-2
+BF16_LOGIT_TOL = 1.6e-2
+BF16_GRAD_TOL = 5e-2
 
 
 @pytest.fixture(scope="module")
@@ -89,7 +91,7 @@ def test_fp32_loss_and_gradients_match_reference(mmu, golden, name):
             assert float((p.grad.cpu() - g).abs().max()) < 1e-3 * scale, (k, rel(p.grad.cpu(), g))
 
 
-def test_bf16_tensor_core_path(mmu, golden):
+def test_bf16_tensor_core_path(mmu, golden, measured):
     c = golden("mmbt_small.pt")["hd64"]  # head_dim 64: sequence-axis attention on tcgen05
     m = build(mmu, c, "bf16").train()
     m.zero_grad()
@@ -97,6 +99,9 @@ def test_bf16_tensor_core_path(mmu, golden):
     logits = m(c["txt"].cuda(), c["mask"].cuda(), c["segment"].cuda(), tokens)
     loss = m.compute_loss(logits, c["y"].cuda())
     loss.backward()
+    measured("mmbt_small/bf16/logits", rel(logits.detach().cpu(), c["logits_train"]))
+    measured("mmbt_small/bf16/loss", abs(float(loss) - float(c["loss"])) / abs(float(c["loss"])))
+    measured("mmbt_small/bf16/dimg", rel(tokens.grad.cpu(), c["dimg_tokens"]))
     assert rel(logits.detach().cpu(), c["logits_train"]) < BF16_LOGIT_TOL
     assert abs(float(loss) - float(c["loss"])) < BF16_LOGIT_TOL * abs(float(c["loss"]))
     assert rel(tokens.grad.cpu(), c["dimg_tokens"]) < BF16_GRAD_TOL
@@ -105,16 +110,18 @@ def test_bf16_tensor_core_path(mmu, golden):
         g = c["grads"][k]
         if float(g.abs().max()) < 1e-5 * gmax:
             continue
+        measured("mmbt_small/bf16/grad", rel(p.grad.cpu(), g))
         assert rel(p.grad.cpu(), g) < BF16_GRAD_TOL, (k, rel(p.grad.cpu(), g))
     m.eval()
     with torch.no_grad():
         for modal, d in c["control"].items():
             out = m.forward_indices(c["txt"].cuda(), c["mask"].cuda(), c["segment"].cuda(), c["img_tokens"].cuda(),
                                     [int(i) for i in d["indices"]]).cpu()
+            measured("mmbt_small/bf16/control_logits", rel(out, d["logits"]))
             assert rel(out, d["logits"]) < BF16_LOGIT_TOL
 
 
-def test_fp32_vs_oracle_at_seq_above_one_tile(mmu):
+def test_fp32_vs_oracle_at_seq_above_one_tile(mmu, measured):
     """A longer ragged batch (S = 3 + 2 + 150 = 155 > 128: several attention tiles) held to the CPU
     oracle on the same seeded inputs, both precisions."""
     from oracle import mmbt as O
@@ -148,12 +155,15 @@ def test_fp32_vs_oracle_at_seq_above_one_tile(mmu):
         logits = m(txt.cuda(), mask.cuda(), segment.cuda(), t)
         loss = m.compute_loss(logits, y.cuda())
         loss.backward()
+        measured(f"mmbt_s155/{prec}/logits", rel(logits.detach().cpu(), ref_logits))
+        measured(f"mmbt_s155/{prec}/dimg", rel(t.grad.cpu(), ref_dtok))
         assert rel(logits.detach().cpu(), ref_logits) < ltol, prec
         assert abs(float(loss) - float(ref_loss)) < ltol * abs(float(ref_loss)), prec
         assert rel(t.grad.cpu(), ref_dtok) < gtol, prec
         for k, p in m.named_parameters():
             if float(ref_grads[k].abs().max()) < 1e-5 * gmax:
                 continue
+            measured(f"mmbt_s155/{prec}/grad", rel(p.grad.cpu(), ref_grads[k]))
             assert rel(p.grad.cpu(), ref_grads[k]) < gtol, (prec, k, rel(p.grad.cpu(), ref_grads[k]))
 
 
@@ -229,7 +239,7 @@ def test_image_encoder_fp32_matches_reference(mmu, golden, name):
             assert rel(sd[k].cpu(), v) < 1e-4, k
 
 
-def test_image_encoder_bf16_and_full_mmbt_from_images(mmu, golden):
+def test_image_encoder_bf16_and_full_mmbt_from_images(mmu, golden, measured):
     """Tensor-core convolutions (bf16 operands) against the golden tokens, then the whole
     MultimodalBertClf from raw images: image encoder -> tokens -> BERT trunk, gradients reaching the
     ResNet stem."""
@@ -237,6 +247,7 @@ def test_image_encoder_bf16_and_full_mmbt_from_images(mmu, golden):
     enc = _encoder(mmu, c, "bf16").eval()
     with torch.no_grad():
         tok = enc(c["x"].cuda()).cpu()
+    measured("image_encoder/bf16/tokens", rel(tok, c["tokens_eval"]))
     assert rel(tok, c["tokens_eval"]) < BF16_LOGIT_TOL
     cos = torch.nn.functional.cosine_similarity(tok.flatten().double(), c["tokens_eval"].flatten().double(), dim=0)
     assert float(cos) > 0.999

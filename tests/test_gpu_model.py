@@ -11,8 +11,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 SMALL = ["plain_E2", "plain_E1", "avgpool_E2", "cls_E3", "plain_E5_h3"]
-BF16_LOGIT_TOL = 6e-2   # relative to max |logit|
-BF16_GRAD_TOL = 0.2     # relative to max |grad| of the tensor
+# bf16 path bounds: <= 3x the errors MEASURED on a B200 (tests/conftest.py writes them to
+# gpurun_out/measured_errors.json; round-2 values in DESIGN.md section 2): logits 8.6e-3 / 5.8e-3 /
+# 3.3e-3 (small goldens / D=768 golden / MIMOTransfomer), loss 7.1e-4, gradients 1.05e-2 of max|g|
+BF16_LOGIT_TOL = 2.5e-2   # relative to max |logit|
+BF16_LOSS_TOL = 2e-3      # relative
+BF16_GRAD_TOL = 3e-2      # relative to max |grad| of the tensor
 
 
 @pytest.fixture(scope="module")
@@ -82,7 +86,7 @@ def test_fp32_matches_reference_goldens(mmu, golden, name):
 
 
 @pytest.mark.parametrize("name", SMALL)
-def test_bf16_tensor_core_path(mmu, golden, name):
+def test_bf16_tensor_core_path(mmu, golden, name, measured):
     c = golden("flava_small.pt")[name]
     cfg = c["cfg"]
     m = build(mmu, cfg, c["state_dict"], "bf16").train()
@@ -90,17 +94,21 @@ def test_bf16_tensor_core_path(mmu, golden, name):
     logits = m((c["img"].cuda(), c["txt"].cuda()))
     loss = m.compute_loss(logits, c["y_train"].cuda())
     loss.backward()
+    measured("flava_small/bf16/logits", rel(logits.detach().cpu(), c["logits"]))
+    measured("flava_small/bf16/loss", abs(float(loss) - float(c["loss"])) / max(1.0, abs(float(c["loss"]))))
     assert rel(logits.detach().cpu(), c["logits"]) < BF16_LOGIT_TOL
-    assert abs(float(loss) - float(c["loss"])) < BF16_LOGIT_TOL * max(1.0, abs(float(c["loss"])))
+    assert abs(float(loss) - float(c["loss"])) < BF16_LOSS_TOL * max(1.0, abs(float(c["loss"])))
     for k, p in m.named_parameters():
         g = c["grads"][k]
         scale = float(g.abs().max())
         if scale > 1e-5:
+            measured("flava_small/bf16/grad", float((p.grad.cpu() - g).abs().max()) / scale)
             assert float((p.grad.cpu() - g).abs().max()) < BF16_GRAD_TOL * scale, k
 
 
-@pytest.mark.parametrize("precision,tol,gtol", [("fp32", 1e-3, 2e-3), ("bf16", BF16_LOGIT_TOL, 0.25)])
-def test_full_width_model(mmu, golden, precision, tol, gtol):
+# bf16 at D=768 (measured: logits 5.8e-3, |grad| L1 sums 9.2e-4, 64-element gradient slices 1.9e-2)
+@pytest.mark.parametrize("precision,tol,gtol", [("fp32", 1e-3, 2e-3), ("bf16", 1.7e-2, 3e-3)])
+def test_full_width_model(mmu, golden, precision, tol, gtol, measured):
     """D=768, 3 heads (hd=256), 3 layers, E=5, C=101: the Food-101-shaped model."""
     from tests.golden.make_golden import det_state_dict
     c = golden("flava_768.pt")
@@ -110,6 +118,7 @@ def test_full_width_model(mmu, golden, precision, tol, gtol):
     logits = m((c["img"].cuda(), c["txt"].cuda()))
     loss = m.compute_loss(logits, c["y_train"].cuda())
     loss.backward()
+    measured(f"flava_768/{precision}/logits", rel(logits.detach().cpu(), c["logits"]))
     assert rel(logits.detach().cpu(), c["logits"]) < tol
     assert abs(float(loss) - float(c["loss"])) < tol * float(c["loss"])
     if precision == "fp32":
@@ -119,10 +128,13 @@ def test_full_width_model(mmu, golden, precision, tol, gtol):
         if float(s[1]) < 1e-6:
             continue
         g = p.grad.double().cpu()
+        measured(f"flava_768/{precision}/grad_l1", abs(float(g.abs().sum()) - float(s[1])) / float(s[1]))
         assert abs(float(g.abs().sum()) - float(s[1])) < gtol * float(s[1]), k
         sl = c["grad_slices"][k]
         scale = max(float(sl.abs().max()), 1e-6)
-        assert float((p.grad.reshape(-1)[:64].cpu() - sl).abs().max()) < max(gtol, 5e-3) * scale + 1e-6, k
+        measured(f"flava_768/{precision}/grad_slice", float((p.grad.reshape(-1)[:64].cpu() - sl).abs().max()) / scale)
+        slice_tol = 5e-3 if precision == "fp32" else 5.5e-2
+        assert float((p.grad.reshape(-1)[:64].cpu() - sl).abs().max()) < slice_tol * scale + 1e-6, k
 
 
 def test_fp32_vs_oracle_mid_size(mmu):
@@ -339,8 +351,9 @@ def test_packed_variants_equal_per_variant_forwards(mmu, golden, name, precision
     assert all(mt["n_samples"] == img.shape[0] for mt in metrics)
 
 
-@pytest.mark.parametrize("precision,tol_l,tol_g", [("fp32", 1e-3, 2e-2), ("bf16", BF16_LOGIT_TOL, 0.25)])
-def test_mimo_transformer_matches_reference_golden(mmu, golden, precision, tol_l, tol_g):
+# bf16 measured: logits 3.3e-3, gradients 6.8e-3
+@pytest.mark.parametrize("precision,tol_l,tol_g", [("fp32", 1e-3, 1e-3), ("bf16", 1e-2, 2e-2)])
+def test_mimo_transformer_matches_reference_golden(mmu, golden, precision, tol_l, tol_g, measured):
     """MIMOTransfomer (reference src/model.py:114-171) on the same engine: logits, loss, every
     gradient against the golden frozen from the unmodified reference module."""
     c = golden("mimo_transformer.pt")
@@ -356,6 +369,7 @@ def test_mimo_transformer_matches_reference_golden(mmu, golden, precision, tol_l
     logits = m(c["x"].cuda())
     loss = m.compute_loss(logits, c["y_train"].cuda())
     loss.backward()
+    measured(f"mimo_transformer/{precision}/logits", rel(logits.detach().cpu(), c["logits"]))
     assert rel(logits.detach().cpu(), c["logits"]) < tol_l
     assert abs(float(loss.detach()) - float(c["loss"])) < tol_l * max(1.0, abs(float(c["loss"])))
     if precision == "fp32":
@@ -363,6 +377,7 @@ def test_mimo_transformer_matches_reference_golden(mmu, golden, precision, tol_l
     for k, p in m.named_parameters():
         g = c["grads"][k]
         if float(g.abs().max()) > 1e-5:
+            measured(f"mimo_transformer/{precision}/grad", float((p.grad.cpu() - g).abs().max() / g.abs().max()))
             assert float((p.grad.cpu() - g).abs().max() / g.abs().max()) < tol_g, k
     opt.step()
     # the four-view zero-fill sweep (eval_robustness.py:82-121) against per-view forwards
@@ -480,7 +495,7 @@ def test_full_baseline_size_properties(mmu):
     assert all(np.isfinite(losses)) and losses[1] < losses[0]
 
 
-def test_mimo_resnet_tensor_core_path(mmu, golden):
+def test_mimo_resnet_tensor_core_path(mmu, golden, measured):
     """MIMOResNet with precision='bf16': convolutions on the tcgen05 GEMM (bf16 operands, fp32
     accumulation and BatchNorm).  bf16 tolerance: 6e-2 of max|logit|; 0.35 of max|grad| per tensor
     on the golden (batch 4-6: bf16 rounding flips ReLU masks the golden's 2e-5 margin protects, and
@@ -497,9 +512,12 @@ def test_mimo_resnet_tensor_core_path(mmu, golden):
     logits = m(c["x"].cuda())
     loss = m.compute_loss(logits, c["y_train"].cuda())
     loss.backward()
+    measured("mimo_resnet/bf16/logits", rel(logits.detach().cpu(), c["logits"]))
     assert rel(logits.detach().cpu(), c["logits"]) < BF16_LOGIT_TOL
     assert abs(float(loss.detach()) - float(c["loss"])) < BF16_LOGIT_TOL * abs(float(c["loss"]))
+    assert rel(logits.detach().cpu(), c["logits"]) < 1.5e-2      # measured 4.8e-3
     for k, p in m.named_parameters():
+        measured("mimo_resnet/bf16/grad_golden_batch6", rel(p.grad.cpu(), c["grads"][k]))
         assert rel(p.grad.cpu(), c["grads"][k]) < 0.35, (k, rel(p.grad.cpu(), c["grads"][k]))
     # batch 64: fp32 engine vs tensor-core engine on the same weights, then a few SGD steps
     g = torch.Generator().manual_seed(9)
@@ -509,12 +527,14 @@ def test_mimo_resnet_tensor_core_path(mmu, golden):
     ref.load_state_dict(c["state_dict"], strict=True)
     ref.cuda().train()
     m.load_state_dict(c["state_dict"], strict=True)
-    assert rel(m(x).detach(), ref(x).detach()) < BF16_LOGIT_TOL
+    measured("mimo_resnet/bf16/logits_b64_vs_fp32_engine", rel(m(x).detach(), ref(x).detach()))
+    assert rel(m(x).detach(), ref(x).detach()) < 1.5e-2          # measured 5.2e-3
     for net in (m, ref):
         net.zero_grad()
         net.compute_loss(net(x), y).backward()
     for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
         cos = torch.nn.functional.cosine_similarity(p.grad.flatten().double(), q.grad.flatten().double(), dim=0)
+        measured("mimo_resnet/bf16/one_minus_cos_b64", 1.0 - float(cos))
         assert float(cos) >= 0.97, (k, float(cos))
     m.load_state_dict(c["state_dict"], strict=True)
     opt = torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9)
