@@ -215,13 +215,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         const int mnb = tile % mn_total;
         const int g = mnb / (m_tiles * n_tiles);
         const int mn = mnb % (m_tiles * n_tiles);
-#ifdef MMU_DBG_SAME_TILE   // timing experiment only: every cluster loads the SAME panels
-        const int m0 = rank * BM + 0 * mn;
-        const int n0 = rank * G::B_ROWS;
-#else
         const int m0 = (mn / n_tiles) * G::BM_TILE + rank * BM;   // this CTA's 128 rows of A
         const int n0 = (mn % n_tiles) * BN + rank * G::B_ROWS;    // pair: this CTA's half of B
-#endif
         const int kb0 = split * kb_per;
         const int kb1 = min(kb_total, kb0 + kb_per);
         const int a_mid = p.batch > 0 ? g / p.a_hdiv : 0;
@@ -383,30 +378,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         ptx::mbar_arrive_expect_tx(&my_aux[c & 1], BOX_BYTES);
         ptx::tma_load_4d(box0 + (c & 1) * BOX_BYTES, &tma_c1, &my_aux[c & 1], n0 + c * NCOL, m0, c2, c3);
       };
-#ifdef MMU_Z_DIRECT
-      // z straight from global memory into registers (each lane: the 64 contiguous bytes of its
-      // row), one chunk ahead: no TMA load into the staging boxes, no LDS -- half the epilogue's
-      // shared-memory traffic
-      uint4 zr[2][4];
-      const int zrow = m0 + lane;
-      auto load_zg = [&](int c) {
-        const __nv_bfloat16* zp = static_cast<const __nv_bfloat16*>(e.aux) +
-                                  static_cast<long long>(zrow) * e.ld_aux + (n0 + c * NCOL);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          zr[c & 1][k] = make_uint4(0u, 0u, 0u, 0u);
-          if (zrow < p.M && n0 + c * NCOL + 8 * k < p.N)
-            zr[c & 1][k] = __ldg(reinterpret_cast<const uint4*>(zp + 8 * k));
-        }
-      };
-      if (MODE == EPI_DGELU && active) load_zg(0);
-#else
       if (MODE == EPI_DGELU && active && lane == 0) {
         ptx::bulk_wait_read<0>();  // the previous tile's stores have drained both boxes
         load_z(0);
         if (n0 + NCOL < p.N) load_z(1);
       }
-#endif
 
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
@@ -549,21 +525,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
               ptx::sts_v4(box + piece(k), make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
             box_store(&tma_c0, box, col0);
           } else if constexpr (MODE == EPI_DGELU) {
-#ifdef MMU_Z_DIRECT
-            if (c + 1 < NCHUNK && col0 + NCOL < p.N) load_zg(c + 1);
-            box_free(c == 0);
-#else
             ptx::mbar_wait(&my_aux[c & 1], aux_phase[c & 1]);
             aux_phase[c & 1] ^= 1;
-#endif
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t a = box + piece(k);
-#ifdef MMU_Z_DIRECT
-              const uint4 z = zr[c & 1][k];
-#else
               const uint4 z = ptx::lds_v4u(a);
-#endif
               const uint32_t zz[4] = {z.x, z.y, z.z, z.w};
               uint32_t o[4];
               if (e.act == 1) {
@@ -580,29 +547,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
               ptx::sts_v4u(a, o[0], o[1], o[2], o[3]);
             }
             box_store(&tma_c0, box, col0);
-#ifndef MMU_Z_DIRECT
             if (c + 2 < NCHUNK && col0 + 2 * NCOL < p.N && lane == 0) {
               ptx::bulk_wait_read<0>();  // the store above has read the box: refill it
               load_z(c + 2);
             }
-#endif
           } else if constexpr (MODE == EPI_QUICKGELU) {
-#ifdef MMU_Z_DIRECT
-            if (e.out != nullptr) {  // training: z leaves straight from the registers
-              const int zrow = m0 + lane;
-              __nv_bfloat16* zp = static_cast<__nv_bfloat16*>(e.out) +
-                                  static_cast<long long>(zrow) * e.ld_out + col0;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (zrow < p.M && col0 + 8 * k < p.N)
-                  *reinterpret_cast<uint4*>(zp + 8 * k) =
-                      make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
-                                 pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
-            }
-            if (false) {
-#else
             if (e.out != nullptr) {  // training: z -> box 0, u -> box 1, each its own bulk group
-#endif
               box_free(c == 0);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -619,13 +569,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
 #pragma unroll
               for (int i = 0; i < NCOL; ++i) v[i] = quick_gelu(v[i]);
             }
-#ifdef MMU_Z_DIRECT
-            const uint32_t ubox = box;
-            box_free(c == 0);
-#else
             const uint32_t ubox = e.out != nullptr ? box0 + BOX_BYTES : box;
             box_free(e.out == nullptr && c == 0);
-#endif
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               ptx::sts_v4u(ubox + piece(k), pack_bf16x2(v[8 * k], v[8 * k + 1]),

@@ -1,8 +1,11 @@
 mkdir -p gpurun_out
-for v in base same zdir; do
-  for c in 7 8 9 10 11 19; do
-    MMU_FORCE_TIMING=1 timeout 120 ./build/gemm_harness_$v $c 2>&1 | grep -E "RESULT|TIMING|error|Error" | sed "s/^/[$v] /"
+{
+for c in 0 1 2 3 4 5 13 14 15 16 17 18; do timeout 120 ./build/gemm_harness_s5 $c 2>&1 | grep -E "RESULT|error|Error|timed out" | sed "s/^/[s5] /"; done
+for v in s5 s4; do
+  for c in 6 7 8 9 10 11 12 19 20 21; do
+    timeout 120 ./build/gemm_harness_$v $c 2>&1 | grep -E "RESULT|TIMING|error|Error|timed out" | sed "s/^/[$v] /"
   done
-done > gpurun_out/r2_harness_variants.log 2>&1
-cat gpurun_out/r2_harness_variants.log
-python -m pytest tests -x -q -m gpu > gpurun_out/r2_gpu_suite.log 2>&1; echo "suite exit $?"; tail -3 gpurun_out/r2_gpu_suite.log
+done
+} > gpurun_out/r2_harness_s5.log 2>&1
+cat gpurun_out/r2_harness_s5.log
+timeout 900 python -m pytest tests/test_gpu_ops.py -x -q > gpurun_out/r2_ops_tests.log 2>&1; echo "ops exit $?"; tail -3 gpurun_out/r2_ops_tests.log
