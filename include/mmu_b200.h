@@ -55,6 +55,11 @@ MMU_API const char* mmu_version(void);
 MMU_API const char* mmu_error_string(int code);
 /* Number of CUDA kernels this library has launched so far in this process (host counter). */
 MMU_API long long mmu_launch_count(void);
+/* SM budget of the persistent tensor-core GEMM grids: n > 0 limits them to n SMs, 0 restores all.
+ * Returns the budget in effect.  Host-side, process-wide; used by the data-parallel wrapper while an
+ * NCCL gradient all-reduce shares the GPU with the backward pass (no reference counterpart: the
+ * reference has no distributed code). */
+MMU_API int mmu_set_gemm_sm_limit(int n);
 /* sizeof() of the ABI structs as compiled into the library, so a binding can verify its mirror:
  * 0 mmu_flava_config, 1 mmu_flava_inputs, 2 mmu_gemm_epilogue, 3 mmu_metric_accum,
  * 4 mmu_param_entry, 5 mmu_posthoc_accum; -1 for anything else. */

@@ -28,7 +28,7 @@ EXPORTS = [
     "mmu_mmbt_backward", "mmu_bertadam_flat_step",
     "mmu_imgenc_param_count", "mmu_imgenc_stat_count", "mmu_imgenc_param_table", "mmu_imgenc_stat_table",
     "mmu_imgenc_workspace_bytes", "mmu_imgenc_forward", "mmu_imgenc_backward",
-    "mmu_seq_attention_fwd", "mmu_seq_attention_bwd", "mmu_modality_keep_mask",
+    "mmu_seq_attention_fwd", "mmu_seq_attention_bwd", "mmu_modality_keep_mask", "mmu_set_gemm_sm_limit",
 ]
 
 
@@ -118,6 +118,7 @@ def _load():
     lib.mmu_gemm.argtypes = [i, vp, ll, i, vp, ll, i, i, i, i, i, C.POINTER(GemmEpilogue), vp]
     lib.mmu_mask_gather_tokens.argtypes = [vp, vp, i, i, i, i, vp, i, vp, i, vp]
     lib.mmu_struct_size.argtypes = [i]
+    lib.mmu_set_gemm_sm_limit.argtypes = [i]
     rcfgp = C.POINTER(ResNetConfig)
     for fn in (lib.mmu_resnet_param_count, lib.mmu_resnet_stat_count):
         fn.restype, fn.argtypes = ll, [rcfgp]

@@ -41,6 +41,11 @@ const char* mmu_version(void) { return "mmu_b200 0.1 (sm_100a)"; }
 
 long long mmu_launch_count(void) { return launch_count(); }
 
+int mmu_set_gemm_sm_limit(int n) {
+  set_gemm_sm_limit(n);
+  return gemm_sms();
+}
+
 int mmu_struct_size(int which) {
   switch (which) {
     case 0: return static_cast<int>(sizeof(mmu_flava_config));

@@ -18,6 +18,10 @@ namespace mmu {
 void count_launch(int n = 1);
 long long launch_count();
 int sm_count();
+// SM budget of the persistent tcgen05 GEMM grids (0 = every SM); see gemm_tcgen05.cu
+void set_gemm_sm_limit(int n);
+int gemm_sm_limit();
+int gemm_sms();
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, long long inner, long long outer,
                       long long ld, int box_inner, int box_outer);
 // 3-D (inner contiguous, mid, outer; element strides), box = box_inner x 1 x box_outer, SWIZZLE_128B

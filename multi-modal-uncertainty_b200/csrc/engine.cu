@@ -268,7 +268,7 @@ GemmEpilogue epi(int mode, void* out, int out_bf16, long long ld_out, const floa
 int wgrad_splits(int Mg, int Ng, int K) {
   const bool pair = Mg >= 512;
   const int tiles = ((Mg + (pair ? 255 : 127)) / (pair ? 256 : 128)) * ((Ng + 255) / 256);
-  const int units = pair ? sm_count() / 2 : sm_count();
+  const int units = pair ? gemm_sms() / 2 : gemm_sms();
   const int kb = (K + 63) / 64;
   int smax = kb / 4;
   if (smax > 16) smax = 16;

@@ -78,6 +78,19 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, long long inner, long 
   return r == CUDA_SUCCESS ? 0 : MMU_ERR_TMAP;
 }
 
+// SMs the persistent GEMM grids may occupy (0 = all).  The data-parallel wrapper lowers it while a
+// gradient all-reduce runs next to the backward: a persistent grid of 148 CTAs that finds some SMs
+// taken by NCCL's CTAs runs its last CTAs -- each with a full static share of the tiles -- AFTER the
+// others, which can double the kernel; a grid sized to the SMs that are really free cannot.
+static std::atomic<int> g_sm_limit{0};
+void set_gemm_sm_limit(int n) { g_sm_limit.store(n < 0 ? 0 : n, std::memory_order_relaxed); }
+int gemm_sm_limit() { return g_sm_limit.load(std::memory_order_relaxed); }
+int gemm_sms() {
+  const int lim = g_sm_limit.load(std::memory_order_relaxed);
+  const int n = sm_count();
+  return (lim > 0 && lim < n) ? (lim < 2 ? 2 : lim) : n;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -191,12 +204,12 @@ int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   const long long n_tiles = (p.N + BN - 1) / BN;
   if (use_pair(p)) {
     const long long tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * n_tiles * p.splits;
-    const long long clusters = sm_count() / 2;
+    const long long clusters = gemm_sms() / 2;
     const int grid = 2 * static_cast<int>(tiles < clusters ? tiles : clusters);
     return launch_kernel<MODE, OBF, 2>(grid, ta, tb, c0, c1, p, e, stream);
   }
   const long long tiles = nbatch * ((p.M + BM - 1) / BM) * n_tiles * p.splits;
-  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  const int grid = static_cast<int>(tiles < gemm_sms() ? tiles : gemm_sms());
   return launch_kernel<MODE, OBF, 1>(grid, ta, tb, c0, c1, p, e, stream);
 }
 

@@ -81,35 +81,102 @@ class DataParallel:
     """Attach to a model + FusedAdamW pair:  ``ddp = DataParallel(model, optimizer)``.
 
     After that ``loss.backward()`` runs the engine backward stage by stage and launches the
-    gradient all-reduce of each finished stage on a communication stream; ``optimizer.step()``
-    waits for them and applies the averaged gradient."""
+    gradient all-reduce of each finished bucket on a communication stream; ``optimizer.step()``
+    waits for them and applies the averaged gradient.
 
-    def __init__(self, model, optimizer, group=None, overlap=True):
-        self.model, self.optimizer, self.group, self.overlap = model, optimizer, group, overlap
+    The backward's persistent tcgen05 GEMM grids and NCCL's CTAs share the SMs.  Left alone
+    (r01), a 148-CTA GEMM grid that finds some SMs taken runs its last CTAs -- each with a full
+    static share of the tiles -- after the others (``profiles/r02_ddp_attribution.json``).  So:
+
+    * ``nccl_max_ctas`` (default 8): the gradient all-reduces run on a communicator of their own
+      whose CTA count is capped (``ncclConfig_t.maxCTAs``); NVSwitch reduces in the fabric (NVLS),
+      a few CTAs saturate it;
+    * ``reserve_sms`` (default = ``nccl_max_ctas``): while the backward runs, the GEMM grids are
+      sized to the remaining SMs (``mmu_set_gemm_sm_limit``), so every CTA is resident at once;
+    * ``merge_stages``: consecutive backward stages whose gradient ranges are adjacent share one
+      all-reduce (fewer, larger collectives; the stem joins the first block's bucket so nothing
+      tiny is left for the end).
+    """
+
+    def __init__(self, model, optimizer, group=None, overlap=True, nccl_max_ctas=8, reserve_sms=None,
+                 merge_stages=1, record_events=False):
+        self.model, self.optimizer, self.overlap = model, optimizer, overlap
         self.rank, self.world = world(group)
+        self.group = group
+        cuda = model._flat.is_cuda
+        if self.world > 1 and cuda and group is None and nccl_max_ctas and dist.get_backend() == "nccl":
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = int(nccl_max_ctas)
+            opts.config.min_ctas = 1
+            self.group = dist.new_group(ranks=list(range(self.world)), pg_options=opts)
+        self.reserve_sms = int(nccl_max_ctas if reserve_sms is None else reserve_sms) if cuda else 0
+        if not (self.world > 1 and overlap):
+            self.reserve_sms = 0
         self.ranges = model.stage_ranges()
+        self.buckets = self._make_buckets(self.ranges, max(1, int(merge_stages)))
         self._works = []
-        self._comm = torch.cuda.Stream() if (overlap and model._flat.is_cuda) else None
-        broadcast_flat(model._flat, 0, group)
+        self._comm = torch.cuda.Stream() if (overlap and cuda) else None
+        self.record_events = record_events
+        self.events = []          # [(bucket, bytes, start_event, end_event)] of the last backward
+        broadcast_flat(model._flat, 0, self.group)
         optimizer.grad_scale = 1.0 / self.world
         model._ddp = self
+
+    @staticmethod
+    def _make_buckets(ranges, merge):
+        """[(last_stage, begin, end)]: the all-reduce of elements [begin, end) may start once the
+        backward stage ``last_stage`` has finished.  Stages are visited in order 0..n-1 and (by the
+        flat layout) finish contiguous ranges, so merged buckets stay contiguous; the last (stem)
+        stage always joins the bucket before it."""
+        groups, cur = [], []
+        for st in range(len(ranges)):
+            cur.append(st)
+            if len(cur) >= merge and st < len(ranges) - 2:
+                groups.append(cur)
+                cur = []
+        if cur:
+            groups.append(cur)
+        out = []
+        for g in groups:
+            b = min(ranges[st][0] for st in g)
+            e = max(ranges[st][1] for st in g)
+            out.append((g[-1], b, e))
+        return out
+
+    def _launch(self, model, bucket):
+        last, b, e = bucket
+        if self._comm is None:
+            self._works += all_reduce_ranges(model._flat_grad, [(b, e)], self.group, True)
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ev)
+            if self.record_events:
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+            self._works += all_reduce_ranges(model._flat_grad, [(b, e)], self.group, True)
+            if self.record_events:
+                t1.record()
+                self.events.append((last, (e - b) * 4, t0, t1))
 
     def backward(self, model, cfg, inp, ws, dlogits):
         n = len(self.ranges)
         if self.world == 1:
             model.backward_stages(cfg, inp, ws, dlogits, 0, n)
             return
-        for st in range(n):
-            model.backward_stages(cfg, inp, ws, dlogits, st, st + 1)
-            b, e = self.ranges[st]
-            if self._comm is None:
-                self._works += all_reduce_ranges(model._flat_grad, [(b, e)], self.group, True)
-                continue
-            ev = torch.cuda.Event()
-            ev.record()
-            with torch.cuda.stream(self._comm):
-                self._comm.wait_event(ev)
-                self._works += all_reduce_ranges(model._flat_grad, [(b, e)], self.group, True)
+        self.events = []
+        if self.reserve_sms:
+            _lib.lib.mmu_set_gemm_sm_limit(max(2, (_sm_count(model._flat.device) - self.reserve_sms) // 2 * 2))
+        try:
+            done = 0
+            for bucket in self.buckets:
+                model.backward_stages(cfg, inp, ws, dlogits, done, bucket[0] + 1)
+                done = bucket[0] + 1
+                self._launch(model, bucket)
+        finally:
+            if self.reserve_sms:
+                _lib.lib.mmu_set_gemm_sm_limit(0)
 
     def wait(self):
         for w in self._works:
@@ -117,6 +184,15 @@ class DataParallel:
         self._works = []
         if self._comm is not None:
             torch.cuda.current_stream().wait_stream(self._comm)
+
+    def bucket_times(self):
+        """[(last_stage, bytes, ms)] of the all-reduces of the last backward (``record_events``)."""
+        torch.cuda.synchronize()
+        return [(st, nbytes, t0.elapsed_time(t1)) for st, nbytes, t0, t1 in self.events]
+
+
+def _sm_count(device):
+    return torch.cuda.get_device_properties(device).multi_processor_count
 
 
 class FlatGradSync:
