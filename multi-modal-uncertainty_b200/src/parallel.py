@@ -84,21 +84,21 @@ class DataParallel:
     gradient all-reduce of each finished bucket on a communication stream; ``optimizer.step()``
     waits for them and applies the averaged gradient.
 
-    The backward's persistent tcgen05 GEMM grids and NCCL's CTAs share the SMs.  Left alone
-    (r01), a 148-CTA GEMM grid that finds some SMs taken runs its last CTAs -- each with a full
-    static share of the tiles -- after the others (``profiles/r02_ddp_attribution.json``).  So:
+    Measured on 8 x B200 (``tools/ddp_probe.py`` -> ``profiles/r02_ddp_attribution_8gpu.json``):
+    the four per-stage all-reduces of the 91 MB fp32 gradient take 0.37 ms back to back and are
+    hidden almost completely by this overlap -- 0.06 ms of a 5.4 ms training step stays exposed.
+    What separates the 8-GPU step from the 1-GPU step is NOT communication: with the gradient
+    exchange switched off the same step is 3.3 % slower when all eight GPUs of the box are busy
+    (5.37 vs 5.20 ms), and the collective-free evaluation sweep 2.5 % (8.92 vs 8.70 ms).
 
-    * ``nccl_max_ctas`` (default 8): the gradient all-reduces run on a communicator of their own
-      whose CTA count is capped (``ncclConfig_t.maxCTAs``); NVSwitch reduces in the fabric (NVLS),
-      a few CTAs saturate it;
-    * ``reserve_sms`` (default = ``nccl_max_ctas``): while the backward runs, the GEMM grids are
-      sized to the remaining SMs (``mmu_set_gemm_sm_limit``), so every CTA is resident at once;
-    * ``merge_stages``: consecutive backward stages whose gradient ranges are adjacent share one
-      all-reduce (fewer, larger collectives; the stem joins the first block's bucket so nothing
-      tiny is left for the end).
+    Knobs that were measured and are OFF by default because they lost: ``nccl_max_ctas`` (a
+    communicator of its own with ``ncclConfig_t.maxCTAs`` capped: the collectives slow down more
+    than the backward speeds up, +0.2 .. +0.8 ms), ``reserve_sms`` (GEMM grids sized to the SMs
+    NCCL leaves free, ``mmu_set_gemm_sm_limit``: neutral), ``merge_stages`` (fewer, larger buckets:
+    the last one is exposed, +0.1 .. +0.5 ms).
     """
 
-    def __init__(self, model, optimizer, group=None, overlap=True, nccl_max_ctas=8, reserve_sms=None,
+    def __init__(self, model, optimizer, group=None, overlap=True, nccl_max_ctas=0, reserve_sms=0,
                  merge_stages=1, record_events=False):
         self.model, self.optimizer, self.overlap = model, optimizer, overlap
         self.rank, self.world = world(group)
@@ -109,7 +109,7 @@ class DataParallel:
             opts.config.max_ctas = int(nccl_max_ctas)
             opts.config.min_ctas = 1
             self.group = dist.new_group(ranks=list(range(self.world)), pg_options=opts)
-        self.reserve_sms = int(nccl_max_ctas if reserve_sms is None else reserve_sms) if cuda else 0
+        self.reserve_sms = int(reserve_sms or 0) if cuda else 0
         if not (self.world > 1 and overlap):
             self.reserve_sms = 0
         self.ranges = model.stage_ranges()
@@ -153,12 +153,15 @@ class DataParallel:
         with torch.cuda.stream(self._comm):
             self._comm.wait_event(ev)
             if self.record_events:
+                # a synchronous-op collective makes THIS stream wait for NCCL's own stream, so the
+                # closing event sees the end of the all-reduce kernel (the host never blocks)
                 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 t0.record()
-            self._works += all_reduce_ranges(model._flat_grad, [(b, e)], self.group, True)
-            if self.record_events:
+                all_reduce_ranges(model._flat_grad, [(b, e)], self.group, False)
                 t1.record()
                 self.events.append((last, (e - b) * 4, t0, t1))
+            else:
+                self._works += all_reduce_ranges(model._flat_grad, [(b, e)], self.group, True)
 
     def backward(self, model, cfg, inp, ws, dlogits):
         n = len(self.ranges)

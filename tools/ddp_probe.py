@@ -95,6 +95,26 @@ def main():
                ("ctas8_reserve8_merge5", dict(nccl_max_ctas=8, reserve_sms=8, merge_stages=5)),
                ("ctas2_reserve2", dict(nccl_max_ctas=2, reserve_sms=2, merge_stages=1))]
     report = {"world": world, "steps": args.steps, "config": CFG, "results": {}}
+    # the evaluation sweep involves no collective at all: its time at N GPUs against N = 1 shows
+    # what part of the 1 -> N slowdown is NOT communication (shared power budget, host contention)
+    torch.manual_seed(0)
+    variants = [mmu.robustness.mask_level_variant(CFG["l_img"], CFG["l_txt"], "image", k, 10) for k in range(10)]
+    model.eval()
+    with torch.no_grad():
+        for _ in range(3):
+            model.forward_variants(batches[0][0], variants)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            model.forward_variants(batches[i % 4][0], variants)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        report["sweep10_ms_no_collective"] = round(float(t), 3)
+    model.train()
     for name, kw in configs:
         model._ddp = None
         opt.grad_scale = 1.0
