@@ -7,7 +7,8 @@ val_acc, val_auc, test_*, time, epoch``) and the same stopping rules (NaN loss; 
 The per-batch body is the hot path: ``data_forming`` (host RNG) -> H2D -> ``model(x)`` ->
 ``compute_loss`` -> ``backward`` -> ``optimizer.step`` -> metrics -> ``scheduler.step``.  It is
 exposed on its own as ``train_step`` / ``eval_step`` so it can be benchmarked through the public
-API.  MMBT / ViLT branches of the reference loop are out of scope for this build and raise.
+API.  The ``mmbt`` branch drives the MMBT engine; the ``vilt`` branch keeps the reference's calling
+convention for transformers' ViLT classifier (dict batches, ``outputs.loss`` / ``.logits``).
 """
 import itertools
 import math
@@ -150,11 +151,40 @@ class Model_:
             return [None if t is None else t.to(self.device, non_blocking=True) for t in x]
         return x.to(self.device, non_blocking=True)
 
-    @staticmethod
-    def _reject(mmbt, vilt):
-        if vilt:
-            raise NotImplementedError("the ViLT branch wraps a third-party pretrained model whose "
-                                      "weights are unavailable offline (SURVEY.md 8c): not built")
+    # ---------------------------------------------------------------- ViLT branch
+    # Reference src/framework.py:163-169, 263-272, 294-304 with train.py:164-182: the model is
+    # transformers' ViltForImagesAndTextClassification (a third-party module with its own loss),
+    # batches are dicts, ``outputs = model(**batch)`` carries ``.loss`` and ``.logits``, labels sit
+    # in ``batch['labels']``, metrics see (B, C) logits (dummy_dim=False), no data_forming.  Every
+    # model that follows that calling convention works; the arithmetic is the library's.
+    def _vilt_batch(self, batch):
+        return {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+    def train_step_vilt(self, batch, global_step, *, gradient_accumulation_steps=1, scheduler_step_on="epoch"):
+        batch = self._vilt_batch(batch)
+        y = batch["labels"]
+        self.optimizer.zero_grad()
+        outputs = self.model(**batch)
+        y_pred, loss = outputs.logits, outputs.loss
+        if gradient_accumulation_steps > 1:
+            loss = loss / gradient_accumulation_steps
+        loss.backward()
+        if global_step % gradient_accumulation_steps == 0:
+            self.optimizer.step()
+            self.optimizer.zero_grad()
+        with torch.no_grad():
+            info = self._compute_metrics(y_pred, y, eval=False, dummy_dim=False)
+        if scheduler_step_on == "batch" and self.scheduler is not None:
+            self.scheduler.step()
+        return loss.item(), info, len(y)
+
+    @torch.no_grad()
+    def eval_step_vilt(self, batch):
+        batch = self._vilt_batch(batch)
+        outputs = self.model(**batch)
+        y = batch["labels"]
+        info = self._compute_metrics(outputs.logits, y, eval=True, dummy_dim=False)
+        return float(outputs.loss), info, len(y), outputs.logits, y
 
     # ---------------------------------------------------------------- hot path
     def train_step(self, x, y, scheduler_step_on="batch", keep_mask=None, sync=True, cuda_graph=False):
@@ -243,7 +273,6 @@ class Model_:
 
     # ---------------------------------------------------------------- loops
     def eval_loop(self, generator, phase, *, steps=None, auc=False, mmbt=False, vilt=False):
-        self._reject(mmbt, vilt)
         steps = len(generator) if steps is None else steps
         it = StepIterator(generator, steps,
                           ValidationProgressionCallback(phase=phase, steps=steps,
@@ -251,13 +280,17 @@ class Model_:
                           self.metrics_names)
         self.model.eval()
         preds, labels = [], []
-        for step, (x, y) in it:
-            loss, info, size, outputs, y_dev = self.eval_step_mmbt(x, y) if mmbt else self.eval_step(x, y)
+        for step, batch in it:
+            if vilt:
+                loss, info, size, outputs, y_dev = self.eval_step_vilt(batch)
+            else:
+                x, y = batch
+                loss, info, size, outputs, y_dev = self.eval_step_mmbt(x, y) if mmbt else self.eval_step(x, y)
             step["size"], step["loss"], step["metrics"] = size, loss, info
             # (B, E, C) -> head-mean logits.  The reference applies the same .mean(1) to MMBT's
             # (B, C) logits (src/framework.py:191), which collapses the class axis and cannot feed
             # its own AUROC line (:198); the (B, C) logits are kept instead.
-            preds.append(outputs if mmbt else outputs.mean(1))
+            preds.append(outputs if (mmbt or vilt) else outputs.mean(1))
             labels.append(y_dev)
         out = {f"{phase}_loss": it.loss,
                **{f"{phase}_{k}": v for k, v in it.extra_lists.items()},
@@ -273,7 +306,6 @@ class Model_:
                    epochs=1000, steps_per_epoch=None, validation_steps=None, test_steps=None,
                    patience=10, callbacks=[], epoch_start=1, scheduler_step_on="epoch", auc=False,
                    mmbt=False, vilt=False, **kwargs):
-        self._reject(mmbt, vilt)
         self._transfer_optimizer_state_to_right_device()
         cbs = CallbackList(callbacks)
         cbs.append(ProgressionCallback(verbose=self.verbose))
@@ -287,12 +319,18 @@ class Model_:
             t0 = timeit.default_timer()
             # metrics_every=N (N > 1): loss / metrics stay on the device and are read back every N
             # steps and at the end of the epoch (StepIterator) -- same epoch means, no per-step sync
-            read_every = 1 if mmbt else int(kwargs.get("metrics_every", 1))
+            read_every = 1 if (mmbt or vilt) else int(kwargs.get("metrics_every", 1))
             it = StepIterator(train_generator, steps_per_epoch, cbs, self.metrics_names, read_every)
             self.model.train(True)
             with torch.enable_grad():
-                for step, (x, y) in it:
-                    if mmbt:
+                for step, batch in it:
+                    x, y = (None, None) if vilt else batch
+                    if vilt:
+                        global_step += 1
+                        loss, info, size = self.train_step_vilt(
+                            batch, global_step, gradient_accumulation_steps=kwargs["gradient_accumulation_steps"],
+                            scheduler_step_on=scheduler_step_on)
+                    elif mmbt:
                         global_step += 1
                         loss, info, size = self.train_step_mmbt(
                             x, y, global_step, freeze_img=epoch < kwargs["freeze_img"],
@@ -310,9 +348,10 @@ class Model_:
             log = {"epoch": epoch, "loss": it.loss,
                    **{f"train_{k}": v for k, v in it.extra_lists.items()}, **it.metrics}
             if valid_generator is not None:
-                log.update(self.eval_loop(valid_generator, "val", steps=validation_steps, auc=auc, mmbt=mmbt))
+                log.update(self.eval_loop(valid_generator, "val", steps=validation_steps, auc=auc, mmbt=mmbt,
+                                          vilt=vilt))
             if test_generator is not None:
-                log.update(self.eval_loop(test_generator, "test", steps=test_steps, auc=auc, mmbt=mmbt))
+                log.update(self.eval_loop(test_generator, "test", steps=test_steps, auc=auc, mmbt=mmbt, vilt=vilt))
             log["time"] = timeit.default_timer() - t0
             log["epoch_begin_time"] = t0
             if scheduler_step_on == "epoch" and self.scheduler is not None:

@@ -250,8 +250,6 @@ def test_trainer_protocol_with_a_plain_torch_model(mmu, tmp_path):
     be = [e for e in events if e[0] == "be"]
     assert be[0][2] >= {"batch", "size", "time", "batch_begin_time", "loss", "acc"}
     assert events[0] == ("eb", 1) and events[1] == ("bw", 1)
-    with pytest.raises(NotImplementedError):
-        trainer.eval_loop(val, "val", vilt=True)
 
 
 def test_train_loop_deferred_readback_gives_the_same_epoch_logs(mmu):
@@ -311,6 +309,50 @@ def test_train_loop_deferred_readback_gives_the_same_epoch_logs(mmu):
                            callbacks=[mmu.src.callbacks.LambdaCallback(on_epoch_end=lambda e, l: seen.append(e))],
                            metrics_every=every)
         assert seen == [1]
+
+
+def test_trainer_vilt_branch_with_transformers_vilt(mmu):
+    """The ``vilt`` branch of Model_ (reference src/framework.py:163-169, 263-304; set up by
+    train.py:164-182) driving the SAME class the reference wraps --
+    transformers.ViltForImagesAndTextClassification, here with a tiny random-init config (the
+    "dandelin/vilt-b32-mlm" checkpoint is unavailable offline): dict batches, ``model(**batch)``,
+    ``outputs.loss`` / ``.logits``, labels from the batch, (B, C) metrics, gradient accumulation,
+    epoch-wise ReduceLROnPlateau on val_acc."""
+    transformers = pytest.importorskip("transformers")
+    torch.manual_seed(0)
+    cfg = transformers.ViltConfig(hidden_size=32, num_hidden_layers=2, num_attention_heads=2, intermediate_size=64,
+                                  image_size=32, patch_size=16, num_labels=3, num_images=1, vocab_size=100,
+                                  max_position_embeddings=16)
+    model = transformers.ViltForImagesAndTextClassification(cfg)
+    g = torch.Generator().manual_seed(1)
+
+    def batches(n):
+        return [dict(input_ids=torch.randint(0, 100, (4, 8), generator=g),
+                     attention_mask=torch.ones(4, 8, dtype=torch.long),
+                     token_type_ids=torch.zeros(4, 8, dtype=torch.long),
+                     pixel_values=torch.randn(4, 1, 3, 32, 32, generator=g),
+                     labels=torch.randint(0, 3, (4,), generator=g)) for _ in range(n)]
+
+    def acc(y_pred, y_true, eval, dummy_dim=False):         # train.py:119-130 with dummy_dim=False
+        assert not dummy_dim and y_pred.dim() == 2
+        return (y_pred.argmax(1) == y_true).float().mean() * 100
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, "max", patience=1, factor=0.5)
+    steps = []
+    orig = opt.step
+    opt.step = lambda *a, **k: (steps.append(1), orig(*a, **k))[1]
+    trainer = mmu.Model_(model, opt, sched, None, metrics=[acc], verbose=False)
+    trainer.to(torch.device("cpu"))
+    logs = []
+    trainer.train_loop(batches(4), valid_generator=batches(2), epochs=2, steps_per_epoch=4, validation_steps=2,
+                       callbacks=[mmu.src.callbacks.LambdaCallback(on_epoch_end=lambda e, l: logs.append(dict(l)))],
+                       scheduler_step_on="epoch", scheduler_metric="val_acc", vilt=True,
+                       gradient_accumulation_steps=2, auc=False)
+    assert len(logs) == 2 and len(steps) == 4                # 8 batches, one optimizer step per 2
+    for k in ("loss", "acc", "val_loss", "val_acc"):
+        assert k in logs[0] and np.isfinite(logs[1][k]), k
+    out = trainer.eval_loop(batches(2), "test", vilt=True)
+    assert set(out) >= {"test_loss", "test_acc"}
 
 
 def test_trainer_mmbt_branch_with_a_plain_torch_model(mmu, monkeypatch):
