@@ -93,6 +93,11 @@ typedef struct {
   long long ld_out, ld_out2, ld_aux;
   int seg_len, seg_stride, seg_off;
   float alpha;
+  /* QUICKGELU / DGELU only: dropout on z BEFORE the activation (src/model.py:195-201); element
+   * counter = row * N + column, mask function of csrc/dropout.cuh.  drop_p == 0: off. */
+  float drop_p;
+  int drop_site;
+  unsigned long long drop_seed;
 } mmu_gemm_epilogue;
 
 MMU_API int mmu_gemm(int dtype, const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
@@ -277,6 +282,13 @@ typedef struct {
   int src_l_img, src_l_txt;  /* 0: cfg->l_img / cfg->l_txt */
   int n_variants;            /* 0 or 1: ordinary forward */
   const int* var_segments;   /* device int32[n_variants][E][2] */
+  /* nn.Dropout(drop) between c_fc and QuickGELU (src/model.py:195-201; training forward and its
+   * backward only): element (row r, column c) of layer i's [B*L, 4D] pre-activation is kept iff
+   * hash(seed, site = i, r * 4D + c) >= floor(p * 2^32) and scaled by 1 / (1 - p) -- the mask
+   * function of csrc/dropout.cuh, restated in oracle/dropout.py.  drop_p == 0: no dropout. */
+  float drop_p;
+  int drop_reserved;
+  unsigned long long drop_seed;
 } mmu_flava_inputs;
 
 /* logits: fp32 (B, E, C), or (n_variants, B, E, C) for a packed-variant forward (eval only).

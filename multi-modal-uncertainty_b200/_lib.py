@@ -40,7 +40,8 @@ class GemmEpilogue(C.Structure):
     _fields_ = [("mode", C.c_int), ("out_lp", C.c_int), ("out", C.c_void_p), ("out2", C.c_void_p),
                 ("bias", C.c_void_p), ("aux", C.c_void_p), ("ld_out", C.c_longlong),
                 ("ld_out2", C.c_longlong), ("ld_aux", C.c_longlong), ("seg_len", C.c_int),
-                ("seg_stride", C.c_int), ("seg_off", C.c_int), ("alpha", C.c_float)]
+                ("seg_stride", C.c_int), ("seg_off", C.c_int), ("alpha", C.c_float),
+                ("drop_p", C.c_float), ("drop_site", C.c_int), ("drop_seed", C.c_ulonglong)]
 
 
 class MetricAccum(C.Structure):
@@ -100,7 +101,8 @@ class FlavaInputs(C.Structure):
     _fields_ = [("img", C.c_void_p), ("txt", C.c_void_p), ("idx_img", C.c_void_p),
                 ("idx_txt", C.c_void_p), ("n_img", C.c_int), ("n_txt", C.c_int),
                 ("keep", C.c_void_p), ("params_bf16", C.c_void_p), ("src_l_img", C.c_int),
-                ("src_l_txt", C.c_int), ("n_variants", C.c_int), ("var_segments", C.c_void_p)]
+                ("src_l_txt", C.c_int), ("n_variants", C.c_int), ("var_segments", C.c_void_p),
+                ("drop_p", C.c_float), ("drop_reserved", C.c_int), ("drop_seed", C.c_ulonglong)]
 
 
 def _load():

@@ -95,6 +95,8 @@ int mmu_gemm(int dtype, const void* A, long long lda, int a_mn_major, const void
   e.seg_stride = epi->seg_stride;
   e.seg_off = epi->seg_off;
   e.alpha = epi->alpha;
+  e.drop = dropout::make_site(epi->drop_p, epi->drop_seed, static_cast<unsigned int>(epi->drop_site));
+  if (epi->drop_p < 0.f || epi->drop_p >= 1.f) return MMU_ERR_ARG;
   if (dtype == MMU_BF16) return gemm_bf16_launch(A, lda, B, ldb, p, e, S(stream));
   if (dtype == MMU_F32)
     return gemm_f32_launch(static_cast<const float*>(A), lda, static_cast<const float*>(B), ldb, p,

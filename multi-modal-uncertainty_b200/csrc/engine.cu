@@ -369,6 +369,7 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
   Shape s;
   MMU_TRY(resolve_shape(c, in, &s));
   if (in.n_variants > 1 && training) return MMU_ERR_ARG;
+  if (!(in.drop_p >= 0.f && in.drop_p < 1.f)) return MMU_ERR_ARG;
   const int src_l_img = in.src_l_img > 0 ? in.src_l_img : c.l_img;
   const int src_l_txt = in.src_l_txt > 0 ? in.src_l_txt : c.l_txt;
   const int bf = c.precision == PREC_BF16;
@@ -440,6 +441,8 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
     {
       GemmEpilogue e = epi(EPI_QUICKGELU, training ? l.z : nullptr, bf, 4 * D, params + p.fc_b);
       e.out2 = l.u; e.ld_out2 = 4 * D;
+      // nn.Dropout between c_fc and QuickGELU (src/model.py:195-201): training with p > 0 only
+      if (training && in.drop_p > 0.f) e.drop = dropout::make_site(in.drop_p, in.drop_seed, i);
       MMU_TRY(gemm(l.h2, D, 0, W(p.fc_w), D, 0, M, 4 * D, D, e));
     }
     MMU_TRY(gemm(l.u, 4 * D, 0, W(p.proj_w), 4 * D, 0, M, D, 4 * D,
@@ -532,6 +535,7 @@ int flava_backward(const FlavaConfig& c, const float* params, const FlavaInputs&
       {  // dz = (dx Wproj) * gelu'(z)
         GemmEpilogue e = epi(EPI_DGELU, w.dbig, bf, 4 * D, nullptr);
         e.aux = l.z; e.ld_aux = 4 * D;
+        if (in.drop_p > 0.f) e.drop = dropout::make_site(in.drop_p, in.drop_seed, i);  // same mask
         MMU_TRY(gemm(w.dx_lp, D, 0, W(p.proj_w), 4 * D, 1, M, 4 * D, D, e));
       }
       // dWproj[D, 4D] += dx^T u

@@ -65,6 +65,11 @@ struct FlavaInputs {
   int src_l_txt;
   int n_variants;           // 0 or 1: ordinary forward
   const int* var_segments;  // device int32 [n_variants][E][2]: rows [begin, end) of head e
+  // nn.Dropout(drop) between c_fc and QuickGELU (src/model.py:195-201), training only: counter-
+  // based masks (csrc/dropout.cuh), site = layer index; the backward must see the same values.
+  float drop_p;
+  int drop_reserved;
+  unsigned long long drop_seed;
 };
 
 int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& in, void* ws,

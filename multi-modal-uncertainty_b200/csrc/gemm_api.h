@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "dropout.cuh"
+
 namespace mmu {
 
 enum GemmEpiMode : int {
@@ -31,6 +33,9 @@ struct GemmEpilogue {
   // EPI_QUICKGELU / EPI_DGELU (bf16 kernel): 0 = QuickGELU z*sigmoid(1.702 z) (src/model.py:185),
   // 1 = erf-GELU z*Phi(z) (BERT's gelu of the MMBT path, src/mmbt.py:124-128)
   int act;
+  // EPI_QUICKGELU / EPI_DGELU: dropout applied to z BEFORE the activation (src/model.py:195-201);
+  // element counter = row * N + column.  thresh == 0: off.
+  dropout::Site drop;
 };
 
 struct GemmProblem {

@@ -518,6 +518,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             }
           }
           const uint32_t box = box0 + static_cast<uint32_t>(c & 1) * BOX_BYTES;
+          // dropout between c_fc and the activation (src/model.py:195-201, training with p > 0
+          // only): the mask is a pure function of (site seed, row * N + column) -- csrc/dropout.cuh.
+          // Forward: z <- dropout(z) before it is saved and activated; backward: d act(dropout(z))
+          // / dz = act'(z_saved) * mask / (1 - p), the mask regenerated here.
+          if constexpr (MODE == EPI_QUICKGELU || MODE == EPI_DGELU) {
+            if (e.drop.on()) {
+              const unsigned int ibase = static_cast<unsigned int>(m0 + lane) * static_cast<unsigned int>(p.N) +
+                                         static_cast<unsigned int>(col0);
+#pragma unroll
+              for (int i = 0; i < NCOL; ++i) v[i] *= e.drop.mult(ibase + i);
+            }
+          }
           if constexpr (!OBF) {
             box_free(c == 0);
 #pragma unroll

@@ -70,6 +70,10 @@ __device__ __forceinline__ void epi4(const GemmEpilogue& e, int grow, int gcol, 
     const int c = gcol + j;
     if (c >= N) break;
     float x = v[j] * e.alpha + (e.bias != nullptr ? e.bias[c] : 0.f);
+    if constexpr (MODE == EPI_QUICKGELU || MODE == EPI_DGELU) {  // dropout before the activation
+      if (e.drop.on()) x *= e.drop.mult(static_cast<unsigned int>(grow) * static_cast<unsigned int>(N) +
+                                        static_cast<unsigned int>(c));
+    }
     float* out = static_cast<float*>(e.out);
     if constexpr (MODE == EPI_STORE) {
       out[orow * e.ld_out + c] = x;

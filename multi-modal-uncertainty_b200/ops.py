@@ -27,7 +27,7 @@ def _cuda(*ts):
 
 
 def gemm(A, B, *, a_mn_major=False, b_mn_major=False, mode=_lib.EPI_STORE, out=None, out2=None,
-         bias=None, aux=None, alpha=1.0, splits=1, seg=None, out_dtype=None):
+         bias=None, aux=None, alpha=1.0, splits=1, seg=None, out_dtype=None, dropout=None):
     """C[M,N] = epilogue(sum_k A(m,k) B(n,k)); see ``mmu_gemm`` in include/mmu_b200.h."""
     _cuda(A, B, out, out2, bias, aux)
     dt = _dt(A)
@@ -49,6 +49,8 @@ def gemm(A, B, *, a_mn_major=False, b_mn_major=False, mode=_lib.EPI_STORE, out=N
     e.ld_aux = aux.stride(0) if aux is not None else 0
     e.seg_len, e.seg_stride, e.seg_off = seg if seg is not None else (0, 0, 0)
     e.alpha = alpha
+    if dropout is not None:   # (p, seed, site): QUICKGELU / DGELU modes only
+        e.drop_p, e.drop_seed, e.drop_site = float(dropout[0]), int(dropout[1]), int(dropout[2])
     check(lib.mmu_gemm(dt, ptr(A), A.stride(0), int(a_mn_major), ptr(B), B.stride(0),
                        int(b_mn_major), M, N, K, splits, C.byref(e), stream_ptr()), "mmu_gemm")
     return out if out is not None else out2

@@ -333,9 +333,8 @@ class FlavaFusionTransfomer(nn.Module):
         if not self._flat.is_cuda:
             raise _lib.MMUError("the model lives on the CPU: call .to('cuda') first -- this "
                                 "package has no CPU execution path")
-        if training and self.drop > 0.0:
-            raise NotImplementedError("dropout > 0 is not implemented in the fused engine "
-                                      "(the reference's own runs use --dropout 0, train.py:59)")
+        if not 0.0 <= self.drop < 1.0:
+            raise ValueError("drop must be in [0, 1)")
         self._new_forward()
         ref = img if img is not None else txt
         B = ref.shape[0]
@@ -358,6 +357,12 @@ class FlavaFusionTransfomer(nn.Module):
         shadow = self._fresh_shadow()
         inp = _lib.FlavaInputs(_lib.ptr(img), _lib.ptr(txt), _lib.ptr(idx_img), _lib.ptr(idx_txt),
                                n_img, n_txt, _lib.ptr(keep), _lib.ptr(shadow))
+        if training and self.drop > 0.0:
+            # nn.Dropout(drop) between c_fc and QuickGELU (reference src/model.py:195-201): the
+            # masks are a function of this seed (drawn from torch's CPU generator, so
+            # torch.manual_seed reproduces a run) and are regenerated by the backward from `inp`
+            inp.drop_p = self.drop
+            inp.drop_seed = self.last_dropout_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         logits = torch.empty(B, self.out_dim, self.num_classes, device=dev, dtype=torch.float32)
         _lib.check(_lib.lib.mmu_flava_forward(C.byref(cfg), self._flat.data_ptr(), C.byref(inp),
                                               ws.data_ptr(), ws.numel(), int(training),

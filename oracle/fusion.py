@@ -58,21 +58,32 @@ def batch_axis_attention(x, in_w, in_b, out_w, out_b, n_head):
     return linear(o, out_w, out_b)
 
 
-def residual_attention_block(x, P, pre, n_head):
+def residual_attention_block(x, P, pre, n_head, drop_mult=None):
     """src/model.py:188-212.  Effective MLP order is c_fc -> dropout -> QuickGELU -> c_proj
-    (duplicate OrderedDict key); dropout p = 0 here."""
+    (duplicate OrderedDict key).  ``drop_mult`` (training with p > 0):
+    the (B, L, 4D) tensor of 0 / (1 / (1 - p)) factors nn.Dropout multiplies the c_fc output by."""
     h = layer_norm(x, P[pre + "ln_1.weight"], P[pre + "ln_1.bias"])
     x = x + batch_axis_attention(h, P[pre + "attn.in_proj_weight"], P[pre + "attn.in_proj_bias"],
                                  P[pre + "attn.out_proj.weight"], P[pre + "attn.out_proj.bias"],
                                  n_head)
     h = layer_norm(x, P[pre + "ln_2.weight"], P[pre + "ln_2.bias"])
-    u = quick_gelu(linear(h, P[pre + "mlp.c_fc.weight"], P[pre + "mlp.c_fc.bias"]))
+    z = linear(h, P[pre + "mlp.c_fc.weight"], P[pre + "mlp.c_fc.bias"])
+    if drop_mult is not None:
+        z = z * drop_mult
+    u = quick_gelu(z)
     return x + linear(u, P[pre + "mlp.c_proj.weight"], P[pre + "mlp.c_proj.bias"])
 
 
-def transformer(x, P, pre, n_layers, n_head):
+def transformer(x, P, pre, n_layers, n_head, dropout=None):
+    """``dropout = (p, seed)``: training-mode masks of the engine's counter-based generator
+    (oracle/dropout.py; site = layer index, element counter = row-major index of (B*L, 4D))."""
     for i in range(n_layers):
-        x = residual_attention_block(x, P, f"{pre}resblocks.{i}.", n_head)
+        mult = None
+        if dropout is not None and dropout[0] > 0:
+            from . import dropout as _d
+            B, L, D = x.shape
+            mult = _d.multiplier(dropout[0], dropout[1], i, B * L * 4 * D, (B, L, 4 * D), x.dtype)
+        x = residual_attention_block(x, P, f"{pre}resblocks.{i}.", n_head, mult)
     return x
 
 
@@ -91,7 +102,7 @@ def count_heads(P):
 
 
 # ------------------------------------------------------------------------------ models
-def flava_fusion_forward(P, x, n_head, avg_pool=False):
+def flava_fusion_forward(P, x, n_head, avg_pool=False, dropout=None):
     """``FlavaFusionTransfomer.forward`` (src/model.py:258-291) and, when ``class_embeddings``
     is present in ``P``, ``FlavaFusionTransfomerwithCLSToken.forward`` (:330-361).
 
@@ -117,7 +128,7 @@ def flava_fusion_forward(P, x, n_head, avg_pool=False):
         mm = torch.cat([cls, mm], dim=1)
         avg_pool = False  # the CLS variant never pools (src/model.py:354-357)
     mm = layer_norm(mm, P["ln_pre.weight"], P["ln_pre.bias"])
-    out = transformer(mm, P, "mm_encoder.", count_layers(P), n_head)
+    out = transformer(mm, P, "mm_encoder.", count_layers(P), n_head, dropout)
     out = layer_norm(out, P["ln_post.weight"], P["ln_post.bias"])
     heads = []
     if avg_pool:
@@ -195,12 +206,12 @@ def predictions(y_pred, eval):
 
 
 # -------------------------------------------------------------------------- train step
-def loss_and_grads(P, x, y, n_head, avg_pool=False, model="flava"):
+def loss_and_grads(P, x, y, n_head, avg_pool=False, model="flava", dropout=None):
     """Forward + CE + backward.  Gradients come from autograd over the explicit forward above
     (this is the checker, not the product).  Returns (logits, loss, {name: grad})."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
     if model == "flava":
-        logits = flava_fusion_forward(leaves, x, n_head, avg_pool)
+        logits = flava_fusion_forward(leaves, x, n_head, avg_pool, dropout)
     else:
         logits = mimo_transformer_forward(leaves, x, n_head)
     loss = compute_loss(logits, y, eval=False)
