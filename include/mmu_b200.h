@@ -341,6 +341,15 @@ typedef struct {
   int cls_id, sep_id; /* args.vocab.stoi["[CLS]"], ["[SEP]"] (src/mmbt.py:62-66) */
   int precision;      /* 0 fp32 (parity path), 1 bf16 operands on tcgen05 */
   int max_seq;        /* workspace capacity in sequence positions; 0 = n_img + 2 + S_txt */
+  /* Dropout (training forward + its backward only; masks = csrc/dropout.cuh, oracle/dropout.py):
+   * drop_hidden = BertConfig.hidden_dropout_prob (text embeddings; attention-output and FFN-output
+   * dense layers before the residual add), drop_attn = attention_probs_dropout_prob (softmax(QK^T)
+   * before P V; the fused attention kernels do not apply it, the three-kernel path runs instead),
+   * drop_img = args.dropout of ImageBertEmbeddings (src/mmbt.py:56,82).  Sites: 0 embeddings,
+   * 4l+1 attention probabilities, 4l+2 attention output, 4l+3 FFN output of layer l; element
+   * counters: row * D + column, resp. ((b * H + h) * S + query) * S + key. */
+  float drop_hidden, drop_attn, drop_img;
+  int drop_reserved;
 } mmu_mmbt_config;
 typedef struct {
   const long long* txt;     /* (B, S_txt) token ids */
@@ -355,6 +364,7 @@ typedef struct {
                                variants of a batch packed along the batch axis into one forward) */
   const void* params_bf16;  /* optional bf16 shadow of params */
   float* dimg;              /* backward: d loss / d img, or NULL */
+  unsigned long long drop_seed; /* seed of this forward's dropout masks; pass the same to the backward */
 } mmu_mmbt_inputs;
 MMU_API long long mmu_mmbt_param_count(const mmu_mmbt_config* cfg);
 MMU_API int mmu_mmbt_param_table(const mmu_mmbt_config* cfg, mmu_param_entry* out /* host */, int max);

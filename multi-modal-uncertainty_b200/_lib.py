@@ -88,13 +88,16 @@ class ImgEncConfig(C.Structure):
 class MmbtConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("B", "S_txt", "n_img", "d_img", "D", "n_head", "n_layers",
                                        "d_ff", "vocab", "max_pos", "n_types", "C", "cls_id",
-                                       "sep_id", "precision", "max_seq")]
+                                       "sep_id", "precision", "max_seq")] + \
+               [("drop_hidden", C.c_float), ("drop_attn", C.c_float), ("drop_img", C.c_float),
+                ("drop_reserved", C.c_int)]
 
 
 class MmbtInputs(C.Structure):
     _fields_ = [("txt", C.c_void_p), ("mask", C.c_void_p), ("segment", C.c_void_p),
                 ("img", C.c_void_p), ("indices", C.c_void_p), ("n_sel", C.c_int),
-                ("indices_per_sample", C.c_int), ("params_bf16", C.c_void_p), ("dimg", C.c_void_p)]
+                ("indices_per_sample", C.c_int), ("params_bf16", C.c_void_p), ("dimg", C.c_void_p),
+                ("drop_seed", C.c_ulonglong)]
 
 
 class FlavaInputs(C.Structure):

@@ -385,20 +385,41 @@ softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, 
     p[c] = __float2bfloat16_rn(c < B ? __expf(s[c] - m) * inv : 0.f);
 }
 
+// `drop` (attention-probability dropout, MMBT training): the incoming gradient is that of the
+// DROPPED probabilities, dP = dPd * mask / (1 - p) with the mask regenerated from the counter
+// row * B + column (csrc/dropout.cuh); off by default.
 __global__ void __launch_bounds__(256)
 softmax_bwd_rows_kernel(const float* __restrict__ dP, const __nv_bfloat16* __restrict__ P,
-                        __nv_bfloat16* __restrict__ dS, int rows, int B, int Bp, float scale) {
+                        __nv_bfloat16* __restrict__ dS, int rows, int B, int Bp, float scale,
+                        const dropout::Site drop = dropout::Site{0u, 0u, 0u, 1.0f}) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float* g = dP + static_cast<size_t>(row) * Bp;
   const __nv_bfloat16* p = P + static_cast<size_t>(row) * Bp;
+  const unsigned int e0 = static_cast<unsigned int>(row) * static_cast<unsigned int>(B);
   float delta = 0.f;
-  for (int c = lane; c < B; c += 32) delta += g[c] * __bfloat162float(p[c]);
+  for (int c = lane; c < B; c += 32)
+    delta += g[c] * (drop.on() ? drop.mult(e0 + c) : 1.0f) * __bfloat162float(p[c]);
   delta = warp_sum(delta);
   __nv_bfloat16* o = dS + static_cast<size_t>(row) * Bp;
   for (int c = lane; c < Bp; c += 32)
-    o[c] = __float2bfloat16_rn(c < B ? __bfloat162float(p[c]) * (g[c] - delta) * scale : 0.f);
+    o[c] = __float2bfloat16_rn(
+        c < B ? __bfloat162float(p[c]) * (g[c] * (drop.on() ? drop.mult(e0 + c) : 1.0f) - delta) * scale : 0.f);
+}
+
+// Pd = P * mask / (1 - p): the dropped probabilities the P V product (and dV = Pd^T dO) consume.
+__global__ void __launch_bounds__(256)
+dropout_rows_kernel(const __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ Pd, int rows, int n,
+                    int np, const dropout::Site drop) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const unsigned int e0 = static_cast<unsigned int>(row) * static_cast<unsigned int>(n);
+  const __nv_bfloat16* p = P + static_cast<size_t>(row) * np;
+  __nv_bfloat16* o = Pd + static_cast<size_t>(row) * np;
+  for (int c = lane; c < np; c += 32)
+    o[c] = __float2bfloat16_rn(c < n ? __bfloat162float(p[c]) * drop.mult(e0 + c) : 0.f);
 }
 
 struct Views {
@@ -512,7 +533,8 @@ int bwd(const void* qkv, const void* dout, const void* probs, float* scores, voi
 // GEMMs as above with the roles of the batch and token axes swapped in the tensor maps.
 __global__ void __launch_bounds__(256)
 softmax_mask_rows_kernel(const float* __restrict__ S, const float* __restrict__ addmask,
-                         __nv_bfloat16* __restrict__ P, int rows, int n, int np, int rows_per_sample) {
+                         __nv_bfloat16* __restrict__ P, int rows, int n, int np, int rows_per_sample,
+                         __nv_bfloat16* __restrict__ Pd, const dropout::Site drop) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -526,8 +548,14 @@ softmax_mask_rows_kernel(const float* __restrict__ S, const float* __restrict__ 
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
   __nv_bfloat16* p = P + static_cast<size_t>(row) * np;
-  for (int c = lane; c < np; c += 32)
-    p[c] = __float2bfloat16_rn(c < n ? __expf(s[c] + am[c] - m) * inv : 0.f);
+  __nv_bfloat16* pd = Pd != nullptr ? Pd + static_cast<size_t>(row) * np : nullptr;
+  const unsigned int e0 = static_cast<unsigned int>(row) * static_cast<unsigned int>(n);
+  for (int c = lane; c < np; c += 32) {
+    const float v = c < n ? __expf(s[c] + am[c] - m) * inv : 0.f;
+    p[c] = __float2bfloat16_rn(v);
+    // the dropped copy is derived from the ROUNDED probability, as the backward regenerates it
+    if (pd != nullptr) pd[c] = __float2bfloat16_rn(c < n ? __bfloat162float(p[c]) * drop.mult(e0 + c) : 0.f);
+  }
 }
 
 BatchedOperand qkv_view_seq(const void* qkv, int B, int S, int D, int H, int third, int mn) {
@@ -548,7 +576,7 @@ BatchedOperand act_view_seq(const void* x, int B, int S, int D, int H, int mn) {
 }
 
 int seq_fwd(const void* qkv, const float* addmask, void* out, void* probs, float* scores, int B, int S,
-            int D, int H, cudaStream_t st) {
+            int D, int H, cudaStream_t st, dropout::Site drop, void* pdrop) {
   const int hd = D / H, G = B * H, Sp = (S + 7) / 8 * 8;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   int rc = gemm_bf16_batched_launch(qkv_view_seq(qkv, B, S, D, H, 0, 0), qkv_view_seq(qkv, B, S, D, H, 1, 0),
@@ -556,13 +584,48 @@ int seq_fwd(const void* qkv, const float* addmask, void* out, void* probs, float
                                     static_cast<long long>(S) * Sp, st);
   if (rc) return rc;
   const int rows = G * S;
+  const bool dropped = drop.on() && pdrop != nullptr;
   softmax_mask_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(
-      scores, addmask, static_cast<__nv_bfloat16*>(probs), rows, S, Sp, H * S);
+      scores, addmask, static_cast<__nv_bfloat16*>(probs), rows, S, Sp, H * S,
+      dropped ? static_cast<__nv_bfloat16*>(pdrop) : nullptr, drop);
   if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
   count_launch();
-  return gemm_bf16_batched_launch(sq_view(probs, G, S, Sp, 0), qkv_view_seq(qkv, B, S, D, H, 2, 1), G, S,
+  return gemm_bf16_batched_launch(sq_view(dropped ? pdrop : probs, G, S, Sp, 0), qkv_view_seq(qkv, B, S, D, H, 2, 1), G, S,
                                   hd, S, store_epi(out, 1, D, 1.0f), H, hd,
                                   static_cast<long long>(S) * D, st);
+}
+
+// With attention-probability dropout: Pd is regenerated into `dprobs` for dV = Pd^T dO FIRST, then
+// dPd = dO V^T, dS = P o (dPd * mask / (1 - p) - delta) / sqrt(hd) overwrites `dprobs`; the fused
+// kernels (no dropout support) are bypassed.
+int seq_bwd_dropout(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
+                    void* dqkv, int B, int S, int D, int H, cudaStream_t st, dropout::Site drop) {
+  const int hd = D / H, G = B * H, Sp = (S + 7) / 8 * 8;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  const int rows = G * S;
+  __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(dqkv);
+  const long long ld = 3LL * D, mid = 3LL * D * S;
+  dropout_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(probs),
+                                                     static_cast<__nv_bfloat16*>(dprobs), rows, S, Sp, drop);
+  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+  count_launch();
+  int rc = gemm_bf16_batched_launch(sq_view(dprobs, G, S, Sp, 1), act_view_seq(dout, B, S, D, H, 1), G, S, hd,
+                                    S, store_epi(dq + 2 * D, 1, ld, 1.0f), H, hd, mid, st);
+  if (rc) return rc;
+  rc = gemm_bf16_batched_launch(act_view_seq(dout, B, S, D, H, 0), qkv_view_seq(qkv, B, S, D, H, 2, 0),
+                                G, S, Sp, hd, store_epi(scores, 0, Sp, 1.0f), 1, 0,
+                                static_cast<long long>(S) * Sp, st);
+  if (rc) return rc;
+  softmax_bwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(
+      scores, static_cast<const __nv_bfloat16*>(probs), static_cast<__nv_bfloat16*>(dprobs), rows, S, Sp,
+      scale, drop);
+  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+  count_launch();
+  rc = gemm_bf16_batched_launch(sq_view(dprobs, G, S, Sp, 1), qkv_view_seq(qkv, B, S, D, H, 0, 1), G, S,
+                                hd, S, store_epi(dq + D, 1, ld, 1.0f), H, hd, mid, st);
+  if (rc) return rc;
+  return gemm_bf16_batched_launch(sq_view(dprobs, G, S, Sp, 0), qkv_view_seq(qkv, B, S, D, H, 1, 1), G, S,
+                                  hd, S, store_epi(dq, 1, ld, 1.0f), H, hd, mid, st);
 }
 
 int seq_bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
@@ -656,16 +719,30 @@ softmax_mask_kernel(float* __restrict__ P, const float* __restrict__ addmask, in
   for (int c = lane; c < n; c += 32) s[c] = expf(s[c] + am[c] - m) / sum;
 }
 __global__ void __launch_bounds__(256)
-softmax_bwd_kernel(float* __restrict__ dP, const float* __restrict__ P, int rows, int n, float scale) {
+softmax_bwd_kernel(float* __restrict__ dP, const float* __restrict__ P, int rows, int n, float scale,
+                   const dropout::Site drop = dropout::Site{0u, 0u, 0u, 1.0f}) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   float* g = dP + static_cast<size_t>(row) * n;
   const float* p = P + static_cast<size_t>(row) * n;
+  const unsigned int e0 = static_cast<unsigned int>(row) * static_cast<unsigned int>(n);
   float delta = 0.f;
-  for (int c = lane; c < n; c += 32) delta += g[c] * p[c];
+  for (int c = lane; c < n; c += 32) delta += g[c] * (drop.on() ? drop.mult(e0 + c) : 1.0f) * p[c];
   delta = warp_sum(delta);
-  for (int c = lane; c < n; c += 32) g[c] = p[c] * (g[c] - delta) * scale;
+  for (int c = lane; c < n; c += 32)
+    g[c] = p[c] * (g[c] * (drop.on() ? drop.mult(e0 + c) : 1.0f) - delta) * scale;
+}
+// Pd = P * mask / (1 - p) (fp32 parity path)
+__global__ void __launch_bounds__(256)
+dropout_rows_kernel(const float* __restrict__ P, float* __restrict__ Pd, int rows, int n,
+                    const dropout::Site drop) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const unsigned int e0 = static_cast<unsigned int>(row) * static_cast<unsigned int>(n);
+  for (int c = lane; c < n; c += 32)
+    Pd[static_cast<size_t>(row) * n + c] = P[static_cast<size_t>(row) * n + c] * drop.mult(e0 + c);
 }
 }  // namespace seq32
 
@@ -673,17 +750,18 @@ softmax_bwd_kernel(float* __restrict__ dP, const float* __restrict__ P, int rows
 
 int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, float* scores,
                       int dtype, int B, int S, int D, int H, cudaStream_t stream, int keep_probs,
-                      int allow_fused) {
+                      int allow_fused, dropout::Site drop, void* pdrop) {
   using namespace attn;
   if (qkv == nullptr || addmask == nullptr || out == nullptr || probs == nullptr) return MMU_ERR_ARG;
   if (B < 1 || S < 1 || H < 1 || D % H != 0) return MMU_ERR_SHAPE;
+  if (drop.on() && pdrop == nullptr) return MMU_ERR_ARG;
   if (dtype == DT_BF16) {
     if ((D / H) % 64 != 0 || scores == nullptr) return MMU_ERR_SHAPE;
-    if (allow_fused) {  // one fused kernel when it applies (head_dim 64, S <= 512)
+    if (allow_fused && !drop.on()) {  // one fused kernel when it applies (head_dim 64, S <= 512)
       const int rc = fused_seq_attention_fwd(qkv, addmask, out, keep_probs ? probs : nullptr, B, S, D, H, stream);
       if (rc <= 0) return rc;
     }
-    return tc::seq_fwd(qkv, addmask, out, probs, scores, B, S, D, H, stream);
+    return tc::seq_fwd(qkv, addmask, out, probs, scores, B, S, D, H, stream, drop, pdrop);
   }
   using seq32::Strided;
   const int hd = D / H, G = B * H;
@@ -697,18 +775,27 @@ int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* pr
   seq32::softmax_mask_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(P, addmask, rows, S, H * S);
   if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
   count_launch();
-  const Strided Pm{P, H * SS, SS, S, 1}, V{q + 2 * D, 3LL * D * S, hd, 1, 3LL * D};
+  const float* Puse = P;
+  if (drop.on()) {  // the dropped copy feeds P V; the undropped P is what the backward keeps
+    seq32::dropout_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(P, static_cast<float*>(pdrop), rows, S, drop);
+    if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+    count_launch();
+    Puse = static_cast<const float*>(pdrop);
+  }
+  const Strided Pm{Puse, H * SS, SS, S, 1}, V{q + 2 * D, 3LL * D * S, hd, 1, 3LL * D};
   return seq32::bgemm(Pm, V, static_cast<float*>(out), static_cast<long long>(S) * D, hd, D, G, S, hd, S, H,
                       1.0f, stream);
 }
 
 int seq_attention_bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
-                      void* dqkv, int dtype, int B, int S, int D, int H, cudaStream_t stream) {
+                      void* dqkv, int dtype, int B, int S, int D, int H, cudaStream_t stream,
+                      dropout::Site drop) {
   using namespace attn;
   if (qkv == nullptr || dout == nullptr || probs == nullptr || scores == nullptr || dqkv == nullptr)
     return MMU_ERR_ARG;
   if (dtype == DT_BF16) {
     if ((D / H) % 64 != 0 || dprobs == nullptr) return MMU_ERR_SHAPE;
+    if (drop.on()) return tc::seq_bwd_dropout(qkv, dout, probs, scores, dprobs, dqkv, B, S, D, H, stream, drop);
     return tc::seq_bwd(qkv, dout, probs, scores, dprobs, dqkv, B, S, D, H, stream);
   }
   using seq32::Strided;
@@ -719,15 +806,25 @@ int seq_attention_bwd(const void* qkv, const void* dout, const void* probs, floa
   float* dq = static_cast<float*>(dqkv);
   float* dS = scores;  // fp32 [G][S][S] scratch
   const long long SS = static_cast<long long>(S) * S, q0 = 3LL * D * S;
+  const int rows = G * S;
+  const Strided dOt{dO, static_cast<long long>(S) * D, hd, 1, D};
+  if (drop.on()) {  // dV = Pd^T dO first (Pd regenerated into the scratch), then the scratch is reused
+    seq32::dropout_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(P, dS, rows, S, drop);
+    if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+    count_launch();
+    const Strided Pdt{dS, H * SS, SS, 1, S};
+    if (int rc = seq32::bgemm(Pdt, dOt, dq + 2 * D, q0, hd, 3LL * D, G, S, hd, S, H, 1.0f, stream)) return rc;
+  }
   const Strided dOv{dO, static_cast<long long>(S) * D, hd, D, 1}, Vn{q + 2 * D, q0, hd, 3LL * D, 1};
   if (int rc = seq32::bgemm(dOv, Vn, dS, H * SS, SS, S, G, S, S, hd, H, 1.0f, stream)) return rc;
-  const int rows = G * S;
   seq32::softmax_bwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(dS, P, rows, S,
-                                                               1.0f / sqrtf(static_cast<float>(hd)));
+                                                               1.0f / sqrtf(static_cast<float>(hd)), drop);
   if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
   count_launch();
-  const Strided Pt{P, H * SS, SS, 1, S}, dOt{dO, static_cast<long long>(S) * D, hd, 1, D};
-  if (int rc = seq32::bgemm(Pt, dOt, dq + 2 * D, q0, hd, 3LL * D, G, S, hd, S, H, 1.0f, stream)) return rc;
+  if (!drop.on()) {
+    const Strided Pt{P, H * SS, SS, 1, S};
+    if (int rc = seq32::bgemm(Pt, dOt, dq + 2 * D, q0, hd, 3LL * D, G, S, hd, S, H, 1.0f, stream)) return rc;
+  }
   const Strided dSt{dS, H * SS, SS, 1, S}, Qt{q, q0, hd, 1, 3LL * D};
   if (int rc = seq32::bgemm(dSt, Qt, dq + D, q0, hd, 3LL * D, G, S, hd, S, H, 1.0f, stream)) return rc;
   const Strided dSn{dS, H * SS, SS, S, 1}, Kt{q + D, q0, hd, 1, 3LL * D};

@@ -6,6 +6,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "dropout.cuh"
+
 namespace mmu {
 
 enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
@@ -46,14 +48,26 @@ int colsum_accumulate(const void* x, int dtype, float* out, int M, int N, cudaSt
 // ---- post-LN residual blocks (BERT encoder of the MMBT path, reference src/mmbt.py:90-128;
 // arithmetic of pytorch_pretrained_bert's BertSelfOutput / BertOutput / BertLayerNorm, eps 1e-12)
 // s_out (fp32, may be null) = x_in + y (both `dtype`; y may be null); h = LN(s; gamma, beta, eps).
+// ydrop (training, hidden dropout): y is multiplied by the counter-based mask (element counter
+// row * D + column, csrc/dropout.cuh) before the residual add.
 int postln_fwd(const void* x_in, const void* y, float* s_out, const float* gamma, const float* beta,
                void* h, int dtype, float* mean, float* rstd, int M, int D, float eps,
-               cudaStream_t stream);
+               cudaStream_t stream, dropout::Site ydrop = dropout::Site{0u, 0u, 0u, 1.0f});
 // dx (fp32) and dx_lp (`dtype`, may be null; with dtype fp32 pass null) = LN'(dy_branch + dy_res);
 // dy_branch (`dtype`) or dy_res (fp32) may be null.  dgamma / dbeta / dcolsum(dx) accumulate.
+// Dropout in the backward of a post-LN sub-layer s = x + dropout(y), h = [dropout](LN(s)):
+//   in_a / in_b : mask the forward applied to the LayerNorm OUTPUT (embedding dropout); rows with
+//                 row_side[row] == 0 use in_b, all others (or row_side == null) in_a;
+//   out         : mask the forward applied to the branch y: dx_lp and dcolsum receive dx * mask
+//                 (what flows into the branch and its bias), dx itself (the residual path) does not.
+struct PostLnDropout {
+  dropout::Site in_a{0u, 0u, 0u, 1.0f}, in_b{0u, 0u, 0u, 1.0f}, out{0u, 0u, 0u, 1.0f};
+  const int* row_side = nullptr;
+};
 int postln_bwd(const void* dy_branch, const float* dy_res, int dtype, const float* x, const float* mean,
                const float* rstd, const float* gamma, float* dx, void* dx_lp, float* dgamma,
-               float* dbeta, float* dcolsum, int M, int D, cudaStream_t stream);
+               float* dbeta, float* dcolsum, int M, int D, cudaStream_t stream,
+               PostLnDropout dr = PostLnDropout{});
 
 // ---- heads: LayerNorm(ln_post) + row gather / segment mean pooling + E small Linears
 struct HeadSegments {
@@ -107,9 +121,13 @@ int attention_bwd(const void* qkv, const void* out, const void* dout, const floa
 // scores fp32 / dprobs bf16 scratch of the same shape (Sp = S rounded up to 8).
 // fp32: probs fp32 [B*H, S, S] kept for the backward, scores fp32 scratch (backward only).
 // keep_probs == 0 (inference): the fused bf16 kernel does not write the probabilities at all.
+// drop (attention-probability dropout, training): element counter ((b*H + h)*S + query)*S + key;
+// the fused kernel is bypassed, `pdrop` (same shape / dtype as probs) receives the dropped copy
+// that feeds P V while `probs` keeps the undropped probabilities for the backward.
 int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, float* scores,
                       int dtype, int B, int S, int D, int H, cudaStream_t stream, int keep_probs = 1,
-                      int allow_fused = 1);
+                      int allow_fused = 1, dropout::Site drop = dropout::Site{0u, 0u, 0u, 1.0f},
+                      void* pdrop = nullptr);
 // Fused forward (fused_attention.cu): head_dim 64, S <= 512; probs may be null (inference: nothing
 // but O is written).  Returns 1 when it does not apply, 0 on success, < 0 on error.
 int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, int B, int S,
@@ -117,7 +135,8 @@ int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, vo
 int fused_seq_attention_bwd_ds(const void* qkv, const void* dout, const void* probs, void* dprobs, void* dqkv,
                                int B, int S, int D, int H, cudaStream_t stream);
 int seq_attention_bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
-                      void* dqkv, int dtype, int B, int S, int D, int H, cudaStream_t stream);
+                      void* dqkv, int dtype, int B, int S, int D, int H, cudaStream_t stream,
+                      dropout::Site drop = dropout::Site{0u, 0u, 0u, 1.0f});
 
 // ---- fused softmax-CE / accuracy / uncertainty / calibration-histogram epilogue
 struct MetricAccum {  // lives in device memory; all-reduced (sum) across ranks

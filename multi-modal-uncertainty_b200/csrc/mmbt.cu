@@ -81,7 +81,14 @@ struct TableBuilder {
   }
 };
 
+int check_config_drop(const MmbtConfig& c) {
+  for (float p : {c.drop_hidden, c.drop_attn, c.drop_img})
+    if (!(p >= 0.f && p < 1.f)) return MMU_ERR_ARG;
+  return 0;
+}
+
 int check_config(const MmbtConfig& c) {
+  if (int rc = check_config_drop(c)) return rc;
   if (c.B < 1 || c.S_txt < 0 || c.n_img < 1 || c.d_img < 8 || c.D < 64 || c.D % 64 != 0 || c.D > 1024)
     return MMU_ERR_SHAPE;
   if (c.n_head < 1 || c.D % c.n_head != 0 || c.n_layers < 1 || c.n_layers > 48) return MMU_ERR_SHAPE;
@@ -164,6 +171,7 @@ struct Ws {
   int* row_pos;
   int* row_type;
   int* row_img;     // b*n_img + slot, or -1
+  int* row_side;    // 1: image side of the sequence ([CLS] img.. [SEP]), 0: text
   float* s0;        // fp32 [M, D] embedding sum (pre-LN)
   float* st0;
   void* h0;         // act [M, D]
@@ -211,6 +219,7 @@ void carve(const MmbtConfig& c, int training, void* base, const Layout& lay, Ws*
   w->row_pos = b.take<int>(M * 4);
   w->row_type = b.take<int>(M * 4);
   w->row_img = b.take<int>(M * 4);
+  w->row_side = b.take<int>(M * 4);
   w->s0 = b.take<float>(M * D * 4);
   w->st0 = b.take<float>(2 * M * 4);
   w->h0 = b.take<void>(M * D * s);
@@ -242,7 +251,9 @@ void carve(const MmbtConfig& c, int training, void* base, const Layout& lay, Ws*
   if (training) {
     w->gA = b.take<float>(M * D * 4);
     w->gB = b.take<float>(M * D * 4);
-    w->g_lp = bf ? b.take<void>(M * D * s) : nullptr;
+    // activation-dtype copy of the gradient stream; with hidden dropout the copy differs from the
+    // stream itself (masked), so the fp32 path needs its own buffer too
+    w->g_lp = (bf || c.drop_hidden > 0.f) ? b.take<void>(M * D * s) : nullptr;
     w->dbig = b.take<void>(M * (F > 3 * D ? F : 3 * D) * s);
     w->dh = b.take<void>(M * D * s);
     w->dprobs = bf ? b.take<void>(sq * 2) : nullptr;
@@ -280,7 +291,8 @@ embed_fwd_kernel(const long long* __restrict__ txt, const long long* __restrict_
                  int S_txt, int n_img, int D, int cls_id, int sep_id, int vocab, int n_types,
                  float* __restrict__ s0, float* __restrict__ st0, T* __restrict__ h0,
                  float* __restrict__ addmask, int* __restrict__ row_word, int* __restrict__ row_pos,
-                 int* __restrict__ row_type, int* __restrict__ row_img) {
+                 int* __restrict__ row_type, int* __restrict__ row_img, int* __restrict__ row_side,
+                 const dropout::Site drop_img, const dropout::Site drop_txt) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int M = B * S;
@@ -331,7 +343,12 @@ embed_fwd_kernel(const long long* __restrict__ txt, const long long* __restrict_
     const int c = lane + 32 * i;
     if (c < D) {
       if (s0 != nullptr) s0[ro + c] = v[i];
-      stf(h0 + ro + c, (v[i] - mean) * rstd * gamma[c] + beta[c]);
+      float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      // embedding dropout after the LayerNorm: ImageBertEmbeddings.dropout (args.dropout,
+      // src/mmbt.py:56,82) on the image side, BertEmbeddings.dropout on the text side
+      const dropout::Site& ds = p < n2 ? drop_img : drop_txt;
+      if (ds.on()) o *= ds.mult(static_cast<unsigned int>(r) * D + c);
+      stf(h0 + ro + c, o);
     }
   }
   if (lane == 0) {
@@ -344,6 +361,7 @@ embed_fwd_kernel(const long long* __restrict__ txt, const long long* __restrict_
     row_pos[r] = pid;
     row_type[r] = tid;
     row_img[r] = iid;
+    row_side[r] = p < n2 ? 1 : 0;
   }
 }
 
@@ -565,6 +583,10 @@ int mmbt_forward(const MmbtConfig& c, const float* params, const MmbtInputs& in,
   }
   MB_TRY(gemm(img_op, c.d_img, 0, W(lay.img_w), c.d_img, 0, Mi, D, c.d_img,
               epi(EPI_STORE, w.imgp, 0, D, params + lay.img_b)));
+  // ---- dropout sites of this forward (training only; csrc/dropout.cuh).  0: embeddings, per layer
+  //      l: 4l+1 attention probabilities, 4l+2 attention-output dense, 4l+3 FFN-output dense.
+  const dropout::Site off{0u, 0u, 0u, 1.0f};
+  auto site = [&](float p, int id) { return (training && p > 0.f) ? dropout::make_site(p, in.drop_seed, id) : off; };
   // ---- embeddings + LayerNorm + mask + bookkeeping, only for the selected positions
   {
     const int grid = (M + 7) / 8;
@@ -575,13 +597,15 @@ int mmbt_forward(const MmbtConfig& c, const float* params, const MmbtInputs& in,
           in.txt, in.mask, in.segment, w.imgp, in.indices, in.indices_per_sample ? S : 0, params + lay.word,
           params + lay.pos, params + lay.type, params + lay.eln_w, params + lay.eln_b, c.B, S, c.S_txt, c.n_img, D,
           c.cls_id, c.sep_id, c.vocab, c.n_types, s0, st0, static_cast<__nv_bfloat16*>(w.h0),
-          w.addmask, w.row_word, w.row_pos, w.row_type, w.row_img);
+          w.addmask, w.row_word, w.row_pos, w.row_type, w.row_img, w.row_side, site(c.drop_img, 0),
+          site(c.drop_hidden, 0));
     else
       embed_fwd_kernel<float><<<grid, 256, 0, stream>>>(
           in.txt, in.mask, in.segment, w.imgp, in.indices, in.indices_per_sample ? S : 0, params + lay.word,
           params + lay.pos, params + lay.type, params + lay.eln_w, params + lay.eln_b, c.B, S, c.S_txt, c.n_img, D,
           c.cls_id, c.sep_id, c.vocab, c.n_types, s0, st0, static_cast<float*>(w.h0), w.addmask,
-          w.row_word, w.row_pos, w.row_type, w.row_img);
+          w.row_word, w.row_pos, w.row_type, w.row_img, w.row_side, site(c.drop_img, 0),
+          site(c.drop_hidden, 0));
     MB_CHECK_LAUNCH();
   }
   // ---- encoder
@@ -590,12 +614,15 @@ int mmbt_forward(const MmbtConfig& c, const float* params, const MmbtInputs& in,
     const LayerP& p = lay.layer[i];
     const LayerWs& l = w.layer[i];
     MB_TRY(gemm(h, D, 0, W(p.q_w), D, 0, M, 3 * D, D, epi(EPI_STORE, l.qkv, bf, 3 * D, params + p.q_b)));
+    // attention-probability dropout: the dropped copy that feeds P V goes to a scratch (bf16: the
+    // backward's dS buffer; fp32: the score scratch, unused by the fp32 forward)
     MB_TRY(seq_attention_fwd(l.qkv, w.addmask, l.ctx, l.probs, w.scores, dt, c.B, S, D, c.n_head, stream,
-                             training));
+                             training, 1, site(c.drop_attn, 4 * i + 1),
+                             bf ? w.dprobs : static_cast<void*>(w.scores)));
     MB_TRY(gemm(l.ctx, D, 0, W(p.ao_w), D, 0, M, D, D, epi(EPI_STORE, w.ybuf, bf, D, params + p.ao_b)));
     MB_TRY(postln_fwd(h, w.ybuf, training ? l.s1 : nullptr, params + p.ln1_w, params + p.ln1_b, l.a, dt,
                       training ? l.st1 : nullptr, training ? l.st1 + M : nullptr, M, D, BERT_LN_EPS,
-                      stream));
+                      stream, site(c.drop_hidden, 4 * i + 2)));
     if (bf) {  // u = gelu_erf(a Wi^T + b) in the GEMM epilogue (z kept only for the backward)
       GemmEpilogue e = epi(EPI_QUICKGELU, training ? l.z : nullptr, 1, F, params + p.i_b);
       e.out2 = l.u; e.ld_out2 = F; e.act = 1;
@@ -610,7 +637,7 @@ int mmbt_forward(const MmbtConfig& c, const float* params, const MmbtInputs& in,
     MB_TRY(gemm(l.u, F, 0, W(p.o_w), F, 0, M, D, F, epi(EPI_STORE, w.ybuf, bf, D, params + p.o_b)));
     MB_TRY(postln_fwd(l.a, w.ybuf, training ? l.s2 : nullptr, params + p.ln2_w, params + p.ln2_b, l.h, dt,
                       training ? l.st2 : nullptr, training ? l.st2 + M : nullptr, M, D, BERT_LN_EPS,
-                      stream));
+                      stream, site(c.drop_hidden, 4 * i + 3)));
     h = l.h;
   }
   // ---- pooler (tanh(dense(first token))) + classifier (src/mmbt.py:129, :246-247)
@@ -653,8 +680,13 @@ int mmbt_backward(const MmbtConfig& c, const float* params, const MmbtInputs& in
     return bf ? static_cast<const void*>(static_cast<const uint16_t*>(shadow) + off)
               : static_cast<const void*>(params + off);
   };
-  // low-precision copy of the fp32 gradient stream (fp32 path: the stream itself)
-  auto LP = [&](float* g) -> void* { return bf ? w.g_lp : static_cast<void*>(g); };
+  // activation-dtype copy of the fp32 gradient stream as the BRANCH sees it (fp32 path without
+  // hidden dropout: the stream itself; with hidden dropout the copy carries the dropout mask)
+  const dropout::Site off{0u, 0u, 0u, 1.0f};
+  auto site = [&](float p, int id) { return p > 0.f ? dropout::make_site(p, in.drop_seed, id) : off; };
+  const bool hdrop = c.drop_hidden > 0.f;
+  auto LP = [&](float* g) -> void* { return (bf || hdrop) ? w.g_lp : static_cast<void*>(g); };
+  auto out_mask = [&](int id) { PostLnDropout d; d.out = site(c.drop_hidden, id); return d; };
 
   // ---- classifier + pooler
   const void* h_last = w.layer[c.n_layers - 1].h;
@@ -693,8 +725,8 @@ int mmbt_backward(const MmbtConfig& c, const float* params, const MmbtInputs& in
     const void* h_in = i > 0 ? w.layer[i - 1].h : w.h0;
     // h' = LN2(s2):  ds2 -> gA ; d(output.dense.bias) += colsum(ds2)
     MB_TRY(postln_bwd(branch, w.gB, dt, l.s2, l.st2, l.st2 + M, params + p.ln2_w, w.gA,
-                      bf ? w.g_lp : nullptr, grads + p.ln2_w, grads + p.ln2_b, grads + p.o_b, M, D,
-                      stream));
+                      (bf || hdrop) ? w.g_lp : nullptr, grads + p.ln2_w, grads + p.ln2_b, grads + p.o_b, M, D,
+                      stream, out_mask(4 * i + 3)));
     // s2 = a + u Wo2^T + b:  du = ds2 Wo2 -> dz = du * gelu'(z)
     if (bf) {  // dGELU fused into the dgrad GEMM epilogue (z arrives by TMA)
       GemmEpilogue e = epi(EPI_DGELU, w.dbig, 1, F, nullptr);
@@ -716,14 +748,14 @@ int mmbt_backward(const MmbtConfig& c, const float* params, const MmbtInputs& in
     MB_TRY(gemm(w.dbig, F, 0, W(p.i_w), D, 1, M, D, F, epi(EPI_STORE, w.dh, bf, D, nullptr)));
     // a = LN1(s1):  ds1 = LN1'(da_branch + ds2) -> gB ; d(attention.output.dense.bias) += colsum
     MB_TRY(postln_bwd(w.dh, w.gA, dt, l.s1, l.st1, l.st1 + M, params + p.ln1_w, w.gB,
-                      bf ? w.g_lp : nullptr, grads + p.ln1_w, grads + p.ln1_b, grads + p.ao_b, M, D,
-                      stream));
+                      (bf || hdrop) ? w.g_lp : nullptr, grads + p.ln1_w, grads + p.ln1_b, grads + p.ao_b, M, D,
+                      stream, out_mask(4 * i + 2)));
     // s1 = h + ctx Wo^T + b:  dWo += ds1^T ctx ; dctx = ds1 Wo
     MB_TRY(gemm(LP(w.gB), D, 1, l.ctx, D, 1, D, D, M, epi(EPI_ATOMIC, grads + p.ao_w, 0, D, nullptr),
                 wsplits(D, D, M)));
     MB_TRY(gemm(LP(w.gB), D, 0, W(p.ao_w), D, 1, M, D, D, epi(EPI_STORE, w.dh, bf, D, nullptr)));
     MB_TRY(seq_attention_bwd(l.qkv, w.dh, l.probs, w.scores, w.dprobs, w.dbig, dt, c.B, S, D, c.n_head,
-                             stream));
+                             stream, site(c.drop_attn, 4 * i + 1)));
     // dWqkv[3D, D] += dqkv^T h ; dbqkv += colsum(dqkv) ; dh_branch = dqkv Wqkv
     MB_TRY(gemm(w.dbig, 3 * D, 1, h_in, D, 1, 3 * D, D, M, epi(EPI_ATOMIC, grads + p.q_w, 0, D, nullptr),
                 wsplits(3 * D, D, M)));
@@ -732,8 +764,12 @@ int mmbt_backward(const MmbtConfig& c, const float* params, const MmbtInputs& in
     branch = w.dh;
   }
   // ---- embeddings: dE = LN_emb'(branch + gB) -> gA, scattered to the tables / image tokens
+  PostLnDropout edrop;  // the forward dropped the OUTPUT of the embedding LayerNorm
+  edrop.in_a = site(c.drop_img, 0);
+  edrop.in_b = site(c.drop_hidden, 0);
+  edrop.row_side = w.row_side;
   MB_TRY(postln_bwd(branch, w.gB, dt, w.s0, w.st0, w.st0 + M, params + lay.eln_w, w.gA, nullptr,
-                    grads + lay.eln_w, grads + lay.eln_b, nullptr, M, D, stream));
+                    grads + lay.eln_w, grads + lay.eln_b, nullptr, M, D, stream, edrop));
   if (cudaMemsetAsync(w.dimgp, 0, static_cast<size_t>(Mi) * D * 4, stream) != cudaSuccess) return MMU_ERR_CUDA;
   embed_bwd_kernel<<<grid1d(static_cast<long long>(M) * D, 256), 256, 0, stream>>>(
       w.gA, w.row_word, w.row_pos, w.row_img, M, D, grads + lay.word, grads + lay.pos, w.dimgp);

@@ -32,6 +32,12 @@ struct MmbtConfig {
   int precision; // Precision
   int max_seq;   // workspace capacity in sequence positions; 0 = n_img + 2 + S_txt.  A caller that
                  // only ever runs short index lists (packed robustness variants) sizes it to n_sel.
+  // Dropout probabilities, applied by a TRAINING forward and its backward only (csrc/dropout.cuh):
+  float drop_hidden;  // BertConfig.hidden_dropout_prob: text embeddings, attention-output and
+                      // FFN-output dense layers (before the residual add + LayerNorm)
+  float drop_attn;    // BertConfig.attention_probs_dropout_prob: softmax(QK^T) before P V
+  float drop_img;     // args.dropout: ImageBertEmbeddings.dropout (src/mmbt.py:56,82)
+  int drop_reserved;
 };
 
 struct MmbtInputs {
@@ -50,6 +56,7 @@ struct MmbtInputs {
   int indices_per_sample;
   const void* params_bf16;   // optional caller-maintained bf16 shadow of params
   float* dimg;               // backward only: d loss / d img (B, n_img, d_img) fp32, or null
+  unsigned long long drop_seed;  // seed of this forward's dropout masks (the backward needs the same)
 };
 
 int mmbt_param_table(const MmbtConfig& c, ParamEntry* out, int max_entries);  // returns count

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(THREADS)
 postln_fwd_kernel(const T* __restrict__ x_in, const T* __restrict__ y, float* __restrict__ s_out,
                   const float* __restrict__ gamma, const float* __restrict__ beta,
                   T* __restrict__ h, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                  int M, int D, float eps) {
+                  int M, int D, float eps, const dropout::Site ydrop) {
   ptx::pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = D >> 2;
@@ -312,6 +312,14 @@ postln_fwd_kernel(const T* __restrict__ x_in, const T* __restrict__ y, float* __
     r.load(x_in + static_cast<size_t>(row) * D, nvec, lane);
     if (y != nullptr) {
       ry.load(y + static_cast<size_t>(row) * D, nvec, lane);
+      if (ydrop.on()) {  // hidden dropout on the branch output, before the residual add
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const unsigned int e0 = static_cast<unsigned int>(row) * D + 4u * (lane + 32 * i);
+          ry.v[i].x *= ydrop.mult(e0); ry.v[i].y *= ydrop.mult(e0 + 1);
+          ry.v[i].z *= ydrop.mult(e0 + 2); ry.v[i].w *= ydrop.mult(e0 + 3);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         r.v[i].x += ry.v[i].x; r.v[i].y += ry.v[i].y; r.v[i].z += ry.v[i].z; r.v[i].w += ry.v[i].w;
@@ -475,7 +483,8 @@ postln_bwd_kernel(const T* __restrict__ dy_branch, const float* __restrict__ dy_
                   const float* __restrict__ x, const float* __restrict__ mean,
                   const float* __restrict__ rstd, const float* __restrict__ gamma,
                   float* __restrict__ dx, T* __restrict__ dx_lp, float* __restrict__ dgamma,
-                  float* __restrict__ dbeta, float* __restrict__ dcolsum, int M, int D) {
+                  float* __restrict__ dbeta, float* __restrict__ dcolsum, int M, int D,
+                  const PostLnDropout dr) {
   ptx::pdl_trigger();
   extern __shared__ float red[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -494,6 +503,17 @@ postln_bwd_kernel(const T* __restrict__ dy_branch, const float* __restrict__ dy_
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         rdy.v[i].x += rr.v[i].x; rdy.v[i].y += rr.v[i].y; rdy.v[i].z += rr.v[i].z; rdy.v[i].w += rr.v[i].w;
+      }
+    }
+    if (dr.in_a.on() || dr.in_b.on()) {  // dropout applied to the LayerNorm OUTPUT in the forward
+      const dropout::Site site = (dr.row_side != nullptr && dr.row_side[row] == 0) ? dr.in_b : dr.in_a;
+      if (site.on()) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const unsigned int e0 = static_cast<unsigned int>(row) * D + 4u * (lane + 32 * i);
+          rdy.v[i].x *= site.mult(e0); rdy.v[i].y *= site.mult(e0 + 1);
+          rdy.v[i].z *= site.mult(e0 + 2); rdy.v[i].w *= site.mult(e0 + 3);
+        }
       }
     }
     const float mu = mean[row], rs = rstd[row];
@@ -528,6 +548,11 @@ postln_bwd_kernel(const T* __restrict__ dy_branch, const float* __restrict__ dy_
         o.z = rs * (d.z - s1 - xv.z * s2);
         o.w = rs * (d.w - s1 - xv.w * s2);
         *reinterpret_cast<float4*>(dx + static_cast<size_t>(row) * D + 4 * c) = o;
+        if (dr.out.on()) {  // the branch (and its bias) see the gradient through their dropout mask
+          const unsigned int e0 = static_cast<unsigned int>(row) * D + 4u * c;
+          o.x *= dr.out.mult(e0); o.y *= dr.out.mult(e0 + 1);
+          o.z *= dr.out.mult(e0 + 2); o.w *= dr.out.mult(e0 + 3);
+        }
         if (dx_lp != nullptr) Vec4<T>::st(dx_lp + static_cast<size_t>(row) * D + 4 * c, o);
         acc_c[i].x += o.x; acc_c[i].y += o.y; acc_c[i].z += o.z; acc_c[i].w += o.w;
       }
@@ -1066,7 +1091,7 @@ int layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* mea
 
 int postln_fwd(const void* x_in, const void* y, float* s_out, const float* gamma, const float* beta,
                void* h, int dtype, float* mean, float* rstd, int M, int D, float eps,
-               cudaStream_t stream) {
+               cudaStream_t stream, dropout::Site ydrop) {
   const int nv = nv_for(D);
   if (nv < 0) return MMU_ERR_SHAPE;
   if (M <= 0) return 0;
@@ -1075,11 +1100,11 @@ int postln_fwd(const void* x_in, const void* y, float* s_out, const float* gamma
     using T = __nv_bfloat16;
     MMU_NV_DISPATCH(nv, (postln_fwd_kernel<NV, T><<<grid, THREADS, 0, stream>>>(
                             static_cast<const T*>(x_in), static_cast<const T*>(y), s_out, gamma, beta,
-                            static_cast<T*>(h), mean, rstd, M, D, eps)));
+                            static_cast<T*>(h), mean, rstd, M, D, eps, ydrop)));
   } else {
     MMU_NV_DISPATCH(nv, (postln_fwd_kernel<NV, float><<<grid, THREADS, 0, stream>>>(
                             static_cast<const float*>(x_in), static_cast<const float*>(y), s_out, gamma,
-                            beta, static_cast<float*>(h), mean, rstd, M, D, eps)));
+                            beta, static_cast<float*>(h), mean, rstd, M, D, eps, ydrop)));
   }
   MMU_CHECK_LAUNCH();
   return 0;
@@ -1087,7 +1112,7 @@ int postln_fwd(const void* x_in, const void* y, float* s_out, const float* gamma
 
 int postln_bwd(const void* dy_branch, const float* dy_res, int dtype, const float* x, const float* mean,
                const float* rstd, const float* gamma, float* dx, void* dx_lp, float* dgamma,
-               float* dbeta, float* dcolsum, int M, int D, cudaStream_t stream) {
+               float* dbeta, float* dcolsum, int M, int D, cudaStream_t stream, PostLnDropout dr) {
   const int nv = nv_for(D);
   if (nv < 0) return MMU_ERR_SHAPE;
   if (M <= 0) return 0;
@@ -1098,11 +1123,11 @@ int postln_bwd(const void* dy_branch, const float* dy_res, int dtype, const floa
     using T = __nv_bfloat16;
     MMU_NV_DISPATCH(nv, (postln_bwd_kernel<NV, T><<<grid, LNB_THREADS, smem, stream>>>(
                             static_cast<const T*>(dy_branch), dy_res, x, mean, rstd, gamma, dx,
-                            static_cast<T*>(dx_lp), dgamma, dbeta, dcolsum, M, D)));
+                            static_cast<T*>(dx_lp), dgamma, dbeta, dcolsum, M, D, dr)));
   } else {
     MMU_NV_DISPATCH(nv, (postln_bwd_kernel<NV, float><<<grid, LNB_THREADS, smem, stream>>>(
                             static_cast<const float*>(dy_branch), dy_res, x, mean, rstd, gamma, dx,
-                            static_cast<float*>(dx_lp), dgamma, dbeta, dcolsum, M, D)));
+                            static_cast<float*>(dx_lp), dgamma, dbeta, dcolsum, M, D, dr)));
   }
   MMU_CHECK_LAUNCH();
   return 0;

@@ -13,9 +13,14 @@ executed by the CUDA MMBT engine (``csrc/mmbt.cu``).
   under both prefixes in ``state_dict()`` exactly as in the reference, so reference checkpoints
   load with ``strict=True``.
 * The BERT arithmetic follows the published definitions of the reference's un-vendored dependency
-  ``pytorch_pretrained_bert`` (restated for the tests in ``oracle/bert_restated.py``).  BERT's
-  internal dropout is not implemented: the engine computes the dropout-free network (the
-  reference's ``eval()`` behaviour, and its ``train()`` behaviour at dropout 0).
+  ``pytorch_pretrained_bert`` (restated for the tests in ``oracle/bert_restated.py``).
+* Dropout in ``train()`` mode as in the reference: BERT's hidden / attention-probability dropouts
+  (``BertConfig`` defaults 0.1; ``bert_config`` keys ``hidden_dropout_prob`` /
+  ``attention_probs_dropout_prob`` or ``args.bert_dropout`` change them) and
+  ``ImageBertEmbeddings.dropout`` (``args.dropout``, ``src/mmbt.py:56,82``).  Masks come from the
+  engine's counter-based generator (``csrc/dropout.cuh``; statistical parity with torch's Philox
+  draws, bit-exact against ``oracle/dropout.py``) and are regenerated in the backward; with
+  attention dropout the three-kernel attention path runs instead of the fused kernels.
 There is no CPU path.
 """
 import ctypes as C
@@ -32,11 +37,15 @@ _PREC = {"fp32": 0, "bf16": 1}
 #: architecture of the checkpoints ``BertModel.from_pretrained(name)`` would fetch (no network here:
 #: weights are random-initialised exactly like ``init_bert_weights`` and meant to be overwritten by
 #: ``load_state_dict``).  ``args.bert_config`` (a dict with the same keys) overrides the lookup.
+# hidden_dropout_prob / attention_probs_dropout_prob: 0.1 in the pretrained checkpoints' configs
+# (and BertConfig's defaults), i.e. what the reference's BertModel applies in train() mode
 BERT_CONFIGS = {
     "bert-base-uncased": dict(vocab=30522, D=768, n_head=12, n_layers=12, d_ff=3072, max_pos=512,
-                              n_types=2, init_range=0.02),
+                              n_types=2, init_range=0.02, hidden_dropout_prob=0.1,
+                              attention_probs_dropout_prob=0.1),
     "bert-large-uncased": dict(vocab=30522, D=1024, n_head=16, n_layers=24, d_ff=4096, max_pos=512,
-                               n_types=2, init_range=0.02),
+                               n_types=2, init_range=0.02, hidden_dropout_prob=0.1,
+                               attention_probs_dropout_prob=0.1),
 }
 
 
@@ -86,6 +95,17 @@ class MultimodalBertClf(nn.Module):
             raise ValueError("args.hidden_sz must equal the BERT hidden size")
         self.precision = _PREC[getattr(args, "precision", "bf16")]
         self._bc = bc
+        # Dropout of a training-mode forward (reference: BertModel's hidden / attention-probability
+        # dropouts, BertConfig defaults 0.1, and ImageBertEmbeddings.dropout = args.dropout,
+        # src/mmbt.py:56).  ``args.bert_dropout`` (optional) overrides both BERT probabilities.
+        bd = getattr(args, "bert_dropout", None)
+        self.drop_hidden = float(bc.get("hidden_dropout_prob", 0.1) if bd is None else bd)
+        self.drop_attn = float(bc.get("attention_probs_dropout_prob", 0.1) if bd is None else bd)
+        self.drop_img = float(getattr(args, "dropout", 0.0) or 0.0)
+        for pr in (self.drop_hidden, self.drop_attn, self.drop_img):
+            if not 0.0 <= pr < 1.0:
+                raise ValueError("dropout probabilities must be in [0, 1)")
+        self.last_dropout_seed = None
         self._n_img = int(args.num_image_embeds)
         self._d_img = int(args.img_hidden_sz)
         self._cls_id = int(args.vocab.stoi["[CLS]"])
@@ -155,7 +175,7 @@ class MultimodalBertClf(nn.Module):
             cfg = self._cfgs[key] = _lib.MmbtConfig(
                 B, S_txt, self._n_img, self._d_img, bc["D"], bc["n_head"], bc["n_layers"], bc["d_ff"],
                 bc["vocab"], bc["max_pos"], bc["n_types"], int(self.args.n_classes), self._cls_id,
-                self._sep_id, self.precision, max_seq)
+                self._sep_id, self.precision, max_seq, self.drop_hidden, self.drop_attn, self.drop_img, 0)
         return cfg
 
     def _own_parameters(self):
@@ -266,24 +286,29 @@ class MultimodalBertClf(nn.Module):
         per_sample = int(idx is not None and idx.dim() == 2)
         if per_sample and idx.shape[0] != B:
             raise ValueError("per-sample index lists must be (B, S)")
+        seed = 0
+        if training and (self.drop_hidden > 0 or self.drop_attn > 0 or self.drop_img > 0):
+            # masks are a function of this seed (torch's CPU generator: torch.manual_seed reproduces
+            # a run); the backward regenerates them from the same value
+            seed = self.last_dropout_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         inp = _lib.MmbtInputs(txt.data_ptr(), mask.data_ptr(), segment.data_ptr(), tokens.data_ptr(),
                               _lib.ptr(idx), 0 if idx is None else idx.shape[-1], per_sample,
-                              _lib.ptr(shadow), None)
+                              _lib.ptr(shadow), None, seed)
         logits = torch.empty(B, int(self.args.n_classes), device=dev, dtype=torch.float32)
         _lib.check(_lib.lib.mmu_mmbt_forward(C.byref(cfg), self._flat.data_ptr(), C.byref(inp),
                                              ws.data_ptr(), ws.numel(), int(training), logits.data_ptr(),
                                              _lib.stream_ptr()), "mmu_mmbt_forward")
-        saved = (cfg, ws, (tokens, txt, mask, segment, idx, shadow), logits)
+        saved = (cfg, ws, (tokens, txt, mask, segment, idx, shadow, seed), logits)
         return stamp_workspace(self, ws, saved) if training else saved
 
     def _engine_backward(self, saved, dlogits, need_dimg):
-        cfg, ws, (tokens, txt, mask, segment, idx, shadow), _ = saved
+        cfg, ws, (tokens, txt, mask, segment, idx, shadow, seed), _ = saved
         check_workspace(self, ws, saved)
         self._ensure_grad_views()
         dimg = torch.empty_like(tokens) if need_dimg else None
         inp = _lib.MmbtInputs(txt.data_ptr(), mask.data_ptr(), segment.data_ptr(), tokens.data_ptr(),
                               _lib.ptr(idx), 0 if idx is None else idx.shape[-1],
-                              int(idx is not None and idx.dim() == 2), _lib.ptr(shadow), _lib.ptr(dimg))
+                              int(idx is not None and idx.dim() == 2), _lib.ptr(shadow), _lib.ptr(dimg), seed)
         _lib.check(_lib.lib.mmu_mmbt_backward(C.byref(cfg), self._flat.data_ptr(), C.byref(inp),
                                               ws.data_ptr(), ws.numel(), dlogits.data_ptr(),
                                               self._flat_grad.data_ptr(), _lib.stream_ptr()),
@@ -306,9 +331,6 @@ class MultimodalBertClf(nn.Module):
         """General entry: ``indices`` (sequence of ints over ``[CLS] img.. [SEP] | text..``, or None
         for all positions) selects what enters the encoder."""
         tokens = self._tokens(img)
-        if self.training and float(getattr(self.args, "dropout", 0.0) or 0.0) > 0.0:
-            raise _lib.MMUError("dropout > 0 in training is not implemented (the engine computes the "
-                                "dropout-free network); train with args.dropout = 0 or call .eval()")
         if self.training and torch.is_grad_enabled():
             if tokens.requires_grad:
                 return _MmbtForward.apply(tokens, self, txt, mask, segment, indices)

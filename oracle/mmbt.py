@@ -73,7 +73,19 @@ def mode_indices(mode, n_img, s_txt):
     raise ValueError(mode)
 
 
-def bert_layer(P, i, h, ext_mask, n_head):
+def _mult(dropout, key, site, like):
+    """0 / (1 / (1 - p)) factors of dropout site ``site`` over the row-major elements of ``like``
+    (the engine's counter-based masks, oracle/dropout.py); None when that dropout is off."""
+    if dropout is None or not dropout.get(key, 0.0) > 0.0:
+        return None
+    from . import dropout as _d
+    return _d.multiplier(dropout[key], dropout["seed"], site, like.numel(), tuple(like.shape), like.dtype)
+
+
+def bert_layer(P, i, h, ext_mask, n_head, dropout=None):
+    """BertLayer (pytorch_pretrained_bert): self-attention with attention-probability dropout,
+    BertSelfOutput / BertOutput with hidden dropout before the residual add (train mode only;
+    ``dropout = dict(hidden=, attn=, img=, seed=)``, sites 4i+1 / 4i+2 / 4i+3)."""
     pre = f"enc.encoder.layer.{i}."
     B, S, D = h.shape
     hd = D // n_head
@@ -88,17 +100,29 @@ def bert_layer(P, i, h, ext_mask, n_head):
     scores = scores - scores.max(dim=-1, keepdim=True)[0]
     e = torch.exp(scores)
     probs = e / e.sum(dim=-1, keepdim=True)
+    m = _mult(dropout, "attn", 4 * i + 1, probs)
+    if m is not None:
+        probs = probs * m
     ctx = (probs @ v).permute(0, 2, 1, 3).reshape(B, S, D)
-    a = layer_norm(linear(ctx, P[pre + "attention.output.dense.weight"], P[pre + "attention.output.dense.bias"]) + h,
-                   P[pre + "attention.output.LayerNorm.weight"], P[pre + "attention.output.LayerNorm.bias"])
+    y = linear(ctx, P[pre + "attention.output.dense.weight"], P[pre + "attention.output.dense.bias"])
+    m = _mult(dropout, "hidden", 4 * i + 2, y)
+    if m is not None:
+        y = y * m
+    a = layer_norm(y + h, P[pre + "attention.output.LayerNorm.weight"], P[pre + "attention.output.LayerNorm.bias"])
     u = gelu(linear(a, P[pre + "intermediate.dense.weight"], P[pre + "intermediate.dense.bias"]))
-    return layer_norm(linear(u, P[pre + "output.dense.weight"], P[pre + "output.dense.bias"]) + a,
-                      P[pre + "output.LayerNorm.weight"], P[pre + "output.LayerNorm.bias"])
+    y = linear(u, P[pre + "output.dense.weight"], P[pre + "output.dense.bias"])
+    m = _mult(dropout, "hidden", 4 * i + 3, y)
+    if m is not None:
+        y = y * m
+    return layer_norm(y + a, P[pre + "output.LayerNorm.weight"], P[pre + "output.LayerNorm.bias"])
 
 
-def forward(P, txt, mask, segment, img_tokens, cfg, indices=None):
+def forward(P, txt, mask, segment, img_tokens, cfg, indices=None, dropout=None):
     """``MultimodalBertClf.forward*`` from the pooled image tokens (B, N, d_img) onward.
-    ``indices``: LongTensor over the full sequence (None = all)."""
+    ``indices``: LongTensor over the full sequence (None = all).  ``dropout`` (train mode):
+    ``dict(hidden=, attn=, img=, seed=)`` -- ImageBertEmbeddings.dropout (src/mmbt.py:82) on the
+    image side of the embedded sequence, BertEmbeddings' on the text side (site 0, element counter
+    over the SELECTED rows), then the per-layer sites of ``bert_layer``."""
     pre = "enc.txt_embeddings."
     B = txt.shape[0]
     n_img = img_tokens.shape[1]
@@ -107,12 +131,18 @@ def forward(P, txt, mask, segment, img_tokens, cfg, indices=None):
     emb = torch.cat([image_bert_embeddings(P, img_tokens, cfg["cls_id"], cfg["sep_id"]),
                      bert_text_embeddings(P, txt, segment)], dim=1)
     emb = layer_norm(emb, P[pre + "LayerNorm.weight"], P[pre + "LayerNorm.bias"])
+    pos = torch.arange(emb.shape[1])
     if indices is not None:
-        emb, full_mask = emb[:, indices], full_mask[:, indices]
+        emb, full_mask, pos = emb[:, indices], full_mask[:, indices], pos[indices]
+    if dropout is not None:
+        m_img, m_txt = _mult(dropout, "img", 0, emb), _mult(dropout, "hidden", 0, emb)
+        one = torch.ones_like(emb)
+        side = (pos < n_img + 2)[None, :, None]
+        emb = emb * torch.where(side, m_img if m_img is not None else one, m_txt if m_txt is not None else one)
     ext = (1.0 - full_mask[:, None, None, :].to(dtype)) * -10000.0
     h = emb
     for i in range(cfg["n_layers"]):
-        h = bert_layer(P, i, h, ext, cfg["n_head"])
+        h = bert_layer(P, i, h, ext, cfg["n_head"], dropout)
     pooled = torch.tanh(linear(h[:, 0], P["enc.pooler.dense.weight"], P["enc.pooler.dense.bias"]))
     return linear(pooled, P["clf.weight"], P["clf.bias"])
 
@@ -123,10 +153,10 @@ def cross_entropy(logits, y):
     return (lse - z.gather(1, y[:, None])[:, 0]).mean()
 
 
-def loss_and_grads(P, txt, mask, segment, img_tokens, y, cfg, indices=None):
+def loss_and_grads(P, txt, mask, segment, img_tokens, y, cfg, indices=None, dropout=None):
     P = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in P.items()}
     img_tokens = img_tokens.detach().clone().requires_grad_(True)
-    logits = forward(P, txt, mask, segment, img_tokens, cfg, indices)
+    logits = forward(P, txt, mask, segment, img_tokens, cfg, indices, dropout)
     loss = cross_entropy(logits, y)
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in P.items()

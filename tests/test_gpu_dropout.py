@@ -129,6 +129,113 @@ def test_flava_training_with_dropout_matches_oracle_under_the_same_masks(mmu, go
         assert rel(m(x).cpu(), c["logits_eval"]) < tl
 
 
+def _mmbt_args(cfg, precision, **kw):
+    import types
+    vocab = types.SimpleNamespace(stoi={"[CLS]": cfg["cls_id"], "[SEP]": cfg["sep_id"], "[PAD]": 0})
+    bc = dict(vocab=cfg["vocab"], D=cfg["D"], n_head=cfg["n_head"], n_layers=cfg["n_layers"], d_ff=cfg["d_ff"],
+              max_pos=cfg["max_pos"], n_types=cfg["n_types"], init_range=0.02)
+    bc.update(kw.pop("bert_config", {}))
+    return types.SimpleNamespace(bert_model="test", hidden_sz=cfg["D"], img_hidden_sz=cfg["d_img"],
+                                 num_image_embeds=cfg["n_img"], img_embed_pool_type="avg", dropout=kw.pop("dropout", 0.0),
+                                 n_classes=cfg["C"], vocab=vocab, precision=precision, img_encoder=None,
+                                 bert_config=bc, **kw)
+
+
+@pytest.mark.parametrize("precision,tl,tg", [("fp32", 1e-3, 1e-3), ("bf16", 1.6e-2, 6e-2)])
+@pytest.mark.parametrize("indices", [None, "control"])
+def test_mmbt_training_with_dropout_matches_oracle_under_the_same_masks(mmu, precision, tl, tg, indices, measured):
+    """MMBT in train() mode with the reference's dropouts switched on (BERT hidden 0.1, attention
+    probabilities 0.15, ImageBertEmbeddings 0.2 -- src/mmbt.py:56,82 and pytorch_pretrained_bert's
+    BertEmbeddings / BertSelfAttention / BertSelfOutput / BertOutput): forward + backward of the
+    engine (three-kernel attention path with the dropped-probability copy, masks regenerated in
+    the backward) against the oracle applying the same counter-based masks; ragged batch, S = 155
+    (> one attention tile), also through a ``forward_control``-style index list."""
+    from oracle import mmbt as O
+    cfg = dict(B=3, S_txt=150, n_img=3, d_img=64, D=128, n_head=2, n_layers=2, d_ff=256, vocab=300,
+               max_pos=160, n_types=2, C=2, cls_id=5, sep_id=6)
+    drop = dict(hidden=0.1, attn=0.15, img=0.2)
+    g = torch.Generator().manual_seed(5)
+    args = _mmbt_args(cfg, precision, dropout=drop["img"],
+                      bert_config=dict(hidden_dropout_prob=drop["hidden"], attention_probs_dropout_prob=drop["attn"]))
+    m = mmu.MultimodalBertClf(args)
+    assert (m.drop_hidden, m.drop_attn, m.drop_img) == pytest.approx((0.1, 0.15, 0.2))
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.08)
+    P = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    txt = torch.randint(7, cfg["vocab"], (3, 150), generator=g)
+    lens = torch.tensor([150, 97, 31])
+    mask = (torch.arange(150)[None] < lens[:, None]).long()
+    txt, segment = txt * mask, mask.clone()
+    tok = torch.randn(3, 3, 64, generator=g)
+    y = torch.tensor([0, 1, 1])
+    idx = None
+    if indices == "control":
+        idx = O.control_indices(155, 60, torch.Generator().manual_seed(9))
+    m.cuda().train()
+    m.zero_grad()
+    t = tok.cuda().requires_grad_(True)
+    torch.manual_seed(123)
+    if idx is None:
+        logits = m(txt.cuda(), mask.cuda(), segment.cuda(), t)
+    else:
+        logits = m.forward_indices(txt.cuda(), mask.cuda(), segment.cuda(), t, [int(i) for i in idx])
+    seed = m.last_dropout_seed
+    loss = m.compute_loss(logits, y.cuda())
+    loss.backward()
+    P64 = {k: (v.double() if v.is_floating_point() else v) for k, v in P.items()}
+    ref_logits, ref_loss, ref_grads, ref_dtok = O.loss_and_grads(
+        P64, txt, mask, segment, tok.double(), y, cfg, idx, dropout=dict(seed=seed, **drop))
+    plain_logits, _, _, _ = O.loss_and_grads(P64, txt, mask, segment, tok.double(), y, cfg, idx)
+    assert rel(ref_logits, plain_logits) > 1e-2                     # dropout changed the network
+    measured(f"mmbt_dropout/{precision}/logits", rel(logits.detach().cpu(), ref_logits))
+    measured(f"mmbt_dropout/{precision}/dimg", rel(t.grad.cpu(), ref_dtok))
+    assert rel(logits.detach().cpu(), ref_logits) < tl
+    assert abs(float(loss.detach()) - float(ref_loss)) < max(tl, 2e-3) * abs(float(ref_loss))
+    assert rel(t.grad.cpu(), ref_dtok) < tg
+    gmax = max(float(v.abs().max()) for v in ref_grads.values())
+    for k, prm in m.named_parameters():
+        if float(ref_grads[k].abs().max()) < 1e-5 * gmax:
+            continue
+        measured(f"mmbt_dropout/{precision}/grad", rel(prm.grad.cpu(), ref_grads[k]))
+        assert rel(prm.grad.cpu(), ref_grads[k]) < tg, (k, rel(prm.grad.cpu(), ref_grads[k]))
+    # reproducible under torch.manual_seed; eval mode = the dropout-free network
+    torch.manual_seed(123)
+    again = (m(txt.cuda(), mask.cuda(), segment.cuda(), tok.cuda()) if idx is None else
+             m.forward_indices(txt.cuda(), mask.cuda(), segment.cuda(), tok.cuda(), [int(i) for i in idx]))
+    assert m.last_dropout_seed == seed and torch.equal(again.detach(), logits.detach())
+    m.eval()
+    with torch.no_grad():
+        ev = (m(txt.cuda(), mask.cuda(), segment.cuda(), tok.cuda()) if idx is None else
+              m.forward_indices(txt.cuda(), mask.cuda(), segment.cuda(), tok.cuda(), [int(i) for i in idx]))
+    assert rel(ev.cpu(), plain_logits) < tl
+
+
+def test_mmbt_default_configuration_applies_the_reference_dropout(mmu):
+    """The reference's default MMBT set-up (bert-base config: hidden / attention dropout 0.1) must
+    not silently train the dropout-free network: defaults are 0.1, ``bert_dropout=0`` opts out."""
+    cfg = dict(B=2, S_txt=6, n_img=2, d_img=16, D=64, n_head=1, n_layers=1, d_ff=64, vocab=30, max_pos=16,
+               n_types=2, C=2, cls_id=1, sep_id=2)
+    m = mmu.MultimodalBertClf(_mmbt_args(cfg, "fp32"))
+    assert m.drop_hidden == pytest.approx(0.1) and m.drop_attn == pytest.approx(0.1) and m.drop_img == 0.0
+    m0 = mmu.MultimodalBertClf(_mmbt_args(cfg, "fp32", bert_dropout=0.0))
+    assert m0.drop_hidden == 0.0 and m0.drop_attn == 0.0
+    m0.load_state_dict(m.state_dict())
+    g = torch.Generator().manual_seed(2)
+    txt = torch.randint(3, 30, (2, 6), generator=g).cuda()
+    mask = torch.ones(2, 6, dtype=torch.long).cuda()
+    tok = torch.randn(2, 2, 16, generator=g).cuda()
+    m.cuda().train(); m0.cuda().train()
+    a, b = m(txt, mask, mask, tok).detach(), m0(txt, mask, mask, tok).detach()
+    assert not torch.equal(a, b) and torch.isfinite(a).all()
+    m.eval(); m0.eval()
+    with torch.no_grad():
+        assert torch.equal(m(txt, mask, mask, tok), m0(txt, mask, mask, tok))
+
+
 def test_cls_variant_default_dropout_trains(mmu):
     """FlavaFusionTransfomerwithCLSToken defaults to drop = 0.1 (reference src/model.py:306-318):
     the default-constructed model must train."""

@@ -38,7 +38,7 @@ def make_args(cfg, precision):
     return types.SimpleNamespace(
         bert_model="golden", hidden_sz=cfg["D"], img_hidden_sz=cfg["d_img"], num_image_embeds=cfg["n_img"],
         img_embed_pool_type="avg", dropout=0.0, n_classes=cfg["C"], vocab=vocab, precision=precision,
-        img_encoder=None,
+        img_encoder=None, bert_dropout=0.0,   # the goldens are the dropout-free network
         bert_config=dict(vocab=cfg["vocab"], D=cfg["D"], n_head=cfg["n_head"], n_layers=cfg["n_layers"],
                          d_ff=cfg["d_ff"], max_pos=cfg["max_pos"], n_types=cfg["n_types"], init_range=0.02))
 
@@ -408,10 +408,10 @@ def test_full_baseline_size_properties(mmu):
         opt.step()
         losses.append(float(loss.detach()))
     assert all(l == l for l in losses) and min(losses[4:]) < losses[0], losses
-    with pytest.raises(mmu._lib.MMUError):
-        args.dropout = 0.1
-        m(*x)
-    args.dropout = 0.0
+    # the training steps above ran with the reference's default BERT dropouts (bert-base config:
+    # hidden / attention probabilities 0.1), i.e. through the three-kernel attention path
+    assert m.drop_hidden == pytest.approx(0.1) and m.drop_attn == pytest.approx(0.1)
+    assert m.last_dropout_seed is not None
 
 
 def test_trainer_runs_the_mmbt_branch_on_the_engine(mmu, golden, tmp_path):

@@ -38,7 +38,7 @@ def test_struct_sizes_match_header(mmu):
                                    mmu._lib.MetricAccum, mmu._lib.ParamEntry,
                                    mmu._lib.PosthocAccum)):
         assert mmu._lib.lib.mmu_struct_size(which) == C.sizeof(klass), klass.__name__
-    assert mmu._lib.lib.mmu_struct_size(6) == C.sizeof(mmu._lib.MmbtConfig) == 16 * 4
+    assert mmu._lib.lib.mmu_struct_size(6) == C.sizeof(mmu._lib.MmbtConfig) == 20 * 4
     assert mmu._lib.lib.mmu_struct_size(7) == C.sizeof(mmu._lib.MmbtInputs)
     assert C.sizeof(mmu._lib.ParamEntry) == 96 + 8 + 8 + 12 + 4  # padded to 8
     assert mmu._lib.ACC_OFF["conf_sum"] == 98

@@ -18,6 +18,7 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--precision", default="bf16")
 ap.add_argument("--images", action="store_true")
 ap.add_argument("--no-cpu", action="store_true")
+ap.add_argument("--bert-dropout", type=float, default=0.0, help="BERT hidden / attention dropout (reference config: 0.1)")
 a = ap.parse_args()
 # one process per GPU under torchrun (weak scaling: `--batch` samples per rank, no data-path
 # collective but the gradient all-reduce inside optimizer.step())
@@ -32,7 +33,8 @@ B, S_txt, n_img, C = a.batch, a.s_txt, 3, 2
 vocab = types.SimpleNamespace(stoi={"[CLS]": 101, "[SEP]": 102, "[PAD]": 0})
 args = types.SimpleNamespace(bert_model="bert-base-uncased", hidden_sz=768, img_hidden_sz=2048,
                              num_image_embeds=n_img, img_embed_pool_type="avg", dropout=0.0, n_classes=C,
-                             vocab=vocab, precision=a.precision, img_encoder="native" if a.images else None)
+                             vocab=vocab, precision=a.precision, img_encoder="native" if a.images else None,
+                             bert_dropout=a.bert_dropout)
 torch.manual_seed(42)
 m = mmu.MultimodalBertClf(args).to(dev).train()
 named = list(m.named_parameters())
