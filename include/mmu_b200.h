@@ -108,10 +108,12 @@ MMU_API int mmu_gemm(int dtype, const void* A, long long lda, int a_mn_major, co
  * Input staging: token-subset gather + per-sample modality zero-fill + cast.
  * Replaces the fancy indexing `img[:, indices_img, :]` of eval_transformer_robustness.py:118-119,
  * the zero-fill masking of eval_robustness.py:92-97 and the H2D-side dtype handling.
- * src fp32 (B, l_src, d) -> dst (B, n_sel, d).  idx: int32[n_sel] or NULL (identity);
- * keep: int32[B,2] or NULL; `modality` (0 image, 1 text) selects the keep column. */
+ * src fp32 (B, l_src, d) -> dst (B, n_sel, d), or (n_sel, B, d) when pos_major != 0 (the engine's
+ * position-major row order).  idx: int32[n_sel] or NULL (identity); keep: int32[B,2] or NULL;
+ * `modality` (0 image, 1 text) selects the keep column. */
 MMU_API int mmu_mask_gather_tokens(const float* src, void* dst, int dst_dtype, int B, int l_src, int d,
-                           const int* idx, int n_sel, const int* keep, int modality, void* stream);
+                           const int* idx, int n_sel, const int* keep, int modality, int pos_major,
+                           void* stream);
 
 /* Guided / random modality dropout (BASELINE.json configs[1]; the reference only NAMES it --
  * configs/training_guided.gin:10-18 -- so the definition is this repo's, oracle/shaping.py
@@ -148,7 +150,10 @@ MMU_API int mmu_layernorm_bwd(const void* dy, int dy_dtype, const float* x, cons
 
 /* Batch-axis multi-head attention (src/model.py:193,205-207: nn.MultiheadAttention with
  * batch_first=False fed (B, L, D), i.e. attention across the mini-batch, per token position).
- * qkv: [B*L, 3D] packed q|k|v; out: [B*L, D].
+ * qkv: [B*L, 3D] packed q|k|v; out: [B*L, D].  pos_major = 0: row of (sample b, position l) is
+ * b*L + l (the reference's (B, L, .) tensors); pos_major = 1: l*B + b -- the engine's layout: the B
+ * rows of one (position, head) problem are adjacent instead of L*3D elements apart, which is what
+ * lets these HBM-bound kernels stream (profiles/r02_attention_layout.md).
  * Tensor-core path (dtype MMU_BF16, head_dim % 64 == 0, probs/scores non-NULL): batched tcgen05
  * GEMMs over the L*H (position, head) problems; probs: bf16 [L*H, B, Bp] written by the forward and
  * read by the backward, scores: fp32 scratch, dprobs: bf16 scratch of the same shape (Bp = B
@@ -156,11 +161,11 @@ MMU_API int mmu_layernorm_bwd(const void* dy, int dy_dtype, const float* x, cons
  * lse fp32[L*H*B] (forward output) and delta_ws fp32[L*H*B]. */
 MMU_API int mmu_batchaxis_attention_fwd(const void* qkv, void* out, float* lse, void* probs,
                                         float* scores, int dtype, int B, int L, int D, int H,
-                                        void* stream);
+                                        int pos_major, void* stream);
 MMU_API int mmu_batchaxis_attention_bwd(const void* qkv, const void* out, const void* dout,
                                         const float* lse, float* delta_ws, const void* probs,
                                         float* scores, void* dprobs, void* dqkv, int dtype, int B,
-                                        int L, int D, int H, void* stream);
+                                        int L, int D, int H, int pos_major, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused softmax / cross-entropy (+gradient) / accuracy / uncertainty / calibration epilogue.

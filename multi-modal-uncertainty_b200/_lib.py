@@ -121,7 +121,7 @@ def _load():
     lib.mmu_error_string.argtypes = [i]
     lib.mmu_launch_count.restype = ll
     lib.mmu_gemm.argtypes = [i, vp, ll, i, vp, ll, i, i, i, i, i, C.POINTER(GemmEpilogue), vp]
-    lib.mmu_mask_gather_tokens.argtypes = [vp, vp, i, i, i, i, vp, i, vp, i, vp]
+    lib.mmu_mask_gather_tokens.argtypes = [vp, vp, i, i, i, i, vp, i, vp, i, i, vp]
     lib.mmu_struct_size.argtypes = [i]
     lib.mmu_set_gemm_sm_limit.argtypes = [i]
     rcfgp = C.POINTER(ResNetConfig)
@@ -141,8 +141,8 @@ def _load():
     lib.mmu_cast_f32_to_bf16.argtypes = [vp, vp, C.c_size_t, vp]
     lib.mmu_layernorm_fwd.argtypes = [vp, vp, vp, vp, i, vp, vp, i, i, vp]
     lib.mmu_layernorm_bwd.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, i, vp, vp, vp, i, i, vp]
-    lib.mmu_batchaxis_attention_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, vp]
-    lib.mmu_batchaxis_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]
+    lib.mmu_batchaxis_attention_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    lib.mmu_batchaxis_attention_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp]
     lib.mmu_heads_uncertainty_epilogue.argtypes = [vp, vp, i, i, i, i, i, i, f, vp, vp, vp, vp, vp]
     lib.mmu_adamw_flat_step.argtypes = [vp, vp, vp, vp, vp, C.c_size_t, f, f, f, f, f, i, f, vp]
     cfgp = C.POINTER(FlavaConfig)

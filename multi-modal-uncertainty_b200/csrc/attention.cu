@@ -224,11 +224,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
-attn_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, float* __restrict__ lse, int B, int L,
-                int D, int H) {
+attn_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, float* __restrict__ lse, int B, int L_,
+                int D, int H, int pos_major) {
   extern __shared__ __align__(16) float smem_f[];
   const Smem s = carve(smem_f, B);
-  const int lh = blockIdx.x, l = lh / H, h = lh % H;
+  // row of (sample b, position lp): b*L + lp (batch-major) or lp*B + b (position-major) -- both are
+  // b*L + l with (L, l) = (L_, lp) resp. (1, lp*B)
+  const int lh = blockIdx.x, lp = lh / H, h = lh % H;
+  const int L = pos_major ? 1 : L_, l = pos_major ? lp * B : lp;
   const int hd = D / H;
   const int t0 = blockIdx.y * TQ;
   const int rows = min(TQ, B - t0);
@@ -265,10 +268,11 @@ template <typename T>
 __global__ void __launch_bounds__(THREADS)
 attn_bwd_dq_kernel(const T* __restrict__ qkv, const T* __restrict__ out, const T* __restrict__ dout,
                    const float* __restrict__ lse, float* __restrict__ delta, T* __restrict__ dqkv,
-                   int B, int L, int D, int H) {
+                   int B, int L_, int D, int H, int pos_major) {
   extern __shared__ __align__(16) float smem_f[];
   const Smem s = carve(smem_f, B);
-  const int lh = blockIdx.x, l = lh / H, h = lh % H;
+  const int lh = blockIdx.x, lp = lh / H, h = lh % H;
+  const int L = pos_major ? 1 : L_, l = pos_major ? lp * B : lp;
   const int hd = D / H;
   const int t0 = blockIdx.y * TQ;
   const int rows = min(TQ, B - t0);
@@ -310,10 +314,11 @@ template <typename T>
 __global__ void __launch_bounds__(THREADS)
 attn_bwd_dkv_kernel(const T* __restrict__ qkv, const T* __restrict__ dout,
                     const float* __restrict__ lse, const float* __restrict__ delta,
-                    T* __restrict__ dqkv, int B, int L, int D, int H) {
+                    T* __restrict__ dqkv, int B, int L_, int D, int H, int pos_major) {
   extern __shared__ __align__(16) float smem_f[];
   const Smem s = carve(smem_f, B);
-  const int lh = blockIdx.x, l = lh / H, h = lh % H;
+  const int lh = blockIdx.x, lp = lh / H, h = lh % H;
+  const int L = pos_major ? 1 : L_, l = pos_major ? lp * B : lp;
   const int hd = D / H;
   const int t0 = blockIdx.y * TQ;  // key tile
   const int rows = min(TQ, B - t0);
@@ -427,19 +432,21 @@ struct Views {
   BatchedOperand q_mn, k_mn, v_mn;  // MN-major views (MN = d, K = b)
 };
 
-BatchedOperand qkv_view(const void* qkv, int B, int L, int D, int H, int third, int mn) {
+// pos: rows are (position, sample) -> l*B + b instead of (sample, position) -> b*L + l
+BatchedOperand qkv_view(const void* qkv, int B, int L, int D, int H, int third, int mn, int pos) {
   BatchedOperand o{};
   o.base = qkv;
   o.inner = 3LL * D; o.mid = L; o.outer = B;
-  o.mid_stride = 3LL * D; o.outer_stride = 3LL * D * L;
+  o.mid_stride = pos ? 3LL * D * B : 3LL * D; o.outer_stride = pos ? 3LL * D : 3LL * D * L;
   o.mn_major = mn; o.hdiv = H; o.hstride = D / H; o.col0 = third * D;
   return o;
 }
-BatchedOperand act_view(const void* x, int B, int L, int D, int H, int mn) {  // (B, L, D) tensors
+BatchedOperand act_view(const void* x, int B, int L, int D, int H, int mn, int pos) {  // [rows, D] tensors
   BatchedOperand o{};
   o.base = x;
   o.inner = D; o.mid = L; o.outer = B;
-  o.mid_stride = D; o.outer_stride = static_cast<long long>(D) * L;
+  o.mid_stride = pos ? static_cast<long long>(D) * B : D;
+  o.outer_stride = pos ? D : static_cast<long long>(D) * L;
   o.mn_major = mn; o.hdiv = H; o.hstride = D / H; o.col0 = 0;
   return o;
 }
@@ -463,7 +470,7 @@ bool eligible(int dtype, int B, int D, int H, const void* probs, const void* sco
          D % 8 == 0 && B >= 1;
 }
 
-int fwd(const void* qkv, void* out, void* probs, float* scores, int B, int L, int D, int H,
+int fwd(const void* qkv, void* out, void* probs, float* scores, int B, int L, int D, int H, int pos,
         cudaStream_t st) {
   const int hd = D / H, G = L * H, Bp = (B + 7) / 8 * 8;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
@@ -473,15 +480,15 @@ int fwd(const void* qkv, void* out, void* probs, float* scores, int B, int L, in
     GemmEpilogue e = store_epi(probs, 1, Bp, scale);
     e.mode = EPI_SOFTMAX;
     e.n_valid = B;
-    const int rc0 = gemm_bf16_batched_launch(qkv_view(qkv, B, L, D, H, 0, 0),
-                                             qkv_view(qkv, B, L, D, H, 1, 0), G, B, Bp, hd, e, 1, 0,
+    const int rc0 = gemm_bf16_batched_launch(qkv_view(qkv, B, L, D, H, 0, 0, pos),
+                                             qkv_view(qkv, B, L, D, H, 1, 0, pos), G, B, Bp, hd, e, 1, 0,
                                              static_cast<long long>(B) * Bp, st);
     if (rc0) return rc0;
-    return gemm_bf16_batched_launch(sq_view(probs, G, B, Bp, 0), qkv_view(qkv, B, L, D, H, 2, 1), G, B,
-                                    hd, B, store_epi(out, 1, static_cast<long long>(L) * D, 1.0f), H,
-                                    hd, D, st);
+    return gemm_bf16_batched_launch(sq_view(probs, G, B, Bp, 0), qkv_view(qkv, B, L, D, H, 2, 1, pos), G, B,
+                                    hd, B, store_epi(out, 1, pos ? D : static_cast<long long>(L) * D, 1.0f), H,
+                                    hd, pos ? static_cast<long long>(B) * D : D, st);
   }
-  int rc = gemm_bf16_batched_launch(qkv_view(qkv, B, L, D, H, 0, 0), qkv_view(qkv, B, L, D, H, 1, 0),
+  int rc = gemm_bf16_batched_launch(qkv_view(qkv, B, L, D, H, 0, 0, pos), qkv_view(qkv, B, L, D, H, 1, 0, pos),
                                     G, B, Bp, hd, store_epi(scores, 0, Bp, scale), 1, 0,
                                     static_cast<long long>(B) * Bp, st);
   if (rc) return rc;
@@ -490,17 +497,17 @@ int fwd(const void* qkv, void* out, void* probs, float* scores, int B, int L, in
                                                       rows, B, Bp);
   if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
   count_launch();
-  return gemm_bf16_batched_launch(sq_view(probs, G, B, Bp, 0), qkv_view(qkv, B, L, D, H, 2, 1), G, B,
-                                  hd, B, store_epi(out, 1, static_cast<long long>(L) * D, 1.0f), H,
-                                  hd, D, st);
+  return gemm_bf16_batched_launch(sq_view(probs, G, B, Bp, 0), qkv_view(qkv, B, L, D, H, 2, 1, pos), G, B,
+                                  hd, B, store_epi(out, 1, pos ? D : static_cast<long long>(L) * D, 1.0f), H,
+                                  hd, pos ? static_cast<long long>(B) * D : D, st);
 }
 
 int bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
-        void* dqkv, int B, int L, int D, int H, cudaStream_t st) {
+        void* dqkv, int B, int L, int D, int H, int pos, cudaStream_t st) {
   const int hd = D / H, G = L * H, Bp = (B + 7) / 8 * 8;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   // dP = dO V^T
-  int rc = gemm_bf16_batched_launch(act_view(dout, B, L, D, H, 0), qkv_view(qkv, B, L, D, H, 2, 0),
+  int rc = gemm_bf16_batched_launch(act_view(dout, B, L, D, H, 0, pos), qkv_view(qkv, B, L, D, H, 2, 0, pos),
                                     G, B, Bp, hd, store_epi(scores, 0, Bp, 1.0f), 1, 0,
                                     static_cast<long long>(B) * Bp, st);
   if (rc) return rc;
@@ -511,18 +518,19 @@ int bwd(const void* qkv, const void* dout, const void* probs, float* scores, voi
   if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
   count_launch();
   __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(dqkv);
-  const long long ld = 3LL * D * L;
+  const long long ld = pos ? 3LL * D : 3LL * D * L;          // row (sample) pitch of dqkv
+  const long long lmid = pos ? 3LL * D * B : 3LL * D;        // position pitch
   // dV = P^T dO
-  rc = gemm_bf16_batched_launch(sq_view(probs, G, B, Bp, 1), act_view(dout, B, L, D, H, 1), G, B, hd,
-                                B, store_epi(dq + 2 * D, 1, ld, 1.0f), H, hd, 3LL * D, st);
+  rc = gemm_bf16_batched_launch(sq_view(probs, G, B, Bp, 1), act_view(dout, B, L, D, H, 1, pos), G, B, hd,
+                                B, store_epi(dq + 2 * D, 1, ld, 1.0f), H, hd, lmid, st);
   if (rc) return rc;
   // dK = dS^T Q
-  rc = gemm_bf16_batched_launch(sq_view(dprobs, G, B, Bp, 1), qkv_view(qkv, B, L, D, H, 0, 1), G, B,
-                                hd, B, store_epi(dq + D, 1, ld, 1.0f), H, hd, 3LL * D, st);
+  rc = gemm_bf16_batched_launch(sq_view(dprobs, G, B, Bp, 1), qkv_view(qkv, B, L, D, H, 0, 1, pos), G, B,
+                                hd, B, store_epi(dq + D, 1, ld, 1.0f), H, hd, lmid, st);
   if (rc) return rc;
   // dQ = dS K
-  return gemm_bf16_batched_launch(sq_view(dprobs, G, B, Bp, 0), qkv_view(qkv, B, L, D, H, 1, 1), G, B,
-                                  hd, B, store_epi(dq, 1, ld, 1.0f), H, hd, 3LL * D, st);
+  return gemm_bf16_batched_launch(sq_view(dprobs, G, B, Bp, 0), qkv_view(qkv, B, L, D, H, 1, 1, pos), G, B,
+                                  hd, B, store_epi(dq, 1, ld, 1.0f), H, hd, lmid, st);
 }
 
 
@@ -832,10 +840,10 @@ int seq_attention_bwd(const void* qkv, const void* dout, const void* probs, floa
 }
 
 int attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* scores, int dtype,
-                  int B, int L, int D, int H, cudaStream_t stream) {
+                  int B, int L, int D, int H, cudaStream_t stream, int pos_major) {
   using namespace attn;
   if (tc::eligible(dtype, B, D, H, probs, scores))
-    return tc::fwd(qkv, out, probs, scores, B, L, D, H, stream);
+    return tc::fwd(qkv, out, probs, scores, B, L, D, H, pos_major, stream);
   if (lse == nullptr) return MMU_ERR_ARG;
   if (int rc = check(B, D, H)) return rc;
   const size_t smem = smem_bytes(B);
@@ -843,11 +851,11 @@ int attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* sc
   if (dtype == DT_BF16) {
     if (set_smem(attn_fwd_kernel<__nv_bfloat16>, smem)) return MMU_ERR_CUDA;
     attn_fwd_kernel<__nv_bfloat16><<<grid, THREADS, smem, stream>>>(
-        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, B, L, D, H);
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, B, L, D, H, pos_major);
   } else {
     if (set_smem(attn_fwd_kernel<float>, smem)) return MMU_ERR_CUDA;
     attn_fwd_kernel<float><<<grid, THREADS, smem, stream>>>(static_cast<const float*>(qkv),
-                                                            static_cast<float*>(out), lse, B, L, D, H);
+                                                            static_cast<float*>(out), lse, B, L, D, H, pos_major);
   }
   if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
   count_launch();
@@ -856,10 +864,10 @@ int attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* sc
 
 int attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                   float* delta_ws, const void* probs, float* scores, void* dprobs, void* dqkv,
-                  int dtype, int B, int L, int D, int H, cudaStream_t stream) {
+                  int dtype, int B, int L, int D, int H, cudaStream_t stream, int pos_major) {
   using namespace attn;
   if (tc::eligible(dtype, B, D, H, probs, scores) && dprobs != nullptr)
-    return tc::bwd(qkv, dout, probs, scores, dprobs, dqkv, B, L, D, H, stream);
+    return tc::bwd(qkv, dout, probs, scores, dprobs, dqkv, B, L, D, H, pos_major, stream);
   if (lse == nullptr || delta_ws == nullptr) return MMU_ERR_ARG;
   if (int rc = check(B, D, H)) return rc;
   const size_t smem = smem_bytes(B);
@@ -870,20 +878,20 @@ int attention_bwd(const void* qkv, const void* out, const void* dout, const floa
       return MMU_ERR_CUDA;
     attn_bwd_dq_kernel<T><<<grid, THREADS, smem, stream>>>(
         static_cast<const T*>(qkv), static_cast<const T*>(out), static_cast<const T*>(dout), lse,
-        delta_ws, static_cast<T*>(dqkv), B, L, D, H);
+        delta_ws, static_cast<T*>(dqkv), B, L, D, H, pos_major);
     attn_bwd_dkv_kernel<T><<<grid, THREADS, smem, stream>>>(
         static_cast<const T*>(qkv), static_cast<const T*>(dout), lse, delta_ws,
-        static_cast<T*>(dqkv), B, L, D, H);
+        static_cast<T*>(dqkv), B, L, D, H, pos_major);
   } else {
     using T = float;
     if (set_smem(attn_bwd_dq_kernel<T>, smem) || set_smem(attn_bwd_dkv_kernel<T>, smem))
       return MMU_ERR_CUDA;
     attn_bwd_dq_kernel<T><<<grid, THREADS, smem, stream>>>(
         static_cast<const T*>(qkv), static_cast<const T*>(out), static_cast<const T*>(dout), lse,
-        delta_ws, static_cast<T*>(dqkv), B, L, D, H);
+        delta_ws, static_cast<T*>(dqkv), B, L, D, H, pos_major);
     attn_bwd_dkv_kernel<T><<<grid, THREADS, smem, stream>>>(
         static_cast<const T*>(qkv), static_cast<const T*>(dout), lse, delta_ws,
-        static_cast<T*>(dqkv), B, L, D, H);
+        static_cast<T*>(dqkv), B, L, D, H, pos_major);
   }
   if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
   count_launch(2);

@@ -105,9 +105,10 @@ int mmu_gemm(int dtype, const void* A, long long lda, int a_mn_major, const void
 }
 
 int mmu_mask_gather_tokens(const float* src, void* dst, int dst_dtype, int B, int l_src, int d,
-                           const int* idx, int n_sel, const int* keep, int modality, void* stream) {
+                           const int* idx, int n_sel, const int* keep, int modality, int pos_major,
+                           void* stream) {
   if (src == nullptr || dst == nullptr) return MMU_ERR_ARG;
-  return cast_gather(src, dst, dst_dtype, B, l_src, d, idx, n_sel, keep, modality, S(stream));
+  return cast_gather(src, dst, dst_dtype, B, l_src, d, idx, n_sel, keep, modality, S(stream), pos_major != 0);
 }
 
 int mmu_modality_keep_mask(const float* u, const float* r, const float* score_img,
@@ -145,18 +146,18 @@ int mmu_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float*
 }
 
 int mmu_batchaxis_attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* scores,
-                                int dtype, int B, int L, int D, int H, void* stream) {
+                                int dtype, int B, int L, int D, int H, int pos_major, void* stream) {
   if (qkv == nullptr || out == nullptr) return MMU_ERR_ARG;
-  return attention_fwd(qkv, out, lse, probs, scores, dtype, B, L, D, H, S(stream));
+  return attention_fwd(qkv, out, lse, probs, scores, dtype, B, L, D, H, S(stream), pos_major != 0);
 }
 
 int mmu_batchaxis_attention_bwd(const void* qkv, const void* out, const void* dout,
                                 const float* lse, float* delta_ws, const void* probs, float* scores,
                                 void* dprobs, void* dqkv, int dtype, int B, int L, int D, int H,
-                                void* stream) {
+                                int pos_major, void* stream) {
   if (qkv == nullptr || out == nullptr || dout == nullptr || dqkv == nullptr) return MMU_ERR_ARG;
   return attention_bwd(qkv, out, dout, lse, delta_ws, probs, scores, dprobs, dqkv, dtype, B, L, D,
-                       H, S(stream));
+                       H, S(stream), pos_major != 0);
 }
 
 int mmu_heads_uncertainty_epilogue(const float* logits, const long long* labels, int label_stride,

@@ -1,6 +1,7 @@
 // FLAVA-fusion engine implementation.  See engine.h.
 //
-// Data layout in HBM (all row-major, row r = b*L + l of the (B, L, .) activation tensors):
+// Data layout in HBM (all row-major; POSITION-major rows: row r = l*B + b holds token position l
+// of sample b, so the B rows one batch-axis attention problem reads are adjacent):
 //   residual stream x          fp32 [B*L, D]      (kept in fp32 in both precisions)
 //   GEMM operands / outputs    fp32 or bf16       (h = LN(x), qkv, attention out, z, u, grads)
 //   parameters / gradients     one flat fp32 buffer each (+ bf16 shadow of the parameters)
@@ -393,18 +394,22 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
   auto Wstem = [&](long long off) -> const void* {
     return stem32 ? static_cast<const void*>(params + off) : W(off);
   };
+  // Rows are POSITION-major from here on: row (l, b) = l*B + b.  The concatenation [CLS | image |
+  // text] along the token axis (torch.cat, src/model.py:273) is then a concatenation of contiguous
+  // row blocks, and the B rows of one token position -- the operands of its batch-axis attention
+  // problems -- are adjacent in memory.
   if (s.n_img > 0) {
     MMU_TRY(cast_gather(in.img, w.img_t, dt_stem, c.B, src_l_img, c.d_img, in.idx_img, s.n_img,
-                        in.keep, 0, stream));
-    GemmEpilogue e = epi(EPI_STORE, w.mm_x, 0, D, params + lay.img_b);
-    e.seg_len = s.n_img; e.seg_stride = s.L; e.seg_off = s.n_cls;
+                        in.keep, 0, stream, 1));
+    GemmEpilogue e = epi(EPI_STORE, w.mm_x + static_cast<long long>(s.n_cls) * c.B * D, 0, D,
+                         params + lay.img_b);
     MMU_TRY(gemm_stem(w.img_t, c.d_img, 0, Wstem(lay.img_w), c.d_img, 0, c.B * s.n_img, D, c.d_img, e));
   }
   if (s.n_txt > 0) {
     MMU_TRY(cast_gather(in.txt, w.txt_t, dt_stem, c.B, src_l_txt, c.d_txt, in.idx_txt, s.n_txt,
-                        in.keep, 1, stream));
-    GemmEpilogue e = epi(EPI_STORE, w.mm_x, 0, D, params + lay.txt_b);
-    e.seg_len = s.n_txt; e.seg_stride = s.L; e.seg_off = s.n_cls + s.n_img;
+                        in.keep, 1, stream, 1));
+    GemmEpilogue e = epi(EPI_STORE, w.mm_x + static_cast<long long>(s.n_cls + s.n_img) * c.B * D, 0, D,
+                         params + lay.txt_b);
     MMU_TRY(gemm_stem(w.txt_t, c.d_txt, 0, Wstem(lay.txt_w), c.d_txt, 0, c.B * s.n_txt, D, c.d_txt, e));
   }
   if (c.cls_token) MMU_TRY(cls_fill(params + lay.cls, w.mm_x, c.B, s.L, D, c.E, stream));
@@ -434,7 +439,7 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
     // closing add+LN
     MMU_TRY(gemm(l.h1, D, 0, W(p.in_w), D, 0, M, 3 * D, D,
                  epi(EPI_STORE, l.qkv, bf, 3 * D, params + p.in_b)));
-    MMU_TRY(attention_fwd(l.qkv, l.o, l.lse, l.probs, w.scores, dt, c.B, s.L, D, c.n_head, stream));
+    MMU_TRY(attention_fwd(l.qkv, l.o, l.lse, l.probs, w.scores, dt, c.B, s.L, D, c.n_head, stream, 1));
     MMU_TRY(gemm(l.o, D, 0, W(p.out_w), D, 0, M, D, D, epi(EPI_STORE, w.ybuf, bf, D, params + p.out_b)));
     MMU_TRY(add_layernorm_fwd(x, w.ybuf, l.x1, params + p.ln2_w, params + p.ln2_b, l.h2, dt, l.stats2,
                               l.stats2 + M, M, D, stream));
@@ -559,7 +564,7 @@ int flava_backward(const FlavaConfig& c, const float* params, const FlavaInputs&
       MMU_TRY(gemm(w.dx_lp, D, 0, W(p.out_w), D, 1, M, D, D, epi(EPI_STORE, w.dh, bf, D, nullptr)));
       // attention backward: dqkv
       MMU_TRY(attention_bwd(l.qkv, l.o, w.dh, l.lse, w.delta, l.probs, w.scores, w.dprobs, w.dbig,
-                            dt, c.B, s.L, D, c.n_head, stream));
+                            dt, c.B, s.L, D, c.n_head, stream, 1));
       // dWin[3D, D] += dqkv^T h1 ; dbin += colsum(dqkv) ; dh1 = dqkv Win
       MMU_TRY(gemm(w.dbig, 3 * D, 1, l.h1, D, 1, 3 * D, D, M,
                    epi(EPI_ATOMIC, grads + p.in_w, 0, D, nullptr), wgrad_splits(3 * D, D, M)));

@@ -15,8 +15,9 @@ enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
 // ---- input staging: token-subset gather + per-sample modality zero-fill + cast
 // src fp32 [B, l_src, d] -> dst (dtype) [B, n_sel, d].  idx (device int32[n_sel]) may be null
 // (identity).  keep (device int32[B, 2]) may be null; modality selects its column.
+// pos_major: destination rows ordered (token position, sample) instead of (sample, position).
 int cast_gather(const float* src, void* dst, int dst_dtype, int B, int l_src, int d, const int* idx,
-                int n_sel, const int* keep, int modality, cudaStream_t stream);
+                int n_sel, const int* keep, int modality, cudaStream_t stream, int pos_major = 0);
 int cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t stream);
 // guided / random modality-dropout keep mask int32[B,2] from host-drawn uniforms u, r (fp32[B]) and,
 // for mode 1 (guided), device-resident per-sample scores (element b at score_*[b*score_stride])
@@ -69,7 +70,8 @@ int postln_bwd(const void* dy_branch, const float* dy_res, int dtype, const floa
                float* dbeta, float* dcolsum, int M, int D, cudaStream_t stream,
                PostLnDropout dr = PostLnDropout{});
 
-// ---- heads: LayerNorm(ln_post) + row gather / segment mean pooling + E small Linears
+// ---- heads: LayerNorm(ln_post) + row gather / segment mean pooling + E small Linears.  x rows are
+// position-major: row (l, b) = l*B + b (the engine's layout).
 struct HeadSegments {
   int E;
   int seg_begin[16];
@@ -98,7 +100,8 @@ int heads_bwd(const float* dlogits, const float* vec, const HeadParams& hp, floa
 int cls_fill(const float* class_emb /*(D,E)*/, float* mm_x, int B, int L, int D, int E,
              cudaStream_t stream);
 int cls_bwd(const float* dmm, float* dclass_emb, int B, int L, int D, int E, cudaStream_t stream);
-// split the (B, L, D) gradient of the concatenated sequence into per-modality compact buffers
+// split the gradient of the concatenated sequence (position-major rows (l, b)) into per-modality
+// compact buffers (rows (l, b) as well)
 int split_rows(const float* dmm, void* dimg, void* dtxt, int dtype, int B, int L, int off_img,
                int l_img, int l_txt, int D, cudaStream_t stream);
 
@@ -108,11 +111,14 @@ int split_rows(const float* dmm, void* dimg, void* dtxt, int dtype, int B, int L
 // (batched tcgen05 GEMMs): probs bf16 [L*H, B, Bp] (kept for the backward), scores fp32 and dprobs
 // bf16 scratch of the same shape, Bp = B rounded up to 8.  Otherwise the fp32 SIMT kernels run
 // (B <= 256) and need lse / delta_ws.
+// pos_major = 0: rows of qkv / out are (sample b, position l) -> b*L + l; 1: (position, sample) ->
+// l*B + b, the engine's layout: the 128 rows of one (position, head) problem are then ADJACENT in
+// memory (a contiguous B x 3D block per position) instead of L*3D elements apart.
 int attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* scores, int dtype,
-                  int B, int L, int D, int H, cudaStream_t stream);
+                  int B, int L, int D, int H, cudaStream_t stream, int pos_major = 0);
 int attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                   float* delta_ws, const void* probs, float* scores, void* dprobs, void* dqkv,
-                  int dtype, int B, int L, int D, int H, cudaStream_t stream);
+                  int dtype, int B, int L, int D, int H, cudaStream_t stream, int pos_major = 0);
 
 // ---- sequence-axis attention (BERT encoder of the MMBT path; reference call site
 // src/mmbt.py:124-128 with the additive mask of :103-107).  qkv (dtype) [B*S, 3D] packed q|k|v,

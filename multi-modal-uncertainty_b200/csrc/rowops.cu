@@ -75,16 +75,16 @@ int grid_for(size_t work_items, int per_block) {
 template <typename T>
 __global__ void cast_gather_kernel(const float* __restrict__ src, T* __restrict__ dst, int B,
                                    int l_src, int d, const int* __restrict__ idx, int n_sel,
-                                   const int* __restrict__ keep, int modality) {
+                                   const int* __restrict__ keep, int modality, int pos_major) {
   ptx::pdl_trigger();  // a following tensor-core GEMM may start its prologue early
   const int dv = d >> 2;
   const size_t total = static_cast<size_t>(B) * n_sel * dv;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % dv);
-    const size_t row = i / dv;
-    const int j = static_cast<int>(row % n_sel);
-    const int b = static_cast<int>(row / n_sel);
+    const size_t row = i / dv;  // destination row: (b, j) batch-major, (j, b) position-major
+    const int j = static_cast<int>(pos_major ? row / B : row % n_sel);
+    const int b = static_cast<int>(pos_major ? row % B : row / n_sel);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (keep == nullptr || keep[b * 2 + modality] != 0) {
       const int l = idx != nullptr ? idx[j] : j;
@@ -605,7 +605,7 @@ pool_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   float4 acc[NV];
   zero_acc<NV>(acc);
   for (int l = s0 + warp; l < s1; l += WARPS) {
-    const size_t row = static_cast<size_t>(b) * L + l;
+    const size_t row = static_cast<size_t>(l) * gridDim.x + b;   // position-major rows (l, b)
     RowRegs<NV> r;
     r.load(x + row * D, nvec, lane);
     float mean, rstd;
@@ -658,7 +658,7 @@ pool_ln_fwd_variants_kernel(const float* __restrict__ x, const float* __restrict
   float4 acc[NV];
   zero_acc<NV>(acc);
   for (int l = s0 + warp; l < s1; l += WARPS) {
-    const size_t row = static_cast<size_t>(b) * L + l;
+    const size_t row = static_cast<size_t>(l) * gridDim.x + b;   // position-major rows (l, b)
     RowRegs<NV> r;
     r.load(x + row * D, nvec, lane);
     float mean, rstd;
@@ -725,7 +725,7 @@ pool_ln_bwd_kernel(const float* __restrict__ dvec, const float* __restrict__ x,
   }
   s1sum = warp_sum(s1sum) / D;
   for (int l = s0 + warp; l < s1; l += WARPS) {
-    const size_t row = static_cast<size_t>(b) * L + l;
+    const size_t row = static_cast<size_t>(l) * gridDim.x + b;   // position-major rows (l, b)
     RowRegs<NV> rx;
     rx.load(x + row * D, nvec, lane);
     const float mu = mean[row], rs = rstd[row];
@@ -880,7 +880,7 @@ __global__ void cls_fill_kernel(const float* __restrict__ emb, float* __restrict
     const int d = static_cast<int>(i % D);
     const int e = static_cast<int>((i / D) % E);
     const int b = static_cast<int>(i / (static_cast<size_t>(D) * E));
-    mm_x[(static_cast<size_t>(b) * L + e) * D + d] = emb[static_cast<size_t>(d) * E + e];
+    mm_x[(static_cast<size_t>(e) * B + b) * D + d] = emb[static_cast<size_t>(d) * E + e];
   }
 }
 
@@ -890,7 +890,7 @@ __global__ void cls_bwd_kernel(const float* __restrict__ dmm, float* __restrict_
   if (i >= D * E) return;
   const int d = i % D, e = i / D;
   float s = 0.f;
-  for (int b = 0; b < B; ++b) s += dmm[(static_cast<size_t>(b) * L + e) * D + d];
+  for (int b = 0; b < B; ++b) s += dmm[(static_cast<size_t>(e) * B + b) * D + d];
   demb[static_cast<size_t>(d) * E + e] += s;
 }
 
@@ -903,14 +903,15 @@ __global__ void split_rows_kernel(const float* __restrict__ dmm, T* __restrict__
   const size_t total = static_cast<size_t>(B) * ltot * dv;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // position-major everywhere: rows (off_img + l, b) of dmm -> rows (l, b) of the modality buffers
     const int c = static_cast<int>(i % dv);
     const size_t r = i / dv;
-    const int l = static_cast<int>(r % ltot);
-    const int b = static_cast<int>(r / ltot);
+    const int b = static_cast<int>(r % B);
+    const int l = static_cast<int>(r / B);
     const float4 v =
-        *reinterpret_cast<const float4*>(dmm + (static_cast<size_t>(b) * L + off_img + l) * D + 4 * c);
-    if (l < l_img) Vec4<T>::st(dimg + (static_cast<size_t>(b) * l_img + l) * D + 4 * c, v);
-    else Vec4<T>::st(dtxt + (static_cast<size_t>(b) * l_txt + (l - l_img)) * D + 4 * c, v);
+        *reinterpret_cast<const float4*>(dmm + (static_cast<size_t>(off_img + l) * B + b) * D + 4 * c);
+    if (l < l_img) Vec4<T>::st(dimg + (static_cast<size_t>(l) * B + b) * D + 4 * c, v);
+    else Vec4<T>::st(dtxt + (static_cast<size_t>(l - l_img) * B + b) * D + 4 * c, v);
   }
 }
 
@@ -928,17 +929,17 @@ int nv_for(int D) {
 
 // ======================================================================= launchers
 int cast_gather(const float* src, void* dst, int dst_dtype, int B, int l_src, int d, const int* idx,
-                int n_sel, const int* keep, int modality, cudaStream_t stream) {
+                int n_sel, const int* keep, int modality, cudaStream_t stream, int pos_major) {
   if (d % 4 != 0) return MMU_ERR_SHAPE;
   if (B <= 0 || n_sel <= 0) return 0;
   const size_t total = static_cast<size_t>(B) * n_sel * (d / 4);
   const int grid = grid_for(total, 256);
   if (dst_dtype == DT_BF16)
     cast_gather_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
-        src, static_cast<__nv_bfloat16*>(dst), B, l_src, d, idx, n_sel, keep, modality);
+        src, static_cast<__nv_bfloat16*>(dst), B, l_src, d, idx, n_sel, keep, modality, pos_major);
   else
     cast_gather_kernel<float><<<grid, 256, 0, stream>>>(src, static_cast<float*>(dst), B, l_src, d,
-                                                        idx, n_sel, keep, modality);
+                                                        idx, n_sel, keep, modality, pos_major);
   MMU_CHECK_LAUNCH();
   return 0;
 }

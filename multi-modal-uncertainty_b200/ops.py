@@ -56,13 +56,15 @@ def gemm(A, B, *, a_mn_major=False, b_mn_major=False, mode=_lib.EPI_STORE, out=N
     return out if out is not None else out2
 
 
-def mask_gather_tokens(src, idx=None, keep=None, modality=0, dtype=torch.float32):
+def mask_gather_tokens(src, idx=None, keep=None, modality=0, dtype=torch.float32, pos_major=False):
+    """(B, l_src, d) -> (B, n_sel, d), or (n_sel, B, d) with ``pos_major`` (the engine's row order)."""
     _cuda(src, idx, keep)
     Bn, l_src, d = src.shape
     n_sel = l_src if idx is None else idx.numel()
-    out = torch.empty(Bn, n_sel, d, device=src.device, dtype=dtype)
+    shape = (n_sel, Bn, d) if pos_major else (Bn, n_sel, d)
+    out = torch.empty(*shape, device=src.device, dtype=dtype)
     check(lib.mmu_mask_gather_tokens(ptr(src), ptr(out), BF16 if dtype == torch.bfloat16 else F32,
-                                     Bn, l_src, d, ptr(idx), n_sel, ptr(keep), modality,
+                                     Bn, l_src, d, ptr(idx), n_sel, ptr(keep), modality, int(pos_major),
                                      stream_ptr()), "mmu_mask_gather_tokens")
     return out
 
@@ -98,8 +100,9 @@ def _tc_attention(qkv, D, H):
     return qkv.dtype == torch.bfloat16 and (D // H) % 64 == 0
 
 
-def attention_fwd(qkv, B, L, D, H):
-    """Returns (out, saved): saved = lse (SIMT path) or the bf16 probabilities (tensor-core path)."""
+def attention_fwd(qkv, B, L, D, H, pos_major=False):
+    """Returns (out, saved): saved = lse (SIMT path) or the bf16 probabilities (tensor-core path).
+    Rows of ``qkv`` / ``out``: ``b*L + l``, or ``l*B + b`` with ``pos_major``."""
     _cuda(qkv)
     out = torch.empty(B * L, D, device=qkv.device, dtype=qkv.dtype)
     if _tc_attention(qkv, D, H):
@@ -107,16 +110,16 @@ def attention_fwd(qkv, B, L, D, H):
         probs = torch.empty(L * H, B, Bp, device=qkv.device, dtype=torch.bfloat16)
         scores = torch.empty(L * H, B, Bp, device=qkv.device, dtype=torch.float32)
         check(lib.mmu_batchaxis_attention_fwd(ptr(qkv), ptr(out), 0, ptr(probs), ptr(scores),
-                                              _dt(qkv), B, L, D, H, stream_ptr()),
+                                              _dt(qkv), B, L, D, H, int(pos_major), stream_ptr()),
               "mmu_batchaxis_attention_fwd")
         return out, probs
     lse = torch.empty(L * H * B, device=qkv.device, dtype=torch.float32)
     check(lib.mmu_batchaxis_attention_fwd(ptr(qkv), ptr(out), ptr(lse), 0, 0, _dt(qkv), B, L, D, H,
-                                          stream_ptr()), "mmu_batchaxis_attention_fwd")
+                                          int(pos_major), stream_ptr()), "mmu_batchaxis_attention_fwd")
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, saved, B, L, D, H):
+def attention_bwd(qkv, out, dout, saved, B, L, D, H, pos_major=False):
     _cuda(qkv, out, dout, saved)
     dqkv = torch.empty_like(qkv)
     if _tc_attention(qkv, D, H):
@@ -124,11 +127,11 @@ def attention_bwd(qkv, out, dout, saved, B, L, D, H):
         dprobs = torch.empty_like(saved)
         check(lib.mmu_batchaxis_attention_bwd(ptr(qkv), ptr(out), ptr(dout), 0, 0, ptr(saved),
                                               ptr(scores), ptr(dprobs), ptr(dqkv), _dt(qkv), B, L, D,
-                                              H, stream_ptr()), "mmu_batchaxis_attention_bwd")
+                                              H, int(pos_major), stream_ptr()), "mmu_batchaxis_attention_bwd")
         return dqkv
     delta = torch.empty(L * H * B, device=qkv.device, dtype=torch.float32)
     check(lib.mmu_batchaxis_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(saved), ptr(delta), 0, 0,
-                                          0, ptr(dqkv), _dt(qkv), B, L, D, H, stream_ptr()),
+                                          0, ptr(dqkv), _dt(qkv), B, L, D, H, int(pos_major), stream_ptr()),
           "mmu_batchaxis_attention_bwd")
     return dqkv
 

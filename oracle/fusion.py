@@ -76,13 +76,14 @@ def residual_attention_block(x, P, pre, n_head, drop_mult=None):
 
 def transformer(x, P, pre, n_layers, n_head, dropout=None):
     """``dropout = (p, seed)``: training-mode masks of the engine's counter-based generator
-    (oracle/dropout.py; site = layer index, element counter = row-major index of (B*L, 4D))."""
+    (oracle/dropout.py; site = layer index, element counter = row-major index of the engine's
+    POSITION-major [L*B, 4D] activation: (l * B + b) * 4D + column)."""
     for i in range(n_layers):
         mult = None
         if dropout is not None and dropout[0] > 0:
             from . import dropout as _d
             B, L, D = x.shape
-            mult = _d.multiplier(dropout[0], dropout[1], i, B * L * 4 * D, (B, L, 4 * D), x.dtype)
+            mult = _d.multiplier(dropout[0], dropout[1], i, B * L * 4 * D, (L, B, 4 * D), x.dtype).permute(1, 0, 2)
         x = residual_attention_block(x, P, f"{pre}resblocks.{i}.", n_head, mult)
     return x
 

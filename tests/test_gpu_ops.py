@@ -172,6 +172,16 @@ def test_batch_axis_attention(mmu, dtype, tol, B, L, D, H):
     o.backward(do.double())
     dqkv = mmu.ops.attention_bwd(qkv.cuda(), out, do.cuda(), saved, B, L, D, H)
     assert rel(dqkv.float().cpu(), q.grad) < tol * 2
+    # position-major rows (l*B + b), the engine's layout: same problems, same kernels, other strides
+    # -> bit-identical results on the permuted tensors
+
+    def pm(t):
+        return t.view(B, L, -1).transpose(0, 1).reshape(L * B, -1).contiguous()
+
+    out_p, saved_p = mmu.ops.attention_fwd(pm(qkv).cuda(), B, L, D, H, pos_major=True)
+    assert torch.equal(out_p.cpu(), pm(out.cpu())) and torch.equal(saved_p.cpu(), saved.cpu())
+    dqkv_p = mmu.ops.attention_bwd(pm(qkv).cuda(), out_p, pm(do).cuda(), saved_p, B, L, D, H, pos_major=True)
+    assert torch.equal(dqkv_p.cpu(), pm(dqkv.cpu()))
 
 
 @pytest.mark.parametrize("N,E,C", [(500, 5, 101), (37, 2, 2), (64, 4, 10), (1001, 1, 101), (33, 3, 300)])
@@ -249,6 +259,9 @@ def test_mask_gather(mmu):
     assert torch.equal(out.cpu(), ref)  # bit-exact masks / gather
     out = mmu.ops.mask_gather_tokens(src.cuda(), None, keep.cuda(), modality=1, dtype=torch.bfloat16)
     assert torch.equal(out.cpu(), (src * keep[:, 1].view(-1, 1, 1)).to(torch.bfloat16))
+    # position-major destination rows (token position, sample): what the engine stages
+    out = mmu.ops.mask_gather_tokens(src.cuda(), idx.cuda(), keep.cuda(), modality=0, pos_major=True)
+    assert torch.equal(out.cpu(), ref.transpose(0, 1))
 
 
 def test_posthoc_scoring_matches_notebook_golden(mmu, golden):
