@@ -642,6 +642,45 @@ def measure_rooflines(mmu, dev, min_seconds=1.0):
     bias = {n: torch.zeros(n, device=dev) for n in (D, 3 * D, 4 * D)}
     g = mmu.ops.gemm
 
+    # ---- HBM-bound kernels FIRST (each timed alone in a short loop on a cool board: the measured copy
+    #      bandwidth is the peak), before the >= 1 s GEMM loop drives the board into its power cap
+    hbm = []
+    n = 22_843_392 // 4 * 4
+    p, gr, m_, v_ = (torch.randn(n, device=dev) for _ in range(4))
+    v_.abs_()
+    sh = torch.empty(n, device=dev, dtype=bf)
+    for _ in range(3):
+        mmu.ops.adamw_flat_step(p, gr, m_, v_, 1, 1e-3, p_bf16=sh)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(20):
+        mmu.ops.adamw_flat_step(p, gr, m_, v_, i + 2, 1e-3, p_bf16=sh)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 20 * 1e3
+    gbs = 28.0 * n / (us * 1e-6) / 1e9
+    hbm.append({"kernel": "adamw_kernel", "bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"],
+                "unit": "GB/s", "frac": round(gbs / pk["hbm"], 3), "bytes_per_param": 28,
+                "us_per_launch": round(us, 1), "note": "22.8 M params (640 MB/launch of p,g,m,v; > L2)"})
+    N = 1 << 20
+    logits = torch.randn(N, CFG["E"], CFG["C"], device=dev)
+    y = torch.randint(0, CFG["C"], (N,), device=dev)
+    acc = mmu.ops.new_accum(dev)
+    for _ in range(2):
+        mmu.ops.heads_uncertainty_epilogue(logits, y, 1, accum=acc)
+    e0.record()
+    for _ in range(5):
+        mmu.ops.heads_uncertainty_epilogue(logits, y, 1, accum=acc)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 5 * 1e3
+    byts = N * (CFG["E"] * CFG["C"] * 4 + 8)
+    gbs = byts / (us * 1e-6) / 1e9
+    hbm.append({"kernel": "ce_uncertainty_kernel", "bound": "hbm", "achieved": round(gbs, 1),
+                "peak": pk["hbm"], "unit": "GB/s", "frac": round(gbs / pk["hbm"], 3),
+                "bytes_per_sample": CFG["E"] * CFG["C"] * 4 + 8, "us_per_launch": round(us, 1),
+                "note": "1 Mi samples x (5 x 101) logits, eval mode (2.1 GB/launch; > L2)"})
+
     def layer_gemms():
         # forward
         g(x768, w[3 * D], out=o2304, bias=bias[3 * D])
@@ -660,7 +699,6 @@ def measure_rooflines(mmu, dev, min_seconds=1.0):
         g(x2304, x768, a_mn_major=True, b_mn_major=True, mode=E_.EPI_ATOMIC, out=gw[(3 * D, D)], splits=3)
 
     flops_layer = 3 * (2 * M * D * 3 * D + 2 * M * D * D + 2 * 2 * M * D * 4 * D)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
         layer_gemms()
     torch.cuda.synchronize()
@@ -694,42 +732,6 @@ def measure_rooflines(mmu, dev, min_seconds=1.0):
             "note": "12 GEMM launches of one transformer block's fwd+bwd (M=30336), operands > L2; "
                     "traffic = average DRAM bytes per launch from the committed ncu capture under profiles/"}
 
-    # ---- HBM-bound kernels (each timed alone in a short loop -> burst copy bandwidth is the peak)
-    hbm = []
-    n = 22_843_392 // 4 * 4
-    p, gr, m_, v_ = (torch.randn(n, device=dev) for _ in range(4))
-    v_.abs_()
-    sh = torch.empty(n, device=dev, dtype=bf)
-    for _ in range(3):
-        mmu.ops.adamw_flat_step(p, gr, m_, v_, 1, 1e-3, p_bf16=sh)
-    e0.record()
-    for i in range(20):
-        mmu.ops.adamw_flat_step(p, gr, m_, v_, i + 2, 1e-3, p_bf16=sh)
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / 20 * 1e3
-    gbs = 28.0 * n / (us * 1e-6) / 1e9
-    hbm.append({"kernel": "adamw_kernel", "bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"],
-                "unit": "GB/s", "frac": round(gbs / pk["hbm"], 3), "bytes_per_param": 28,
-                "us_per_launch": round(us, 1), "note": "22.8 M params (640 MB/launch of p,g,m,v; > L2)"})
-    N = 1 << 20
-    logits = torch.randn(N, CFG["E"], CFG["C"], device=dev)
-    y = torch.randint(0, CFG["C"], (N,), device=dev)
-    acc = mmu.ops.new_accum(dev)
-    for _ in range(2):
-        mmu.ops.heads_uncertainty_epilogue(logits, y, 1, accum=acc)
-    e0.record()
-    for _ in range(5):
-        mmu.ops.heads_uncertainty_epilogue(logits, y, 1, accum=acc)
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / 5 * 1e3
-    byts = N * (CFG["E"] * CFG["C"] * 4 + 8)
-    gbs = byts / (us * 1e-6) / 1e9
-    hbm.append({"kernel": "ce_uncertainty_kernel", "bound": "hbm", "achieved": round(gbs, 1),
-                "peak": pk["hbm"], "unit": "GB/s", "frac": round(gbs / pk["hbm"], 3),
-                "bytes_per_sample": CFG["E"] * CFG["C"] * 4 + 8, "us_per_launch": round(us, 1),
-                "note": "1 Mi samples x (5 x 101) logits, eval mode (2.1 GB/launch; > L2)"})
     return roof, hbm
 
 
