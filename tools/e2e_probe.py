@@ -1,0 +1,119 @@
+#!/usr/bin/env python
+"""Where do the 0.7 ms between bench.py's `value` (resident inputs) and `e2e` (pinned host ->
+prefetcher -> public API -> D2H of loss / acc) go?  Times the headline step under switches:
+
+  resident_manual   : bench.py's step_resident (the `value` leg)
+  resident_trainer  : resident batches through Model_.train_step(sync=False), no read-back
+  prefetch_noread   : pinned host batches through DevicePrefetcher, no read-back
+  prefetch_read_lag : + float() of the previous step's loss / acc (bench.py's `e2e` leg)
+"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+import mmu_b200 as mmu  # noqa: E402
+from functools import partial  # noqa: E402
+
+CFG = bench.CFG
+dev = torch.device("cuda", 0)
+torch.cuda.set_device(0)
+torch.manual_seed(42)
+model = mmu.FlavaFusionTransfomer(out_dim=CFG["E"], num_classes=CFG["C"], multimodal_num_attention_heads=CFG["heads"],
+                                  multimodal_num_hidden_layers=CFG["layers"], drop=0.0, avg_pool=False, precision="bf16")
+opt = mmu.FusedAdamW(model.parameters(), lr=CFG["lr"], betas=(0.9, 0.98), eps=1e-9, weight_decay=CFG["wd"])
+sched = mmu.get_cosine_schedule_with_warmup(opt, 300, 10000)
+shaping = partial(mmu.dataset.data_forming_func_transformer, model_type="MultiHead")
+
+
+def multihead5(x, y, phase):
+    x, y = shaping(x, y, phase)
+    return x, (y[:, :1].repeat(1, CFG["E"]) if phase == "train" else y)
+
+
+trainer = mmu.Model_(model, opt, sched, multihead5, metrics=[mmu.acc], verbose=False)
+trainer.to(dev)
+meter = mmu.metrics.UncertaintyMeter(dev, CFG["C"], CFG["E"])
+B, nb = CFG["B"], 4
+host = bench.make_host_batches(nb, B, 1000, pin=True)
+resident = [((i.to(dev), t.to(dev)), y.to(dev)) for (i, t), y in host]
+
+
+def sweep_and_mask(img, txt, y, seed):
+    variants = bench.draw_level_variants(mmu.robustness.mask_level_variant, seed)
+    model.eval()
+    with torch.no_grad():
+        logits = model.forward_variants((img, txt), variants)
+        _, scores = meter.update(logits.view(-1, CFG["E"], CFG["C"]), y.repeat(len(variants)), want_scores=True)
+    model.train()
+    lv = CFG["levels"]
+    return mmu.robustness.modality_dropout_mask_device(B, CFG["p_drop"], "guided", dev,
+                                                       score_img=scores[(lv - 1) * B:, 0], score_txt=scores[:B, 0])
+
+
+def step_manual(i):
+    (img, txt), y = resident[i % nb]
+    keep = sweep_and_mask(img, txt, y, i)
+    yt = y.unsqueeze(1).repeat(1, CFG["E"])
+    opt.zero_grad()
+    logits = model((img, txt), keep_mask=keep)
+    loss = model.compute_loss(logits, yt)
+    loss.backward()
+    opt.step()
+    mmu.acc(logits, yt, False, True)
+    sched.step()
+
+
+def step_trainer(batch, i):
+    (img, txt), y = batch
+    keep = sweep_and_mask(img, txt, y, i)
+    return trainer.train_step((img, txt), y, keep_mask=keep, sync=False)[:2]
+
+
+def timed(fn, steps=20):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_manual(steps):
+    for i in range(steps):
+        step_manual(i)
+
+
+def run_resident_trainer(steps):
+    for i in range(steps):
+        step_trainer(resident[i % nb], i)
+
+
+prefetcher = mmu.dataset.DevicePrefetcher([], dev)
+
+
+def run_prefetch(steps, read):
+    prefetcher.loader = [host[i % nb] for i in range(steps)]
+    pending = None
+    for i, batch in enumerate(prefetcher):
+        cur = step_trainer(batch, i)
+        if read and pending is not None:
+            float(pending[0]), [float(v) for v in pending[1]]
+        pending = cur
+    if read:
+        float(pending[0])
+
+
+model.train()
+out = {}
+for name, fn in (("resident_manual", run_manual), ("resident_trainer", run_resident_trainer),
+                 ("prefetch_noread", lambda n: run_prefetch(n, False)),
+                 ("prefetch_read_lag", lambda n: run_prefetch(n, True)),
+                 ("resident_manual_again", run_manual)):
+    fn(4)
+    out[name] = round(timed(fn), 3)
+print(json.dumps(out))
