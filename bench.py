@@ -287,19 +287,25 @@ def run_gpu(args):
         """Public-API loop: pinned host batches -> DevicePrefetcher (H2D of batch i+1 on a side
         stream while step i runs) -> packed sweep -> Model_.train_step.  Every step's batch is
         copied host->device and every step's loss / acc is read back device->host inside the timed
-        region; the read of step i happens after step i+1 has been enqueued (one-step lag, the way
-        an asynchronous logger consumes them) so the host never drains the queue."""
+        region; the read of step i is collected after step i+1 has been enqueued (one-step lag,
+        the way an asynchronous logger consumes them) and is copied on a side stream, so the host
+        never drains the queue."""
         prefetcher.loader = [host[i % nb] for i in range(steps)]
         pending, history = None, []
         for i, batch in enumerate(prefetcher):
-            cur = step_e2e(batch, i)
+            loss, info = step_e2e(batch, i)
+            # D2H of this step's loss / acc on a side stream behind an event (metrics.AsyncScalars):
+            # a plain float(loss) would copy on the compute stream, i.e. behind the step that has
+            # just been enqueued, and stall the host until THAT step ends
+            ticket = reader.push([loss] + list(info))
             if pending is not None:
-                history.append((float(pending[0]), [float(v) for v in pending[1]]))
-            pending = cur
-        history.append((float(pending[0]), [float(v) for v in pending[1]]))
+                history.append(reader.pop(pending))
+            pending = ticket
+        history.append(reader.pop(pending))
         return history
 
     prefetcher = mmu.dataset.DevicePrefetcher([], dev)  # its two device slots persist across runs
+    reader = mmu.metrics.AsyncScalars(dev)
 
     def barrier():
         torch.cuda.synchronize()

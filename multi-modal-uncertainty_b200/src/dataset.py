@@ -208,6 +208,10 @@ class DevicePrefetcher:
         self.loader, self.device, self.pin = loader, torch.device(device), pin
         self.stream = torch.cuda.Stream(device=self.device)
         self._bufs = [dict() for _ in range(self.SLOTS)]
+        # event behind the consumer's last use of each slot; kept across __iter__ calls so that a
+        # second pass over the loader never refills a slot the previous pass's last steps (still
+        # queued on the GPU) are reading
+        self._released = [None] * self.SLOTS
 
     def _copy(self, obj, slot, path):
         if obj is None:
@@ -220,6 +224,10 @@ class DevicePrefetcher:
         if buf is None or buf.shape != obj.shape or buf.dtype != obj.dtype:
             buf = torch.empty(obj.shape, dtype=obj.dtype, device=self.device)
             self._bufs[slot][path] = buf
+            # the caching allocator may hand out a block that kernels ALREADY QUEUED on the
+            # consumer's stream still use (freed by the host, not yet by the GPU): reuse is only
+            # ordered on the allocating stream, so the copy stream must get behind that work
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             buf.copy_(obj, non_blocking=True)
         return buf
@@ -229,7 +237,7 @@ class DevicePrefetcher:
 
     def __iter__(self):
         it = iter(self.loader)
-        released = [None] * self.SLOTS  # event behind the consumer's last use of each slot
+        released = self._released
         state = {"k": 0}
 
         def fetch():
@@ -252,7 +260,9 @@ class DevicePrefetcher:
             cur = torch.cuda.current_stream(self.device)
             nxt = fetch()            # batch i+1 starts copying now (into the other slot)
             cur.wait_event(ready)    # batch i has landed before the step touches it
-            yield batch
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.device))
-            released[slot] = ev
+            try:
+                yield batch
+            finally:        # also when the consumer breaks out of the loop
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                released[slot] = ev

@@ -44,6 +44,49 @@ def acc(y_pred, y_true, eval, dummy_dim=False, model=None):
     return correct / rows * 100
 
 
+class AsyncScalars:
+    """Device -> host read of per-step scalars (loss, metrics) that does NOT drain the work queued
+    behind them.  ``tensor.item()`` / ``float(tensor)`` copies on the CURRENT stream, i.e. behind
+    every kernel already enqueued -- with one-step-lagged logging the host then waits for the step
+    it has just launched, and the GPU idles while the next step is being prepared (0.37 ms per
+    13.8 ms step, ``tools/e2e_probe.py``).  ``push`` records an event behind the producing step,
+    copies on a side stream into pinned memory and returns a ticket; ``pop`` waits for that copy
+    only.  Replaces the two per-step ``.item()`` reads of reference ``src/framework.py:305-312``
+    for a logger that may lag by a step."""
+
+    def __init__(self, device, slots=4, width=8):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.host = [torch.empty(width, dtype=torch.float32).pin_memory() for _ in range(slots)]
+        self.stage = [torch.empty(width, dtype=torch.float32, device=self.device) for _ in range(slots)]
+        self.done = [None] * slots
+        self.n = [0] * slots
+        self.k = -1
+
+    def push(self, scalars):
+        """``scalars``: 0-dim device tensors.  Returns a ticket for :meth:`pop`."""
+        self.k = (self.k + 1) % len(self.host)
+        k = self.k
+        if self.done[k] is not None:
+            self.done[k].synchronize()          # the slot's previous copy has landed
+        vals = torch.stack([s.detach().reshape(()).float() for s in scalars])
+        self.n[k] = vals.numel()
+        self.stage[k][:vals.numel()].copy_(vals)   # on the producing stream, behind the step
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            self.host[k].copy_(self.stage[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self.done[k] = ev
+        return k
+
+    def pop(self, ticket):
+        self.done[ticket].synchronize()
+        return self.host[ticket][:self.n[ticket]].tolist()
+
+
 class UncertaintyMeter:
     """Device-side accumulator of the fused epilogue's metrics over a sweep.
 

@@ -320,6 +320,32 @@ def test_device_prefetcher_yields_host_batches_in_order(mmu):
     assert seen == len(host)
 
 
+def test_device_prefetcher_never_overtakes_queued_work(mmu):
+    """The copy stream must not write into (a) a freshly allocated slot whose memory block queued
+    consumer-stream kernels still read (the caching allocator orders reuse on ONE stream only),
+    nor (b) a slot the previous pass's last steps still read.  Regression test of the illegal
+    address `tools/e2e_probe.py` hit when the host ran several steps ahead of the GPU."""
+    n = 32 << 20                                            # 128 MiB of fp32
+    dev = torch.device("cuda")
+    host = [((torch.full((n,), 7.0).pin_memory(), None), torch.zeros(1, dtype=torch.int64).pin_memory())
+            for _ in range(3)]
+    torch.cuda.synchronize()
+    x = torch.ones(n, device=dev)
+    acc = torch.zeros(n, device=dev)
+    for _ in range(300):                                    # ~15 ms of queued readers of x
+        acc.add_(x)
+    del x                                                   # host-side free: block back in the pool
+    pf = mmu.dataset.DevicePrefetcher(host, dev)
+    sums = []
+    for (img, _), _y in pf:                                 # pass 1: slots are allocated here
+        sums.append(torch.stack([img.min(), img.max()]))
+    for (img, _), _y in pf:                                 # pass 2: slots are re-filled
+        sums.append(torch.stack([img.min(), img.max()]))
+    torch.cuda.synchronize()
+    assert float(acc.min()) == 300.0 and float(acc.max()) == 300.0
+    assert all(s.tolist() == [7.0, 7.0] for s in sums)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["plain_E2", "avgpool_E2", "plain_E5_h3"])
 def test_packed_variants_equal_per_variant_forwards(mmu, golden, name, precision):

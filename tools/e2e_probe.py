@@ -108,12 +108,31 @@ def run_prefetch(steps, read):
         float(pending[0])
 
 
+reader = mmu.metrics.AsyncScalars(dev)
+
+
+def run_prefetch_async(steps):
+    prefetcher.loader = [host[i % nb] for i in range(steps)]
+    pending = None
+    for i, batch in enumerate(prefetcher):
+        loss, info = step_trainer(batch, i)
+        ticket = reader.push([loss] + list(info))
+        if pending is not None:
+            reader.pop(pending)
+        pending = ticket
+    reader.pop(pending)
+
+
 model.train()
-out = {}
-for name, fn in (("resident_manual", run_manual), ("resident_trainer", run_resident_trainer),
-                 ("prefetch_noread", lambda n: run_prefetch(n, False)),
-                 ("prefetch_read_lag", lambda n: run_prefetch(n, True)),
-                 ("resident_manual_again", run_manual)):
+legs = (("resident_manual", run_manual), ("resident_trainer", run_resident_trainer),
+        ("prefetch_noread", lambda n: run_prefetch(n, False)),
+        ("prefetch_read_item", lambda n: run_prefetch(n, True)),
+        ("prefetch_read_async", run_prefetch_async))
+for _, fn in legs:
     fn(4)
-    out[name] = round(timed(fn), 3)
+out = {name: [] for name, _ in legs}
+for rnd in range(4):            # interleaved rounds cancel the thermal drift of the board
+    for name, fn in legs:
+        out[name].append(round(timed(fn, 10), 3))
+out["mean"] = {k: round(sum(v) / len(v), 3) for k, v in out.items()}
 print(json.dumps(out))

@@ -1,9 +1,4 @@
 mkdir -p gpurun_out
-{
-for pf in 0 2 4 8 16 32; do
-  for c in 9 19 20 11 21 7 8; do
-    MMU_GEMM_L2PF=$pf timeout 120 ./build/gemm_harness_pf $c 2>&1 | grep -E "RESULT|TIMING|error|Error|timed out" | sed "s/^/[pf=$pf] /"
-  done
-done
-} > gpurun_out/r2_harness_l2pf.log 2>&1
-grep TIMING gpurun_out/r2_harness_l2pf.log
+( time python -m pytest tests -m gpu -x -q ) > gpurun_out/r2b_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/r2b_pytest_gpu.log
+python tools/e2e_probe.py > gpurun_out/r2_e2e_probe_a.json 2> gpurun_out/r2_e2e_probe_a.err; echo "probe exit $?"; cat gpurun_out/r2_e2e_probe_a.json | head -c 900; grep -m3 "Error\|error" gpurun_out/r2_e2e_probe_a.err
+python bench.py > gpurun_out/r2b_bench.json 2> gpurun_out/r2b_bench.err; echo "bench exit $?"; head -c 1500 gpurun_out/r2b_bench.json
