@@ -16,6 +16,7 @@
 #include "engine.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -149,6 +150,11 @@ struct Ws {
   void* dprobs;    // bf16 [L*H, B, Bp] scratch (dS)
   void* dimg;
   void* dtxt;
+  // eval, bf16: LayerNorm folded into the consumer GEMMs (fold_path): per-layer folded weights
+  // (in_proj with ln_1, c_fc with ln_2) and two row-statistics buffers [M][nt][2]
+  struct FoldedLayer { void* in_wf; float* in_cw; float* in_bf; void* fc_wf; float* fc_cw; float* fc_bf; };
+  FoldedLayer fold[64];
+  float* fold_stats[2];
   long long bytes;
 };
 
@@ -162,6 +168,18 @@ struct Bump {
     return base != nullptr ? reinterpret_cast<T*>(base + o) : nullptr;
   }
 };
+
+// Eval forwards of the bf16 engine never materialise LayerNorm outputs: the projections that close
+// a residual branch add the fp32 residual stream in their epilogue (EPI_RESID_LN: x' fp32, a raw
+// bf16 copy, per-slab row sums) and the GEMMs that consume ln_1 / ln_2 apply the normalisation in
+// THEIR epilogue from those sums (GemmEpilogue::ln_stats) -- the add+LayerNorm row kernels and their
+// 12 B/element of HBM traffic disappear.  Training keeps the row kernels (their outputs and
+// statistics are what the backward reads).  MMU_EVAL_NOFOLD=1: A/B switch back to the row kernels.
+int fold_slabs(const FlavaConfig& c) { return (c.D + 127) / 128; }
+bool fold_path(const FlavaConfig& c, int training) {
+  static const bool disabled = getenv("MMU_EVAL_NOFOLD") != nullptr;
+  return !training && !disabled && c.precision == PREC_BF16 && c.n_layers > 0 && fold_slabs(c) <= 8;
+}
 
 // The tensor-core path needs 16-byte rows (feature widths % 8): a stem whose input width is not
 // (MIMOTransfomer: 14*14 = 196 pixels per view) runs its small projection GEMMs in fp32 instead.
@@ -221,6 +239,18 @@ void carve(const FlavaConfig& c, int training, void* base, const Layout& lay, Ws
   } else {
     w->dvec = nullptr; w->dx = nullptr; w->dx_lp = nullptr; w->dbig = nullptr; w->dh = nullptr;
     w->delta = nullptr; w->dprobs = nullptr; w->dimg = nullptr; w->dtxt = nullptr;
+  }
+  if (fold_path(c, training)) {
+    for (int i = 0; i < c.n_layers; ++i) {
+      Ws::FoldedLayer& f = w->fold[i];
+      f.in_wf = b.take<void>(3 * D * D * 2);
+      f.in_cw = b.take<float>(3 * D * 4);
+      f.in_bf = b.take<float>(3 * D * 4);
+      f.fc_wf = b.take<void>(4 * D * D * 2);
+      f.fc_cw = b.take<float>(4 * D * 4);
+      f.fc_bf = b.take<float>(4 * D * 4);
+    }
+    for (int k = 0; k < 2; ++k) w->fold_stats[k] = b.take<float>(M * fold_slabs(c) * 2 * 4);
   }
   w->bytes = b.off;
 }
@@ -415,6 +445,53 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
   if (c.cls_token) MMU_TRY(cls_fill(params + lay.cls, w.mm_x, c.B, s.L, D, c.E, stream));
 
   float* x = training && c.n_layers > 0 ? w.layer[0].x0 : w.x_out[0];
+  if (fold_path(c, training)) {
+    // ---- eval, bf16: no LayerNorm output ever reaches HBM (see fold_path)
+    const int nt = fold_slabs(c);
+    const float inv_d = 1.0f / static_cast<float>(D);
+    for (int i = 0; i < c.n_layers; ++i) {
+      const LayerParams& p = lay.layer[i];
+      const Ws::FoldedLayer& f = w.fold[i];
+      MMU_TRY(ln_fold_weights(params + p.in_w, params + p.ln1_w, params + p.ln1_b, params + p.in_b, f.in_wf,
+                              f.in_cw, f.in_bf, 3 * D, params + p.fc_w, params + p.ln2_w, params + p.ln2_b,
+                              params + p.fc_b, f.fc_wf, f.fc_cw, f.fc_bf, 4 * D, D, stream));
+    }
+    auto folded = [&](GemmEpilogue e, const float* stats, const float* cw) {
+      e.ln_stats = stats; e.ln_cw = cw; e.ln_nt = nt; e.ln_inv_d = inv_d; e.ln_eps = 1e-5f;
+      return e;
+    };
+    auto resid = [&](const float* x_in, float* x_out, void* raw, float* stats, const float* bias) {
+      GemmEpilogue e = epi(EPI_RESID_LN, x_out, 0, D, bias);
+      e.aux = x_in; e.ld_aux = D;
+      e.out2 = raw; e.ld_out2 = D;
+      e.stats_out = stats; e.stats_nt = nt;
+      return e;
+    };
+    const LayerWs& l = w.layer[0];  // eval: one slot shared by every layer
+    // x = ln_pre(mm_x) in fp32 + its raw bf16 copy + row sums (the first ln_1 is folded into in_proj)
+    MMU_TRY(layernorm_raw_stats_fwd(w.mm_x, params + lay.lnpre_w, params + lay.lnpre_b, x, l.h1,
+                                    w.fold_stats[0], nt, M, D, stream));
+    for (int i = 0; i < c.n_layers; ++i) {
+      const LayerParams& p = lay.layer[i];
+      const Ws::FoldedLayer& f = w.fold[i];
+      float* x_next = w.x_out[(i + 1) & 1];
+      const bool last = i + 1 == c.n_layers;
+      MMU_TRY(gemm(l.h1, D, 0, f.in_wf, D, 0, M, 3 * D, D,
+                   folded(epi(EPI_STORE, l.qkv, 1, 3 * D, f.in_bf), w.fold_stats[0], f.in_cw)));
+      MMU_TRY(attention_fwd(l.qkv, l.o, l.lse, l.probs, w.scores, dt, c.B, s.L, D, c.n_head, stream, 1));
+      MMU_TRY(gemm(l.o, D, 0, W(p.out_w), D, 0, M, D, D,
+                   resid(x, l.x1, l.h2, w.fold_stats[1], params + p.out_b)));
+      {
+        GemmEpilogue e = epi(EPI_QUICKGELU, nullptr, 1, 4 * D, f.fc_bf);
+        e.out2 = l.u; e.ld_out2 = 4 * D;
+        MMU_TRY(gemm(l.h2, D, 0, f.fc_wf, D, 0, M, 4 * D, D, folded(e, w.fold_stats[1], f.fc_cw)));
+      }
+      MMU_TRY(gemm(l.u, 4 * D, 0, W(p.proj_w), 4 * D, 0, M, D, 4 * D,
+                   resid(l.x1, x_next, last ? nullptr : l.h1, last ? nullptr : w.fold_stats[0],
+                         params + p.proj_b)));
+      x = x_next;
+    }
+  } else {
   if (c.n_layers > 0) {  // ln_pre chained with the first block's ln_1 in one pass over the rows
     const LayerParams& p0 = lay.layer[0];
     const LayerWs& l0 = w.layer[0];
@@ -463,6 +540,8 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
     }
     x = x_next;
   }
+
+  }  // !fold_path
 
   // ---- ln_post + row gather / mean pooling + heads (src/model.py:277-289)
   HeadParams hp{};

@@ -15,6 +15,10 @@ enum GemmEpiMode : int {
   EPI_ATOMIC = 4,     // out(f32) += alpha*acc   (split-K partial sums)
   EPI_SOFTMAX = 5,    // out(bf16) = softmax over columns [0, n_valid) of alpha*acc, 0 beyond
                       // (batched bf16 path, N <= 128: the attention probabilities, fused)
+  EPI_RESID_LN = 6,   // bf16 kernel, unbatched: out(f32) = aux(f32) + alpha*acc + bias (the residual
+                      // stream, src/model.py:210-211; aux may alias out), out2(bf16, optional) =
+                      // bf16(out) = the RAW operand of the next LN-folded GEMM, stats_out
+                      // (optional)[row][n/128] = (sum, sum of squares) of out over a 128-column slab
 };
 
 struct GemmEpilogue {
@@ -36,6 +40,19 @@ struct GemmEpilogue {
   // EPI_QUICKGELU / EPI_DGELU: dropout applied to z BEFORE the activation (src/model.py:195-201);
   // element counter = row * N + column.  thresh == 0: off.
   dropout::Site drop;
+  // LayerNorm FOLDED into the GEMM that consumes the normalised rows (EPI_STORE / EPI_QUICKGELU of
+  // the bf16 kernel, bf16 out, unbatched; src/model.py:209-212 ln_1 -> in_proj, ln_2 -> c_fc):
+  // A holds the raw rows x, B holds W diag(gamma), and with the row statistics
+  //   mean_r = S1_r / D, rstd_r = rsqrt(S2_r / D - mean_r^2 + eps)   (S1, S2 summed over ln_nt partials)
+  //   out = rstd_r * (acc - mean_r * ln_cw[n]) + bias[n],  ln_cw[n] = sum_k B[n][k],
+  //   bias[n] = b[n] + sum_k beta[k] W[n][k]      (so that out = LN(x) W^T + b exactly)
+  const float* ln_stats;  // [M][ln_nt][2] partial (sum, sum of squares) per row; nullptr: off
+  const float* ln_cw;     // [N]
+  int ln_nt;
+  float ln_inv_d, ln_eps;
+  // EPI_RESID_LN: partial row statistics of `out`, [M][stats_nt][2], slab n/128 (nullptr: off)
+  float* stats_out;
+  int stats_nt;
 };
 
 struct GemmProblem {

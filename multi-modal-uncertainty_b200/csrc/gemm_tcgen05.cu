@@ -148,12 +148,12 @@ bool use_pair(const GemmProblem& p) {
   return p.batch == 0 && p.M >= 512 && p.N > gemm::BN / 2 && pair_mode_enabled();
 }
 
-template <int MODE, bool OBF, int NCTA>
+template <int MODE, bool OBF, int NCTA, bool FOLD = false>
 int launch_kernel(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& c0,
-                  const CUtensorMap& c1, const GemmProblem& p, const GemmEpilogue& e,
-                  cudaStream_t stream) {
+                  const CUtensorMap& c1, const CUtensorMap& c2, const GemmProblem& p,
+                  const GemmEpilogue& e, cudaStream_t stream) {
   using namespace gemm;
-  auto kernel = gemm_bf16_tcgen05_kernel<MODE, OBF, NCTA>;
+  auto kernel = gemm_bf16_tcgen05_kernel<MODE, OBF, NCTA, FOLD>;
   static cudaError_t attr_err =
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (attr_err != cudaSuccess) {
@@ -163,7 +163,7 @@ int launch_kernel(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const 
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(NUM_THREADS + (FOLD ? 32 : 0));  // FOLD: + the statistics warp
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -185,7 +185,7 @@ int launch_kernel(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const 
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  const cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, ta, tb, c0, c1, p, e);
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, kernel, ta, tb, c0, c1, c2, p, e);
   if (err != cudaSuccess) {
     fprintf(stderr, "mmu: gemm launch failed: %s\n", cudaGetErrorString(err));
     return MMU_ERR_CUDA;
@@ -198,19 +198,29 @@ int launch_kernel(int grid, const CUtensorMap& ta, const CUtensorMap& tb, const 
 template <int MODE, bool OBF>
 int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& c0,
                 const CUtensorMap& c1, const GemmProblem& p, const GemmEpilogue& e,
-                cudaStream_t stream) {
+                cudaStream_t stream, const CUtensorMap* c2p = nullptr) {
+  const CUtensorMap& c2 = c2p != nullptr ? *c2p : c1;
   using namespace gemm;
   const int nbatch = p.batch > 0 ? p.batch : 1;
   const long long n_tiles = (p.N + BN - 1) / BN;
+  constexpr bool CAN_FOLD = (MODE == EPI_STORE || MODE == EPI_QUICKGELU) && OBF;
+  const bool fold = e.ln_stats != nullptr;
+  if (fold && !CAN_FOLD) return MMU_ERR_ARG;
   if (use_pair(p)) {
     const long long tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * n_tiles * p.splits;
     const long long clusters = gemm_sms() / 2;
     const int grid = 2 * static_cast<int>(tiles < clusters ? tiles : clusters);
-    return launch_kernel<MODE, OBF, 2>(grid, ta, tb, c0, c1, p, e, stream);
+    if constexpr (CAN_FOLD) {
+      if (fold) return launch_kernel<MODE, OBF, 2, true>(grid, ta, tb, c0, c1, c2, p, e, stream);
+    }
+    return launch_kernel<MODE, OBF, 2>(grid, ta, tb, c0, c1, c2, p, e, stream);
   }
   const long long tiles = nbatch * ((p.M + BM - 1) / BM) * n_tiles * p.splits;
   const int grid = static_cast<int>(tiles < gemm_sms() ? tiles : gemm_sms());
-  return launch_kernel<MODE, OBF, 1>(grid, ta, tb, c0, c1, p, e, stream);
+  if constexpr (CAN_FOLD) {
+    if (fold) return launch_kernel<MODE, OBF, 1, true>(grid, ta, tb, c0, c1, c2, p, e, stream);
+  }
+  return launch_kernel<MODE, OBF, 1>(grid, ta, tb, c0, c1, c2, p, e, stream);
 }
 
 // Output maps + mode dispatch shared by the plain and the batched entry points.  `rows`/`cols`
@@ -225,7 +235,29 @@ int launch_with_epilogue(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
   };
   CUtensorMap c0, c1;
   int rc;
+  if (e.ln_stats != nullptr) {  // LayerNorm folded into the epilogue: see gemm_api.h
+    if ((e.mode != EPI_STORE && e.mode != EPI_QUICKGELU) || !obf || p.batch > 0 || e.ln_cw == nullptr ||
+        e.ln_nt < 1 || e.ln_nt > gemm::LN_MAX_NT || e.alpha != 1.0f || (reinterpret_cast<uintptr_t>(e.ln_cw) & 3) != 0 ||
+        (reinterpret_cast<uintptr_t>(e.ln_stats) & 7) != 0)
+      return MMU_ERR_ARG;
+  }
   switch (e.mode) {
+    case EPI_RESID_LN: {
+      // out fp32 (c0), optional bf16 copy out2 (c1), fp32 residual aux (c2)
+      if (obf || e.out == nullptr || e.aux == nullptr || p.batch > 0 || p.splits > 1) return MMU_ERR_ARG;
+      if (e.stats_out != nullptr && (e.stats_nt < (p.N + gemm::BN / 2 - 1) / (gemm::BN / 2) ||
+                                     (reinterpret_cast<uintptr_t>(e.stats_out) & 7) != 0))
+        return MMU_ERR_ARG;
+      CUtensorMap c2;
+      if ((rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;
+      if ((rc = omap(&c2, e.aux, e.ld_aux)) != 0) return rc;
+      c1 = c0;
+      if (e.out2 != nullptr &&
+          (rc = make_tmap_out_4d(&c1, e.out2, 1, p.N, p.M, e.ld_out2, hdiv, p.out_hstride, nmid,
+                                 p.out_mid_stride)) != 0)
+        return rc;
+      return launch_mode<EPI_RESID_LN, false>(ta, tb, c0, c1, p, e, stream, &c2);
+    }
     case EPI_STORE:
       if (e.out == nullptr) return MMU_ERR_ARG;
       if ((rc = omap(&c0, e.out, e.ld_out)) != 0) return rc;

@@ -42,34 +42,49 @@ constexpr int UMMA_K = 16;
 //           Operand bytes through shared memory per FLOP drop by a third -- the single-CTA
 //           kernel is shared-memory-bandwidth bound (TMA writes + UMMA reads = 192 B/clk of the
 //           SM's 128 B/clk at full tensor rate; ncu: tensor pipe 66 % active, all barriers idle).
-template <int NCTA> struct Geo {
-  static constexpr int STAGES = NCTA == 2 ? 6 : 4;
-  static constexpr int A_STAGE_BYTES = BM * BK * 2;            // 16 KiB
-  static constexpr int B_ROWS = BN / NCTA;                     // n-rows of B staged by this CTA
-  static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;        // 32 / 16 KiB
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int BM_TILE = BM * NCTA;                    // output rows per tile
-};
-constexpr int OPERAND_BYTES = 4 * (BM * BK * 2 + BN * BK * 2);  // 192 KiB in both geometries
-static_assert(Geo<1>::STAGES * Geo<1>::STAGE_BYTES == OPERAND_BYTES, "operand ring size");
-static_assert(Geo<2>::STAGES * Geo<2>::STAGE_BYTES == OPERAND_BYTES, "operand ring size");
-constexpr int MAX_STAGES = 6;
+// EPI_RESID_LN streams the fp32 residual tile through the epilogue (TMA load -> add in place -> TMA
+// store, plus a bf16 copy): its warps own FOUR staging boxes (three fp32 boxes in a ring + one bf16
+// box) instead of two, paid for with one operand stage.
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = 2 * BN;                       // two accumulator stages (512 = all of TMEM)
 constexpr int BOX_ROWS = 32;
 constexpr int BOX_BYTES = BOX_ROWS * 64;                // 32 rows x 64 B (32 bf16 / 16 fp32 columns)
-constexpr int STG_WARP_BYTES = 2 * BOX_BYTES;           // two boxes per epilogue warp
-constexpr int OFF_STG = OPERAND_BYTES;                  // 1024-aligned
-constexpr int OFF_BIAS = OFF_STG + NUM_EPI_WARPS * STG_WARP_BYTES;
-constexpr int OFF_BARS = OFF_BIAS + 2 * BN * 4;         // bias tile, double buffered
-constexpr int SMEM_USED = OFF_BARS + 320;               // + barriers (32 x 8 B) and the TMEM slot
+constexpr int MAX_STAGES = 6;
+constexpr int LN_MAX_NT = 8;                            // partials per row of a folded LayerNorm
+constexpr int AUX_BARS = 3;                             // per epilogue warp (operand boxes in flight)
+constexpr int NUM_BARS = 2 * MAX_STAGES + 4 + AUX_BARS * NUM_EPI_WARPS;
+// FOLD (LayerNorm folded into the epilogue, gemm_api.h) also gives up one operand stage: an extra
+// warp stages the tile's folded-weight column sums and its rows' (-mean, rstd) in shared memory one
+// tile ahead of the epilogue warps.
+template <int NCTA, int MODE, bool FOLD = false> struct Geo {
+  static constexpr bool RESID = MODE == EPI_RESID_LN;
+  static constexpr int STAGES = NCTA == 2 ? ((RESID || FOLD) ? 5 : 6) : ((RESID || FOLD) ? 3 : 4);
+  static constexpr int A_STAGE_BYTES = BM * BK * 2;            // 16 KiB
+  static constexpr int B_ROWS = BN / NCTA;                     // n-rows of B staged by this CTA
+  static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;        // 32 / 16 KiB
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int BM_TILE = BM * NCTA;                    // output rows per tile
+  static constexpr int OPERAND_BYTES = STAGES * STAGE_BYTES;   // 192 KiB (RESID: 160 / 144 KiB)
+  static constexpr int BOXES = RESID ? 4 : 2;                  // staging boxes per epilogue warp
+  static constexpr int STG_WARP_BYTES = BOXES * BOX_BYTES;
+  static constexpr int OFF_STG = OPERAND_BYTES;                // 1024-aligned
+  static constexpr int OFF_BIAS = OFF_STG + NUM_EPI_WARPS * STG_WARP_BYTES;
+  static constexpr int OFF_CW = OFF_BIAS + 2 * BN * 4;         // bias tile, double buffered
+  static constexpr int OFF_ROWST = OFF_CW + (FOLD ? 2 * BN * 4 : 0);     // FOLD: column sums [2][BN]
+  static constexpr int OFF_BARS = OFF_ROWST + (FOLD ? 2 * BM * 8 : 0);   // FOLD: (-mean, rstd) [2][BM]
+  static constexpr int SMEM_USED = OFF_BARS + NUM_BARS * 8 + 16;  // + barriers and the TMEM slot
+  static_assert(OFF_STG % 1024 == 0, "staging boxes must stay aligned for the swizzle pattern");
+};
 constexpr int SMEM_BYTES = 227 * 1024;                  // everything an SM has; the kernel checks
                                                         // that SMEM_USED fits behind the 1024-byte
                                                         // alignment of the dynamic window
-static_assert(OFF_STG % 1024 == 0, "staging boxes must stay aligned for the swizzle pattern");
-static_assert(SMEM_USED <= SMEM_BYTES, "shared memory budget exceeded");
+static_assert(Geo<1, EPI_STORE>::OPERAND_BYTES == 192 * 1024 && Geo<2, EPI_STORE>::OPERAND_BYTES == 192 * 1024,
+              "operand ring size");
+static_assert(Geo<1, EPI_STORE>::SMEM_USED <= SMEM_BYTES && Geo<2, EPI_RESID_LN>::SMEM_USED <= SMEM_BYTES &&
+              Geo<1, EPI_RESID_LN>::SMEM_USED <= SMEM_BYTES && Geo<1, EPI_STORE, true>::SMEM_USED <= SMEM_BYTES &&
+              Geo<2, EPI_STORE, true>::SMEM_USED <= SMEM_BYTES, "shared memory budget exceeded");
 
 // sigmoid(1.702 z) = 0.5 tanh(0.851 z) + 0.5: ONE MUFU op (tanh.approx, rel. error ~2^-11, far
 // below bf16 resolution) instead of ex2 + rcp -- the GELU epilogues are MUFU-bound otherwise.
@@ -123,16 +138,21 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // MODE: GemmEpiMode; OBF: outputs (and the dGELU operand) are bf16, else fp32; NCTA: CTAs per
 // tile (2 = cta_group::2 pair, launched as a cluster of 2; not used for batched problems).
-// tma_c0: `out`; tma_c1: `out2` (QUICKGELU) or `aux` (DGELU).  Both are 4-D maps
-// (columns, rows, batch % out_hdiv, batch / out_hdiv) with a [32 x 64 B] box.
-template <int MODE, bool OBF, int NCTA>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// tma_c0: `out`; tma_c1: `out2` (QUICKGELU, RESID_LN) or `aux` (DGELU); tma_c2: the fp32 `aux` of
+// RESID_LN.  All are 4-D maps (columns, rows, batch % out_hdiv, batch / out_hdiv) with a
+// [32 x 64 B] box.
+template <int MODE, bool OBF, int NCTA, bool FOLD = false>
+__global__ void __launch_bounds__(NUM_THREADS + (FOLD ? 32 : 0), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                          const __grid_constant__ CUtensorMap tma_b,
                          const __grid_constant__ CUtensorMap tma_c0,
-                         const __grid_constant__ CUtensorMap tma_c1, const GemmProblem p,
+                         const __grid_constant__ CUtensorMap tma_c1,
+                         const __grid_constant__ CUtensorMap tma_c2, const GemmProblem p,
                          const GemmEpilogue e) {
-  using G = Geo<NCTA>;
+  static_assert(!FOLD || ((MODE == EPI_STORE || MODE == EPI_QUICKGELU) && OBF), "FOLD: bf16 STORE / QUICKGELU");
+  using G = Geo<NCTA, MODE, FOLD>;
+  constexpr int OFF_STG = G::OFF_STG, OFF_BIAS = G::OFF_BIAS, OFF_BARS = G::OFF_BARS;
+  constexpr int SMEM_USED = G::SMEM_USED, STG_WARP_BYTES = G::STG_WARP_BYTES;
   constexpr int STAGES = G::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles and staging boxes need 1024-byte alignment.
@@ -145,8 +165,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   uint64_t* empty_bar = bars + MAX_STAGES;           // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * MAX_STAGES;       // [2]       MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;  // [2]       epilogue -> MMA (pair: the leader's)
-  uint64_t* aux_bar = bars + 2 * MAX_STAGES + 4;     // [NUM_EPI_WARPS][2] dGELU operand box landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4 + 2 * NUM_EPI_WARPS);
+  uint64_t* aux_bar = bars + 2 * MAX_STAGES + 4;     // [NUM_EPI_WARPS][AUX_BARS] operand box landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
   if (threadIdx.x == 0 && (smem - smem_raw) + SMEM_USED > SMEM_BYTES) {
     printf("mmu: dynamic shared memory window is not 1024-byte aligned (offset %d)\n",
            static_cast<int>(smem - smem_raw));
@@ -172,7 +192,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     ptx::prefetch_tmap(&tma_a);
     ptx::prefetch_tmap(&tma_b);
     ptx::prefetch_tmap(&tma_c0);
-    if (MODE == EPI_QUICKGELU || MODE == EPI_DGELU) ptx::prefetch_tmap(&tma_c1);
+    if (MODE == EPI_QUICKGELU || MODE == EPI_DGELU || MODE == EPI_RESID_LN) ptx::prefetch_tmap(&tma_c1);
+    if (MODE == EPI_RESID_LN) ptx::prefetch_tmap(&tma_c2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -183,7 +204,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], NCTA * NUM_EPI_WARPS);  // pair: both CTAs' epilogue warps
     }
-    for (int i = 0; i < 2 * NUM_EPI_WARPS; ++i) ptx::mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < AUX_BARS * NUM_EPI_WARPS; ++i) ptx::mbar_init(&aux_bar[i], 1);
     ptx::fence_mbar_init();
     ptx::fence_proxy_async();
   }
@@ -329,6 +350,44 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (FOLD && warp == 2 + NUM_EPI_WARPS) {
+    // ------------------------------------------- LN fold: statistics / column-sum staging warp
+    // Runs one tile ahead of the epilogue warps and joins their per-tile barrier: buffer `as` of
+    // tile i is written before barrier i; the loads of tile i + 1 overlap the epilogue of tile i.
+    float* cw_s = reinterpret_cast<float*>(smem + G::OFF_CW);
+    float2* rowst_s = reinterpret_cast<float2*>(smem + G::OFF_ROWST);
+    int as = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int mn = (tile % mn_total) % (m_tiles * n_tiles);
+      const int nt0 = (mn % n_tiles) * BN;
+      const int mrow0 = (mn / n_tiles) * G::BM_TILE + rank * BM;
+      float2 st[BM / 32];
+#pragma unroll
+      for (int rr = 0; rr < BM / 32; ++rr) {
+        const int row = min(mrow0 + rr * 32 + lane, p.M - 1);
+        const float2* part = reinterpret_cast<const float2*>(e.ln_stats) + static_cast<long long>(row) * e.ln_nt;
+        float s1 = 0.f, s2 = 0.f;
+        for (int j = 0; j < e.ln_nt; ++j) {
+          const float2 t = __ldg(part + j);
+          s1 += t.x;
+          s2 += t.y;
+        }
+        const float mean = s1 * e.ln_inv_d;
+        st[rr] = make_float2(-mean, rsqrtf(fmaxf(fmaf(s2, e.ln_inv_d, -mean * mean), 0.f) + e.ln_eps));
+      }
+      float cwv[BN / 32];
+#pragma unroll
+      for (int j = 0; j < BN / 32; ++j) {
+        const int col = nt0 + j * 32 + lane;
+        cwv[j] = col < p.N ? __ldg(e.ln_cw + col) : 0.f;
+      }
+#pragma unroll
+      for (int rr = 0; rr < BM / 32; ++rr) rowst_s[as * BM + rr * 32 + lane] = st[rr];
+#pragma unroll
+      for (int j = 0; j < BN / 32; ++j) cw_s[as * BN + j * 32 + lane] = cwv[j];
+      named_bar_sync(1, NUM_EPI_THREADS + 32);
+      as ^= 1;
+    }
   } else {
     // ---------------------------------------------------------------- epilogue
     const int we = warp - 2;         // 0..7
@@ -344,9 +403,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     const bool has_bias = e.bias != nullptr;
     constexpr int NCOL = OBF ? 32 : 16;         // columns per chunk = per staging box
     constexpr int NCHUNK = BN / 2 / NCOL;
-    uint64_t* my_aux = aux_bar + 2 * we;
+    uint64_t* my_aux = aux_bar + AUX_BARS * we;
     int as = 0;
-    uint32_t aphase = 0, aux_phase[2] = {0, 0};
+    uint32_t aphase = 0, aux_phase[AUX_BARS] = {0, 0, 0};
+    constexpr bool fold = FOLD;  // LayerNorm folded into this GEMM (gemm_api.h)
+    const uint32_t cw_addr = ptx::smem_u32(smem + G::OFF_CW);
+    const float2* rowst_s = reinterpret_cast<const float2*>(smem + G::OFF_ROWST);
     auto release_tmem = [&](int stage_idx) {  // one arrival per epilogue warp per tile
       ptx::tc_fence_before();
       __syncwarp();
@@ -371,7 +433,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         const int col = nt0 + et;
         bias_s[as * BN + et] = col < p.N ? e.bias[col] : 0.f;
       }
-      named_bar_sync(1, NUM_EPI_THREADS);
+      named_bar_sync(1, NUM_EPI_THREADS + (FOLD ? 32 : 0));
+
+      // LN fold: this lane's row statistics (lane = row), staged by the statistics warp
+      float ln_nmean = 0.f, ln_rstd = 1.f;
+      if constexpr (fold) {
+        const float2 t = rowst_s[as * BM + q * 32 + lane];
+        ln_nmean = t.x;
+        ln_rstd = t.y;
+      }
 
       // dGELU: the z boxes of the first two chunks start loading while the MMAs of the tile run
       auto load_z = [&](int c) {  // lane 0 only; box (c & 1) must be drained
@@ -383,6 +453,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         load_z(0);
         if (n0 + NCOL < p.N) load_z(1);
       }
+      // RESID_LN: the fp32 residual boxes of the first two chunks (ring of three boxes: chunk c
+      // lives in box c % 3, is updated in place and stored from there; box 3 takes the bf16 copy)
+      auto load_x = [&](int c) {  // lane 0 only; box c % 3 must be drained
+        ptx::mbar_arrive_expect_tx(&my_aux[c % 3], BOX_BYTES);
+        ptx::tma_load_4d(box0 + (c % 3) * BOX_BYTES, &tma_c2, &my_aux[c % 3], n0 + c * NCOL, m0, c2, c3);
+      };
+      if (MODE == EPI_RESID_LN && active && lane == 0) {
+        ptx::bulk_wait_read<0>();
+        load_x(0);
+        if (n0 + NCOL < p.N) load_x(1);
+      }
+      float st_s1 = 0.f, st_s2 = 0.f;  // RESID_LN: this lane's row sums over the warp's 128 columns
 
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
@@ -507,14 +589,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
           float v[NCOL];
           {
             const uint32_t baddr = bias_addr + static_cast<uint32_t>(as * BN + h * (BN / 2) + c * NCOL) * 4u;
+            if constexpr (fold) {
+              // out = rstd * (acc - mean * cw[n]) + bias'[n]  (alpha == 1, checked on the host)
 #pragma unroll
-            for (int j = 0; j < NCOL / 4; ++j) {
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (has_bias) b4 = ptx::lds_v4(baddr + 16 * j);
-              v[4 * j + 0] = fmaf(__uint_as_float(r[c & 1][4 * j + 0]), e.alpha, b4.x);
-              v[4 * j + 1] = fmaf(__uint_as_float(r[c & 1][4 * j + 1]), e.alpha, b4.y);
-              v[4 * j + 2] = fmaf(__uint_as_float(r[c & 1][4 * j + 2]), e.alpha, b4.z);
-              v[4 * j + 3] = fmaf(__uint_as_float(r[c & 1][4 * j + 3]), e.alpha, b4.w);
+              for (int j = 0; j < NCOL / 4; ++j) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_bias) b4 = ptx::lds_v4(baddr + 16 * j);
+                // columns >= N are clipped by the store: any in-range address will do for them
+                const float4 w4 = ptx::lds_v4(cw_addr + (baddr - bias_addr) + 16 * j);
+                v[4 * j + 0] = fmaf(fmaf(ln_nmean, w4.x, __uint_as_float(r[c & 1][4 * j + 0])), ln_rstd, b4.x);
+                v[4 * j + 1] = fmaf(fmaf(ln_nmean, w4.y, __uint_as_float(r[c & 1][4 * j + 1])), ln_rstd, b4.y);
+                v[4 * j + 2] = fmaf(fmaf(ln_nmean, w4.z, __uint_as_float(r[c & 1][4 * j + 2])), ln_rstd, b4.z);
+                v[4 * j + 3] = fmaf(fmaf(ln_nmean, w4.w, __uint_as_float(r[c & 1][4 * j + 3])), ln_rstd, b4.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < NCOL / 4; ++j) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_bias) b4 = ptx::lds_v4(baddr + 16 * j);
+                v[4 * j + 0] = fmaf(__uint_as_float(r[c & 1][4 * j + 0]), e.alpha, b4.x);
+                v[4 * j + 1] = fmaf(__uint_as_float(r[c & 1][4 * j + 1]), e.alpha, b4.y);
+                v[4 * j + 2] = fmaf(__uint_as_float(r[c & 1][4 * j + 2]), e.alpha, b4.z);
+                v[4 * j + 3] = fmaf(__uint_as_float(r[c & 1][4 * j + 3]), e.alpha, b4.w);
+              }
             }
           }
           const uint32_t box = box0 + static_cast<uint32_t>(c & 1) * BOX_BYTES;
@@ -530,7 +627,47 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
               for (int i = 0; i < NCOL; ++i) v[i] *= e.drop.mult(ibase + i);
             }
           }
-          if constexpr (!OBF) {
+          if constexpr (MODE == EPI_RESID_LN) {
+            const uint32_t fb = box0 + static_cast<uint32_t>(c % 3) * BOX_BYTES;
+            ptx::mbar_wait(&my_aux[c % 3], aux_phase[c % 3]);
+            aux_phase[c % 3] ^= 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t a = fb + piece(k);
+              const float4 x4 = ptx::lds_v4(a);
+              v[4 * k + 0] += x4.x;
+              v[4 * k + 1] += x4.y;
+              v[4 * k + 2] += x4.z;
+              v[4 * k + 3] += x4.w;
+              ptx::sts_v4(a, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+            }
+#pragma unroll
+            for (int i = 0; i < NCOL; ++i) {
+              st_s1 += v[i];
+              st_s2 = fmaf(v[i], v[i], st_s2);
+            }
+            box_store(&tma_c0, fb, col0);
+            if (e.out2 != nullptr) {
+              // bf16 copy: two 16-column chunks share one [32 x 64 B] box (pieces 0-1 / 2-3)
+              const uint32_t hb = box0 + 3u * BOX_BYTES;
+              if ((c & 1) == 0) {  // the store of the previous pair has read the box
+                if (lane == 0) ptx::bulk_wait_read<1>();  // (only the fp32 store above may be pending)
+                __syncwarp();
+              }
+              ptx::sts_v4u(hb + piece(2 * (c & 1)), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                           pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              ptx::sts_v4u(hb + piece(2 * (c & 1) + 1), pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                           pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+              if ((c & 1) == 1 || col0 + NCOL >= p.N) box_store(&tma_c1, hb, col0 - (c & 1) * NCOL);
+            }
+            // refill: chunk c + 2 goes to the box chunk c - 1 was stored from; at most its bf16
+            // store and this chunk's two stores were committed after that one
+            if (c + 2 < NCHUNK && col0 + 2 * NCOL < p.N && lane == 0) {
+              if (e.out2 != nullptr) ptx::bulk_wait_read<2>();
+              else ptx::bulk_wait_read<1>();
+              load_x(c + 2);
+            }
+          } else if constexpr (!OBF) {
             box_free(c == 0);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -601,6 +738,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
         }
       }
       if (!active) release_tmem(as);  // nothing to read: still one arrival per warp per tile
+      if (MODE == EPI_RESID_LN && active && e.stats_out != nullptr && m0 + lane < p.M)
+        reinterpret_cast<float2*>(e.stats_out)[static_cast<long long>(m0 + lane) * e.stats_nt + n0 / (BN / 2)] =
+            make_float2(st_s1, st_s2);
       }  // MODE != EPI_SOFTMAX
       if (++as == 2) { as = 0; aphase ^= 1; }
     }

@@ -34,6 +34,17 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y
 int layernorm2_fwd(const float* x, const float* g1, const float* b1, float* y1, float* mean1,
                    float* rstd1, const float* g2, const float* b2, void* y2, int y2_dtype,
                    float* mean2, float* rstd2, int M, int D, cudaStream_t stream);
+// Eval path with LayerNorm folded into the consumer GEMM (gemm_api.h: GemmEpilogue::ln_stats):
+// y (fp32) = LN(x; gamma, beta), yraw = bf16(y) (RAW rows, the consumer's A operand),
+// stats[row][nt][2]: (sum, sum of squares) of y in partial 0, zeros in partials 1..nt-1.
+int layernorm_raw_stats_fwd(const float* x, const float* gamma, const float* beta, float* y,
+                            void* yraw_bf16, float* stats, int nt, int M, int D, cudaStream_t stream);
+// Folded weights of up to two Linears that consume LayerNorm output (N1 == 0: one):
+// Wf = bf16(W diag(gamma)) [N][K], cw[n] = sum_k Wf[n][k], bf[n] = bias[n] + sum_k beta[k] W[n][k].
+int ln_fold_weights(const float* W0, const float* gamma0, const float* beta0, const float* bias0,
+                    void* Wf0, float* cw0, float* bf0, int N0, const float* W1, const float* gamma1,
+                    const float* beta1, const float* bias1, void* Wf1, float* cw1, float* bf1, int N1,
+                    int K, cudaStream_t stream);
 // x_out = x_in + y (y and h in `dtype`); h = LN(x_out) unless gamma == nullptr (sum only).
 int add_layernorm_fwd(const float* x_in, const void* y, float* x_out, const float* gamma,
                       const float* beta, void* h, int dtype, float* mean, float* rstd, int M, int D,

@@ -247,6 +247,92 @@ layernorm2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ g1,
   }
 }
 
+// Eval path with LayerNorm folded into the consumer GEMM (gemm_api.h, ln_stats): y = LN(x; g, b)
+// in fp32 (the residual stream after ln_pre), a RAW bf16 copy of y (the next GEMM's A operand) and
+// the row's (sum, sum of squares) in partial slot 0 of stats[row][nt][2] (slots 1.. zeroed).
+template <int NV>
+__global__ void __launch_bounds__(THREADS)
+layernorm_raw_stats_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                           const float* __restrict__ b, float* __restrict__ y,
+                           __nv_bfloat16* __restrict__ yraw, float* __restrict__ stats, int nt, int M,
+                           int D) {
+  ptx::pdl_trigger();  // a following tensor-core GEMM may start its prologue early
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D >> 2;
+  for (int row = blockIdx.x * WARPS + warp; row < M; row += gridDim.x * WARPS) {
+    RowRegs<NV> r;
+    r.load(x + static_cast<size_t>(row) * D, nvec, lane);
+    float mean, rstd;
+    row_stats<NV>(r, nvec, lane, D, mean, rstd);
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 gg = *reinterpret_cast<const float4*>(g + 4 * c);
+        const float4 bb = *reinterpret_cast<const float4*>(b + 4 * c);
+        float4& v = r.v[i];
+        v.x = (v.x - mean) * rstd * gg.x + bb.x;
+        v.y = (v.y - mean) * rstd * gg.y + bb.y;
+        v.z = (v.z - mean) * rstd * gg.z + bb.z;
+        v.w = (v.w - mean) * rstd * gg.w + bb.w;
+        *reinterpret_cast<float4*>(y + static_cast<size_t>(row) * D + 4 * c) = v;
+        Vec4<__nv_bfloat16>::st(yraw + static_cast<size_t>(row) * D + 4 * c, v);
+        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      }
+    }
+    const float s1 = warp_sum(r.sum());
+    s2 = warp_sum(s2);
+    if (lane < nt) {
+      float2 o = make_float2(0.f, 0.f);
+      if (lane == 0) o = make_float2(s1, s2);
+      reinterpret_cast<float2*>(stats)[static_cast<size_t>(row) * nt + lane] = o;
+    }
+  }
+}
+
+// Weights of a Linear that consumes LayerNorm output, folded for the LN-in-the-epilogue GEMM:
+//   Wf[n][k] = bf16(W[n][k] * gamma[k]);  cw[n] = sum_k float(Wf[n][k]);
+//   bf[n] = bias[n] + sum_k beta[k] * W[n][k]
+// so that  LN(x) W^T + bias = rstd * (x Wf^T - mean * cw) + bf.   One warp per output row n;
+// blockIdx.y selects one of two (W, gamma, beta, bias) sets (in_proj with ln_1, c_fc with ln_2).
+struct FoldSet {
+  const float* W; const float* gamma; const float* beta; const float* bias;
+  __nv_bfloat16* Wf; float* cw; float* bf;
+  int N;
+};
+__global__ void __launch_bounds__(256)
+ln_fold_weights_kernel(FoldSet s0, FoldSet s1, int K) {
+  const FoldSet s = blockIdx.y == 0 ? s0 : s1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kv = K >> 2;
+  for (int n = blockIdx.x * 8 + warp; n < s.N; n += gridDim.x * 8) {
+    const float* w = s.W + static_cast<size_t>(n) * K;
+    float acc_w = 0.f, acc_b = 0.f;
+    for (int c = lane; c < kv; c += 32) {
+      const float4 wv = *reinterpret_cast<const float4*>(w + 4 * c);
+      const float4 g = *reinterpret_cast<const float4*>(s.gamma + 4 * c);
+      const float4 b = *reinterpret_cast<const float4*>(s.beta + 4 * c);
+      const __nv_bfloat16 f0 = __float2bfloat16_rn(wv.x * g.x), f1 = __float2bfloat16_rn(wv.y * g.y),
+                          f2 = __float2bfloat16_rn(wv.z * g.z), f3 = __float2bfloat16_rn(wv.w * g.w);
+      __nv_bfloat162 lo, hi;
+      lo.x = f0; lo.y = f1; hi.x = f2; hi.y = f3;
+      uint2 packed;
+      packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+      packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(s.Wf + static_cast<size_t>(n) * K + 4 * c) = packed;
+      acc_w += (__bfloat162float(f0) + __bfloat162float(f1)) + (__bfloat162float(f2) + __bfloat162float(f3));
+      acc_b += (wv.x * b.x + wv.y * b.y) + (wv.z * b.z + wv.w * b.w);
+    }
+    acc_w = warp_sum(acc_w);
+    acc_b = warp_sum(acc_b);
+    if (lane == 0) {
+      s.cw[n] = acc_w;
+      s.bf[n] = (s.bias != nullptr ? s.bias[n] : 0.f) + acc_b;
+    }
+  }
+}
+
 // x_out = x_in + y (branch output of the preceding projection GEMM, stored in the activation
 // dtype); h = LayerNorm(x_out).  Fusing the residual add here keeps the GEMM epilogues free of the
 // fp32 residual-stream traffic (a streaming row kernel moves those bytes at ~HBM peak; a GEMM
@@ -1034,6 +1120,32 @@ int layernorm2_fwd(const float* x, const float* g1, const float* b1, float* y1, 
                             x, g1, b1, y1, mean1, rstd1, g2, b2, static_cast<float*>(y2), mean2,
                             rstd2, M, D)));
   }
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int layernorm_raw_stats_fwd(const float* x, const float* gamma, const float* beta, float* y,
+                            void* yraw_bf16, float* stats, int nt, int M, int D, cudaStream_t stream) {
+  const int nv = nv_for(D);
+  if (nv < 0 || nt < 1 || nt > 32) return MMU_ERR_SHAPE;
+  if (M <= 0) return 0;
+  const int grid = grid_for(M, WARPS);
+  MMU_NV_DISPATCH(nv, (layernorm_raw_stats_kernel<NV><<<grid, THREADS, 0, stream>>>(
+                          x, gamma, beta, y, static_cast<__nv_bfloat16*>(yraw_bf16), stats, nt, M, D)));
+  MMU_CHECK_LAUNCH();
+  return 0;
+}
+
+int ln_fold_weights(const float* W0, const float* gamma0, const float* beta0, const float* bias0,
+                    void* Wf0, float* cw0, float* bf0, int N0, const float* W1, const float* gamma1,
+                    const float* beta1, const float* bias1, void* Wf1, float* cw1, float* bf1, int N1,
+                    int K, cudaStream_t stream) {
+  if (K % 4 != 0 || N0 < 1 || N1 < 0) return MMU_ERR_SHAPE;
+  FoldSet s0{W0, gamma0, beta0, bias0, static_cast<__nv_bfloat16*>(Wf0), cw0, bf0, N0};
+  FoldSet s1{W1, gamma1, beta1, bias1, static_cast<__nv_bfloat16*>(Wf1), cw1, bf1, N1};
+  const int nmax = N0 > N1 ? N0 : N1;
+  dim3 grid((nmax + 7) / 8, N1 > 0 ? 2 : 1);
+  ln_fold_weights_kernel<<<grid, 256, 0, stream>>>(s0, s1, K);
   MMU_CHECK_LAUNCH();
   return 0;
 }
