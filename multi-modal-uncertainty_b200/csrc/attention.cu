@@ -840,8 +840,12 @@ int seq_attention_bwd(const void* qkv, const void* dout, const void* probs, floa
 }
 
 int attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* scores, int dtype,
-                  int B, int L, int D, int H, cudaStream_t stream, int pos_major) {
+                  int B, int L, int D, int H, cudaStream_t stream, int pos_major, int keep_probs) {
   using namespace attn;
+  if (dtype == DT_BF16 && qkv != nullptr && out != nullptr && (!keep_probs || probs != nullptr)) {
+    const int rc = fused_batch_attention_fwd(qkv, out, keep_probs ? probs : nullptr, B, L, D, H, pos_major, stream);
+    if (rc <= 0) return rc;
+  }
   if (tc::eligible(dtype, B, D, H, probs, scores))
     return tc::fwd(qkv, out, probs, scores, B, L, D, H, pos_major, stream);
   if (lse == nullptr) return MMU_ERR_ARG;

@@ -148,7 +148,8 @@ int mmu_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float*
 int mmu_batchaxis_attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* scores,
                                 int dtype, int B, int L, int D, int H, int pos_major, void* stream) {
   if (qkv == nullptr || out == nullptr) return MMU_ERR_ARG;
-  return attention_fwd(qkv, out, lse, probs, scores, dtype, B, L, D, H, S(stream), pos_major != 0);
+  return attention_fwd(qkv, out, lse, probs, scores, dtype, B, L, D, H, S(stream), (pos_major & 1) != 0,
+                       (pos_major & 2) == 0);
 }
 
 int mmu_batchaxis_attention_bwd(const void* qkv, const void* out, const void* dout,

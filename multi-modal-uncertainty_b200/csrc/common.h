@@ -28,4 +28,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, long long inner, long 
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, long long inner, long long mid,
                       long long outer, long long mid_stride, long long outer_stride, int box_inner,
                       int box_outer);
+// 4-D output / epilogue-operand map (columns, rows, batch % hdiv, batch / hdiv) with a
+// [32 rows x 64 B] SWIZZLE_64B box (gemm_tcgen05.cu); stores clip at the extents, loads zero-fill
+int make_tmap_out_4d(CUtensorMap* out, const void* base, int is_bf16, long long cols, long long rows,
+                     long long ld, long long hdiv, long long hstride, long long nmid,
+                     long long mid_stride);
 }  // namespace mmu

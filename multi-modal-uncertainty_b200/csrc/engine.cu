@@ -478,7 +478,7 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
       const bool last = i + 1 == c.n_layers;
       MMU_TRY(gemm(l.h1, D, 0, f.in_wf, D, 0, M, 3 * D, D,
                    folded(epi(EPI_STORE, l.qkv, 1, 3 * D, f.in_bf), w.fold_stats[0], f.in_cw)));
-      MMU_TRY(attention_fwd(l.qkv, l.o, l.lse, l.probs, w.scores, dt, c.B, s.L, D, c.n_head, stream, 1));
+      MMU_TRY(attention_fwd(l.qkv, l.o, l.lse, l.probs, w.scores, dt, c.B, s.L, D, c.n_head, stream, 1, 0));
       MMU_TRY(gemm(l.o, D, 0, W(p.out_w), D, 0, M, D, D,
                    resid(x, l.x1, l.h2, w.fold_stats[1], params + p.out_b)));
       {

@@ -125,8 +125,15 @@ int split_rows(const float* dmm, void* dimg, void* dtxt, int dtype, int B, int L
 // pos_major = 0: rows of qkv / out are (sample b, position l) -> b*L + l; 1: (position, sample) ->
 // l*B + b, the engine's layout: the 128 rows of one (position, head) problem are then ADJACENT in
 // memory (a contiguous B x 3D block per position) instead of L*3D elements apart.
+// bf16, head_dim 256, B <= 128 runs ONE fused kernel (battn_fused.cu); keep_probs = 0 (eval: no
+// backward will read the probabilities) leaves `probs` untouched.
 int attention_fwd(const void* qkv, void* out, float* lse, void* probs, float* scores, int dtype,
-                  int B, int L, int D, int H, cudaStream_t stream, int pos_major = 0);
+                  int B, int L, int D, int H, cudaStream_t stream, int pos_major = 0,
+                  int keep_probs = 1);
+// the fused kernel itself: 0 launched, > 0 not applicable, < 0 error; probs (bf16 [L*H][B][Bp]) may
+// be null (eval)
+int fused_batch_attention_fwd(const void* qkv, void* out, void* probs, int B, int L, int D, int H,
+                              int pos_major, cudaStream_t stream);
 int attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                   float* delta_ws, const void* probs, float* scores, void* dprobs, void* dqkv,
                   int dtype, int B, int L, int D, int H, cudaStream_t stream, int pos_major = 0);

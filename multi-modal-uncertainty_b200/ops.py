@@ -100,17 +100,20 @@ def _tc_attention(qkv, D, H):
     return qkv.dtype == torch.bfloat16 and (D // H) % 64 == 0
 
 
-def attention_fwd(qkv, B, L, D, H, pos_major=False):
+def attention_fwd(qkv, B, L, D, H, pos_major=False, keep_probs=True):
     """Returns (out, saved): saved = lse (SIMT path) or the bf16 probabilities (tensor-core path).
-    Rows of ``qkv`` / ``out``: ``b*L + l``, or ``l*B + b`` with ``pos_major``."""
+    Rows of ``qkv`` / ``out``: ``b*L + l``, or ``l*B + b`` with ``pos_major``.
+    ``keep_probs=False`` (eval: no backward follows) lets bf16 problems with head_dim 256 and
+    B <= 128 run as ONE fused kernel; ``saved`` is then not written."""
     _cuda(qkv)
     out = torch.empty(B * L, D, device=qkv.device, dtype=qkv.dtype)
     if _tc_attention(qkv, D, H):
         Bp = (B + 7) // 8 * 8
         probs = torch.empty(L * H, B, Bp, device=qkv.device, dtype=torch.bfloat16)
         scores = torch.empty(L * H, B, Bp, device=qkv.device, dtype=torch.float32)
+        flags = int(bool(pos_major)) | (0 if keep_probs else 2)
         check(lib.mmu_batchaxis_attention_fwd(ptr(qkv), ptr(out), 0, ptr(probs), ptr(scores),
-                                              _dt(qkv), B, L, D, H, int(pos_major), stream_ptr()),
+                                              _dt(qkv), B, L, D, H, flags, stream_ptr()),
               "mmu_batchaxis_attention_fwd")
         return out, probs
     lse = torch.empty(L * H * B, device=qkv.device, dtype=torch.float32)

@@ -184,6 +184,31 @@ def test_batch_axis_attention(mmu, dtype, tol, B, L, D, H):
     assert torch.equal(dqkv_p.cpu(), pm(dqkv.cpu()))
 
 
+@pytest.mark.parametrize("B,L,D,H", [(128, 5, 768, 3), (100, 3, 768, 3), (37, 4, 512, 2), (128, 160, 768, 3),
+                                     (8, 2, 256, 1)])
+def test_fused_batch_axis_attention_eval(mmu, B, L, D, H, measured):
+    """The fused eval kernel (head_dim 256, B <= 128; keep_probs=False) against the oracle and
+    against the two-kernel path, in both row orders; rows / keys beyond B are padding inside the
+    kernel and must not leak into the result."""
+    hd = D // H
+    qkv = rnd(B * L, 3 * D, seed=3).to(torch.bfloat16)
+    t = qkv.double().view(B, L, 3, H, hd)
+    qq, kk, vv = (t[:, :, i].permute(1, 2, 0, 3) for i in range(3))  # (L, H, B, hd)
+    o = (torch.softmax((qq / math.sqrt(hd)) @ kk.transpose(-1, -2), -1) @ vv).permute(2, 0, 1, 3).reshape(B * L, D)
+    two, _ = mmu.ops.attention_fwd(qkv.cuda(), B, L, D, H)
+    fused, _ = mmu.ops.attention_fwd(qkv.cuda(), B, L, D, H, keep_probs=False)
+    err = rel(fused.float().cpu(), o)
+    measured("battn_fused/bf16/out", err)
+    assert err < 1.5e-2 and rel(two.float().cpu(), o) < 1.5e-2
+    assert rel(fused.float().cpu(), two.float().cpu()) < 1.5e-2
+
+    def pm(x):
+        return x.view(B, L, -1).transpose(0, 1).reshape(L * B, -1).contiguous()
+
+    fused_p, _ = mmu.ops.attention_fwd(pm(qkv).cuda(), B, L, D, H, pos_major=True, keep_probs=False)
+    assert torch.equal(fused_p.cpu(), pm(fused.cpu()))  # same problems, other strides: bit-identical
+
+
 @pytest.mark.parametrize("N,E,C", [(500, 5, 101), (37, 2, 2), (64, 4, 10), (1001, 1, 101), (33, 3, 300)])
 def test_uncertainty_epilogue(mmu, N, E, C):
     from oracle import fusion, uncertainty

@@ -1,10 +1,5 @@
 mkdir -p gpurun_out
-set -x
-CMD="python bench.py --steps 1 --warmup 1 --profile"
-$CMD > gpurun_out/r2d_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/r2d_launches.csv $CMD > gpurun_out/r2d_ncu_list.log 2>&1
-for c in 27 28 29 30; do
-./build/gemm_harness $c > gpurun_out/r2d_harness_plain_$c.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tcgen05 -s 2 -c 1 -o gpurun_out/r2d_gemm_case$c ./build/gemm_harness $c > gpurun_out/r2d_ncu_case$c.log 2>&1
-done
-ls -la gpurun_out/ | grep r2d
+( time python -m pytest tests -m gpu -x -q ) > gpurun_out/r2f_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/r2f_pytest_gpu.log
+python tools/step_timeline.py 5 > gpurun_out/r2f_timeline.json 2> gpurun_out/r2f_timeline.err; echo "exit $?"; tail -1 gpurun_out/r2f_timeline.err
+python bench.py > gpurun_out/r2f_bench.json 2> gpurun_out/r2f_bench.err; echo "bench exit $?"; head -c 300 gpurun_out/r2f_bench.json; echo
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2f_smoke.log 2>&1; echo "smoke exit $?"; tail -3 gpurun_out/r2f_smoke.log
