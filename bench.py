@@ -738,6 +738,45 @@ def measure_rooflines(mmu, dev, min_seconds=1.0):
             "note": "12 GEMM launches of one transformer block's fwd+bwd (M=30336), operands > L2; "
                     "traffic = average DRAM bytes per launch from the committed ncu capture under profiles/"}
 
+    # ---- the sweep's GEMMs: the four launches of one block's EVAL forward at the packed sweep's size
+    #      (in_proj / c_fc with the LayerNorm folded into the epilogue, out_proj / c_proj with the
+    #      residual-stream epilogue), in the same sustained state
+    del x768, x2304, x3072, o2304, o3072, o3072b, o768
+    Ms = B * sum(a + b for a, b in level_token_counts())
+    nt = (D + 127) // 128
+    raw = torch.randn(Ms, D, device=dev).to(bf)
+    xs = torch.randn(Ms, D, device=dev)
+    qkv = torch.empty(Ms, 3 * D, device=dev, dtype=bf)
+    u = torch.empty(Ms, 4 * D, device=dev, dtype=bf)
+    stats = torch.stack([xs.sum(1), (xs * xs).sum(1)], 1).reshape(Ms, 1, 2).repeat(1, nt, 1).contiguous() / nt
+    cw = {n: torch.zeros(n, device=dev) for n in (3 * D, 4 * D)}
+    xs2, raw2, stats2 = torch.empty_like(xs), torch.empty_like(raw), torch.empty_like(stats)
+
+    def eval_gemms():   # outputs go to separate buffers so that repetitions see the same inputs
+        g(raw, w[3 * D], out=qkv, bias=bias[3 * D], ln_fold=(stats, cw[3 * D], 1e-5))
+        g(raw, w[D], mode=E_.EPI_RESID_LN, out=xs2, out2=raw2, bias=bias[D], aux=xs, stats_out=stats2)
+        g(raw, w[4 * D], mode=E_.EPI_QUICKGELU, out2=u, bias=bias[4 * D], ln_fold=(stats, cw[4 * D], 1e-5))
+        g(u, w_proj, mode=E_.EPI_RESID_LN, out=xs2, out2=raw2, bias=bias[D], aux=xs, stats_out=stats2)
+
+    flops_eval = 2 * Ms * D * 3 * D + 2 * Ms * D * D + 2 * 2 * Ms * D * 4 * D
+    for _ in range(3):
+        eval_gemms()
+    torch.cuda.synchronize()
+    reps_e = max(20, int(0.5 * min_seconds * 1e3 / (flops_eval / 1.1e15 * 1e3)) + 1)
+    e0.record()
+    for _ in range(reps_e):
+        eval_gemms()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e = e0.elapsed_time(e1) / reps_e
+    tf_e = flops_eval / (ms_e * 1e-3) / 1e12
+    roof["eval_gemms"] = {
+        "achieved": round(tf_e, 1), "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+        "frac": round(tf_e / pk["tensor_sustained"], 3), "rows": Ms, "launches_per_rep": 4,
+        "ms_per_rep": round(ms_e, 3), "timed_seconds": round(ms_e * reps_e / 1e3, 2),
+        "note": "one block's eval forward at the packed 10-level sweep's size: in_proj / c_fc with ln_1 / ln_2 "
+                "folded into the epilogue, out_proj / c_proj adding the fp32 residual stream in theirs "
+                "(10 B/element of residual traffic ride inside these launches)"}
     return roof, hbm
 
 

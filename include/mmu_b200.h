@@ -50,6 +50,7 @@ extern "C" {
 #define MMU_EPI_RESIDUAL 2
 #define MMU_EPI_DGELU 3
 #define MMU_EPI_ATOMIC 4
+#define MMU_EPI_RESID_LN 6
 
 MMU_API const char* mmu_version(void);
 MMU_API const char* mmu_error_string(int code);
@@ -81,6 +82,15 @@ MMU_API int mmu_struct_size(int which);
  *              LayerNorm kernel that consumes the sum
  *   DGELU      out = alpha*acc * d/dz QuickGELU(z), z = aux (dtype)
  *   ATOMIC     out(fp32) += alpha*acc, split-K `splits` ways (weight gradients)
+ *   RESID_LN   (MMU_BF16 only; the eval path of src/model.py:209-212) out(fp32) = aux(fp32) + alpha*acc
+ *              + bias -- the residual stream; aux may alias out --, out2 (bf16, may be NULL) = the
+ *              same values rounded, i.e. the RAW rows the next GEMM consumes, stats_out (may be NULL)
+ *              [M][stats_nt][2] = (sum, sum of squares) of out over each 128-column slab
+ * LayerNorm FOLDED into the consumer (STORE / QUICKGELU, MMU_BF16, out_lp = 1): with ln_stats !=
+ * NULL, A holds raw rows x, B holds W diag(gamma) (mmu_ln_fold_weights), and
+ *   out = rstd_r (acc - mean_r ln_cw[n]) + bias[n],   mean_r, rstd_r from the ln_nt partial
+ *   (sum, sum of squares) pairs of row r (eps ln_eps, 1/D = ln_inv_d), ln_cw[n] = sum_k B[n][k],
+ *   bias = the folded bias of mmu_ln_fold_weights  =>  out = LayerNorm(x) W^T + b.
  * seg_len > 0 remaps output rows r -> (r/seg_len)*seg_stride + seg_off + r%seg_len, which writes
  * a per-modality projection straight into the concatenated sequence (fuses torch.cat :273). */
 typedef struct {
@@ -98,11 +108,30 @@ typedef struct {
   float drop_p;
   int drop_site;
   unsigned long long drop_seed;
+  /* LayerNorm folded into the epilogue (see above); ln_stats == NULL: off */
+  const float* ln_stats;
+  const float* ln_cw;
+  int ln_nt;
+  float ln_inv_d, ln_eps;
+  /* RESID_LN: per-slab row sums of out; NULL: not written.  stats_nt >= ceil(N / 128) */
+  int stats_nt;
+  float* stats_out;
 } mmu_gemm_epilogue;
 
 MMU_API int mmu_gemm(int dtype, const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
              int b_mn_major, int M, int N, int K, int splits, const mmu_gemm_epilogue* epi,
              void* stream);
+
+/* Companions of the folded-LayerNorm eval path.
+ * mmu_ln_fold_weights: Wf[n][k] = bf16(W[n][k] gamma[k]), cw[n] = sum_k Wf[n][k],
+ *   bf[n] = bias[n] + sum_k beta[k] W[n][k]   (W fp32 [N][K]; bias may be NULL).
+ * mmu_layernorm_raw_stats: y (fp32) = LayerNorm(x; gamma, beta) (eps 1e-5), yraw = bf16(y),
+ *   stats[row][nt][2] = (sum, sum of squares) of y in partial 0, zeros in partials 1..nt-1 -- the
+ *   ln_stats layout a following folded GEMM expects (ln_pre feeding the first block's ln_1). */
+MMU_API int mmu_ln_fold_weights(const float* W, const float* gamma, const float* beta, const float* bias,
+                                void* Wf_bf16, float* cw, float* bf, int N, int K, void* stream);
+MMU_API int mmu_layernorm_raw_stats(const float* x, const float* gamma, const float* beta, float* y,
+                                    void* yraw_bf16, float* stats, int nt, int M, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Input staging: token-subset gather + per-sample modality zero-fill + cast.
@@ -158,7 +187,10 @@ MMU_API int mmu_layernorm_bwd(const void* dy, int dy_dtype, const float* x, cons
  * GEMMs over the L*H (position, head) problems; probs: bf16 [L*H, B, Bp] written by the forward and
  * read by the backward, scores: fp32 scratch, dprobs: bf16 scratch of the same shape (Bp = B
  * rounded up to 8).  Otherwise (fp32, or NULL buffers): fp32 SIMT kernels, B <= 256, which need
- * lse fp32[L*H*B] (forward output) and delta_ws fp32[L*H*B]. */
+ * lse fp32[L*H*B] (forward output) and delta_ws fp32[L*H*B].
+ * The forward's `pos_major` argument is a flag word: bit 0 = position-major rows, bit 1 = the
+ * probabilities are not needed (eval).  bf16 with head_dim 256 and B <= 128 runs as ONE fused kernel
+ * (QK^T -> softmax -> PV on chip, csrc/battn_fused.cu); with bit 1 set `probs` is then not written. */
 MMU_API int mmu_batchaxis_attention_fwd(const void* qkv, void* out, float* lse, void* probs,
                                         float* scores, int dtype, int B, int L, int D, int H,
                                         int pos_major, void* stream);

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libmmu_b200.so")
 
 F32, BF16 = 0, 1
 EPI_STORE, EPI_QUICKGELU, EPI_RESIDUAL, EPI_DGELU, EPI_ATOMIC = 0, 1, 2, 3, 4
+EPI_RESID_LN = 6
 
 EXPORTS = [
     "mmu_version", "mmu_error_string", "mmu_launch_count", "mmu_gemm", "mmu_mask_gather_tokens", "mmu_layernorm_fwd",
@@ -29,6 +30,7 @@ EXPORTS = [
     "mmu_imgenc_param_count", "mmu_imgenc_stat_count", "mmu_imgenc_param_table", "mmu_imgenc_stat_table",
     "mmu_imgenc_workspace_bytes", "mmu_imgenc_forward", "mmu_imgenc_backward",
     "mmu_seq_attention_fwd", "mmu_seq_attention_bwd", "mmu_modality_keep_mask", "mmu_set_gemm_sm_limit",
+    "mmu_ln_fold_weights", "mmu_layernorm_raw_stats",
 ]
 
 
@@ -41,7 +43,10 @@ class GemmEpilogue(C.Structure):
                 ("bias", C.c_void_p), ("aux", C.c_void_p), ("ld_out", C.c_longlong),
                 ("ld_out2", C.c_longlong), ("ld_aux", C.c_longlong), ("seg_len", C.c_int),
                 ("seg_stride", C.c_int), ("seg_off", C.c_int), ("alpha", C.c_float),
-                ("drop_p", C.c_float), ("drop_site", C.c_int), ("drop_seed", C.c_ulonglong)]
+                ("drop_p", C.c_float), ("drop_site", C.c_int), ("drop_seed", C.c_ulonglong),
+                ("ln_stats", C.c_void_p), ("ln_cw", C.c_void_p), ("ln_nt", C.c_int),
+                ("ln_inv_d", C.c_float), ("ln_eps", C.c_float), ("stats_nt", C.c_int),
+                ("stats_out", C.c_void_p)]
 
 
 class MetricAccum(C.Structure):
@@ -122,6 +127,8 @@ def _load():
     lib.mmu_launch_count.restype = ll
     lib.mmu_gemm.argtypes = [i, vp, ll, i, vp, ll, i, i, i, i, i, C.POINTER(GemmEpilogue), vp]
     lib.mmu_mask_gather_tokens.argtypes = [vp, vp, i, i, i, i, vp, i, vp, i, i, vp]
+    lib.mmu_ln_fold_weights.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, vp]
+    lib.mmu_layernorm_raw_stats.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.mmu_struct_size.argtypes = [i]
     lib.mmu_set_gemm_sm_limit.argtypes = [i]
     rcfgp = C.POINTER(ResNetConfig)

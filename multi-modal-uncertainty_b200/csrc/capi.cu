@@ -96,12 +96,37 @@ int mmu_gemm(int dtype, const void* A, long long lda, int a_mn_major, const void
   e.seg_off = epi->seg_off;
   e.alpha = epi->alpha;
   e.drop = dropout::make_site(epi->drop_p, epi->drop_seed, static_cast<unsigned int>(epi->drop_site));
+  e.ln_stats = epi->ln_stats;
+  e.ln_cw = epi->ln_cw;
+  e.ln_nt = epi->ln_nt;
+  e.ln_inv_d = epi->ln_inv_d;
+  e.ln_eps = epi->ln_eps;
+  e.stats_out = epi->stats_out;
+  e.stats_nt = epi->stats_nt;
+  if (dtype != MMU_BF16 && (e.ln_stats != nullptr || e.mode == EPI_RESID_LN)) return MMU_ERR_ARG;
   if (epi->drop_p < 0.f || epi->drop_p >= 1.f) return MMU_ERR_ARG;
   if (dtype == MMU_BF16) return gemm_bf16_launch(A, lda, B, ldb, p, e, S(stream));
   if (dtype == MMU_F32)
     return gemm_f32_launch(static_cast<const float*>(A), lda, static_cast<const float*>(B), ldb, p,
                            e, S(stream));
   return MMU_ERR_ARG;
+}
+
+int mmu_ln_fold_weights(const float* W, const float* gamma, const float* beta, const float* bias,
+                        void* Wf_bf16, float* cw, float* bf, int N, int K, void* stream) {
+  if (W == nullptr || gamma == nullptr || beta == nullptr || Wf_bf16 == nullptr || cw == nullptr ||
+      bf == nullptr)
+    return MMU_ERR_ARG;
+  return ln_fold_weights(W, gamma, beta, bias, Wf_bf16, cw, bf, N, nullptr, nullptr, nullptr, nullptr,
+                         nullptr, nullptr, nullptr, 0, K, S(stream));
+}
+
+int mmu_layernorm_raw_stats(const float* x, const float* gamma, const float* beta, float* y,
+                            void* yraw_bf16, float* stats, int nt, int M, int D, void* stream) {
+  if (x == nullptr || gamma == nullptr || beta == nullptr || y == nullptr || yraw_bf16 == nullptr ||
+      stats == nullptr)
+    return MMU_ERR_ARG;
+  return layernorm_raw_stats_fwd(x, gamma, beta, y, yraw_bf16, stats, nt, M, D, S(stream));
 }
 
 int mmu_mask_gather_tokens(const float* src, void* dst, int dst_dtype, int B, int l_src, int d,

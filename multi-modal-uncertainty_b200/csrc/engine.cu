@@ -449,12 +449,15 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
     // ---- eval, bf16: no LayerNorm output ever reaches HBM (see fold_path)
     const int nt = fold_slabs(c);
     const float inv_d = 1.0f / static_cast<float>(D);
-    for (int i = 0; i < c.n_layers; ++i) {
-      const LayerParams& p = lay.layer[i];
-      const Ws::FoldedLayer& f = w.fold[i];
+    {  // folded weights of every layer in one launch (layers are laid out at fixed strides)
+      const LayerParams& p = lay.layer[0];
+      const Ws::FoldedLayer& f = w.fold[0];
+      const long long pstride = c.n_layers > 1 ? lay.layer[1].in_w - lay.layer[0].in_w : 0;
+      const long long wstride = c.n_layers > 1 ? static_cast<char*>(w.fold[1].in_wf) - static_cast<char*>(w.fold[0].in_wf) : 0;
       MMU_TRY(ln_fold_weights(params + p.in_w, params + p.ln1_w, params + p.ln1_b, params + p.in_b, f.in_wf,
                               f.in_cw, f.in_bf, 3 * D, params + p.fc_w, params + p.ln2_w, params + p.ln2_b,
-                              params + p.fc_b, f.fc_wf, f.fc_cw, f.fc_bf, 4 * D, D, stream));
+                              params + p.fc_b, f.fc_wf, f.fc_cw, f.fc_bf, 4 * D, D, stream, c.n_layers, pstride,
+                              wstride));
     }
     auto folded = [&](GemmEpilogue e, const float* stats, const float* cw) {
       e.ln_stats = stats; e.ln_cw = cw; e.ln_nt = nt; e.ln_inv_d = inv_d; e.ln_eps = 1e-5f;

@@ -41,10 +41,13 @@ int layernorm_raw_stats_fwd(const float* x, const float* gamma, const float* bet
                             void* yraw_bf16, float* stats, int nt, int M, int D, cudaStream_t stream);
 // Folded weights of up to two Linears that consume LayerNorm output (N1 == 0: one):
 // Wf = bf16(W diag(gamma)) [N][K], cw[n] = sum_k Wf[n][k], bf[n] = bias[n] + sum_k beta[k] W[n][k].
+// n_layers > 1: the same pair for every layer in ONE launch, input pointers advancing by pstride
+// floats and output pointers by wstride bytes per layer.
 int ln_fold_weights(const float* W0, const float* gamma0, const float* beta0, const float* bias0,
                     void* Wf0, float* cw0, float* bf0, int N0, const float* W1, const float* gamma1,
                     const float* beta1, const float* bias1, void* Wf1, float* cw1, float* bf1, int N1,
-                    int K, cudaStream_t stream);
+                    int K, cudaStream_t stream, int n_layers = 1, long long pstride = 0,
+                    long long wstride = 0);
 // x_out = x_in + y (y and h in `dtype`); h = LN(x_out) unless gamma == nullptr (sum only).
 int add_layernorm_fwd(const float* x_in, const void* y, float* x_out, const float* gamma,
                       const float* beta, void* h, int dtype, float* mean, float* rstd, int M, int D,

@@ -301,9 +301,19 @@ struct FoldSet {
   __nv_bfloat16* Wf; float* cw; float* bf;
   int N;
 };
+// blockIdx.z = layer: every pointer of a set moves by a fixed stride per layer (pstride floats for
+// the parameters, wstride BYTES for the folded outputs)
 __global__ void __launch_bounds__(256)
-ln_fold_weights_kernel(FoldSet s0, FoldSet s1, int K) {
-  const FoldSet s = blockIdx.y == 0 ? s0 : s1;
+ln_fold_weights_kernel(FoldSet s0, FoldSet s1, int K, long long pstride, long long wstride) {
+  FoldSet s = blockIdx.y == 0 ? s0 : s1;
+  {
+    const long long po = pstride * blockIdx.z, wo = wstride * blockIdx.z;
+    s.W += po; s.gamma += po; s.beta += po;
+    if (s.bias != nullptr) s.bias += po;
+    s.Wf = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(s.Wf) + wo);
+    s.cw = reinterpret_cast<float*>(reinterpret_cast<char*>(s.cw) + wo);
+    s.bf = reinterpret_cast<float*>(reinterpret_cast<char*>(s.bf) + wo);
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kv = K >> 2;
   for (int n = blockIdx.x * 8 + warp; n < s.N; n += gridDim.x * 8) {
@@ -1139,13 +1149,13 @@ int layernorm_raw_stats_fwd(const float* x, const float* gamma, const float* bet
 int ln_fold_weights(const float* W0, const float* gamma0, const float* beta0, const float* bias0,
                     void* Wf0, float* cw0, float* bf0, int N0, const float* W1, const float* gamma1,
                     const float* beta1, const float* bias1, void* Wf1, float* cw1, float* bf1, int N1,
-                    int K, cudaStream_t stream) {
-  if (K % 4 != 0 || N0 < 1 || N1 < 0) return MMU_ERR_SHAPE;
+                    int K, cudaStream_t stream, int n_layers, long long pstride, long long wstride) {
+  if (K % 4 != 0 || N0 < 1 || N1 < 0 || n_layers < 1) return MMU_ERR_SHAPE;
   FoldSet s0{W0, gamma0, beta0, bias0, static_cast<__nv_bfloat16*>(Wf0), cw0, bf0, N0};
   FoldSet s1{W1, gamma1, beta1, bias1, static_cast<__nv_bfloat16*>(Wf1), cw1, bf1, N1};
   const int nmax = N0 > N1 ? N0 : N1;
-  dim3 grid((nmax + 7) / 8, N1 > 0 ? 2 : 1);
-  ln_fold_weights_kernel<<<grid, 256, 0, stream>>>(s0, s1, K);
+  dim3 grid((nmax + 7) / 8, N1 > 0 ? 2 : 1, n_layers);
+  ln_fold_weights_kernel<<<grid, 256, 0, stream>>>(s0, s1, K, pstride, wstride);
   MMU_CHECK_LAUNCH();
   return 0;
 }

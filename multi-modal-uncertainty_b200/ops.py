@@ -27,9 +27,12 @@ def _cuda(*ts):
 
 
 def gemm(A, B, *, a_mn_major=False, b_mn_major=False, mode=_lib.EPI_STORE, out=None, out2=None,
-         bias=None, aux=None, alpha=1.0, splits=1, seg=None, out_dtype=None, dropout=None):
-    """C[M,N] = epilogue(sum_k A(m,k) B(n,k)); see ``mmu_gemm`` in include/mmu_b200.h."""
-    _cuda(A, B, out, out2, bias, aux)
+         bias=None, aux=None, alpha=1.0, splits=1, seg=None, out_dtype=None, dropout=None,
+         ln_fold=None, stats_out=None):
+    """C[M,N] = epilogue(sum_k A(m,k) B(n,k)); see ``mmu_gemm`` in include/mmu_b200.h.
+    ``ln_fold=(stats, cw, eps)``: LayerNorm folded into a STORE / QUICKGELU epilogue (A = raw rows,
+    B = folded weights, stats fp32 (M, nt, 2)); ``stats_out`` fp32 (M, nt, 2): EPI_RESID_LN's row sums."""
+    _cuda(A, B, out, out2, bias, aux, stats_out)
     dt = _dt(A)
     if a_mn_major:
         K, M = A.shape
@@ -51,9 +54,40 @@ def gemm(A, B, *, a_mn_major=False, b_mn_major=False, mode=_lib.EPI_STORE, out=N
     e.alpha = alpha
     if dropout is not None:   # (p, seed, site): QUICKGELU / DGELU modes only
         e.drop_p, e.drop_seed, e.drop_site = float(dropout[0]), int(dropout[1]), int(dropout[2])
+    if ln_fold is not None:
+        stats, cw, eps = ln_fold
+        _cuda(stats, cw)
+        e.ln_stats, e.ln_cw, e.ln_nt = ptr(stats), ptr(cw), stats.shape[1]
+        e.ln_inv_d, e.ln_eps = 1.0 / K, float(eps)
+    if stats_out is not None:
+        e.stats_out, e.stats_nt = ptr(stats_out), stats_out.shape[1]
     check(lib.mmu_gemm(dt, ptr(A), A.stride(0), int(a_mn_major), ptr(B), B.stride(0),
                        int(b_mn_major), M, N, K, splits, C.byref(e), stream_ptr()), "mmu_gemm")
     return out if out is not None else out2
+
+
+def ln_fold_weights(W, gamma, beta, bias=None):
+    """(Wf bf16 (N, K), cw fp32 (N,), bf fp32 (N,)) of a Linear that consumes LayerNorm output."""
+    _cuda(W, gamma, beta, bias)
+    N, K = W.shape
+    Wf = torch.empty(N, K, device=W.device, dtype=torch.bfloat16)
+    cw = torch.empty(N, device=W.device, dtype=torch.float32)
+    bf = torch.empty(N, device=W.device, dtype=torch.float32)
+    check(lib.mmu_ln_fold_weights(ptr(W), ptr(gamma), ptr(beta), ptr(bias), ptr(Wf), ptr(cw), ptr(bf), N, K,
+                                  stream_ptr()), "mmu_ln_fold_weights")
+    return Wf, cw, bf
+
+
+def layernorm_raw_stats(x, gamma, beta, nt):
+    """(y fp32, yraw bf16, stats fp32 (M, nt, 2)): LayerNorm output, its raw bf16 copy and row sums."""
+    _cuda(x, gamma, beta)
+    M, D = x.shape
+    y = torch.empty_like(x)
+    yraw = torch.empty(M, D, device=x.device, dtype=torch.bfloat16)
+    stats = torch.empty(M, nt, 2, device=x.device, dtype=torch.float32)
+    check(lib.mmu_layernorm_raw_stats(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(yraw), ptr(stats), nt, M, D,
+                                      stream_ptr()), "mmu_layernorm_raw_stats")
+    return y, yraw, stats
 
 
 def mask_gather_tokens(src, idx=None, keep=None, modality=0, dtype=torch.float32, pos_major=False):

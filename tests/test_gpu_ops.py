@@ -184,6 +184,57 @@ def test_batch_axis_attention(mmu, dtype, tol, B, L, D, H):
     assert torch.equal(dqkv_p.cpu(), pm(dqkv.cpu()))
 
 
+@pytest.mark.parametrize("M,D,N", [(300, 192, 520), (1000, 768, 2304), (640, 128, 512)])
+def test_gemm_folded_layernorm_and_residual_epilogue(mmu, M, D, N, measured):
+    """The eval path's two GEMM epilogues through the C ABI (reference src/model.py:209-212):
+    RESID_LN (x' = x + o W^T + b in fp32, raw bf16 copy, per-slab row sums) feeding a GEMM with the
+    LayerNorm FOLDED into its epilogue, against LayerNorm -> Linear computed in fp64."""
+    E_ = mmu._lib
+    bf = torch.bfloat16
+    o = rnd(M, D, seed=1).to(bf)
+    w_out, b_out = (rnd(D, D, seed=2) / math.sqrt(D)).to(bf), rnd(D, seed=3)
+    x = rnd(M, D, seed=4, scale=2.0) + 0.7                      # residual stream with a row mean
+    gamma, beta = 1.0 + 0.2 * rnd(D, seed=5), 0.3 * rnd(D, seed=6)
+    w_fc, b_fc = rnd(N, D, seed=7) / math.sqrt(D), rnd(N, seed=8)
+    nt = (D + 127) // 128
+    x1 = torch.empty(M, D, device="cuda")
+    raw = torch.empty(M, D, device="cuda", dtype=bf)
+    stats = torch.zeros(M, nt, 2, device="cuda")
+    mmu.ops.gemm(o.cuda(), w_out.cuda(), mode=E_.EPI_RESID_LN, out=x1, out2=raw, bias=b_out.cuda(),
+                 aux=x.cuda(), stats_out=stats)
+    x1_ref = x.double() + o.double() @ w_out.double().t() + b_out.double()
+    assert rel(x1.cpu(), x1_ref) < 1e-5
+    assert torch.equal(raw.cpu(), x1.cpu().to(bf))               # exact copy of what was written
+    s_ref = torch.stack([x1.cpu().double().sum(1), (x1.cpu().double() ** 2).sum(1)], 1)
+    assert rel(stats.cpu().double().sum(1), s_ref) < 1e-5
+    # in-place residual update (aux aliases out) gives the same bits
+    x2 = x.cuda().clone()
+    mmu.ops.gemm(o.cuda(), w_out.cuda(), mode=E_.EPI_RESID_LN, out=x2, bias=b_out.cuda(), aux=x2)
+    assert torch.equal(x2, x1)
+    # folded consumer: LayerNorm(x1) W_fc^T + b_fc, plain and with QuickGELU
+    wf, cw, bfold = mmu.ops.ln_fold_weights(w_fc.cuda(), gamma.cuda(), beta.cuda(), b_fc.cuda())
+    assert rel(wf.float().cpu(), w_fc * gamma) < 5e-3 and rel(cw.cpu(), wf.float().cpu().sum(1)) < 1e-5
+    assert rel(bfold.cpu(), b_fc.double() + w_fc.double() @ beta.double()) < 1e-5
+    ln = torch.nn.functional.layer_norm(x1_ref, (D,), gamma.double(), beta.double(), 1e-5)
+    z_ref = ln @ w_fc.double().t() + b_fc.double()
+    z = mmu.ops.gemm(raw, wf, bias=bfold, ln_fold=(stats, cw, 1e-5))
+    u = torch.empty(M, N, device="cuda", dtype=bf)
+    mmu.ops.gemm(raw, wf, mode=E_.EPI_QUICKGELU, out2=u, bias=bfold, ln_fold=(stats, cw, 1e-5))
+    measured("gemm_fold/bf16/z", rel(z.float().cpu(), z_ref))
+    assert rel(z.float().cpu(), z_ref) < 1.5e-2
+    assert rel(u.float().cpu(), z_ref * torch.sigmoid(1.702 * z_ref)) < 1.5e-2
+    # the unfolded path on the same inputs (LayerNorm kernel -> bf16 -> GEMM) is no closer
+    h, _, _ = mmu.ops.layernorm_fwd(x1, gamma.cuda(), beta.cuda(), out_dtype=bf)
+    z_two = mmu.ops.gemm(h, w_fc.to(bf).cuda(), bias=b_fc.cuda())
+    measured("gemm_fold/bf16/z_unfolded", rel(z_two.float().cpu(), z_ref))
+    # ln_pre companion: LayerNorm output + raw copy + sums in partial 0
+    y, yraw, st = mmu.ops.layernorm_raw_stats(x.cuda(), gamma.cuda(), beta.cuda(), nt)
+    y_ref = torch.nn.functional.layer_norm(x.double(), (D,), gamma.double(), beta.double(), 1e-5)
+    assert rel(y.cpu(), y_ref) < 1e-5 and torch.equal(yraw.cpu(), y.cpu().to(bf))
+    assert rel(st[:, 0].cpu(), torch.stack([y_ref.sum(1), (y_ref ** 2).sum(1)], 1)) < 1e-4
+    assert float(st[:, 1:].abs().max()) == 0.0 if nt > 1 else True
+
+
 @pytest.mark.parametrize("B,L,D,H", [(128, 5, 768, 3), (100, 3, 768, 3), (37, 4, 512, 2), (128, 160, 768, 3),
                                      (8, 2, 256, 1)])
 def test_fused_batch_axis_attention_eval(mmu, B, L, D, H, measured):

@@ -22,7 +22,7 @@ torch.cuda.set_device(0)
 torch.manual_seed(42)
 model = mmu.FlavaFusionTransfomer(out_dim=CFG["E"], num_classes=CFG["C"], multimodal_num_attention_heads=CFG["heads"],
                                   multimodal_num_hidden_layers=CFG["layers"], drop=0.0, avg_pool=False,
-                                  precision="bf16").to(dev)
+                                  precision="bf16", live_tokens=bool(os.environ.get("MMU_TL_LIVE"))).to(dev)
 opt = mmu.FusedAdamW(model.parameters(), lr=CFG["lr"], betas=(0.9, 0.98), eps=1e-9, weight_decay=CFG["wd"])
 sched = mmu.get_cosine_schedule_with_warmup(opt, 300, 10000)
 meter = mmu.metrics.UncertaintyMeter(dev, CFG["C"], CFG["E"])
