@@ -251,6 +251,22 @@ class FlavaFusionTransfomer(nn.Module):
         self._ws.clear()
         self._live_idx = {}
 
+    def train(self, mode: bool = True):
+        """``nn.Module.train`` without the recursive ``__setattr__`` walk: a sweep-then-train loop
+        toggles eval() / train() every batch, and the generic walk over this model's ~40 parameter
+        holders costs 0.3-0.4 ms of host time per toggle pair -- a fifth of a live-token step,
+        which is host bound (``tools/host_profile.py``).  ``training`` is a plain instance
+        attribute of every module, so writing it directly is equivalent."""
+        if not isinstance(mode, bool):
+            raise ValueError("training mode is expected to be boolean")
+        cache = self.__dict__.get("_mode_modules")
+        if cache is None or cache[0] != len(self._modules):
+            cache = (len(self._modules), list(self.modules()))
+            self.__dict__["_mode_modules"] = cache
+        for m in cache[1]:
+            m.__dict__["training"] = mode
+        return self
+
     def _ensure_grad_views(self):
         """The kernels accumulate into the flat gradient buffer; ``p.grad`` must be its views.
         ``torch.optim.Optimizer.zero_grad()`` (set_to_none=True, the default) drops them: treat a
