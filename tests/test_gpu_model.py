@@ -320,6 +320,23 @@ def test_device_prefetcher_yields_host_batches_in_order(mmu):
     assert seen == len(host)
 
 
+def test_async_scalars_reads_behind_queued_work(mmu):
+    """metrics.AsyncScalars: per-step scalars leave on a side stream behind an event; popping ticket
+    i returns step i's values even though later work (and later pushes) is already queued."""
+    dev = torch.device("cuda")
+    reader = mmu.metrics.AsyncScalars(dev, slots=3)
+    x = torch.zeros(1 << 24, device=dev)
+    tickets = []
+    for i in range(7):                      # more pushes than slots: slots are recycled safely
+        x.add_(1.0)
+        tickets.append(reader.push([x[0], x[-1] * 2, x.sum() / x.numel()]))
+        for _ in range(20):
+            x.mul_(1.0)                     # queued work behind the push
+        if i >= 2:
+            assert reader.pop(tickets[i - 2]) == [float(i - 1), 2.0 * (i - 1), float(i - 1)]
+    assert reader.pop(tickets[-1]) == [7.0, 14.0, 7.0]
+
+
 def test_device_prefetcher_never_overtakes_queued_work(mmu):
     """The copy stream must not write into (a) a freshly allocated slot whose memory block queued
     consumer-stream kernels still read (the caching allocator orders reuse on ONE stream only),

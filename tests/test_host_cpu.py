@@ -133,6 +133,24 @@ def test_stage_ranges_partition_the_flat_buffer(mmu):
     assert ranges[0][0] > ranges[-1][0]  # heads live at the end of the buffer, stem at the start
 
 
+def test_train_eval_toggle_matches_nn_module(mmu):
+    """The model's train() / eval() write `training` directly instead of walking the module tree with
+    __setattr__ (a live-token step is host bound): the flags must end up exactly where
+    nn.Module.train puts them, also after a submodule is added."""
+    m = mmu.FlavaFusionTransfomer(out_dim=2, num_classes=5, image_hidden_size=16, text_hidden_size=16,
+                                  multimodal_hidden_size=32, multimodal_num_attention_heads=2,
+                                  multimodal_num_hidden_layers=2, avg_pool=False)
+    assert m.eval() is m and not any(x.training for x in m.modules())
+    assert m.train() is m and all(x.training for x in m.modules())
+    m.add_module("extra", torch.nn.Dropout(0.5))
+    m.eval()
+    assert not m.extra.training and not any(x.training for x in m.modules())
+    torch.nn.Module.train(m, True)          # the generic walk and the fast path agree
+    assert all(x.training for x in m.modules())
+    with pytest.raises(ValueError):
+        m.train("yes")
+
+
 def test_no_cpu_fallback(mmu):
     m = small_model(mmu)
     with pytest.raises(mmu._lib.MMUError):
