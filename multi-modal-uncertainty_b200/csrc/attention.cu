@@ -604,8 +604,9 @@ int seq_fwd(const void* qkv, const float* addmask, void* out, void* probs, float
 }
 
 // With attention-probability dropout: Pd is regenerated into `dprobs` for dV = Pd^T dO FIRST, then
-// dPd = dO V^T, dS = P o (dPd * mask / (1 - p) - delta) / sqrt(hd) overwrites `dprobs`; the fused
-// kernels (no dropout support) are bypassed.
+// dPd = dO V^T, dS = P o (dPd * mask / (1 - p) - delta) / sqrt(hd) overwrites `dprobs` -- by the
+// fused kernel (dPd stays in TMEM, the mask is regenerated there, dQ = dS K comes with it) when it
+// applies, else by the dP GEMM + row kernel.
 int seq_bwd_dropout(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
                     void* dqkv, int B, int S, int D, int H, cudaStream_t st, dropout::Site drop) {
   const int hd = D / H, G = B * H, Sp = (S + 7) / 8 * 8;
@@ -620,18 +621,23 @@ int seq_bwd_dropout(const void* qkv, const void* dout, const void* probs, float*
   int rc = gemm_bf16_batched_launch(sq_view(dprobs, G, S, Sp, 1), act_view_seq(dout, B, S, D, H, 1), G, S, hd,
                                     S, store_epi(dq + 2 * D, 1, ld, 1.0f), H, hd, mid, st);
   if (rc) return rc;
-  rc = gemm_bf16_batched_launch(act_view_seq(dout, B, S, D, H, 0), qkv_view_seq(qkv, B, S, D, H, 2, 0),
-                                G, S, Sp, hd, store_epi(scores, 0, Sp, 1.0f), 1, 0,
-                                static_cast<long long>(S) * Sp, st);
-  if (rc) return rc;
-  softmax_bwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(
-      scores, static_cast<const __nv_bfloat16*>(probs), static_cast<__nv_bfloat16*>(dprobs), rows, S, Sp,
-      scale, drop);
-  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
-  count_launch();
+  rc = fused_seq_attention_bwd_ds(qkv, dout, probs, dprobs, dqkv, B, S, D, H, st, drop);
+  if (rc < 0) return rc;
+  const bool dq_done = rc == 0;  // the fused kernel also produced dQ = dS K
+  if (rc > 0) {
+    rc = gemm_bf16_batched_launch(act_view_seq(dout, B, S, D, H, 0), qkv_view_seq(qkv, B, S, D, H, 2, 0),
+                                  G, S, Sp, hd, store_epi(scores, 0, Sp, 1.0f), 1, 0,
+                                  static_cast<long long>(S) * Sp, st);
+    if (rc) return rc;
+    softmax_bwd_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(
+        scores, static_cast<const __nv_bfloat16*>(probs), static_cast<__nv_bfloat16*>(dprobs), rows, S, Sp,
+        scale, drop);
+    if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+    count_launch();
+  }
   rc = gemm_bf16_batched_launch(sq_view(dprobs, G, S, Sp, 1), qkv_view_seq(qkv, B, S, D, H, 0, 1), G, S,
                                 hd, S, store_epi(dq + D, 1, ld, 1.0f), H, hd, mid, st);
-  if (rc) return rc;
+  if (rc || dq_done) return rc;
   return gemm_bf16_batched_launch(sq_view(dprobs, G, S, Sp, 0), qkv_view_seq(qkv, B, S, D, H, 1, 1), G, S,
                                   hd, S, store_epi(dq, 1, ld, 1.0f), H, hd, mid, st);
 }
@@ -765,8 +771,9 @@ int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* pr
   if (drop.on() && pdrop == nullptr) return MMU_ERR_ARG;
   if (dtype == DT_BF16) {
     if ((D / H) % 64 != 0 || scores == nullptr) return MMU_ERR_SHAPE;
-    if (allow_fused && !drop.on()) {  // one fused kernel when it applies (head_dim 64, S <= 512)
-      const int rc = fused_seq_attention_fwd(qkv, addmask, out, keep_probs ? probs : nullptr, B, S, D, H, stream);
+    if (allow_fused) {  // one fused kernel when it applies (head_dim 64, S <= 512)
+      const int rc = fused_seq_attention_fwd(qkv, addmask, out, keep_probs ? probs : nullptr, B, S, D, H, stream,
+                                             drop);
       if (rc <= 0) return rc;
     }
     return tc::seq_fwd(qkv, addmask, out, probs, scores, B, S, D, H, stream, drop, pdrop);

@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "common.h"
+#include "dropout.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -59,11 +60,18 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 }
 __device__ __forceinline__ void nbar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <bool SAVE_P>
+// DROP (training with attention-probability dropout, pytorch_pretrained_bert BertSelfAttention):
+// the UNDROPPED rounded probabilities go to the probs tensor (the backward needs them where the
+// mask is 0 too), the dropped ones Pd = bf16(P * mask / (1 - p)) feed MMA2.  Each column half then
+// uses its two P buffers as (store staging, MMA operand) instead of double-buffering one role;
+// element counter = (g * S + query) * S + key, the mask function of csrc/dropout.cuh.
+template <bool SAVE_P, bool DROP>
 __global__ void __launch_bounds__(THREADS, 1)
 fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_v,
                  const __grid_constant__ CUtensorMap tm_p, const float* __restrict__ addmask,
-                 __nv_bfloat16* __restrict__ out, int B, int S, int D, int H, float scale, int tiles_per_cta) {
+                 __nv_bfloat16* __restrict__ out, int B, int S, int D, int H, float scale, int tiles_per_cta,
+                 const dropout::Site drop) {
+  static_assert(!DROP || SAVE_P, "dropout exists in training only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -156,11 +164,12 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
           for (int hh = 0; hh < 2; ++hh) {
             const int c = hh * 4 + i;
             if (c >= n_ch) continue;
-            const int buf = i & 1;
+            const int buf = DROP ? 1 : (i & 1);
             // global use index of this P buffer (a half with n chunks uses buffer 0 ceil(n/2) and
-            // buffer 1 floor(n/2) times per query tile): the barrier phase is its parity
+            // buffer 1 floor(n/2) times per query tile; DROP: buffer 1 for every chunk): the
+            // barrier phase is its parity
             const int n_half = max(0, min(n_ch, hh * 4 + 4) - hh * 4);
-            const int use = qt * ((n_half - buf + 1) / 2) + (i >> 1);
+            const int use = DROP ? qt * n_half + i : qt * ((n_half - buf + 1) / 2) + (i >> 1);
             ptx::mbar_wait(&p_full[hh * 2 + buf], use & 1);
             ptx::tc_fence_after();
             const uint32_t sp = ptx::smem_u32(smem + OFF_P + (hh * 2 + buf) * P_BYTES);
@@ -246,17 +255,21 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
       const float inv = SAVE_P ? 1.0f / sum : 1.0f;
       // last pass: probabilities -> bf16 -> swizzled K-major tile -> MMA2 (and the probs tensor)
       for (int c = c_begin; c < c_end; ++c) {
-        const int i = c - c_begin, buf = i & 1;
-        const uint32_t pbuf = ptx::smem_u32(smem + OFF_P + (hh * 2 + buf) * P_BYTES);
+        const int i = c - c_begin, buf = DROP ? 1 : (i & 1);
+        const uint32_t pbuf = ptx::smem_u32(smem + OFF_P + (hh * 2 + buf) * P_BYTES);   // MMA2 operand
+        const uint32_t pst = DROP ? ptx::smem_u32(smem + OFF_P + (hh * 2) * P_BYTES) : pbuf;  // TMA-store source
         // buffer reuse: its previous tile (this query tile's use i - 2, or the previous query
         // tile's last use of this buffer) must have been consumed by MMA2 and by its TMA store.
-        // Completions of p_empty[buf] come in use order, 2 (or 1) per query tile.
-        const int uses_per_tile = (n_mine - buf + 1) / 2;           // uses of this buffer per tile
-        const int use = qt * uses_per_tile + (i >> 1);              // global use index of this write
+        // Completions of p_empty[buf] come in use order, 2 (or 1) per query tile (DROP: one per chunk).
+        const int uses_per_tile = DROP ? n_mine : (n_mine - buf + 1) / 2;   // uses of this buffer per tile
+        const int use = qt * uses_per_tile + (DROP ? i : (i >> 1));         // global use index of this write
         if (use > 0) {
           ptx::mbar_wait(&p_empty[hh * 2 + buf], (use - 1) & 1);
           if (SAVE_P) {
-            if (issuer) ptx::bulk_wait_read<1>();
+            if (issuer) {
+              if (DROP) ptx::bulk_wait_read<0>();   // one staging buffer: its last store has read it
+              else ptx::bulk_wait_read<1>();
+            }
             nbar(1 + hh, 128);
           }
         }
@@ -275,9 +288,21 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               const uint32_t piece = static_cast<uint32_t>(step * 2 + k);
-              ptx::sts_v4u(pbuf + prow + ((piece ^ sw) << 4), pack2(v[8 * k], v[8 * k + 1]),
-                           pack2(v[8 * k + 2], v[8 * k + 3]), pack2(v[8 * k + 4], v[8 * k + 5]),
-                           pack2(v[8 * k + 6], v[8 * k + 7]));
+              const uint32_t w[4] = {pack2(v[8 * k], v[8 * k + 1]), pack2(v[8 * k + 2], v[8 * k + 3]),
+                                     pack2(v[8 * k + 4], v[8 * k + 5]), pack2(v[8 * k + 6], v[8 * k + 7])};
+              ptx::sts_v4u(pst + prow + ((piece ^ sw) << 4), w[0], w[1], w[2], w[3]);
+              if constexpr (DROP) {
+                // the dropped copy is derived from the ROUNDED probability, as the backward regenerates it
+                const unsigned int e0 = (static_cast<unsigned int>(g) * static_cast<unsigned int>(S) +
+                                         static_cast<unsigned int>(q0 + row)) * static_cast<unsigned int>(S) +
+                                        static_cast<unsigned int>(c * CH + step * 16 + 8 * k);
+                uint32_t d[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  d[t] = pack2(__uint_as_float(w[t] << 16) * drop.mult(e0 + 2 * t),
+                               __uint_as_float(w[t] & 0xffff0000u) * drop.mult(e0 + 2 * t + 1));
+                ptx::sts_v4u(pbuf + prow + ((piece ^ sw) << 4), d[0], d[1], d[2], d[3]);
+              }
             }
           };
           const uint32_t tc = trow + c * CH;
@@ -300,7 +325,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
         if (issuer) {
           ptx::mbar_arrive(&p_full[hh * 2 + buf]);
           if (SAVE_P) {
-            ptx::tma_store_3d(&tm_p, pbuf, c * CH, g, q0);
+            ptx::tma_store_3d(&tm_p, pst, c * CH, g, q0);
             ptx::bulk_commit();
           }
         }
@@ -363,11 +388,13 @@ constexpr int B_OFF_XCH = B_OFF_P + 8 * P_BYTES;      // float [2][128]
 constexpr int B_OFF_BARS = B_OFF_XCH + 2 * BQ * 4;
 constexpr int B_SMEM_BYTES = B_OFF_BARS + 16 * 8 + 16 + 1024;
 
+// DROP: dP = dPd * mask / (1 - p) with the forward's mask regenerated from the element counter.
+template <bool DROP>
 __global__ void __launch_bounds__(THREADS, 1)
 fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_v,
                     const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_ds,
                     const __grid_constant__ CUtensorMap tm_k, __nv_bfloat16* __restrict__ dqkv, int S, int D,
-                    int H, float scale) {
+                    int H, float scale, const dropout::Site drop) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -475,6 +502,16 @@ fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_cons
     ptx::mbar_wait(s_full, 0);
     ptx::tc_fence_after();
     uint32_t r[32];
+    // element counter of (this query row, key 0) in the forward's mask
+    const unsigned int e_row = (static_cast<unsigned int>(g) * static_cast<unsigned int>(S) +
+                                static_cast<unsigned int>(q0 + row)) * static_cast<unsigned int>(S);
+    auto undrop = [&](int c, int j) {   // dPd -> dP in place (registers)
+      if constexpr (DROP) {
+        const unsigned int e0 = e_row + static_cast<unsigned int>(c * CH + j * 32);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * drop.mult(e0 + i));
+      }
+    };
     // pass 1: delta = sum_j dP_ij P_ij
     float delta = 0.f;
     for (int c = c_begin; c < c_end; ++c) {
@@ -487,6 +524,7 @@ fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_cons
         for (int k = 0; k < 4; ++k)
           pk[k] = ptx::lds_v4u(pbase + c * P_BYTES + prow + ((static_cast<uint32_t>(j * 4 + k) ^ sw) << 4));
         ptx::tmem_ld_wait();
+        undrop(c, j);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint32_t w[4] = {pk[k].x, pk[k].y, pk[k].z, pk[k].w};
@@ -512,6 +550,7 @@ fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_cons
         for (int k = 0; k < 4; ++k)
           pk[k] = ptx::lds_v4u(pbase + c * P_BYTES + prow + ((static_cast<uint32_t>(j * 4 + k) ^ sw) << 4));
         ptx::tmem_ld_wait();
+        undrop(c, j);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint32_t w[4] = {pk[k].x, pk[k].y, pk[k].z, pk[k].w};
@@ -566,10 +605,11 @@ fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_cons
 
 // Returns 1 when the fused kernel does not apply (caller falls back to the three-kernel path).
 int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, int B, int S,
-                            int D, int H, cudaStream_t stream) {
+                            int D, int H, cudaStream_t stream, dropout::Site drop) {
   using namespace fattn;
   static const bool disabled = getenv("MMU_ATTN_UNFUSED") != nullptr;  // A/B switch
   if (disabled || D / H != HD || D % H != 0 || S > SMAX || S < 1) return 1;
+  if (drop.on() && probs == nullptr) return 1;   // dropout: training only
   const int Sp = (S + 7) / 8 * 8;
   CUtensorMap tq, tv, tp;
   int rc = make_tmap_bf16_3d(&tq, qkv, 3LL * D, B, S, 3LL * D * S, 3LL * D, HD, KB);
@@ -598,18 +638,19 @@ int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, vo
     attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (attr != cudaSuccess) return MMU_ERR_CUDA;
     kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tq, tv, tp, addmask, static_cast<__nv_bfloat16*>(out), B, S,
-                                                  D, H, scale, tpc);
+                                                  D, H, scale, tpc, drop);
     if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
     count_launch();
     return 0;
   };
-  return probs != nullptr ? launch(fattn_fwd_kernel<true>) : launch(fattn_fwd_kernel<false>);
+  if (drop.on()) return launch(fattn_fwd_kernel<true, true>);
+  return probs != nullptr ? launch(fattn_fwd_kernel<true, false>) : launch(fattn_fwd_kernel<false, false>);
 }
 
 // dprobs (bf16 [G, S, Sp]) = dS and the q third of dqkv = dS K.  Returns 1 when the fused kernel
 // does not apply.
 int fused_seq_attention_bwd_ds(const void* qkv, const void* dout, const void* probs, void* dprobs, void* dqkv,
-                               int B, int S, int D, int H, cudaStream_t stream) {
+                               int B, int S, int D, int H, cudaStream_t stream, dropout::Site drop) {
   using namespace fattn;
   static const bool disabled = getenv("MMU_ATTN_UNFUSED") != nullptr;
   if (disabled || D / H != HD || D % H != 0 || S > SMAX || S < 1) return 1;
@@ -626,13 +667,18 @@ int fused_seq_attention_bwd_ds(const void* qkv, const void* dout, const void* pr
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&tk, qkv, 3LL * D, B, S, 3LL * D * S, 3LL * D, HD, CH);
   if (rc) return rc;
-  static cudaError_t attr =
-      cudaFuncSetAttribute(fattn_bwd_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM_BYTES);
-  if (attr != cudaSuccess) return MMU_ERR_CUDA;
+  static cudaError_t attr[2] = {
+      cudaFuncSetAttribute(fattn_bwd_ds_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM_BYTES),
+      cudaFuncSetAttribute(fattn_bwd_ds_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM_BYTES)};
+  if (attr[0] != cudaSuccess || attr[1] != cudaSuccess) return MMU_ERR_CUDA;
   const int grid = static_cast<int>(G) * ((S + BQ - 1) / BQ);
-  fattn_bwd_ds_kernel<<<grid, THREADS, B_SMEM_BYTES, stream>>>(tdo, tv, tp, tds, tk,
-                                                               static_cast<__nv_bfloat16*>(dqkv), S, D, H,
-                                                               1.0f / sqrtf(static_cast<float>(HD)));
+  const float scale = 1.0f / sqrtf(static_cast<float>(HD));
+  if (drop.on())
+    fattn_bwd_ds_kernel<true><<<grid, THREADS, B_SMEM_BYTES, stream>>>(
+        tdo, tv, tp, tds, tk, static_cast<__nv_bfloat16*>(dqkv), S, D, H, scale, drop);
+  else
+    fattn_bwd_ds_kernel<false><<<grid, THREADS, B_SMEM_BYTES, stream>>>(
+        tdo, tv, tp, tds, tk, static_cast<__nv_bfloat16*>(dqkv), S, D, H, scale, drop);
   if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
   count_launch();
   return 0;

@@ -157,10 +157,14 @@ int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* pr
                       void* pdrop = nullptr);
 // Fused forward (fused_attention.cu): head_dim 64, S <= 512; probs may be null (inference: nothing
 // but O is written).  Returns 1 when it does not apply, 0 on success, < 0 on error.
+// drop (training): the undropped probabilities are stored, the dropped ones feed P V / dP is
+// multiplied by the regenerated mask.
 int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, int B, int S,
-                            int D, int H, cudaStream_t stream);
+                            int D, int H, cudaStream_t stream,
+                            dropout::Site drop = dropout::Site{0u, 0u, 0u, 1.0f});
 int fused_seq_attention_bwd_ds(const void* qkv, const void* dout, const void* probs, void* dprobs, void* dqkv,
-                               int B, int S, int D, int H, cudaStream_t stream);
+                               int B, int S, int D, int H, cudaStream_t stream,
+                               dropout::Site drop = dropout::Site{0u, 0u, 0u, 1.0f});
 int seq_attention_bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
                       void* dqkv, int dtype, int B, int S, int D, int H, cudaStream_t stream,
                       dropout::Site drop = dropout::Site{0u, 0u, 0u, 1.0f});

@@ -142,17 +142,20 @@ def _mmbt_args(cfg, precision, **kw):
 
 
 @pytest.mark.parametrize("precision,tl,tg", [("fp32", 1e-3, 1e-3), ("bf16", 1.6e-2, 6e-2)])
-@pytest.mark.parametrize("indices", [None, "control"])
-def test_mmbt_training_with_dropout_matches_oracle_under_the_same_masks(mmu, precision, tl, tg, indices, measured):
+@pytest.mark.parametrize("indices,s_txt", [(None, 150), ("control", 150), (None, 330)])
+def test_mmbt_training_with_dropout_matches_oracle_under_the_same_masks(mmu, precision, tl, tg, indices, s_txt,
+                                                                        measured):
     """MMBT in train() mode with the reference's dropouts switched on (BERT hidden 0.1, attention
     probabilities 0.15, ImageBertEmbeddings 0.2 -- src/mmbt.py:56,82 and pytorch_pretrained_bert's
     BertEmbeddings / BertSelfAttention / BertSelfOutput / BertOutput): forward + backward of the
-    engine (three-kernel attention path with the dropped-probability copy, masks regenerated in
-    the backward) against the oracle applying the same counter-based masks; ragged batch, S = 155
-    (> one attention tile), also through a ``forward_control``-style index list."""
+    engine (bf16: the fused attention kernels -- undropped P stored, dropped P into P V, mask
+    regenerated in the fused backward --, fp32: the SIMT path with a dropped-probability copy)
+    against the oracle applying the same counter-based masks; ragged batch, S = 155 (two query
+    tiles, three 64-key chunks) and S = 335 (three tiles, chunks in both column halves), also
+    through a ``forward_control``-style index list."""
     from oracle import mmbt as O
-    cfg = dict(B=3, S_txt=150, n_img=3, d_img=64, D=128, n_head=2, n_layers=2, d_ff=256, vocab=300,
-               max_pos=160, n_types=2, C=2, cls_id=5, sep_id=6)
+    cfg = dict(B=3, S_txt=s_txt, n_img=3, d_img=64, D=128, n_head=2, n_layers=2, d_ff=256, vocab=300,
+               max_pos=s_txt + 10, n_types=2, C=2, cls_id=5, sep_id=6)
     drop = dict(hidden=0.1, attn=0.15, img=0.2)
     g = torch.Generator().manual_seed(5)
     args = _mmbt_args(cfg, precision, dropout=drop["img"],
@@ -166,15 +169,15 @@ def test_mmbt_training_with_dropout_matches_oracle_under_the_same_masks(mmu, pre
             else:
                 p.copy_(torch.randn(p.shape, generator=g) * 0.08)
     P = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    txt = torch.randint(7, cfg["vocab"], (3, 150), generator=g)
-    lens = torch.tensor([150, 97, 31])
-    mask = (torch.arange(150)[None] < lens[:, None]).long()
+    txt = torch.randint(7, cfg["vocab"], (3, s_txt), generator=g)
+    lens = torch.tensor([s_txt, (2 * s_txt) // 3 - 3, 31])
+    mask = (torch.arange(s_txt)[None] < lens[:, None]).long()
     txt, segment = txt * mask, mask.clone()
     tok = torch.randn(3, 3, 64, generator=g)
     y = torch.tensor([0, 1, 1])
     idx = None
     if indices == "control":
-        idx = O.control_indices(155, 60, torch.Generator().manual_seed(9))
+        idx = O.control_indices(s_txt + 5, 60, torch.Generator().manual_seed(9))
     m.cuda().train()
     m.zero_grad()
     t = tok.cuda().requires_grad_(True)

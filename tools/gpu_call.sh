@@ -1,10 +1,5 @@
 mkdir -p gpurun_out
-( time python -m pytest tests -m gpu -x -q ) > gpurun_out/r2j_pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/r2j_pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2j_smoke.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/r2j_smoke.log
-python bench.py > gpurun_out/r2j_bench.json 2> gpurun_out/r2j_bench.err; echo "bench exit $?"; python -c "
-import json
-d=json.loads(open('gpurun_out/r2j_bench.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e'], d['clocks'])
-print(d['roofline']['achieved'], d['roofline']['frac'], d['roofline']['eval_gemms']['frac'], d['whole_step']['frac'])
-print({k: (v if not isinstance(v, dict) else {kk: vv for kk, vv in v.items() if kk in ('value','ms_per_step','samples_per_s')}) for k, v in d.get('incumbent', {}).items()} if isinstance(d.get('incumbent'), dict) else d.get('incumbent'))
-print(d.get('cpu_baseline'))"
+( timeout 900 python -m pytest tests/test_gpu_dropout.py tests/test_gpu_mmbt.py -m gpu -x -q ) > gpurun_out/r2k_pytest_mmbt.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/r2k_pytest_mmbt.log
+python tools/bench_mmbt.py --bert-dropout 0.1 > gpurun_out/r2k_mmbt_drop01.log 2>&1; echo "exit $?"; tail -3 gpurun_out/r2k_mmbt_drop01.log
+MMU_ATTN_UNFUSED=1 python tools/bench_mmbt.py --bert-dropout 0.1 > gpurun_out/r2k_mmbt_drop01_unfused.log 2>&1; echo "exit $?"; tail -3 gpurun_out/r2k_mmbt_drop01_unfused.log
+python tools/bench_mmbt.py > gpurun_out/r2k_mmbt_drop0.log 2>&1; echo "exit $?"; tail -3 gpurun_out/r2k_mmbt_drop0.log
