@@ -381,7 +381,7 @@ typedef struct {
   /* Dropout (training forward + its backward only; masks = csrc/dropout.cuh, oracle/dropout.py):
    * drop_hidden = BertConfig.hidden_dropout_prob (text embeddings; attention-output and FFN-output
    * dense layers before the residual add), drop_attn = attention_probs_dropout_prob (softmax(QK^T)
-   * before P V; the fused attention kernels do not apply it, the three-kernel path runs instead),
+   * before P V; applied inside the fused attention kernels, mask regenerated in the backward),
    * drop_img = args.dropout of ImageBertEmbeddings (src/mmbt.py:56,82).  Sites: 0 embeddings,
    * 4l+1 attention probabilities, 4l+2 attention output, 4l+3 FFN output of layer l; element
    * counters: row * D + column, resp. ((b * H + h) * S + query) * S + key. */

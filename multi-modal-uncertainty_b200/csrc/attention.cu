@@ -608,17 +608,22 @@ int seq_fwd(const void* qkv, const float* addmask, void* out, void* probs, float
 // fused kernel (dPd stays in TMEM, the mask is regenerated there, dQ = dS K comes with it) when it
 // applies, else by the dP GEMM + row kernel.
 int seq_bwd_dropout(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
-                    void* dqkv, int B, int S, int D, int H, cudaStream_t st, dropout::Site drop) {
+                    void* dqkv, int B, int S, int D, int H, cudaStream_t st, dropout::Site drop,
+                    const void* pdrop_saved) {
   const int hd = D / H, G = B * H, Sp = (S + 7) / 8 * 8;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   const int rows = G * S;
   __nv_bfloat16* dq = static_cast<__nv_bfloat16*>(dqkv);
   const long long ld = 3LL * D, mid = 3LL * D * S;
-  dropout_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(probs),
-                                                     static_cast<__nv_bfloat16*>(dprobs), rows, S, Sp, drop);
-  if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
-  count_launch();
-  int rc = gemm_bf16_batched_launch(sq_view(dprobs, G, S, Sp, 1), act_view_seq(dout, B, S, D, H, 1), G, S, hd,
+  const void* pd = pdrop_saved;
+  if (pd == nullptr) {  // the forward's dropped copy was not kept: regenerate it
+    dropout_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(probs),
+                                                       static_cast<__nv_bfloat16*>(dprobs), rows, S, Sp, drop);
+    if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
+    count_launch();
+    pd = dprobs;
+  }
+  int rc = gemm_bf16_batched_launch(sq_view(pd, G, S, Sp, 1), act_view_seq(dout, B, S, D, H, 1), G, S, hd,
                                     S, store_epi(dq + 2 * D, 1, ld, 1.0f), H, hd, mid, st);
   if (rc) return rc;
   rc = fused_seq_attention_bwd_ds(qkv, dout, probs, dprobs, dqkv, B, S, D, H, st, drop);
@@ -773,7 +778,7 @@ int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* pr
     if ((D / H) % 64 != 0 || scores == nullptr) return MMU_ERR_SHAPE;
     if (allow_fused) {  // one fused kernel when it applies (head_dim 64, S <= 512)
       const int rc = fused_seq_attention_fwd(qkv, addmask, out, keep_probs ? probs : nullptr, B, S, D, H, stream,
-                                             drop);
+                                             drop, pdrop);
       if (rc <= 0) return rc;
     }
     return tc::seq_fwd(qkv, addmask, out, probs, scores, B, S, D, H, stream, drop, pdrop);
@@ -804,13 +809,14 @@ int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* pr
 
 int seq_attention_bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
                       void* dqkv, int dtype, int B, int S, int D, int H, cudaStream_t stream,
-                      dropout::Site drop) {
+                      dropout::Site drop, const void* pdrop_saved) {
   using namespace attn;
   if (qkv == nullptr || dout == nullptr || probs == nullptr || scores == nullptr || dqkv == nullptr)
     return MMU_ERR_ARG;
   if (dtype == DT_BF16) {
     if ((D / H) % 64 != 0 || dprobs == nullptr) return MMU_ERR_SHAPE;
-    if (drop.on()) return tc::seq_bwd_dropout(qkv, dout, probs, scores, dprobs, dqkv, B, S, D, H, stream, drop);
+    if (drop.on())
+      return tc::seq_bwd_dropout(qkv, dout, probs, scores, dprobs, dqkv, B, S, D, H, stream, drop, pdrop_saved);
     return tc::seq_bwd(qkv, dout, probs, scores, dprobs, dqkv, B, S, D, H, stream);
   }
   using seq32::Strided;

@@ -68,9 +68,9 @@ __device__ __forceinline__ void nbar(int id, int n) { asm volatile("bar.sync %0,
 template <bool SAVE_P, bool DROP>
 __global__ void __launch_bounds__(THREADS, 1)
 fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_v,
-                 const __grid_constant__ CUtensorMap tm_p, const float* __restrict__ addmask,
-                 __nv_bfloat16* __restrict__ out, int B, int S, int D, int H, float scale, int tiles_per_cta,
-                 const dropout::Site drop) {
+                 const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_pd,
+                 const float* __restrict__ addmask, __nv_bfloat16* __restrict__ out, int B, int S, int D, int H,
+                 float scale, int tiles_per_cta, const dropout::Site drop, int save_pd) {
   static_assert(!DROP || SAVE_P, "dropout exists in training only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -104,6 +104,7 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
     ptx::prefetch_tmap(&tm_qk);
     ptx::prefetch_tmap(&tm_v);
     if (SAVE_P) ptx::prefetch_tmap(&tm_p);
+    if (DROP) ptx::prefetch_tmap(&tm_pd);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 12; ++i) ptx::mbar_init(&bars[i], 1);
@@ -326,6 +327,8 @@ fattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constan
           ptx::mbar_arrive(&p_full[hh * 2 + buf]);
           if (SAVE_P) {
             ptx::tma_store_3d(&tm_p, pst, c * CH, g, q0);
+            // the dropped copy too (dV = Pd^T dO reads it): the MMA operand tile, read concurrently by MMA2
+            if (DROP && save_pd) ptx::tma_store_3d(&tm_pd, pbuf, c * CH, g, q0);
             ptx::bulk_commit();
           }
         }
@@ -505,7 +508,10 @@ fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_cons
     // element counter of (this query row, key 0) in the forward's mask
     const unsigned int e_row = (static_cast<unsigned int>(g) * static_cast<unsigned int>(S) +
                                 static_cast<unsigned int>(q0 + row)) * static_cast<unsigned int>(S);
-    auto undrop = [&](int c, int j) {   // dPd -> dP in place (registers)
+    // dPd -> dP in place (registers); the mask function is evaluated in both passes (keeping one
+    // bit per element from pass 1 in eight registers made the kernel 35 % SLOWER: the fully
+    // unrolled passes lose the overlap of the TMEM loads with the arithmetic)
+    auto undrop = [&](int c, int j) {
       if constexpr (DROP) {
         const unsigned int e0 = e_row + static_cast<unsigned int>(c * CH + j * 32);
 #pragma unroll
@@ -605,13 +611,13 @@ fattn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_do, const __grid_cons
 
 // Returns 1 when the fused kernel does not apply (caller falls back to the three-kernel path).
 int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, int B, int S,
-                            int D, int H, cudaStream_t stream, dropout::Site drop) {
+                            int D, int H, cudaStream_t stream, dropout::Site drop, void* pdrop) {
   using namespace fattn;
   static const bool disabled = getenv("MMU_ATTN_UNFUSED") != nullptr;  // A/B switch
   if (disabled || D / H != HD || D % H != 0 || S > SMAX || S < 1) return 1;
   if (drop.on() && probs == nullptr) return 1;   // dropout: training only
   const int Sp = (S + 7) / 8 * 8;
-  CUtensorMap tq, tv, tp;
+  CUtensorMap tq, tv, tp, tpd;
   int rc = make_tmap_bf16_3d(&tq, qkv, 3LL * D, B, S, 3LL * D * S, 3LL * D, HD, KB);
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&tv, qkv, 3LL * D, B, S, 3LL * D * S, 3LL * D, HD, CH);
@@ -619,6 +625,13 @@ int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, vo
   tp = tq;
   if (probs != nullptr) {
     rc = make_tmap_bf16_3d(&tp, probs, Sp, static_cast<long long>(B) * H, S, static_cast<long long>(S) * Sp,
+                           Sp, CH, BQ);
+    if (rc) return rc;
+  }
+  tpd = tp;
+  const int save_pd = (drop.on() && pdrop != nullptr) ? 1 : 0;
+  if (save_pd) {
+    rc = make_tmap_bf16_3d(&tpd, pdrop, Sp, static_cast<long long>(B) * H, S, static_cast<long long>(S) * Sp,
                            Sp, CH, BQ);
     if (rc) return rc;
   }
@@ -637,8 +650,8 @@ int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, vo
     static cudaError_t attr = cudaSuccess;
     attr = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (attr != cudaSuccess) return MMU_ERR_CUDA;
-    kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tq, tv, tp, addmask, static_cast<__nv_bfloat16*>(out), B, S,
-                                                  D, H, scale, tpc, drop);
+    kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tq, tv, tp, tpd, addmask, static_cast<__nv_bfloat16*>(out),
+                                                  B, S, D, H, scale, tpc, drop, save_pd);
     if (cudaGetLastError() != cudaSuccess) return MMU_ERR_CUDA;
     count_launch();
     return 0;

@@ -161,13 +161,15 @@ int seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* pr
 // multiplied by the regenerated mask.
 int fused_seq_attention_fwd(const void* qkv, const float* addmask, void* out, void* probs, int B, int S,
                             int D, int H, cudaStream_t stream,
-                            dropout::Site drop = dropout::Site{0u, 0u, 0u, 1.0f});
+                            dropout::Site drop = dropout::Site{0u, 0u, 0u, 1.0f}, void* pdrop = nullptr);
 int fused_seq_attention_bwd_ds(const void* qkv, const void* dout, const void* probs, void* dprobs, void* dqkv,
                                int B, int S, int D, int H, cudaStream_t stream,
                                dropout::Site drop = dropout::Site{0u, 0u, 0u, 1.0f});
+// pdrop_saved (bf16 path with dropout): the dropped probabilities the forward wrote to its `pdrop`
+// argument, if the caller kept them; else they are regenerated from `probs`.
 int seq_attention_bwd(const void* qkv, const void* dout, const void* probs, float* scores, void* dprobs,
                       void* dqkv, int dtype, int B, int S, int D, int H, cudaStream_t stream,
-                      dropout::Site drop = dropout::Site{0u, 0u, 0u, 1.0f});
+                      dropout::Site drop = dropout::Site{0u, 0u, 0u, 1.0f}, const void* pdrop_saved = nullptr);
 
 // ---- fused softmax-CE / accuracy / uncertainty / calibration-histogram epilogue
 struct MetricAccum {  // lives in device memory; all-reduced (sum) across ranks

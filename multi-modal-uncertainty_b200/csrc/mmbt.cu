@@ -152,6 +152,7 @@ int build_layout(const MmbtConfig& c, Layout* L, ParamEntry* out, int max_entrie
 struct LayerWs {
   void* qkv;     // act [M, 3D]
   void* probs;   // bf16 [G, S, Sp] / fp32 [G, S, S]
+  void* pdrop;   // bf16 training with attention dropout: the dropped probabilities (dV = Pd^T dO)
   void* ctx;     // act [M, D]
   float* s1;     // fp32 [M, D]  h + attention branch (pre-LN)
   float* st1;    // mean | rstd
@@ -234,6 +235,7 @@ void carve(const MmbtConfig& c, int training, void* base, const Layout& lay, Ws*
     }
     l.qkv = b.take<void>(M * 3 * D * s);
     l.probs = b.take<void>(sq * (bf ? 2 : 4));
+    l.pdrop = (training && bf && c.drop_attn > 0.f) ? b.take<void>(sq * 2) : nullptr;
     l.ctx = b.take<void>(M * D * s);
     l.s1 = b.take<float>(M * D * 4);
     l.st1 = b.take<float>(2 * M * 4);
@@ -618,7 +620,7 @@ int mmbt_forward(const MmbtConfig& c, const float* params, const MmbtInputs& in,
     // backward's dS buffer; fp32: the score scratch, unused by the fp32 forward)
     MB_TRY(seq_attention_fwd(l.qkv, w.addmask, l.ctx, l.probs, w.scores, dt, c.B, S, D, c.n_head, stream,
                              training, 1, site(c.drop_attn, 4 * i + 1),
-                             bf ? w.dprobs : static_cast<void*>(w.scores)));
+                             bf ? (l.pdrop != nullptr ? l.pdrop : w.dprobs) : static_cast<void*>(w.scores)));
     MB_TRY(gemm(l.ctx, D, 0, W(p.ao_w), D, 0, M, D, D, epi(EPI_STORE, w.ybuf, bf, D, params + p.ao_b)));
     MB_TRY(postln_fwd(h, w.ybuf, training ? l.s1 : nullptr, params + p.ln1_w, params + p.ln1_b, l.a, dt,
                       training ? l.st1 : nullptr, training ? l.st1 + M : nullptr, M, D, BERT_LN_EPS,
@@ -755,7 +757,7 @@ int mmbt_backward(const MmbtConfig& c, const float* params, const MmbtInputs& in
                 wsplits(D, D, M)));
     MB_TRY(gemm(LP(w.gB), D, 0, W(p.ao_w), D, 1, M, D, D, epi(EPI_STORE, w.dh, bf, D, nullptr)));
     MB_TRY(seq_attention_bwd(l.qkv, w.dh, l.probs, w.scores, w.dprobs, w.dbig, dt, c.B, S, D, c.n_head,
-                             stream, site(c.drop_attn, 4 * i + 1)));
+                             stream, site(c.drop_attn, 4 * i + 1), bf ? l.pdrop : nullptr));
     // dWqkv[3D, D] += dqkv^T h ; dbqkv += colsum(dqkv) ; dh_branch = dqkv Wqkv
     MB_TRY(gemm(w.dbig, 3 * D, 1, h_in, D, 1, 3 * D, D, M, epi(EPI_ATOMIC, grads + p.q_w, 0, D, nullptr),
                 wsplits(3 * D, D, M)));

@@ -19,8 +19,8 @@ executed by the CUDA MMBT engine (``csrc/mmbt.cu``).
   ``attention_probs_dropout_prob`` or ``args.bert_dropout`` change them) and
   ``ImageBertEmbeddings.dropout`` (``args.dropout``, ``src/mmbt.py:56,82``).  Masks come from the
   engine's counter-based generator (``csrc/dropout.cuh``; statistical parity with torch's Philox
-  draws, bit-exact against ``oracle/dropout.py``) and are regenerated in the backward; with
-  attention dropout the three-kernel attention path runs instead of the fused kernels.
+  draws, bit-exact against ``oracle/dropout.py``) and are regenerated in the backward, also
+  inside the fused attention kernels (bf16, head_dim 64, S <= 512).
 There is no CPU path.
 """
 import ctypes as C
