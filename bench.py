@@ -352,6 +352,16 @@ def run_gpu(args):
 
     for i in range(args.warmup):
         step_resident(i)
+    # Both timed legs should see the board in the SAME state.  A B200 under this step reaches its
+    # power cap after a few hundred ms; the second leg used to start on an already capped board --
+    # an apparent 3-6 % "end-to-end overhead" that an interleaved measurement (tools/e2e_probe.py:
+    # 13.47 vs 13.43-13.52 ms) and the CUPTI timeline of the e2e loop (0.05 ms idle per step) do
+    # not show.  So each leg now starts the same way: >= --leg-pause-s of idle, then W warm-up steps.
+    # --settle-steps N (default 0) adds N untimed steps before the first leg instead, for a
+    # sustained-state number (same count on every rank; reported as config.settle_steps).
+    settle_steps = 0 if args.profile else max(0, int(args.settle_steps))
+    for i in range(settle_steps):
+        step_resident(i)
     ms, launches, clocks = timed(step_resident, args.steps, sampler)
     meter.all_reduce()
     summary = meter.compute()
@@ -360,6 +370,9 @@ def run_gpu(args):
             print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps,
                               "gpu_launches": int(launches)}))
         return
+    if args.leg_pause_s > 0:
+        barrier()
+        time.sleep(args.leg_pause_s)
     run_e2e(max(2, args.warmup))
     meter.reset()
     barrier()
@@ -423,6 +436,8 @@ def run_gpu(args):
                        "parallelism": f"dp{world}",
                        "dead_tokens": "skipped (live-token path: only positions < E computed)" if live
                        else "computed (as written)",
+                       "legs": f"value, then e2e; each after idle (>= {args.leg_pause_s} s before e2e) + warm-up steps; "
+                               f"{settle_steps} extra settle steps before value",
                        "l2": "working set ~6 GB/step >> 126 MB L2, inputs rotate over 4 batches"},
             "e2e": {"value": round(e2e_value, 2), "unit": "samples/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * world,  # loss + acc, 4 B each, per rank
@@ -923,6 +938,12 @@ def main():
     ap.add_argument("--no-incumbent", action="store_true", help="skip the eager-on-B200 incumbent leg")
     ap.add_argument("--rooflines-only", action="store_true",
                     help="only the per-kernel roofline legs (for ncu --metrics dram__bytes_* captures)")
+    ap.add_argument("--settle-steps", type=int, default=0,
+                    help="untimed extra steps beyond --warmup before the first timed leg (40 = ~0.5 s: the board "
+                         "is in its sustained, power-capped state when the timing starts)")
+    ap.add_argument("--leg-pause-s", type=float, default=1.5,
+                    help="idle time before the warm-up of the second (e2e) timed leg, so that it starts from the "
+                         "same board state as the first")
     ap.add_argument("--profile", action="store_true",
                     help="skip the e2e / roofline / CPU legs (short run for ncu)")
     args = ap.parse_args()

@@ -136,3 +136,28 @@ for rnd in range(4):            # interleaved rounds cancel the thermal drift of
         out[name].append(round(timed(fn, 10), 3))
 out["mean"] = {k: round(sum(v) / len(v), 3) for k, v in out.items()}
 print(json.dumps(out))
+
+# ---- CUPTI view of the e2e loop: where does the GPU idle?  (MMU_E2E_TIMELINE=1)
+if os.environ.get("MMU_E2E_TIMELINE"):
+    from torch.profiler import ProfilerActivity, profile
+    run_prefetch_async(30)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        run_prefetch_async(6)
+        torch.cuda.synchronize()
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    kern = sorted((e for e in ev if "Memcpy" not in e.name and "Memset" not in e.name), key=lambda e: e.time_range.start)
+    copies = [e for e in ev if "Memcpy HtoD" in e.name]
+    t0, t1 = kern[0].time_range.start, max(e.time_range.end for e in kern)
+    gaps, cur = [], kern[0].time_range.end
+    for e in kern[1:]:
+        if e.time_range.start > cur + 5:      # > 5 us of no kernel running
+            gaps.append((round(cur - t0, 1), round(e.time_range.start - cur, 1), e.name[:60]))
+        cur = max(cur, e.time_range.end)
+    gaps.sort(key=lambda g: -g[1])
+    big = [e for e in copies if e.time_range.end - e.time_range.start > 100]
+    print(json.dumps({"span_ms_per_step": (t1 - t0) / 6e3, "idle_ms_per_step": sum(g[1] for g in gaps) / 6e3,
+                      "largest_gaps_us(at, len, next kernel)": gaps[:12],
+                      "h2d_big_copies": len(big),
+                      "h2d_ms_per_step": sum(e.time_range.end - e.time_range.start for e in big) / 6e3,
+                      "h2d_GBps": [round((93194240 / 2 if False else 0), 1)][:0]}), file=sys.stderr)
