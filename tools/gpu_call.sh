@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
-for i in 1 2; do
-python bench.py --no-incumbent --no-cpu --no-other-configs > gpurun_out/r2p_bench$i.json 2> gpurun_out/r2p_bench$i.err; echo "bench exit $?"; python -c "
-import json
-d=json.loads(open('gpurun_out/r2p_bench$i.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e'], d['clocks'], d['config'].get('legs'))"
-done
+CMD="python bench.py --steps 1 --warmup 1 --profile"
+$CMD > gpurun_out/r2q_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:battn_fwd -s 3 -c 2 -o gpurun_out/r2q_battn $CMD > gpurun_out/r2q_ncu_battn.log 2>&1
+echo "exit $?"; tail -3 gpurun_out/r2q_ncu_battn.log
