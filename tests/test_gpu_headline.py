@@ -180,6 +180,27 @@ def sweep_oracle(mmu, case):
     return variants, ref
 
 
+def test_packed_sweep_is_bit_reproducible_at_headline_size(mmu, case):
+    """The bf16 eval forward has no atomics (residual / LayerNorm epilogues, fused batch-axis
+    attention, per-slab row sums): twelve runs of the packed 10-level sweep at B = 128, 1 327
+    positions -- with other work queued in between to move the timing -- must agree bit for bit.
+    A missing barrier or a staging box recycled too early in the new kernels would show up here."""
+    m = make_model(mmu, "bf16")
+    m.load_state_dict(case["P"], strict=True)
+    m.cuda().eval()
+    variants = sweep_variants(mmu)
+    img, txt = case["img"].cuda(), case["txt"].cuda()
+    noise = torch.randn(4096, 4096, device="cuda")
+    with torch.no_grad():
+        first = m.forward_variants((img, txt), variants).clone()
+        for i in range(11):
+            if i % 3 == 0:
+                noise = noise @ noise * 1e-4       # unrelated work in the queue
+            again = m.forward_variants((img, txt), variants)
+            assert torch.equal(again, first), f"run {i + 1} differs from run 0"
+    assert torch.isfinite(first).all()
+
+
 def _sweep_compare(mmu, case, sweep_oracle, precision):
     from oracle import uncertainty
     variants, ref = sweep_oracle
