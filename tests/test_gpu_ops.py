@@ -152,7 +152,8 @@ def test_layernorm(mmu, D):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 3e-2)])
 @pytest.mark.parametrize("B,L,D,H", [(4, 8, 64, 2), (9, 11, 96, 3), (128, 3, 768, 3), (70, 2, 48, 2),
-                                     (50, 5, 128, 2), (128, 4, 256, 2), (200, 2, 768, 3)])
+                                     (50, 5, 128, 2), (128, 4, 256, 2), (200, 2, 768, 3), (90, 60, 768, 3),
+                                     (33, 7, 256, 1)])
 def test_batch_axis_attention(mmu, dtype, tol, B, L, D, H):
     """Against the oracle's restatement of nn.MultiheadAttention(batch_first=False) on (B, L, D)."""
     hd = D // H
@@ -236,7 +237,7 @@ def test_gemm_folded_layernorm_and_residual_epilogue(mmu, M, D, N, measured):
 
 
 @pytest.mark.parametrize("B,L,D,H", [(128, 5, 768, 3), (100, 3, 768, 3), (37, 4, 512, 2), (128, 160, 768, 3),
-                                     (8, 2, 256, 1)])
+                                     (8, 2, 256, 1), (50, 70, 768, 3), (72, 200, 256, 1)])
 def test_fused_batch_axis_attention_eval(mmu, B, L, D, H, measured):
     """The fused eval kernel (head_dim 256, B <= 128; keep_probs=False) against the oracle and
     against the two-kernel path, in both row orders; rows / keys beyond B are padding inside the
