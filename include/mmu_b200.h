@@ -302,8 +302,8 @@ MMU_API long long mmu_flava_workspace_bytes(const mmu_flava_config* cfg, int tra
 MMU_API int mmu_flava_num_stages(const mmu_flava_config* cfg);
 
 typedef struct {
-  const float* img;    /* (B, l_img, d_img) fp32 or NULL (modality absent) */
-  const float* txt;    /* (B, l_txt, d_txt) fp32 or NULL */
+  const void* img;     /* (B, l_img, d_img) fp32 (bf16 with src_bf16) or NULL (modality absent) */
+  const void* txt;     /* (B, l_txt, d_txt) fp32 (bf16 with src_bf16) or NULL */
   const int* idx_img;  /* int32[n_img] token subset or NULL (first n_img tokens) */
   const int* idx_txt;
   int n_img, n_txt;    /* tokens fed to the model (<= l_img / l_txt) */
@@ -324,7 +324,9 @@ typedef struct {
    * hash(seed, site = i, r * 4D + c) >= floor(p * 2^32) and scaled by 1 / (1 - p) -- the mask
    * function of csrc/dropout.cuh, restated in oracle/dropout.py.  drop_p == 0: no dropout. */
   float drop_p;
-  int drop_reserved;
+  int src_bf16;  /* 1: img / txt point to bf16 tensors of the same shapes (bf16 host staging: half the
+                    host->device bytes; the bf16 engine rounds its inputs to bf16 in the stem anyway, so
+                    the results are bit-identical to feeding the fp32 values that round to them) */
   unsigned long long drop_seed;
 } mmu_flava_inputs;
 

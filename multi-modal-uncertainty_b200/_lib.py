@@ -110,7 +110,7 @@ class FlavaInputs(C.Structure):
                 ("idx_txt", C.c_void_p), ("n_img", C.c_int), ("n_txt", C.c_int),
                 ("keep", C.c_void_p), ("params_bf16", C.c_void_p), ("src_l_img", C.c_int),
                 ("src_l_txt", C.c_int), ("n_variants", C.c_int), ("var_segments", C.c_void_p),
-                ("drop_p", C.c_float), ("drop_reserved", C.c_int), ("drop_seed", C.c_ulonglong)]
+                ("drop_p", C.c_float), ("src_bf16", C.c_int), ("drop_seed", C.c_ulonglong)]
 
 
 def _load():

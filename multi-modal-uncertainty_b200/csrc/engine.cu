@@ -430,14 +430,14 @@ int flava_forward(const FlavaConfig& c, const float* params, const FlavaInputs& 
   // problems -- are adjacent in memory.
   if (s.n_img > 0) {
     MMU_TRY(cast_gather(in.img, w.img_t, dt_stem, c.B, src_l_img, c.d_img, in.idx_img, s.n_img,
-                        in.keep, 0, stream, 1));
+                        in.keep, 0, stream, 1, in.src_bf16 ? DT_BF16 : DT_F32));
     GemmEpilogue e = epi(EPI_STORE, w.mm_x + static_cast<long long>(s.n_cls) * c.B * D, 0, D,
                          params + lay.img_b);
     MMU_TRY(gemm_stem(w.img_t, c.d_img, 0, Wstem(lay.img_w), c.d_img, 0, c.B * s.n_img, D, c.d_img, e));
   }
   if (s.n_txt > 0) {
     MMU_TRY(cast_gather(in.txt, w.txt_t, dt_stem, c.B, src_l_txt, c.d_txt, in.idx_txt, s.n_txt,
-                        in.keep, 1, stream, 1));
+                        in.keep, 1, stream, 1, in.src_bf16 ? DT_BF16 : DT_F32));
     GemmEpilogue e = epi(EPI_STORE, w.mm_x + static_cast<long long>(s.n_cls + s.n_img) * c.B * D, 0, D,
                          params + lay.txt_b);
     MMU_TRY(gemm_stem(w.txt_t, c.d_txt, 0, Wstem(lay.txt_w), c.d_txt, 0, c.B * s.n_txt, D, c.d_txt, e));

@@ -46,8 +46,8 @@ long long flava_workspace_bytes(const FlavaConfig& c, int training);
 int flava_num_stages(const FlavaConfig& c);  // backward stages: heads, layers (reversed), stem
 
 struct FlavaInputs {
-  const float* img;     // (B, l_img, d_img) fp32 or null
-  const float* txt;     // (B, l_txt, d_txt) fp32 or null
+  const void* img;      // (B, l_img, d_img) fp32 (bf16 with src_bf16) or null
+  const void* txt;      // (B, l_txt, d_txt) fp32 (bf16 with src_bf16) or null
   const int* idx_img;   // device int32[n_img] token subset, or null for identity
   const int* idx_txt;
   int n_img;            // tokens used (0: modality absent); <= l_img
@@ -68,7 +68,7 @@ struct FlavaInputs {
   // nn.Dropout(drop) between c_fc and QuickGELU (src/model.py:195-201), training only: counter-
   // based masks (csrc/dropout.cuh), site = layer index; the backward must see the same values.
   float drop_p;
-  int drop_reserved;
+  int src_bf16;  // 1: img / txt point to bf16 tensors (bf16 host staging), 0: fp32
   unsigned long long drop_seed;
 };
 

@@ -16,8 +16,10 @@ enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
 // src fp32 [B, l_src, d] -> dst (dtype) [B, n_sel, d].  idx (device int32[n_sel]) may be null
 // (identity).  keep (device int32[B, 2]) may be null; modality selects its column.
 // pos_major: destination rows ordered (token position, sample) instead of (sample, position).
-int cast_gather(const float* src, void* dst, int dst_dtype, int B, int l_src, int d, const int* idx,
-                int n_sel, const int* keep, int modality, cudaStream_t stream, int pos_major = 0);
+// src_dtype: DT_F32 (the reference's embeddings) or DT_BF16 (bf16 host staging: half the H2D bytes).
+int cast_gather(const void* src, void* dst, int dst_dtype, int B, int l_src, int d, const int* idx,
+                int n_sel, const int* keep, int modality, cudaStream_t stream, int pos_major = 0,
+                int src_dtype = DT_F32);
 int cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t stream);
 // guided / random modality-dropout keep mask int32[B,2] from host-drawn uniforms u, r (fp32[B]) and,
 // for mode 1 (guided), device-resident per-sample scores (element b at score_*[b*score_stride])

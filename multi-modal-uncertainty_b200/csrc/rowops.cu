@@ -72,8 +72,8 @@ int grid_for(size_t work_items, int per_block) {
 }
 
 // ------------------------------------------------------------------ cast / gather / mask
-template <typename T>
-__global__ void cast_gather_kernel(const float* __restrict__ src, T* __restrict__ dst, int B,
+template <typename T, typename TS = float>
+__global__ void cast_gather_kernel(const TS* __restrict__ src, T* __restrict__ dst, int B,
                                    int l_src, int d, const int* __restrict__ idx, int n_sel,
                                    const int* __restrict__ keep, int modality, int pos_major) {
   ptx::pdl_trigger();  // a following tensor-core GEMM may start its prologue early
@@ -88,7 +88,7 @@ __global__ void cast_gather_kernel(const float* __restrict__ src, T* __restrict_
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (keep == nullptr || keep[b * 2 + modality] != 0) {
       const int l = idx != nullptr ? idx[j] : j;
-      v = *reinterpret_cast<const float4*>(src + (static_cast<size_t>(b) * l_src + l) * d + 4 * c);
+      v = Vec4<TS>::ld(src + (static_cast<size_t>(b) * l_src + l) * d + 4 * c);
     }
     Vec4<T>::st(dst + row * d + 4 * c, v);
   }
@@ -1024,18 +1024,29 @@ int nv_for(int D) {
 }  // namespace
 
 // ======================================================================= launchers
-int cast_gather(const float* src, void* dst, int dst_dtype, int B, int l_src, int d, const int* idx,
-                int n_sel, const int* keep, int modality, cudaStream_t stream, int pos_major) {
+int cast_gather(const void* src, void* dst, int dst_dtype, int B, int l_src, int d, const int* idx,
+                int n_sel, const int* keep, int modality, cudaStream_t stream, int pos_major, int src_dtype) {
   if (d % 4 != 0) return MMU_ERR_SHAPE;
   if (B <= 0 || n_sel <= 0) return 0;
   const size_t total = static_cast<size_t>(B) * n_sel * (d / 4);
   const int grid = grid_for(total, 256);
-  if (dst_dtype == DT_BF16)
-    cast_gather_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
-        src, static_cast<__nv_bfloat16*>(dst), B, l_src, d, idx, n_sel, keep, modality, pos_major);
-  else
-    cast_gather_kernel<float><<<grid, 256, 0, stream>>>(src, static_cast<float*>(dst), B, l_src, d,
-                                                        idx, n_sel, keep, modality, pos_major);
+  using bf = __nv_bfloat16;
+  if (src_dtype == DT_BF16) {  // host staging in bf16 (half the H2D bytes; the bf16 stem rounds anyway)
+    if (dst_dtype == DT_BF16)
+      cast_gather_kernel<bf, bf><<<grid, 256, 0, stream>>>(static_cast<const bf*>(src), static_cast<bf*>(dst), B,
+                                                           l_src, d, idx, n_sel, keep, modality, pos_major);
+    else
+      cast_gather_kernel<float, bf><<<grid, 256, 0, stream>>>(static_cast<const bf*>(src),
+                                                              static_cast<float*>(dst), B, l_src, d, idx,
+                                                              n_sel, keep, modality, pos_major);
+  } else if (dst_dtype == DT_BF16) {
+    cast_gather_kernel<bf><<<grid, 256, 0, stream>>>(static_cast<const float*>(src), static_cast<bf*>(dst), B,
+                                                     l_src, d, idx, n_sel, keep, modality, pos_major);
+  } else {
+    cast_gather_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(src),
+                                                        static_cast<float*>(dst), B, l_src, d, idx, n_sel,
+                                                        keep, modality, pos_major);
+  }
   MMU_CHECK_LAUNCH();
   return 0;
 }

@@ -345,6 +345,15 @@ class FlavaFusionTransfomer(nn.Module):
             self._ws[key] = ws
         return ws
 
+    @staticmethod
+    def _inputs_bf16(img, txt):
+        """bf16 host staging: when every given modality arrives as a bf16 tensor it is handed to the
+        engine as is (half the host->device bytes).  The bf16 engine rounds its inputs to bf16 in
+        the stem anyway, so this is bit-identical to feeding the fp32 values that round to them;
+        the fp32 engine widens them exactly.  Mixed or other dtypes are converted to fp32."""
+        given = [t for t in (img, txt) if t is not None]
+        return bool(given) and all(t.dtype == torch.bfloat16 for t in given)
+
     def _engine_forward(self, img, txt, idx_img, idx_txt, keep, training):
         if not self._flat.is_cuda:
             raise _lib.MMUError("the model lives on the CPU: call .to('cuda') first -- this "
@@ -356,8 +365,10 @@ class FlavaFusionTransfomer(nn.Module):
         B = ref.shape[0]
         dev = self._flat.device
 
+        src_bf16 = self._inputs_bf16(img, txt)
+
         def prep(t):
-            return None if t is None else t.to(device=dev, dtype=torch.float32).contiguous()
+            return None if t is None else t.to(device=dev, dtype=torch.bfloat16 if src_bf16 else torch.float32).contiguous()
 
         def prep_idx(i):
             return None if i is None else i.to(device=dev, dtype=torch.int32).contiguous()
@@ -373,6 +384,7 @@ class FlavaFusionTransfomer(nn.Module):
         shadow = self._fresh_shadow()
         inp = _lib.FlavaInputs(_lib.ptr(img), _lib.ptr(txt), _lib.ptr(idx_img), _lib.ptr(idx_txt),
                                n_img, n_txt, _lib.ptr(keep), _lib.ptr(shadow))
+        inp.src_bf16 = int(src_bf16)
         if training and self.drop > 0.0:
             # nn.Dropout(drop) between c_fc and QuickGELU (reference src/model.py:195-201): the
             # masks are a function of this seed (drawn from torch's CPU generator, so
@@ -471,8 +483,10 @@ class FlavaFusionTransfomer(nn.Module):
         idx_img = packed[seg_t.numel(): seg_t.numel() + Ni] if Ni else None
         idx_txt = packed[seg_t.numel() + Ni:] if Nt else None
 
+        src_bf16 = self._inputs_bf16(img if Ni else None, txt if Nt else None)
+
         def prep(t):
-            return None if t is None else t.to(device=dev, dtype=torch.float32).contiguous()
+            return None if t is None else t.to(device=dev, dtype=torch.bfloat16 if src_bf16 else torch.float32).contiguous()
 
         img, txt = prep(img) if Ni else None, prep(txt) if Nt else None
         B = (img if img is not None else txt).shape[0]
@@ -488,6 +502,7 @@ class FlavaFusionTransfomer(nn.Module):
                                Ni, Nt, 0, _lib.ptr(self._fresh_shadow()),
                                img.shape[1] if img is not None else 0,
                                txt.shape[1] if txt is not None else 0, V, _lib.ptr(seg_d))
+        inp.src_bf16 = int(src_bf16)
         logits = torch.empty(V, B, self.out_dim, self.num_classes, device=dev, dtype=torch.float32)
         _lib.check(_lib.lib.mmu_flava_forward(C.byref(cfg), self._flat.data_ptr(), C.byref(inp),
                                               ws.data_ptr(), ws.numel(), 0, logits.data_ptr(),

@@ -320,6 +320,37 @@ def test_device_prefetcher_yields_host_batches_in_order(mmu):
     assert seen == len(host)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_bf16_host_staging_is_bit_identical(mmu, golden, precision):
+    """Inputs handed over as bf16 tensors (half the host->device bytes) give, bit for bit, what the
+    fp32 tensors holding the same (bf16-representable) values give: training forward, eval forward
+    and the packed-variant sweep (gradients: to the summation order of the split-K atomics)."""
+    c = golden("flava_small.pt")["plain_E5_h3"]
+    cfg = c["cfg"]
+    img16, txt16 = c["img"].to(torch.bfloat16), c["txt"].to(torch.bfloat16)
+    img32, txt32 = img16.float(), txt16.float()
+    outs = []
+    for img, txt in ((img32, txt32), (img16, txt16)):
+        m = build(mmu, cfg, c["state_dict"], precision).train()
+        m.zero_grad()
+        logits = m((img.cuda(), txt.cuda()))
+        m.compute_loss(logits, c["y_train"].cuda()).backward()
+        grads = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()
+        m.eval()
+        with torch.no_grad():
+            ev = m((img.cuda(), txt.cuda()))
+            variants = [(torch.arange(cfg["l_img"]), torch.arange(cfg["l_txt"])),
+                        (torch.arange(cfg["l_img"])[::2], None)]
+            variants = [v for v in variants if sum(len(i) for i in v if i is not None) >= cfg["E"]]
+            sw = m.forward_variants((img.cuda(), txt.cuda()), variants)
+        outs.append((logits.detach().clone(), grads, ev.clone(), sw.clone()))
+    for k, (a, b) in enumerate(zip(*outs)):
+        if k == 1:   # gradients: split-K atomics make two runs differ in the summation order
+            assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max())
+        else:
+            assert torch.equal(a, b)
+
+
 def test_async_scalars_reads_behind_queued_work(mmu):
     """metrics.AsyncScalars: per-step scalars leave on a side stream behind an event; popping ticket
     i returns step i's values even though later work (and later pushes) is already queued."""
