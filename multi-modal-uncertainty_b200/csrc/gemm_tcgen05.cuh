@@ -124,6 +124,85 @@ __device__ __forceinline__ float erf_gelu_grad(float z) {
   return fmaf(z, pdf, cdf);
 }
 
+// Packed fp32 pairs: sm_100a issues FFMA2 / FMUL2 on a 64-bit register pair -- the IEEE result of
+// the scalar op in each half for ONE issue slot.  The epilogue warps are instruction-issue limited
+// (removing ~8 FP32 instructions per element from the dGELU epilogue made its launch 13 % shorter,
+// profiles/r02_harness_act_grad_v1.log), so the per-element arithmetic below runs on pairs of
+// adjacent columns; same operations in the same order as the scalar helpers above.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t bc2(float x) { return pk2(x, x); }
+__device__ __forceinline__ void up2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sigmoid_1702_2(uint64_t z) {
+  float a0, a1, t0, t1;
+  up2(mul2(z, bc2(0.851f)), a0, a1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+  return fma2(pk2(t0, t1), bc2(0.5f), bc2(0.5f));
+}
+// (z0, z1) <- QuickGELU of the pair
+__device__ __forceinline__ void quick_gelu_pair(float& z0, float& z1) {
+  const uint64_t z = pk2(z0, z1);
+  up2(mul2(z, sigmoid_1702_2(z)), z0, z1);
+}
+// (v0, v1) <- (v0, v1) * QuickGELU'(z0, z1)
+__device__ __forceinline__ void quick_gelu_grad_pair(float& v0, float& v1, float z0, float z1) {
+  const uint64_t z = pk2(z0, z1);
+  const uint64_t sg = sigmoid_1702_2(z);
+  const uint64_t oms = fma2(sg, bc2(-1.0f), bc2(1.0f));                  // 1 - s, one rounding
+  const uint64_t g = mul2(sg, fma2(mul2(z, bc2(1.702f)), oms, bc2(1.0f)));
+  up2(mul2(pk2(v0, v1), g), v0, v1);
+}
+// erf-GELU terms of a pair: gelu_erf_terms() operation by operation (|z| k == |z k| and
+// (-c x) x is sign-symmetric, so working on the signed x = z / sqrt 2 changes no bit).
+__device__ __forceinline__ void gelu_erf_terms2(uint64_t z, uint64_t& cdf, uint64_t& pdf) {
+  const uint64_t xs = mul2(z, bc2(0.70710678118654752f));
+  float x0, x1, d0, d1, t0, t1, m0, m1, e0, e1;
+  up2(xs, x0, x1);
+  up2(fma2(bc2(0.47047f), pk2(fabsf(x0), fabsf(x1)), bc2(1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  up2(mul2(mul2(xs, bc2(-1.4426950408889634f)), xs), m0, m1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(m0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(m1));
+  const uint64_t t = pk2(t0, t1), ex = pk2(e0, e1);
+  const uint64_t poly = mul2(t, fma2(t, fma2(t, bc2(0.7478556f), bc2(-0.0958798f)), bc2(0.3480242f)));
+  const uint64_t he = mul2(mul2(bc2(0.5f), poly), ex);     // 0.5 * erfc(|z| / sqrt 2)
+  float h0, h1, o0, o1, z0, z1;
+  up2(he, h0, h1);
+  up2(fma2(he, bc2(-1.0f), bc2(1.0f)), o0, o1);            // 1 - half_erfc, one rounding
+  up2(z, z0, z1);
+  cdf = pk2(z0 >= 0.f ? o0 : h0, z1 >= 0.f ? o1 : h1);
+  pdf = mul2(bc2(0.3989422804014327f), ex);
+}
+__device__ __forceinline__ void erf_gelu_pair(float& z0, float& z1) {
+  const uint64_t z = pk2(z0, z1);
+  uint64_t cdf, pdf;
+  gelu_erf_terms2(z, cdf, pdf);
+  up2(mul2(z, cdf), z0, z1);
+}
+__device__ __forceinline__ void erf_gelu_grad_pair(float& v0, float& v1, float z0, float z1) {
+  const uint64_t z = pk2(z0, z1);
+  uint64_t cdf, pdf;
+  gelu_erf_terms2(z, cdf, pdf);
+  up2(mul2(pk2(v0, v1), fma2(z, pdf, cdf)), v0, v1);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -597,20 +676,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
                 if (has_bias) b4 = ptx::lds_v4(baddr + 16 * j);
                 // columns >= N are clipped by the store: any in-range address will do for them
                 const float4 w4 = ptx::lds_v4(cw_addr + (baddr - bias_addr) + 16 * j);
-                v[4 * j + 0] = fmaf(fmaf(ln_nmean, w4.x, __uint_as_float(r[c & 1][4 * j + 0])), ln_rstd, b4.x);
-                v[4 * j + 1] = fmaf(fmaf(ln_nmean, w4.y, __uint_as_float(r[c & 1][4 * j + 1])), ln_rstd, b4.y);
-                v[4 * j + 2] = fmaf(fmaf(ln_nmean, w4.z, __uint_as_float(r[c & 1][4 * j + 2])), ln_rstd, b4.z);
-                v[4 * j + 3] = fmaf(fmaf(ln_nmean, w4.w, __uint_as_float(r[c & 1][4 * j + 3])), ln_rstd, b4.w);
+                const uint64_t nm2 = bc2(ln_nmean), rs2 = bc2(ln_rstd);
+                up2(fma2(fma2(nm2, pk2(w4.x, w4.y),
+                              pk2(__uint_as_float(r[c & 1][4 * j + 0]), __uint_as_float(r[c & 1][4 * j + 1]))),
+                         rs2, pk2(b4.x, b4.y)), v[4 * j + 0], v[4 * j + 1]);
+                up2(fma2(fma2(nm2, pk2(w4.z, w4.w),
+                              pk2(__uint_as_float(r[c & 1][4 * j + 2]), __uint_as_float(r[c & 1][4 * j + 3]))),
+                         rs2, pk2(b4.z, b4.w)), v[4 * j + 2], v[4 * j + 3]);
               }
             } else {
 #pragma unroll
               for (int j = 0; j < NCOL / 4; ++j) {
                 float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (has_bias) b4 = ptx::lds_v4(baddr + 16 * j);
-                v[4 * j + 0] = fmaf(__uint_as_float(r[c & 1][4 * j + 0]), e.alpha, b4.x);
-                v[4 * j + 1] = fmaf(__uint_as_float(r[c & 1][4 * j + 1]), e.alpha, b4.y);
-                v[4 * j + 2] = fmaf(__uint_as_float(r[c & 1][4 * j + 2]), e.alpha, b4.z);
-                v[4 * j + 3] = fmaf(__uint_as_float(r[c & 1][4 * j + 3]), e.alpha, b4.w);
+                const uint64_t al2 = bc2(e.alpha);
+                up2(fma2(pk2(__uint_as_float(r[c & 1][4 * j + 0]), __uint_as_float(r[c & 1][4 * j + 1])), al2,
+                         pk2(b4.x, b4.y)), v[4 * j + 0], v[4 * j + 1]);
+                up2(fma2(pk2(__uint_as_float(r[c & 1][4 * j + 2]), __uint_as_float(r[c & 1][4 * j + 3])), al2,
+                         pk2(b4.z, b4.w)), v[4 * j + 2], v[4 * j + 3]);
               }
             }
           }
@@ -684,14 +767,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
               uint32_t o[4];
               if (e.act == 1) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  o[i] = pack_bf16x2(v[8 * k + 2 * i] * erf_gelu_grad(bf16_lo(zz[i])),
-                                     v[8 * k + 2 * i + 1] * erf_gelu_grad(bf16_hi(zz[i])));
+                for (int i = 0; i < 4; ++i) {
+                  erf_gelu_grad_pair(v[8 * k + 2 * i], v[8 * k + 2 * i + 1], bf16_lo(zz[i]), bf16_hi(zz[i]));
+                  o[i] = pack_bf16x2(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+                }
               } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  o[i] = pack_bf16x2(v[8 * k + 2 * i] * quick_gelu_grad(bf16_lo(zz[i])),
-                                     v[8 * k + 2 * i + 1] * quick_gelu_grad(bf16_hi(zz[i])));
+                for (int i = 0; i < 4; ++i) {
+                  quick_gelu_grad_pair(v[8 * k + 2 * i], v[8 * k + 2 * i + 1], bf16_lo(zz[i]), bf16_hi(zz[i]));
+                  o[i] = pack_bf16x2(v[8 * k + 2 * i], v[8 * k + 2 * i + 1]);
+                }
               }
               ptx::sts_v4u(a, o[0], o[1], o[2], o[3]);
             }
@@ -713,10 +798,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
             }
             if (e.act == 1) {
 #pragma unroll
-              for (int i = 0; i < NCOL; ++i) v[i] = erf_gelu(v[i]);
+              for (int i = 0; i < NCOL; i += 2) erf_gelu_pair(v[i], v[i + 1]);
             } else {
 #pragma unroll
-              for (int i = 0; i < NCOL; ++i) v[i] = quick_gelu(v[i]);
+              for (int i = 0; i < NCOL; i += 2) quick_gelu_pair(v[i], v[i + 1]);
             }
             const uint32_t ubox = e.out != nullptr ? box0 + BOX_BYTES : box;
             box_free(e.out == nullptr && c == 0);

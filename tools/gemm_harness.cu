@@ -27,6 +27,7 @@ struct Case {
   int M, N, K, a_mn, b_mn, mode, out_bf16, splits, bias, seg, timed;
   int fold;    // LayerNorm folded into the epilogue (EPI_STORE / EPI_QUICKGELU)
   int no_out;  // QUICKGELU: eval mode (u only); RESID_LN: no bf16 copy
+  int act;     // QUICKGELU / DGELU: 1 = erf-GELU (the MMBT path)
 };
 
 static const Case kCases[] = {
@@ -67,6 +68,13 @@ static const Case kCases[] = {
     {"sweep_inproj", 30336, 2304, 768, 0, 0, EPI_STORE, 1, 1, 1, 0, 1},
     {"sweep_cfc_eval", 30336, 3072, 768, 0, 0, EPI_QUICKGELU, 1, 1, 1, 0, 1, 0, 1},
     {"resid_nocopy", 1000, 520, 200, 0, 0, EPI_RESID_LN, 0, 1, 1, 0, 0, 0, 1},
+    // 36.. : erf-GELU epilogues (BERT's activation), single-CTA and CTA-pair kernels
+    {"erf_gelu_tails", 300, 520, 192, 0, 0, EPI_QUICKGELU, 1, 1, 1, 0, 0, 0, 0, 1},
+    {"erf_gelu_pair_tails", 1000, 520, 200, 0, 0, EPI_QUICKGELU, 1, 1, 1, 0, 0, 0, 0, 1},
+    {"erf_dgelu_tails", 300, 520, 192, 0, 1, EPI_DGELU, 1, 1, 0, 0, 0, 0, 0, 1},
+    {"erf_dgelu_pair_tails", 1000, 520, 200, 0, 1, EPI_DGELU, 1, 1, 0, 0, 0, 0, 0, 1},
+    {"erf_cfc", 16384, 3072, 768, 0, 0, EPI_QUICKGELU, 1, 1, 1, 0, 1, 0, 0, 1},
+    {"erf_dgrad_dgelu", 16384, 3072, 768, 0, 1, EPI_DGELU, 1, 1, 0, 0, 1, 0, 0, 1},
 };
 
 __global__ void ref_gemm(const __nv_bfloat16* A, const __nv_bfloat16* B, float* C, int M, int N,
@@ -91,6 +99,10 @@ static float qgelu(float z) { return z / (1.f + expf(-1.702f * z)); }
 static float qgelu_grad(float z) {
   float s = 1.f / (1.f + expf(-1.702f * z));
   return s * (1.f + 1.702f * z * (1.f - s));
+}
+static float egelu(float z) { return 0.5f * z * (1.f + erff(z * 0.70710678f)); }
+static float egelu_grad(float z) {
+  return 0.5f * (1.f + erff(z * 0.70710678f)) + z * 0.3989422804f * expf(-0.5f * z * z);
 }
 static float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
@@ -211,6 +223,7 @@ int main(int argc, char** argv) {
   e.seg_stride = L;
   e.seg_off = 0;
   e.alpha = 1.0f;
+  e.act = c.act;
   const long long lda = c.a_mn ? M : K, ldb = c.b_mn ? N : K;
 
   int rc = gemm_bf16_launch(dA, lda, dB, ldb, p, e, 0);
@@ -264,10 +277,14 @@ int main(int argc, char** argv) {
       if (c.fold) ref = hrstd[m] * (href[(size_t)m * N + n] - hmean[m] * hcw[n]) + (c.bias ? hbias[n] : 0.f);
       float ref2 = 0.f;
       switch (c.mode) {
-        case EPI_QUICKGELU: ref2 = qgelu(ref); break;
+        case EPI_QUICKGELU: ref2 = c.act ? egelu(ref) : qgelu(ref); break;
         case EPI_RESIDUAL:
         case EPI_RESID_LN: ref += haux_f[(size_t)orow * N + n]; break;
-        case EPI_DGELU: ref *= qgelu_grad(__bfloat162float(haux_b[(size_t)m * N + n])); break;
+        case EPI_DGELU: {
+          const float z = __bfloat162float(haux_b[(size_t)m * N + n]);
+          ref *= c.act ? egelu_grad(z) : qgelu_grad(z);
+          break;
+        }
         default: break;
       }
       float g = got[(size_t)orow * N + n];
