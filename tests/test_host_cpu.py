@@ -575,3 +575,124 @@ def test_graphed_train_step_host_logic(mmu):
         G(types.SimpleNamespace(model=net, optimizer=adam, metrics=[], device=None))
     G(types.SimpleNamespace(model=net, optimizer=torch.optim.Adam(net.parameters(), capturable=True),
                             metrics=[], device=None))
+
+
+# ---- dropout masks: the product's mask function compiled for the HOST against the oracle ---------
+
+_DROPOUT_SHIM = r"""
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#include "dropout.cuh"
+extern "C" void site_params(float p, unsigned long long seed, unsigned int site, unsigned int* out3, float* scale) {
+  const mmu::dropout::Site s = mmu::dropout::make_site(p, seed, site);
+  out3[0] = s.lo; out3[1] = s.hi; out3[2] = s.thresh; *scale = s.scale;
+}
+extern "C" void keep_range(float p, unsigned long long seed, unsigned int site, unsigned int first,
+                           unsigned int n, unsigned char* keep, float* mult) {
+  const mmu::dropout::Site s = mmu::dropout::make_site(p, seed, site);
+  for (unsigned int i = 0; i < n; ++i) { keep[i] = s.keep(first + i); mult[i] = s.mult(first + i); }
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def dropout_host(tmp_path_factory):
+    """csrc/dropout.cuh is __host__ __device__ code: built here with g++ as the product's own mask
+    function (no GPU, no oracle involved in producing it)."""
+    import ctypes
+    import subprocess
+    d = tmp_path_factory.mktemp("dropout_host")
+    src = d / "shim.cpp"
+    src.write_text(_DROPOUT_SHIM)
+    so = d / "libdropout_host.so"
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-std=c++17",
+                           "-I", os.path.join(ROOT, "multi-modal-uncertainty_b200", "csrc"),
+                           "-o", str(so), str(src)])
+    lib = ctypes.CDLL(str(so))
+    lib.site_params.argtypes = [ctypes.c_float, ctypes.c_ulonglong, ctypes.c_uint,
+                                ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_float)]
+    lib.keep_range.argtypes = [ctypes.c_float, ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint,
+                               ctypes.c_void_p, ctypes.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("p", [0.0, 0.1, 0.25, 0.5, 0.9, 1.0])
+def test_dropout_mask_function_of_the_kernels_equals_the_oracle_restatement(dropout_host, p):
+    """Bit-exact: site seed (splitmix64), threshold, hash and multiplier of csrc/dropout.cuh against
+    oracle/dropout.py -- over several seeds / sites, a counter range that wraps 2^32, and the
+    extreme probabilities (p = 0: everything kept, scale 1; p = 1: threshold saturates)."""
+    import ctypes
+    from oracle import dropout
+    n = 1 << 16
+    for seed, site, first in ((0, 0, 0), (42, 3, 12345), (2 ** 63 + 11, 70, 2 ** 32 - 1000), (2 ** 64 - 1, 2 ** 32 - 1, 7)):
+        out3, scale = (ctypes.c_uint * 3)(), ctypes.c_float()
+        dropout_host.site_params(p, seed, site, out3, ctypes.byref(scale))
+        ss = dropout.site_seed(seed, site)
+        assert (out3[0], out3[1]) == (ss & 0xFFFFFFFF, ss >> 32)
+        assert out3[2] == dropout.threshold(p)
+        keep = np.zeros(n, dtype=np.uint8)
+        mult = np.zeros(n, dtype=np.float32)
+        dropout_host.keep_range(p, seed, site, first, n, keep.ctypes.data, mult.ctypes.data)
+        ref_keep = dropout.keep_mask(p, seed, site, n, offset=first)
+        assert torch.equal(torch.from_numpy(keep).bool(), ref_keep)
+        if p < 1.0:
+            assert torch.equal(torch.from_numpy(mult), dropout.multiplier(p, seed, site, n, offset=first))
+        if p == 0.0:
+            assert keep.all() and scale.value == 1.0
+
+
+def test_dropout_masks_have_the_statistics_of_nn_dropout():
+    """Statistical parity with nn.Dropout's definition (src/model.py:195-201): each element kept
+    independently with probability 1 - p, survivors scaled by 1 / (1 - p) so that the expectation is
+    the identity; different sites / seeds give independent masks; the mask is a pure function of
+    (seed, site, index)."""
+    from oracle import dropout
+    n = 1 << 20
+    for p in (0.1, 0.25, 0.5):
+        k = dropout.keep_mask(p, 1234, 5, n).double()
+        sigma = (p * (1 - p) / n) ** 0.5
+        assert abs(float(k.mean()) - (1 - p)) < 4 * sigma
+        m = dropout.multiplier(p, 1234, 5, n)
+        assert abs(float(m.double().mean()) - 1.0) < 4 * sigma / (1 - p)
+        assert set(m.unique().tolist()) == {0.0, float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))}
+        c = k - k.mean()
+        var = float((c * c).mean())
+        for lag in (1, 2, 7, 768, 3072):   # neighbours along a row and down a column of the GEMM outputs
+            assert abs(float((c[:-lag] * c[lag:]).mean()) / var) < 5 / n ** 0.5
+        for other in (dropout.keep_mask(p, 1234, 6, n), dropout.keep_mask(p, 1235, 5, n)):   # site, seed
+            o = other.double() - other.double().mean()
+            assert abs(float((c * o).mean()) / var) < 5 / n ** 0.5
+        assert torch.equal(dropout.keep_mask(p, 1234, 5, n), dropout.keep_mask(p, 1234, 5, n))
+        assert torch.equal(dropout.keep_mask(p, 1234, 5, 1000, offset=500), dropout.keep_mask(p, 1234, 5, n)[500:1500])
+
+
+def test_c_abi_argument_errors_need_no_device(mmu):
+    """Error behaviour of the boundary (include/mmu_b200.h: 'return value: 0 on success, a negative
+    MMU_ERR_* code otherwise; nothing throws'): every code has its own message, and null configs /
+    null tensors are rejected with MMU_ERR_ARG by the host-side validation, before any CUDA call --
+    so the check runs on a machine without a GPU."""
+    import ctypes as C
+    L = mmu._lib.lib
+    hdr = open(os.path.join(ROOT, "include", "mmu_b200.h")).read()
+    codes = {n: int(v) for n, v in re.findall(r"#define (MMU_(?:OK|ERR_[A-Z]+)) \(?(-?\d+)\)?", hdr)}
+    assert codes["MMU_OK"] == 0 and len(codes) == 8 and sorted(codes.values()) == list(range(-7, 1))
+    msgs = {c: L.mmu_error_string(c).decode() for c in codes.values()}
+    assert all(msgs.values()) and len(set(msgs.values())) == len(msgs)
+    assert L.mmu_error_string(-99).decode() not in set(msgs.values())
+    ARG = codes["MMU_ERR_ARG"]
+    for count in (L.mmu_flava_param_count, L.mmu_resnet_param_count, L.mmu_mmbt_param_count, L.mmu_imgenc_param_count):
+        assert count(None) == ARG
+    assert L.mmu_mask_gather_tokens(None, None, 1, 1, 1, 1, None, 0, None, 0, 0, None) == ARG
+    assert L.mmu_layernorm_fwd(None, None, None, None, 0, None, None, 4, 4, None) == ARG
+    assert L.mmu_cast_f32_to_bf16(None, None, 16, None) == ARG
+    assert L.mmu_ragged_pad(None, None, None, 1, 1, 1, None) == ARG
+    assert L.mmu_heads_uncertainty_epilogue(None, None, 1, 1, 1, 1, 1, 1, 0.0, None, None, None, None, None) == ARG
+    assert L.mmu_adamw_flat_step(None, None, None, None, None, 16, 0.1, 0.9, 0.98, 1e-9, 0.0, 1, 1.0, None) == ARG
+    assert L.mmu_flava_forward(None, None, None, None, 0, 0, None, None) == ARG
+    assert L.mmu_gemm(0, None, 0, 0, None, 0, 0, 4, 4, 4, 1, None, None) == ARG
+    e = mmu._lib.GemmEpilogue()
+    e.drop_p = 1.5   # nn.Dropout accepts p in [0, 1]; the epilogue needs 1 / (1 - p) finite
+    assert L.mmu_gemm(0, None, 0, 0, None, 0, 0, 4, 4, 4, 1, C.byref(e), None) == ARG
+    with pytest.raises(mmu._lib.MMUError, match="bad argument"):
+        mmu._lib.check(ARG, "probe")
