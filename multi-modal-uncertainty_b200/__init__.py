@@ -14,7 +14,7 @@ from .src import (callbacks, dataset, framework, graphs, metrics, mmbt, model, o
 from .src.framework import Model_  # noqa: F401
 from .src.metrics import acc  # noqa: F401
 from .src.model import (FlavaFusionTransfomer, FlavaFusionTransfomerwithCLSToken,  # noqa: F401
-                        MIMOTransfomer)
+                        MIMOTransfomer, model_configure)
 from .src.resnet import MIMOResNet  # noqa: F401
 from .src.mmbt import MultimodalBertClf  # noqa: F401
 from .src.optim import BertAdam, FusedAdamW, get_cosine_schedule_with_warmup  # noqa: F401

@@ -55,6 +55,19 @@ def data_forming_func(x, y, phase, model_type):
     return x, y
 
 
+def quarter_views(x):
+    """The four-view FashionMNIST input format (reference ``QuarterCrop`` + per-crop ``ToTensor``
+    stack inside ``get_fmnist``, src/dataset.py:105-151) as a tensor op: ``(B, C, H, W)`` ->
+    ``(B, 4, C, H/2, W/2)`` (or ``(C, H, W)`` -> ``(4, C, H/2, W/2)`` for one sample), views in the
+    reference's order upper left, upper right, lower left, lower right.  Works on host or device
+    tensors (slicing only), so a loader can keep whole 28 x 28 images in pinned memory and split
+    them after the copy."""
+    if x.dim() not in (3, 4) or x.shape[-1] % 2 or x.shape[-2] % 2:
+        raise ValueError("quarter_views expects (C, H, W) or (B, C, H, W) with even H and W")
+    hh, hw = x.shape[-2] // 2, x.shape[-1] // 2
+    return torch.stack([x[..., :hh, :hw], x[..., :hh, hw:], x[..., hh:, :hw], x[..., hh:, hw:]], dim=x.dim() - 3)
+
+
 def collate_fn_flava(batch):
     """Reference src/dataset.py:216-226: zero-pad ragged (l_i, 768) embeddings to the batch max."""
     def pad(seqs):

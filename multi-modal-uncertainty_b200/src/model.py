@@ -17,6 +17,25 @@ import torch.nn as nn
 
 from ._backend import _lib, ops
 
+# (emb_dim, out_dim) per --model_type of the FashionMNIST scripts (reference src/model.py:8-15)
+model_configure = {
+    "Vanilla": (4, 1),
+    "MIMO-shuffle-instance": (4, 4),
+    "MIMO-shuffle-view": (4, 4),
+    "MultiHead": (4, 4),
+    "MIMO-shuffle-all": (4, 4),
+    "single-model-weight-sharing": (1, 1),
+}
+
+
+def __getattr__(name):
+    # ``from src.model import MIMOResNet, model_configure, MIMOTransfomer`` (train_fashionmnist.py:17,
+    # eval_robustness.py:16): the conv model lives in resnet.py, which imports this module
+    if name == "MIMOResNet":
+        from .resnet import MIMOResNet
+        return MIMOResNet
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
 _PREC = {"fp32": _lib.F32, "bf16": _lib.BF16, torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
 
 

@@ -144,29 +144,54 @@ def run_transformer_robustness(model, batches, device, n_repeats=20, ref_bug_com
     return out
 
 
+def view_sweep_inputs(x, i, model_type=None):
+    """Input of sweep step i (reference ``eval_robustness.py:88-112``) for a ``(B, m, c, h, w)``
+    batch of views.  Multi-head models: view i zero-filled, every other view kept (:92-97).
+    ``single-model-weight-sharing``: view i REMOVED and the remaining m - 1 views laid out as the
+    ``(B * (m - 1), c, h, w)`` batch the shared single-view model takes (:99-110; what
+    ``data_forming_func(x_, y, 'eval', model_type)`` returns)."""
+    if model_type == "single-model-weight-sharing":
+        b, m, c, h, w = x.shape
+        keep = [j for j in range(m) if j != i]
+        return x[:, keep].reshape(b * (m - 1), c, h, w)
+    x_ = x.clone()
+    x_[:, i] = 0
+    return x_
+
+
 @torch.no_grad()
-def run_view_robustness(model, batches, device, n_views=4, collect=True):
-    """FashionMNIST four-view sweep (reference ``eval_robustness.py:82-121``): for view i, zero-fill
-    view i of every sample, forward, collect the logits.  Returns (outputs (n_views, S, E, C) numpy
-    or None, labels numpy, [per-view metric dicts]) -- the array the reference saves as
-    ``{ckpt}_predictions_robustness.npy``; the metrics accumulate on device per zero-filled view."""
+def run_view_robustness(model, batches, device, n_views=4, collect=True, model_type=None, metrics=True):
+    """FashionMNIST four-view sweep (reference ``eval_robustness.py:82-126``): for view i, zero-fill
+    view i of every sample (``model_type="single-model-weight-sharing"``: remove it and run the
+    shared single-view model on the other three, logits regrouped to ``(B, 3, C)``, :99-114),
+    forward, collect the logits.  Returns (outputs ``(n_views, S, E, C)`` numpy or None, labels
+    numpy, [per-view metric dicts]) -- the arrays the reference saves as
+    ``{ckpt}_predictions_robustness.npy`` / ``{ckpt}_labels.npy`` (with weight sharing the labels
+    are the ones ``data_forming_func`` returns, each repeated m - 1 times, as the reference
+    stores them); the metrics accumulate on device per left-out view (``metrics=False``: none,
+    as in the reference)."""
     model.eval()
-    meters = [UncertaintyMeter(device, model.num_classes, model.out_dim) for _ in range(n_views)]
+    shared = model_type == "single-model-weight-sharing"
+    meters = None
     outs, labels = [[] for _ in range(n_views)], []
     for x, y in batches:
         x, y = x.to(device), y.to(device).reshape(-1)
+        b, m = x.shape[0], x.shape[1]
         for i in range(n_views):
-            x_ = x.clone()
-            x_[:, i] = 0  # every other view is kept (reference :92-97 builds the same tensor)
-            logits = model(x_)
-            meters[i].update(logits, y)
+            logits = model(view_sweep_inputs(x, i, model_type))
+            if shared:
+                logits = logits.reshape(b, m - 1, logits.shape[-1])
+            if metrics:
+                if meters is None:
+                    meters = [UncertaintyMeter(device, logits.shape[-1], logits.shape[1]) for _ in range(n_views)]
+                meters[i].update(logits, y)
             if collect:
                 outs[i].append(logits.cpu())
-        labels.append(y.cpu())
-    for m in meters:
-        m.all_reduce()
+        labels.append((y.unsqueeze(1).repeat(1, m - 1).reshape(-1) if shared else y).cpu())
+    for mt in meters or []:
+        mt.all_reduce()
     P = torch.stack([torch.cat(o) for o in outs]).numpy() if collect and labels else None
-    return P, torch.cat(labels).numpy(), [m.compute() for m in meters]
+    return P, torch.cat(labels).numpy(), [mt.compute() for mt in meters or []]
 
 
 @torch.no_grad()

@@ -136,6 +136,30 @@ def leave_one_view_out(x, i):
     return out
 
 
+def drop_one_view(x, i):
+    """eval_robustness.py:99-108 (``single-model-weight-sharing``): view i REMOVED -- the remaining
+    m - 1 views of a (B, m, c, h, w) batch, in order, as a (B, m - 1, c, h, w) tensor."""
+    b, m, c, h, w = x.shape
+    out = torch.zeros(b, m - 1, c, h, w, dtype=x.dtype)
+    k = 0
+    for j in range(m):
+        if j != i:
+            out[:, k] = x[:, j]
+            k += 1
+    return out
+
+
+def quarter_views(img):
+    """src/dataset.py:105-151: ``QuarterCrop((28, 28))`` crops (top, left) = (0, 0), (0, 14), (14, 0),
+    (14, 14) -- upper left, upper right, lower left, lower right -- of a (..., 28, 28) image, each
+    its own view: (..., 28, 28) -> (4, ..., 14, 14) stacked like the reference's per-crop ToTensor."""
+    hh, hw = img.shape[-2] // 2, img.shape[-1] // 2
+    crops = []
+    for top, left in ((0, 0), (0, hw), (hh, 0), (hh, hw)):
+        crops.append(img[..., top:top + hh, left:left + hw])
+    return torch.stack(crops, dim=0)
+
+
 # ------------------------------------------------- modality dropout (north-star extension)
 def modality_dropout_mask(batch_size, p_drop, mode="random", scores=None, generator=None):
     """Per-sample keep mask (B, 2) int32 over (image, text).  NO REFERENCE IMPLEMENTATION

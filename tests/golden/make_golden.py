@@ -269,6 +269,52 @@ def shaping_cases(ref_dataset):
     return out
 
 
+def fmnist_views_case(ref_dataset):
+    """Either side of the FashionMNIST path: (1) the quarter-view input format -- the reference's
+    ``QuarterCrop((28, 28))`` + per-crop ``ToTensor`` stack exactly as ``get_fmnist`` composes them
+    (src/dataset.py:105-151) on seeded uint8 images; (2) the four-view robustness sweep of
+    ``eval_robustness.py:82-122``: the statements of the script's own ``__main__`` body, from
+    ``outputs = []`` to ``labels = np.concatenate(...)``, are executed from its AST (the script
+    itself cannot be imported: argparse, dataset download, checkpoint) with a deterministic linear
+    stand-in for the model -- once for a multi-head model (view i zero-filled) and once for
+    ``single-model-weight-sharing`` (view i removed, the remaining three views through the shared
+    model)."""
+    from PIL import Image
+    from torchvision import transforms
+    rng = np.random.RandomState(5)
+    imgs = rng.randint(0, 256, size=(6, 28, 28)).astype(np.uint8)
+    tq = transforms.Compose([
+        ref_dataset.QuarterCrop((28, 28)),
+        transforms.Lambda(lambda crops: torch.stack([transforms.ToTensor()(crop) for crop in crops]))])
+    quarters = torch.stack([tq(Image.fromarray(im, mode="L")) for im in imgs])      # (6, 4, 1, 14, 14)
+
+    src = open(os.path.join(REF, "eval_robustness.py")).read()
+    tree = ast.parse(src)
+    main_if = [n for n in tree.body if isinstance(n, ast.If)][-1]
+    names = [ast.unparse(n.targets[0]) if isinstance(n, ast.Assign) else None for n in main_if.body]
+    first = names.index("outputs")
+    last = max(i for i, n in enumerate(names) if n == "labels")
+    body = [n for n in main_if.body[first:last + 1]
+            if not (isinstance(n, ast.Expr) and isinstance(n.value, ast.Call)
+                    and getattr(n.value.func, "id", "") == "print")]
+    code = compile(ast.Module(body=body, type_ignores=[]), "eval_robustness_main", "exec")
+
+    g = torch.Generator().manual_seed(9)
+    C_ = 10
+    valid = [(torch.rand(b, 4, 1, 14, 14, generator=g), torch.randint(0, C_, (b,), generator=g)) for b in (5, 3)]
+    W4 = torch.randn(4 * 196, 4 * C_, generator=g)      # multi-head stand-in: (B, 4, 1, 14, 14) -> (B, 4, C)
+    W1 = torch.randn(196, C_, generator=g)               # weight sharing: (B * 3, 1, 14, 14) -> (B * 3, 1, C)
+    out = {"images_u8": torch.from_numpy(imgs), "quarters": quarters, "valid": valid, "W4": W4, "W1": W1}
+    for model_type, model in (("MultiHead", lambda x: (x.reshape(x.shape[0], -1) @ W4).view(-1, 4, C_)),
+                              ("single-model-weight-sharing",
+                               lambda x: (x.reshape(x.shape[0], -1) @ W1).view(-1, 1, C_))):
+        ns = {"torch": torch, "np": np, "dataset": ref_dataset, "model": model, "valid": valid,
+              "args": types.SimpleNamespace(model_type=model_type, device="cpu")}
+        exec(code, ns)
+        out[model_type] = dict(outputs=torch.from_numpy(ns["outputs"]), labels=torch.from_numpy(ns["labels"]))
+    return out
+
+
 def sampling_case():
     """``input_sampling`` lives in a script that cannot be imported (argparse at module level is
     under __main__, but it imports dataset loaders that do not exist); exec its source."""
@@ -417,6 +463,9 @@ def main():
         torch.save(rank_case(), os.path.join(HERE, "rank_stats.pt"))
         return
     ref_model, ref_dataset, _ = import_reference()
+    if sys.argv[1:] == ["fmnist_views"]:   # only the FashionMNIST view-format / view-sweep fixture
+        torch.save(fmnist_views_case(ref_dataset), os.path.join(HERE, "fmnist_views.pt"))
+        return
     small = dict(C=7, D=64, heads=2, layers=2, d_img=32, d_txt=48, l_img=5, l_txt=3, B=4)
     cases = {
         "plain_E2": flava_case(ref_model, "plain_E2", cls=False, avg_pool=False, E=2, seed=21, **small),
@@ -438,6 +487,7 @@ def main():
     torch.save(notebook_case(), os.path.join(HERE, "notebook_scoring.pt"))
     torch.save(init_case(ref_model), os.path.join(HERE, "init_seed123.pt"))
     torch.save(rank_case(), os.path.join(HERE, "rank_stats.pt"))
+    torch.save(fmnist_views_case(ref_dataset), os.path.join(HERE, "fmnist_views.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -696,3 +696,46 @@ def test_c_abi_argument_errors_need_no_device(mmu):
     assert L.mmu_gemm(0, None, 0, 0, None, 0, 0, 4, 4, 4, 1, C.byref(e), None) == ARG
     with pytest.raises(mmu._lib.MMUError, match="bad argument"):
         mmu._lib.check(ARG, "probe")
+
+
+def test_fmnist_view_format_sweep_and_model_table(mmu, golden):
+    """Either side of the FashionMNIST path, against the reference run in the build container
+    (tests/golden/fmnist_views.pt): ``dataset.quarter_views`` == QuarterCrop + ToTensor (batched and
+    per sample, bit-exact); ``robustness.run_view_robustness`` == the reference script's own sweep
+    statements for a multi-head model (view zero-filled) and for ``single-model-weight-sharing``
+    (view removed, labels repeated as the reference saves them) -- host shaping only, with the
+    golden's linear stand-in model and without the device-side meters; and the names the
+    reference's FashionMNIST scripts import from ``src.model`` resolve."""
+    import importlib
+    c = golden("fmnist_views.pt")
+    imgs = c["images_u8"].float().div(255).unsqueeze(1)
+    assert torch.equal(mmu.dataset.quarter_views(imgs), c["quarters"])
+    assert torch.equal(mmu.dataset.quarter_views(imgs[2]), c["quarters"][2])
+    with pytest.raises(ValueError):
+        mmu.dataset.quarter_views(torch.zeros(1, 27, 28))
+    C_ = 10
+
+    class Lin(torch.nn.Module):
+        def __init__(self, W, heads):
+            super().__init__()
+            self.W, self.heads = W, heads
+
+        def forward(self, x):
+            return (x.reshape(x.shape[0], -1) @ self.W).view(-1, self.heads, C_)
+
+    for mt, model in (("MultiHead", Lin(c["W4"], 4)), ("single-model-weight-sharing", Lin(c["W1"], 1))):
+        P, labels, per_view = mmu.robustness.run_view_robustness(model, c["valid"], "cpu", model_type=mt, metrics=False)
+        assert per_view == []
+        assert torch.equal(torch.from_numpy(P), c[mt]["outputs"])
+        assert torch.equal(torch.from_numpy(labels), c[mt]["labels"])
+    x = c["valid"][0][0]
+    assert mmu.robustness.view_sweep_inputs(x, 1, "single-model-weight-sharing").shape == (x.shape[0] * 3, 1, 14, 14)
+    # `from src.model import MIMOResNet, model_configure, MIMOTransfomer` (train_fashionmnist.py:17)
+    src_model = importlib.import_module("multi-modal-uncertainty_b200.src.model")
+    assert src_model.MIMOResNet is mmu.MIMOResNet and src_model.MIMOTransfomer is mmu.MIMOTransfomer
+    assert src_model.model_configure == {"Vanilla": (4, 1), "MIMO-shuffle-instance": (4, 4), "MIMO-shuffle-view": (4, 4),
+                                         "MultiHead": (4, 4), "MIMO-shuffle-all": (4, 4),
+                                         "single-model-weight-sharing": (1, 1)}
+    assert mmu.model_configure is src_model.model_configure
+    with pytest.raises(AttributeError):
+        src_model.no_such_name

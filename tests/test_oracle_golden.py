@@ -387,3 +387,34 @@ def test_restated_bert_matches_transformers_bertmodel():
     keep = mask.bool()
     assert float((o.last_hidden_state - last)[keep].abs().max()) < 1e-12
     assert float((o.pooler_output - pooled).abs().max()) < 1e-12
+
+
+def test_fmnist_view_format_and_view_sweep(golden):
+    """Oracle restatements of the FashionMNIST view handling against the reference run in the build
+    container (tests/golden/make_golden.py::fmnist_views_case): ``quarter_views`` against the
+    reference's QuarterCrop + ToTensor composition on uint8 images (bit-exact), and the sweep
+    inputs (zero-filled view / removed view) against the reference script's own sweep statements
+    executed over a linear stand-in model (both model types, outputs and saved labels)."""
+    from oracle import shaping
+    c = golden("fmnist_views.pt")
+    imgs = c["images_u8"].float().div(255).unsqueeze(1)                  # ToTensor of an 'L' image
+    q = torch.stack([shaping.quarter_views(im) for im in imgs])          # per sample, as the transform does
+    assert torch.equal(q, c["quarters"])
+    C_ = 10
+    for mt, fwd in (("MultiHead", lambda x: (x.reshape(x.shape[0], -1) @ c["W4"]).view(-1, 4, C_)),
+                    ("single-model-weight-sharing", lambda x: (x.reshape(x.shape[0], -1) @ c["W1"]).view(-1, 1, C_))):
+        outs, labels = [], []
+        for i in range(4):
+            per = []
+            for x, y in c["valid"]:
+                if mt == "MultiHead":
+                    per.append(fwd(shaping.leave_one_view_out(x, i)))
+                    y_saved = y
+                else:
+                    x_, y_saved = shaping.data_forming_func(shaping.drop_one_view(x, i), y, "eval", mt)
+                    per.append(fwd(x_).view(x.shape[0], 3, C_))
+                if i == 0:
+                    labels.append(y_saved)
+            outs.append(torch.cat(per))
+        assert torch.equal(torch.stack(outs), c[mt]["outputs"])
+        assert torch.equal(torch.cat(labels), c[mt]["labels"])
