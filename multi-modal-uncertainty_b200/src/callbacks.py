@@ -24,6 +24,7 @@ class Callback:
         if not ignore:
             self.model = model
 
+    def get_meta_data(self): return self.meta_data
     def get_dataloader(self): return self.data
     def get_optimizer(self): return self.optimizer
     def get_params(self): return self.params
@@ -80,7 +81,10 @@ class LambdaCallback(Callback):
 
 class ModelCheckpoint(Callback):
     """Save {'model','optimizer'} when the monitored value improves (or every `period` epochs);
-    reference src/callbacks.py:188-254 (which breaks on NumPy >= 2 through ``np.Inf``)."""
+    reference src/callbacks.py:188-254 (which breaks on NumPy >= 2 through ``np.Inf``).  With
+    ``save_best_only=False`` the reference's ``save_weights`` call sits under ``if self.verbose > 0``
+    (:252-254, an indentation slip: nothing is written at verbose 0); here every period saves.
+    Pickles without its model / optimizer references, like the reference (:217-226)."""
 
     def __init__(self, filepath, monitor="val_loss", verbose=0, save_best_only=False, mode="auto",
                  period=1):
@@ -91,6 +95,18 @@ class ModelCheckpoint(Callback):
             mode = "max" if ("acc" in monitor or monitor.startswith("fmeasure")) else "min"
         self.monitor_op = np.greater if mode == "max" else np.less
         self.best = -np.inf if mode == "max" else np.inf
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("model", None)
+        state.pop("optimizer", None)
+        return state
+
+    def __setstate__(self, newstate):
+        for k in ("model", "optimizer"):   # keep the live references of the unpickling object, if any
+            if k in self.__dict__:
+                newstate[k] = self.__dict__[k]
+        self.__dict__.update(newstate)
 
     def on_epoch_end(self, epoch, logs=None):
         logs = logs or {}

@@ -739,3 +739,108 @@ def test_fmnist_view_format_sweep_and_model_table(mmu, golden):
     assert mmu.model_configure is src_model.model_configure
     with pytest.raises(AttributeError):
         src_model.no_such_name
+
+
+def test_resume_from_last_epoch_checkpoint_as_train_py_does(mmu, tmp_path):
+    """The reference's resume path (train.py:273-283): reload ``model_last_epoch.pt`` strictly into a
+    freshly constructed model, rebuild ``H`` from ``history.csv``, continue at
+    ``epoch_start = len(H['epoch']) + 1`` with the default callbacks -- the history keeps growing in
+    the same file, the per-epoch checkpoints continue their numbering, and the best-validation
+    checkpoint is only replaced by a better epoch."""
+    import pandas as pd
+    from functools import partial
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = torch.nn.Linear(6, 3 * 2)
+
+        def forward(self, x):
+            img, txt = x
+            return self.fc(torch.cat([img.mean(1), txt.mean(1)], -1)).view(-1, 2, 3)
+
+        def compute_loss(self, y_hat, y, eval=False):
+            y_hat = y_hat.mean(1) if eval else y_hat.reshape(-1, 3)
+            return torch.nn.functional.cross_entropy(y_hat, y.reshape(-1))
+
+    def acc(y_pred, y_true, eval, dummy_dim=False):
+        y_pred = y_pred.mean(1) if eval else y_pred.reshape(-1, 3)
+        return (y_pred.argmax(1) == y_true.reshape(-1)).float().mean() * 100
+
+    tl = mmu.src.training_loop
+    train, val, test = mmu.dataset.get_synthetic_flava(4, 12, 8, 8, l_img=3, l_txt=2, dim=3, num_classes=3)
+
+    def run(net, H, epoch_start, epochs):
+        opt = torch.optim.SGD(net.parameters(), lr=0.1)
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0)
+        cbs = tl._construct_default_callbacks(net, opt, H, str(tmp_path), checkpoint_monitor="val_acc")
+        for cb in cbs:
+            cb.set_save_path(str(tmp_path)); cb.set_model(net, ignore=False); cb.set_optimizer(opt)
+        trainer = mmu.Model_(net, opt, sched, partial(mmu.dataset.data_forming_func_transformer, model_type="MultiHead"),
+                             metrics=[acc], verbose=False)
+        trainer.to(torch.device("cpu"))
+        trainer.train_loop(train, valid_generator=val, test_generator=test, epochs=epochs, epoch_start=epoch_start,
+                           steps_per_epoch=len(train), validation_steps=len(val), test_steps=len(test),
+                           callbacks=cbs, scheduler_step_on="batch", scheduler_metric=None)
+
+    torch.manual_seed(0)
+    first = Tiny()
+    run(first, {}, 1, 2)
+    saved = {k: v.clone() for k, v in first.state_dict().items()}
+
+    # ---- what train.py does under --resume
+    torch.manual_seed(1)
+    net = Tiny()
+    checkpoint = torch.load(tmp_path / "model_last_epoch.pt")
+    assert set(checkpoint) == {"model", "optimizer"}
+    net.load_state_dict(checkpoint["model"])
+    assert all(torch.equal(v, saved[k]) for k, v in net.state_dict().items())
+    H = pd.read_csv(tmp_path / "history.csv")
+    H = {col: list(H[col].values) for col in H.columns if col != "Unnamed: 0"}
+    epoch_start = len(H["epoch"]) + 1
+    assert epoch_start == 3
+    best_before = torch.load(tmp_path / "model_best_val.pt")["model"]
+    run(net, H, epoch_start, 4)
+
+    H2 = pd.read_csv(tmp_path / "history.csv")
+    assert list(H2["epoch"]) == [1, 2, 3, 4] and len(H2["val_acc"]) == 4 and not H2["loss"].isna().any()
+    for e in (1, 2, 3, 4):
+        assert os.path.exists(tmp_path / f"model_epoch_{e}.pt")
+    last = torch.load(tmp_path / "model_last_epoch.pt")["model"]
+    assert all(torch.equal(last[k], v) for k, v in net.state_dict().items())
+    # a ModelCheckpoint created for the resumed run starts from its own best (= -inf), as in the
+    # reference: the file is rewritten by the first resumed epoch and afterwards only by a better one
+    best_after = torch.load(tmp_path / "model_best_val.pt")["model"]
+    resumed_best_epoch = 3 if H2["val_acc"][3] <= H2["val_acc"][2] else 4
+    expect = torch.load(tmp_path / f"model_epoch_{resumed_best_epoch}.pt")["model"]
+    assert all(torch.equal(best_after[k], expect[k]) for k in expect)
+    assert set(best_before) == set(best_after)
+
+
+def test_callback_accessors_and_checkpoint_pickling(mmu, tmp_path):
+    """Reference src/callbacks.py:82-125 (setter / getter pairs of ``Callback``) and :217-226
+    (``ModelCheckpoint`` pickles without its model / optimizer)."""
+    import pickle
+    cbm = mmu.src.callbacks
+    cb = cbm.Callback()
+    for name, value in (("meta_data", {"a": 1}), ("save_path", "p"), ("optimizer", object()), ("params", {"epochs": 3}),
+                        ("dataloader", [1, 2])):
+        getattr(cb, "set_" + name)(value)
+        assert getattr(cb, "get_" + name)() is value
+    lin = torch.nn.Linear(2, 2)
+    cb.set_model(lin)                      # ignore=True is the default: the reference's "trick"
+    assert not hasattr(cb, "model")
+    cb.set_model(lin, ignore=False)
+    assert cb.get_model() is lin
+    ck = cbm.ModelCheckpoint(str(tmp_path / "best.pt"), monitor="val_acc", save_best_only=True, mode="max")
+    ck.set_model(lin, ignore=False)
+    ck.set_optimizer(torch.optim.SGD(lin.parameters(), lr=0.1))
+    ck.on_epoch_end(1, {"val_acc": 50.0})
+    blob = pickle.dumps(ck)
+    assert b"Linear" not in blob
+    ck2 = pickle.loads(blob)
+    assert ck2.best == 50.0 and ck2.monitor == "val_acc" and not hasattr(ck2, "model")
+    ck.on_epoch_end(2, {"val_acc": 40.0})  # not better: file untouched
+    t = os.path.getmtime(tmp_path / "best.pt")
+    ck.on_epoch_end(3, {"val_acc": 60.0})
+    assert ck.best == 60.0 and os.path.getmtime(tmp_path / "best.pt") >= t
