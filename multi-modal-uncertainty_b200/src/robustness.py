@@ -195,6 +195,38 @@ def run_view_robustness(model, batches, device, n_views=4, collect=True, model_t
 
 
 @torch.no_grad()
+def run_predictions(model, batches, device, model_type=None, metrics=True):
+    """Plain FashionMNIST prediction dump (reference ``eval_prediction_saving.py:77-104``): eval-mode
+    forward of every batch, logits ``(S, M, C)`` and labels ``(S,)`` -- the arrays the reference saves
+    as ``{ckpt}_predictions.npy`` / ``{ckpt}_labels.npy``.  With
+    ``model_type="single-model-weight-sharing"`` the shared single-view model sees the
+    ``(B * m, c, h, w)`` batch ``data_forming_func`` builds and its logits are regrouped to
+    ``(B, m, C)`` (:84-95).  Returns (outputs numpy, labels numpy, metric dict | None); the
+    uncertainty / calibration metrics of the dump accumulate on the device (``metrics=False``:
+    none, as in the reference)."""
+    from .dataset import data_forming_func
+    model.eval()
+    shared = model_type == "single-model-weight-sharing"
+    meter, outs, labels = None, [], []
+    for x, y in batches:
+        b, m = x.shape[0], x.shape[1]
+        y = y.reshape(-1)
+        x_, _ = data_forming_func(x, y, "eval", model_type)
+        logits = model(x_.to(device))
+        if shared:
+            logits = logits.reshape(b, m, logits.shape[-1])
+        if metrics:
+            if meter is None:
+                meter = UncertaintyMeter(device, logits.shape[-1], logits.shape[1])
+            meter.update(logits, y.to(device))
+        outs.append(logits.cpu())
+        labels.append(y.cpu())
+    if meter is not None:
+        meter.all_reduce()
+    return torch.cat(outs).numpy(), torch.cat(labels).numpy(), (meter.compute() if meter is not None else None)
+
+
+@torch.no_grad()
 def run_mmbt_robustness(model, generator, n_repeats=20, device=None, posthoc=None):
     """The MMBT sweep of reference ``eval_mmbt_robustness.py:76-96``: per batch the full forward,
     ``forward_img_only``, ``forward_txt_only`` and ``n_repeats`` ``forward_control`` draws for

@@ -312,6 +312,25 @@ def fmnist_views_case(ref_dataset):
               "args": types.SimpleNamespace(model_type=model_type, device="cpu")}
         exec(code, ns)
         out[model_type] = dict(outputs=torch.from_numpy(ns["outputs"]), labels=torch.from_numpy(ns["labels"]))
+
+    # (3) the plain prediction dump of eval_prediction_saving.py:77-104, same recipe
+    src = open(os.path.join(REF, "eval_prediction_saving.py")).read()
+    main_if = [n for n in ast.parse(src).body if isinstance(n, ast.If)][-1]
+    names = [ast.unparse(n.targets[0]) if isinstance(n, ast.Assign) else None for n in main_if.body]
+    first = names.index("outputs")
+    last = max(i for i, n in enumerate(names) if n == "labels")
+    body = [n for n in main_if.body[first:last + 1]
+            if not (isinstance(n, ast.Expr) and isinstance(n.value, ast.Call)
+                    and getattr(n.value.func, "id", "") == "print")]
+    code = compile(ast.Module(body=body, type_ignores=[]), "eval_prediction_saving_main", "exec")
+    for model_type, model in (("MultiHead", lambda x: (x.reshape(x.shape[0], -1) @ W4).view(-1, 4, C_)),
+                              ("single-model-weight-sharing",
+                               lambda x: (x.reshape(x.shape[0], -1) @ W1).view(-1, 1, C_))):
+        ns = {"torch": torch, "np": np, "dataset": ref_dataset, "model": model, "valid": valid,
+              "args": types.SimpleNamespace(model_type=model_type, device="cpu")}
+        exec(code, ns)
+        out["predictions/" + model_type] = dict(outputs=torch.from_numpy(ns["outputs"]),
+                                                labels=torch.from_numpy(ns["labels"]))
     return out
 
 

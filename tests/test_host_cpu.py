@@ -728,6 +728,11 @@ def test_fmnist_view_format_sweep_and_model_table(mmu, golden):
         assert per_view == []
         assert torch.equal(torch.from_numpy(P), c[mt]["outputs"])
         assert torch.equal(torch.from_numpy(labels), c[mt]["labels"])
+        # the plain prediction dump (eval_prediction_saving.py:77-104) with the same stand-in model
+        P, labels, summary = mmu.robustness.run_predictions(model, c["valid"], "cpu", model_type=mt, metrics=False)
+        assert summary is None
+        assert torch.equal(torch.from_numpy(P), c["predictions/" + mt]["outputs"])
+        assert torch.equal(torch.from_numpy(labels), c["predictions/" + mt]["labels"])
     x = c["valid"][0][0]
     assert mmu.robustness.view_sweep_inputs(x, 1, "single-model-weight-sharing").shape == (x.shape[0] * 3, 1, 14, 14)
     # `from src.model import MIMOResNet, model_configure, MIMOTransfomer` (train_fashionmnist.py:17)
