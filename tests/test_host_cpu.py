@@ -849,3 +849,56 @@ def test_callback_accessors_and_checkpoint_pickling(mmu, tmp_path):
     t = os.path.getmtime(tmp_path / "best.pt")
     ck.on_epoch_end(3, {"val_acc": 60.0})
     assert ck.best == 60.0 and os.path.getmtime(tmp_path / "best.pt") >= t
+
+
+def test_bench_accounting_and_reference_arm_contract(monkeypatch, capsys):
+    """bench.py on the CPU: (1) the algorithmic FLOP count `roofline` / `whole_step` divide by is
+    SURVEY 8d's formula at BASELINE.json's configuration (10.63 GFLOP forward, ~31.9 GFLOP train
+    per sample, all positions as written); the sweep's token counts follow the 10-level grid;
+    (2) the `--impl reference` line keeps the contract (same metric / unit / config / direction as
+    the product arm, `impl`, zero-copy `e2e`, a `cpu_baseline` of this run, bounded steps) and only
+    rank 0 prints it; (3) without a GPU the product arm refuses to run instead of falling back."""
+    import argparse
+    import json
+    import bench
+    cfg = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert bench.CFG["B"] == 128 and (bench.CFG["l_img"], bench.CFG["l_txt"]) == (197, 40)
+    assert (bench.CFG["D"], bench.CFG["layers"], bench.CFG["E"], bench.CFG["C"]) == (768, 3, 5, 101)
+    assert "samples/sec" in cfg["metric"] or "samples" in json.dumps(cfg)
+    f = bench.fwd_flops_per_sample(197, 40, 128)
+    L, D = 237, 768
+    assert f == 2 * L * D * D + 3 * (24 * L * D * D + 4 * L * 128 * D) + 2 * 5 * D * 101
+    assert abs(f / 1e9 - 10.63) < 0.01
+    total, train, sweep = bench.step_flops(128)
+    assert total == train + sweep and abs(train / 128 / 1e9 - 31.9) < 0.4
+    counts = bench.level_token_counts()
+    assert len(counts) == 10 and counts[0] == (0, 40) and counts[-1] == (197, 0)
+    assert all(0 <= a <= 197 and 0 <= b <= 40 for a, b in counts)
+    assert [a for a, _ in counts] == sorted(a for a, _ in counts)
+    assert sweep == 128 * sum(bench.fwd_flops_per_sample(a, b, 128) for a, b in counts)
+
+    calls = []
+
+    def fake_cpu_reference(steps, warmup, B=None):
+        calls.append((steps, warmup))
+        return {"value": 8.5, "unit": "samples/s", "cores": 16, "kind": "port", "sample": "stub", "s_per_step": 15.0}
+
+    monkeypatch.setattr(bench, "cpu_reference", fake_cpu_reference)
+    args = argparse.Namespace(steps=20, warmup=3, gpus=1)
+    monkeypatch.setenv("RANK", "0")
+    bench.run_reference(args)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert calls == [(3, 1)]                                   # bounded: the whole run ends within minutes
+    assert line["impl"] == "reference" and line["metric"] == "train+robustness-eval samples/sec"
+    assert line["unit"] == "samples/s" and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["value"] == 8.5 and line["e2e"] == {"value": 8.5, "unit": "samples/s", "h2d_bytes_per_step": 0,
+                                                     "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 16
+    assert line["config"]["workload"] == bench.WORKLOAD_NAME and line["config"]["per_gpu_batch"] == 128
+    monkeypatch.setenv("RANK", "1")                            # other ranks exit without work or output
+    bench.run_reference(args)
+    assert capsys.readouterr().out == "" and calls == [(3, 1)]
+    if not torch.cuda.is_available():
+        monkeypatch.setattr(sys, "argv", ["bench.py"])
+        with pytest.raises(SystemExit, match="no CPU fallback"):
+            bench.main()
