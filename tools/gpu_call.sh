@@ -1,5 +1,6 @@
+# The command this repo hands to gpurun for a full verification of the tree (tests, smoke, bench):
+#   gpurun --timeout 400 -- 'bash tools/gpu_call.sh'
 mkdir -p gpurun_out
-export MMU_TIMING_ONLY=1
-./build/gemm_harness 8 > gpurun_out/r2c_plain8.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 5 -c 1 -o gpurun_out/r2c_cfc_train_f32x2 ./build/gemm_harness 8 > gpurun_out/r2c_ncu8.log 2>&1
-./build/gemm_harness 34 > gpurun_out/r2c_plain34.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 5 -c 1 -o gpurun_out/r2c_cfc_eval_plain_f32x2 ./build/gemm_harness 34 > gpurun_out/r2c_ncu34.log 2>&1
-ls -la gpurun_out/*.ncu-rep | tail -2
+( time python -m pytest tests -m gpu -q ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; grep -c "smoke\[" gpurun_out/smoke.log
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; tail -c 600 gpurun_out/bench.json
