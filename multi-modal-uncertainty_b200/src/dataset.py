@@ -81,6 +81,22 @@ def collate_fn_flava(batch):
     return (imgs, txts), labels
 
 
+def collate_fn(batch):
+    """Reference src/dataset.py:420-438, the MMBT batch format: rows ``(tokens (l_i,), segment (l_i,),
+    image, label (1,))`` as ``JsonlDataset.__getitem__`` returns them -> ``((text, segment, mask,
+    image), target)`` with the three token-axis tensors zero-padded to the batch maximum (int64)
+    and ``mask`` = 1 on real tokens.  (``Model_`` calls ``model(*x)`` on this tuple, so ``segment``
+    lands in the model's ``mask`` argument and vice versa -- src/framework.py:172-176; the two are
+    equal, ones on real tokens, so nothing changes.)"""
+    lens = [int(row[0].shape[0]) for row in batch]
+    text = torch.nn.utils.rnn.pad_sequence([row[0].long() for row in batch], batch_first=True)
+    segment = torch.nn.utils.rnn.pad_sequence([row[1].long() for row in batch], batch_first=True)
+    mask = (torch.arange(max(lens)).unsqueeze(0) < torch.tensor(lens).unsqueeze(1)).long()
+    img = torch.stack([row[2] for row in batch])
+    tgt = torch.cat([row[3] for row in batch]).long()
+    return (text, segment, mask, img), tgt
+
+
 class SyntheticFlavaDataset(Dataset):
     """Synthetic stand-in for ``FlavaEncodedDataset`` (reference src/dataset.py:196-213): the same
     item protocol (image_embeddings (l_img, d), text_embeddings (l_txt_i, d), LongTensor([label]))

@@ -76,6 +76,25 @@ def collate_fn_flava(batch):
     return (imgs, txts), labels
 
 
+def collate_fn(batch):
+    """src/dataset.py:420-438 (MMBT): rows (tokens (l_i,), segment (l_i,), image, label (1,)) ->
+    ((text, segment, mask, image), target); token / segment / mask rows zero-padded to the batch
+    maximum, all int64."""
+    lens = [int(row[0].shape[0]) for row in batch]
+    n, lmax = len(batch), max(lens)
+    text = torch.zeros(n, lmax, dtype=torch.int64)
+    segment = torch.zeros(n, lmax, dtype=torch.int64)
+    mask = torch.zeros(n, lmax, dtype=torch.int64)
+    for i, (row, l) in enumerate(zip(batch, lens)):
+        for t in range(l):
+            text[i, t] = int(row[0][t])
+            segment[i, t] = int(row[1][t])
+            mask[i, t] = 1
+    img = torch.stack([row[2] for row in batch])
+    tgt = torch.cat([row[3] for row in batch]).long()
+    return (text, segment, mask, img), tgt
+
+
 # --------------------------------------------------------------------- robustness sweeps
 def input_sampling(l_img, l_txt, type="image"):
     """eval_transformer_robustness.py:37-52.  n ~ U{0..l} from NumPy's global state, then two

@@ -334,6 +334,19 @@ def fmnist_views_case(ref_dataset):
     return out
 
 
+def mmbt_collate_case(ref_dataset):
+    """The MMBT input format (reference src/dataset.py:371-438): rows as ``JsonlDataset.__getitem__``
+    returns them -- (token ids (l_i,) int64, segment (l_i,) FLOAT ones, image (3, h, w), label (1,)) --
+    through the reference's own ``collate_fn``."""
+    g = torch.Generator().manual_seed(17)
+    rows = []
+    for l, c in ((5, 1), (2, 0), (7, 1), (1, 0)):
+        rows.append((torch.randint(1, 30000, (l,), generator=g), torch.zeros(l) + 1,
+                     torch.randn(3, 4, 4, generator=g), torch.LongTensor([c])))
+    (txt, segment, mask, img), tgt = ref_dataset.collate_fn(rows)
+    return dict(rows=rows, txt=txt, segment=segment, mask=mask, img=img, tgt=tgt)
+
+
 def sampling_case():
     """``input_sampling`` lives in a script that cannot be imported (argparse at module level is
     under __main__, but it imports dataset loaders that do not exist); exec its source."""
@@ -482,6 +495,9 @@ def main():
         torch.save(rank_case(), os.path.join(HERE, "rank_stats.pt"))
         return
     ref_model, ref_dataset, _ = import_reference()
+    if sys.argv[1:] == ["mmbt_collate"]:
+        torch.save(mmbt_collate_case(ref_dataset), os.path.join(HERE, "mmbt_collate.pt"))
+        return
     if sys.argv[1:] == ["fmnist_views"]:   # only the FashionMNIST view-format / view-sweep fixture
         torch.save(fmnist_views_case(ref_dataset), os.path.join(HERE, "fmnist_views.pt"))
         return
@@ -507,6 +523,7 @@ def main():
     torch.save(init_case(ref_model), os.path.join(HERE, "init_seed123.pt"))
     torch.save(rank_case(), os.path.join(HERE, "rank_stats.pt"))
     torch.save(fmnist_views_case(ref_dataset), os.path.join(HERE, "fmnist_views.pt"))
+    torch.save(mmbt_collate_case(ref_dataset), os.path.join(HERE, "mmbt_collate.pt"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

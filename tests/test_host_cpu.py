@@ -902,3 +902,14 @@ def test_bench_accounting_and_reference_arm_contract(monkeypatch, capsys):
         monkeypatch.setattr(sys, "argv", ["bench.py"])
         with pytest.raises(SystemExit, match="no CPU fallback"):
             bench.main()
+
+
+def test_product_mmbt_collate_bit_exact(mmu, golden):
+    """dataset.collate_fn (the MMBT batch format) against the reference's own collate_fn, dtypes
+    included; segment == mask on every real token, which is why the reference's ``model(*x)``
+    argument order (segment in the mask slot) is harmless."""
+    c = golden("mmbt_collate.pt")
+    (txt, segment, mask, img), tgt = mmu.dataset.collate_fn(c["rows"])
+    for got, key in ((txt, "txt"), (segment, "segment"), (mask, "mask"), (img, "img"), (tgt, "tgt")):
+        assert got.dtype == c[key].dtype and torch.equal(got, c[key]), key
+    assert torch.equal(segment, mask)

@@ -418,3 +418,12 @@ def test_fmnist_view_format_and_view_sweep(golden):
             outs.append(torch.cat(per))
         assert torch.equal(torch.stack(outs), c[mt]["outputs"])
         assert torch.equal(torch.cat(labels), c[mt]["labels"])
+
+
+def test_mmbt_collate_bit_exact(golden):
+    """oracle.shaping.collate_fn against the reference's own MMBT ``collate_fn`` (src/dataset.py:420-438)."""
+    from oracle import shaping
+    c = golden("mmbt_collate.pt")
+    (txt, segment, mask, img), tgt = shaping.collate_fn(c["rows"])
+    for got, key in ((txt, "txt"), (segment, "segment"), (mask, "mask"), (img, "img"), (tgt, "tgt")):
+        assert got.dtype == c[key].dtype and torch.equal(got, c[key]), key
