@@ -913,3 +913,52 @@ def test_product_mmbt_collate_bit_exact(mmu, golden):
     for got, key in ((txt, "txt"), (segment, "segment"), (mask, "mask"), (img, "img"), (tgt, "tgt")):
         assert got.dtype == c[key].dtype and torch.equal(got, c[key]), key
     assert torch.equal(segment, mask)
+
+
+def test_epoch_stepped_plateau_scheduler_as_train_fashionmnist_does(mmu):
+    """train_fashionmnist.py:111-130,196-213: SGD + ``ReduceLROnPlateau`` stepped ONCE PER EPOCH on
+    ``epoch_log[scheduler_metric]`` (src/framework.py:337-338), four-view batches through
+    ``data_forming_func(model_type='MultiHead')``, ``acc`` with ``dummy_dim=True``."""
+    from functools import partial
+
+    class TinyViews(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = torch.nn.Linear(4 * 14 * 14, 4 * 10)
+
+        def forward(self, x):                      # (B, 4, 1, 14, 14) -> (B, 4, 10)
+            return self.fc(x.reshape(x.shape[0], -1)).view(-1, 4, 10)
+
+        def compute_loss(self, y_hat, y, eval=False):
+            y_hat = y_hat.mean(1) if eval else y_hat.reshape(-1, 10)
+            return torch.nn.functional.cross_entropy(y_hat, y.reshape(-1))
+
+    def acc(y_pred, y_true, eval, dummy_dim=False):     # train.py:119-130 on the host (mmu.acc runs on the device)
+        if dummy_dim:
+            y_pred, y_true = (y_pred.mean(1), y_true) if eval else (y_pred.reshape(-1, y_pred.shape[2]), y_true.reshape(-1))
+        return (y_pred.max(1)[1] == y_true).float().mean() * 100
+
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.rand(6, 4, 1, 14, 14, generator=g), torch.randint(0, 10, (6,), generator=g)) for _ in range(3)]
+    net = TinyViews()
+    opt = torch.optim.SGD(net.parameters(), lr=0.1, weight_decay=0.001, momentum=0.9)
+    seen = []
+
+    class Plateau(torch.optim.lr_scheduler.ReduceLROnPlateau):
+        def step(self, metrics, *a, **k):
+            seen.append(float(metrics))
+            return super().step(metrics, *a, **k)
+
+    sched = Plateau(opt, mode="min", factor=0.1, patience=0, threshold=1e9, threshold_mode="abs")  # never "better"
+    logs = []
+    trainer = mmu.Model_(net, opt, sched, partial(mmu.dataset.data_forming_func, model_type="MultiHead"),
+                         metrics=[acc], verbose=False)
+    trainer.to(torch.device("cpu"))
+    cb = mmu.src.callbacks.LambdaCallback(on_epoch_end=lambda e, l: logs.append(dict(l)))
+    trainer.train_loop(batches, valid_generator=batches[:2], test_generator=batches[:1], epochs=3,
+                       steps_per_epoch=3, validation_steps=2, test_steps=1, callbacks=[cb],
+                       scheduler_step_on="epoch", scheduler_metric="val_loss")
+    assert len(seen) == 3 and seen == [l["val_loss"] for l in logs]          # one step per epoch, on val_loss
+    # epoch 1 sets the best value; epochs 2 and 3 are "not better" with patience 0: two reductions
+    assert abs(opt.param_groups[0]["lr"] - 0.1 * 0.1 ** 2) < 1e-12
+    assert {"epoch", "loss", "acc", "val_loss", "val_acc", "test_loss", "test_acc"} <= set(logs[0])
