@@ -962,3 +962,27 @@ def test_epoch_stepped_plateau_scheduler_as_train_fashionmnist_does(mmu):
     # epoch 1 sets the best value; epochs 2 and 3 are "not better" with patience 0: two reductions
     assert abs(opt.param_groups[0]["lr"] - 0.1 * 0.1 ** 2) < 1e-12
     assert {"epoch", "loss", "acc", "val_loss", "val_acc", "test_loss", "test_acc"} <= set(logs[0])
+
+
+def test_bertadam_accepts_the_fmnist_transformer_configuration(mmu):
+    """train_fashionmnist.py:91-109: ``MIMOTransfomer`` + ``BertAdam`` over the (decay / no-decay)
+    parameter groups + ``ReduceLROnPlateau(optimizer, 'max')`` -- construction and the scheduler's
+    view of the groups need no device; a torch module's parameters are refused (no per-tensor
+    fallback)."""
+    m = mmu.MIMOTransfomer(out_dim=4, num_classes=10, image_dim=196, hidden_size=64,
+                           multimodal_num_attention_heads=2, multimodal_num_hidden_layers=2, drop=0.0)
+    named = list(m.named_parameters())
+    no_decay = ["bias", "LayerNorm.bias", "LayerNorm.weight"]
+    groups = [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
+              {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+    assert groups[0]["params"] and groups[1]["params"]
+    opt = mmu.BertAdam(groups, lr=1e-3, warmup=0.1, t_total=100)
+    assert [g["weight_decay"] for g in opt.param_groups] == [0.01, 0.0] and len(opt._owners) == 1
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, "max", patience=0, factor=0.5)
+    sched.step(50.0)
+    sched.step(40.0)                                    # worse: halves the lr of both groups
+    assert [g["lr"] for g in opt.param_groups] == [5e-4, 5e-4]
+    with pytest.raises(ValueError):
+        mmu.BertAdam(torch.nn.Linear(2, 2).parameters(), lr=1e-3)
+    with pytest.raises(ValueError):
+        mmu.BertAdam(groups, lr=1e-3, schedule="warmup_cosine")
